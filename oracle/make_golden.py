@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE — writes tests/golden/*.npz by running the UNMODIFIED reference head.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+Inputs and weights are pure functions of seeds (`poem_v2_b200.synth`), so only OUTPUTS of the
+reference are stored: final coordinates plus strided slices of the stage boundaries.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import ref_shim  # noqa: E402
+from poem_v2_b200 import synth  # noqa: E402
+from poem_v2_b200.config import release_dims  # noqa: E402
+
+# name -> (size, views, weight seed, input seed, weight mode)
+CASES = {
+    "small_v2_b1": ("small", [2], 0, 1, "stress"),
+    "small_v1_b2": ("small", [1, 1], 0, 2, "stress"),
+    "small_ragged_b3": ("small", [3, 1, 2], 3, 4, "stress"),
+    "small_v4_b2_init": ("small", [4, 4], 5, 6, "init"),
+    "medium_v8_b1": ("medium", [8], 0, 1, "stress"),
+    "large_v2_b1": ("large", [2], 0, 1, "stress"),
+}
+ROW_STRIDE = 37
+
+
+def run_reference(size, views, wseed, iseed, mode):
+    dims = release_dims(size)
+    head, _ = ref_shim.build_reference_head(size, template_fn=synth.standin_template)
+    sd = synth.make_state_dict(dims, wseed, mode)
+    missing, unexpected = head.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    live = set(sd)
+    assert live.isdisjoint(missing)
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, iseed)
+    cap = {}
+    tr = head.transformer
+
+    def pre(mod, args, kwargs):
+        cap["pt_feats"] = kwargs["pt_feats"].detach().clone()
+        cap["pt_xyz"] = kwargs["pt_xyz"].detach().clone()
+        cap["q_xyz"] = kwargs["query_xyz"].detach().clone()
+    h = [tr.register_forward_pre_hook(pre, with_kwargs=True)]
+    for i, blk in enumerate(tr.pt_metro_encoder):
+        def post(mod, args, out, i=i):
+            cap[f"b{i}.out"] = out[0].detach().clone()
+            cap[f"b{i}.xyz"] = out[1].detach().clone()
+        h.append(blk.register_forward_hook(post))
+    with torch.no_grad():
+        res = head(mlvl_feat=feat, img_metas=metas, reference_joints=ref_j, debug_metas=None)
+    for x in h:
+        x.remove()
+    cap["all_coords_preds"] = res["all_coords_preds"].detach().clone()
+    return cap
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, (size, views, wseed, iseed, mode) in CASES.items():
+        cap = run_reference(size, views, wseed, iseed, mode)
+        out = {
+            "all_coords_preds": cap["all_coords_preds"].numpy(),
+            "pt_feats_rows": cap["pt_feats"][:, ::ROW_STRIDE].numpy(),
+            "pt_xyz_rows": cap["pt_xyz"][:, ::ROW_STRIDE].numpy(),
+            "q_xyz": cap["q_xyz"].numpy(),
+        }
+        for k in cap:
+            if k.endswith(".out"):
+                out[k + "_rows"] = cap[k][:, ::ROW_STRIDE].numpy()
+            if k.endswith(".xyz"):
+                out[k] = cap[k].numpy()
+        meta = dict(size=size, views=views, wseed=wseed, iseed=iseed, mode=mode, row_stride=ROW_STRIDE)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), meta=np.array(repr(meta)), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

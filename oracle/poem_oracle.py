@@ -1,0 +1,237 @@
+"""TEST INFRASTRUCTURE — CPU/fp32 restatement of the reference decoder path. NOT product code.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+import this file; the product (`poem-v2_b200/`) must never route through it.
+
+Parity status: **pinned against outputs of the reference itself run in the build container** —
+`oracle/make_golden.py` runs the unmodified reference `POEM_Generalized_Head` (under the stub layer
+`oracle/ref_shim.py`) on seeded inputs/weights and stores its outputs under `tests/golden/`;
+`tests/test_oracle.py` asserts this restatement reproduces them (≤1e-5 normalised units).
+Unpinned sub-parts (third-party arithmetic absent offline): pytorch3d `knn_points` tie order and the
+real MANO template (a seeded stand-in is used) — see DESIGN.md.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------ a2
+def sine_pos_3d(n_views, h, w, num_feats, normalize=True, temperature=10000.0, scale=2 * math.pi, eps=1e-6):
+    """`SinePositionalEncoding3D.forward` on an all-false mask (lib/models/layers/petr_transformer.py:434-469).
+    Returns (n_views, 3*num_feats, h, w); channel order [view, y, x]."""
+    ones = torch.ones(1, n_views, h, w, dtype=torch.float32)
+    n_e, y_e, x_e = ones.cumsum(1), ones.cumsum(2), ones.cumsum(3)
+    if normalize:
+        n_e = n_e / (n_e[:, -1:] + eps) * scale
+        y_e = y_e / (y_e[:, :, -1:] + eps) * scale
+        x_e = x_e / (x_e[:, :, :, -1:] + eps) * scale
+    i = torch.arange(num_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / num_feats)
+
+    def enc(e):
+        p = e[..., None] / dim_t
+        # NB: stacking a 5-D tensor at dim=4 gives (...,2,F/2): all sines first, then all cosines
+        # (NOT interleaved as in the 2-D DETR encoding) — petr_transformer.py:465-467
+        return torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=4).reshape(1, n_views, h, w, -1)
+    pos = torch.cat((enc(n_e), enc(y_e), enc(x_e)), dim=4).permute(0, 1, 4, 2, 3)
+    return pos[0].contiguous()
+
+
+def feature_volume(sd, feat, view_counts, dims):
+    """x = input_proj(feat) + adapt_pos3d(sine) (lib/models/heads/ptEmb_head.py:835-870)."""
+    D = dims.embed_dims
+    x = F.conv2d(feat, sd["input_proj.weight"], sd["input_proj.bias"])
+    pos = []
+    for n in view_counts:
+        s = sine_pos_3d(int(n), x.shape[-2], x.shape[-1], dims.pos_feats, dims.pos_normalize).to(feat.device)
+        pos.append(F.conv2d(s, sd["adapt_pos3d.weight"], sd["adapt_pos3d.bias"]))
+    return x + torch.cat(pos, dim=0)
+
+
+# ------------------------------------------------------------------------------------------ a3/a4
+def project_bps(bps_world, cam_intr, cam_extr, view_counts, inp_res):
+    """lib/utils/collation.py:48-65 + lib/utils/transform.py:898-930 + ptEmb_head.py:880-883.
+    bps_world (B,P,3); returns the grid_sample grid (BV,P,1,2) in [-1,1] units."""
+    out = []
+    s = 0
+    for b, n in enumerate(view_counts):
+        n = int(n)
+        T = torch.linalg.inv(cam_extr[s:s + n])                      # master -> camera
+        p = bps_world[b][None].expand(n, -1, -1)                    # (n,P,3)
+        pc = (T[:, :3, :3] @ p.transpose(1, 2)).transpose(1, 2) + T[:, :3, 3][:, None]
+        q = (cam_intr[s:s + n] @ pc.transpose(1, 2)).transpose(1, 2)
+        z = q[..., 2:].clone()
+        z[z.abs() < 1e-7] = 1e-7
+        out.append(q[..., :2] / z)
+        s += n
+    uv = torch.cat(out, dim=0)[:, :, None, :]                       # (BV,P,1,2)
+    uv = uv * (1.0 / inp_res)
+    return uv * 2 - 1
+
+
+# ------------------------------------------------------------------------------------------ a6
+def _mlp2(sd, prefix, x):
+    x = F.relu(F.linear(x, sd[prefix + ".0.weight"], sd[prefix + ".0.bias"]))
+    return F.linear(x, sd[prefix + ".2.weight"], sd[prefix + ".2.bias"])
+
+
+def merge_views(sd, sampled, view_counts):
+    """Raw `.view(1,-1,N,D)` regroup + merge_features_mv / _sv (ptEmb_head.py:745-771,910-926)."""
+    outs = []
+    s = 0
+    D = sampled.shape[1]
+    for n in view_counts:
+        n = int(n)
+        q = sampled[s:s + n].contiguous().view(1, -1, n, D)         # memory reinterpretation, NOT a permute
+        s += n
+        if n == 1:
+            q = q.squeeze(2)
+            outs.append(q + _mlp2(sd, "merge_net_feature.1", _mlp2(sd, "merge_net_feature.0", q)))
+            continue
+        q1 = q[:, :, 0]
+        m = _mlp2(sd, "merge_net_feature.0", q)                     # (1,P,n,D/2)
+        master, other = m[:, :, 0], m[:, :, 1:]
+        w = other @ master[..., None]                               # (1,P,n-1,1)
+        agg = (other.transpose(2, 3) @ w).squeeze(-1)               # (1,P,D/2)
+        outs.append(q1 + _mlp2(sd, "merge_net_feature.1", agg) / n)
+    return torch.cat(outs, dim=0)
+
+
+# ------------------------------------------------------------------------------------------ a10
+def bert_cross_attention(sd, prefix, hidden, enc, n_heads):
+    """HF 4.x `BertAttention` with `encoder_hidden_states`: Q from `hidden`, K/V from `enc`, no mask,
+    then BertSelfOutput (dense + residual + LayerNorm eps 1e-12). Call sites
+    lib/models/bricks/pt_metro_transformer.py:57-74."""
+    B, Lq, D = hidden.shape
+    hd = D // n_heads
+
+    def split(t):
+        return t.view(B, -1, n_heads, hd).transpose(1, 2)
+    q = split(F.linear(hidden, sd[prefix + ".self.query.weight"], sd[prefix + ".self.query.bias"]))
+    k = split(F.linear(enc, sd[prefix + ".self.key.weight"], sd[prefix + ".self.key.bias"]))
+    v = split(F.linear(enc, sd[prefix + ".self.value.weight"], sd[prefix + ".self.value.bias"]))
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    ctx = (p @ v).transpose(1, 2).reshape(B, Lq, D)
+    o = F.linear(ctx, sd[prefix + ".output.dense.weight"], sd[prefix + ".output.dense.bias"])
+    return F.layer_norm(o + hidden, (D,), sd[prefix + ".output.LayerNorm.weight"],
+                        sd[prefix + ".output.LayerNorm.bias"], eps=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ a14
+def knn(query_xyz, ref_xyz, K):
+    """pytorch3d `knn_points(p1,p2,K)` (third-party, v0.7.2, not vendored): squared L2, K smallest in
+    ascending order; ties resolved towards the lower index. Returns idx (B,Lq,K) int64."""
+    d = ((query_xyz[:, :, None, :] - ref_xyz[:, None, :, :]) ** 2).sum(-1)
+    return torch.sort(d, dim=-1, stable=True).indices[..., :K]
+
+
+def gather_rows(table, idx):
+    """`index_points` (lib/utils/points_utils.py:9-20): table (B,N,C), idx (B,S,K) -> (B,S,K,C)."""
+    B, S, K = idx.shape
+    flat = idx.reshape(B, S * K)
+    return torch.gather(table, 1, flat[..., None].expand(-1, -1, table.shape[-1])).reshape(B, S, K, -1)
+
+
+# ------------------------------------------------------------------------------------------ a12/a13
+def _vector_attention_core(sd, p, q, k, v, rel):
+    pos = _mlp2(sd, p + "fc_delta", rel)
+    a = _mlp2(sd, p + "fc_gamma", q[:, :, None] - k + pos)
+    a = torch.softmax(a / math.sqrt(k.shape[-1]), dim=-2)
+    return (a * (v + pos)).sum(dim=2)
+
+
+def vec_self_attention(sd, p, xyz, feats, K, anchors=None):
+    """`ptTransformerBlock._forward` (lib/models/bricks/point_transformers.py:70-96)."""
+    B = xyz.shape[0]
+    if anchors is not None:                                          # block 0: fixed anchors for every query
+        a_xyz, a_idx = anchors
+        idx = a_idx[None, None].expand(B, xyz.shape[1], -1)
+        nbr_xyz = a_xyz[None, None].expand(B, xyz.shape[1], -1, -1)
+    else:
+        idx = knn(xyz, xyz, K)
+        nbr_xyz = gather_rows(xyz, idx)
+    x = F.linear(feats, sd[p + "fc1.weight"], sd[p + "fc1.bias"])
+    q = F.linear(x, sd[p + "w_qs.weight"])
+    k = gather_rows(F.linear(x, sd[p + "w_ks.weight"]), idx)
+    v = gather_rows(F.linear(x, sd[p + "w_vs.weight"]), idx)
+    res = _vector_attention_core(sd, p, q, k, v, xyz[:, :, None] - nbr_xyz)
+    return F.linear(res, sd[p + "fc2.weight"], sd[p + "fc2.bias"]) + feats, idx
+
+
+def vec_cross_attention(sd, p, pt_xyz, pt_feats, q_xyz, q_feats, K, anchors=None):
+    """`ptTransformerBlock_CrossAttn._forward` (lib/models/bricks/point_transformers.py:125-156)."""
+    B = q_xyz.shape[0]
+    if anchors is not None:                                          # anchor idx gathers rows of the 4096-row table
+        a_xyz, a_idx = anchors
+        idx = a_idx[None, None].expand(B, q_xyz.shape[1], -1)
+        nbr_xyz = a_xyz[None, None].expand(B, q_xyz.shape[1], -1, -1)
+    else:
+        idx = knn(q_xyz, pt_xyz, K)
+        nbr_xyz = gather_rows(pt_xyz, idx)
+    nf = gather_rows(pt_feats, idx)
+    q = F.linear(q_feats, sd[p + "w_qs.weight"])
+    x = F.linear(nf, sd[p + "fc1.weight"], sd[p + "fc1.bias"])
+    k = F.linear(x, sd[p + "w_ks.weight"])
+    v = F.linear(x, sd[p + "w_vs.weight"])
+    res = _vector_attention_core(sd, p, q, k, v, q_xyz[:, :, None] - nbr_xyz)
+    return F.linear(res, sd[p + "fc2.weight"], sd[p + "fc2.bias"]) + q_feats, idx
+
+
+# ------------------------------------------------------------------------------------------ a9-a11
+def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=None):
+    """`point_METRO_block.forward` + `point_METRO_layer.forward` + `pointer_layer.forward`
+    (lib/models/bricks/pt_metro_transformer.py:153-200, 56-91, 34-40); eval mode (dropout = identity)."""
+    p = f"transformer.pt_metro_encoder.{i}."
+    D = dims.embed_dims
+    qe = F.linear(q_feats, sd[p + "embedding.weight"], sd[p + "embedding.bias"])
+    ke = F.linear(pt_feats, sd[p + "embedding.weight"], sd[p + "embedding.bias"])
+    a1 = bert_cross_attention(sd, p + "encoder.attn", qe, ke, dims.n_heads)
+    a2 = bert_cross_attention(sd, p + "encoder.cross_attn", a1, ke, dims.n_heads)
+    anc = anchors if i == 0 else None
+    f1, idx_s = vec_self_attention(sd, p + "encoder.vec_attn.query_self_attn.", q_xyz, a2, dims.n_neighbor, anc)
+    f2, idx_c = vec_cross_attention(sd, p + "encoder.vec_attn.query_cross_attn.", pt_xyz, ke, q_xyz, f1,
+                                    dims.n_neighbor, anc)
+    xyz = _mlp2(sd, p + "encoder.vec_attn.reg_branch", f2) + q_xyz
+    h = F.gelu(F.linear(f2, sd[p + "encoder.intermediate.dense.weight"], sd[p + "encoder.intermediate.dense.bias"]))
+    o = F.linear(h, sd[p + "encoder.output.dense.weight"], sd[p + "encoder.output.dense.bias"])
+    out = F.layer_norm(o + f2, (D,), sd[p + "encoder.output.LayerNorm.weight"],
+                       sd[p + "encoder.output.LayerNorm.bias"], eps=1e-12)
+    if stages is not None:
+        stages[f"b{i}.a1"], stages[f"b{i}.a2"], stages[f"b{i}.f1"], stages[f"b{i}.f2"] = a1, a2, f1, f2
+        stages[f"b{i}.xyz"], stages[f"b{i}.out"] = xyz, out
+        stages[f"b{i}.idx_self"], stages[f"b{i}.idx_cross"] = idx_s, idx_c
+    return out, xyz
+
+
+# ------------------------------------------------------------------------------------------ a1
+def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anchor_xyz, anchor_idx, stages=None):
+    """`POEM_Generalized_Head.forward` (lib/models/heads/ptEmb_head.py:825-964), non-parametric output.
+    Returns all_coords_preds (NB,B,799,3) in metres."""
+    views = [int(v) for v in img_metas["cam_view_num"]]
+    B = len(views)
+    inp_w, inp_h = img_metas["inp_img_shape"]
+    inp_res = torch.tensor([float(inp_w), float(inp_h)])
+    x = feature_volume(sd, feat, views, dims)
+    centre = reference_joints[:, dims.center_idx]                   # (B,3)
+    bps_world = bps[None] + centre[:, None]
+    grid = project_bps(bps_world, img_metas["cam_intr"], img_metas["cam_extr"], views, inp_res)
+    sampled = F.grid_sample(x, grid, align_corners=False).squeeze(-1)   # (BV,D,P)
+    pt_feats = merge_views(sd, sampled, views)                       # (B,P,D)
+    q_feats = sd["query_feat_embedding.weight"][None].expand(B, -1, -1)
+    pt_xyz = (bps_world - centre[:, None]) / dims.radius
+    q_xyz = ((centre[:, None] + template[None]) - centre[:, None]) / dims.radius
+    if stages is not None:
+        stages.update(x=x, grid=grid, sampled=sampled, pt_feats=pt_feats, pt_xyz=pt_xyz, q_xyz=q_xyz)
+    anchors = (anchor_xyz, anchor_idx)
+    xyz_all = []
+    for i in range(dims.n_blocks):
+        q_feats, q_xyz = metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages)
+        xyz_all.append(q_xyz)
+    coords = torch.nan_to_num(torch.stack(xyz_all))
+    if stages is not None:
+        stages["xyz_norm"] = coords
+    return coords * dims.radius + centre[None, :, None, :]

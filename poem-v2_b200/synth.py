@@ -1,0 +1,174 @@
+"""Seeded synthetic inputs, weights and constants for the decoder path.
+
+Everything here is a pure function of integer seeds and `HeadDims`, generated with a CPU
+`torch.Generator`, so the container that writes `tests/golden/` and the GPU box regenerate
+bit-identical tensors.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from .config import HeadDims, N_QUERY
+
+_ASSET_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+def load_assets():
+    """Frozen constants of the path: BPS offsets (4096,3) f32, anchor xyz (32,3) f32, anchor idx (32,) i64.
+
+    Same bytes as the reference's `assets/{bps,anchor,anchor_idx}.npy` (data, not code; loaded by the
+    reference at `ptEmb_head.py:790-809` and `point_transformers.py:10-32`)."""
+    bps = np.load(os.path.join(_ASSET_DIR, "bps.npy")).reshape(-1, 3).astype(np.float32)
+    anchor = np.load(os.path.join(_ASSET_DIR, "anchor.npy")).reshape(-1, 3).astype(np.float32)
+    anchor_idx = np.load(os.path.join(_ASSET_DIR, "anchor_idx.npy")).reshape(-1).astype(np.int64)
+    return torch.from_numpy(bps), torch.from_numpy(anchor), torch.from_numpy(anchor_idx)
+
+
+def standin_template(seed: int = 7) -> torch.Tensor:
+    """(799,3) stand-in for the MANO zero-pose template (joints ‖ verts, centred on joint 9).
+
+    manotorch + the licensed MANO pickles are absent; SURVEY §8d prescribes a seeded 0.05·N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    t = 0.05 * torch.randn(N_QUERY, 3, generator=g)
+    return t - t[9:10]
+
+
+def _view_list(B, V):
+    return [int(V)] * B if isinstance(V, (int, np.integer)) else [int(v) for v in V]
+
+
+def make_cameras(B: int, V, seed: int = 1):
+    """cam_intr (ΣV,3,3), cam_extr (ΣV,4,4) cam->master; view 0 of each sample is the master (identity).
+    V is an int or a per-sample list (ragged batches, reference `collation_random_n_views`)."""
+    g = torch.Generator().manual_seed(seed + 101)
+    K = torch.tensor([[900.0, 0.0, 128.0], [0.0, 900.0, 128.0], [0.0, 0.0, 1.0]])
+    c0 = torch.tensor([0.0, 0.0, 0.6])
+    views = _view_list(B, V)
+    mats = []
+    for b in range(B):
+        V = views[b]
+        for v in range(V):
+            yaw = v * 2.0 * math.pi / V * 0.25
+            pitch = 0.0 if v == 0 else (torch.rand(1, generator=g).item() * 2 - 1) * math.radians(5.0)
+            cy, sy, cp, sp = math.cos(yaw), math.sin(yaw), math.cos(pitch), math.sin(pitch)
+            Ry = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]], dtype=torch.float32)
+            Rx = torch.tensor([[1, 0, 0], [0, cp, -sp], [0, sp, cp]], dtype=torch.float32)
+            R = Ry @ Rx
+            # rotate the camera about the hand centre c0: p_master = R (p_cam - c0) + c0
+            T = torch.eye(4)
+            T[:3, :3] = R
+            T[:3, 3] = c0 - R @ c0
+            mats.append(T)
+    extr = torch.stack(mats)
+    intr = K[None].repeat(extr.shape[0], 1, 1)
+    return intr.contiguous(), extr.contiguous()
+
+
+def make_inputs(dims: HeadDims, B: int, V, seed: int = 1):
+    """Decoder-only inputs: mlvl_feat ~ N(0,1) (ΣV,C,16,16); reference_joints = c0 + 0.03 N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    views = _view_list(B, V)
+    feat = torch.randn(sum(views), dims.in_channels, dims.feat_hw, dims.feat_hw, generator=g)
+    c0 = torch.tensor([0.0, 0.0, 0.6])
+    ref_joints = c0 + 0.03 * torch.randn(B, 21, 3, generator=g)
+    intr, extr = make_cameras(B, V, seed)
+    img_metas = {
+        "inp_img_shape": (256, 256),
+        "cam_intr": intr,
+        "cam_extr": extr,
+        "master_id": [0] * B,
+        "cam_view_num": np.array(views),
+    }
+    return feat, img_metas, ref_joints
+
+
+def live_param_shapes(dims: HeadDims):
+    """name -> shape of every parameter the path reads (reference state-dict names, relative to the head)."""
+    D, C = dims.embed_dims, dims.in_channels
+    H = D // 2
+    s = {
+        "input_proj.weight": (D, C, 1, 1), "input_proj.bias": (D,),
+        "adapt_pos3d.weight": (D, 3 * dims.pos_feats, 1, 1), "adapt_pos3d.bias": (D,),
+        "merge_net_feature.0.0.weight": (D, D), "merge_net_feature.0.0.bias": (D,),
+        "merge_net_feature.0.2.weight": (H, D), "merge_net_feature.0.2.bias": (H,),
+        "merge_net_feature.1.0.weight": (H, H), "merge_net_feature.1.0.bias": (H,),
+        "merge_net_feature.1.2.weight": (D, H), "merge_net_feature.1.2.bias": (D,),
+        "query_feat_embedding.weight": (dims.n_query, D),
+    }
+    for i in range(dims.n_blocks):
+        p = f"transformer.pt_metro_encoder.{i}."
+        s[p + "embedding.weight"] = (D, D)
+        s[p + "embedding.bias"] = (D,)
+        for a in ("attn", "cross_attn"):
+            for n in ("self.query", "self.key", "self.value", "output.dense"):
+                s[p + f"encoder.{a}.{n}.weight"] = (D, D)
+                s[p + f"encoder.{a}.{n}.bias"] = (D,)
+            s[p + f"encoder.{a}.output.LayerNorm.weight"] = (D,)
+            s[p + f"encoder.{a}.output.LayerNorm.bias"] = (D,)
+        for a in ("query_self_attn", "query_cross_attn"):
+            q = p + f"encoder.vec_attn.{a}."
+            for n in ("fc1", "fc2", "fc_delta.2", "fc_gamma.0", "fc_gamma.2"):
+                s[q + n + ".weight"] = (D, D)
+                s[q + n + ".bias"] = (D,)
+            s[q + "fc_delta.0.weight"] = (D, 3)
+            s[q + "fc_delta.0.bias"] = (D,)
+            for n in ("w_qs", "w_ks", "w_vs"):
+                s[q + n + ".weight"] = (D, D)
+        s[p + "encoder.vec_attn.reg_branch.0.weight"] = (D, D)
+        s[p + "encoder.vec_attn.reg_branch.0.bias"] = (D,)
+        s[p + "encoder.vec_attn.reg_branch.2.weight"] = (3, D)
+        s[p + "encoder.vec_attn.reg_branch.2.bias"] = (3,)
+        s[p + "encoder.intermediate.dense.weight"] = (4 * D, D)
+        s[p + "encoder.intermediate.dense.bias"] = (4 * D,)
+        s[p + "encoder.output.dense.weight"] = (D, 4 * D)
+        s[p + "encoder.output.dense.bias"] = (D,)
+        s[p + "encoder.output.LayerNorm.weight"] = (D,)
+        s[p + "encoder.output.LayerNorm.bias"] = (D,)
+        if dims.parametric:
+            s[p + "flat_verts.weight"] = (1, dims.n_query)
+            s[p + "flat_verts.bias"] = (1,)
+            s[p + "mano_linear.weight"] = (106, D)
+            s[p + "mano_linear.bias"] = (106,)
+    return s
+
+
+# per-layer gains that keep every stage O(1) (logit std ~1-2, per-block xyz update ~0.03 radius units)
+_STRESS_GAIN = {
+    "merge_net_feature.0.2.weight": 0.35,
+    "fc_delta.0.weight": 2.0,
+    "reg_branch.2.weight": 0.08,
+    "vec_attn.query_self_attn.fc2.weight": 0.5,
+    "vec_attn.query_cross_attn.fc2.weight": 0.5,
+}
+
+
+def make_state_dict(dims: HeadDims, seed: int = 0, mode: str = "stress"):
+    """Seeded live weights under the reference's key names.
+
+    mode "stress": every matrix ~ N(0, 1/fan_in) (biases 0.1·N(0,1), LayerNorm γ = 1 + 0.1·N) so that
+    attention logits, softmaxes and residual branches are all O(1) and non-degenerate;
+    the coordinate regression layer is scaled so per-block updates are ~0.05 normalised units.
+    mode "init": BERT-style N(0, 0.02) matrices, zero biases.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in live_param_shapes(dims).items():
+        if "LayerNorm.weight" in name:
+            w = 1.0 + (0.1 * torch.randn(shape, generator=g) if mode == "stress" else 0.0)
+            w = w if torch.is_tensor(w) else torch.ones(shape)
+        elif name.endswith(".bias"):
+            w = 0.1 * torch.randn(shape, generator=g) if mode == "stress" else torch.zeros(shape)
+        elif name == "query_feat_embedding.weight":
+            w = torch.randn(shape, generator=g)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            std = (1.0 / math.sqrt(fan_in)) if mode == "stress" else 0.02
+            w = std * torch.randn(shape, generator=g)
+            if mode == "stress":
+                for suffix, gain in _STRESS_GAIN.items():
+                    if name.endswith(suffix):
+                        w = w * gain
+        sd[name] = w.float().contiguous()
+    return sd
