@@ -1,0 +1,193 @@
+/* poem_b200.h — C ABI of the B200-native POEM-v2 point-embedded transformer decoder.
+ *
+ * The reference has no native code and no FFI: its plug-in boundary for this path is a Python class
+ * resolved through a registry (`@HEAD.register_module() class POEM_Generalized_Head`,
+ * /root/reference/lib/models/heads/ptEmb_head.py:683-684; `@TRANSFORMER.register_module() class PtEmbedTRv4`,
+ * lib/models/layers/ptEmb_transformer.py:303-304; resolved by lib/utils/builder.py:9-47).  The entry points
+ * below are what a reference-side `nn.Module` binds through ctypes; each cites the
+ * reference call it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative POEM_E_* code; poem_last_error() gives a message
+ *   - all device buffers are caller-allocated; the library allocates nothing and keeps no mutable global
+ *     state besides the last-error string (thread local)
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*)
+ *   - "bf16" buffers are raw 16-bit bfloat16 (uint16_t storage)
+ */
+#ifndef POEM_B200_H
+#define POEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POEM_ABI_VERSION 1
+
+#define POEM_OK 0
+#define POEM_E_BADDIM (-1)      /* unsupported / inconsistent dimensions */
+#define POEM_E_NULL (-2)        /* required pointer is NULL */
+#define POEM_E_WORKSPACE (-3)   /* workspace too small */
+#define POEM_E_CUDA (-4)        /* CUDA runtime / driver error */
+#define POEM_E_ALIGN (-5)       /* pointer or leading dimension not 16-byte aligned */
+
+typedef uint16_t poem_bf16;
+
+/* Dimensions read from cfg.MODEL.HEAD (ptEmb_head.py:57-76,686-695; ptEmb_transformer.py:312-324). */
+typedef struct PoemDims {
+  int32_t embed_dims;   /* D: 128 | 256 | 512 | 1024 */
+  int32_t in_channels;  /* C: 160 */
+  int32_t n_sample;     /* P: 4096 */
+  int32_t n_query;      /* Q: 799 */
+  int32_t n_blocks;     /* NB: 3 */
+  int32_t n_heads;      /* h: 4 */
+  int32_t n_neighbor;   /* K: 32 */
+  int32_t feat_h;       /* 16 */
+  int32_t feat_w;       /* 16 */
+  int32_t center_idx;   /* 9 */
+  float radius;         /* 0.1 */
+  int32_t max_views;    /* rows of the positional table cover view counts 1..max_views */
+  int32_t run_last_ffn; /* 1 if the last block's FFN output is needed (parametric tail) */
+} PoemDims;
+
+/* One Linear layer in kernel layout: weight bf16 [out, in] row-major (K-major), bias fp32 [out] or NULL. */
+typedef struct PoemLinear {
+  const poem_bf16* w;
+  const float* b;
+} PoemLinear;
+
+/* Vector-attention (Point-Transformer) layer, reference lib/models/bricks/point_transformers.py:47-156. */
+typedef struct PoemVecAttn {
+  const float* wd1;     /* fc_delta.0 weight fp32 [D,3] */
+  const float* bd1;     /* fc_delta.0 bias   fp32 [D]   */
+  PoemLinear delta2;    /* fc_delta.2 */
+  PoemLinear gamma1;    /* fc_gamma.0 */
+  PoemLinear gamma2;    /* fc_gamma.2 */
+  PoemLinear fc2;       /* fc2 */
+} PoemVecAttn;
+
+/* One point_METRO_block (pt_metro_transformer.py:94-200), weights folded at pack time:
+ *   pt_proj : [6D, D]  rows = K1 | K2 | k'_cross | v'_cross | V1 | V2   each composed with `embedding`
+ *             (and with query_cross_attn.fc1 for k', v'); bias folded likewise
+ *   self_qkv: [3D, D]  rows = w_qs·fc1 | w_ks·fc1 | w_vs·fc1 of query_self_attn                         */
+typedef struct PoemBlock {
+  PoemLinear embedding;     /* embedding (applied to the query stream) */
+  PoemLinear pt_proj;
+  PoemLinear q1, o1;        /* encoder.attn.self.query, encoder.attn.output.dense */
+  const float *ln1_g, *ln1_b;
+  PoemLinear q2, o2;        /* encoder.cross_attn.* */
+  const float *ln2_g, *ln2_b;
+  PoemLinear self_qkv;
+  PoemVecAttn self_attn;
+  PoemLinear cross_q;       /* query_cross_attn.w_qs (no bias) */
+  PoemVecAttn cross_attn;
+  PoemLinear reg1;          /* reg_branch.0 */
+  const float* reg2_w;      /* reg_branch.2 weight fp32 [3,D] */
+  const float* reg2_b;      /* fp32 [3] */
+  PoemLinear ffn1, ffn2;    /* encoder.intermediate.dense, encoder.output.dense */
+  const float *ln3_g, *ln3_b;
+} PoemBlock;
+
+#define POEM_MAX_BLOCKS 8
+
+typedef struct PoemWeights {
+  PoemLinear input_proj;        /* [D, C] (1x1 conv, ptEmb_head.py:94) */
+  const float* pos_table;       /* fp32 [sum_{N=1..max_views} N, feat_h*feat_w, D]:
+                                   adapt_pos3d(sine3d(N))[n] + adapt_pos3d.bias, rows ordered N=1:(n=0), N=2:(n=0,1), ... */
+  PoemLinear merge0a, merge0b;  /* merge_net_feature.0.{0,2} */
+  PoemLinear merge1a, merge1b;  /* merge_net_feature.1.{0,2} */
+  const float* query_embed;     /* query_feat_embedding.weight fp32 [Q, D] */
+  const float* bps;             /* fp32 [P,3]  (assets/bps.npy) */
+  const float* anchor_xyz;      /* fp32 [32,3] (assets/anchor.npy) */
+  const int32_t* anchor_idx;    /* int32 [32]  (assets/anchor_idx.npy) */
+  const float* template_xyz;    /* fp32 [Q,3]  MANO zero-pose template, joints then vertices */
+  PoemBlock blocks[POEM_MAX_BLOCKS];
+} PoemWeights;
+
+/* Per-call inputs of POEM_Generalized_Head.forward (ptEmb_head.py:825). */
+typedef struct PoemInputs {
+  int32_t batch;                /* B */
+  int32_t n_images;             /* sum of views */
+  const int32_t* view_counts;   /* HOST pointer, int32 [B]  (img_metas["cam_view_num"]) */
+  const float* mlvl_feat;       /* fp32 [n_images, C, feat_h, feat_w] */
+  const float* cam_intr;        /* fp32 [n_images, 3, 3] */
+  const float* cam_extr;        /* fp32 [n_images, 4, 4]  camera -> master */
+  const float* reference_joints;/* fp32 [B, 21, 3] metres, master frame */
+  float inp_img_w, inp_img_h;   /* img_metas["inp_img_shape"] */
+} PoemInputs;
+
+int poem_abi_version(void);
+const char* poem_last_error(void);
+
+/* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
+size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);
+
+/* Whole decoder path, device buffers.  Replaces POEM_Generalized_Head.forward + PtEmbedTRv4.forward
+ * (ptEmb_head.py:825-964, ptEmb_transformer.py:371-376).
+ *   out_coords : fp32 [NB, B, Q, 3] metres (`all_coords_preds`)
+ *   out_feats  : optional fp32 [B, Q, D] output of the last block's FFN (needs dims->run_last_ffn) or NULL */
+int poem_head_forward(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
+                      float* out_feats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Decoder blocks only.  Replaces PtEmbedTRv4.forward(query_xyz, query_feat, pt_xyz, pt_feats)
+ * (ptEmb_transformer.py:371-376): all inputs fp32 device buffers in normalised (radius) units,
+ *   query_xyz [B,Q,3], query_feat [B,Q,D], pt_xyz [B,P,3], pt_feats [B,P,D];
+ *   out_xyz fp32 [NB,B,Q,3] (normalised, stacked per block); out_feats optional fp32 [B,Q,D]. */
+size_t poem_transformer_workspace_bytes(const PoemDims* dims, int batch);
+int poem_transformer_forward(const PoemDims* dims, const PoemWeights* w, int batch, const float* query_xyz,
+                             const float* query_feat, const float* pt_xyz, const float* pt_feats, float* out_xyz,
+                             float* out_feats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST input/output buffers (pinned memory recommended): copies inputs to the staging area at
+ * the head of `workspace`, runs, copies `all_coords_preds` back.  Weights and workspace stay on the device.
+ * workspace must hold poem_workspace_bytes() + poem_staging_bytes(). */
+size_t poem_staging_bytes(const PoemDims* dims, int batch, int n_images);
+int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* host_in,
+                           float* host_out_coords, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stage-level entry points (unit-testable building blocks; same kernels the whole path uses) ---- */
+
+/* C = act(A·W^T + bias) (+ residual); A bf16 [M,K] (lda), W bf16 [N,K] (ldw); outputs optional.
+ * act: 0 none, 1 relu, 2 gelu(erf).  Replaces nn.Linear / 1x1 nn.Conv2d call sites (cuBLAS/cuDNN). */
+int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N, int K,
+                int act, const float* residual, int ld_res, float* out_f32, int ld_f32, poem_bf16* out_bf16,
+                int ld_bf16, void* stream);
+
+/* softmax(Q K^T / sqrt(hd)) V per head, no mask.  Q bf16 [B*Lq, ldq], K bf16 [B*Lk, ldk],
+ * Vt bf16 [B, D, Lk] (value projection stored transposed), ctx bf16 [B*Lq, ld_ctx].  Lk % 128 == 0.
+ * Replaces HF BertSelfAttention's matmul-softmax-matmul (pt_metro_transformer.py:57-72). */
+int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* Vt, poem_bf16* ctx,
+             int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream);
+
+/* idx int32 [B, Lq, 32]: 32 nearest reference points, ascending squared-L2, lower index wins ties.
+ * Replaces pytorch3d.ops.knn_points(K=32) (point_transformers.py:83,134). */
+int poem_knn32(const float* query_xyz, const float* ref_xyz, int32_t* idx, int B, int Lq, int Lr, void* stream);
+
+/* Camera projection + bilinear sampling in the reference's reinterpreted (token, view, channel) row order.
+ * xmap fp32 [n_images, D, fh*fw]; X bf16 [sum_views*P, D].  Replaces collation.py:48-65 + F.grid_sample +
+ * the raw .view regroup (ptEmb_head.py:874-915). */
+int poem_project_sample(const float* xmap, const float* cam_intr, const float* cam_extr, const float* bps,
+                        const float* centre, const int32_t* host_view_counts, int B, int n_images, int D, int P,
+                        int fh, int fw, float img_w, float img_h, poem_bf16* X, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Vector attention core: res[b,i,:] = sum_j softmax_j(gamma(q_i - k_j + pos_ij)/sqrt(D)) * (v_j + pos_ij),
+ * pos_ij = delta(xyz_i - nbr_xyz_j).  q bf16 [B*Lq, ldq]; ktab/vtab bf16 [B*Lr, ldk/ldv]; idx int32 [B*Lq*32]
+ * (or NULL with anchors: anchor_idx int32[32], anchor_xyz fp32[32,3]); res bf16 [B*Lq, D].
+ * Replaces point_transformers.py:86-94 / 139-150. */
+int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, int ldq, const poem_bf16* ktab, int ldk,
+                          const poem_bf16* vtab, int ldv, const float* q_xyz, const float* ref_xyz,
+                          const int32_t* idx, const int32_t* anchor_idx, const float* anchor_xyz, int B, int Lq,
+                          int Lr, int D, poem_bf16* res, void* workspace, size_t workspace_bytes, void* stream);
+size_t poem_vector_attention_workspace_bytes(int B, int Lq, int D);
+
+/* y = LayerNorm(x) over the last dim, eps 1e-12 (HF BertSelfOutput/BertOutput). */
+int poem_layernorm(const float* x, const float* gamma, const float* beta, float* y_f32, poem_bf16* y_bf16, int rows,
+                   int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POEM_B200_H */

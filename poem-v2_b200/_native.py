@@ -1,0 +1,159 @@
+"""ctypes binding of the C-ABI in include/poem_b200.h (libpoem_b200.so, built in-tree by `build()`).
+
+There is no CPU fallback: `load()` raises if the library is missing or cannot be loaded.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpoem_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+SOURCES = ["poem_b200.cu"]
+HEADERS = ["common.cuh", "gemm.cuh", "mha.cuh", "simt.cuh"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+POEM_MAX_BLOCKS = 8
+
+
+def _nvcc():
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if p and os.path.exists(p):
+            return p
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "poem_b200.h")]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> csrc/libpoem_b200.so (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+# ------------------------------------------------------------------------------------------ structs
+class PoemDims(C.Structure):
+    _fields_ = [("embed_dims", C.c_int32), ("in_channels", C.c_int32), ("n_sample", C.c_int32),
+                ("n_query", C.c_int32), ("n_blocks", C.c_int32), ("n_heads", C.c_int32), ("n_neighbor", C.c_int32),
+                ("feat_h", C.c_int32), ("feat_w", C.c_int32), ("center_idx", C.c_int32), ("radius", C.c_float),
+                ("max_views", C.c_int32), ("run_last_ffn", C.c_int32)]
+
+
+class PoemLinear(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
+
+
+class PoemVecAttn(C.Structure):
+    _fields_ = [("wd1", C.c_void_p), ("bd1", C.c_void_p), ("delta2", PoemLinear), ("gamma1", PoemLinear),
+                ("gamma2", PoemLinear), ("fc2", PoemLinear)]
+
+
+class PoemBlock(C.Structure):
+    _fields_ = [("embedding", PoemLinear), ("pt_proj", PoemLinear), ("q1", PoemLinear), ("o1", PoemLinear),
+                ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p), ("q2", PoemLinear), ("o2", PoemLinear),
+                ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p), ("self_qkv", PoemLinear), ("self_attn", PoemVecAttn),
+                ("cross_q", PoemLinear), ("cross_attn", PoemVecAttn), ("reg1", PoemLinear), ("reg2_w", C.c_void_p),
+                ("reg2_b", C.c_void_p), ("ffn1", PoemLinear), ("ffn2", PoemLinear), ("ln3_g", C.c_void_p),
+                ("ln3_b", C.c_void_p)]
+
+
+class PoemWeights(C.Structure):
+    _fields_ = [("input_proj", PoemLinear), ("pos_table", C.c_void_p), ("merge0a", PoemLinear),
+                ("merge0b", PoemLinear), ("merge1a", PoemLinear), ("merge1b", PoemLinear), ("query_embed", C.c_void_p),
+                ("bps", C.c_void_p), ("anchor_xyz", C.c_void_p), ("anchor_idx", C.c_void_p),
+                ("template_xyz", C.c_void_p), ("blocks", PoemBlock * POEM_MAX_BLOCKS)]
+
+
+class PoemInputs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_images", C.c_int32), ("view_counts", C.c_void_p), ("mlvl_feat", C.c_void_p),
+                ("cam_intr", C.c_void_p), ("cam_extr", C.c_void_p), ("reference_joints", C.c_void_p),
+                ("inp_img_w", C.c_float), ("inp_img_h", C.c_float)]
+
+
+# every symbol include/poem_b200.h declares
+EXPORTS = ["poem_abi_version", "poem_last_error", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+           "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
+           "poem_mha", "poem_knn32", "poem_project_sample", "poem_vector_attention",
+           "poem_vector_attention_workspace_bytes", "poem_layernorm"]
+
+_lib = None
+
+
+class PoemError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libpoem_b200.so; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PoemError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    lib.poem_abi_version.restype = i
+    lib.poem_last_error.restype = C.c_char_p
+    lib.poem_workspace_bytes.restype = sz
+    lib.poem_workspace_bytes.argtypes = [C.POINTER(PoemDims), i, i]
+    lib.poem_staging_bytes.restype = sz
+    lib.poem_staging_bytes.argtypes = [C.POINTER(PoemDims), i, i]
+    lib.poem_head_forward.restype = i
+    lib.poem_head_forward.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), C.POINTER(PoemInputs), vp, vp, vp,
+                                      sz, vp]
+    lib.poem_head_forward_host.restype = i
+    lib.poem_head_forward_host.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), C.POINTER(PoemInputs), vp, vp,
+                                           sz, vp]
+    lib.poem_transformer_workspace_bytes.restype = sz
+    lib.poem_transformer_workspace_bytes.argtypes = [C.POINTER(PoemDims), i]
+    lib.poem_transformer_forward.restype = i
+    lib.poem_transformer_forward.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), i, vp, vp, vp, vp, vp, vp,
+                                             vp, sz, vp]
+    lib.poem_linear.restype = i
+    lib.poem_linear.argtypes = [vp, i, vp, i, vp, i, i, i, i, vp, i, vp, i, vp, i, vp]
+    lib.poem_mha.restype = i
+    lib.poem_mha.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, i, vp]
+    lib.poem_knn32.restype = i
+    lib.poem_knn32.argtypes = [vp, vp, vp, i, i, i, vp]
+    lib.poem_project_sample.restype = i
+    lib.poem_project_sample.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, f, f, vp, vp, sz, vp]
+    lib.poem_vector_attention_workspace_bytes.restype = sz
+    lib.poem_vector_attention_workspace_bytes.argtypes = [i, i, i]
+    lib.poem_vector_attention.restype = i
+    lib.poem_vector_attention.argtypes = [C.POINTER(PoemVecAttn), vp, i, vp, i, vp, i, vp, vp, vp, vp, vp, i, i, i, i,
+                                          vp, vp, sz, vp]
+    lib.poem_layernorm.restype = i
+    lib.poem_layernorm.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PoemError(f"libpoem_b200 error {rc}: {load().poem_last_error().decode()}")
+
+
+def make_dims(d, max_views=10, run_last_ffn=False):
+    return PoemDims(d.embed_dims, d.in_channels, d.n_sample, d.n_query, d.n_blocks, d.n_heads, d.n_neighbor,
+                    d.feat_hw, d.feat_hw, d.center_idx, d.radius, max_views, int(run_last_ffn))
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,304 @@
+// Persistent warp-specialised tcgen05 GEMM:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
+//   A, W : bf16, K-major (row-major with K contiguous), staged by TMA (SWIZZLE_128B, 64-element K blocks)
+//   accumulate fp32 in TMEM (two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue (one TMEM lane quarter each)
+// Every Linear / 1x1-conv of the decoder path runs through this kernel (reference call sites: cuBLAS GEMMs
+// behind nn.Linear / nn.Conv2d(k=1) in lib/models/heads/ptEmb_head.py:94,755,760 and
+// lib/models/bricks/pt_metro_transformer.py:180-181, point_transformers.py:86-95,139-151).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace poem {
+
+enum GemmAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum GemmRes : int {
+  RES_NONE = 0,
+  RES_F32 = 1,      // out += res_f32[m * res_ld + n]
+  RES_POSADD = 2,   // out += res_f32[(row_tab[m / 256] * 256 + m % 256) * res_ld + n]   (positional term per view)
+  RES_MERGE = 3     // out = out * row_scale[m / P] + res_bf16[(row_base[m / P] + (m % P) * row_cnt[m / P]) * res_ld + n]
+};
+
+struct GemmEpilogue {
+  const float* bias;   // [N] or nullptr
+  int act;
+  int res_mode;
+  const float* res_f32;
+  const __nv_bfloat16* res_bf16;
+  int res_ld;
+  const int* row_tab;      // RES_POSADD: per-image row of the positional table; RES_MERGE: row_base per sample
+  const int* row_cnt;      // RES_MERGE: views per sample
+  int rows_per_group;      // RES_MERGE: P
+  float* out_f32;          // row-major [M, ld_f32] or nullptr
+  int ld_f32;
+  __nv_bfloat16* out_bf16; // row-major [M, ld_bf16] or nullptr
+  int ld_bf16;
+  // columns >= trans_from go to a per-group transposed buffer:
+  //   out_t[(m / t_rows) * t_group_stride + (n - trans_from) * t_rows + (m % t_rows)]
+  int trans_from;          // = N when unused
+  int t_rows;
+  long long t_group_stride;
+  __nv_bfloat16* out_t_bf16;
+  float* out_t_f32;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 4;
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kWBytes = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kABytes + kWBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
+                    int N, int K, GemmEpilogue ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                         // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full[s], 1);
+        mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * GEMM_BM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sw = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+          tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sw = sa + Cfg::kABytes;
+          const uint64_t da = make_kmajor_desc<128>(sa);
+          const uint64_t dw = make_kmajor_desc<128>(sw);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * GEMM_BM;
+      const int n0 = (tile % tiles_n) * BN;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < M;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+
+      // per-row epilogue state
+      const float* res_row_f32 = nullptr;
+      const __nv_bfloat16* res_row_bf16 = nullptr;
+      float row_scale = 1.0f;
+      if (row_ok) {
+        if (ep.res_mode == RES_F32) {
+          res_row_f32 = ep.res_f32 + (size_t)m * ep.res_ld;
+        } else if (ep.res_mode == RES_POSADD) {
+          res_row_f32 = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
+        } else if (ep.res_mode == RES_MERGE) {
+          const int g = m / ep.rows_per_group;
+          const int cnt = ep.row_cnt[g];
+          row_scale = 1.0f / (float)cnt;
+          res_row_bf16 = ep.res_bf16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+        }
+      }
+      size_t t_base = 0;
+      if (ep.trans_from < N && row_ok) {
+        const int g = m / ep.t_rows;
+        t_base = (size_t)g * ep.t_group_stride + (size_t)(m - g * ep.t_rows);
+      }
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (row_ok && n < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (n + j < N) ? __ldg(ep.bias + n + j) : 0.f;
+          }
+          if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (ep.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          const bool full = (n + 32 <= N);
+          if (res_row_f32 != nullptr) {
+            if (full) {
+              const float4* p = reinterpret_cast<const float4*>(res_row_f32 + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(p + j);
+                v[4 * j + 0] += t.x;
+                v[4 * j + 1] += t.y;
+                v[4 * j + 2] += t.z;
+                v[4 * j + 3] += t.w;
+              }
+            } else {
+              for (int j = 0; j < 32 && n + j < N; ++j) v[j] += res_row_f32[n + j];
+            }
+          } else if (res_row_bf16 != nullptr) {
+            for (int j = 0; j < 32; ++j)
+              if (n + j < N) v[j] = v[j] * row_scale + __bfloat162float(res_row_bf16[n + j]);
+          }
+          if (n >= ep.trans_from) {
+            // transposed store: consecutive lanes (rows) are contiguous in memory
+            const int tc = n - ep.trans_from;
+            if (ep.out_t_bf16 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < N) ep.out_t_bf16[t_base + (size_t)(tc + j) * ep.t_rows] = __float2bfloat16(v[j]);
+            }
+            if (ep.out_t_f32 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < N) ep.out_t_f32[t_base + (size_t)(tc + j) * ep.t_rows] = v[j];
+            }
+          } else {
+            if (ep.out_f32 != nullptr) {
+              float* o = ep.out_f32 + (size_t)m * ep.ld_f32 + n;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+                for (int j = 0; j < 32 && n + j < N; ++j) o[j] = v[j];
+              }
+            }
+            if (ep.out_bf16 != nullptr) {
+              __nv_bfloat16* o = ep.out_bf16 + (size_t)m * ep.ld_bf16 + n;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 pk;
+                  pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                  pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                  pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                  pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                  reinterpret_cast<uint4*>(o)[j] = pk;
+                }
+              } else {
+                for (int j = 0; j < 32 && n + j < N; ++j) o[j] = __float2bfloat16(v[j]);
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above) -> hand the accumulator back
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace poem

@@ -1,0 +1,766 @@
+// C-ABI implementation (include/poem_b200.h): host-side launch logic + whole-path orchestration.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/poem_b200.h"
+#include "gemm.cuh"
+#include "mha.cuh"
+#include "simt.cuh"
+
+using namespace poem;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail(POEM_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define POEM_TRY(expr)        \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != POEM_OK) return _r; \
+  } while (0)
+#define LAUNCH_CHECK(name)                                                                       \
+  do {                                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess) return fail(POEM_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" int poem_abi_version(void) { return POEM_ABI_VERSION; }
+extern "C" const char* poem_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = [box_cols, box_rows]; swizzle by box width.
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15))
+    return fail(POEM_E_ALIGN, "TMA operand needs 16-byte aligned base and pitch (base=%p ld=%llu)", base,
+                (unsigned long long)ld);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = (box_cols * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (box_cols * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return fail(POEM_E_BADDIM, "unsupported TMA box width %u", box_cols);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return POEM_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launch
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, const GemmEpilogue& ep,
+                          cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  GemmCfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(ta, tw, M, N, K, ep);
+  LAUNCH_CHECK("gemm_bf16_tc_kernel");
+  return POEM_OK;
+}
+
+static GemmEpilogue epi_default(int N) {
+  GemmEpilogue e;
+  memset(&e, 0, sizeof(e));
+  e.trans_from = N;
+  e.t_rows = 1;
+  return e;
+}
+
+static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+                       const GemmEpilogue& ep, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(POEM_E_BADDIM, "gemm: bad shape %d %d %d", M, N, K);
+  if (!A || !W) return fail(POEM_E_NULL, "gemm: null operand");
+  if (N % 32) return fail(POEM_E_BADDIM, "gemm: N=%d must be a multiple of 32", N);
+  if ((ep.out_f32 && (ep.ld_f32 % 4)) || (ep.out_bf16 && (ep.ld_bf16 % 8)) ||
+      (ep.res_mode == RES_F32 && (ep.res_ld % 4)))
+    return fail(POEM_E_ALIGN, "gemm: output/residual leading dimensions must keep rows 16-byte aligned");
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+  CUtensorMap ta, tw;
+  POEM_TRY(make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM));
+  POEM_TRY(make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, GEMM_BK, (uint32_t)BN));
+  if (BN == 256) return launch_gemm_bn<256>(ta, tw, M, N, K, ep, st);
+  if (BN == 128) return launch_gemm_bn<128>(ta, tw, M, N, K, ep, st);
+  return launch_gemm_bn<64>(ta, tw, M, N, K, ep, st);
+}
+
+extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N,
+                           int K, int act, const float* residual, int ld_res, float* out_f32, int ld_f32,
+                           poem_bf16* out_bf16, int ld_bf16, void* stream) {
+  GemmEpilogue e = epi_default(N);
+  e.bias = bias;
+  e.act = act;
+  if (residual) {
+    e.res_mode = RES_F32;
+    e.res_f32 = residual;
+    e.res_ld = ld_res;
+  }
+  e.out_f32 = out_f32;
+  e.ld_f32 = ld_f32;
+  e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  e.ld_bf16 = ld_bf16;
+  return launch_gemm(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W), ldw, M,
+                     N, K, e, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MHA launch
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, __nv_bfloat16* ctx,
+                         int ld_ctx, int B, int Lq, int Lk, int n_heads, int vt_batch_rows, int q_col0, int k_col0,
+                         int vt_row0, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(mha_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  MhaCfg<HD>::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid((Lq + MHA_BQ - 1) / MHA_BQ, n_heads, B);
+  const float scale_log2e = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+  mha_fwd_tc_kernel<HD><<<grid, MHA_THREADS, MhaCfg<HD>::kSmemBytes, st>>>(tq, tk, tv, ctx, ld_ctx, Lq, Lk,
+                                                                           vt_batch_rows, q_col0, k_col0, vt_row0,
+                                                                           scale_log2e);
+  LAUNCH_CHECK("mha_fwd_tc_kernel");
+  return POEM_OK;
+}
+
+// Q [B*Lq, ldq] (columns q_col0..), K [B*Lk, ldk] (columns k_col0..), Vt [B*vt_batch_rows, Lk] (rows vt_row0.. per batch)
+static int launch_mha(const __nv_bfloat16* Q, int ldq, int q_col0, const __nv_bfloat16* K, int ldk, int k_col0,
+                      const __nv_bfloat16* Vt, int vt_batch_rows, int vt_row0, __nv_bfloat16* ctx, int ld_ctx, int B,
+                      int Lq, int Lk, int D, int n_heads, cudaStream_t st) {
+  if (D % n_heads) return fail(POEM_E_BADDIM, "mha: D %% heads != 0");
+  const int hd = D / n_heads;
+  if (Lk % MHA_BKEY) return fail(POEM_E_BADDIM, "mha: Lk=%d must be a multiple of %d", Lk, MHA_BKEY);
+  if (ld_ctx % 8) return fail(POEM_E_ALIGN, "mha: ld_ctx must be a multiple of 8");
+  const uint32_t boxc = hd < 64 ? (uint32_t)hd : 64u;
+  CUtensorMap tq, tk, tv;
+  POEM_TRY(make_tmap_bf16(&tq, Q, (uint64_t)B * Lq, (uint64_t)ldq, (uint64_t)ldq, boxc, MHA_BQ));
+  POEM_TRY(make_tmap_bf16(&tk, K, (uint64_t)B * Lk, (uint64_t)ldk, (uint64_t)ldk, boxc, MHA_BKEY));
+  POEM_TRY(make_tmap_bf16(&tv, Vt, (uint64_t)B * vt_batch_rows, (uint64_t)Lk, (uint64_t)Lk, 64, (uint32_t)hd));
+  switch (hd) {
+    case 32: return launch_mha_hd<32>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, vt_batch_rows, q_col0, k_col0, vt_row0, st);
+    case 64: return launch_mha_hd<64>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, vt_batch_rows, q_col0, k_col0, vt_row0, st);
+    case 128: return launch_mha_hd<128>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, vt_batch_rows, q_col0, k_col0, vt_row0, st);
+    default: return fail(POEM_E_BADDIM, "mha: head dim %d unsupported (32, 64, 128)", hd);
+  }
+}
+
+extern "C" int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* Vt, poem_bf16* ctx,
+                        int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream) {
+  if (!Q || !K || !Vt || !ctx) return fail(POEM_E_NULL, "mha: null pointer");
+  return launch_mha(reinterpret_cast<const __nv_bfloat16*>(Q), ldq, 0, reinterpret_cast<const __nv_bfloat16*>(K), ldk,
+                    0, reinterpret_cast<const __nv_bfloat16*>(Vt), D, 0, reinterpret_cast<__nv_bfloat16*>(ctx), ld_ctx,
+                    B, Lq, Lk, D, n_heads, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small stages
+// ------------------------------------------------------------------------------------------------
+static int launch_knn(const float* q, const float* r, int* idx, int B, int Lq, int Lr, cudaStream_t st) {
+  if (Lr < 32) return fail(POEM_E_BADDIM, "knn: need at least 32 reference points");
+  const int total = B * Lq;
+  const int threads = 256;
+  const int blocks = (total * 32 + threads - 1) / threads;
+  knn32_kernel<<<blocks, threads, 0, st>>>(q, r, idx, Lq, Lr, total);
+  LAUNCH_CHECK("knn32_kernel");
+  return POEM_OK;
+}
+extern "C" int poem_knn32(const float* query_xyz, const float* ref_xyz, int32_t* idx, int B, int Lq, int Lr,
+                          void* stream) {
+  if (!query_xyz || !ref_xyz || !idx) return fail(POEM_E_NULL, "knn: null pointer");
+  return launch_knn(query_xyz, ref_xyz, idx, B, Lq, Lr, (cudaStream_t)stream);
+}
+
+static int launch_layernorm(const float* x, const float* g, const float* b, float* y32, __nv_bfloat16* y16, int rows,
+                            int D, cudaStream_t st) {
+  if (D % 32 || D > 1024) return fail(POEM_E_BADDIM, "layernorm: D=%d", D);
+  const int threads = 256;
+  layernorm_kernel<<<(rows * 32 + threads - 1) / threads, threads, 0, st>>>(x, g, b, y32, y16, rows, D, 1e-12f);
+  LAUNCH_CHECK("layernorm_kernel");
+  return POEM_OK;
+}
+extern "C" int poem_layernorm(const float* x, const float* gamma, const float* beta, float* y_f32, poem_bf16* y_bf16,
+                              int rows, int D, void* stream) {
+  if (!x || !gamma || !beta) return fail(POEM_E_NULL, "layernorm: null pointer");
+  return launch_layernorm(x, gamma, beta, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), rows, D,
+                          (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace bump allocator
+// ------------------------------------------------------------------------------------------------
+struct Bump {
+  uint8_t* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// per-image / per-sample index tables derived from view_counts
+struct ViewTables {
+  int *img_sample, *img_view, *img_posrow, *sample_rowbase, *sample_views;
+};
+static size_t view_tables_ints(int B, int NV) { return (size_t)3 * NV + 2 * B; }
+static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, int max_views, int* dev, ViewTables* vt,
+                              cudaStream_t st) {
+  std::vector<int> h(view_tables_ints(B, NV));
+  int* img_sample = h.data();
+  int* img_view = img_sample + NV;
+  int* img_posrow = img_view + NV;
+  int* rowbase = img_posrow + NV;
+  int* views = rowbase + B;
+  int img = 0;
+  long long rb = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = host_views[b];
+    if (n < 1 || n > max_views) return fail(POEM_E_BADDIM, "view count %d of sample %d outside [1,%d]", n, b, max_views);
+    rowbase[b] = (int)rb;
+    views[b] = n;
+    for (int v = 0; v < n; ++v, ++img) {
+      if (img >= NV) return fail(POEM_E_BADDIM, "sum(view_counts) exceeds n_images=%d", NV);
+      img_sample[img] = b;
+      img_view[img] = v;
+      img_posrow[img] = n * (n - 1) / 2 + v;
+    }
+    rb += (long long)n * P;
+    if (rb > 0x7fffffffLL) return fail(POEM_E_BADDIM, "too many merge rows");
+  }
+  if (img != NV) return fail(POEM_E_BADDIM, "sum(view_counts)=%d != n_images=%d", img, NV);
+  CUDA_TRY(cudaMemcpyAsync(dev, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  vt->img_sample = dev;
+  vt->img_view = dev + NV;
+  vt->img_posrow = dev + 2 * NV;
+  vt->sample_rowbase = dev + 3 * NV;
+  vt->sample_views = dev + 3 * NV + B;
+  return POEM_OK;
+}
+
+static int launch_project_sample(const float* xmap, const float* intr, const float* extr, const float* bps,
+                                 const float* centre, const ViewTables& vt, float* proj, int NV, int D, int P, int fh,
+                                 int fw, float img_w, float img_h, __nv_bfloat16* X, cudaStream_t st) {
+  if (P != SAMPLE_THREADS * 8) return fail(POEM_E_BADDIM, "sampler is specialised for P=4096 (got %d)", P);
+  if (D % SAMPLE_CH || P % D) return fail(POEM_E_BADDIM, "sampler: D=%d must divide P and be a multiple of 32", D);
+  camera_prep_kernel<<<(NV + 63) / 64, 64, 0, st>>>(intr, extr, proj, NV);
+  LAUNCH_CHECK("camera_prep_kernel");
+  const size_t smem = (size_t)SAMPLE_CH * fh * fw * sizeof(float);
+  if (smem > 48 * 1024) return fail(POEM_E_BADDIM, "feature map %dx%d too large for the sampler", fh, fw);
+  dim3 grid(D / SAMPLE_CH, NV);
+  project_sample_kernel<<<grid, SAMPLE_THREADS, smem, st>>>(xmap, proj, bps, centre, vt.img_sample, vt.img_view,
+                                                           vt.sample_rowbase, X, D, P, fh, fw, 1.0f / img_w,
+                                                           1.0f / img_h);
+  LAUNCH_CHECK("project_sample_kernel");
+  return POEM_OK;
+}
+
+extern "C" int poem_project_sample(const float* xmap, const float* cam_intr, const float* cam_extr, const float* bps,
+                                   const float* centre, const int32_t* host_view_counts, int B, int n_images, int D,
+                                   int P, int fh, int fw, float img_w, float img_h, poem_bf16* X, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!xmap || !cam_intr || !cam_extr || !bps || !centre || !host_view_counts || !X || !workspace)
+    return fail(POEM_E_NULL, "project_sample: null pointer");
+  Bump bump{reinterpret_cast<uint8_t*>(workspace), 0};
+  int* tab = bump.take<int>(view_tables_ints(B, n_images));
+  float* proj = bump.take<float>((size_t)n_images * 24);
+  if (bump.off > workspace_bytes) return fail(POEM_E_WORKSPACE, "project_sample: workspace %zu < %zu", workspace_bytes, bump.off);
+  ViewTables vt;
+  POEM_TRY(upload_view_tables(host_view_counts, B, n_images, P, 64, tab, &vt, (cudaStream_t)stream));
+  return launch_project_sample(xmap, cam_intr, cam_extr, bps, centre, vt, proj, n_images, D, P, fh, fw, img_w, img_h,
+                               reinterpret_cast<__nv_bfloat16*>(X), (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector attention
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t poem_vector_attention_workspace_bytes(int B, int Lq, int D) {
+  return 3 * (((size_t)B * Lq * 32 * D * 2 + 1023) & ~size_t(1023)) + 4096;
+}
+
+// Un-fused composition: token tensors (B*Lq*32, D) live in HBM between the three D x D GEMMs.
+//   t0: h_delta -> tmix -> a ; t1: pos ; t2: relu(gamma1)
+static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* ktab, int ldk,
+                          const __nv_bfloat16* vtab, int ldv, const float* q_xyz, const float* ref_xyz, const int* idx,
+                          const int* anchor_idx, const float* anchor_xyz, int B, int Lq, int Lr, int D,
+                          __nv_bfloat16* res, __nv_bfloat16* t0, __nv_bfloat16* t1, __nv_bfloat16* t2,
+                          cudaStream_t st) {
+  if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->gamma1.w || !w->gamma2.w)
+    return fail(POEM_E_NULL, "vector_attention: weight pointer missing");
+  const size_t n_query = (size_t)B * Lq;
+  const size_t T = n_query * 32;
+  if (T > 0x7fffffffULL) return fail(POEM_E_BADDIM, "vector_attention: too many tokens");
+  va_hdelta_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(q_xyz, ref_xyz, idx, anchor_xyz, w->wd1, w->bd1, t0, Lq, Lr,
+                                                          D, T);
+  LAUNCH_CHECK("va_hdelta_kernel");
+  auto lin = [&](const __nv_bfloat16* A, const PoemLinear& l, int act, __nv_bfloat16* out) {
+    GemmEpilogue e = epi_default(D);
+    e.bias = l.b;
+    e.act = act;
+    e.out_bf16 = out;
+    e.ld_bf16 = D;
+    return launch_gemm(A, D, reinterpret_cast<const __nv_bfloat16*>(l.w), D, (int)T, D, D, e, st);
+  };
+  POEM_TRY(lin(t0, w->delta2, ACT_NONE, t1));  // pos
+  {
+    const size_t total = T * (D / 8);
+    va_tmix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, ldq, ktab, ldk, idx, anchor_idx, t1, t0, Lq, Lr,
+                                                                   D, T);
+    LAUNCH_CHECK("va_tmix_kernel");
+  }
+  POEM_TRY(lin(t0, w->gamma1, ACT_RELU, t2));
+  POEM_TRY(lin(t2, w->gamma2, ACT_NONE, t0));  // attention logits
+  {
+    const size_t total = n_query * D;
+    va_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t0, t1, vtab, ldv, idx, anchor_idx, res, Lq, Lr, D,
+                                                                     1.0f / sqrtf((float)D), n_query);
+    LAUNCH_CHECK("va_reduce_kernel");
+  }
+  return POEM_OK;
+}
+
+static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* ktab,
+                                   int ldk, const __nv_bfloat16* vtab, int ldv, const float* q_xyz,
+                                   const float* ref_xyz, const int* idx, const int* anchor_idx,
+                                   const float* anchor_xyz, int B, int Lq, int Lr, int D, __nv_bfloat16* res,
+                                   __nv_bfloat16* t0, __nv_bfloat16* t1, __nv_bfloat16* t2, cudaStream_t st) {
+  if ((idx == nullptr) == (anchor_idx == nullptr)) return fail(POEM_E_NULL, "vector_attention: give idx XOR anchors");
+  if (anchor_idx && !anchor_xyz) return fail(POEM_E_NULL, "vector_attention: anchor_xyz missing");
+  if (D % 32) return fail(POEM_E_BADDIM, "vector_attention: D=%d", D);
+  return launch_vecattn(w, q, ldq, ktab, ldk, vtab, ldv, q_xyz, ref_xyz, idx, anchor_idx, anchor_xyz, B, Lq, Lr, D,
+                        res, t0, t1, t2, st);
+}
+
+extern "C" int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, int ldq, const poem_bf16* ktab, int ldk,
+                                     const poem_bf16* vtab, int ldv, const float* q_xyz, const float* ref_xyz,
+                                     const int32_t* idx, const int32_t* anchor_idx, const float* anchor_xyz, int B,
+                                     int Lq, int Lr, int D, poem_bf16* res, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  if (!w || !q || !ktab || !vtab || !q_xyz || !res || !workspace) return fail(POEM_E_NULL, "vector_attention: null");
+  if (workspace_bytes < poem_vector_attention_workspace_bytes(B, Lq, D))
+    return fail(POEM_E_WORKSPACE, "vector_attention: workspace too small");
+  Bump bump{reinterpret_cast<uint8_t*>(workspace), 0};
+  const size_t n = (size_t)B * Lq * 32 * D;
+  __nv_bfloat16* t0 = bump.take<__nv_bfloat16>(n);
+  __nv_bfloat16* t1 = bump.take<__nv_bfloat16>(n);
+  __nv_bfloat16* t2 = bump.take<__nv_bfloat16>(n);
+  return launch_vector_attention(w, reinterpret_cast<const __nv_bfloat16*>(q), ldq,
+                                 reinterpret_cast<const __nv_bfloat16*>(ktab), ldk,
+                                 reinterpret_cast<const __nv_bfloat16*>(vtab), ldv, q_xyz, ref_xyz, idx, anchor_idx,
+                                 anchor_xyz, B, Lq, Lr, D, reinterpret_cast<__nv_bfloat16*>(res), t0, t1, t2,
+                                 (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole path
+// ------------------------------------------------------------------------------------------------
+struct BlockPlan {   // decoder blocks (PtEmbedTRv4)
+  float *pt_xyz, *xyz;  // xyz: (NB+1) buffers of B*Q*3
+  __nv_bfloat16 *ptf, *KK, *VT;
+  float *qf32, *qe32, *tmp32, *a1_32, *a2_32, *f1_32, *f2_32;
+  __nv_bfloat16 *qf16, *qe16, *qp16, *ctx16, *a1_16, *a2_16, *qkv16, *res16, *f1_16, *qc16, *f2_16, *r1_16, *ffn16;
+  int *idx_self, *idx_cross;
+  __nv_bfloat16 *t0, *t1, *t2;
+};
+struct HeadPlan {    // everything in front of the blocks
+  int* tables;
+  float *proj, *centre, *xmap;
+  __nv_bfloat16 *featT, *X, *H1, *Mm, *S, *H2;
+};
+
+static int check_dims(const PoemDims* d) {
+  if (!d) return fail(POEM_E_NULL, "dims is NULL");
+  const int D = d->embed_dims;
+  if (!(D == 128 || D == 256 || D == 512 || D == 1024)) return fail(POEM_E_BADDIM, "embed_dims=%d unsupported", D);
+  if (d->n_heads <= 0 || D % d->n_heads) return fail(POEM_E_BADDIM, "n_heads=%d", d->n_heads);
+  const int hd = D / d->n_heads;
+  if (!(hd == 32 || hd == 64 || hd == 128)) return fail(POEM_E_BADDIM, "head dim %d unsupported", hd);
+  if (d->n_sample != 4096) return fail(POEM_E_BADDIM, "n_sample=%d (kernels are specialised for 4096)", d->n_sample);
+  if (d->n_neighbor != 32) return fail(POEM_E_BADDIM, "n_neighbor=%d (kernels are specialised for 32)", d->n_neighbor);
+  if (d->feat_h * d->feat_w != 256) return fail(POEM_E_BADDIM, "feature map must have 256 pixels");
+  if (d->n_blocks < 1 || d->n_blocks > POEM_MAX_BLOCKS) return fail(POEM_E_BADDIM, "n_blocks=%d", d->n_blocks);
+  if (d->in_channels % 8) return fail(POEM_E_BADDIM, "in_channels=%d must be a multiple of 8", d->in_channels);
+  if (d->n_query < 32 || d->max_views < 1) return fail(POEM_E_BADDIM, "n_query / max_views");
+  return POEM_OK;
+}
+
+static void plan_blocks(const PoemDims* d, int B, Bump& b, BlockPlan* p) {
+  const size_t D = d->embed_dims, P = d->n_sample, Q = d->n_query;
+  const size_t BP = (size_t)B * P, BQ = (size_t)B * Q, T = BQ * 32;
+  p->pt_xyz = b.take<float>(BP * 3);
+  p->xyz = b.take<float>((size_t)(d->n_blocks + 1) * BQ * 3);
+  p->ptf = b.take<__nv_bfloat16>(BP * D);
+  p->KK = b.take<__nv_bfloat16>(BP * 4 * D);
+  p->VT = b.take<__nv_bfloat16>(BP * 2 * D);
+  p->qf32 = b.take<float>(BQ * D);
+  p->qe32 = b.take<float>(BQ * D);
+  p->tmp32 = b.take<float>(BQ * D);
+  p->a1_32 = b.take<float>(BQ * D);
+  p->a2_32 = b.take<float>(BQ * D);
+  p->f1_32 = b.take<float>(BQ * D);
+  p->f2_32 = b.take<float>(BQ * D);
+  p->qf16 = b.take<__nv_bfloat16>(BQ * D);
+  p->qe16 = b.take<__nv_bfloat16>(BQ * D);
+  p->qp16 = b.take<__nv_bfloat16>(BQ * D);
+  p->ctx16 = b.take<__nv_bfloat16>(BQ * D);
+  p->a1_16 = b.take<__nv_bfloat16>(BQ * D);
+  p->a2_16 = b.take<__nv_bfloat16>(BQ * D);
+  p->qkv16 = b.take<__nv_bfloat16>(BQ * 3 * D);
+  p->res16 = b.take<__nv_bfloat16>(BQ * D);
+  p->f1_16 = b.take<__nv_bfloat16>(BQ * D);
+  p->qc16 = b.take<__nv_bfloat16>(BQ * D);
+  p->f2_16 = b.take<__nv_bfloat16>(BQ * D);
+  p->r1_16 = b.take<__nv_bfloat16>(BQ * D);
+  p->ffn16 = b.take<__nv_bfloat16>(BQ * 4 * D);
+  p->idx_self = b.take<int>(T);
+  p->idx_cross = b.take<int>(T);
+  p->t0 = b.take<__nv_bfloat16>(T * D);
+  p->t1 = b.take<__nv_bfloat16>(T * D);
+  p->t2 = b.take<__nv_bfloat16>(T * D);
+}
+
+static void plan_head(const PoemDims* d, int B, int NV, Bump& b, HeadPlan* p) {
+  const size_t D = d->embed_dims, C = d->in_channels, P = d->n_sample, F = 256;
+  const size_t R = (size_t)NV * P, BP = (size_t)B * P;
+  p->tables = b.take<int>(view_tables_ints(B, NV));
+  p->proj = b.take<float>((size_t)NV * 24);
+  p->centre = b.take<float>((size_t)B * 3);
+  p->featT = b.take<__nv_bfloat16>((size_t)NV * F * C);
+  p->xmap = b.take<float>((size_t)NV * D * F);
+  p->X = b.take<__nv_bfloat16>(R * D);
+  p->H1 = b.take<__nv_bfloat16>(R * D);
+  p->Mm = b.take<__nv_bfloat16>(R * D / 2);
+  p->S = b.take<__nv_bfloat16>(BP * D / 2);
+  p->H2 = b.take<__nv_bfloat16>(BP * D / 2);
+}
+
+extern "C" size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images) {
+  if (check_dims(dims) != POEM_OK || batch < 1 || n_images < batch) return 0;
+  Bump b{nullptr, 0};
+  HeadPlan hp;
+  BlockPlan bp;
+  plan_head(dims, batch, n_images, b, &hp);
+  plan_blocks(dims, batch, b, &bp);
+  return b.off + 1024;
+}
+extern "C" size_t poem_transformer_workspace_bytes(const PoemDims* dims, int batch) {
+  if (check_dims(dims) != POEM_OK || batch < 1) return 0;
+  Bump b{nullptr, 0};
+  BlockPlan bp;
+  plan_blocks(dims, batch, b, &bp);
+  return b.off + 1024;
+}
+
+static inline const __nv_bfloat16* W16(const PoemLinear& l) { return reinterpret_cast<const __nv_bfloat16*>(l.w); }
+
+static int linear(const __nv_bfloat16* A, int lda, const PoemLinear& l, int M, int N, int K, int act,
+                  const float* res32, float* o32, __nv_bfloat16* o16, cudaStream_t st) {
+  if (!l.w) return fail(POEM_E_NULL, "weight pointer missing");
+  GemmEpilogue e = epi_default(N);
+  e.bias = l.b;
+  e.act = act;
+  if (res32) {
+    e.res_mode = RES_F32;
+    e.res_f32 = res32;
+    e.res_ld = N;
+  }
+  e.out_f32 = o32;
+  e.ld_f32 = N;
+  e.out_bf16 = o16;
+  e.ld_bf16 = N;
+  return launch_gemm(A, lda, W16(l), K, M, N, K, e, st);
+}
+
+// a8-a13: the NB decoder blocks. Expects p.ptf (bf16 BPS features), p.pt_xyz, p.xyz[0], p.qf32/p.qf16 filled.
+// coords_out[i] = nan_to_num(xyz_i) * radius + centre when centre != NULL, else the raw normalised xyz_i.
+static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const BlockPlan& p, const float* centre,
+                      float* coords_out, float* out_feats, cudaStream_t st) {
+  const int D = dims->embed_dims, P = dims->n_sample, Q = dims->n_query, NB = dims->n_blocks;
+  const int BQ = B * Q, BP = B * P;
+  for (int i = 0; i < NB; ++i) {
+    const PoemBlock& k = w->blocks[i];
+    float* xyz_in = p.xyz + (size_t)i * BQ * 3;
+    float* xyz_out = p.xyz + (size_t)(i + 1) * BQ * 3;
+    // BPS-token projections: K1 | K2 | k' | v' row-major, V1 | V2 transposed per sample
+    {
+      if (!k.pt_proj.w) return fail(POEM_E_NULL, "block %d: pt_proj missing", i);
+      GemmEpilogue e = epi_default(6 * D);
+      e.bias = k.pt_proj.b;
+      e.out_bf16 = p.KK;
+      e.ld_bf16 = 4 * D;
+      e.trans_from = 4 * D;
+      e.t_rows = P;
+      e.t_group_stride = (long long)2 * D * P;
+      e.out_t_bf16 = p.VT;
+      POEM_TRY(launch_gemm(p.ptf, D, W16(k.pt_proj), D, BP, 6 * D, D, e, st));
+    }
+    POEM_TRY(linear(p.qf16, D, k.embedding, BQ, D, D, ACT_NONE, nullptr, p.qe32, p.qe16, st));
+    // MHA 1
+    POEM_TRY(linear(p.qe16, D, k.q1, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
+    POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 4 * D, 0, p.VT, 2 * D, 0, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
+    POEM_TRY(linear(p.ctx16, D, k.o1, BQ, D, D, ACT_NONE, p.qe32, p.tmp32, nullptr, st));
+    POEM_TRY(launch_layernorm(p.tmp32, k.ln1_g, k.ln1_b, p.a1_32, p.a1_16, BQ, D, st));
+    // MHA 2
+    POEM_TRY(linear(p.a1_16, D, k.q2, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
+    POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 4 * D, D, p.VT, 2 * D, D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
+    POEM_TRY(linear(p.ctx16, D, k.o2, BQ, D, D, ACT_NONE, p.a1_32, p.tmp32, nullptr, st));
+    POEM_TRY(launch_layernorm(p.tmp32, k.ln2_g, k.ln2_b, p.a2_32, p.a2_16, BQ, D, st));
+    // vector self-attention
+    POEM_TRY(linear(p.a2_16, D, k.self_qkv, BQ, 3 * D, D, ACT_NONE, nullptr, nullptr, p.qkv16, st));
+    const bool anchors = (i == 0);
+    if (!anchors) POEM_TRY(launch_knn(xyz_in, xyz_in, p.idx_self, B, Q, Q, st));
+    POEM_TRY(launch_vector_attention(&k.self_attn, p.qkv16, 3 * D, p.qkv16 + D, 3 * D, p.qkv16 + 2 * D, 3 * D, xyz_in,
+                                     xyz_in, anchors ? nullptr : p.idx_self, anchors ? w->anchor_idx : nullptr,
+                                     anchors ? w->anchor_xyz : nullptr, B, Q, Q, D, p.res16, p.t0, p.t1, p.t2, st));
+    POEM_TRY(linear(p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
+    // vector cross-attention (queries <- BPS tokens)
+    POEM_TRY(linear(p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
+    if (!anchors) POEM_TRY(launch_knn(xyz_in, p.pt_xyz, p.idx_cross, B, Q, P, st));
+    POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 4 * D, p.KK + 3 * D, 4 * D, xyz_in,
+                                     p.pt_xyz, anchors ? nullptr : p.idx_cross, anchors ? w->anchor_idx : nullptr,
+                                     anchors ? w->anchor_xyz : nullptr, B, Q, P, D, p.res16, p.t0, p.t1, p.t2, st));
+    POEM_TRY(linear(p.res16, D, k.cross_attn.fc2, BQ, D, D, ACT_NONE, p.f1_32, p.f2_32, p.f2_16, st));
+    // coordinate regression
+    POEM_TRY(linear(p.f2_16, D, k.reg1, BQ, D, D, ACT_RELU, nullptr, nullptr, p.r1_16, st));
+    {
+      if (!k.reg2_w || !k.reg2_b) return fail(POEM_E_NULL, "block %d: reg_branch.2 missing", i);
+      const int threads = 256;
+      reg_out_kernel<<<((size_t)BQ * 32 + threads - 1) / threads, threads, 0, st>>>(
+          p.r1_16, k.reg2_w, k.reg2_b, xyz_in, xyz_out, coords_out + (size_t)i * BQ * 3, centre, dims->radius, Q, D,
+          BQ);
+      LAUNCH_CHECK("reg_out_kernel");
+    }
+    // feed-forward (its output only feeds the next block)
+    const bool last = (i == NB - 1);
+    if (!last || dims->run_last_ffn) {
+      POEM_TRY(linear(p.f2_16, D, k.ffn1, BQ, 4 * D, D, ACT_GELU, nullptr, nullptr, p.ffn16, st));
+      POEM_TRY(linear(p.ffn16, 4 * D, k.ffn2, BQ, D, 4 * D, ACT_NONE, p.f2_32, p.tmp32, nullptr, st));
+      float* dst32 = (last && out_feats) ? out_feats : p.qf32;
+      POEM_TRY(launch_layernorm(p.tmp32, k.ln3_g, k.ln3_b, dst32, p.qf16, BQ, D, st));
+    }
+  }
+  return POEM_OK;
+}
+
+extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights* w, int B, const float* query_xyz,
+                                        const float* query_feat, const float* pt_xyz, const float* pt_feats,
+                                        float* out_xyz, float* out_feats, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  POEM_TRY(check_dims(dims));
+  if (!w || !query_xyz || !query_feat || !pt_xyz || !pt_feats || !out_xyz || !workspace)
+    return fail(POEM_E_NULL, "transformer_forward: null pointer");
+  if (B < 1) return fail(POEM_E_BADDIM, "batch=%d", B);
+  if (out_feats && !dims->run_last_ffn) return fail(POEM_E_BADDIM, "out_feats needs dims->run_last_ffn");
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump b{reinterpret_cast<uint8_t*>(workspace), 0};
+  BlockPlan p;
+  plan_blocks(dims, B, b, &p);
+  if (b.off + 1024 > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, b.off + 1024);
+  const size_t D = dims->embed_dims, BP = (size_t)B * dims->n_sample, BQ = (size_t)B * dims->n_query;
+  CUDA_TRY(cudaMemcpyAsync(p.pt_xyz, pt_xyz, BP * 3 * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(p.xyz, query_xyz, BQ * 3 * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(p.qf32, query_feat, BQ * D * 4, cudaMemcpyDeviceToDevice, st));
+  f32_to_bf16_kernel<<<(unsigned)((BQ * D + 255) / 256), 256, 0, st>>>(query_feat, p.qf16, BQ * D);
+  LAUNCH_CHECK("f32_to_bf16_kernel");
+  f32_to_bf16_kernel<<<(unsigned)((BP * D + 255) / 256), 256, 0, st>>>(pt_feats, p.ptf, BP * D);
+  LAUNCH_CHECK("f32_to_bf16_kernel");
+  return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, st);
+}
+
+extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
+                                 float* out_feats, void* workspace, size_t workspace_bytes, void* stream) {
+  POEM_TRY(check_dims(dims));
+  if (!w || !in || !out_coords || !workspace) return fail(POEM_E_NULL, "head_forward: null pointer");
+  if (!in->view_counts || !in->mlvl_feat || !in->cam_intr || !in->cam_extr || !in->reference_joints)
+    return fail(POEM_E_NULL, "head_forward: null input");
+  if (!w->pos_table || !w->query_embed || !w->bps || !w->anchor_xyz || !w->anchor_idx || !w->template_xyz)
+    return fail(POEM_E_NULL, "head_forward: null constant table");
+  const int B = in->batch, NV = in->n_images;
+  if (B < 1 || NV < B) return fail(POEM_E_BADDIM, "batch=%d n_images=%d", B, NV);
+  if (out_feats && !dims->run_last_ffn) return fail(POEM_E_BADDIM, "out_feats needs dims->run_last_ffn");
+  const int D = dims->embed_dims, C = dims->in_channels, P = dims->n_sample, Q = dims->n_query;
+  const int F = 256, H = D / 2;
+  const int BQ = B * Q, BP = B * P;
+  const long long R = (long long)NV * P;
+  if (R > 0x7fffffffLL || (long long)BQ * 32 > 0x7fffffffLL) return fail(POEM_E_BADDIM, "problem too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  Bump bump{reinterpret_cast<uint8_t*>(workspace), 0};
+  HeadPlan h;
+  BlockPlan p;
+  plan_head(dims, B, NV, bump, &h);
+  plan_blocks(dims, B, bump, &p);
+  if (bump.off + 1024 > workspace_bytes)
+    return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, bump.off + 1024);
+
+  ViewTables vt;
+  POEM_TRY(upload_view_tables(in->view_counts, B, NV, P, dims->max_views, h.tables, &vt, st));
+
+  // ---- a2: x = input_proj(feat) + positional term, written channel-planar (NV, D, 256) fp32
+  {
+    dim3 grid((F + 31) / 32, (C + 31) / 32, NV), block(32, 8);
+    nchw_to_rows_bf16_kernel<<<grid, block, 0, st>>>(in->mlvl_feat, h.featT, C, F);
+    LAUNCH_CHECK("nchw_to_rows_bf16_kernel");
+    GemmEpilogue e = epi_default(D);
+    e.bias = w->input_proj.b;
+    e.res_mode = RES_POSADD;
+    e.res_f32 = w->pos_table;
+    e.res_ld = D;
+    e.row_tab = vt.img_posrow;
+    e.trans_from = 0;
+    e.t_rows = F;
+    e.t_group_stride = (long long)D * F;
+    e.out_t_f32 = h.xmap;
+    POEM_TRY(launch_gemm(h.featT, C, W16(w->input_proj), C, NV * F, D, C, e, st));
+  }
+  // ---- a3/a7: centre, normalised point sets
+  gather_centre_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(in->reference_joints, h.centre, dims->center_idx, B);
+  LAUNCH_CHECK("gather_centre_kernel");
+  {
+    const int total = B * (P + Q) * 3;
+    normalise_points_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->bps, w->template_xyz, h.centre, p.pt_xyz, p.xyz, P,
+                                                                Q, dims->radius, B);
+    LAUNCH_CHECK("normalise_points_kernel");
+  }
+  // ---- a4/a5 (+ the raw .view regroup of a6): X rows
+  POEM_TRY(launch_project_sample(h.xmap, in->cam_intr, in->cam_extr, w->bps, h.centre, vt, h.proj, NV, D, P,
+                                 dims->feat_h, dims->feat_w, in->inp_img_w, in->inp_img_h, h.X, st));
+  // ---- a6: merge network
+  POEM_TRY(linear(h.X, D, w->merge0a, (int)R, D, D, ACT_RELU, nullptr, nullptr, h.H1, st));
+  POEM_TRY(linear(h.H1, D, w->merge0b, (int)R, H, D, ACT_NONE, nullptr, nullptr, h.Mm, st));
+  {
+    const int threads = 256;
+    merge_reduce_kernel<<<(unsigned)(((size_t)BP * 32 + threads - 1) / threads), threads, 0, st>>>(
+        h.Mm, vt.sample_rowbase, vt.sample_views, h.S, H, P, BP);
+    LAUNCH_CHECK("merge_reduce_kernel");
+  }
+  POEM_TRY(linear(h.S, H, w->merge1a, BP, H, H, ACT_RELU, nullptr, nullptr, h.H2, st));
+  {
+    if (!w->merge1b.w) return fail(POEM_E_NULL, "merge_net_feature.1.2 missing");
+    GemmEpilogue e = epi_default(D);
+    e.bias = w->merge1b.b;
+    e.res_mode = RES_MERGE;
+    e.res_bf16 = h.X;
+    e.res_ld = D;
+    e.row_tab = vt.sample_rowbase;
+    e.row_cnt = vt.sample_views;
+    e.rows_per_group = P;
+    e.out_bf16 = p.ptf;
+    e.ld_bf16 = D;
+    POEM_TRY(launch_gemm(h.H2, H, W16(w->merge1b), H, BP, D, H, e, st));
+  }
+  // ---- a7: query features
+  {
+    const size_t total = (size_t)BQ * D;
+    broadcast_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w->query_embed, p.qf32, p.qf16, Q * D,
+                                                                             total);
+    LAUNCH_CHECK("broadcast_queries_kernel");
+  }
+  // ---- a8-a15
+  return run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer variant
+// ------------------------------------------------------------------------------------------------
+static size_t align1k(size_t x) { return (x + 1023) & ~size_t(1023); }
+extern "C" size_t poem_staging_bytes(const PoemDims* d, int B, int NV) {
+  if (check_dims(d) != POEM_OK) return 0;
+  return align1k((size_t)NV * d->in_channels * 256 * 4) + align1k((size_t)NV * 9 * 4) + align1k((size_t)NV * 16 * 4) +
+         align1k((size_t)B * 63 * 4) + align1k((size_t)d->n_blocks * B * d->n_query * 3 * 4) + 1024;
+}
+
+extern "C" int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* hin,
+                                      float* host_out, void* workspace, size_t workspace_bytes, void* stream) {
+  POEM_TRY(check_dims(dims));
+  if (!hin || !host_out || !workspace) return fail(POEM_E_NULL, "head_forward_host: null pointer");
+  const int B = hin->batch, NV = hin->n_images;
+  const size_t stage = poem_staging_bytes(dims, B, NV);
+  const size_t need = stage + poem_workspace_bytes(dims, B, NV);
+  if (workspace_bytes < need) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump b{reinterpret_cast<uint8_t*>(workspace), 0};
+  const size_t n_feat = (size_t)NV * dims->in_channels * 256;
+  float* d_feat = b.take<float>(n_feat);
+  float* d_intr = b.take<float>((size_t)NV * 9);
+  float* d_extr = b.take<float>((size_t)NV * 16);
+  float* d_ref = b.take<float>((size_t)B * 63);
+  const size_t n_out = (size_t)dims->n_blocks * B * dims->n_query * 3;
+  float* d_out = b.take<float>(n_out);
+  CUDA_TRY(cudaMemcpyAsync(d_feat, hin->mlvl_feat, n_feat * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_intr, hin->cam_intr, (size_t)NV * 9 * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_extr, hin->cam_extr, (size_t)NV * 16 * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_ref, hin->reference_joints, (size_t)B * 63 * 4, cudaMemcpyHostToDevice, st));
+  PoemInputs din = *hin;
+  din.mlvl_feat = d_feat;
+  din.cam_intr = d_intr;
+  din.cam_extr = d_extr;
+  din.reference_joints = d_ref;
+  POEM_TRY(poem_head_forward(dims, w, &din, d_out, nullptr, reinterpret_cast<uint8_t*>(workspace) + stage,
+                             workspace_bytes - stage, stream));
+  CUDA_TRY(cudaMemcpyAsync(host_out, d_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+  return POEM_OK;
+}

@@ -1,0 +1,463 @@
+// HBM-bound / latency-bound SIMT kernels of the decoder path: layout conversion, camera projection +
+// bilinear sampling, cross-view reduce, LayerNorm, 32-NN search, vector-attention glue, coordinate regression.
+#pragma once
+#include "common.cuh"
+
+namespace poem {
+
+// ------------------------------------------------------------------------------------------------
+// (BV,C,256) f32 NCHW feature maps -> (BV*256, C) bf16 rows (K-major A operand of the input projection)
+// reference: input of nn.Conv2d(k=1) at lib/models/heads/ptEmb_head.py:835
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_rows_bf16_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ rows, int C,
+                                         int HW) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? feat[((size_t)img * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (c < C && p < HW) rows[((size_t)img * HW + p) * C + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Camera preparation: P = K · inv(cam_extr)[:3,:]  (3x4), one thread per image.
+// reference: torch.linalg.inv + batch_cam_extr_transf + batch_cam_intr_projection
+// (lib/utils/collation.py:60-61, lib/utils/transform.py:898-930)
+// ------------------------------------------------------------------------------------------------
+__global__ void camera_prep_kernel(const float* __restrict__ intr, const float* __restrict__ extr,
+                                   float* __restrict__ proj, int n_img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img) return;
+  float a[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      a[r][c] = extr[i * 16 + r * 4 + c];
+      a[r][4 + c] = (r == c) ? 1.f : 0.f;
+    }
+  // Gauss-Jordan with partial pivoting
+  for (int col = 0; col < 4; ++col) {
+    int piv = col;
+    float best = fabsf(a[col][col]);
+    for (int r = col + 1; r < 4; ++r)
+      if (fabsf(a[r][col]) > best) {
+        best = fabsf(a[r][col]);
+        piv = r;
+      }
+    if (piv != col)
+      for (int c = 0; c < 8; ++c) {
+        const float t = a[col][c];
+        a[col][c] = a[piv][c];
+        a[piv][c] = t;
+      }
+    const float inv = 1.0f / a[col][col];
+    for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+    for (int r = 0; r < 4; ++r)
+      if (r != col) {
+        const float f = a[r][col];
+        for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+      }
+  }
+  // T = inverse (master -> camera); keep rows 0..2, then store [R|t] and K separately (two-step like the reference)
+  float* o = proj + i * 24;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) o[r * 4 + c] = a[r][4 + c];
+  for (int k = 0; k < 9; ++k) o[12 + k] = intr[i * 9 + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Projection + bilinear sampling, emitted directly in the reference's reinterpreted order.
+//   xmap : (NV, D, 256) f32 channel-planar feature volume (input_proj + positional term)
+//   X    : merge-MLP input rows. For sample b with N views and row base R_b, row R_b + r (r < N*P) holds
+//          element (n, d, p) of the sampled tensor S[n,d,p] with n = r / P, d = (r / (P/D)) % D,
+//          p = (r % (P/D)) * D + d'   -- the raw `.view(1,-1,N,D)` of ptEmb_head.py:914-915.
+// grid = (D / CH, NV); block = 512 threads, each owning 8 of the 4096 points.
+// reference: generate_grid_sample_proj (collation.py:48-65), normalisation ptEmb_head.py:880-883,
+//            F.grid_sample(bilinear, zeros, align_corners=False) ptEmb_head.py:900-901
+// ------------------------------------------------------------------------------------------------
+constexpr int SAMPLE_CH = 32;
+constexpr int SAMPLE_THREADS = 512;
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ proj,
+                      const float* __restrict__ bps, const float* __restrict__ centre,
+                      const int* __restrict__ img_sample, const int* __restrict__ img_view,
+                      const int* __restrict__ sample_rowbase, __nv_bfloat16* __restrict__ X, int D, int P, int FH,
+                      int FW, float inv_w, float inv_h) {
+  extern __shared__ float planes[];  // [SAMPLE_CH][FH*FW]
+  const int img = blockIdx.y;
+  const int d0 = blockIdx.x * SAMPLE_CH;
+  const int F = FH * FW;
+  const int b = img_sample[img];
+  const int n = img_view[img];
+  for (int i = threadIdx.x; i < SAMPLE_CH * F; i += SAMPLE_THREADS)
+    planes[i] = xmap[((size_t)img * D + d0) * F + i];
+  const float* pm = proj + img * 24;
+  const float cx = centre[b * 3 + 0], cy = centre[b * 3 + 1], cz = centre[b * 3 + 2];
+  constexpr int PTS = 8;
+  int tap[PTS];       // top-left pixel index (may be out of range; validity folded into weights)
+  float w00[PTS], w01[PTS], w10[PTS], w11[PTS];
+  int o00[PTS], o01[PTS], o10[PTS], o11[PTS];
+#pragma unroll
+  for (int j = 0; j < PTS; ++j) {
+    const int p = threadIdx.x + j * SAMPLE_THREADS;
+    // world point (bps + centre), then master->camera, then intrinsics (same two-step order as the reference)
+    const float wx = bps[p * 3 + 0] + cx, wy = bps[p * 3 + 1] + cy, wz = bps[p * 3 + 2] + cz;
+    const float X0 = pm[0] * wx + pm[1] * wy + pm[2] * wz + pm[3];
+    const float Y0 = pm[4] * wx + pm[5] * wy + pm[6] * wz + pm[7];
+    const float Z0 = pm[8] * wx + pm[9] * wy + pm[10] * wz + pm[11];
+    const float qx = pm[12] * X0 + pm[13] * Y0 + pm[14] * Z0;
+    const float qy = pm[15] * X0 + pm[16] * Y0 + pm[17] * Z0;
+    float qz = pm[18] * X0 + pm[19] * Y0 + pm[20] * Z0;
+    if (fabsf(qz) < 1e-7f) qz = 1e-7f;
+    const float gx = (qx / qz) * inv_w * 2.f - 1.f;
+    const float gy = (qy / qz) * inv_h * 2.f - 1.f;
+    // align_corners=False unnormalisation
+    const float ix = ((gx + 1.f) * FW - 1.f) * 0.5f;
+    const float iy = ((gy + 1.f) * FH - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float ax = ix - fx0, ay = iy - fy0;
+    // clamp before the int conversion so far-away projections cannot overflow
+    const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)FW + 1.f);
+    const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)FH + 1.f);
+    const bool in_range = (fx0 >= -2.f) && (fx0 <= (float)FW + 1.f) && (fy0 >= -2.f) && (fy0 <= (float)FH + 1.f);
+    const bool vx0 = in_range && x0 >= 0 && x0 < FW, vx1 = in_range && x0 + 1 >= 0 && x0 + 1 < FW;
+    const bool vy0 = in_range && y0 >= 0 && y0 < FH, vy1 = in_range && y0 + 1 >= 0 && y0 + 1 < FH;
+    w00[j] = (vx0 && vy0) ? (1.f - ax) * (1.f - ay) : 0.f;
+    w01[j] = (vx1 && vy0) ? ax * (1.f - ay) : 0.f;
+    w10[j] = (vx0 && vy1) ? (1.f - ax) * ay : 0.f;
+    w11[j] = (vx1 && vy1) ? ax * ay : 0.f;
+    o00[j] = (vx0 && vy0) ? y0 * FW + x0 : 0;
+    o01[j] = (vx1 && vy0) ? y0 * FW + x0 + 1 : 0;
+    o10[j] = (vx0 && vy1) ? (y0 + 1) * FW + x0 : 0;
+    o11[j] = (vx1 && vy1) ? (y0 + 1) * FW + x0 + 1 : 0;
+    tap[j] = p;
+  }
+  __syncthreads();
+  const int chunks = P / D;  // rows per (view, channel)
+  const size_t row0 = (size_t)sample_rowbase[b] + (size_t)n * P;
+  for (int dd = 0; dd < SAMPLE_CH; ++dd) {
+    const float* pl = planes + dd * F;
+    const size_t rbase = row0 + (size_t)(d0 + dd) * chunks;
+#pragma unroll
+    for (int j = 0; j < PTS; ++j) {
+      const int p = tap[j];
+      // ATen accumulates the four taps in the order nw, ne, sw, se
+      float v = pl[o00[j]] * w00[j];
+      v += pl[o01[j]] * w01[j];
+      v += pl[o10[j]] * w10[j];
+      v += pl[o11[j]] * w11[j];
+      X[(rbase + p / D) * D + (p % D)] = __float2bfloat16(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-view reduce of the merge network (ptEmb_head.py:755-759):
+//   m (rows of D/2) for token p', views 0..N-1 at rows R_b + p'*N + n.
+//   N == 1 : s = m_0                                   (merge_features_sv feeds MLP1 directly)
+//   N  > 1 : w_n = <m_n, m_0>, s = sum_{n>=1} w_n m_n
+// one warp per token.
+// ------------------------------------------------------------------------------------------------
+__global__ void merge_reduce_kernel(const __nv_bfloat16* __restrict__ m, const int* __restrict__ sample_rowbase,
+                                    const int* __restrict__ sample_views, __nv_bfloat16* __restrict__ s, int H, int P,
+                                    int n_tokens) {
+  const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tok >= n_tokens) return;
+  const int b = tok / P, pp = tok - b * P;
+  const int N = sample_views[b];
+  const __nv_bfloat16* base = m + ((size_t)sample_rowbase[b] + (size_t)pp * N) * H;
+  const int per = H / 32;  // H in {64,128,256,512}: 2..16 values per lane
+  float m0[16], acc[16];
+  for (int i = 0; i < per; ++i) {
+    m0[i] = __bfloat162float(base[lane + 32 * i]);
+    acc[i] = (N == 1) ? m0[i] : 0.f;
+  }
+  for (int nn = 1; nn < N; ++nn) {
+    const __nv_bfloat16* r = base + (size_t)nn * H;
+    float mv[16];
+    float dot = 0.f;
+    for (int i = 0; i < per; ++i) {
+      mv[i] = __bfloat162float(r[lane + 32 * i]);
+      dot += mv[i] * m0[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int i = 0; i < per; ++i) acc[i] += dot * mv[i];
+  }
+  for (int i = 0; i < per; ++i) s[(size_t)tok * H + lane + 32 * i] = __float2bfloat16(acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps 1e-12, biased variance) — HF BertSelfOutput / BertOutput.
+// one warp per row; writes fp32 and bf16 copies.
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* __restrict__ y_f32,
+                                 __nv_bfloat16* __restrict__ y_bf16, int rows, int D, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * D;
+  float v[32];  // D <= 1024
+  const int per = D / 32;
+  float sum = 0.f;
+  for (int i = 0; i < per; ++i) {
+    v[i] = xr[lane + 32 * i];
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)D;
+  float var = 0.f;
+  for (int i = 0; i < per; ++i) {
+    const float d = v[i] - mean;
+    var += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)D + eps);
+  for (int i = 0; i < per; ++i) {
+    const int c = lane + 32 * i;
+    const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    if (y_f32) y_f32[(size_t)row * D + c] = o;
+    if (y_bf16) y_bf16[(size_t)row * D + c] = __float2bfloat16(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 32 nearest neighbours (squared L2, ascending, lower index wins ties) — pytorch3d `knn_points(K=32)`
+// as called at lib/models/bricks/point_transformers.py:83,134.  One warp per query; the warp keeps the
+// current best 32 sorted across its lanes and inserts candidates with ballot/shuffle.
+// Distances are (dx*dx + dy*dy) + dz*dz with separate fp32 roundings (no FMA contraction) so that the
+// neighbour sets are bit-identical to the fp32 oracle given identical coordinates.
+// ------------------------------------------------------------------------------------------------
+__global__ void knn32_kernel(const float* __restrict__ query, const float* __restrict__ ref, int* __restrict__ idx_out,
+                             int Lq, int Lr, int n_query_total) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (qi >= n_query_total) return;
+  const int b = qi / Lq;
+  const float qx = query[qi * 3 + 0], qy = query[qi * 3 + 1], qz = query[qi * 3 + 2];
+  const float* rb = ref + (size_t)b * Lr * 3;
+  float best_d = INFINITY;  // lane l holds the (l+1)-th smallest so far
+  int best_i = -1;
+  for (int base = 0; base < Lr; base += 32) {
+    const int c = base + lane;
+    float d = INFINITY;
+    if (c < Lr) {
+      const float dx = __fsub_rn(qx, rb[c * 3 + 0]);
+      const float dy = __fsub_rn(qy, rb[c * 3 + 1]);
+      const float dz = __fsub_rn(qz, rb[c * 3 + 2]);
+      d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    }
+    float thr = __shfl_sync(0xffffffffu, best_d, 31);
+    unsigned cand = __ballot_sync(0xffffffffu, d < thr);
+    while (cand) {
+      const int src = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float cd = __shfl_sync(0xffffffffu, d, src);
+      if (cd < thr) {  // warp-uniform
+        // stable position: after every element <= cd (earlier index wins ties)
+        const unsigned le = __ballot_sync(0xffffffffu, best_d <= cd);
+        const int pos = __popc(le);
+        const float up_d = __shfl_up_sync(0xffffffffu, best_d, 1);
+        const int up_i = __shfl_up_sync(0xffffffffu, best_i, 1);
+        if (lane > pos) {
+          best_d = up_d;
+          best_i = up_i;
+        } else if (lane == pos) {
+          best_d = cd;
+          best_i = base + src;
+        }
+        thr = __shfl_sync(0xffffffffu, best_d, 31);
+      }
+    }
+  }
+  idx_out[(size_t)qi * 32 + lane] = best_i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vector attention (Point-Transformer layer) glue, un-fused variant (token tensors in HBM):
+//   tokens t = (b, i, j), j < 32 neighbours.  reference: point_transformers.py:86-95,139-151
+// ------------------------------------------------------------------------------------------------
+// h_delta[t, c] = relu(Wd1[c,:] · (xyz_i - nbr_xyz_j) + bd1[c])
+__global__ void va_hdelta_kernel(const float* __restrict__ q_xyz, const float* __restrict__ ref_xyz,
+                                 const int* __restrict__ idx, const float* __restrict__ anchor_xyz,
+                                 const float* __restrict__ wd1, const float* __restrict__ bd1,
+                                 __nv_bfloat16* __restrict__ hdelta, int Lq, int Lr, int D, size_t n_tokens) {
+  const size_t t = blockIdx.x;  // one block per token group of 8
+  const int sub = threadIdx.x / (blockDim.x / 8);
+  const int tl = threadIdx.x % (blockDim.x / 8);
+  const size_t tok = t * 8 + sub;
+  if (tok >= n_tokens) return;
+  const size_t qi = tok >> 5;
+  const int j = (int)(tok & 31);
+  const int b = (int)(qi / Lq);
+  float nx, ny, nz;
+  if (anchor_xyz != nullptr) {
+    nx = anchor_xyz[j * 3 + 0], ny = anchor_xyz[j * 3 + 1], nz = anchor_xyz[j * 3 + 2];
+  } else {
+    const int r = idx[tok];
+    const float* rp = ref_xyz + ((size_t)b * Lr + r) * 3;
+    nx = rp[0], ny = rp[1], nz = rp[2];
+  }
+  const float rx = q_xyz[qi * 3 + 0] - nx, ry = q_xyz[qi * 3 + 1] - ny, rz = q_xyz[qi * 3 + 2] - nz;
+  for (int c = tl; c < D; c += blockDim.x / 8) {
+    float v = wd1[c * 3 + 0] * rx;
+    v += wd1[c * 3 + 1] * ry;
+    v += wd1[c * 3 + 2] * rz;
+    v += bd1[c];
+    hdelta[tok * D + c] = __float2bfloat16(fmaxf(v, 0.f));
+  }
+}
+
+// tmix[t, c] = q[i, c] - k[nbr_j, c] + pos[t, c]
+__global__ void va_tmix_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ ktab,
+                               int ldk, const int* __restrict__ idx, const int* __restrict__ anchor_idx,
+                               const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ tmix, int Lq, int Lr,
+                               int D, size_t n_tokens) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vec = D / 8;
+  const size_t tok = gid / vec;
+  const int c = (int)(gid % vec) * 8;
+  if (tok >= n_tokens) return;
+  const size_t qi = tok >> 5;
+  const int j = (int)(tok & 31);
+  const int b = (int)(qi / Lq);
+  const int r = (anchor_idx != nullptr) ? anchor_idx[j] : idx[tok];
+  const uint4 qv = *reinterpret_cast<const uint4*>(q + qi * ldq + c);
+  const uint4 kv = *reinterpret_cast<const uint4*>(ktab + ((size_t)b * Lr + r) * ldk + c);
+  const uint4 pv = *reinterpret_cast<const uint4*>(pos + tok * D + c);
+  const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+  const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
+  const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+  uint4 ov;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __bfloat1622float2(q2[i]), bb = __bfloat1622float2(k2[i]), cc = __bfloat1622float2(p2[i]);
+    o[i] = pack_bf16x2(a.x - bb.x + cc.x, a.y - bb.y + cc.y);
+  }
+  *reinterpret_cast<uint4*>(tmix + tok * D + c) = ov;
+}
+
+// res[i, c] = sum_j softmax_j(a[t, c] * inv_sqrt_d) * (v[nbr_j, c] + pos[t, c]);  one thread per (query, channel)
+__global__ void va_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ pos,
+                                 const __nv_bfloat16* __restrict__ vtab, int ldv, const int* __restrict__ idx,
+                                 const int* __restrict__ anchor_idx, __nv_bfloat16* __restrict__ res, int Lq, int Lr,
+                                 int D, float inv_sqrt_d, size_t n_query) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t qi = gid / D;
+  const int c = (int)(gid % D);
+  if (qi >= n_query) return;
+  const int b = (int)(qi / Lq);
+  float av[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    av[j] = __bfloat162float(a[(qi * 32 + j) * D + c]) * inv_sqrt_d;
+    mx = fmaxf(mx, av[j]);
+  }
+  float sum = 0.f, acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float e = __expf(av[j] - mx);
+    const int r = (anchor_idx != nullptr) ? anchor_idx[j] : idx[qi * 32 + j];
+    const float val = __bfloat162float(vtab[((size_t)b * Lr + r) * ldv + c]) + __bfloat162float(pos[(qi * 32 + j) * D + c]);
+    sum += e;
+    acc += e * val;
+  }
+  res[qi * D + c] = __float2bfloat16(acc / sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coordinate regression tail: xyz' = xyz + W2 · h + b2 (h = relu(W1 f + b1) from the GEMM), W2 is (3,D).
+// Also writes the de-normalised prediction  out = nan_to_num(xyz') * r + centre  (ptEmb_head.py:944-948).
+// one warp per query.
+// ------------------------------------------------------------------------------------------------
+__global__ void reg_out_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ w2,
+                               const float* __restrict__ b2, const float* __restrict__ xyz_in,
+                               float* __restrict__ xyz_out, float* __restrict__ coords_out,
+                               const float* __restrict__ centre, float radius, int Lq, int D, int n_query) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (qi >= n_query) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float hv = __bfloat162float(h[(size_t)qi * D + c]);
+    a0 += hv * w2[c];
+    a1 += hv * w2[D + c];
+    a2 += hv * w2[2 * D + c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane < 3) {
+    const float d = (lane == 0) ? a0 : (lane == 1) ? a1 : a2;
+    float v = xyz_in[qi * 3 + lane] + d + b2[lane];
+    xyz_out[qi * 3 + lane] = v;
+    if (centre == nullptr) {  // transformer-only call: raw normalised coordinates
+      coords_out[qi * 3 + lane] = v;
+    } else {
+      // torch.nan_to_num: nan -> 0, +-inf -> +-FLT_MAX
+      if (isnan(v)) v = 0.f;
+      else if (isinf(v)) v = (v > 0.f) ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+      const int b = qi / Lq;
+      coords_out[qi * 3 + lane] = v * radius + centre[b * 3 + lane];
+    }
+  }
+}
+
+// pt_xyz = ((bps + c) - c) / r  and  q_xyz = ((c + template) - c) / r  in the reference's rounding order
+// (ptEmb_head.py:808,896-897,933-934)
+__global__ void normalise_points_kernel(const float* __restrict__ bps, const float* __restrict__ templ,
+                                        const float* __restrict__ centre, float* __restrict__ pt_xyz,
+                                        float* __restrict__ q_xyz, int P, int Q, float radius, int B) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = (P + Q) * 3;
+  if (gid >= B * per) return;
+  const int b = gid / per, r = gid - b * per;
+  if (r < P * 3) {
+    const float c = centre[b * 3 + r % 3];
+    pt_xyz[(size_t)b * P * 3 + r] = __fdiv_rn(__fsub_rn(__fadd_rn(bps[r], c), c), radius);
+  } else {
+    const int k = r - P * 3;
+    const float c = centre[b * 3 + k % 3];
+    q_xyz[(size_t)b * Q * 3 + k] = __fdiv_rn(__fsub_rn(__fadd_rn(c, templ[k]), c), radius);
+  }
+}
+
+// centre[b] = reference_joints[b, centre_idx]
+__global__ void gather_centre_kernel(const float* __restrict__ ref_joints, float* __restrict__ centre, int centre_idx,
+                                     int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 3) centre[i] = ref_joints[(i / 3) * 63 + centre_idx * 3 + (i % 3)];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16(x[i]);
+}
+
+// broadcast the (Q,D) query embedding table to (B*Q, D) fp32 + bf16
+__global__ void broadcast_queries_kernel(const float* __restrict__ table, float* __restrict__ out_f32,
+                                         __nv_bfloat16* __restrict__ out_bf16, int QD, size_t total) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const float v = table[gid % QD];
+  out_f32[gid] = v;
+  out_bf16[gid] = __float2bfloat16(v);
+}
+
+}  // namespace poem

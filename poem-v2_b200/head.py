@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference plug-in interface for the decoder path.
+
+`POEM_Generalized_Head(cfg)` / `PtEmbedTRv4(cfg)` keep the reference's class names, `cfg` constructor,
+`forward()` signatures, return values, error behaviour and state-dict keys
+(reference lib/models/heads/ptEmb_head.py:683-964, lib/models/layers/ptEmb_transformer.py:303-376), so they can be
+registered under the same names in the reference registries (lib/utils/builder.py:252-304) — see INTEGRATION.md.
+All arithmetic happens in libpoem_b200.so; there is no PyTorch/CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+from . import synth
+from .config import HeadDims, dims_from_cfg
+from .pack import PackedWeights
+
+MAX_VIEWS = 10   # reference README: evaluated with 1..8 (up to 10 in the view sweep) cameras per sample
+
+
+class _Tree(nn.Module):
+    """Container whose children/parameters are created from dotted reference key names."""
+
+    def add(self, dotted, tensor):
+        head, _, rest = dotted.partition(".")
+        if not rest:
+            self.register_parameter(head, nn.Parameter(tensor, requires_grad=False))
+            return
+        if head not in self._modules:
+            self.add_module(head, _Tree())
+        self._modules[head].add(rest, tensor)
+
+
+def _resolve_template(dims, template):
+    if template is not None:
+        t = torch.as_tensor(template, dtype=torch.float32).reshape(dims.n_query, 3)
+        return t
+    try:  # the reference builds it from manotorch on every forward (ptEmb_head.py:886-894)
+        from manotorch.manolayer import ManoLayer  # type: ignore
+        layer = ManoLayer(joint_rot_mode="axisang", use_pca=False, mano_assets_root="assets/mano_v1_2",
+                          center_idx=dims.center_idx, flat_hand_mean=True)
+        out = layer(torch.zeros(1, 48), torch.zeros(1, 10))
+        return torch.cat([out.joints, out.verts], dim=1)[0].float()
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError("MANO template unavailable (manotorch / assets/mano_v1_2 missing): pass "
+                           "`template_mesh=(799,3)` to the head or call `set_template()`") from e
+
+
+class _NativeDecoder(nn.Module):
+    """Parameters under the reference's names + lazily packed kernel weights + workspace cache."""
+
+    def __init__(self, dims: HeadDims, key_prefix: str, template_mesh=None):
+        super().__init__()
+        self.dims = dims
+        self._key_prefix = key_prefix           # "" for the head, "transformer." stripped for PtEmbedTRv4
+        shapes = synth.live_param_shapes(dims)
+        self._live = []
+        for name, shape in shapes.items():
+            if not name.startswith(key_prefix):
+                continue
+            local = name[len(key_prefix):]
+            self._live.append(local)
+            self.add_param(local, torch.zeros(shape))
+        bps, a_xyz, a_idx = synth.load_assets()
+        self.register_buffer("bps_points", bps, persistent=False)
+        self.register_buffer("anchor_xyz", a_xyz, persistent=False)
+        self.register_buffer("anchor_idx", a_idx, persistent=False)
+        self._template = None if template_mesh is None else _resolve_template(dims, template_mesh)
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+
+    def add_param(self, dotted, tensor):
+        head, _, rest = dotted.partition(".")
+        if not rest:
+            self.register_parameter(head, nn.Parameter(tensor, requires_grad=False))
+            return
+        if head not in self._modules:
+            self.add_module(head, _Tree())
+        self._modules[head].add(rest, tensor)
+
+    # dead reference keys (BERT word tables, pooler, unused head layers) are accepted and ignored
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        live = {prefix + k for k in self._live}
+        for k in [k for k in state_dict if k.startswith(prefix) and k not in live]:
+            del state_dict[k]
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+
+    def set_template(self, template_mesh):
+        self._template = _resolve_template(self.dims, template_mesh)
+        self._packed = None
+
+    def live_state(self):
+        sd = self.state_dict()
+        return {self._key_prefix + k: sd[k] for k in self._live}
+
+    def packed(self, device):
+        params = [p for p in self.parameters()]
+        key = (str(device), tuple((p.data_ptr(), p._version) for p in params))
+        if self._packed is None or self._packed_key != key:
+            if self._template is None:
+                self._template = _resolve_template(self.dims, None)
+            full = {}
+            for name, shape in synth.live_param_shapes(self.dims).items():   # head-only keys absent for the TR class
+                full[name] = torch.zeros(shape)
+            full.update(self.live_state())
+            self._packed = PackedWeights(full, self.dims, device, self._template, self.bps_points, self.anchor_xyz,
+                                         self.anchor_idx, MAX_VIEWS)
+            self._packed_key = key
+        return self._packed
+
+    def workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != torch.device(device):
+            self._ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        off = (-self._ws.data_ptr()) % 1024
+        return self._ws.data_ptr() + off, self._ws.numel() - off
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise nat.PoemError(f"{what} must be a CUDA tensor: the decoder path has no CPU implementation")
+
+
+class POEM_Generalized_Head(_NativeDecoder):
+    """Drop-in for the reference head: `forward(mlvl_feat, img_metas, reference_joints, **kwargs)` ->
+    {"all_coords_preds": (NB,B,799,3) metres}."""
+
+    def __init__(self, cfg, template_mesh=None):
+        dims = cfg if isinstance(cfg, HeadDims) else dims_from_cfg(cfg)
+        super().__init__(dims, "", template_mesh)
+        self.num_preds = dims.n_blocks            # read by the model shell (reference POEM.py:115)
+        self.parametric_output = dims.parametric
+        if dims.parametric:
+            raise NotImplementedError("PARAMETRIC_OUTPUT (medium_MANO tail) is not built yet: needs the MANO layer")
+
+    @torch.no_grad()
+    def forward(self, mlvl_feat, img_metas, reference_joints, **kwargs):
+        d = self.dims
+        _require_cuda(mlvl_feat, "mlvl_feat")
+        dev = mlvl_feat.device
+        views = np.asarray(img_metas["cam_view_num"]).astype(np.int32).reshape(-1)
+        B = len(img_metas["master_id"])
+        assert int(np.sum(np.asarray(img_metas["master_id"]))) == 0, "only support master_id is 0"
+        assert len(views) == B and int(views.sum()) == mlvl_feat.shape[0]
+        assert mlvl_feat.shape[1] == d.in_channels and tuple(mlvl_feat.shape[-2:]) == (d.feat_hw, d.feat_hw)
+        inp_w, inp_h = img_metas["inp_img_shape"]   # the reference unpacks (H,W) as (w,h) (ptEmb_head.py:831)
+        img_metas["inp_res"] = torch.tensor([inp_w, inp_h], dtype=torch.float32, device=dev)
+        feat = mlvl_feat.contiguous().float()
+        intr = img_metas["cam_intr"].to(dev, torch.float32).contiguous()
+        extr = img_metas["cam_extr"].to(dev, torch.float32).contiguous()
+        refj = reference_joints.to(dev, torch.float32).contiguous()
+        assert refj.shape == (B, 21, 3)
+        lib = nat.load()
+        pw = self.packed(dev)
+        cd = nat.make_dims(d, MAX_VIEWS)
+        NV = int(feat.shape[0])
+        need = lib.poem_workspace_bytes(C.byref(cd), B, NV)
+        if need == 0:
+            raise nat.PoemError("unsupported dimensions: " + lib.poem_last_error().decode())
+        ws_ptr, ws_bytes = self.workspace(need, dev)
+        out = torch.empty(d.n_blocks, B, d.n_query, 3, dtype=torch.float32, device=dev)
+        inp = nat.PoemInputs(B, NV, views.ctypes.data, feat.data_ptr(), intr.data_ptr(), extr.data_ptr(),
+                             refj.data_ptr(), float(inp_w), float(inp_h))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nat.check(lib.poem_head_forward(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), None, ws_ptr,
+                                        ws_bytes, stream))
+        return {"all_coords_preds": out}
+
+    @torch.no_grad()
+    def forward_host(self, mlvl_feat, img_metas, reference_joints, out=None):
+        """Same path through `poem_head_forward_host`: HOST (pinned) inputs, HOST output; H2D/D2H inside the call."""
+        d = self.dims
+        dev = next(self.parameters()).device
+        views = np.asarray(img_metas["cam_view_num"]).astype(np.int32).reshape(-1)
+        B, NV = len(views), int(mlvl_feat.shape[0])
+        lib = nat.load()
+        pw = self.packed(dev)
+        cd = nat.make_dims(d, MAX_VIEWS)
+        need = lib.poem_workspace_bytes(C.byref(cd), B, NV) + lib.poem_staging_bytes(C.byref(cd), B, NV)
+        ws_ptr, ws_bytes = self.workspace(need, dev)
+        if out is None:
+            out = torch.empty(d.n_blocks, B, d.n_query, 3, dtype=torch.float32).pin_memory()
+        inp_w, inp_h = img_metas["inp_img_shape"]
+        for t in (mlvl_feat, img_metas["cam_intr"], img_metas["cam_extr"], reference_joints):
+            assert not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        inp = nat.PoemInputs(B, NV, views.ctypes.data, mlvl_feat.data_ptr(), img_metas["cam_intr"].data_ptr(),
+                             img_metas["cam_extr"].data_ptr(), reference_joints.data_ptr(), float(inp_w), float(inp_h))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nat.check(lib.poem_head_forward_host(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), ws_ptr,
+                                             ws_bytes, stream))
+        return out
+
+
+class PtEmbedTRv4(_NativeDecoder):
+    """Drop-in for the reference transformer: `forward(query_xyz, query_feat, pt_xyz, pt_feats)` ->
+    (xyz (NB,B,799,3) normalised, pred_pose None, pred_shape None)."""
+
+    def __init__(self, cfg):
+        if isinstance(cfg, HeadDims):
+            dims = cfg
+        else:
+            g = cfg.get if hasattr(cfg, "get") else (lambda k, dflt=None: getattr(cfg, k, dflt))
+            dims = HeadDims(embed_dims=int(g("INPUT_FEAT_DIM")), n_blocks=int(g("N_BLOCKS")),
+                            n_heads=int(g("NUM_ATTENTION_HEADS")), n_sample=int(g("BPS_FEAT_DIM")),
+                            n_neighbor=int(g("N_NEIGHBOR")), parametric=bool(g("PARAMETRIC_OUTPUT", False)),
+                            center_idx=int(g("TRANSFORMER_CENTER_IDX", 9)))
+        super().__init__(dims, "transformer.", template_mesh=torch.zeros(dims.n_query, 3))
+        self.name = type(self).__name__
+        if dims.parametric:
+            raise NotImplementedError("PARAMETRIC_OUTPUT is not built yet")
+
+    @torch.no_grad()
+    def forward(self, query_xyz, query_feat, pt_xyz, pt_feats):
+        d = self.dims
+        _require_cuda(query_feat, "query_feat")
+        dev = query_feat.device
+        B = query_feat.shape[0]
+        lib = nat.load()
+        pw = self.packed(dev)
+        cd = nat.make_dims(d, MAX_VIEWS)
+        need = lib.poem_transformer_workspace_bytes(C.byref(cd), B)
+        ws_ptr, ws_bytes = self.workspace(need, dev)
+        args = [t.to(dev, torch.float32).contiguous() for t in (query_xyz, query_feat.expand(B, -1, -1), pt_xyz, pt_feats)]
+        out = torch.empty(d.n_blocks, B, d.n_query, 3, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nat.check(lib.poem_transformer_forward(C.byref(cd), C.byref(pw.struct), B, args[0].data_ptr(),
+                                               args[1].data_ptr(), args[2].data_ptr(), args[3].data_ptr(),
+                                               out.data_ptr(), None, ws_ptr, ws_bytes, stream))
+        return out, None, None
+
+
+def register_into(head_registry=None, transformer_registry=None):
+    """Re-register the native classes under the reference's names (`force=True`, builder.py:237-239,252-304)."""
+    if head_registry is not None:
+        head_registry.register_module(name="POEM_Generalized_Head", force=True, module=POEM_Generalized_Head)
+    if transformer_registry is not None:
+        transformer_registry.register_module(name="PtEmbedTRv4", force=True, module=PtEmbedTRv4)

@@ -1,0 +1,62 @@
+"""Sample sharding across the GPUs of one box.
+
+Samples are independent units of the decoder path (all views of a sample stay together because the cross-view
+merge mixes them), so N ranks each run the whole path on a contiguous slice of the batch; there is no
+data-path collective.  The only optional exchange is an all_gather of the (NB, B/N, 799, 3) results.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(view_counts, world_size):
+    """Contiguous split of the samples into `world_size` slices, balanced by number of views (the unit of work
+    of the sampler / merge stage).  Returns [(s0, e0), ...] sample ranges; slices may be empty when B < world."""
+    v = np.asarray(view_counts, dtype=np.int64)
+    B = len(v)
+    cum = np.concatenate([[0], np.cumsum(v)])
+    total = cum[-1]
+    bounds, start = [], 0
+    for r in range(world_size):
+        if r == world_size - 1:
+            end = B
+        else:
+            target = total * (r + 1) / world_size
+            end = int(np.searchsorted(cum, target, side="left"))
+            end = min(max(end, start), B)
+            # choose the closer of end-1 / end to the target
+            if end > start and abs(cum[end - 1] - target) <= abs(cum[end] - target):
+                end -= 1
+            end = max(end, min(start + 1, B - (world_size - 1 - r)))  # leave at least one sample per later rank
+            end = min(end, B)
+        bounds.append((start, end))
+        start = end
+    return bounds
+
+
+def shard_inputs(mlvl_feat, img_metas, reference_joints, rank, world_size):
+    """Slice one rank's samples (and their images) out of a full batch."""
+    views = np.asarray(img_metas["cam_view_num"]).astype(np.int64)
+    s, e = shard_bounds(views, world_size)[rank]
+    img0, img1 = int(views[:s].sum()), int(views[:e].sum())
+    metas = dict(img_metas)
+    metas["cam_intr"] = img_metas["cam_intr"][img0:img1]
+    metas["cam_extr"] = img_metas["cam_extr"][img0:img1]
+    metas["cam_view_num"] = views[s:e]
+    metas["master_id"] = list(img_metas["master_id"][s:e])
+    return mlvl_feat[img0:img1], metas, reference_joints[s:e], (s, e)
+
+
+def gather_outputs(local_coords, batch_total, bounds, group=None):
+    """all_gather the per-rank (NB, b_r, Q, 3) predictions into (NB, B, Q, 3) on every rank."""
+    world = dist.get_world_size(group)
+    nb, _, q, _ = local_coords.shape
+    width = max(e - s for s, e in bounds)
+    pad = torch.zeros(nb, width, q, 3, dtype=local_coords.dtype, device=local_coords.device)
+    pad[:, :local_coords.shape[1]] = local_coords
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = torch.empty(nb, batch_total, q, 3, dtype=local_coords.dtype, device=local_coords.device)
+    for (s, e), part in zip(bounds, parts):
+        out[:, s:e] = part[:, :e - s]
+    return out

@@ -1,0 +1,205 @@
+"""CPU-side checks: C-ABI surface, weight packing/folding, module boundary, sharding (gloo, world_size 2)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import poem_oracle as orc
+from poem_v2_b200 import _native as nat
+from poem_v2_b200 import pack, shard, synth
+from poem_v2_b200.config import release_dims, dims_from_cfg
+from poem_v2_b200.head import POEM_Generalized_Head, PtEmbedTRv4
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    nat.build()
+    header = open(os.path.join(ROOT, "include", "poem_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(poem_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(nat.EXPORTS), declared ^ set(nat.EXPORTS)
+    lib = nat.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.poem_abi_version() == 1
+
+
+def test_workspace_query_and_dim_validation_need_no_gpu():
+    import ctypes as C
+    lib = nat.load()
+    d = nat.make_dims(release_dims("medium"))
+    n = lib.poem_workspace_bytes(C.byref(d), 32, 256)
+    assert 2 << 30 < n < 16 << 30
+    assert lib.poem_transformer_workspace_bytes(C.byref(d), 32) < n
+    bad = nat.make_dims(release_dims("medium"))
+    bad.embed_dims = 200
+    assert lib.poem_workspace_bytes(C.byref(bad), 1, 1) == 0
+    assert b"embed_dims" in lib.poem_last_error()
+
+
+def test_sine_table_matches_oracle():
+    for n, f in [(1, 64), (3, 128), (8, 256)]:
+        a = pack.sine_pos_3d(n, 16, 16, f)
+        b = orc.sine_pos_3d(n, 16, 16, f)
+        assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_packed_folds_are_algebraically_exact():
+    """Folded projections (done in fp64) must equal the unfolded reference chain."""
+    dims = release_dims("small")
+    sd = synth.make_state_dict(dims, 3)
+    bps, a_xyz, a_idx = synth.load_assets()
+    pw = pack.PackedWeights(sd, dims, "cpu", synth.standin_template(), bps, a_xyz, a_idx, max_views=4)
+    by_ptr = {t.data_ptr(): t for t in pw._keep}
+    blk = pw.struct.blocks[1]
+    W = by_ptr[blk.pt_proj.w].float()
+    b = by_ptr[blk.pt_proj.b]
+    D = dims.embed_dims
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(50, D, generator=g)
+    p = "transformer.pt_metro_encoder.1."
+    ke = F.linear(x, sd[p + "embedding.weight"], sd[p + "embedding.bias"])
+    c = p + "encoder.vec_attn.query_cross_attn."
+    xc = F.linear(ke, sd[c + "fc1.weight"], sd[c + "fc1.bias"])
+    want = torch.cat([
+        F.linear(ke, sd[p + "encoder.attn.self.key.weight"], sd[p + "encoder.attn.self.key.bias"]),
+        F.linear(ke, sd[p + "encoder.cross_attn.self.key.weight"], sd[p + "encoder.cross_attn.self.key.bias"]),
+        F.linear(xc, sd[c + "w_ks.weight"]), F.linear(xc, sd[c + "w_vs.weight"]),
+        F.linear(ke, sd[p + "encoder.attn.self.value.weight"], sd[p + "encoder.attn.self.value.bias"]),
+        F.linear(ke, sd[p + "encoder.cross_attn.self.value.weight"], sd[p + "encoder.cross_attn.self.value.bias"]),
+    ], dim=1)
+    got = x @ W.t() + b
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()     # bf16 rounding of the folded matrix
+    s = p + "encoder.vec_attn.query_self_attn."
+    Wq = by_ptr[blk.self_qkv.w].float()
+    xs = F.linear(x, sd[s + "fc1.weight"], sd[s + "fc1.bias"])
+    want = torch.cat([F.linear(xs, sd[s + n + ".weight"]) for n in ("w_qs", "w_ks", "w_vs")], dim=1)
+    got = x @ Wq.t() + by_ptr[blk.self_qkv.b]
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+    # positional table rows: N=1 -> row 0, N=2 -> rows 1,2, N=3 -> rows 3..5
+    tab = by_ptr[pw.struct.pos_table]
+    assert tab.shape == (10, 256, D)
+    s3 = orc.sine_pos_3d(3, 16, 16, dims.pos_feats)
+    want3 = F.conv2d(s3, sd["adapt_pos3d.weight"], sd["adapt_pos3d.bias"])      # (3, D, 16, 16)
+    assert torch.allclose(tab[3:6], want3.flatten(2).transpose(1, 2), atol=1e-4)
+
+
+def _reference_like_state_dict(dims, seed):
+    sd = synth.make_state_dict(dims, seed)
+    # dead keys the reference checkpoint also carries: must be accepted by a strict load
+    sd["transformer.pt_metro_encoder.0.embeddings.word_embeddings.weight"] = torch.zeros(8, dims.embed_dims)
+    sd["transformer.pt_metro_encoder.2.pooler.dense.weight"] = torch.zeros(dims.embed_dims, dims.embed_dims)
+    sd["center_shift_layer.0.weight"] = torch.zeros(799, 799)
+    sd["reg_branches.1.2.bias"] = torch.zeros(3)
+    return sd
+
+
+def test_module_keeps_reference_state_dict_keys():
+    dims = release_dims("small")
+    head = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    assert head.num_preds == 3
+    sd = _reference_like_state_dict(dims, 1)
+    head.load_state_dict(sd, strict=True)
+    live = synth.live_param_shapes(dims)
+    own = head.state_dict()
+    assert set(own) == set(live)
+    for k in live:
+        assert torch.equal(own[k], sd[k])
+    # a missing LIVE key is still an error
+    bad = dict(sd)
+    del bad["input_proj.weight"]
+    with pytest.raises(RuntimeError):
+        POEM_Generalized_Head(dims, template_mesh=synth.standin_template()).load_state_dict(bad, strict=True)
+    # as a sub-module of a model shell the keys carry the 'ptEmb_head.' prefix (reference POEM.py:114)
+    shell = torch.nn.Module()
+    shell.ptEmb_head = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    shell.load_state_dict({"ptEmb_head." + k: v for k, v in sd.items()}, strict=True)
+    tr = PtEmbedTRv4(dims)
+    tr.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=True)
+
+
+def test_module_reads_reference_config_and_fails_loudly_without_gpu():
+    class Node(dict):
+        __getattr__ = dict.__getitem__
+    cfg = Node(TYPE="POEM_Generalized_Head", EMBED_DIMS=256, POINTS_FEAT_DIM=256, IN_CHANNELS=160, N_SAMPLE=4096,
+               NUM_QUERY=799, NUM_PREDS=3, RADIUS_SAMPLE=0.1, CAM_FEAT_MERGE="attn", QUERY_TYPE="KPT",
+               TRANSFORMER=Node(TYPE="PtEmbedTRv4", N_BLOCKS=3, INPUT_FEAT_DIM=256, NUM_ATTENTION_HEADS=4,
+                                DROPOUT=0.1, BPS_FEAT_DIM=4096, N_NEIGHBOR=32, N_NEIGHBOR_QUERY=32),
+               POSITIONAL_ENCODING=Node(TYPE="SinePositionalEncoding3D", NUM_FEATS=128, NORMALIZE=True))
+    assert dims_from_cfg(cfg) == release_dims("medium")
+    head = POEM_Generalized_Head(cfg, template_mesh=synth.standin_template())
+    feat, metas, ref_j = synth.make_inputs(head.dims, 1, [2], 1)
+    with pytest.raises(nat.PoemError, match="no CPU implementation"):
+        head(mlvl_feat=feat, img_metas=metas, reference_joints=ref_j)
+    cfg2 = Node(cfg)
+    cfg2["QUERY_TYPE"] = "POEM"
+    with pytest.raises(AssertionError):                 # reference asserts query_type == "KPT" (ptEmb_head.py:721)
+        POEM_Generalized_Head(cfg2)
+    with pytest.raises(RuntimeError, match="MANO template unavailable"):
+        POEM_Generalized_Head(cfg).packed("cpu")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/lib"), reason="reference tree not mounted")
+def test_registers_under_reference_names():
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import ref_shim; ref_shim.install()\n"
+        "import lib.models.layers.ptEmb_transformer, lib.models.heads.ptEmb_head\n"
+        "from lib.utils.builder import HEAD, TRANSFORMER, build_from_cfg\n"
+        "from poem_v2_b200 import head as h, synth\n"
+        "h.register_into(HEAD, TRANSFORMER)\n"
+        "import yaml; from lib.utils.config import CN\n"
+        "cfg = CN(yaml.safe_load(open('config/release/train_medium.yaml')))\n"
+        "m = build_from_cfg(cfg.MODEL.HEAD, HEAD, data_preset=cfg.DATA_PRESET)\n"
+        "assert type(m) is h.POEM_Generalized_Head and m.dims.embed_dims == 256 and m.num_preds == 3\n"
+        "t = build_from_cfg(cfg.MODEL.HEAD.TRANSFORMER, TRANSFORMER)\n"
+        "assert type(t) is h.PtEmbedTRv4\n"
+        "print('REGISTERED-OK')\n") % (ROOT, os.path.join(ROOT, "oracle"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "REGISTERED-OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_shard_bounds_cover_and_balance():
+    for views, world in [([8] * 32, 8), ([8] * 32, 2), ([1, 8, 2, 2, 7, 3], 2), ([4, 4, 4], 4), ([2] * 5, 4)]:
+        b = shard.shard_bounds(views, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == len(views)
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(e >= s for s, e in b)
+    assert shard.shard_bounds([8] * 32, 8) == [(4 * r, 4 * r + 4) for r in range(8)]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dims = release_dims("small")
+    views = [2, 1, 3, 2, 2]
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 3)
+    f, m, r, (s, e) = shard.shard_inputs(feat, metas, ref_j, rank, world)
+    assert f.shape[0] == int(np.sum(m["cam_view_num"])) and r.shape[0] == e - s == len(m["master_id"])
+    # stand-in for the per-rank decoder call: something that depends on every input of the slice
+    local = torch.stack([r[:, :1, :].expand(-1, 799, -1) + f.sum() * 0 + i for i in range(3)])
+    bounds = shard.shard_bounds(views, world)
+    full = shard.gather_outputs(local, len(views), bounds)
+    want = torch.stack([ref_j[:, :1, :].expand(-1, 799, -1) + i for i in range(3)])
+    q.put((rank, bool(torch.equal(full, want))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_gather_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

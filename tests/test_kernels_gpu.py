@@ -1,0 +1,223 @@
+"""Stage-level parity: every C-ABI building block against a plain PyTorch fp32 restatement of the same op.
+
+bf16 operands are generated as bf16 and up-cast for the fp32 reference, so the only differences are the
+accumulation order (fp32 in TMEM) and the bf16 rounding of outputs; tolerances are stated per test.
+"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import poem_oracle as orc  # noqa: E402
+from poem_v2_b200 import _native as nat  # noqa: E402
+from poem_v2_b200 import synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return nat.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes):
+    t = torch.empty(nbytes + 2048, dtype=torch.uint8, device="cuda")
+    off = (-t.data_ptr()) % 1024
+    return t, t.data_ptr() + off, nbytes + 1024
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,act,res", [
+    (128, 256, 256, 0, False),
+    (300, 256, 256, 1, True),
+    (1000, 64, 128, 0, False),
+    (4173, 768, 256, 2, False),
+    (513, 128, 160, 0, True),       # K not a multiple of 64 (input_proj: 160 channels)
+    (799 * 2, 1536, 256, 0, False),
+    (257, 512, 1024, 1, True),
+    (2048, 128, 64, 0, False),      # K = one block (merge net of POEM-small)
+    (20000, 256, 256, 1, False),    # more tiles than SMs: persistent loop + TMEM double buffering
+])
+def test_linear(lib, M, N, K, act, res):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g) if res else None
+    o32 = torch.full((M, N), float("nan"), device="cuda")
+    o16 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    nat.check(lib.poem_linear(_p(A), K, _p(W), K, _p(bias), M, N, K, act, _p(R), N, _p(o32), N, _p(o16), N, _stream()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    ref = torch.relu(ref) if act == 1 else torch.nn.functional.gelu(ref) if act == 2 else ref
+    if res:
+        ref = ref + R
+    assert torch.isfinite(o32).all()
+    assert (o32 - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert (o16.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_linear_rejects_bad_arguments(lib):
+    A = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    assert lib.poem_linear(_p(A), 64, _p(A), 64, None, 128, 100, 64, 0, None, 0, None, 0, _p(A), 100, _stream()) == -1
+    assert lib.poem_linear(None, 64, _p(A), 64, None, 128, 128, 64, 0, None, 0, None, 0, _p(A), 128, _stream()) == -2
+    assert b"null" in lib.poem_last_error()
+
+
+# ------------------------------------------------------------------------------------------ MHA
+@pytest.mark.parametrize("D,B,Lq,Lk", [(128, 2, 799, 512), (256, 2, 799, 4096), (512, 1, 799, 1024), (256, 3, 130, 256)])
+def test_mha(lib, D, B, Lq, Lk):
+    h = 4
+    hd = D // h
+    g = torch.Generator(device="cuda").manual_seed(D + Lk)
+    Q = torch.randn(B * Lq, D, device="cuda", generator=g).bfloat16()
+    K = torch.randn(B * Lk, D, device="cuda", generator=g).bfloat16()
+    V = torch.randn(B, Lk, D, device="cuda", generator=g).bfloat16()
+    Vt = V.transpose(1, 2).contiguous()                      # (B, D, Lk)
+    ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+    nat.check(lib.poem_mha(_p(Q), D, _p(K), D, _p(Vt), _p(ctx), D, B, Lq, Lk, D, h, _stream()))
+    torch.cuda.synchronize()
+    q = Q.float().view(B, Lq, h, hd).transpose(1, 2)
+    k = K.float().view(B, Lk, h, hd).transpose(1, 2)
+    v = V.float().view(B, Lk, h, hd).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(B * Lq, D)
+    # P is rounded to bf16 before P·V (rel 2^-9) and the output is bf16: tolerance 2e-2 of the output scale
+    assert (ctx.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert (ctx.float() - ref).abs().mean().item() <= 2e-3
+
+
+# ------------------------------------------------------------------------------------------ KNN
+@pytest.mark.parametrize("B,Lq,Lr", [(2, 799, 799), (2, 799, 4096), (1, 40, 33)])
+def test_knn32_bit_exact(lib, B, Lq, Lr):
+    g = torch.Generator().manual_seed(Lr)
+    ref = torch.randn(B, Lr, 3, generator=g)
+    ref[:, 5] = ref[:, 3]                                     # duplicates: ties must resolve to the lower index
+    ref[:, Lr - 1] = ref[:, 0]
+    qry = ref[:, :Lq].clone() if Lq <= Lr else torch.randn(B, Lq, 3, generator=g)
+    if Lr == 4096:
+        qry = torch.randn(B, Lq, 3, generator=g) * 0.5
+    idx = torch.full((B, Lq, 32), -7, dtype=torch.int32, device="cuda")
+    nat.check(lib.poem_knn32(_p(qry.cuda()), _p(ref.cuda()), _p(idx), B, Lq, Lr, _stream()))
+    torch.cuda.synchronize()
+    want = orc.knn(qry, ref, 32)
+    assert torch.equal(idx.cpu().long(), want)               # index work: bit-exact, order included
+
+
+# ------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("D,views", [(128, [2]), (256, [3, 1, 2]), (512, [1])])
+def test_project_sample(lib, D, views):
+    B, NV, P = len(views), sum(views), 4096
+    dims = synth.HeadDims(embed_dims=D)
+    _, metas, refj = synth.make_inputs(dims, B, views, seed=3)
+    # push one view far off so a good part of the points falls outside the image (zero padding path)
+    metas["cam_intr"][-1, 0, 2] += 120.0
+    g = torch.Generator().manual_seed(D)
+    xmap = torch.randn(NV, D, 16, 16, generator=g)
+    bps, _, _ = synth.load_assets()
+    centre = refj[:, 9].contiguous()
+    X = torch.zeros(NV * P, D, device="cuda", dtype=torch.bfloat16)
+    wst, wsp, wsb = _ws(1 << 20)
+    import numpy as np
+    vc = np.asarray(views, dtype=np.int32)
+    nat.check(lib.poem_project_sample(_p(xmap.cuda()), _p(metas["cam_intr"].cuda()), _p(metas["cam_extr"].cuda()),
+                                      _p(bps.cuda()), _p(centre.cuda()), vc.ctypes.data, B, NV, D, P, 16, 16, 256.0,
+                                      256.0, _p(X), wsp, wsb, _stream()))
+    torch.cuda.synchronize()
+    grid = orc.project_bps(bps[None] + centre[:, None], metas["cam_intr"], metas["cam_extr"], views,
+                           torch.tensor([256.0, 256.0]))
+    sampled = torch.nn.functional.grid_sample(xmap, grid, align_corners=False).squeeze(-1)   # (NV, D, P)
+    rows, s = [], 0
+    for n in views:
+        rows.append(sampled[s:s + n].contiguous().view(-1, D))     # the raw .view regroup, flattened to rows
+        s += n
+    ref = torch.cat(rows)
+    got = X.float().cpu()
+    # bf16 output rounding (rel 2^-9 of |x| <= ~5) plus fp32 projection differences through the bilinear weights
+    assert (got - ref).abs().max().item() <= 4e-2
+    assert (got - ref).abs().mean().item() <= 3e-3
+    assert (ref == 0).float().mean().item() > 0.01                 # the out-of-image path was exercised
+
+
+# ------------------------------------------------------------------------------------------ vector attention
+def _vecattn_weights(D, g):
+    sd = {}
+    for n, shape in [("fc_delta.0", (D, 3)), ("fc_delta.2", (D, D)), ("fc_gamma.0", (D, D)), ("fc_gamma.2", (D, D))]:
+        sd[n + ".weight"] = torch.randn(shape, generator=g) / math.sqrt(shape[1])
+        sd[n + ".bias"] = 0.1 * torch.randn(shape[0], generator=g)
+    return sd
+
+
+@pytest.mark.parametrize("D,B,Lq,Lr,anchors", [(128, 2, 799, 799, False), (256, 1, 799, 4096, False),
+                                               (256, 2, 799, 4096, True), (512, 1, 200, 300, False)])
+def test_vector_attention(lib, D, B, Lq, Lr, anchors):
+    g = torch.Generator().manual_seed(D + Lr)
+    sd = _vecattn_weights(D, g)
+    q = torch.randn(B * Lq, D, generator=g).bfloat16()
+    ktab = torch.randn(B * Lr, D, generator=g).bfloat16()
+    vtab = torch.randn(B * Lr, D, generator=g).bfloat16()
+    q_xyz = torch.randn(B, Lq, 3, generator=g) * 0.5
+    r_xyz = torch.randn(B, Lr, 3, generator=g) * 0.5
+    _, a_xyz, a_idx = synth.load_assets()
+    if anchors:
+        idx = a_idx[None, None].expand(B, Lq, -1)
+        nbr = a_xyz[None, None].expand(B, Lq, -1, -1)
+    else:
+        idx = orc.knn(q_xyz, r_xyz, 32)
+        nbr = orc.gather_rows(r_xyz, idx)
+    keep = []
+
+    def dev(t, dt):
+        t = t.to(dt).contiguous().cuda()
+        keep.append(t)
+        return t.data_ptr()
+    w = nat.PoemVecAttn(dev(sd["fc_delta.0.weight"], torch.float32), dev(sd["fc_delta.0.bias"], torch.float32),
+                        nat.PoemLinear(dev(sd["fc_delta.2.weight"], torch.bfloat16), dev(sd["fc_delta.2.bias"], torch.float32)),
+                        nat.PoemLinear(dev(sd["fc_gamma.0.weight"], torch.bfloat16), dev(sd["fc_gamma.0.bias"], torch.float32)),
+                        nat.PoemLinear(dev(sd["fc_gamma.2.weight"], torch.bfloat16), dev(sd["fc_gamma.2.bias"], torch.float32)),
+                        nat.PoemLinear(None, None))
+    res = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+    nb = lib.poem_vector_attention_workspace_bytes(B, Lq, D)
+    wst, wsp, wsb = _ws(nb)
+    idx32 = idx.to(torch.int32).contiguous().cuda()
+    nat.check(lib.poem_vector_attention(C.byref(w), _p(q.cuda()), D, _p(ktab.cuda()), D, _p(vtab.cuda()), D,
+                                        _p(q_xyz.cuda()), _p(r_xyz.cuda()), None if anchors else _p(idx32),
+                                        dev(a_idx, torch.int32) if anchors else None,
+                                        dev(a_xyz, torch.float32) if anchors else None, B, Lq, Lr, D, _p(res), wsp, wsb,
+                                        _stream()))
+    torch.cuda.synchronize()
+    # fp32 reference on the bf16-rounded tables / weights
+    sdr = {k: (v.bfloat16().float() if k.endswith("weight") and v.shape[1] != 3 else v) for k, v in sd.items()}
+    k_g = orc.gather_rows(ktab.float().view(B, Lr, D), idx)
+    v_g = orc.gather_rows(vtab.float().view(B, Lr, D), idx)
+    ref = orc._vector_attention_core(sdr, "", q.float().view(B, Lq, D), k_g, v_g, q_xyz[:, :, None] - nbr)
+    got = res.float().cpu().view(B, Lq, D)
+    # three chained bf16 GEMMs with bf16 intermediates: 3e-2 of the output scale (|res| ~ 1-3)
+    assert (got - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().mean().item() <= 5e-3
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,D", [(799, 128), (1000, 256), (33, 1024)])
+def test_layernorm(lib, rows, D):
+    g = torch.Generator(device="cuda").manual_seed(D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 1
+    gamma = torch.randn(D, device="cuda", generator=g)
+    beta = torch.randn(D, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    y16 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    nat.check(lib.poem_layernorm(_p(x), _p(gamma), _p(beta), _p(y), _p(y16), rows, D, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps=1e-12)
+    assert (y - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    assert (y16.float() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
