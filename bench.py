@@ -1,0 +1,320 @@
+"""bench.py — samples/sec of the point-embedded transformer decoder path (POEM_Generalized_Head.forward:
+mlvl_feat -> all_coords_preds) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload medium_v8_b32] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  N>1: launched by torchrun, one rank per
+GPU, samples sharded across ranks with no data-path collective (weak scaling: 32 samples per GPU).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT,):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {   # name -> (release size, views, samples per GPU)
+    "small_v4_b8": ("small", 4, 8),          # BASELINE.json configs[1] (bring-up)
+    "medium_v8_b32": ("medium", 8, 32),      # configs[2]: the configuration the target is quoted on
+    "large_v8_b8": ("large", 8, 8),          # configs[4] per-GPU slice (global 64 on 8 GPUs)
+}
+N_ROTATE = 4   # distinct input sets cycled through the timed loop (4 x 42 MB > L2 for medium_v8_b32)
+
+
+def analytic_roofline(D, V, C=160, F=256, P=4096, Q=799, K=32, NB=3):
+    """algorithmic FLOPs (2·MAC) and bytes per sample of the decoder path."""
+    head = 2 * C * D * F * V + 3 * D * D * F * V + 3 * D * D * P * V + 1.5 * D * D * P
+    block = 2 * (4 * D * D * Q + 4 * D * D * P + 4 * Q * P * D) + (10 * D * D * Q + (6 * D * D + 6 * D) * Q * K) \
+        + (4 * D * D * Q + 4 * D * D * P + (6 * D * D + 6 * D) * Q * K) + 2 * D * D * (Q + P) + 2 * (D * D + 3 * D) * Q \
+        + 16 * D * D * Q
+    flops = head + NB * block
+    a = 2
+    byts = (V * C * F * a + 100 * V + 252 + 12 * NB * Q) + 2 * V * D * F * a + (1 + NB) * P * D * a \
+        + NB * (8 * P * D * a + 4 * P * D * a + 12 * Q * D * a)
+    return flops, byts
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "MEASURED_PEAKS.json (hbm copy; bf16 sustained)"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_pass(size, V, B, steps, warmup):
+    """The reference's PyTorch CPU path for the same unit of work, via the oracle port (the reference is pure
+    Python needing /root/reference + a stub layer, which does not exist on the GPU box)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import poem_oracle as orc
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    dims = release_dims(size)
+    sd = synth.make_state_dict(dims, 0)
+    feat, metas, ref_j = synth.make_inputs(dims, B, V, 1)
+    bps, a_xyz, a_idx = synth.load_assets()
+    tmpl = synth.standin_template()
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.head_forward(sd, dims, feat, metas, ref_j, tmpl, bps, a_xyz, a_idx)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return B * len(times) / sum(times), sum(times) / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="medium_v8_b32", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    size, V, B = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"POEM-{size} decoder head, {V} views, batch {B} per GPU", "size": size, "views": V,
+              "batch_per_gpu": B, "global_batch": B * max(world, 1), "parallelism": f"sample-sharded x{max(world, 1)}",
+              "l2": f"{N_ROTATE} input sets rotated + per-step working set >> 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 1)
+        sb = max(1, args.cpu_sample_batch)
+        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+        sps, sec = cpu_reference_pass(size, V, sb, steps, warm)
+        sample = f"oracle port (fp32 torch CPU) of head.forward on {sb} samples x {V} views per step, {steps} steps"
+        line = {"impl": "reference", "metric": "samples/sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from poem_v2_b200 import _native as nat
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    from poem_v2_b200.head import POEM_Generalized_Head
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dims = release_dims(size)
+    lib = nat.load()
+    head = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    head.load_state_dict(synth.make_state_dict(dims, 0), strict=True)
+    head = head.to(dev).eval()
+
+    # synthetic inputs: N_ROTATE distinct sets per rank, resident in HBM (device arm) and in pinned host memory (e2e)
+    dev_sets, host_sets = [], []
+    for r in range(N_ROTATE):
+        feat, metas, ref_j = synth.make_inputs(dims, B, V, seed=1 + 17 * r + 1000 * rank)
+        hm = dict(metas)
+        hm["cam_intr"], hm["cam_extr"] = metas["cam_intr"].pin_memory(), metas["cam_extr"].pin_memory()
+        host_sets.append((feat.pin_memory(), hm, ref_j.pin_memory()))
+        dm = dict(metas)
+        dm["cam_intr"], dm["cam_extr"] = metas["cam_intr"].to(dev), metas["cam_extr"].to(dev)
+        dev_sets.append((feat.to(dev), dm, ref_j.to(dev)))
+    host_out = torch.empty(dims.n_blocks, B, dims.n_query, 3).pin_memory()
+
+    def step_device(i):
+        f, m, r = dev_sets[i % N_ROTATE]
+        return head(mlvl_feat=f, img_metas=m, reference_joints=r)["all_coords_preds"]
+
+    def step_host(i):
+        f, m, r = host_sets[i % N_ROTATE]
+        return head.forward_host(f, m, r, out=host_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_device(i)
+        step_host(i)
+    barrier()
+
+    # ---- (1) device-resident arm: inputs already in HBM, CUDA events on the launching stream
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.poem_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = step_device(i)
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    launches = lib.poem_kernel_launches() - launches0
+    clk = clocks.stop() if clocks else None
+    assert torch.isfinite(out).all()
+
+    # ---- (2) end to end through the C-ABI host entry point: pinned host inputs -> H2D -> path -> D2H result
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_host(i)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    h2d = sum(t.numel() * 4 for t in (host_sets[0][0], host_sets[0][1]["cam_intr"], host_sets[0][1]["cam_extr"], host_sets[0][2]))
+    d2h = host_out.numel() * 4
+
+    # ---- (3) per-kernel CUDA-event timing inside a timed step loop (same stream), for the roofline of the top kernel
+    lib.poem_profile_enable(1)
+    prof_steps = min(args.steps, 5)
+    for i in range(prof_steps):
+        step_device(i)
+    torch.cuda.synchronize()
+    prof = nat.profile_summary()
+    lib.poem_profile_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_gpus = max(world, 1)
+    total_samples = B * n_gpus * args.steps
+    value = total_samples / (ms_dev * 1e-3)
+    e2e_value = total_samples / (ms_e2e * 1e-3)
+    peaks = measured_peaks()
+    D = dims.embed_dims
+    flops_s, bytes_s = analytic_roofline(D, V)
+
+    # dominant kernel = the launch class with the largest share of the profiled step
+    by_kernel = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    top_name, top = by_kernel[0] if by_kernel else ("none", {"ms": 0.0, "n": 1})
+    T = B * dims.n_query * dims.n_neighbor
+    R = B * V * dims.n_sample
+    # algorithmic bytes / flops per launch for the launch classes that can dominate
+    per_launch = {
+        "gemm_bf16_tc_kernel:va_token": ("hbm", T * D * 2 * 2 + D * D * 2, 2.0 * T * D * D),
+        "gemm_bf16_tc_kernel:merge0a": ("hbm", R * D * 2 * 2 + D * D * 2, 2.0 * R * D * D),
+        "gemm_bf16_tc_kernel:merge0b": ("hbm", R * D * 2 + R * D + D * D, 1.0 * R * D * D),
+        "gemm_bf16_tc_kernel:pt_proj": ("hbm", B * 4096 * D * 2 * 7 + 6 * D * D * 2, 2.0 * B * 4096 * D * 6 * D),
+        "mha_fwd_tc_kernel": ("tensor", 0, 4.0 * B * dims.n_query * 4096 * D),
+        "va_fused_kernel": ("tensor", 0, 6.0 * T * D * D),
+    }
+    roofline = {"kernel": top_name, "share_of_step": top["ms"] / total_prof_ms, "launches_profiled": top["n"],
+                "avg_launch_ms": top["ms"] / max(top["n"], 1)}
+    key = top_name if top_name in per_launch else top_name.split(":")[0]
+    if key in per_launch:
+        bound, byts, flops = per_launch[key]
+        sec = roofline["avg_launch_ms"] * 1e-3
+        if bound == "hbm":
+            ach = byts / sec / 1e9
+            roofline.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": byts})
+        else:
+            ach = flops / sec / 1e12
+            roofline.update({"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": ach / peaks["bf16_tflops"], "algorithmic_flops_per_launch": flops})
+    else:
+        roofline.update({"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None})
+    roofline["traffic"] = None      # dram bytes per launch from the ncu --set full capture: see profiles/
+    roofline["peak_source"] = peaks["source"]
+    # whole-path roofline: the decoder is tensor-bound at stage-boundary traffic
+    t_tc = flops_s / (peaks["bf16_tflops"] * 1e12)
+    t_hbm = bytes_s / (peaks["hbm_gbs"] * 1e9)
+    per_gpu_sps = value / n_gpus
+    path = {"flops_per_sample": flops_s, "bytes_per_sample": bytes_s, "roofline_samples_per_s": 1.0 / max(t_tc, t_hbm),
+            "frac_of_path_roofline": per_gpu_sps * max(t_tc, t_hbm), "frac_of_hbm_only_bound": per_gpu_sps * t_hbm}
+
+    cpu = None
+    if not args.no_cpu_baseline and n_gpus == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sb = max(1, args.cpu_sample_batch)
+        sps, sec = cpu_reference_pass(size, V, sb, 3, 1)
+        cpu = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"oracle port (fp32 torch CPU) on {sb} samples x {V} views, 3 passes, {sec:.2f} s/pass"}
+
+    line = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "path_roofline": path,
+            "cpu_baseline": cpu,
+            "kernel_breakdown_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in by_kernel[:12]}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,12 @@ typedef struct PoemInputs {
 int poem_abi_version(void);
 const char* poem_last_error(void);
 
+/* Instrumentation (bench.py): number of kernels launched by this library so far; optional per-launch CUDA-event
+ * timing of every kernel on its launching stream, summarised as a JSON object keyed by "<kernel>:<stage>". */
+long long poem_kernel_launches(void);
+void poem_profile_enable(int on);
+size_t poem_profile_summary(char* buf, size_t cap);
+
 /* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
 size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);
 

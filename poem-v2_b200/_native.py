@@ -87,7 +87,8 @@ class PoemInputs(C.Structure):
 
 
 # every symbol include/poem_b200.h declares
-EXPORTS = ["poem_abi_version", "poem_last_error", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
+           "poem_profile_summary", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
@@ -111,6 +112,11 @@ def load():
     vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     lib.poem_abi_version.restype = i
     lib.poem_last_error.restype = C.c_char_p
+    lib.poem_kernel_launches.restype = C.c_longlong
+    lib.poem_profile_enable.argtypes = [i]
+    lib.poem_profile_enable.restype = None
+    lib.poem_profile_summary.restype = sz
+    lib.poem_profile_summary.argtypes = [C.c_char_p, sz]
     lib.poem_workspace_bytes.restype = sz
     lib.poem_workspace_bytes.argtypes = [C.POINTER(PoemDims), i, i]
     lib.poem_staging_bytes.restype = sz
@@ -143,6 +149,14 @@ def load():
     lib.poem_layernorm.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
     _lib = lib
     return lib
+
+
+def profile_summary():
+    """dict {"<kernel>:<stage>": {"ms": total, "n": launches}} of the launches since poem_profile_enable(1)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    n = load().poem_profile_summary(buf, len(buf))
+    return json.loads(buf.value.decode()) if n else {}
 
 
 def check(rc):

@@ -37,11 +37,84 @@ static int fail(int code, const char* fmt, ...) {
     int _r = (expr);          \
     if (_r != POEM_OK) return _r; \
   } while (0)
+
+// ---- launch accounting + optional per-launch CUDA-event timing (poem_profile_*) ----
+#include <atomic>
+#include <map>
+#include <string>
+struct ProfRec {
+  std::string tag;
+  cudaEvent_t a, b;
+};
+static std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static thread_local const char* g_tag = nullptr;   // stage label for the generic GEMM launches
+static thread_local cudaEvent_t g_prof_a = nullptr;
+static thread_local cudaStream_t g_prof_stream = nullptr;
+static void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventCreate(&g_prof_a);
+  cudaEventRecord(g_prof_a, st);
+  g_prof_stream = st;
+}
+static void prof_end(const char* name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on || g_prof_a == nullptr) return;
+  ProfRec r;
+  r.tag = g_tag ? (std::string(name) + ":" + g_tag) : std::string(name);
+  r.a = g_prof_a;
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, g_prof_stream);
+  g_prof.push_back(r);
+  g_prof_a = nullptr;
+}
+struct TagScope {
+  const char* prev;
+  explicit TagScope(const char* t) : prev(g_tag) { g_tag = t; }
+  ~TagScope() { g_tag = prev; }
+};
 #define LAUNCH_CHECK(name)                                                                       \
   do {                                                                                           \
     cudaError_t _e = cudaGetLastError();                                                         \
+    prof_end(name);                                                                              \
     if (_e != cudaSuccess) return fail(POEM_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
+
+extern "C" long long poem_kernel_launches(void) { return g_launches.load(); }
+extern "C" void poem_profile_enable(int on) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = (on != 0);
+}
+// JSON object {"<kernel>:<stage>": {"ms": total, "n": launches}, ...}; returns bytes written (0 if buf too small)
+extern "C" size_t poem_profile_summary(char* buf, size_t cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<double, int>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      agg[r.tag].first += ms;
+      agg[r.tag].second += 1;
+    }
+  }
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\"%s\": {\"ms\": %.6f, \"n\": %d}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  if (out.size() + 1 > cap) return 0;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return out.size();
+}
 
 extern "C" int poem_abi_version(void) { return POEM_ABI_VERSION; }
 extern "C" const char* poem_last_error(void) { return g_err; }
@@ -113,6 +186,7 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  prof_begin(st);
   gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(ta, tw, M, N, K, ep);
   LAUNCH_CHECK("gemm_bf16_tc_kernel");
   return POEM_OK;
@@ -177,6 +251,7 @@ static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   }
   dim3 grid((Lq + MHA_BQ - 1) / MHA_BQ, n_heads, B);
   const float scale_log2e = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+  prof_begin(st);
   mha_fwd_tc_kernel<HD><<<grid, MHA_THREADS, MhaCfg<HD>::kSmemBytes, st>>>(tq, tk, tv, ctx, ld_ctx, Lq, Lk,
                                                                            vt_batch_rows, q_col0, k_col0, vt_row0,
                                                                            scale_log2e);
@@ -221,6 +296,7 @@ static int launch_knn(const float* q, const float* r, int* idx, int B, int Lq, i
   const int total = B * Lq;
   const int threads = 256;
   const int blocks = (total * 32 + threads - 1) / threads;
+  prof_begin(st);
   knn32_kernel<<<blocks, threads, 0, st>>>(q, r, idx, Lq, Lr, total);
   LAUNCH_CHECK("knn32_kernel");
   return POEM_OK;
@@ -235,6 +311,7 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
                             int D, cudaStream_t st) {
   if (D % 32 || D > 1024) return fail(POEM_E_BADDIM, "layernorm: D=%d", D);
   const int threads = 256;
+  prof_begin(st);
   layernorm_kernel<<<(rows * 32 + threads - 1) / threads, threads, 0, st>>>(x, g, b, y32, y16, rows, D, 1e-12f);
   LAUNCH_CHECK("layernorm_kernel");
   return POEM_OK;
@@ -305,11 +382,13 @@ static int launch_project_sample(const float* xmap, const float* intr, const flo
                                  int fw, float img_w, float img_h, __nv_bfloat16* X, cudaStream_t st) {
   if (P != SAMPLE_THREADS * 8) return fail(POEM_E_BADDIM, "sampler is specialised for P=4096 (got %d)", P);
   if (D % SAMPLE_CH || P % D) return fail(POEM_E_BADDIM, "sampler: D=%d must divide P and be a multiple of 32", D);
+  prof_begin(st);
   camera_prep_kernel<<<(NV + 63) / 64, 64, 0, st>>>(intr, extr, proj, NV);
   LAUNCH_CHECK("camera_prep_kernel");
   const size_t smem = (size_t)SAMPLE_CH * fh * fw * sizeof(float);
   if (smem > 48 * 1024) return fail(POEM_E_BADDIM, "feature map %dx%d too large for the sampler", fh, fw);
   dim3 grid(D / SAMPLE_CH, NV);
+  prof_begin(st);
   project_sample_kernel<<<grid, SAMPLE_THREADS, smem, st>>>(xmap, proj, bps, centre, vt.img_sample, vt.img_view,
                                                            vt.sample_rowbase, X, D, P, fh, fw, 1.0f / img_w,
                                                            1.0f / img_h);
@@ -352,10 +431,12 @@ static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq,
   const size_t n_query = (size_t)B * Lq;
   const size_t T = n_query * 32;
   if (T > 0x7fffffffULL) return fail(POEM_E_BADDIM, "vector_attention: too many tokens");
+  prof_begin(st);
   va_hdelta_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(q_xyz, ref_xyz, idx, anchor_xyz, w->wd1, w->bd1, t0, Lq, Lr,
                                                           D, T);
   LAUNCH_CHECK("va_hdelta_kernel");
   auto lin = [&](const __nv_bfloat16* A, const PoemLinear& l, int act, __nv_bfloat16* out) {
+    TagScope ts("va_token");
     GemmEpilogue e = epi_default(D);
     e.bias = l.b;
     e.act = act;
@@ -366,6 +447,7 @@ static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq,
   POEM_TRY(lin(t0, w->delta2, ACT_NONE, t1));  // pos
   {
     const size_t total = T * (D / 8);
+    prof_begin(st);
     va_tmix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, ldq, ktab, ldk, idx, anchor_idx, t1, t0, Lq, Lr,
                                                                    D, T);
     LAUNCH_CHECK("va_tmix_kernel");
@@ -374,6 +456,7 @@ static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq,
   POEM_TRY(lin(t2, w->gamma2, ACT_NONE, t0));  // attention logits
   {
     const size_t total = n_query * D;
+    prof_begin(st);
     va_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t0, t1, vtab, ldv, idx, anchor_idx, res, Lq, Lr, D,
                                                                      1.0f / sqrtf((float)D), n_query);
     LAUNCH_CHECK("va_reduce_kernel");
@@ -515,8 +598,9 @@ extern "C" size_t poem_transformer_workspace_bytes(const PoemDims* dims, int bat
 
 static inline const __nv_bfloat16* W16(const PoemLinear& l) { return reinterpret_cast<const __nv_bfloat16*>(l.w); }
 
-static int linear(const __nv_bfloat16* A, int lda, const PoemLinear& l, int M, int N, int K, int act,
+static int linear(const char* tag, const __nv_bfloat16* A, int lda, const PoemLinear& l, int M, int N, int K, int act,
                   const float* res32, float* o32, __nv_bfloat16* o16, cudaStream_t st) {
+  TagScope ts(tag);
   if (!l.w) return fail(POEM_E_NULL, "weight pointer missing");
   GemmEpilogue e = epi_default(N);
   e.bias = l.b;
@@ -554,39 +638,41 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
       e.t_rows = P;
       e.t_group_stride = (long long)2 * D * P;
       e.out_t_bf16 = p.VT;
+      TagScope ts("pt_proj");
       POEM_TRY(launch_gemm(p.ptf, D, W16(k.pt_proj), D, BP, 6 * D, D, e, st));
     }
-    POEM_TRY(linear(p.qf16, D, k.embedding, BQ, D, D, ACT_NONE, nullptr, p.qe32, p.qe16, st));
+    POEM_TRY(linear("q_embed", p.qf16, D, k.embedding, BQ, D, D, ACT_NONE, nullptr, p.qe32, p.qe16, st));
     // MHA 1
-    POEM_TRY(linear(p.qe16, D, k.q1, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
+    POEM_TRY(linear("mha_q", p.qe16, D, k.q1, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
     POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 4 * D, 0, p.VT, 2 * D, 0, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
-    POEM_TRY(linear(p.ctx16, D, k.o1, BQ, D, D, ACT_NONE, p.qe32, p.tmp32, nullptr, st));
+    POEM_TRY(linear("mha_out", p.ctx16, D, k.o1, BQ, D, D, ACT_NONE, p.qe32, p.tmp32, nullptr, st));
     POEM_TRY(launch_layernorm(p.tmp32, k.ln1_g, k.ln1_b, p.a1_32, p.a1_16, BQ, D, st));
     // MHA 2
-    POEM_TRY(linear(p.a1_16, D, k.q2, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
+    POEM_TRY(linear("mha_q", p.a1_16, D, k.q2, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
     POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 4 * D, D, p.VT, 2 * D, D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
-    POEM_TRY(linear(p.ctx16, D, k.o2, BQ, D, D, ACT_NONE, p.a1_32, p.tmp32, nullptr, st));
+    POEM_TRY(linear("mha_out", p.ctx16, D, k.o2, BQ, D, D, ACT_NONE, p.a1_32, p.tmp32, nullptr, st));
     POEM_TRY(launch_layernorm(p.tmp32, k.ln2_g, k.ln2_b, p.a2_32, p.a2_16, BQ, D, st));
     // vector self-attention
-    POEM_TRY(linear(p.a2_16, D, k.self_qkv, BQ, 3 * D, D, ACT_NONE, nullptr, nullptr, p.qkv16, st));
+    POEM_TRY(linear("va_self_qkv", p.a2_16, D, k.self_qkv, BQ, 3 * D, D, ACT_NONE, nullptr, nullptr, p.qkv16, st));
     const bool anchors = (i == 0);
     if (!anchors) POEM_TRY(launch_knn(xyz_in, xyz_in, p.idx_self, B, Q, Q, st));
     POEM_TRY(launch_vector_attention(&k.self_attn, p.qkv16, 3 * D, p.qkv16 + D, 3 * D, p.qkv16 + 2 * D, 3 * D, xyz_in,
                                      xyz_in, anchors ? nullptr : p.idx_self, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, Q, D, p.res16, p.t0, p.t1, p.t2, st));
-    POEM_TRY(linear(p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
+    POEM_TRY(linear("va_fc2", p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
     // vector cross-attention (queries <- BPS tokens)
-    POEM_TRY(linear(p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
+    POEM_TRY(linear("va_cross_q", p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
     if (!anchors) POEM_TRY(launch_knn(xyz_in, p.pt_xyz, p.idx_cross, B, Q, P, st));
     POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 4 * D, p.KK + 3 * D, 4 * D, xyz_in,
                                      p.pt_xyz, anchors ? nullptr : p.idx_cross, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, P, D, p.res16, p.t0, p.t1, p.t2, st));
-    POEM_TRY(linear(p.res16, D, k.cross_attn.fc2, BQ, D, D, ACT_NONE, p.f1_32, p.f2_32, p.f2_16, st));
+    POEM_TRY(linear("va_fc2", p.res16, D, k.cross_attn.fc2, BQ, D, D, ACT_NONE, p.f1_32, p.f2_32, p.f2_16, st));
     // coordinate regression
-    POEM_TRY(linear(p.f2_16, D, k.reg1, BQ, D, D, ACT_RELU, nullptr, nullptr, p.r1_16, st));
+    POEM_TRY(linear("reg1", p.f2_16, D, k.reg1, BQ, D, D, ACT_RELU, nullptr, nullptr, p.r1_16, st));
     {
       if (!k.reg2_w || !k.reg2_b) return fail(POEM_E_NULL, "block %d: reg_branch.2 missing", i);
       const int threads = 256;
+      prof_begin(st);
       reg_out_kernel<<<((size_t)BQ * 32 + threads - 1) / threads, threads, 0, st>>>(
           p.r1_16, k.reg2_w, k.reg2_b, xyz_in, xyz_out, coords_out + (size_t)i * BQ * 3, centre, dims->radius, Q, D,
           BQ);
@@ -595,8 +681,8 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
     // feed-forward (its output only feeds the next block)
     const bool last = (i == NB - 1);
     if (!last || dims->run_last_ffn) {
-      POEM_TRY(linear(p.f2_16, D, k.ffn1, BQ, 4 * D, D, ACT_GELU, nullptr, nullptr, p.ffn16, st));
-      POEM_TRY(linear(p.ffn16, 4 * D, k.ffn2, BQ, D, 4 * D, ACT_NONE, p.f2_32, p.tmp32, nullptr, st));
+      POEM_TRY(linear("ffn1", p.f2_16, D, k.ffn1, BQ, 4 * D, D, ACT_GELU, nullptr, nullptr, p.ffn16, st));
+      POEM_TRY(linear("ffn2", p.ffn16, 4 * D, k.ffn2, BQ, D, 4 * D, ACT_NONE, p.f2_32, p.tmp32, nullptr, st));
       float* dst32 = (last && out_feats) ? out_feats : p.qf32;
       POEM_TRY(launch_layernorm(p.tmp32, k.ln3_g, k.ln3_b, dst32, p.qf16, BQ, D, st));
     }
@@ -623,8 +709,10 @@ extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights*
   CUDA_TRY(cudaMemcpyAsync(p.pt_xyz, pt_xyz, BP * 3 * 4, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(p.xyz, query_xyz, BQ * 3 * 4, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(p.qf32, query_feat, BQ * D * 4, cudaMemcpyDeviceToDevice, st));
+  prof_begin(st);
   f32_to_bf16_kernel<<<(unsigned)((BQ * D + 255) / 256), 256, 0, st>>>(query_feat, p.qf16, BQ * D);
   LAUNCH_CHECK("f32_to_bf16_kernel");
+  prof_begin(st);
   f32_to_bf16_kernel<<<(unsigned)((BP * D + 255) / 256), 256, 0, st>>>(pt_feats, p.ptf, BP * D);
   LAUNCH_CHECK("f32_to_bf16_kernel");
   return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, st);
@@ -662,6 +750,7 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
   // ---- a2: x = input_proj(feat) + positional term, written channel-planar (NV, D, 256) fp32
   {
     dim3 grid((F + 31) / 32, (C + 31) / 32, NV), block(32, 8);
+    prof_begin(st);
     nchw_to_rows_bf16_kernel<<<grid, block, 0, st>>>(in->mlvl_feat, h.featT, C, F);
     LAUNCH_CHECK("nchw_to_rows_bf16_kernel");
     GemmEpilogue e = epi_default(D);
@@ -674,13 +763,16 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
     e.t_rows = F;
     e.t_group_stride = (long long)D * F;
     e.out_t_f32 = h.xmap;
+    TagScope ts("input_proj");
     POEM_TRY(launch_gemm(h.featT, C, W16(w->input_proj), C, NV * F, D, C, e, st));
   }
   // ---- a3/a7: centre, normalised point sets
+  prof_begin(st);
   gather_centre_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(in->reference_joints, h.centre, dims->center_idx, B);
   LAUNCH_CHECK("gather_centre_kernel");
   {
     const int total = B * (P + Q) * 3;
+    prof_begin(st);
     normalise_points_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->bps, w->template_xyz, h.centre, p.pt_xyz, p.xyz, P,
                                                                 Q, dims->radius, B);
     LAUNCH_CHECK("normalise_points_kernel");
@@ -689,15 +781,16 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
   POEM_TRY(launch_project_sample(h.xmap, in->cam_intr, in->cam_extr, w->bps, h.centre, vt, h.proj, NV, D, P,
                                  dims->feat_h, dims->feat_w, in->inp_img_w, in->inp_img_h, h.X, st));
   // ---- a6: merge network
-  POEM_TRY(linear(h.X, D, w->merge0a, (int)R, D, D, ACT_RELU, nullptr, nullptr, h.H1, st));
-  POEM_TRY(linear(h.H1, D, w->merge0b, (int)R, H, D, ACT_NONE, nullptr, nullptr, h.Mm, st));
+  POEM_TRY(linear("merge0a", h.X, D, w->merge0a, (int)R, D, D, ACT_RELU, nullptr, nullptr, h.H1, st));
+  POEM_TRY(linear("merge0b", h.H1, D, w->merge0b, (int)R, H, D, ACT_NONE, nullptr, nullptr, h.Mm, st));
   {
     const int threads = 256;
+    prof_begin(st);
     merge_reduce_kernel<<<(unsigned)(((size_t)BP * 32 + threads - 1) / threads), threads, 0, st>>>(
         h.Mm, vt.sample_rowbase, vt.sample_views, h.S, H, P, BP);
     LAUNCH_CHECK("merge_reduce_kernel");
   }
-  POEM_TRY(linear(h.S, H, w->merge1a, BP, H, H, ACT_RELU, nullptr, nullptr, h.H2, st));
+  POEM_TRY(linear("merge1a", h.S, H, w->merge1a, BP, H, H, ACT_RELU, nullptr, nullptr, h.H2, st));
   {
     if (!w->merge1b.w) return fail(POEM_E_NULL, "merge_net_feature.1.2 missing");
     GemmEpilogue e = epi_default(D);
@@ -710,11 +803,13 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
     e.rows_per_group = P;
     e.out_bf16 = p.ptf;
     e.ld_bf16 = D;
+    TagScope ts("merge1b");
     POEM_TRY(launch_gemm(h.H2, H, W16(w->merge1b), H, BP, D, H, e, st));
   }
   // ---- a7: query features
   {
     const size_t total = (size_t)BQ * D;
+    prof_begin(st);
     broadcast_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w->query_embed, p.qf32, p.qf16, Q * D,
                                                                              total);
     LAUNCH_CHECK("broadcast_queries_kernel");

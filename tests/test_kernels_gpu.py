@@ -108,7 +108,8 @@ def test_knn32_bit_exact(lib, B, Lq, Lr):
     if Lr == 4096:
         qry = torch.randn(B, Lq, 3, generator=g) * 0.5
     idx = torch.full((B, Lq, 32), -7, dtype=torch.int32, device="cuda")
-    nat.check(lib.poem_knn32(_p(qry.cuda()), _p(ref.cuda()), _p(idx), B, Lq, Lr, _stream()))
+    qry_d, ref_d = qry.cuda(), ref.cuda()                    # keep the device copies alive across the call
+    nat.check(lib.poem_knn32(_p(qry_d), _p(ref_d), _p(idx), B, Lq, Lr, _stream()))
     torch.cuda.synchronize()
     want = orc.knn(qry, ref, 32)
     assert torch.equal(idx.cpu().long(), want)               # index work: bit-exact, order included
@@ -130,9 +131,9 @@ def test_project_sample(lib, D, views):
     wst, wsp, wsb = _ws(1 << 20)
     import numpy as np
     vc = np.asarray(views, dtype=np.int32)
-    nat.check(lib.poem_project_sample(_p(xmap.cuda()), _p(metas["cam_intr"].cuda()), _p(metas["cam_extr"].cuda()),
-                                      _p(bps.cuda()), _p(centre.cuda()), vc.ctypes.data, B, NV, D, P, 16, 16, 256.0,
-                                      256.0, _p(X), wsp, wsb, _stream()))
+    dv = [t.cuda() for t in (xmap, metas["cam_intr"], metas["cam_extr"], bps, centre)]   # kept alive
+    nat.check(lib.poem_project_sample(_p(dv[0]), _p(dv[1]), _p(dv[2]), _p(dv[3]), _p(dv[4]), vc.ctypes.data, B, NV, D,
+                                      P, 16, 16, 256.0, 256.0, _p(X), wsp, wsb, _stream()))
     torch.cuda.synchronize()
     grid = orc.project_bps(bps[None] + centre[:, None], metas["cam_intr"], metas["cam_extr"], views,
                            torch.tensor([256.0, 256.0]))
@@ -190,8 +191,9 @@ def test_vector_attention(lib, D, B, Lq, Lr, anchors):
     nb = lib.poem_vector_attention_workspace_bytes(B, Lq, D)
     wst, wsp, wsb = _ws(nb)
     idx32 = idx.to(torch.int32).contiguous().cuda()
-    nat.check(lib.poem_vector_attention(C.byref(w), _p(q.cuda()), D, _p(ktab.cuda()), D, _p(vtab.cuda()), D,
-                                        _p(q_xyz.cuda()), _p(r_xyz.cuda()), None if anchors else _p(idx32),
+    dv = [t.cuda() for t in (q, ktab, vtab, q_xyz, r_xyz)]          # kept alive across the call
+    nat.check(lib.poem_vector_attention(C.byref(w), _p(dv[0]), D, _p(dv[1]), D, _p(dv[2]), D,
+                                        _p(dv[3]), _p(dv[4]), None if anchors else _p(idx32),
                                         dev(a_idx, torch.int32) if anchors else None,
                                         dev(a_xyz, torch.float32) if anchors else None, B, Lq, Lr, D, _p(res), wsp, wsb,
                                         _stream()))
