@@ -126,6 +126,9 @@ const char* poem_last_error(void);
 long long poem_kernel_launches(void);
 void poem_profile_enable(int on);
 size_t poem_profile_summary(char* buf, size_t cap);
+/* Test hook: route poem_vector_attention through the un-fused composition (token tensors in HBM) so the fused
+ * kernel can be checked against it on the device.  Not used by the product path. */
+void poem_debug_force_unfused(int on);
 
 /* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
 size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);

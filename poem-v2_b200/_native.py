@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpoem_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["poem_b200.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "mha.cuh", "simt.cuh"]
+HEADERS = ["common.cuh", "gemm.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -88,7 +88,7 @@ class PoemInputs(C.Structure):
 
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
-           "poem_profile_summary", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+           "poem_profile_summary", "poem_debug_force_unfused", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
@@ -115,6 +115,8 @@ def load():
     lib.poem_kernel_launches.restype = C.c_longlong
     lib.poem_profile_enable.argtypes = [i]
     lib.poem_profile_enable.restype = None
+    lib.poem_debug_force_unfused.argtypes = [i]
+    lib.poem_debug_force_unfused.restype = None
     lib.poem_profile_summary.restype = sz
     lib.poem_profile_summary.argtypes = [C.c_char_p, sz]
     lib.poem_workspace_bytes.restype = sz

@@ -13,6 +13,7 @@
 #include "gemm.cuh"
 #include "mha.cuh"
 #include "simt.cuh"
+#include "vecattn.cuh"
 
 using namespace poem;
 
@@ -464,6 +465,31 @@ static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq,
   return POEM_OK;
 }
 
+// Fused kernel (vecattn.cuh): the three D x D GEMMs, both MLP epilogues, the neighbour gathers and the per-channel
+// softmax/reduction in one launch; nothing token-sized touches HBM.
+static bool g_force_unfused = false;
+extern "C" void poem_debug_force_unfused(int on) { g_force_unfused = (on != 0); }
+
+template <int D>
+static int launch_vecattn_fused(const PoemVecAttn* w, const VaParams& prm, cudaStream_t st) {
+  using Cfg = VaCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(va_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap t1, t2, t3;
+  POEM_TRY(make_tmap_bf16(&t1, w->delta2.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_bf16(&t2, w->gamma1.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_bf16(&t3, w->gamma2.w, D, D, D, 64, 128));
+  const int tiles = (prm.n_query + Cfg::QT - 1) / Cfg::QT;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  prof_begin(st);
+  va_fused_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t1, t2, t3, prm);
+  LAUNCH_CHECK("va_fused_kernel");
+  return POEM_OK;
+}
+
 static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* ktab,
                                    int ldk, const __nv_bfloat16* vtab, int ldv, const float* q_xyz,
                                    const float* ref_xyz, const int* idx, const int* anchor_idx,
@@ -472,6 +498,22 @@ static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q,
   if ((idx == nullptr) == (anchor_idx == nullptr)) return fail(POEM_E_NULL, "vector_attention: give idx XOR anchors");
   if (anchor_idx && !anchor_xyz) return fail(POEM_E_NULL, "vector_attention: anchor_xyz missing");
   if (D % 32) return fail(POEM_E_BADDIM, "vector_attention: D=%d", D);
+  if (!g_force_unfused && (D == 128 || D == 256 || D == 512)) {
+    if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->delta2.b || !w->gamma1.w || !w->gamma1.b || !w->gamma2.w ||
+        !w->gamma2.b)
+      return fail(POEM_E_NULL, "vector_attention: weight pointer missing");
+    VaParams prm;
+    prm.q = q, prm.ktab = ktab, prm.vtab = vtab;
+    prm.ldq = ldq, prm.ldk = ldk, prm.ldv = ldv;
+    prm.q_xyz = q_xyz, prm.ref_xyz = ref_xyz, prm.idx = idx, prm.anchor_idx = anchor_idx, prm.anchor_xyz = anchor_xyz;
+    prm.wd1 = w->wd1, prm.bd1 = w->bd1, prm.bd2 = w->delta2.b, prm.bg1 = w->gamma1.b, prm.bg2 = w->gamma2.b;
+    prm.res = res;
+    prm.Lq = Lq, prm.Lr = Lr, prm.n_query = B * Lq;
+    prm.softmax_scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+    if (D == 128) return launch_vecattn_fused<128>(w, prm, st);
+    if (D == 256) return launch_vecattn_fused<256>(w, prm, st);
+    return launch_vecattn_fused<512>(w, prm, st);
+  }
   return launch_vecattn(w, q, ldq, ktab, ldk, vtab, ldv, q_xyz, ref_xyz, idx, anchor_idx, anchor_xyz, B, Lq, Lr, D,
                         res, t0, t1, t2, st);
 }

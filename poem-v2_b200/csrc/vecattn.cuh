@@ -1,0 +1,327 @@
+// Fused Point-Transformer vector attention (reference lib/models/bricks/point_transformers.py:86-94, 139-150):
+//
+//   pos_ij = W_d2 relu(W_d1 (xyz_i - nbr_j) + b_d1) + b_d2
+//   a_ij   = W_g2 relu(W_g1 (q_i - k_j + pos_ij) + b_g1) + b_g2
+//   res_i  = sum_j softmax_j(a_ij / sqrt(D)) * (v_j + pos_ij)            (per channel, over the 32 neighbours)
+//
+// The reference materialises ~10 (B,799,32,D) fp32 tensors; here a tile of NT tokens (NT/32 queries x 32 neighbours)
+// goes through the three D x D GEMMs without leaving the SM:
+//   * the GEMMs are computed TRANSPOSED on the tensor cores: out[c, t] = sum_k W[c,k] act[t,k]  (tcgen05.mma, M = 128
+//     output channels per accumulator tile, N = NT tokens, K = D).  A = weights, streamed by TMA (SWIZZLE_128B,
+//     64-wide K blocks) through a ring of smem stages; B = activations, written by the epilogue warps straight into
+//     a SWIZZLE_128B K-major smem tile; accumulators live in TMEM.
+//   * with channels on the TMEM lanes, one thread owns one channel for all tokens of the tile, so the per-channel
+//     softmax over a query's 32 neighbours (32 consecutive TMEM columns) is thread-local register work — no
+//     shuffles, no smem round trip.
+//   * pos stays in TMEM (first MT*NT columns) until the final reduction; the gamma hidden layer / logits reuse the
+//     other MT*NT columns.
+// warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2.. = MT*4 "channel" warps.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace poem {
+
+template <int D>
+struct VaCfg {
+  static constexpr int MT = D / 128;                 // accumulator tiles along the channel (M) axis
+  static constexpr int KB = D / 64;                  // 64-wide K blocks
+  static constexpr int NT = (D <= 256) ? 128 : 64;   // tokens per tile (TMEM: 2 * MT * NT <= 512 columns)
+  static constexpr int QT = NT / 32;                 // queries per tile
+  static constexpr int EP = MT * 128;                // channel threads
+  static constexpr int THREADS = 64 + EP;
+  static constexpr int W_STAGES = 6;
+  static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] bf16
+  static constexpr int ACT_BYTES = NT * D * 2;       // KB blocks of [NT tokens x 64 k] bf16
+  static constexpr int TMEM_COLS = (2 * MT * NT <= 256) ? 256 : 512;
+  static constexpr int GROUPS = EP / NT;             // stage-A: thread groups per token
+  static constexpr int CPT = D / GROUPS;             // stage-A: channels per thread
+  // smem: act | weight ring | wd1 (float4 per channel) | token rows (int) | token rel xyz (float4) | barriers
+  static constexpr int OFF_W = ACT_BYTES;
+  static constexpr int OFF_WD1 = OFF_W + W_STAGES * W_TILE_BYTES;
+  static constexpr int OFF_ROWS = OFF_WD1 + D * 16;
+  static constexpr int OFF_REL = OFF_ROWS + NT * 4;
+  static constexpr int OFF_BARS = OFF_REL + NT * 16;
+  static constexpr int SMEM_BYTES = OFF_BARS + 256;
+};
+
+struct VaParams {
+  const __nv_bfloat16* q;      // [n_query, ldq]
+  const __nv_bfloat16* ktab;   // [B*Lr, ldk]
+  const __nv_bfloat16* vtab;   // [B*Lr, ldv]
+  int ldq, ldk, ldv;
+  const float* q_xyz;          // [n_query, 3]
+  const float* ref_xyz;        // [B*Lr, 3] (unused with anchors)
+  const int* idx;              // [n_query, 32] or nullptr
+  const int* anchor_idx;       // [32] or nullptr
+  const float* anchor_xyz;     // [32,3] or nullptr
+  const float* wd1;            // [D,3]
+  const float* bd1;            // [D]
+  const float* bd2;            // [D]
+  const float* bg1;            // [D]
+  const float* bg2;            // [D]
+  __nv_bfloat16* res;          // [n_query, D]
+  int Lq, Lr, n_query;
+  float softmax_scale_log2e;   // log2(e) / sqrt(D)
+};
+
+template <int D>
+__global__ void __launch_bounds__(VaCfg<D>::THREADS, 1)
+va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_constant__ CUtensorMap tmap_wg1,
+                const __grid_constant__ CUtensorMap tmap_wg2, VaParams p) {
+  using Cfg = VaCfg<D>;
+  constexpr int MT = Cfg::MT, KB = Cfg::KB, NT = Cfg::NT, QT = Cfg::QT, EP = Cfg::EP;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* s_act = smem;
+  uint8_t* s_w = smem + Cfg::OFF_W;
+  float4* s_wd1 = reinterpret_cast<float4*>(smem + Cfg::OFF_WD1);
+  int* s_rows = reinterpret_cast<int*>(smem + Cfg::OFF_ROWS);
+  float4* s_rel = reinterpret_cast<float4*>(smem + Cfg::OFF_REL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
+  uint64_t* w_full = bars;                        // [W_STAGES]
+  uint64_t* w_empty = bars + Cfg::W_STAGES;       // [W_STAGES]
+  uint64_t* act_full = bars + 2 * Cfg::W_STAGES;  // channel threads -> MMA: B operand ready (count EP)
+  uint64_t* acc_full = act_full + 1;              // MMA -> channel threads: accumulator ready (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.n_query + QT - 1) / QT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_wd2);
+    tma_prefetch_desc(&tmap_wg1);
+    tma_prefetch_desc(&tmap_wg2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::W_STAGES; ++s) {
+        mbar_init(&w_full[s], 1);
+        mbar_init(&w_empty[s], 1);
+      }
+      mbar_init(act_full, EP);
+      mbar_init(acc_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  // fc_delta.0 (3 -> D) as float4 (w0, w1, w2, b) per channel
+  for (int c = threadIdx.x; c < D; c += Cfg::THREADS)
+    s_wd1[c] = make_float4(p.wd1[c * 3 + 0], p.wd1[c * 3 + 1], p.wd1[c * 3 + 2], p.bd1[c]);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_pos = tmem_base;                 // MT tiles of NT columns
+  const uint32_t tmem_h = tmem_base + MT * NT;         // MT tiles of NT columns
+
+  if (warp == 0) {
+    // ===================== TMA weight producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int g = 0; g < 3; ++g) {
+          const CUtensorMap* tm = (g == 0) ? &tmap_wd2 : (g == 1) ? &tmap_wg1 : &tmap_wg2;
+          for (int kb = 0; kb < KB; ++kb)
+            for (int mt = 0; mt < MT; ++mt) {
+              mbar_wait(&w_empty[stage], phase ^ 1);
+              mbar_expect_tx(&w_full[stage], Cfg::W_TILE_BYTES);
+              tma_load_2d(s_w + stage * Cfg::W_TILE_BYTES, tm, &w_full[stage], kb * 64, mt * 128);
+              if (++stage == Cfg::W_STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t act_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int g = 0; g < 3; ++g) {
+          mbar_wait(act_full, act_phase);
+          act_phase ^= 1;
+          tc_fence_after_sync();
+          const uint32_t acc = (g == 0) ? tmem_pos : tmem_h;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t db = make_kmajor_desc<128>(smem_u32(s_act) + kb * (NT * 128));
+            for (int mt = 0; mt < MT; ++mt) {
+              mbar_wait(&w_full[stage], phase);
+              tc_fence_after_sync();
+              const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * NT, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              umma_commit(&w_empty[stage]);
+              if (++stage == Cfg::W_STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // ===================== channel warps =====================
+    const int et = threadIdx.x - 64;                 // 0 .. EP-1
+    const int quarter = warp & 3;
+    const int mt = (warp - 2) >> 2;
+    const int c = mt * 128 + quarter * 32 + lane;    // the channel this thread owns
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float bd2 = p.bd2[c], bg1 = p.bg1[c], bg2 = p.bg2[c];
+    // byte offset of (token row t, channel c) inside the activation tile: block c/64, 16-byte chunk (c%64)/8
+    const uint32_t act_blk = (uint32_t)(c >> 6) * (NT * 128);
+    const uint32_t act_chunk = (uint32_t)(c & 63) >> 3;
+    const uint32_t act_byte = (uint32_t)(c & 7) * 2;
+    uint32_t acc_phase = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int q_first = tile * QT;
+      // ---- tile metadata: gather row + relative position of every token
+      if (et < NT) {
+        const int qg = q_first + (et >> 5);
+        const int j = et & 31;
+        int row = 0;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (qg < p.n_query) {
+          const int b = qg / p.Lq;
+          float nx, ny, nz;
+          if (p.anchor_idx != nullptr) {
+            row = b * p.Lr + p.anchor_idx[j];
+            nx = p.anchor_xyz[j * 3 + 0], ny = p.anchor_xyz[j * 3 + 1], nz = p.anchor_xyz[j * 3 + 2];
+          } else {
+            row = b * p.Lr + p.idx[(size_t)qg * 32 + j];
+            const float* rp = p.ref_xyz + (size_t)row * 3;
+            nx = rp[0], ny = rp[1], nz = rp[2];
+          }
+          rx = p.q_xyz[(size_t)qg * 3 + 0] - nx;
+          ry = p.q_xyz[(size_t)qg * 3 + 1] - ny;
+          rz = p.q_xyz[(size_t)qg * 3 + 2] - nz;
+        }
+        s_rows[et] = row;
+        s_rel[et] = make_float4(rx, ry, rz, 0.f);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+
+      // ---- stage A: h_delta = relu(W_d1 rel + b_d1) -> activation tile (B operand of GEMM 1)
+      {
+        const int t = et % NT;
+        const int c_first = (et / NT) * Cfg::CPT;
+        const float4 rel = s_rel[t];
+#pragma unroll 4
+        for (int cc = 0; cc < Cfg::CPT; cc += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 w0 = s_wd1[c_first + cc + 2 * i];
+            const float4 w1 = s_wd1[c_first + cc + 2 * i + 1];
+            const float h0 = fmaxf(fmaf(w0.x, rel.x, fmaf(w0.y, rel.y, fmaf(w0.z, rel.z, w0.w))), 0.f);
+            const float h1 = fmaxf(fmaf(w1.x, rel.x, fmaf(w1.y, rel.y, fmaf(w1.z, rel.z, w1.w))), 0.f);
+            pk[i] = pack_bf16x2(h0, h1);
+          }
+          const int ch = c_first + cc;
+          uint8_t* dst = s_act + (ch >> 6) * (NT * 128) + sw128_offset(t, (ch & 63) >> 3);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(act_full);
+
+      // ---- epilogue 1: tmix = q_i - k_j + pos  -> activation tile (B operand of GEMM 2); pos stays in TMEM
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int qi = 0; qi < QT; ++qi) {
+        const int qg = q_first + qi;
+        uint32_t r[32];
+        tmem_ld32(tmem_pos + lane_off + mt * NT + qi * 32, r);
+        const float qv = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
+        float kv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) kv[j] = __bfloat162float(p.ktab[(size_t)s_rows[qi * 32 + j] * p.ldk + c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int t = qi * 32 + j;
+          const float v = qv - kv[j] + (__uint_as_float(r[j]) + bd2);
+          *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(act_full);
+
+      // ---- epilogue 2: relu(gamma1) -> activation tile (B operand of GEMM 3)
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int qi = 0; qi < QT; ++qi) {
+        uint32_t r[32];
+        tmem_ld32(tmem_h + lane_off + mt * NT + qi * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int t = qi * 32 + j;
+          const float v = fmaxf(__uint_as_float(r[j]) + bg1, 0.f);
+          *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(act_full);
+
+      // ---- epilogue 3: per-channel softmax over the 32 neighbours, weighted sum of (v + pos)
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int qi = 0; qi < QT; ++qi) {
+        const int qg = q_first + qi;
+        uint32_t a[32], ps[32];
+        tmem_ld32(tmem_h + lane_off + mt * NT + qi * 32, a);
+        tmem_ld32(tmem_pos + lane_off + mt * NT + qi * 32, ps);
+        float vv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vv[j] = __bfloat162float(p.vtab[(size_t)s_rows[qi * 32 + j] * p.ldv + c]);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(a[j]));
+        // softmax((a + b_g2) / sqrt(D)): the bias is constant over j and cancels
+        float sum = 0.f, acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = exp2f((__uint_as_float(a[j]) - mx) * p.softmax_scale_log2e);
+          sum += e;
+          acc = fmaf(e, vv[j] + (__uint_as_float(ps[j]) + bd2), acc);
+        }
+        if (qg < p.n_query) p.res[(size_t)qg * D + c] = __float2bfloat16(acc / sum);
+      }
+      (void)bg2;
+      tc_fence_before_sync();
+      // the next tile's metadata overwrite s_rows/s_rel: every channel thread must be done reading them
+      asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace poem

@@ -11,5 +11,5 @@ run linear 240 tests/test_kernels_gpu.py -k "linear"
 run ln_knn 200 tests/test_kernels_gpu.py -k "layernorm or knn"
 run sample 200 tests/test_kernels_gpu.py -k "project_sample"
 run mha 240 tests/test_kernels_gpu.py -k "mha"
-run vecattn 240 tests/test_kernels_gpu.py -k "vector_attention"
+run vecattn 300 tests/test_kernels_gpu.py -k "vector_attention"
 run parity 900 tests/test_parity_gpu.py

@@ -161,7 +161,17 @@ def _vecattn_weights(D, g):
 
 @pytest.mark.parametrize("D,B,Lq,Lr,anchors", [(128, 2, 799, 799, False), (256, 1, 799, 4096, False),
                                                (256, 2, 799, 4096, True), (512, 1, 200, 300, False)])
-def test_vector_attention(lib, D, B, Lq, Lr, anchors):
+@pytest.mark.parametrize("unfused", [False, True])
+def test_vector_attention(lib, D, B, Lq, Lr, anchors, unfused):
+    """Both the fused tcgen05 kernel (default) and the un-fused composition against the fp32 formula."""
+    lib.poem_debug_force_unfused(int(unfused))
+    try:
+        _check_vector_attention(lib, D, B, Lq, Lr, anchors)
+    finally:
+        lib.poem_debug_force_unfused(0)
+
+
+def _check_vector_attention(lib, D, B, Lq, Lr, anchors):
     g = torch.Generator().manual_seed(D + Lr)
     sd = _vecattn_weights(D, g)
     q = torch.randn(B * Lq, D, generator=g).bfloat16()
