@@ -46,6 +46,7 @@ struct GemmEpilogue {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_STAGE_LD = 36;   // floats per staging row (32 + 4 pad: conflict-free 128-bit accesses)
 
 template <int BN>
 struct GemmCfg {
@@ -53,7 +54,9 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kWBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * GEMM_STAGE_LD * 4;   // per-epilogue-warp transpose tile
+  static constexpr int kBiasBytes = 2 * BN * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -67,7 +70,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* s_stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kBiasBytes);
   uint64_t* full_bar = bars;                         // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;     // [2]
@@ -166,118 +171,161 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue warps (2..5) =====================
+    // TMEM hands each lane one accumulator ROW (32 columns at a time).  Row-major outputs are re-distributed
+    // through a per-warp smem staging tile so that 4 lanes cover 32 consecutive columns of one row (full 32-byte
+    // sectors, bias/residual as vector loads); transposed outputs keep the TMEM layout (lanes = consecutive rows =
+    // consecutive addresses).
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    const int ew = warp - 2;       // 0..3
+    float* stage = s_stage + ew * (32 * GEMM_STAGE_LD);
+    const int sr = lane >> 2;          // sub-row 0..7 in the row-major phase
+    const int cg = (lane & 3) * 8;     // first of this lane's 8 columns inside a 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * GEMM_BM;
       const int n0 = (tile % tiles_n) * BN;
-      const int m = m0 + quarter * 32 + lane;
-      const bool row_ok = m < M;
+      // bias of this tile's columns -> smem (double buffered by accumulator stage)
+      float* sb = s_bias + acc * BN;
+      for (int j = threadIdx.x - 64; j < BN; j += 128)
+        sb[j] = (ep.bias != nullptr && n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
 
-      // per-row epilogue state
-      const float* res_row_f32 = nullptr;
-      const __nv_bfloat16* res_row_bf16 = nullptr;
-      float row_scale = 1.0f;
-      if (row_ok) {
-        if (ep.res_mode == RES_F32) {
-          res_row_f32 = ep.res_f32 + (size_t)m * ep.res_ld;
-        } else if (ep.res_mode == RES_POSADD) {
-          res_row_f32 = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
-        } else if (ep.res_mode == RES_MERGE) {
-          const int g = m / ep.rows_per_group;
-          const int cnt = ep.row_cnt[g];
-          row_scale = 1.0f / (float)cnt;
-          res_row_bf16 = ep.res_bf16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+      // row-major phase: this lane handles rows rr[i] = quarter*32 + 8*i + sr, columns cg..cg+7 of every chunk
+      const float* resf[4];
+      const __nv_bfloat16* resb[4];
+      float rscale[4];
+      int mrow[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + quarter * 32 + 8 * i + sr;
+        mrow[i] = m;
+        resf[i] = nullptr;
+        resb[i] = nullptr;
+        rscale[i] = 1.0f;
+        if (m < M) {
+          if (ep.res_mode == RES_F32) {
+            resf[i] = ep.res_f32 + (size_t)m * ep.res_ld;
+          } else if (ep.res_mode == RES_POSADD) {
+            resf[i] = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
+          } else if (ep.res_mode == RES_MERGE) {
+            const int g = m / ep.rows_per_group;
+            const int cnt = ep.row_cnt[g];
+            rscale[i] = 1.0f / (float)cnt;
+            resb[i] = ep.res_bf16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+          }
         }
       }
+      // transposed phase: this lane handles row quarter*32 + lane
+      const int mt_row = m0 + quarter * 32 + lane;
       size_t t_base = 0;
-      if (ep.trans_from < N && row_ok) {
-        const int g = m / ep.t_rows;
-        t_base = (size_t)g * ep.t_group_stride + (size_t)(m - g * ep.t_rows);
+      if (ep.trans_from < N && mt_row < M) {
+        const int g = mt_row / ep.t_rows;
+        t_base = (size_t)g * ep.t_group_stride + (size_t)(mt_row - g * ep.t_rows);
       }
 
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n = n0 + c0;
+        if (n >= N) break;   // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
         tmem_ld_wait();
-        const int n = n0 + c0;
-        if (row_ok && n < N) {
-          float v[32];
+        if (n >= ep.trans_from) {
+          // ---------------- transposed store (lane = row) ----------------
+          if (mt_row < M) {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias != nullptr) {
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+            }
+            if (ep.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (n + j < N) ? __ldg(ep.bias + n + j) : 0.f;
-          }
-          if (ep.act == ACT_RELU) {
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (ep.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (ep.act == ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          }
-          const bool full = (n + 32 <= N);
-          if (res_row_f32 != nullptr) {
-            if (full) {
-              const float4* p = reinterpret_cast<const float4*>(res_row_f32 + n);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (ep.res_mode == RES_F32 || ep.res_mode == RES_POSADD) {
+              const float* rp = (ep.res_mode == RES_F32)
+                                    ? ep.res_f32 + (size_t)mt_row * ep.res_ld
+                                    : ep.res_f32 + ((size_t)ep.row_tab[mt_row >> 8] * 256 + (mt_row & 255)) * ep.res_ld;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg(p + j);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(rp + n) + j);
                 v[4 * j + 0] += t.x;
                 v[4 * j + 1] += t.y;
                 v[4 * j + 2] += t.z;
                 v[4 * j + 3] += t.w;
               }
-            } else {
-              for (int j = 0; j < 32 && n + j < N; ++j) v[j] += res_row_f32[n + j];
             }
-          } else if (res_row_bf16 != nullptr) {
-            for (int j = 0; j < 32; ++j)
-              if (n + j < N) v[j] = v[j] * row_scale + __bfloat162float(res_row_bf16[n + j]);
-          }
-          if (n >= ep.trans_from) {
-            // transposed store: consecutive lanes (rows) are contiguous in memory
             const int tc = n - ep.trans_from;
             if (ep.out_t_bf16 != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n + j < N) ep.out_t_bf16[t_base + (size_t)(tc + j) * ep.t_rows] = __float2bfloat16(v[j]);
+              for (int j = 0; j < 32; ++j) ep.out_t_bf16[t_base + (size_t)(tc + j) * ep.t_rows] = __float2bfloat16(v[j]);
             }
             if (ep.out_t_f32 != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n + j < N) ep.out_t_f32[t_base + (size_t)(tc + j) * ep.t_rows] = v[j];
+              for (int j = 0; j < 32; ++j) ep.out_t_f32[t_base + (size_t)(tc + j) * ep.t_rows] = v[j];
             }
-          } else {
-            if (ep.out_f32 != nullptr) {
-              float* o = ep.out_f32 + (size_t)m * ep.ld_f32 + n;
-              if (full) {
+          }
+        } else {
+          // ---------------- row-major store through the staging tile ----------------
+          __syncwarp();   // previous chunk's reads of the staging tile are done
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              } else {
-                for (int j = 0; j < 32 && n + j < N; ++j) o[j] = v[j];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stage + lane * GEMM_STAGE_LD + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + cg);
+          const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + cg + 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (mrow[i] >= M) continue;
+            const float* sp = stage + (8 * i + sr) * GEMM_STAGE_LD + cg;
+            const float4 x0 = *reinterpret_cast<const float4*>(sp);
+            const float4 x1 = *reinterpret_cast<const float4*>(sp + 4);
+            float v[8] = {x0.x + b0.x, x0.y + b0.y, x0.z + b0.z, x0.w + b0.w,
+                          x1.x + b1.x, x1.y + b1.y, x1.z + b1.z, x1.w + b1.w};
+            if (ep.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (ep.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            }
+            if (resf[i] != nullptr) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg));
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg + 4));
+              v[0] += t0.x, v[1] += t0.y, v[2] += t0.z, v[3] += t0.w;
+              v[4] += t1.x, v[5] += t1.y, v[6] += t1.z, v[7] += t1.w;
+            } else if (resb[i] != nullptr) {
+              const uint4 t = __ldg(reinterpret_cast<const uint4*>(resb[i] + n + cg));
+              const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(t2[j]);
+                v[2 * j] = v[2 * j] * rscale[i] + f.x;
+                v[2 * j + 1] = v[2 * j + 1] * rscale[i] + f.y;
               }
+            }
+            if (ep.out_f32 != nullptr) {
+              float4* o = reinterpret_cast<float4*>(ep.out_f32 + (size_t)mrow[i] * ep.ld_f32 + n + cg);
+              o[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
             if (ep.out_bf16 != nullptr) {
-              __nv_bfloat16* o = ep.out_bf16 + (size_t)m * ep.ld_bf16 + n;
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 pk;
-                  pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                  pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                  pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                  pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                  reinterpret_cast<uint4*>(o)[j] = pk;
-                }
-              } else {
-                for (int j = 0; j < 32 && n + j < N; ++j) o[j] = __float2bfloat16(v[j]);
-              }
+              uint4 pk;
+              pk.x = pack_bf16x2(v[0], v[1]);
+              pk.y = pack_bf16x2(v[2], v[3]);
+              pk.z = pack_bf16x2(v[4], v[5]);
+              pk.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(ep.out_bf16 + (size_t)mrow[i] * ep.ld_bf16 + n + cg) = pk;
             }
           }
         }

@@ -197,10 +197,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         for (int i = 0; i < 16; ++i) {
           const float p0 = exp2f(__uint_as_float(r[2 * i]) * scale_log2e - m_scaled);
           const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2e - m_scaled);
-          // accumulate the sum from the bf16-rounded values so numerator and denominator match
-          const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          l_blk += __bfloat162float(h.x) + __bfloat162float(h.y);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+          l_blk += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
         }
         uint8_t* tile = sP + (c0 >> 6) * (MHA_BQ * 128);
         const int chunk0 = (c0 & 63) >> 3;

@@ -15,7 +15,9 @@
 //     shuffles, no smem round trip.
 //   * pos stays in TMEM (first MT*NT columns) until the final reduction; the gamma hidden layer / logits reuse the
 //     other MT*NT columns.
-// warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2.. = MT*4 "channel" warps.
+// warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2.. = SETS*MT*4 "channel" warps
+// (two sets of channel warps share the TMEM lanes and split the tile's queries, doubling the warps that hide the
+// neighbour-gather latency).
 #pragma once
 #include <cuda.h>
 
@@ -29,7 +31,9 @@ struct VaCfg {
   static constexpr int KB = D / 64;                  // 64-wide K blocks
   static constexpr int NT = (D <= 256) ? 128 : 64;   // tokens per tile (TMEM: 2 * MT * NT <= 512 columns)
   static constexpr int QT = NT / 32;                 // queries per tile
-  static constexpr int EP = MT * 128;                // channel threads
+  static constexpr int SETS = (D <= 256) ? 2 : 1;    // channel-thread sets; each set owns QT/SETS queries of a tile
+  static constexpr int QPS = QT / SETS;              // queries per thread and tile (== 2 for every supported D)
+  static constexpr int EP = MT * 128 * SETS;         // channel threads
   static constexpr int THREADS = 64 + EP;
   static constexpr int W_STAGES = 6;
   static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] bf16
@@ -173,17 +177,34 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     }
   } else {
     // ===================== channel warps =====================
+    static_assert(Cfg::QPS == 2, "the epilogues are written for two queries per thread and tile");
     const int et = threadIdx.x - 64;                 // 0 .. EP-1
     const int quarter = warp & 3;
-    const int mt = (warp - 2) >> 2;
+    const int e2 = (warp - 2) % (MT * 4);
+    const int set = (warp - 2) / (MT * 4);
+    const int mt = e2 >> 2;
     const int c = mt * 128 + quarter * 32 + lane;    // the channel this thread owns
+    const int qi0 = set * Cfg::QPS;                  // first of this thread's two queries inside the tile
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const float bd2 = p.bd2[c], bg1 = p.bg1[c], bg2 = p.bg2[c];
+    const float bd2 = p.bd2[c], bg1 = p.bg1[c];
     // byte offset of (token row t, channel c) inside the activation tile: block c/64, 16-byte chunk (c%64)/8
     const uint32_t act_blk = (uint32_t)(c >> 6) * (NT * 128);
     const uint32_t act_chunk = (uint32_t)(c & 63) >> 3;
     const uint32_t act_byte = (uint32_t)(c & 7) * 2;
     uint32_t acc_phase = 0;
+
+    // 32 bf16 values of column c from the gather rows of one query, packed two per register
+    auto gather32 = [&](const __nv_bfloat16* tab, int ld, int qi, uint32_t(&out)[16]) {
+      const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tab) + c;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t lo = __ldg(t16 + (size_t)s_rows[qi * 32 + 2 * j] * ld);
+        const uint32_t hi = __ldg(t16 + (size_t)s_rows[qi * 32 + 2 * j + 1] * ld);
+        out[j] = lo | (hi << 16);
+      }
+    };
+    auto bf_lo = [](uint32_t x) { return __uint_as_float(x << 16); };
+    auto bf_hi = [](uint32_t x) { return __uint_as_float(x & 0xffff0000u); };
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int q_first = tile * QT;
@@ -237,25 +258,30 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(act_full);
 
-      // ---- epilogue 1: tmix = q_i - k_j + pos  -> activation tile (B operand of GEMM 2); pos stays in TMEM
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int qi = 0; qi < QT; ++qi) {
-        const int qg = q_first + qi;
-        uint32_t r[32];
-        tmem_ld32(tmem_pos + lane_off + mt * NT + qi * 32, r);
-        const float qv = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
-        float kv[32];
+      // ---- epilogue 1: tmix = q_i - k_j + pos  -> activation tile (B operand of GEMM 2); pos stays in TMEM.
+      //      The k gathers of the first query are issued before waiting for GEMM 1.
+      {
+        uint32_t kk[16];
+        gather32(p.ktab, p.ldk, qi0, kk);
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) kv[j] = __bfloat162float(p.ktab[(size_t)s_rows[qi * 32 + j] * p.ldk + c]);
-        tmem_ld_wait();
+        for (int u = 0; u < 2; ++u) {
+          const int qg = q_first + qi0 + u;
+          uint32_t r[32];
+          tmem_ld32(tmem_pos + lane_off + mt * NT + (qi0 + u) * 32, r);
+          if (u == 1) gather32(p.ktab, p.ldk, qi0 + 1, kk);
+          const float qv = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int t = qi * 32 + j;
-          const float v = qv - kv[j] + (__uint_as_float(r[j]) + bd2);
-          *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v);
+          for (int j = 0; j < 16; ++j) {
+            const int t = (qi0 + u) * 32 + 2 * j;
+            const float v0 = qv - bf_lo(kk[j]) + (__uint_as_float(r[2 * j]) + bd2);
+            const float v1 = qv - bf_hi(kk[j]) + (__uint_as_float(r[2 * j + 1]) + bd2);
+            *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
+            *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
+          }
         }
       }
       tc_fence_before_sync();
@@ -266,14 +292,14 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1;
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int qi = 0; qi < QT; ++qi) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
         uint32_t r[32];
-        tmem_ld32(tmem_h + lane_off + mt * NT + qi * 32, r);
+        tmem_ld32(tmem_h + lane_off + mt * NT + (qi0 + u) * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int t = qi * 32 + j;
+          const int t = (qi0 + u) * 32 + j;
           const float v = fmaxf(__uint_as_float(r[j]) + bg1, 0.f);
           *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v);
         }
@@ -282,34 +308,47 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(act_full);
 
-      // ---- epilogue 3: per-channel softmax over the 32 neighbours, weighted sum of (v + pos)
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int qi = 0; qi < QT; ++qi) {
-        const int qg = q_first + qi;
-        uint32_t a[32], ps[32];
-        tmem_ld32(tmem_h + lane_off + mt * NT + qi * 32, a);
-        tmem_ld32(tmem_pos + lane_off + mt * NT + qi * 32, ps);
-        float vv[32];
+      // ---- epilogue 3: per-channel softmax over the 32 neighbours, weighted sum of (v + pos).
+      //      softmax((a + b_g2) / sqrt(D)): the bias is constant over the neighbours and cancels.
+      {
+        uint32_t vv[16];
+        gather32(p.vtab, p.ldv, qi0, vv);
+        mbar_wait(acc_full, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) vv[j] = __bfloat162float(p.vtab[(size_t)s_rows[qi * 32 + j] * p.ldv + c]);
-        tmem_ld_wait();
-        float mx = -INFINITY;
+        for (int u = 0; u < 2; ++u) {
+          const int qg = q_first + qi0 + u;
+          uint32_t a[32];
+          tmem_ld32(tmem_h + lane_off + mt * NT + (qi0 + u) * 32, a);
+          if (u == 1) gather32(p.vtab, p.ldv, qi0 + 1, vv);
+          tmem_ld_wait();
+          float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(a[j]));
-        // softmax((a + b_g2) / sqrt(D)): the bias is constant over j and cancels
-        float sum = 0.f, acc = 0.f;
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(a[j]));
+          float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float e = exp2f((__uint_as_float(a[j]) - mx) * p.softmax_scale_log2e);
-          sum += e;
-          acc = fmaf(e, vv[j] + (__uint_as_float(ps[j]) + bd2), acc);
+          for (int j = 0; j < 32; ++j) {
+            const float e = exp2f((__uint_as_float(a[j]) - mx) * p.softmax_scale_log2e);
+            sum += e;
+            a[j] = __float_as_uint(e);
+          }
+          float acc = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t ps[16];
+            tmem_ld16(tmem_pos + lane_off + mt * NT + (qi0 + u) * 32 + h * 16, ps);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int jj = h * 8 + j;
+              acc = fmaf(__uint_as_float(a[2 * jj]), bf_lo(vv[jj]) + (__uint_as_float(ps[2 * j]) + bd2), acc);
+              acc = fmaf(__uint_as_float(a[2 * jj + 1]), bf_hi(vv[jj]) + (__uint_as_float(ps[2 * j + 1]) + bd2), acc);
+            }
+          }
+          if (qg < p.n_query) p.res[(size_t)qg * D + c] = __float2bfloat16(acc / sum);
         }
-        if (qg < p.n_query) p.res[(size_t)qg * D + c] = __float2bfloat16(acc / sum);
       }
-      (void)bg2;
       tc_fence_before_sync();
       // the next tile's metadata overwrite s_rows/s_rel: every channel thread must be done reading them
       asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");

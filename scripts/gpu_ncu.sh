@@ -1,0 +1,12 @@
+#!/bin/bash
+# ncu --set full captures of the hot kernels (one launch each), reports into gpurun_out/
+mkdir -p gpurun_out
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+cap() { # name regex skip
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/$1 $CMD > gpurun_out/ncu_$1.log 2>&1
+  echo "== ncu $1 exit $? =="; ls -la gpurun_out/$1.ncu-rep 2>/dev/null
+}
+cap va_fused va_fused 8
+cap mha mha_fwd 6
+cap gemm_merge0a gemm_bf16 1
+cap gemm_ptproj gemm_bf16 5
