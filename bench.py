@@ -310,7 +310,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "path_roofline": path,
             "cpu_baseline": cpu,
-            "kernel_breakdown_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in by_kernel[:12]}}
+            "kernel_breakdown_ms_per_step": {k: [round(v["ms"] / prof_steps, 4), v["n"] // prof_steps] for k, v in by_kernel}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -58,20 +58,25 @@ typedef struct PoemLinear {
   const float* b;
 } PoemLinear;
 
-/* Vector-attention (Point-Transformer) layer, reference lib/models/bricks/point_transformers.py:47-156. */
+/* Vector-attention (Point-Transformer) layer, reference lib/models/bricks/point_transformers.py:47-156.
+ * fc_gamma.0 is linear, so it is distributed over (q_i - k_j + pos_ij) at pack time:
+ *   fc_gamma.0(q_i - k_j + pos_ij) = gamma1_delta2 · h_ij + qt_i - kt_j,   h_ij = relu(fc_delta.0(xyz_i - nbr_j))
+ *   gamma1_delta2 = W_g1 · W_d2;   qt_i = W_g1 q_i + W_g1 b_d2 + b_g1;   kt_j = W_g1 k_j
+ * qt / kt are produced by the query / key projections (their weights are pre-multiplied by W_g1). */
 typedef struct PoemVecAttn {
-  const float* wd1;     /* fc_delta.0 weight fp32 [D,3] */
-  const float* bd1;     /* fc_delta.0 bias   fp32 [D]   */
-  PoemLinear delta2;    /* fc_delta.2 */
-  PoemLinear gamma1;    /* fc_gamma.0 */
-  PoemLinear gamma2;    /* fc_gamma.2 */
-  PoemLinear fc2;       /* fc2 */
+  const float* wd1;          /* fc_delta.0 weight fp32 [D,3] */
+  const float* bd1;          /* fc_delta.0 bias   fp32 [D]   */
+  PoemLinear delta2;         /* fc_delta.2 */
+  PoemLinear gamma1_delta2;  /* W_g1 · W_d2 (bias unused: folded into qt) */
+  PoemLinear gamma2;         /* fc_gamma.2 */
+  PoemLinear fc2;            /* fc2 */
 } PoemVecAttn;
 
 /* One point_METRO_block (pt_metro_transformer.py:94-200), weights folded at pack time:
- *   pt_proj : [6D, D]  rows = K1 | K2 | k'_cross | v'_cross | V1 | V2   each composed with `embedding`
- *             (and with query_cross_attn.fc1 for k', v'); bias folded likewise
- *   self_qkv: [3D, D]  rows = w_qs·fc1 | w_ks·fc1 | w_vs·fc1 of query_self_attn                         */
+ *   pt_proj : [6D, D]  rows = K1 | K2 | kt_cross | v_cross | V1 | V2   each composed with `embedding`
+ *             (and with query_cross_attn.fc1 for kt, v; kt additionally with fc_gamma.0); bias folded likewise
+ *   self_qkv: [3D, D]  rows = qt | kt | v of query_self_attn (w_qs·fc1, w_ks·fc1 pre-multiplied by fc_gamma.0)
+ *   cross_q : [D, D]   qt of query_cross_attn (fc_gamma.0 · w_qs, bias W_g1 b_d2 + b_g1)                  */
 typedef struct PoemBlock {
   PoemLinear embedding;     /* embedding (applied to the query stream) */
   PoemLinear pt_proj;
@@ -81,7 +86,7 @@ typedef struct PoemBlock {
   const float *ln2_g, *ln2_b;
   PoemLinear self_qkv;
   PoemVecAttn self_attn;
-  PoemLinear cross_q;       /* query_cross_attn.w_qs (no bias) */
+  PoemLinear cross_q;       /* qt projection of query_cross_attn */
   PoemVecAttn cross_attn;
   PoemLinear reg1;          /* reg_branch.0 */
   const float* reg2_w;      /* reg_branch.2 weight fp32 [3,D] */
@@ -183,7 +188,8 @@ int poem_project_sample(const float* xmap, const float* cam_intr, const float* c
                         size_t workspace_bytes, void* stream);
 
 /* Vector attention core: res[b,i,:] = sum_j softmax_j(gamma(q_i - k_j + pos_ij)/sqrt(D)) * (v_j + pos_ij),
- * pos_ij = delta(xyz_i - nbr_xyz_j).  q bf16 [B*Lq, ldq]; ktab/vtab bf16 [B*Lr, ldk/ldv]; idx int32 [B*Lq*32]
+ * pos_ij = delta(xyz_i - nbr_xyz_j), in the folded form documented at PoemVecAttn:
+ * q = qt bf16 [B*Lq, ldq]; ktab = kt, vtab = v bf16 [B*Lr, ldk/ldv]; idx int32 [B*Lq*32]
  * (or NULL with anchors: anchor_idx int32[32], anchor_xyz fp32[32,3]); res bf16 [B*Lq, D].
  * Replaces point_transformers.py:86-94 / 139-150. */
 int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, int ldq, const poem_bf16* ktab, int ldk,

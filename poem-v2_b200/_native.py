@@ -60,7 +60,7 @@ class PoemLinear(C.Structure):
 
 
 class PoemVecAttn(C.Structure):
-    _fields_ = [("wd1", C.c_void_p), ("bd1", C.c_void_p), ("delta2", PoemLinear), ("gamma1", PoemLinear),
+    _fields_ = [("wd1", C.c_void_p), ("bd1", C.c_void_p), ("delta2", PoemLinear), ("gamma1_delta2", PoemLinear),
                 ("gamma2", PoemLinear), ("fc2", PoemLinear)]
 
 

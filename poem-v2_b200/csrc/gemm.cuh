@@ -1,7 +1,7 @@
 // Persistent warp-specialised tcgen05 GEMM:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
 //   A, W : bf16, K-major (row-major with K contiguous), staged by TMA (SWIZZLE_128B, 64-element K blocks)
 //   accumulate fp32 in TMEM (two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue (one TMEM lane quarter each)
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two per TMEM lane quarter)
 // Every Linear / 1x1-conv of the decoder path runs through this kernel (reference call sites: cuBLAS GEMMs
 // behind nn.Linear / nn.Conv2d(k=1) in lib/models/heads/ptEmb_head.py:94,755,760 and
 // lib/models/bricks/pt_metro_transformer.py:180-181, point_transformers.py:86-95,139-151).
@@ -45,16 +45,17 @@ struct GemmEpilogue {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, interleaved over the 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGE_LD = 36;   // floats per staging row (32 + 4 pad: conflict-free 128-bit accesses)
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 4;
+  static constexpr int kStages = (BN == 256) ? 3 : 4;   // 227 KB smem: 3 x 48 KB stages + 36 KB epilogue staging
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kWBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStagingBytes = 4 * 32 * GEMM_STAGE_LD * 4;   // per-epilogue-warp transpose tile
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_STAGE_LD * 4;   // per-epilogue-warp transpose tile
   static constexpr int kBiasBytes = 2 * BN * 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -98,7 +99,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full[s], 1);
-        mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);  // one arrive per epilogue warp
       }
       fence_mbar_init();
     }
@@ -170,13 +171,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     // TMEM hands each lane one accumulator ROW (32 columns at a time).  Row-major outputs are re-distributed
     // through a per-warp smem staging tile so that 4 lanes cover 32 consecutive columns of one row (full 32-byte
     // sectors, bias/residual as vector loads); transposed outputs keep the TMEM layout (lanes = consecutive rows =
     // consecutive addresses).
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
-    const int ew = warp - 2;       // 0..3
+    const int ew = warp - 2;       // 0..7
+    const int chunk_par = ew >> 2; // this warp handles 32-column chunks with (chunk index & 1) == chunk_par
     float* stage = s_stage + ew * (32 * GEMM_STAGE_LD);
     const int sr = lane >> 2;          // sub-row 0..7 in the row-major phase
     const int cg = (lane & 3) * 8;     // first of this lane's 8 columns inside a 32-column chunk
@@ -187,9 +189,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int n0 = (tile % tiles_n) * BN;
       // bias of this tile's columns -> smem (double buffered by accumulator stage)
       float* sb = s_bias + acc * BN;
-      for (int j = threadIdx.x - 64; j < BN; j += 128)
+      for (int j = threadIdx.x - 64; j < BN; j += 32 * GEMM_EPI_WARPS)
         sb[j] = (ep.bias != nullptr && n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
 
@@ -227,7 +229,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
         const int n = n0 + c0;
         if (n >= N) break;   // warp-uniform
         uint32_t r[32];

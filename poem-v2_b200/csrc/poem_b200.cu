@@ -420,14 +420,14 @@ extern "C" size_t poem_vector_attention_workspace_bytes(int B, int Lq, int D) {
   return 3 * (((size_t)B * Lq * 32 * D * 2 + 1023) & ~size_t(1023)) + 4096;
 }
 
-// Un-fused composition: token tensors (B*Lq*32, D) live in HBM between the three D x D GEMMs.
-//   t0: h_delta -> tmix -> a ; t1: pos ; t2: relu(gamma1)
+// Un-fused composition of the same folded math: token tensors (B*Lq*32, D) live in HBM between the D x D GEMMs.
+//   t0: h -> logits ; t1: pos ; t2: gamma1_pre -> relu(gamma1_pre + qt_i - kt_j)
 static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* ktab, int ldk,
                           const __nv_bfloat16* vtab, int ldv, const float* q_xyz, const float* ref_xyz, const int* idx,
                           const int* anchor_idx, const float* anchor_xyz, int B, int Lq, int Lr, int D,
                           __nv_bfloat16* res, __nv_bfloat16* t0, __nv_bfloat16* t1, __nv_bfloat16* t2,
                           cudaStream_t st) {
-  if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->gamma1.w || !w->gamma2.w)
+  if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->gamma1_delta2.w || !w->gamma2.w)
     return fail(POEM_E_NULL, "vector_attention: weight pointer missing");
   const size_t n_query = (size_t)B * Lq;
   const size_t T = n_query * 32;
@@ -436,25 +436,23 @@ static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq,
   va_hdelta_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(q_xyz, ref_xyz, idx, anchor_xyz, w->wd1, w->bd1, t0, Lq, Lr,
                                                           D, T);
   LAUNCH_CHECK("va_hdelta_kernel");
-  auto lin = [&](const __nv_bfloat16* A, const PoemLinear& l, int act, __nv_bfloat16* out) {
+  auto lin = [&](const __nv_bfloat16* A, const PoemLinear& l, bool bias, __nv_bfloat16* out) {
     TagScope ts("va_token");
     GemmEpilogue e = epi_default(D);
-    e.bias = l.b;
-    e.act = act;
+    e.bias = bias ? l.b : nullptr;
     e.out_bf16 = out;
     e.ld_bf16 = D;
     return launch_gemm(A, D, reinterpret_cast<const __nv_bfloat16*>(l.w), D, (int)T, D, D, e, st);
   };
-  POEM_TRY(lin(t0, w->delta2, ACT_NONE, t1));  // pos
+  POEM_TRY(lin(t0, w->delta2, true, t1));          // pos
+  POEM_TRY(lin(t0, w->gamma1_delta2, false, t2));  // (W_g1 W_d2) h
   {
     const size_t total = T * (D / 8);
     prof_begin(st);
-    va_tmix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, ldq, ktab, ldk, idx, anchor_idx, t1, t0, Lq, Lr,
-                                                                   D, T);
-    LAUNCH_CHECK("va_tmix_kernel");
+    va_gmix_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, ldq, ktab, ldk, idx, anchor_idx, t2, Lq, Lr, D, T);
+    LAUNCH_CHECK("va_gmix_kernel");
   }
-  POEM_TRY(lin(t0, w->gamma1, ACT_RELU, t2));
-  POEM_TRY(lin(t2, w->gamma2, ACT_NONE, t0));  // attention logits
+  POEM_TRY(lin(t2, w->gamma2, true, t0));          // attention logits
   {
     const size_t total = n_query * D;
     prof_begin(st);
@@ -480,7 +478,7 @@ static int launch_vecattn_fused(const PoemVecAttn* w, const VaParams& prm, cudaS
   }
   CUtensorMap t1, t2, t3;
   POEM_TRY(make_tmap_bf16(&t1, w->delta2.w, D, D, D, 64, 128));
-  POEM_TRY(make_tmap_bf16(&t2, w->gamma1.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_bf16(&t2, w->gamma1_delta2.w, D, D, D, 64, 128));
   POEM_TRY(make_tmap_bf16(&t3, w->gamma2.w, D, D, D, 64, 128));
   const int tiles = (prm.n_query + Cfg::QT - 1) / Cfg::QT;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -499,14 +497,13 @@ static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q,
   if (anchor_idx && !anchor_xyz) return fail(POEM_E_NULL, "vector_attention: anchor_xyz missing");
   if (D % 32) return fail(POEM_E_BADDIM, "vector_attention: D=%d", D);
   if (!g_force_unfused && (D == 128 || D == 256 || D == 512)) {
-    if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->delta2.b || !w->gamma1.w || !w->gamma1.b || !w->gamma2.w ||
-        !w->gamma2.b)
+    if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->delta2.b || !w->gamma1_delta2.w || !w->gamma2.w)
       return fail(POEM_E_NULL, "vector_attention: weight pointer missing");
     VaParams prm;
     prm.q = q, prm.ktab = ktab, prm.vtab = vtab;
     prm.ldq = ldq, prm.ldk = ldk, prm.ldv = ldv;
     prm.q_xyz = q_xyz, prm.ref_xyz = ref_xyz, prm.idx = idx, prm.anchor_idx = anchor_idx, prm.anchor_xyz = anchor_xyz;
-    prm.wd1 = w->wd1, prm.bd1 = w->bd1, prm.bd2 = w->delta2.b, prm.bg1 = w->gamma1.b, prm.bg2 = w->gamma2.b;
+    prm.wd1 = w->wd1, prm.bd1 = w->bd1, prm.bd2 = w->delta2.b;
     prm.res = res;
     prm.Lq = Lq, prm.Lr = Lr, prm.n_query = B * Lq;
     prm.softmax_scale_log2e = 1.4426950408889634f / sqrtf((float)D);

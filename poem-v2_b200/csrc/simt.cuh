@@ -319,11 +319,10 @@ __global__ void va_hdelta_kernel(const float* __restrict__ q_xyz, const float* _
   }
 }
 
-// tmix[t, c] = q[i, c] - k[nbr_j, c] + pos[t, c]
-__global__ void va_tmix_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ ktab,
+// g[t, c] = relu(g[t, c] + qt[i, c] - kt[nbr_j, c])   (in place; g holds (W_g1 W_d2) h on entry)
+__global__ void va_gmix_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ ktab,
                                int ldk, const int* __restrict__ idx, const int* __restrict__ anchor_idx,
-                               const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ tmix, int Lq, int Lr,
-                               int D, size_t n_tokens) {
+                               __nv_bfloat16* __restrict__ g, int Lq, int Lr, int D, size_t n_tokens) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int vec = D / 8;
   const size_t tok = gid / vec;
@@ -335,18 +334,18 @@ __global__ void va_tmix_kernel(const __nv_bfloat16* __restrict__ q, int ldq, con
   const int r = (anchor_idx != nullptr) ? anchor_idx[j] : idx[tok];
   const uint4 qv = *reinterpret_cast<const uint4*>(q + qi * ldq + c);
   const uint4 kv = *reinterpret_cast<const uint4*>(ktab + ((size_t)b * Lr + r) * ldk + c);
-  const uint4 pv = *reinterpret_cast<const uint4*>(pos + tok * D + c);
+  const uint4 gv = *reinterpret_cast<const uint4*>(g + tok * D + c);
   const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
   const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
-  const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+  const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
   uint4 ov;
   uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 a = __bfloat1622float2(q2[i]), bb = __bfloat1622float2(k2[i]), cc = __bfloat1622float2(p2[i]);
-    o[i] = pack_bf16x2(a.x - bb.x + cc.x, a.y - bb.y + cc.y);
+    const float2 a = __bfloat1622float2(q2[i]), bb = __bfloat1622float2(k2[i]), cc = __bfloat1622float2(g2[i]);
+    o[i] = pack_bf16x2(fmaxf(cc.x + (a.x - bb.x), 0.f), fmaxf(cc.y + (a.y - bb.y), 0.f));
   }
-  *reinterpret_cast<uint4*>(tmix + tok * D + c) = ov;
+  *reinterpret_cast<uint4*>(g + tok * D + c) = ov;
 }
 
 // res[i, c] = sum_j softmax_j(a[t, c] * inv_sqrt_d) * (v[nbr_j, c] + pos[t, c]);  one thread per (query, channel)

@@ -4,6 +4,12 @@
 //   a_ij   = W_g2 relu(W_g1 (q_i - k_j + pos_ij) + b_g1) + b_g2
 //   res_i  = sum_j softmax_j(a_ij / sqrt(D)) * (v_j + pos_ij)            (per channel, over the 32 neighbours)
 //
+// Algebraic form used here (exact in real arithmetic, folds done at pack time in fp64):
+//   W_g1 (q_i - k_j + pos_ij) + b_g1 = (W_g1 W_d2) h_ij + qt_i - kt_j,   h_ij = relu(W_d1 (xyz_i - nbr_j) + b_d1),
+//   qt_i = W_g1 q_i + W_g1 b_d2 + b_g1 (per query),  kt_j = W_g1 k_j (per reference point)
+// so the gamma hidden layer and pos are BOTH plain GEMMs of h (no dependency between them) and the only per-token
+// tensors are h, relu(gamma1) and the logits.
+//
 // The reference materialises ~10 (B,799,32,D) fp32 tensors; here a tile of NT tokens (NT/32 queries x 32 neighbours)
 // goes through the three D x D GEMMs without leaving the SM:
 //   * the GEMMs are computed TRANSPOSED on the tensor cores: out[c, t] = sum_k W[c,k] act[t,k]  (tcgen05.mma, M = 128
@@ -51,8 +57,8 @@ struct VaCfg {
 };
 
 struct VaParams {
-  const __nv_bfloat16* q;      // [n_query, ldq]
-  const __nv_bfloat16* ktab;   // [B*Lr, ldk]
+  const __nv_bfloat16* q;      // [n_query, ldq]  qt_i (gamma1-folded query term)
+  const __nv_bfloat16* ktab;   // [B*Lr, ldk]     kt_j (gamma1-folded key term)
   const __nv_bfloat16* vtab;   // [B*Lr, ldv]
   int ldq, ldk, ldv;
   const float* q_xyz;          // [n_query, 3]
@@ -63,8 +69,6 @@ struct VaParams {
   const float* wd1;            // [D,3]
   const float* bd1;            // [D]
   const float* bd2;            // [D]
-  const float* bg1;            // [D]
-  const float* bg2;            // [D]
   __nv_bfloat16* res;          // [n_query, D]
   int Lq, Lr, n_query;
   float softmax_scale_log2e;   // log2(e) / sqrt(D)
@@ -72,7 +76,7 @@ struct VaParams {
 
 template <int D>
 __global__ void __launch_bounds__(VaCfg<D>::THREADS, 1)
-va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_constant__ CUtensorMap tmap_wg1,
+va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_constant__ CUtensorMap tmap_wg1,   // wg1 = W_g1 W_d2
                 const __grid_constant__ CUtensorMap tmap_wg2, VaParams p) {
   using Cfg = VaCfg<D>;
   constexpr int MT = Cfg::MT, KB = Cfg::KB, NT = Cfg::NT, QT = Cfg::QT, EP = Cfg::EP;
@@ -151,23 +155,27 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       uint32_t phase = 0;
       uint32_t act_phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int g = 0; g < 3; ++g) {
+        for (int round = 0; round < 2; ++round) {
           mbar_wait(act_full, act_phase);
           act_phase ^= 1;
           tc_fence_after_sync();
-          const uint32_t acc = (g == 0) ? tmem_pos : tmem_h;
-          for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t db = make_kmajor_desc<128>(smem_u32(s_act) + kb * (NT * 128));
-            for (int mt = 0; mt < MT; ++mt) {
-              mbar_wait(&w_full[stage], phase);
-              tc_fence_after_sync();
-              const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
+          // round 0: pos = W_d2 h  and  gamma1_pre = (W_g1 W_d2) h   (same B operand); round 1: logits = W_g2 relu(.)
+          const int g_first = (round == 0) ? 0 : 2, g_last = (round == 0) ? 1 : 2;
+          for (int g = g_first; g <= g_last; ++g) {
+            const uint32_t acc = (g == 0) ? tmem_pos : tmem_h;
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t db = make_kmajor_desc<128>(smem_u32(s_act) + kb * (NT * 128));
+              for (int mt = 0; mt < MT; ++mt) {
+                mbar_wait(&w_full[stage], phase);
+                tc_fence_after_sync();
+                const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * NT, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-              umma_commit(&w_empty[stage]);
-              if (++stage == Cfg::W_STAGES) {
-                stage = 0;
-                phase ^= 1;
+                for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * NT, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&w_empty[stage]);
+                if (++stage == Cfg::W_STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
           }
@@ -186,7 +194,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     const int c = mt * 128 + quarter * 32 + lane;    // the channel this thread owns
     const int qi0 = set * Cfg::QPS;                  // first of this thread's two queries inside the tile
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const float bd2 = p.bd2[c], bg1 = p.bg1[c];
+    const float bd2 = p.bd2[c];
     // byte offset of (token row t, channel c) inside the activation tile: block c/64, 16-byte chunk (c%64)/8
     const uint32_t act_blk = (uint32_t)(c >> 6) * (NT * 128);
     const uint32_t act_chunk = (uint32_t)(c & 63) >> 3;
@@ -234,7 +242,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
 
-      // ---- stage A: h_delta = relu(W_d1 rel + b_d1) -> activation tile (B operand of GEMM 1)
+      // ---- stage A: h = relu(W_d1 rel + b_d1) -> activation tile (B operand of the pos and gamma1 GEMMs)
       {
         const int t = et % NT;
         const int c_first = (et / NT) * Cfg::CPT;
@@ -258,8 +266,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(act_full);
 
-      // ---- epilogue 1: tmix = q_i - k_j + pos  -> activation tile (B operand of GEMM 2); pos stays in TMEM.
-      //      The k gathers of the first query are issued before waiting for GEMM 1.
+      // ---- epilogue 2: relu((W_g1 W_d2) h + qt_i - kt_j) -> activation tile (B operand of the logits GEMM).
+      //      The kt gathers of the first query are issued before waiting for the accumulators.
       {
         uint32_t kk[16];
         gather32(p.ktab, p.ldk, qi0, kk);
@@ -270,38 +278,18 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         for (int u = 0; u < 2; ++u) {
           const int qg = q_first + qi0 + u;
           uint32_t r[32];
-          tmem_ld32(tmem_pos + lane_off + mt * NT + (qi0 + u) * 32, r);
+          tmem_ld32(tmem_h + lane_off + mt * NT + (qi0 + u) * 32, r);
           if (u == 1) gather32(p.ktab, p.ldk, qi0 + 1, kk);
           const float qv = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int t = (qi0 + u) * 32 + 2 * j;
-            const float v0 = qv - bf_lo(kk[j]) + (__uint_as_float(r[2 * j]) + bd2);
-            const float v1 = qv - bf_hi(kk[j]) + (__uint_as_float(r[2 * j + 1]) + bd2);
+            const float v0 = fmaxf(__uint_as_float(r[2 * j]) + (qv - bf_lo(kk[j])), 0.f);
+            const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + (qv - bf_hi(kk[j])), 0.f);
             *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
             *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
           }
-        }
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(act_full);
-
-      // ---- epilogue 2: relu(gamma1) -> activation tile (B operand of GEMM 3)
-      mbar_wait(acc_full, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after_sync();
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        uint32_t r[32];
-        tmem_ld32(tmem_h + lane_off + mt * NT + (qi0 + u) * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int t = (qi0 + u) * 32 + j;
-          const float v = fmaxf(__uint_as_float(r[j]) + bg1, 0.f);
-          *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v);
         }
       }
       tc_fence_before_sync();

@@ -8,6 +8,8 @@ Host-side, one-off (re-run only when parameters change):
         per point instead of once per (query, neighbour) pair  (reference point_transformers.py:136-141,
         pt_metro_transformer.py:180-181)
       - query_self_attn.fc1 composed into w_qs / w_ks / w_vs (point_transformers.py:86-87)
+      - fc_gamma.0 distributed over (q - k + pos): W_g1 is composed into the q and k projections and with fc_delta.2
+        (point_transformers.py:90-91,144-147), so pos and the gamma hidden layer are independent GEMMs of the same input
   * positional table: adapt_pos3d(SinePositionalEncoding3D(N views)) + bias for N = 1..max_views — it depends
     only on the weights and the view count, not on the input (ptEmb_head.py:842-860,
     layers/petr_transformer.py:434-469)
@@ -102,7 +104,7 @@ class PackedWeights:
         dst.wd1 = self._f32(f64[p + "fc_delta.0.weight"])
         dst.bd1 = self._f32(f64[p + "fc_delta.0.bias"])
         dst.delta2 = self._linear(f64[p + "fc_delta.2.weight"], f64[p + "fc_delta.2.bias"])
-        dst.gamma1 = self._linear(f64[p + "fc_gamma.0.weight"], f64[p + "fc_gamma.0.bias"])
+        dst.gamma1_delta2 = self._linear(f64[p + "fc_gamma.0.weight"] @ f64[p + "fc_delta.2.weight"], None)
         dst.gamma2 = self._linear(f64[p + "fc_gamma.2.weight"], f64[p + "fc_gamma.2.bias"])
         dst.fc2 = self._linear(f64[p + "fc2.weight"], f64[p + "fc2.bias"])
 
@@ -115,10 +117,13 @@ class PackedWeights:
             return w @ We, w @ be + (b if b is not None else 0.0)
         c = e + "vec_attn.query_cross_attn."
         W1c, b1c = f64[c + "fc1.weight"], f64[c + "fc1.bias"]
+        # fc_gamma.0 distributed over (q - k + pos): kt = W_g1 k, qt = W_g1 q + W_g1 b_d2 + b_g1 (include/poem_b200.h)
+        Wg1c = f64[c + "fc_gamma.0.weight"]
+        qt_bias_c = Wg1c @ f64[c + "fc_delta.2.bias"] + f64[c + "fc_gamma.0.bias"]
         parts = [
             through_embedding(f64[e + "attn.self.key.weight"], f64[e + "attn.self.key.bias"]),
             through_embedding(f64[e + "cross_attn.self.key.weight"], f64[e + "cross_attn.self.key.bias"]),
-            through_embedding(f64[c + "w_ks.weight"] @ W1c, f64[c + "w_ks.weight"] @ b1c),
+            through_embedding(Wg1c @ f64[c + "w_ks.weight"] @ W1c, Wg1c @ f64[c + "w_ks.weight"] @ b1c),
             through_embedding(f64[c + "w_vs.weight"] @ W1c, f64[c + "w_vs.weight"] @ b1c),
             through_embedding(f64[e + "attn.self.value.weight"], f64[e + "attn.self.value.bias"]),
             through_embedding(f64[e + "cross_attn.self.value.weight"], f64[e + "cross_attn.self.value.bias"]),
@@ -134,11 +139,15 @@ class PackedWeights:
         blk.ln2_b = self._f32(f64[e + "cross_attn.output.LayerNorm.bias"])
         s = e + "vec_attn.query_self_attn."
         W1s, b1s = f64[s + "fc1.weight"], f64[s + "fc1.bias"]
-        qkv_w = torch.cat([f64[s + n + ".weight"] @ W1s for n in ("w_qs", "w_ks", "w_vs")])
-        qkv_b = torch.cat([f64[s + n + ".weight"] @ b1s for n in ("w_qs", "w_ks", "w_vs")])
+        Wg1s = f64[s + "fc_gamma.0.weight"]
+        qt_bias_s = Wg1s @ f64[s + "fc_delta.2.bias"] + f64[s + "fc_gamma.0.bias"]
+        pre = {"w_qs": Wg1s, "w_ks": Wg1s, "w_vs": torch.eye(Wg1s.shape[0], dtype=torch.float64)}
+        qkv_w = torch.cat([pre[n] @ f64[s + n + ".weight"] @ W1s for n in ("w_qs", "w_ks", "w_vs")])
+        qkv_b = torch.cat([pre[n] @ f64[s + n + ".weight"] @ b1s + (qt_bias_s if n == "w_qs" else 0.0)
+                           for n in ("w_qs", "w_ks", "w_vs")])
         blk.self_qkv = self._linear(qkv_w, qkv_b)
         self._vec_attn(blk.self_attn, f64, s)
-        blk.cross_q = self._linear(f64[c + "w_qs.weight"], None)
+        blk.cross_q = self._linear(Wg1c @ f64[c + "w_qs.weight"], qt_bias_c)
         self._vec_attn(blk.cross_attn, f64, c)
         blk.reg1 = self._linear(f64[e + "vec_attn.reg_branch.0.weight"], f64[e + "vec_attn.reg_branch.0.bias"])
         blk.reg2_w = self._f32(f64[e + "vec_attn.reg_branch.2.weight"])

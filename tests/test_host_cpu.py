@@ -69,7 +69,8 @@ def test_packed_folds_are_algebraically_exact():
     want = torch.cat([
         F.linear(ke, sd[p + "encoder.attn.self.key.weight"], sd[p + "encoder.attn.self.key.bias"]),
         F.linear(ke, sd[p + "encoder.cross_attn.self.key.weight"], sd[p + "encoder.cross_attn.self.key.bias"]),
-        F.linear(xc, sd[c + "w_ks.weight"]), F.linear(xc, sd[c + "w_vs.weight"]),
+        F.linear(F.linear(xc, sd[c + "w_ks.weight"]), sd[c + "fc_gamma.0.weight"]),     # kt = W_g1 k
+        F.linear(xc, sd[c + "w_vs.weight"]),
         F.linear(ke, sd[p + "encoder.attn.self.value.weight"], sd[p + "encoder.attn.self.value.bias"]),
         F.linear(ke, sd[p + "encoder.cross_attn.self.value.weight"], sd[p + "encoder.cross_attn.self.value.bias"]),
     ], dim=1)
@@ -78,7 +79,10 @@ def test_packed_folds_are_algebraically_exact():
     s = p + "encoder.vec_attn.query_self_attn."
     Wq = by_ptr[blk.self_qkv.w].float()
     xs = F.linear(x, sd[s + "fc1.weight"], sd[s + "fc1.bias"])
-    want = torch.cat([F.linear(xs, sd[s + n + ".weight"]) for n in ("w_qs", "w_ks", "w_vs")], dim=1)
+    g1w, g1b, d2b = sd[s + "fc_gamma.0.weight"], sd[s + "fc_gamma.0.bias"], sd[s + "fc_delta.2.bias"]
+    want = torch.cat([F.linear(F.linear(xs, sd[s + "w_qs.weight"]), g1w) + g1w @ d2b + g1b,   # qt
+                      F.linear(F.linear(xs, sd[s + "w_ks.weight"]), g1w),                     # kt
+                      F.linear(xs, sd[s + "w_vs.weight"])], dim=1)
     got = x @ Wq.t() + by_ptr[blk.self_qkv.b]
     assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
     # positional table rows: N=1 -> row 0, N=2 -> rows 1,2, N=3 -> rows 3..5

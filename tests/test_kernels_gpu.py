@@ -192,9 +192,15 @@ def _check_vector_attention(lib, D, B, Lq, Lr, anchors):
         t = t.to(dt).contiguous().cuda()
         keep.append(t)
         return t.data_ptr()
+    # folded form (include/poem_b200.h, PoemVecAttn): the kernel takes qt = W_g1 q + W_g1 b_d2 + b_g1, kt = W_g1 k and
+    # the composed matrix W_g1 W_d2; built here in fp64 exactly like pack.py does
+    Wg1, Wd2 = sd["fc_gamma.0.weight"].double(), sd["fc_delta.2.weight"].double()
+    q_raw, k_raw = q, ktab                                  # bf16 un-folded inputs of the fp32 reference
+    q = (q_raw.double() @ Wg1.t() + Wg1 @ sd["fc_delta.2.bias"].double() + sd["fc_gamma.0.bias"].double()).bfloat16()
+    ktab = (k_raw.double() @ Wg1.t()).bfloat16()
     w = nat.PoemVecAttn(dev(sd["fc_delta.0.weight"], torch.float32), dev(sd["fc_delta.0.bias"], torch.float32),
                         nat.PoemLinear(dev(sd["fc_delta.2.weight"], torch.bfloat16), dev(sd["fc_delta.2.bias"], torch.float32)),
-                        nat.PoemLinear(dev(sd["fc_gamma.0.weight"], torch.bfloat16), dev(sd["fc_gamma.0.bias"], torch.float32)),
+                        nat.PoemLinear(dev(Wg1 @ Wd2, torch.bfloat16), None),
                         nat.PoemLinear(dev(sd["fc_gamma.2.weight"], torch.bfloat16), dev(sd["fc_gamma.2.bias"], torch.float32)),
                         nat.PoemLinear(None, None))
     res = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
@@ -210,9 +216,9 @@ def _check_vector_attention(lib, D, B, Lq, Lr, anchors):
     torch.cuda.synchronize()
     # fp32 reference on the bf16-rounded tables / weights
     sdr = {k: (v.bfloat16().float() if k.endswith("weight") and v.shape[1] != 3 else v) for k, v in sd.items()}
-    k_g = orc.gather_rows(ktab.float().view(B, Lr, D), idx)
+    k_g = orc.gather_rows(k_raw.float().view(B, Lr, D), idx)
     v_g = orc.gather_rows(vtab.float().view(B, Lr, D), idx)
-    ref = orc._vector_attention_core(sdr, "", q.float().view(B, Lq, D), k_g, v_g, q_xyz[:, :, None] - nbr)
+    ref = orc._vector_attention_core(sdr, "", q_raw.float().view(B, Lq, D), k_g, v_g, q_xyz[:, :, None] - nbr)
     got = res.float().cpu().view(B, Lq, D)
     # three chained bf16 GEMMs with bf16 intermediates: 3e-2 of the output scale (|res| ~ 1-3)
     assert (got - ref).abs().max().item() <= 3e-2 * max(1.0, ref.abs().max().item())
