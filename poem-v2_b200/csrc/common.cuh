@@ -26,6 +26,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// 2^x on the SFU (MUFU.EX2), no range fix-up: inputs here are <= 0 after max subtraction
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -183,7 +183,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
       }
       const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
+      const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
       const float m_scaled = m_new * scale_log2e;
       float l_blk = 0.f;
       // pass B: probabilities -> bf16 -> swizzled smem (A operand of P·V)
@@ -195,8 +195,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(__uint_as_float(r[2 * i]) * scale_log2e - m_scaled);
-          const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2e - m_scaled);
+          const float p0 = fast_exp2(__uint_as_float(r[2 * i]) * scale_log2e - m_scaled);
+          const float p1 = fast_exp2(__uint_as_float(r[2 * i + 1]) * scale_log2e - m_scaled);
           l_blk += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }

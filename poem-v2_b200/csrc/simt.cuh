@@ -101,12 +101,11 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
   const float* pm = proj + img * 24;
   const float cx = centre[b * 3 + 0], cy = centre[b * 3 + 1], cz = centre[b * 3 + 2];
   constexpr int PTS = 8;
-  int tap[PTS];       // top-left pixel index (may be out of range; validity folded into weights)
   float w00[PTS], w01[PTS], w10[PTS], w11[PTS];
   int o00[PTS], o01[PTS], o10[PTS], o11[PTS];
 #pragma unroll
   for (int j = 0; j < PTS; ++j) {
-    const int p = threadIdx.x + j * SAMPLE_THREADS;
+    const int p = threadIdx.x * PTS + j;   // 8 consecutive points per thread -> one 16-byte store per channel
     // world point (bps + centre), then master->camera, then intrinsics (same two-step order as the reference)
     const float wx = bps[p * 3 + 0] + cx, wy = bps[p * 3 + 1] + cy, wz = bps[p * 3 + 2] + cz;
     const float X0 = pm[0] * wx + pm[1] * wy + pm[2] * wz + pm[3];
@@ -137,24 +136,30 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
     o01[j] = (vx1 && vy0) ? y0 * FW + x0 + 1 : 0;
     o10[j] = (vx0 && vy1) ? (y0 + 1) * FW + x0 : 0;
     o11[j] = (vx1 && vy1) ? (y0 + 1) * FW + x0 + 1 : 0;
-    tap[j] = p;
   }
   __syncthreads();
   const int chunks = P / D;  // rows per (view, channel)
   const size_t row0 = (size_t)sample_rowbase[b] + (size_t)n * P;
+  const int p0 = threadIdx.x * PTS;
   for (int dd = 0; dd < SAMPLE_CH; ++dd) {
     const float* pl = planes + dd * F;
     const size_t rbase = row0 + (size_t)(d0 + dd) * chunks;
+    float v[PTS];
 #pragma unroll
     for (int j = 0; j < PTS; ++j) {
-      const int p = tap[j];
       // ATen accumulates the four taps in the order nw, ne, sw, se
-      float v = pl[o00[j]] * w00[j];
-      v += pl[o01[j]] * w01[j];
-      v += pl[o10[j]] * w10[j];
-      v += pl[o11[j]] * w11[j];
-      X[(rbase + p / D) * D + (p % D)] = __float2bfloat16(v);
+      float t = pl[o00[j]] * w00[j];
+      t += pl[o01[j]] * w01[j];
+      t += pl[o10[j]] * w10[j];
+      t += pl[o11[j]] * w11[j];
+      v[j] = t;
     }
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]);
+    pk.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(X + (rbase + p0 / D) * D + (p0 % D)) = pk;
   }
 }
 

@@ -317,7 +317,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           float sum = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float e = exp2f((__uint_as_float(a[j]) - mx) * p.softmax_scale_log2e);
+            const float e = fast_exp2((__uint_as_float(a[j]) - mx) * p.softmax_scale_log2e);
             sum += e;
             a[j] = __float_as_uint(e);
           }
