@@ -1,12 +1,15 @@
 // Cross-view multi-head attention, 799 queries -> 4096 BPS tokens, no mask (reference: HF BertSelfAttention
 // reached from lib/models/bricks/pt_metro_transformer.py:57-72; scores (B,h,799,4096) never materialised here).
 //
-// One CTA = 128 queries of one (sample, head). Per 128-key block:
-//   S = Q·K^T   tcgen05.mma (M=128, N=128, K=HD)  -> TMEM
-//   softmax warps (thread == query row): running max / sum in fp32, P = exp2(...) written as bf16 into a
-//   SWIZZLE_128B K-major smem tile, then O_blk = P·V (M=128, N=HD, K=128) -> TMEM, accumulated in registers
-//   with the usual online-softmax rescale.
-// Q/K tiles [rows x HD] and V^T tiles [HD x 64 keys] are staged by TMA; K/V are double buffered.
+// One CTA = 128 queries of one (sample, head). Per 128-key block j:
+//   S(j) = Q·K(j)^T     tcgen05.mma (M=128, N=128, K=HD) -> TMEM buffer j%2          (double buffered)
+//   softmax warps (thread == query row, no cross-lane traffic): pass A row max, pass B P = exp2(..) as bf16 into a
+//   SWIZZLE_128B K-major smem tile
+//   O_blk(j) = P(j)·V(j) (M=128, N=HD, K=128) -> TMEM, written over the first HD columns of the ALREADY CONSUMED
+//   S(j) buffer, so 256 TMEM columns hold two S buffers and the P·V result (2 CTAs per SM for HD <= 64)
+//   O_blk(j) is folded into the register accumulator (online-softmax rescale) one iteration later, while the
+//   tensor core already works on S(j+2) / P·V(j+1): the softmax warps never wait for an MMA in steady state.
+// Q/K tiles [rows x HD] and V^T tiles [HD x 64 keys] are staged by TMA; K and V rings are 2 deep.
 // warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = softmax + output.
 #pragma once
 #include "common.cuh"
@@ -25,9 +28,8 @@ struct MhaCfg {
   static constexpr int kKBytes = MHA_BKEY * HD * 2;
   static constexpr int kVBytes = HD * MHA_BKEY * 2;              // two [HD x 64 keys] SWIZZLE_128B tiles
   static constexpr int kPBytes = MHA_BQ * MHA_BKEY * 2;          // two [128 x 64 keys] SWIZZLE_128B tiles
-  static constexpr int kStages = 2;
-  static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 256;
-  static constexpr int kTmemCols = (128 + HD <= 256) ? 256 : 512;  // S: 128 columns, O_blk: HD columns
+  static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 256;
+  static constexpr int kTmemCols = 256;                          // two S buffers; O_blk aliases the consumed one
 };
 
 template <int HD>
@@ -42,16 +44,20 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + Cfg::kQBytes;                               // stage s: K at s*(K+V), V right after
-  uint8_t* sP = sKV + Cfg::kStages * (Cfg::kKBytes + Cfg::kVBytes);
+  uint8_t* sK = sQ + Cfg::kQBytes;               // 2 stages
+  uint8_t* sV = sK + 2 * Cfg::kKBytes;           // 2 stages
+  uint8_t* sP = sV + 2 * Cfg::kVBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;       // [2] TMA -> MMA
+  uint64_t* k_empty = bars + 3;      // [2] MMA -> TMA (S(j) retired)
+  uint64_t* v_full = bars + 5;       // [2]
+  uint64_t* v_empty = bars + 7;      // [2] (P·V(j) retired)
+  uint64_t* s_full = bars + 9;       // [2] MMA -> softmax: S(j) in TMEM buffer j%2
+  uint64_t* o_full = bars + 11;      // [2] MMA -> softmax: O_blk(j) in TMEM buffer j%2 (and P smem tile free)
+  uint64_t* o_done = bars + 13;      // [2] softmax -> MMA: O_blk(j) folded, buffer j%2 may take S(j+2)   (count 128)
+  uint64_t* p_full = bars + 15;      //     softmax -> MMA: P(j) in smem, S(j) consumed                   (count 128)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -69,12 +75,15 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     if (lane == 0) {
       mbar_init(q_full, 1);
       for (int s = 0; s < 2; ++s) {
-        mbar_init(&kv_full[s], 1);
-        mbar_init(&kv_empty[s], 1);
+        mbar_init(&k_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&v_empty[s], 1);
+        mbar_init(&s_full[s], 1);
+        mbar_init(&o_full[s], 1);
+        mbar_init(&o_done[s], 128);
       }
-      mbar_init(s_full, 1);
       mbar_init(p_full, 128);
-      mbar_init(o_full, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -83,9 +92,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_base = *tmem_slot;   // buffer i at columns [128*i, 128*i + 128)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -93,23 +100,19 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       mbar_expect_tx(q_full, Cfg::kQBytes);
       for (int kb = 0; kb < Cfg::kKBlocks; ++kb)
         tma_load_2d(sQ + kb * (MHA_BQ * Cfg::kRowBytes), &tmap_q, q_full, q_col0 + head * HD + kb * 64, b * Lq + q0);
-      int stage = 0;
-      uint32_t phase = 0;
       for (int j = 0; j < n_kblocks; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sK = sKV + stage * (Cfg::kKBytes + Cfg::kVBytes);
-        uint8_t* sV = sK + Cfg::kKBytes;
-        mbar_expect_tx(&kv_full[stage], Cfg::kKBytes + Cfg::kVBytes);
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::kKBytes);
         for (int kb = 0; kb < Cfg::kKBlocks; ++kb)
-          tma_load_2d(sK + kb * (MHA_BKEY * Cfg::kRowBytes), &tmap_k, &kv_full[stage],
+          tma_load_2d(sK + st * Cfg::kKBytes + kb * (MHA_BKEY * Cfg::kRowBytes), &tmap_k, &k_full[st],
                       k_col0 + head * HD + kb * 64, b * Lk + j * MHA_BKEY);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], Cfg::kVBytes);
         for (int kb = 0; kb < 2; ++kb)
-          tma_load_2d(sV + kb * (HD * 128), &tmap_vt, &kv_full[stage], j * MHA_BKEY + kb * 64,
+          tma_load_2d(sV + st * Cfg::kVBytes + kb * (HD * 128), &tmap_vt, &v_full[st], j * MHA_BKEY + kb * 64,
                       vt_row0 + b * vt_batch_rows + head * HD);
-        if (++stage == 2) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
     }
   } else if (warp == 1) {
@@ -117,45 +120,45 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(MHA_BQ, MHA_BKEY);
       constexpr uint32_t idesc_o = make_idesc_bf16(MHA_BQ, HD);
-      auto issue_S = [&](int stage) {
-        const uint32_t sK = smem_u32(sKV + stage * (Cfg::kKBytes + Cfg::kVBytes));
+      auto issue_S = [&](int j) {   // S(j) -> TMEM buffer j%2, from K stage j%2
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (uint32_t)(j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(sK + st * Cfg::kKBytes);
 #pragma unroll
         for (int kb = 0; kb < Cfg::kKBlocks; ++kb) {
           const uint64_t dq = make_kmajor_desc<Cfg::kRowBytes>(smem_u32(sQ) + kb * (MHA_BQ * Cfg::kRowBytes));
-          const uint64_t dk = make_kmajor_desc<Cfg::kRowBytes>(sK + kb * (MHA_BKEY * Cfg::kRowBytes));
+          const uint64_t dk = make_kmajor_desc<Cfg::kRowBytes>(k_addr + kb * (MHA_BKEY * Cfg::kRowBytes));
 #pragma unroll
-          for (int k = 0; k < Cfg::kRowBytes / 32; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, (kb | k) != 0);
+          for (int k = 0; k < Cfg::kRowBytes / 32; ++k)
+            umma_bf16(tmem_base + st * 128, dq + 2 * k, dk + 2 * k, idesc_s, (kb | k) != 0);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after_sync();
       issue_S(0);
-      int stage = 0;
-      uint32_t phase = 0;
+      if (n_kblocks > 1) issue_S(1);
       for (int j = 0; j < n_kblocks; ++j) {
-        // P(j) is in smem and S(j) has been consumed
-        mbar_wait(p_full, j & 1);
+        const int st = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1;
+        mbar_wait(p_full, (uint32_t)j & 1);          // P(j) in smem, S(j) consumed by every softmax thread
+        mbar_wait(&v_full[st], ph);
         tc_fence_after_sync();
-        const uint32_t sV = smem_u32(sKV + stage * (Cfg::kKBytes + Cfg::kVBytes) + Cfg::kKBytes);
+        const uint32_t v_addr = smem_u32(sV + st * Cfg::kVBytes);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t dp = make_kmajor_desc<128>(smem_u32(sP) + kb * (MHA_BQ * 128));
-          const uint64_t dv = make_kmajor_desc<128>(sV + kb * (HD * 128));
+          const uint64_t dv = make_kmajor_desc<128>(v_addr + kb * (HD * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_O, dp + 2 * k, dv + 2 * k, idesc_o, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + st * 128, dp + 2 * k, dv + 2 * k, idesc_o, (kb | k) != 0);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[stage]);
-        if (++stage == 2) {
-          stage = 0;
-          phase ^= 1;
-        }
-        if (j + 1 < n_kblocks) {
-          mbar_wait(&kv_full[stage], phase);
+        umma_commit(&o_full[st]);
+        umma_commit(&v_empty[st]);
+        if (j + 2 < n_kblocks) {
+          mbar_wait(&o_done[st], ph);                // O_blk(j) has been read out of buffer st
           tc_fence_after_sync();
-          issue_S(stage);
+          issue_S(j + 2);
         }
       }
     }
@@ -169,15 +172,35 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     for (int c = 0; c < HD; ++c) o_acc[c] = 0.f;
     float m_run = -INFINITY;   // running max of raw scores
     float l_run = 0.f;         // running sum of exp
+    float alpha_prev = 0.f;    // rescale that belongs to the not-yet-folded O_blk(j-1)
+
+    auto fold_o = [&](int j, float alpha) {         // o_acc = o_acc * alpha + O_blk(j)
+      const int st = j & 1;
+      mbar_wait(&o_full[st], (uint32_t)(j >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + st * 128 + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(r[i]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&o_done[st]);
+    };
+
     for (int j = 0; j < n_kblocks; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int st = j & 1;
+      const uint32_t tmem_S = tmem_base + lane_off + st * 128;
+      mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1);
       tc_fence_after_sync();
       // pass A: block max
       float m_blk = -INFINITY;
 #pragma unroll 1
       for (int c0 = 0; c0 < MHA_BKEY; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_S + lane_off + c0, r);
+        tmem_ld32(tmem_S + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
@@ -185,12 +208,15 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
       const float m_scaled = m_new * scale_log2e;
-      float l_blk = 0.f;
+      // fold the previous block's P·V (finished long ago) — this also guarantees the P tile is free again
+      if (j > 0) fold_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
       // pass B: probabilities -> bf16 -> swizzled smem (A operand of P·V)
+      float l_blk = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < MHA_BKEY; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_S + lane_off + c0, r);
+        tmem_ld32(tmem_S + c0, r);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
@@ -211,21 +237,11 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
       fence_proxy_async_smem();     // P visible to the tensor-core (async) proxy
-      tc_fence_before_sync();       // our TMEM reads of S are done before the next S MMA may overwrite it
+      tc_fence_before_sync();       // our TMEM reads of S(j) are done before P·V(j) overwrites the buffer
       mbar_arrive(p_full);
-      // O_blk
-      mbar_wait(o_full, j & 1);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_O + lane_off + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(r[i]);
-      }
-      tc_fence_before_sync();
     }
+    fold_o(n_kblocks - 1, alpha_prev);
+
     const int q = q0 + row;
     if (q < Lq) {
       const float inv = 1.0f / l_run;
