@@ -267,28 +267,36 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       mbar_arrive(act_full);
 
       // ---- epilogue 2: relu((W_g1 W_d2) h + qt_i - kt_j) -> activation tile (B operand of the logits GEMM).
-      //      The kt gathers of the first query are issued before waiting for the accumulators.
+      //      All kt gathers of this thread's two queries are in flight before it waits for the accumulators.
       {
-        uint32_t kk[16];
-        gather32(p.ktab, p.ldk, qi0, kk);
+        uint32_t kk[2][16];
+        gather32(p.ktab, p.ldk, qi0, kk[0]);
+        gather32(p.ktab, p.ldk, qi0 + 1, kk[1]);
+        float qv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int qg = q_first + qi0 + u;
+          qv[u] = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
+        }
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int qg = q_first + qi0 + u;
-          uint32_t r[32];
-          tmem_ld32(tmem_h + lane_off + mt * NT + (qi0 + u) * 32, r);
-          if (u == 1) gather32(p.ktab, p.ldk, qi0 + 1, kk);
-          const float qv = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int t = (qi0 + u) * 32 + 2 * j;
-            const float v0 = fmaxf(__uint_as_float(r[2 * j]) + (qv - bf_lo(kk[j])), 0.f);
-            const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + (qv - bf_hi(kk[j])), 0.f);
-            *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
-            *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[16];
+            tmem_ld16(tmem_h + lane_off + mt * NT + (qi0 + u) * 32 + h * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int t = (qi0 + u) * 32 + h * 16 + 2 * j;
+              const uint32_t kp = kk[u][h * 8 + j];
+              const float v0 = fmaxf(__uint_as_float(r[2 * j]) + (qv[u] - bf_lo(kp)), 0.f);
+              const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + (qv[u] - bf_hi(kp)), 0.f);
+              *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
+              *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
+            }
           }
         }
       }
@@ -299,39 +307,42 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       // ---- epilogue 3: per-channel softmax over the 32 neighbours, weighted sum of (v + pos).
       //      softmax((a + b_g2) / sqrt(D)): the bias is constant over the neighbours and cancels.
       {
-        uint32_t vv[16];
-        gather32(p.vtab, p.ldv, qi0, vv);
+        uint32_t vv[2][16];
+        gather32(p.vtab, p.ldv, qi0, vv[0]);
+        gather32(p.vtab, p.ldv, qi0 + 1, vv[1]);
         mbar_wait(acc_full, acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int qg = q_first + qi0 + u;
-          uint32_t a[32];
-          tmem_ld32(tmem_h + lane_off + mt * NT + (qi0 + u) * 32, a);
-          if (u == 1) gather32(p.vtab, p.ldv, qi0 + 1, vv);
-          tmem_ld_wait();
+          const uint32_t col = lane_off + mt * NT + (qi0 + u) * 32;
+          // pass 1: max of the 32 logits
           float mx = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(a[j]));
-          float sum = 0.f;
+          for (int h = 0; h < 2; ++h) {
+            uint32_t a[16];
+            tmem_ld16(tmem_h + col + h * 16, a);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = fast_exp2((__uint_as_float(a[j]) - mx) * p.softmax_scale_log2e);
-            sum += e;
-            a[j] = __float_as_uint(e);
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a[j]));
           }
-          float acc = 0.f;
+          // pass 2: exp, sum, weighted sum
+          float sum = 0.f, acc = 0.f;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t ps[16];
-            tmem_ld16(tmem_pos + lane_off + mt * NT + (qi0 + u) * 32 + h * 16, ps);
+            uint32_t a[16], ps[16];
+            tmem_ld16(tmem_h + col + h * 16, a);
+            tmem_ld16(tmem_pos + col + h * 16, ps);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int jj = h * 8 + j;
-              acc = fmaf(__uint_as_float(a[2 * jj]), bf_lo(vv[jj]) + (__uint_as_float(ps[2 * j]) + bd2), acc);
-              acc = fmaf(__uint_as_float(a[2 * jj + 1]), bf_hi(vv[jj]) + (__uint_as_float(ps[2 * j + 1]) + bd2), acc);
+              const uint32_t vp = vv[u][h * 8 + j];
+              const float e0 = fast_exp2((__uint_as_float(a[2 * j]) - mx) * p.softmax_scale_log2e);
+              const float e1 = fast_exp2((__uint_as_float(a[2 * j + 1]) - mx) * p.softmax_scale_log2e);
+              sum += e0 + e1;
+              acc = fmaf(e0, bf_lo(vp) + (__uint_as_float(ps[2 * j]) + bd2), acc);
+              acc = fmaf(e1, bf_hi(vp) + (__uint_as_float(ps[2 * j + 1]) + bd2), acc);
             }
           }
           if (qg < p.n_query) p.res[(size_t)qg * D + c] = __float2bfloat16(acc / sum);
