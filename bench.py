@@ -114,7 +114,17 @@ def cpu_reference_pass(size, V, B, steps, warmup):
     return B * len(times) / sum(times), sum(times) / len(times)
 
 
+def emit(line):
+    """Write the ONE JSON line to the real stdout (fd 1 is pointed at stderr while the bench runs so that library
+    chatter such as NCCL's version banner cannot end up in front of it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -148,7 +158,7 @@ def main():
                                  "sample": sample},
                 "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -230,8 +240,9 @@ def main():
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    h2d = sum(t.numel() * 4 for t in (host_sets[0][0], host_sets[0][1]["cam_intr"], host_sets[0][1]["cam_extr"], host_sets[0][2]))
-    d2h = host_out.numel() * 4
+    h2d = world * sum(t.numel() * 4 for t in (host_sets[0][0], host_sets[0][1]["cam_intr"], host_sets[0][1]["cam_extr"],
+                                             host_sets[0][2]))   # whole job, like `value`
+    d2h = world * host_out.numel() * 4
 
     # ---- (3) per-kernel CUDA-event timing inside a timed step loop (same stream), for the roofline of the top kernel
     lib.poem_profile_enable(1)
@@ -311,7 +322,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "path_roofline": path,
             "cpu_baseline": cpu,
             "kernel_breakdown_ms_per_step": {k: [round(v["ms"] / prof_steps, 4), v["n"] // prof_steps] for k, v in by_kernel}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
