@@ -41,14 +41,14 @@ struct VaCfg {
   static constexpr int QPS = QT / SETS;              // queries per thread and tile (== 2 for every supported D)
   static constexpr int EP = MT * 128 * SETS;         // channel threads
   static constexpr int THREADS = 64 + EP;
-  static constexpr int W_STAGES = 6;
+  static constexpr int W_STAGES = 5;
   static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] bf16
   static constexpr int ACT_BYTES = NT * D * 2;       // KB blocks of [NT tokens x 64 k] bf16
   static constexpr int TMEM_COLS = (2 * MT * NT <= 256) ? 256 : 512;
   static constexpr int GROUPS = EP / NT;             // stage-A: thread groups per token
   static constexpr int CPT = D / GROUPS;             // stage-A: channels per thread
-  // smem: act | weight ring | wd1 (float4 per channel) | token rows (int) | token rel xyz (float4) | barriers
-  static constexpr int OFF_W = ACT_BYTES;
+  // smem: act0 (h) | act1 (relu gamma1) | weight ring | wd1 (float4 per channel) | token rows | token rel xyz | barriers
+  static constexpr int OFF_W = 2 * ACT_BYTES;
   static constexpr int OFF_WD1 = OFF_W + W_STAGES * W_TILE_BYTES;
   static constexpr int OFF_ROWS = OFF_WD1 + D * 16;
   static constexpr int OFF_REL = OFF_ROWS + NT * 4;
@@ -82,7 +82,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   constexpr int MT = Cfg::MT, KB = Cfg::KB, NT = Cfg::NT, QT = Cfg::QT, EP = Cfg::EP;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* s_act = smem;
+  uint8_t* s_act = smem;                       // B operand of the pos / gamma1 GEMMs (stage A output)
+  uint8_t* s_act1 = smem + Cfg::ACT_BYTES;     // B operand of the logits GEMM (epilogue 2 output)
   uint8_t* s_w = smem + Cfg::OFF_W;
   float4* s_wd1 = reinterpret_cast<float4*>(smem + Cfg::OFF_WD1);
   int* s_rows = reinterpret_cast<int*>(smem + Cfg::OFF_ROWS);
@@ -91,8 +92,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   uint64_t* w_full = bars;                        // [W_STAGES]
   uint64_t* w_empty = bars + Cfg::W_STAGES;       // [W_STAGES]
   uint64_t* act_full = bars + 2 * Cfg::W_STAGES;  // channel threads -> MMA: B operand ready (count EP)
-  uint64_t* acc_full = act_full + 1;              // MMA -> channel threads: accumulator ready (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = act_full + 1;              // [MT] MMA -> channel threads of tile mt: accumulators ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + MT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,7 +111,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         mbar_init(&w_empty[s], 1);
       }
       mbar_init(act_full, EP);
-      mbar_init(acc_full, 1);
+      for (int m = 0; m < MT; ++m) mbar_init(&acc_full[m], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -132,16 +133,20 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int g = 0; g < 3; ++g) {
-          const CUtensorMap* tm = (g == 0) ? &tmap_wd2 : (g == 1) ? &tmap_wg1 : &tmap_wg2;
-          for (int kb = 0; kb < KB; ++kb)
-            for (int mt = 0; mt < MT; ++mt) {
-              mbar_wait(&w_empty[stage], phase ^ 1);
-              mbar_expect_tx(&w_full[stage], Cfg::W_TILE_BYTES);
-              tma_load_2d(s_w + stage * Cfg::W_TILE_BYTES, tm, &w_full[stage], kb * 64, mt * 128);
-              if (++stage == Cfg::W_STAGES) {
-                stage = 0;
-                phase ^= 1;
+        // order = consumption order of the MMA issuer: per round, per channel tile mt, per GEMM g, per K block
+        for (int round = 0; round < 2; ++round) {
+          const int g_first = (round == 0) ? 0 : 2, g_last = (round == 0) ? 1 : 2;
+          for (int mt = 0; mt < MT; ++mt)
+            for (int g = g_first; g <= g_last; ++g) {
+              const CUtensorMap* tm = (g == 0) ? &tmap_wd2 : (g == 1) ? &tmap_wg1 : &tmap_wg2;
+              for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&w_empty[stage], phase ^ 1);
+                mbar_expect_tx(&w_full[stage], Cfg::W_TILE_BYTES);
+                tma_load_2d(s_w + stage * Cfg::W_TILE_BYTES, tm, &w_full[stage], kb * 64, mt * 128);
+                if (++stage == Cfg::W_STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
               }
             }
         }
@@ -160,17 +165,19 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           act_phase ^= 1;
           tc_fence_after_sync();
           // round 0: pos = W_d2 h  and  gamma1_pre = (W_g1 W_d2) h   (same B operand); round 1: logits = W_g2 relu(.)
+          // Channel tile mt is finished (and committed to its own barrier) before mt+1 starts, so the channel warps
+          // of tile mt run their epilogue while the tensor core works on the next tile.
           const int g_first = (round == 0) ? 0 : 2, g_last = (round == 0) ? 1 : 2;
-          for (int g = g_first; g <= g_last; ++g) {
-            const uint32_t acc = (g == 0) ? tmem_pos : tmem_h;
-            for (int kb = 0; kb < KB; ++kb) {
-              const uint64_t db = make_kmajor_desc<128>(smem_u32(s_act) + kb * (NT * 128));
-              for (int mt = 0; mt < MT; ++mt) {
+          for (int mt = 0; mt < MT; ++mt) {
+            for (int g = g_first; g <= g_last; ++g) {
+              const uint32_t acc = ((g == 0) ? tmem_pos : tmem_h) + mt * NT;
+              for (int kb = 0; kb < KB; ++kb) {
+                const uint64_t db = make_kmajor_desc<128>(smem_u32(round == 0 ? s_act : s_act1) + kb * (NT * 128));
                 mbar_wait(&w_full[stage], phase);
                 tc_fence_after_sync();
                 const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * NT, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                 umma_commit(&w_empty[stage]);
                 if (++stage == Cfg::W_STAGES) {
                   stage = 0;
@@ -178,8 +185,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
                 }
               }
             }
+            umma_commit(&acc_full[mt]);
           }
-          umma_commit(acc_full);
         }
       }
     }
@@ -278,7 +285,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           const int qg = q_first + qi0 + u;
           qv[u] = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
         }
-        mbar_wait(acc_full, acc_phase);
+        mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
 #pragma unroll
@@ -294,8 +301,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
               const uint32_t kp = kk[u][h * 8 + j];
               const float v0 = fmaxf(__uint_as_float(r[2 * j]) + (qv[u] - bf_lo(kp)), 0.f);
               const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + (qv[u] - bf_hi(kp)), 0.f);
-              *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
-              *reinterpret_cast<__nv_bfloat16*>(s_act + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
+              *reinterpret_cast<__nv_bfloat16*>(s_act1 + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
+              *reinterpret_cast<__nv_bfloat16*>(s_act1 + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
             }
           }
         }
@@ -310,7 +317,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         uint32_t vv[2][16];
         gather32(p.vtab, p.ldv, qi0, vv[0]);
         gather32(p.vtab, p.ldv, qi0 + 1, vv[1]);
-        mbar_wait(acc_full, acc_phase);
+        mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
 #pragma unroll
