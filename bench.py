@@ -64,7 +64,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -211,14 +211,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here so that nvidia-smi's start-up cost is not paid inside the timed region)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
         step_device(i)
         step_host(i)
     barrier()
 
     # ---- (1) device-resident arm: inputs already in HBM, CUDA events on the launching stream
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.poem_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

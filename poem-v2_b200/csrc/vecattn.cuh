@@ -209,13 +209,16 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     uint32_t acc_phase = 0;
 
     // 32 bf16 values of column c from the gather rows of one query, packed two per register
-    auto gather32 = [&](const __nv_bfloat16* tab, int ld, int qi, uint32_t(&out)[16]) {
+    auto gather32 = [&](const __nv_bfloat16* tab, int qi, uint32_t(&out)[16]) {
       const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tab) + c;
+      const int4* rows4 = reinterpret_cast<const int4*>(s_rows + qi * 32);   // s_rows = row * ld (elements)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const uint32_t lo = __ldg(t16 + (size_t)s_rows[qi * 32 + 2 * j] * ld);
-        const uint32_t hi = __ldg(t16 + (size_t)s_rows[qi * 32 + 2 * j + 1] * ld);
-        out[j] = lo | (hi << 16);
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const int4 o = rows4[j4];
+        const uint32_t a0 = __ldg(t16 + (uint32_t)o.x), a1 = __ldg(t16 + (uint32_t)o.y);
+        const uint32_t a2 = __ldg(t16 + (uint32_t)o.z), a3 = __ldg(t16 + (uint32_t)o.w);
+        out[2 * j4] = a0 | (a1 << 16);
+        out[2 * j4 + 1] = a2 | (a3 << 16);
       }
     };
     auto bf_lo = [](uint32_t x) { return __uint_as_float(x << 16); };
@@ -244,7 +247,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           ry = p.q_xyz[(size_t)qg * 3 + 1] - ny;
           rz = p.q_xyz[(size_t)qg * 3 + 2] - nz;
         }
-        s_rows[et] = row;
+        s_rows[et] = row * p.ldk;   // element offset of the gather row (ldk == ldv, checked on the host)
         s_rel[et] = make_float4(rx, ry, rz, 0.f);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
@@ -277,13 +280,15 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       //      All kt gathers of this thread's two queries are in flight before it waits for the accumulators.
       {
         uint32_t kk[2][16];
-        gather32(p.ktab, p.ldk, qi0, kk[0]);
-        gather32(p.ktab, p.ldk, qi0 + 1, kk[1]);
+        gather32(p.ktab, qi0, kk[0]);
+        gather32(p.ktab, qi0 + 1, kk[1]);
         float qv[2];
+        uint32_t act1_q[2];   // smem address of (token row (qi0+u)*32, channel c) before the swizzle XOR
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int qg = q_first + qi0 + u;
           qv[u] = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
+          act1_q[u] = smem_u32(s_act1) + act_blk + (act_chunk << 4) + act_byte + (uint32_t)(qi0 + u) * (32 * 128);
         }
         mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
@@ -297,12 +302,13 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int t = (qi0 + u) * 32 + h * 16 + 2 * j;
               const uint32_t kp = kk[u][h * 8 + j];
               const float v0 = fmaxf(__uint_as_float(r[2 * j]) + (qv[u] - bf_lo(kp)), 0.f);
               const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + (qv[u] - bf_hi(kp)), 0.f);
-              *reinterpret_cast<__nv_bfloat16*>(s_act1 + act_blk + sw128_offset(t, act_chunk) + act_byte) = __float2bfloat16(v0);
-              *reinterpret_cast<__nv_bfloat16*>(s_act1 + act_blk + sw128_offset(t + 1, act_chunk) + act_byte) = __float2bfloat16(v1);
+              // token row t = (qi0+u)*32 + tl: SWIZZLE_128B flips address bits 4..6 with (t & 7) == (tl & 7)
+              const int tl = h * 16 + 2 * j;
+              st_shared_b16((act1_q[u] ^ ((uint32_t)(tl & 7) << 4)) + tl * 128, v0);
+              st_shared_b16((act1_q[u] ^ ((uint32_t)((tl + 1) & 7) << 4)) + (tl + 1) * 128, v1);
             }
           }
         }
@@ -315,8 +321,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       //      softmax((a + b_g2) / sqrt(D)): the bias is constant over the neighbours and cancels.
       {
         uint32_t vv[2][16];
-        gather32(p.vtab, p.ldv, qi0, vv[0]);
-        gather32(p.vtab, p.ldv, qi0 + 1, vv[1]);
+        gather32(p.vtab, qi0, vv[0]);
+        gather32(p.vtab, qi0 + 1, vv[1]);
         mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
