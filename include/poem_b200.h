@@ -161,6 +161,32 @@ size_t poem_staging_bytes(const PoemDims* dims, int batch, int n_images);
 int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* host_in,
                            float* host_out_coords, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- HRNet-W40 stage 4 (reference lib/models/backbones/hrnet.py:272-277: 3 HighResolutionModules of 4 branches x
+ * 4 BasicBlocks + all-to-all fuse layers).  Convolution weights have eval-mode BatchNorm folded in and are stored as
+ * bf16 [Cout_p, k*k*Cin_p] (K ordered (ky, kx, c); channel counts padded to multiples of 64 with zeros), bias fp32
+ * [Cout_p].  Activations are converted NCHW fp32 <-> NHWC bf16 inside the call. */
+#define POEM_HR_MAX_MODULES 4
+typedef struct PoemHRModule {
+  PoemLinear branch[4][4][2];   /* [branch][block][conv1 | conv2] */
+  PoemLinear fuse[4][4][3];     /* [i][j][k]: j > i: k = 0 is the 1x1 conv; j < i: k = 0..i-j-1 stride-2 3x3 chain */
+} PoemHRModule;
+typedef struct PoemHRStage4 {
+  int32_t n_modules;            /* 3 */
+  int32_t channels[4];          /* 40, 80, 160, 320 */
+  PoemHRModule modules[POEM_HR_MAX_MODULES];
+} PoemHRStage4;
+size_t poem_hrnet_stage4_workspace_bytes(const PoemHRStage4* w, int n_images, int base_res);
+/* in[b] / out[b]: fp32 NCHW (n_images, channels[b], base_res >> b, base_res >> b), device pointers.
+ * Replaces `y_list = self.stage4(x_list)` (hrnet.py:417). */
+int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, int base_res, const float* const* in,
+                              float* const* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
+ * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
+ * Replaces nn.Conv2d + nn.BatchNorm2d(eval) (+ReLU, + identity) of hrnet.py:38-67,177-207. */
+int poem_conv_nhwc(const poem_bf16* in, int n_images, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
+                   int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out, void* stream);
+
 /* ---- stage-level entry points (unit-testable building blocks; same kernels the whole path uses) ---- */
 
 /* C = act(A·W^T + bias) (+ residual); A bf16 [M,K] (lda), W bf16 [N,K] (ldw); outputs optional.

@@ -60,8 +60,36 @@ def run_reference(size, views, wseed, iseed, mode):
     return cap
 
 
+def run_reference_stage4(n_images, wseed, iseed):
+    """The real reference `HighResolutionModule` x3 (= `HighResolutionNet.stage4`, hrnet.py:272-277) on CPU."""
+    ref_shim.install(synth.standin_template)
+    import lib.external.metro.hrnet  # noqa: F401  (bare package; the backbone imports its config from there)
+    import types
+    cfgmod = types.ModuleType("lib.external.metro.hrnet.config")
+    cfgmod.config = None
+    cfgmod.update_config = lambda *a, **k: None
+    sys.modules.setdefault("lib.external.metro.hrnet", types.ModuleType("lib.external.metro.hrnet"))
+    sys.modules.setdefault("lib.external.metro.hrnet.config", cfgmod)
+    import lib.models.backbones.hrnet as hr
+    ch = [40, 80, 160, 320]
+    mods = torch.nn.Sequential(*[hr.HighResolutionModule(4, hr.BasicBlock, [4] * 4, list(ch), list(ch), "SUM", True)
+                                 for _ in range(3)]).eval()
+    sd = synth.make_stage4_state_dict(wseed)
+    mods.load_state_dict(sd, strict=True)
+    xs = synth.make_stage4_inputs(n_images, 64, iseed)
+    with torch.no_grad():
+        ys = mods(list(xs))
+    return ys
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    ys = run_reference_stage4(2, 0, 1)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hrnet_stage4_n2.npz"),
+                        meta=np.array(repr(dict(kind="hrnet_stage4", n_images=2, wseed=0, iseed=1, stride=4))),
+                        y0=ys[0][:, :, ::4, ::4].numpy(), y1=ys[1][:, :, ::2, ::2].numpy(), y2=ys[2].numpy(),
+                        y3=ys[3].numpy())
+    print("hrnet_stage4_n2", [tuple(y.shape) for y in ys])
     for name, (size, views, wseed, iseed, mode) in CASES.items():
         cap = run_reference(size, views, wseed, iseed, mode)
         out = {

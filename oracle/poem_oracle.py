@@ -235,3 +235,45 @@ def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anc
     if stages is not None:
         stages["xyz_norm"] = coords
     return coords * dims.radius + centre[None, :, None, :]
+
+
+# ------------------------------------------------------------------------------------------ a17
+def _conv_bn(sd, conv_key, bn_key, x, stride=1, relu=False):
+    """Conv2d(bias=False) + BatchNorm2d in eval mode (+ ReLU)."""
+    w = sd[conv_key + ".weight"]
+    y = F.conv2d(x, w, None, stride=stride, padding=w.shape[-1] // 2)
+    y = F.batch_norm(y, sd[bn_key + ".running_mean"], sd[bn_key + ".running_var"], sd[bn_key + ".weight"],
+                     sd[bn_key + ".bias"], training=False, eps=1e-5)
+    return F.relu(y) if relu else y
+
+
+def hrnet_stage4(sd, x_list, n_modules=3):
+    """`HighResolutionNet.stage4` = n_modules x `HighResolutionModule.forward`
+    (lib/models/backbones/hrnet.py:217-234; BasicBlock :38-67; fuse layers :177-207). sd keys relative to `stage4.`"""
+    xs = list(x_list)
+    nb = len(xs)
+    for m in range(n_modules):
+        for b in range(nb):
+            x = xs[b]
+            for k in range(4):
+                p = f"{m}.branches.{b}.{k}."
+                t = _conv_bn(sd, p + "conv1", p + "bn1", x, relu=True)
+                x = F.relu(_conv_bn(sd, p + "conv2", p + "bn2", t) + x)
+            xs[b] = x
+        fused = []
+        for i in range(nb):
+            y = None
+            for j in range(nb):
+                p = f"{m}.fuse_layers.{i}.{j}."
+                if j == i:
+                    t = xs[j]
+                elif j > i:
+                    t = F.interpolate(_conv_bn(sd, p + "0", p + "1", xs[j]), scale_factor=2 ** (j - i), mode="nearest")
+                else:
+                    t = xs[j]
+                    for k in range(i - j):
+                        t = _conv_bn(sd, p + f"{k}.0", p + f"{k}.1", t, stride=2, relu=(k != i - j - 1))
+                y = t if y is None else y + t
+            fused.append(F.relu(y))
+        xs = fused
+    return xs

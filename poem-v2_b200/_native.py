@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpoem_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["poem_b200.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh"]
+HEADERS = ["common.cuh", "gemm.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh", "hrnet.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -80,6 +80,17 @@ class PoemWeights(C.Structure):
                 ("template_xyz", C.c_void_p), ("blocks", PoemBlock * POEM_MAX_BLOCKS)]
 
 
+POEM_HR_MAX_MODULES = 4
+
+
+class PoemHRModule(C.Structure):
+    _fields_ = [("branch", ((PoemLinear * 2) * 4) * 4), ("fuse", ((PoemLinear * 3) * 4) * 4)]
+
+
+class PoemHRStage4(C.Structure):
+    _fields_ = [("n_modules", C.c_int32), ("channels", C.c_int32 * 4), ("modules", PoemHRModule * POEM_HR_MAX_MODULES)]
+
+
 class PoemInputs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_images", C.c_int32), ("view_counts", C.c_void_p), ("mlvl_feat", C.c_void_p),
                 ("cam_intr", C.c_void_p), ("cam_extr", C.c_void_p), ("reference_joints", C.c_void_p),
@@ -88,7 +99,8 @@ class PoemInputs(C.Structure):
 
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
-           "poem_profile_summary", "poem_debug_force_unfused", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+           "poem_profile_summary", "poem_debug_force_unfused", "poem_hrnet_stage4_workspace_bytes",
+           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
@@ -147,6 +159,12 @@ def load():
     lib.poem_vector_attention.restype = i
     lib.poem_vector_attention.argtypes = [C.POINTER(PoemVecAttn), vp, i, vp, i, vp, i, vp, vp, vp, vp, vp, i, i, i, i,
                                           vp, vp, sz, vp]
+    lib.poem_hrnet_stage4_workspace_bytes.restype = sz
+    lib.poem_hrnet_stage4_workspace_bytes.argtypes = [C.POINTER(PoemHRStage4), i, i]
+    lib.poem_hrnet_stage4_forward.restype = i
+    lib.poem_hrnet_stage4_forward.argtypes = [C.POINTER(PoemHRStage4), i, i, C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
+    lib.poem_conv_nhwc.restype = i
+    lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp]
     lib.poem_layernorm.restype = i
     lib.poem_layernorm.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
     _lib = lib

@@ -17,7 +17,20 @@ enum GemmRes : int {
   RES_NONE = 0,
   RES_F32 = 1,      // out += res_f32[m * res_ld + n]
   RES_POSADD = 2,   // out += res_f32[(row_tab[m / 256] * 256 + m % 256) * res_ld + n]   (positional term per view)
-  RES_MERGE = 3     // out = out * row_scale[m / P] + res_bf16[(row_base[m / P] + (m % P) * row_cnt[m / P]) * res_ld + n]
+  RES_MERGE = 3,    // out = out * row_scale[m / P] + res_bf16[(row_base[m / P] + (m % P) * row_cnt[m / P]) * res_ld + n]
+  RES_BF16 = 4      // out += res_bf16[m * res_ld + n]   (BasicBlock identity shortcut, NHWC)
+};
+
+// Implicit-GEMM convolution: the A operand is gathered by TMA straight from an NHWC activation tensor
+// (4-D tensor map, zero fill outside the image = conv padding); K block kb = (filter tap, 64-channel block).
+// An M tile is 128 consecutive NHWC output pixels (whole image rows), so the epilogue addressing is unchanged.
+struct ConvOperand {
+  int enabled;
+  int ksize;     // 1 or 3
+  int pad;       // 0 or 1
+  int stride;    // 1 or 2
+  int cblocks;   // padded input channels / 64
+  int Hout, Wout;
 };
 
 struct GemmEpilogue {
@@ -66,7 +79,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
-                    int N, int K, GemmEpilogue ep) {
+                    int N, int K, GemmEpilogue ep, ConvOperand conv) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -124,7 +137,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sw = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+          if (conv.enabled) {
+            const int tap = kb / conv.cblocks, cc = kb - tap * conv.cblocks;
+            const int ky = tap / conv.ksize, kx = tap - ky * conv.ksize;
+            const int pix = conv.Hout * conv.Wout;
+            const int n_img = m0 / pix, y0 = (m0 - n_img * pix) / conv.Wout;
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], cc * 64, kx - conv.pad, y0 * conv.stride + ky - conv.pad, n_img);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+          }
           tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -212,6 +233,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             resf[i] = ep.res_f32 + (size_t)m * ep.res_ld;
           } else if (ep.res_mode == RES_POSADD) {
             resf[i] = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
+          } else if (ep.res_mode == RES_BF16) {
+            resb[i] = ep.res_bf16 + (size_t)m * ep.res_ld;
           } else if (ep.res_mode == RES_MERGE) {
             const int g = m / ep.rows_per_group;
             const int cnt = ep.row_cnt[g];

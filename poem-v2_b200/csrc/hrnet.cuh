@@ -1,0 +1,86 @@
+// HRNet-W40 stage 4 glue kernels (reference lib/models/backbones/hrnet.py:38-67,217-234,272-277).
+// Activations live as NHWC bf16 with the channel count padded to a multiple of 64 (one SWIZZLE_128B atom), so
+// every 3x3 / 1x1 convolution is an implicit GEMM of gemm_bf16_tc_kernel (TMA gathers the shifted image rows, zero
+// fill = padding); BatchNorm (eval) is folded into the weights/bias at pack time.
+#pragma once
+#include "common.cuh"
+
+namespace poem {
+
+// (N, C, H*W) fp32 -> (N, H*W, Cp) bf16, channels >= C zero-filled.  32x32 smem transpose tiles.
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Cp,
+                                             int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (c < C && p < HW) ? in[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (c < Cp && p < HW) out[((size_t)n * HW + p) * Cp + c] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+// (N, H*W, Cp) bf16 -> (N, C, H*W) fp32 (only the C real channels)
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int Cp,
+                                             int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    tile[i][tx] = (c < Cp && p < HW) ? __bfloat162float(in[((size_t)n * HW + p) * Cp + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[tx][i];
+  }
+}
+
+// Fuse layer sum (hrnet.py:225-233): out[n,y,x,c] = relu(sum_j in_j[n, y >> s_j, x >> s_j, c]); in_j has resolution
+// (H >> s_j, W >> s_j) — nearest-neighbour upsampling by 2^s_j of the 1x1-conv terms, s_j = 0 for the others.
+struct FuseSumArgs {
+  const __nv_bfloat16* in[4];
+  int shift[4];
+  int n_in;
+};
+__global__ void fuse_sum_relu_kernel(FuseSumArgs a, __nv_bfloat16* __restrict__ out, int H, int W, int Cp, size_t total8) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total8) return;
+  const int c8 = Cp / 8;
+  const int c = (int)(gid % c8) * 8;
+  size_t pix = gid / c8;
+  const int x = (int)(pix % W);
+  pix /= W;
+  const int y = (int)(pix % H);
+  const size_t n = pix / H;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int j = 0; j < a.n_in; ++j) {
+    const int s = a.shift[j];
+    const int hj = H >> s, wj = W >> s;
+    const uint4 v = *reinterpret_cast<const uint4*>(a.in[j] + ((n * hj + (y >> s)) * wj + (x >> s)) * Cp + c);
+    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(v2[i]);
+      acc[2 * i] += f.x;
+      acc[2 * i + 1] += f.y;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+  o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+  o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+  *reinterpret_cast<uint4*>(out + gid * 8) = o;
+}
+
+}  // namespace poem

@@ -12,6 +12,7 @@
 #include "../../include/poem_b200.h"
 #include "gemm.cuh"
 #include "mha.cuh"
+#include "hrnet.cuh"
 #include "simt.cuh"
 #include "vecattn.cuh"
 
@@ -174,11 +175,26 @@ static int num_sms() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// workspace bump allocator
+// ------------------------------------------------------------------------------------------------
+struct Bump {
+  uint8_t* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // GEMM launch
 // ------------------------------------------------------------------------------------------------
 template <int BN>
 static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, const GemmEpilogue& ep,
-                          cudaStream_t st) {
+                          const ConvOperand& conv, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -188,7 +204,7 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_begin(st);
-  gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(ta, tw, M, N, K, ep);
+  gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(ta, tw, M, N, K, ep, conv);
   LAUNCH_CHECK("gemm_bf16_tc_kernel");
   return POEM_OK;
 }
@@ -213,9 +229,198 @@ static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   CUtensorMap ta, tw;
   POEM_TRY(make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM));
   POEM_TRY(make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, GEMM_BK, (uint32_t)BN));
-  if (BN == 256) return launch_gemm_bn<256>(ta, tw, M, N, K, ep, st);
-  if (BN == 128) return launch_gemm_bn<128>(ta, tw, M, N, K, ep, st);
-  return launch_gemm_bn<64>(ta, tw, M, N, K, ep, st);
+  ConvOperand none;
+  memset(&none, 0, sizeof(none));
+  if (BN == 256) return launch_gemm_bn<256>(ta, tw, M, N, K, ep, none, st);
+  if (BN == 128) return launch_gemm_bn<128>(ta, tw, M, N, K, ep, none, st);
+  return launch_gemm_bn<64>(ta, tw, M, N, K, ep, none, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM convolution on NHWC bf16 (HRNet stage 4)
+// ------------------------------------------------------------------------------------------------
+// 4-D bf16 tensor map over an NHWC activation tensor: dims (C, W, H, N); box (64, bw*stride, bh*stride, bn) with
+// traversal stride `stride` along W and H, SWIZZLE_128B, zero fill outside (= convolution padding).
+static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int Cp, int bw, int bh, int bn,
+                          int stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (Cp % 64)) return fail(POEM_E_ALIGN, "conv: bad activation tensor");
+  cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d)", (int)r);
+  return POEM_OK;
+}
+
+// out[N, Hout, Wout, Cout_p] = act(conv(in[N, Hin, Win, Cin_p], w[Cout_p, k*k*Cin_p]) + b) (+ res)
+static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
+                       int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
+                       cudaStream_t st) {
+  if (!wt.w || !wt.b) return fail(POEM_E_NULL, "conv: weight pointer missing");
+  if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
+    return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
+  const int Hout = Hin / stride, Wout = Win / stride;
+  if (Wout < 1 || 128 % Wout || Wout > 128 || Cin_p % 64 || Cout_p % 32)
+    return fail(POEM_E_BADDIM, "conv: unsupported shape %dx%d C %d -> %d", Hin, Win, Cin_p, Cout_p);
+  int bh = 128 / Wout, bn = 1;
+  if (bh > Hout) {
+    bn = bh / Hout;
+    bh = Hout;
+  }
+  if (bh * stride > 256 || Wout * stride > 256) return fail(POEM_E_BADDIM, "conv: TMA box too large");
+  const int taps = ksize * ksize, cblocks = Cin_p / 64;
+  const int M = N * Hout * Wout, K = taps * Cin_p;
+  CUtensorMap ta, tw;
+  POEM_TRY(make_tmap_nhwc(&ta, in, N, Hin, Win, Cin_p, Wout, bh, bn, stride));
+  const int BN = (Cout_p <= 256) ? Cout_p : 160;
+  if (!(BN == 64 || BN == 128 || BN == 160 || BN == 192 || BN == 256) || Cout_p % BN)
+    return fail(POEM_E_BADDIM, "conv: Cout_p=%d has no tile", Cout_p);
+  POEM_TRY(make_tmap_bf16(&tw, wt.w, (uint64_t)Cout_p, (uint64_t)K, (uint64_t)K, GEMM_BK, (uint32_t)BN));
+  GemmEpilogue e = epi_default(Cout_p);
+  e.bias = wt.b;
+  e.act = relu ? ACT_RELU : ACT_NONE;
+  if (res) {
+    e.res_mode = RES_BF16;
+    e.res_bf16 = res;
+    e.res_ld = Cout_p;
+  }
+  e.out_bf16 = out;
+  e.ld_bf16 = Cout_p;
+  ConvOperand cv;
+  cv.enabled = 1, cv.ksize = ksize, cv.pad = ksize / 2, cv.stride = stride, cv.cblocks = cblocks, cv.Hout = Hout,
+  cv.Wout = Wout;
+  TagScope ts(ksize == 3 ? (stride == 1 ? "conv3x3" : "conv3x3s2") : "conv1x1");
+  switch (BN) {
+    case 64: return launch_gemm_bn<64>(ta, tw, M, Cout_p, K, e, cv, st);
+    case 128: return launch_gemm_bn<128>(ta, tw, M, Cout_p, K, e, cv, st);
+    case 160: return launch_gemm_bn<160>(ta, tw, M, Cout_p, K, e, cv, st);
+    case 192: return launch_gemm_bn<192>(ta, tw, M, Cout_p, K, e, cv, st);
+    default: return launch_gemm_bn<256>(ta, tw, M, Cout_p, K, e, cv, st);
+  }
+}
+
+extern "C" int poem_conv_nhwc(const poem_bf16* in, int N, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
+                              int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out,
+                              void* stream) {
+  if (!in || !out) return fail(POEM_E_NULL, "conv: null pointer");
+  PoemLinear wt;
+  wt.w = w;
+  wt.b = b;
+  return launch_conv(reinterpret_cast<const __nv_bfloat16*>(in), N, H, W, Cin_p, wt, Cout_p, ksize, stride, relu != 0,
+                     reinterpret_cast<const __nv_bfloat16*>(res), reinterpret_cast<__nv_bfloat16*>(out),
+                     (cudaStream_t)stream);
+}
+
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+struct HrPlan {
+  __nv_bfloat16* x[4][3];     // per branch: current / scratch / next
+  __nv_bfloat16* term[4][4];  // fuse terms (i, j != i) at the size of branch i
+  __nv_bfloat16* chain[2];    // intermediates of the stride-2 chains
+};
+static size_t hr_plan(int N, int R0, const int* ch, uint8_t* base, HrPlan* p) {
+  Bump b{base, 0};
+  size_t chain_max = 0;
+  for (int i = 0; i < 4; ++i) {
+    const size_t n = (size_t)N * (R0 >> i) * (R0 >> i) * pad64(ch[i]);
+    for (int k = 0; k < 3; ++k) p->x[i][k] = b.take<__nv_bfloat16>(n);
+    for (int j = 0; j < 4; ++j) p->term[i][j] = (j == i) ? nullptr : b.take<__nv_bfloat16>(n);
+    if (i >= 1 && i <= 2) {
+      const size_t c = (size_t)N * (R0 >> i) * (R0 >> i) * pad64(ch[0]);   // largest chain intermediate at this res
+      chain_max = c > chain_max ? c : chain_max;
+    }
+  }
+  for (int k = 0; k < 2; ++k) p->chain[k] = b.take<__nv_bfloat16>(chain_max > 0 ? chain_max : 64);
+  return b.off + 1024;
+}
+
+extern "C" size_t poem_hrnet_stage4_workspace_bytes(const PoemHRStage4* w, int n_images, int base_res) {
+  if (!w || n_images < 1 || base_res < 8) return 0;
+  HrPlan p;
+  return hr_plan(n_images, base_res, w->channels, nullptr, &p);
+}
+
+extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, int base_res, const float* const* in,
+                                         float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !in || !out || !workspace) return fail(POEM_E_NULL, "hrnet_stage4: null pointer");
+  if (w->n_modules < 1 || w->n_modules > POEM_HR_MAX_MODULES) return fail(POEM_E_BADDIM, "n_modules=%d", w->n_modules);
+  if (base_res != 64 && base_res != 32 && base_res != 128) return fail(POEM_E_BADDIM, "base_res=%d", base_res);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  const int N = n_images, R0 = base_res;
+  const int* ch = w->channels;
+  cudaStream_t st = (cudaStream_t)stream;
+  HrPlan p;
+  const size_t need = hr_plan(N, R0, ch, reinterpret_cast<uint8_t*>(workspace), &p);
+  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  int Cp[4], R[4];
+  for (int i = 0; i < 4; ++i) {
+    Cp[i] = pad64(ch[i]);
+    R[i] = R0 >> i;
+    if (!in[i] || !out[i]) return fail(POEM_E_NULL, "hrnet_stage4: branch %d pointer missing", i);
+    dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
+    prof_begin(st);
+    nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], Cp[i], R[i] * R[i]);
+    LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+  }
+  int cur[4] = {0, 0, 0, 0};   // index of the buffer holding the branch's current activation
+  for (int m = 0; m < w->n_modules; ++m) {
+    const PoemHRModule& mod = w->modules[m];
+    // ---- branches: 4 BasicBlocks each (hrnet.py:38-67)
+    for (int b = 0; b < 4; ++b) {
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat16* x = p.x[b][cur[b]];
+        __nv_bfloat16* t = p.x[b][(cur[b] + 1) % 3];
+        __nv_bfloat16* y = p.x[b][(cur[b] + 2) % 3];
+        POEM_TRY(launch_conv(x, N, R[b], R[b], Cp[b], mod.branch[b][k][0], Cp[b], 3, 1, true, nullptr, t, st));
+        POEM_TRY(launch_conv(t, N, R[b], R[b], Cp[b], mod.branch[b][k][1], Cp[b], 3, 1, true, x, y, st));
+        cur[b] = (cur[b] + 2) % 3;
+      }
+    }
+    // ---- fuse layers (hrnet.py:177-207, 225-233)
+    for (int i = 0; i < 4; ++i) {
+      FuseSumArgs fa;
+      fa.n_in = 0;
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16* xj = p.x[j][cur[j]];
+        if (j == i) {
+          fa.in[fa.n_in] = xj, fa.shift[fa.n_in] = 0;
+        } else if (j > i) {   // 1x1 conv + BN at the low resolution, upsampled by the sum kernel
+          POEM_TRY(launch_conv(xj, N, R[j], R[j], Cp[j], mod.fuse[i][j][0], Cp[i], 1, 1, false, nullptr, p.term[i][j], st));
+          fa.in[fa.n_in] = p.term[i][j], fa.shift[fa.n_in] = j - i;
+        } else {              // chain of (i - j) stride-2 3x3 convs; all but the last keep C_j channels and ReLU
+          const __nv_bfloat16* src = xj;
+          int r = R[j];
+          for (int k = 0; k < i - j; ++k) {
+            const bool last = (k == i - j - 1);
+            __nv_bfloat16* dst = last ? p.term[i][j] : p.chain[k & 1];
+            POEM_TRY(launch_conv(src, N, r, r, Cp[j], mod.fuse[i][j][k], last ? Cp[i] : Cp[j], 3, 2, !last, nullptr, dst, st));
+            src = dst;
+            r >>= 1;
+          }
+          fa.in[fa.n_in] = p.term[i][j], fa.shift[fa.n_in] = 0;
+        }
+        ++fa.n_in;
+      }
+      __nv_bfloat16* dst = p.x[i][(cur[i] + 1) % 3];
+      const size_t total8 = (size_t)N * R[i] * R[i] * Cp[i] / 8;
+      prof_begin(st);
+      fuse_sum_relu_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cp[i], total8);
+      LAUNCH_CHECK("fuse_sum_relu_kernel");
+    }
+    for (int i = 0; i < 4; ++i) cur[i] = (cur[i] + 1) % 3;
+  }
+  for (int i = 0; i < 4; ++i) {
+    dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
+    prof_begin(st);
+    nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, st>>>(p.x[i][cur[i]], out[i], ch[i], Cp[i], R[i] * R[i]);
+    LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
+  }
+  return POEM_OK;
 }
 
 extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N,
@@ -323,21 +528,6 @@ extern "C" int poem_layernorm(const float* x, const float* gamma, const float* b
   return launch_layernorm(x, gamma, beta, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), rows, D,
                           (cudaStream_t)stream);
 }
-
-// ------------------------------------------------------------------------------------------------
-// workspace bump allocator
-// ------------------------------------------------------------------------------------------------
-struct Bump {
-  uint8_t* base;
-  size_t off;
-  template <typename T>
-  T* take(size_t n) {
-    off = (off + 1023) & ~size_t(1023);
-    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
-    off += n * sizeof(T);
-    return p;
-  }
-};
 
 // per-image / per-sample index tables derived from view_counts
 struct ViewTables {

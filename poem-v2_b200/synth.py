@@ -172,3 +172,30 @@ def make_state_dict(dims: HeadDims, seed: int = 0, mode: str = "stress"):
                         w = w * gain
         sd[name] = w.float().contiguous()
     return sd
+
+
+def make_stage4_state_dict(seed: int = 0, n_modules: int = 3):
+    """Seeded weights for HRNet stage 4 under the reference key names: He-style conv weights, BatchNorm statistics
+    and affine terms perturbed around identity so that folding is exercised (gamma, var != 1; beta, mean != 0)."""
+    from .hrnet import stage4_param_shapes
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in stage4_param_shapes(n_modules).items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(100)
+        elif name.endswith("running_var"):
+            sd[name] = 0.5 + torch.rand(shape, generator=g)
+        elif name.endswith("running_mean") or name.endswith(".bias"):
+            sd[name] = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:                       # BN gamma
+            sd[name] = 0.6 + 0.2 * torch.rand(shape, generator=g)
+        else:                                       # conv weight
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[name] = torch.randn(shape, generator=g) * math.sqrt(1.0 / fan_in)
+    return sd
+
+
+def make_stage4_inputs(n_images: int, base_res: int = 64, seed: int = 1):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.relu(torch.randn(n_images, c, base_res >> b, base_res >> b, generator=g))
+            for b, c in enumerate((40, 80, 160, 320))]

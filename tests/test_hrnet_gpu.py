@@ -1,0 +1,101 @@
+"""HRNet-W40 stage 4: implicit-GEMM convolutions and the whole stage against the fp32 oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import poem_oracle as orc  # noqa: E402
+from poem_v2_b200 import _native as nat  # noqa: E402
+from poem_v2_b200 import synth  # noqa: E402
+from poem_v2_b200.hrnet import HRNetStage4  # noqa: E402
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+@pytest.mark.parametrize("N,R,cin,cout,k,stride,relu,res", [
+    (2, 64, 40, 40, 3, 1, True, False),
+    (2, 32, 80, 80, 3, 1, True, True),
+    (3, 16, 160, 160, 3, 1, False, True),
+    (3, 8, 320, 320, 3, 1, True, True),      # 64 pixels per image: two images per 128-row tile, odd image count
+    (2, 64, 40, 80, 3, 2, False, False),     # fuse-layer downsampling, last conv of a chain
+    (2, 32, 40, 40, 3, 2, True, False),
+    (2, 16, 160, 320, 3, 2, False, False),
+    (2, 8, 320, 40, 1, 1, False, False),     # fuse-layer 1x1 (upsampled later)
+    (2, 32, 80, 40, 1, 1, False, False),
+])
+def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res):
+    lib = nat.load()
+    g = torch.Generator().manual_seed(R * 7 + cin + cout + k)
+    cin_p, cout_p = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
+    x = torch.randn(N, cin, R, R, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = 0.1 * torch.randn(cout, generator=g)
+    Ro = R // stride
+    r = torch.randn(N, cout, Ro, Ro, generator=g).bfloat16().float() if res else None
+    xp = torch.zeros(N, R, R, cin_p)
+    xp[..., :cin] = x.permute(0, 2, 3, 1)
+    wp = torch.zeros(cout_p, k, k, cin_p)
+    wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
+    bp = torch.zeros(cout_p)
+    bp[:cout] = b
+    rp = None
+    if res:
+        rp = torch.zeros(N, Ro, Ro, cout_p)
+        rp[..., :cout] = r.permute(0, 2, 3, 1)
+    d = [t.bfloat16().contiguous().cuda() if t is not None else None for t in (xp, wp.reshape(cout_p, -1), rp)]
+    bd = bp.cuda()
+    out = torch.full((N, Ro, Ro, cout_p), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nat.check(lib.poem_conv_nhwc(_p(d[0]), N, R, R, cin_p, _p(d[1]), _p(bd), cout_p, k, stride, int(relu), _p(d[2]),
+                                 _p(out), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x, w, b, stride=stride, padding=k // 2)
+    if res:
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got[..., cout:] == 0).all()                                  # padded channels stay exactly zero
+    err = (got[..., :cout].permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err <= 1e-2 * max(1.0, ref.abs().max().item())                # bf16 output rounding, fp32 accumulation
+
+
+@pytest.mark.parametrize("N", [2, 5])
+def test_stage4_matches_oracle(N):
+    sd = synth.make_stage4_state_dict(0)
+    xs = synth.make_stage4_inputs(N, 64, 1)
+    with torch.no_grad():
+        want = orc.hrnet_stage4(sd, xs)
+    m = HRNetStage4()
+    m.load_state_dict(sd, strict=True)
+    got = m([x.cuda() for x in xs])
+    for b, (g_, w_) in enumerate(zip(got, want)):
+        g_ = g_.cpu()
+        assert g_.shape == w_.shape and torch.isfinite(g_).all()
+        err = (g_ - w_).abs()
+        scale = w_.abs().max().item()
+        print(f"stage4 N={N} branch {b}: max err {err.max().item():.4f} mean err {err.mean().item():.5f} "
+              f"(|ref| max {scale:.2f}, mean {w_.abs().mean().item():.3f})")
+        # 3 modules x (8 bf16 convs per branch + fuse) with bf16 activations in between: 3e-2 of the output range
+        assert err.max().item() <= 3e-2 * scale
+        assert err.mean().item() <= 3e-3 * scale
+
+
+def test_stage4_matches_reference_golden():
+    import ast
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hrnet_stage4_n2.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    sd = synth.make_stage4_state_dict(meta["wseed"])
+    xs = synth.make_stage4_inputs(meta["n_images"], 64, meta["iseed"])
+    m = HRNetStage4()
+    m.load_state_dict(sd, strict=True)
+    got = [g.cpu() for g in m([x.cuda() for x in xs])]
+    want = [torch.from_numpy(z[f"y{b}"]) for b in range(4)]
+    sub = [got[0][:, :, ::4, ::4], got[1][:, :, ::2, ::2], got[2], got[3]]
+    for g_, w_ in zip(sub, want):
+        assert (g_ - w_).abs().max().item() <= 3e-2 * w_.abs().max().item()

@@ -43,3 +43,19 @@ def test_view_regroup_is_a_reinterpretation():
         f = pp * N * D + nn_ * D + dd
         n, d, p = f // (D * P), (f // P) % D, f % P
         assert q[0, pp, nn_, dd] == s[n, d, p]
+
+
+def test_hrnet_stage4_oracle_matches_reference_golden():
+    """oracle.hrnet_stage4 vs the real reference `HighResolutionModule` x3 (tests/golden/hrnet_stage4_n2.npz)."""
+    import ast
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hrnet_stage4_n2.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    sd = synth.make_stage4_state_dict(meta["wseed"])
+    xs = synth.make_stage4_inputs(meta["n_images"], 64, meta["iseed"])
+    with torch.no_grad():
+        ys = orc.hrnet_stage4(sd, xs)
+    sub = [ys[0][:, :, ::4, ::4], ys[1][:, :, ::2, ::2], ys[2], ys[3]]
+    for b in range(4):
+        assert torch.allclose(sub[b], torch.from_numpy(z[f"y{b}"]), atol=1e-5)
