@@ -35,7 +35,8 @@ struct ConvOperand {
 
 struct GemmEpilogue {
   const float* bias;   // [N] or nullptr
-  int act;
+  int act;             // applied before the residual
+  int act_after_res;   // applied after the residual (row-major path only)
   int res_mode;
   const float* res_f32;
   const __nv_bfloat16* res_bf16;
@@ -338,6 +339,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 v[2 * j] = v[2 * j] * rscale[i] + f.x;
                 v[2 * j + 1] = v[2 * j + 1] * rscale[i] + f.y;
               }
+            }
+            if (ep.act_after_res == ACT_RELU) {   // BasicBlock: relu(bn2(conv2(.)) + identity)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (ep.out_f32 != nullptr) {
               float4* o = reinterpret_cast<float4*>(ep.out_f32 + (size_t)mrow[i] * ep.ld_f32 + n + cg);

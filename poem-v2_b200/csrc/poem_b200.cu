@@ -283,7 +283,8 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   POEM_TRY(make_tmap_bf16(&tw, wt.w, (uint64_t)Cout_p, (uint64_t)K, (uint64_t)K, GEMM_BK, (uint32_t)BN));
   GemmEpilogue e = epi_default(Cout_p);
   e.bias = wt.b;
-  e.act = relu ? ACT_RELU : ACT_NONE;
+  e.act = (relu && !res) ? ACT_RELU : ACT_NONE;
+  e.act_after_res = (relu && res) ? ACT_RELU : ACT_NONE;
   if (res) {
     e.res_mode = RES_BF16;
     e.res_bf16 = res;
