@@ -108,6 +108,9 @@ typedef struct PoemWeights {
   const float* anchor_xyz;      /* fp32 [32,3] (assets/anchor.npy) */
   const int32_t* anchor_idx;    /* int32 [32]  (assets/anchor_idx.npy) */
   const float* template_xyz;    /* fp32 [Q,3]  MANO zero-pose template, joints then vertices */
+  const int32_t* bps_perm;      /* optional int32 [P]: BPS indices in k-d chunk order of bps / radius (32-NN pruning) */
+  const float* bps_chunk_box;   /* optional fp32 [P/32, 6]: (min xyz, max xyz) of each 32-point chunk of that order,
+                                   in normalised units, grown by 1e-4; NULL -> brute-force 32-NN */
   PoemBlock blocks[POEM_MAX_BLOCKS];
 } PoemWeights;
 
@@ -204,6 +207,11 @@ int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poe
 /* idx int32 [B, Lq, 32]: 32 nearest reference points, ascending squared-L2, lower index wins ties.
  * Replaces pytorch3d.ops.knn_points(K=32) (point_transformers.py:83,134). */
 int poem_knn32(const float* query_xyz, const float* ref_xyz, int32_t* idx, int B, int Lq, int Lr, void* stream);
+
+/* Same result as poem_knn32 for a reference set that is (up to rounding) the fixed BPS: perm / boxes as in PoemWeights;
+ * ref_xyz_sorted[b][k] = ref_xyz[b][perm[k]] (chunk order). */
+int poem_knn32_bps(const float* query_xyz, const float* ref_xyz_sorted, const int32_t* perm, const float* boxes,
+                   int32_t* idx, int B, int Lq, int Lr, void* stream);
 
 /* Camera projection + bilinear sampling in the reference's reinterpreted (token, view, channel) row order.
  * xmap fp32 [n_images, D, fh*fw]; X bf16 [sum_views*P, D].  Replaces collation.py:48-65 + F.grid_sample +

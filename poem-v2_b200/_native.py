@@ -77,7 +77,8 @@ class PoemWeights(C.Structure):
     _fields_ = [("input_proj", PoemLinear), ("pos_table", C.c_void_p), ("merge0a", PoemLinear),
                 ("merge0b", PoemLinear), ("merge1a", PoemLinear), ("merge1b", PoemLinear), ("query_embed", C.c_void_p),
                 ("bps", C.c_void_p), ("anchor_xyz", C.c_void_p), ("anchor_idx", C.c_void_p),
-                ("template_xyz", C.c_void_p), ("blocks", PoemBlock * POEM_MAX_BLOCKS)]
+                ("template_xyz", C.c_void_p), ("bps_perm", C.c_void_p), ("bps_chunk_box", C.c_void_p),
+                ("blocks", PoemBlock * POEM_MAX_BLOCKS)]
 
 
 POEM_HR_MAX_MODULES = 4
@@ -102,7 +103,7 @@ EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_
            "poem_profile_summary", "poem_debug_force_unfused", "poem_hrnet_stage4_workspace_bytes",
            "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
-           "poem_mha", "poem_knn32", "poem_project_sample", "poem_vector_attention",
+           "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
 
 _lib = None
@@ -150,6 +151,8 @@ def load():
     lib.poem_linear.argtypes = [vp, i, vp, i, vp, i, i, i, i, vp, i, vp, i, vp, i, vp]
     lib.poem_mha.restype = i
     lib.poem_mha.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, i, vp]
+    lib.poem_knn32_bps.restype = i
+    lib.poem_knn32_bps.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.poem_knn32.restype = i
     lib.poem_knn32.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.poem_project_sample.restype = i

@@ -508,6 +508,21 @@ static int launch_knn(const float* q, const float* r, int* idx, int B, int Lq, i
   LAUNCH_CHECK("knn32_kernel");
   return POEM_OK;
 }
+static int launch_knn_bps(const float* q, const float* r, const int* perm, const float* boxes, int* idx, int B, int Lq,
+                          int Lr, cudaStream_t st) {
+  if (Lr % 32 || Lr > 4096 || Lr < 32) return fail(POEM_E_BADDIM, "knn_bps: Lr=%d must be a multiple of 32, <= 4096", Lr);
+  const int total = B * Lq;
+  const int threads = 256;
+  prof_begin(st);
+  knn32_bps_kernel<<<(total * 32 + threads - 1) / threads, threads, 0, st>>>(q, r, perm, boxes, idx, Lq, Lr, total);
+  LAUNCH_CHECK("knn32_bps_kernel");
+  return POEM_OK;
+}
+extern "C" int poem_knn32_bps(const float* query_xyz, const float* ref_xyz, const int32_t* perm, const float* boxes,
+                              int32_t* idx, int B, int Lq, int Lr, void* stream) {
+  if (!query_xyz || !ref_xyz || !perm || !boxes || !idx) return fail(POEM_E_NULL, "knn_bps: null pointer");
+  return launch_knn_bps(query_xyz, ref_xyz, perm, boxes, idx, B, Lq, Lr, (cudaStream_t)stream);
+}
 extern "C" int poem_knn32(const float* query_xyz, const float* ref_xyz, int32_t* idx, int B, int Lq, int Lr,
                           void* stream) {
   if (!query_xyz || !ref_xyz || !idx) return fail(POEM_E_NULL, "knn: null pointer");
@@ -731,7 +746,7 @@ extern "C" int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, i
 // whole path
 // ------------------------------------------------------------------------------------------------
 struct BlockPlan {   // decoder blocks (PtEmbedTRv4)
-  float *pt_xyz, *xyz;  // xyz: (NB+1) buffers of B*Q*3
+  float *pt_xyz, *pt_xyz_sorted, *xyz;  // xyz: (NB+1) buffers of B*Q*3; pt_xyz_sorted: BPS in k-d chunk order
   __nv_bfloat16 *ptf, *KK, *VT;
   float *qf32, *qe32, *tmp32, *a1_32, *a2_32, *f1_32, *f2_32;
   __nv_bfloat16 *qf16, *qe16, *qp16, *ctx16, *a1_16, *a2_16, *qkv16, *res16, *f1_16, *qc16, *f2_16, *r1_16, *ffn16;
@@ -764,6 +779,7 @@ static void plan_blocks(const PoemDims* d, int B, Bump& b, BlockPlan* p) {
   const size_t D = d->embed_dims, P = d->n_sample, Q = d->n_query;
   const size_t BP = (size_t)B * P, BQ = (size_t)B * Q, T = BQ * 32;
   p->pt_xyz = b.take<float>(BP * 3);
+  p->pt_xyz_sorted = b.take<float>(BP * 3);
   p->xyz = b.take<float>((size_t)(d->n_blocks + 1) * BQ * 3);
   p->ptf = b.take<__nv_bfloat16>(BP * D);
   p->KK = b.take<__nv_bfloat16>(BP * 4 * D);
@@ -851,7 +867,7 @@ static int linear(const char* tag, const __nv_bfloat16* A, int lda, const PoemLi
 // a8-a13: the NB decoder blocks. Expects p.ptf (bf16 BPS features), p.pt_xyz, p.xyz[0], p.qf32/p.qf16 filled.
 // coords_out[i] = nan_to_num(xyz_i) * radius + centre when centre != NULL, else the raw normalised xyz_i.
 static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const BlockPlan& p, const float* centre,
-                      float* coords_out, float* out_feats, cudaStream_t st) {
+                      float* coords_out, float* out_feats, bool pt_is_bps, cudaStream_t st) {
   const int D = dims->embed_dims, P = dims->n_sample, Q = dims->n_query, NB = dims->n_blocks;
   const int BQ = B * Q, BP = B * P;
   for (int i = 0; i < NB; ++i) {
@@ -893,7 +909,12 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
     POEM_TRY(linear("va_fc2", p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
     // vector cross-attention (queries <- BPS tokens)
     POEM_TRY(linear("va_cross_q", p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
-    if (!anchors) POEM_TRY(launch_knn(xyz_in, p.pt_xyz, p.idx_cross, B, Q, P, st));
+    if (!anchors) {
+      if (pt_is_bps && w->bps_perm && w->bps_chunk_box)
+        POEM_TRY(launch_knn_bps(xyz_in, p.pt_xyz_sorted, w->bps_perm, w->bps_chunk_box, p.idx_cross, B, Q, P, st));
+      else
+        POEM_TRY(launch_knn(xyz_in, p.pt_xyz, p.idx_cross, B, Q, P, st));
+    }
     POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 4 * D, p.KK + 3 * D, 4 * D, xyz_in,
                                      p.pt_xyz, anchors ? nullptr : p.idx_cross, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, P, D, p.res16, p.t0, p.t1, p.t2, st));
@@ -946,7 +967,7 @@ extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights*
   prof_begin(st);
   f32_to_bf16_kernel<<<(unsigned)((BP * D + 255) / 256), 256, 0, st>>>(pt_feats, p.ptf, BP * D);
   LAUNCH_CHECK("f32_to_bf16_kernel");
-  return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, st);
+  return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, /*pt_is_bps=*/false, st);
 }
 
 extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
@@ -1005,7 +1026,8 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
     const int total = B * (P + Q) * 3;
     prof_begin(st);
     normalise_points_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->bps, w->template_xyz, h.centre, p.pt_xyz, p.xyz, P,
-                                                                Q, dims->radius, B);
+                                                                Q, dims->radius, B, w->bps_chunk_box ? w->bps_perm : nullptr,
+                                                                p.pt_xyz_sorted);
     LAUNCH_CHECK("normalise_points_kernel");
   }
   // ---- a4/a5 (+ the raw .view regroup of a6): X rows
@@ -1046,7 +1068,7 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
     LAUNCH_CHECK("broadcast_queries_kernel");
   }
   // ---- a8-a15
-  return run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, st);
+  return run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, /*pt_is_bps=*/true, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -290,6 +290,105 @@ __global__ void knn32_kernel(const float* __restrict__ query, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// 32-NN against the FIXED basis-point set (cross attention, point_transformers.py:134): same result as knn32_kernel,
+// but the 4096 BPS points are visited in a spatially sorted (Morton) order prepared at pack time, 32 per chunk, and a
+// chunk is skipped when the distance from the query to its bounding box already exceeds the current 32nd-best
+// distance.  The per-sample coordinates ((bps + c) - c) / r differ from the canonical bps / r only by rounding, so
+// the boxes are grown by 1e-4 at pack time; distances are still evaluated exactly on the per-sample coordinates
+// (passed in chunk order: ref_sorted[b][k] = ref[b][perm[k]]) and
+// ties are broken by the ORIGINAL index, so the output is bit-identical to the brute-force kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void knn32_bps_kernel(const float* __restrict__ query, const float* __restrict__ ref_sorted,
+                                 const int* __restrict__ perm, const float* __restrict__ boxes,
+                                 int* __restrict__ idx_out, int Lq, int Lr, int n_query_total) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (qi >= n_query_total) return;
+  const int b = qi / Lq;
+  const float qx = query[qi * 3 + 0], qy = query[qi * 3 + 1], qz = query[qi * 3 + 2];
+  const float* rb = ref_sorted + (size_t)b * Lr * 3;   // per-sample coordinates already in chunk order
+  const int n_chunks = Lr >> 5;          // Lr is a multiple of 32 (4096)
+  constexpr int SLOTS = 4;               // up to 128 chunks: lane l owns chunks l, l+32, l+64, l+96
+  float lb[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int c = s * 32 + lane;
+    float v = INFINITY;
+    if (c < n_chunks) {
+      const float* bx = boxes + c * 6;
+      const float dx = fmaxf(fmaxf(bx[0] - qx, qx - bx[3]), 0.f);
+      const float dy = fmaxf(fmaxf(bx[1] - qy, qy - bx[4]), 0.f);
+      const float dz = fmaxf(fmaxf(bx[2] - qz, qz - bx[5]), 0.f);
+      v = (dx * dx + dy * dy + dz * dz) * 0.9999f;   // strict lower bound of any true distance in the chunk
+    }
+    lb[s] = v;
+  }
+  float best_d = INFINITY;   // lane l holds the (l+1)-th smallest so far, ordered by (distance, original index)
+  int best_i = -1;
+
+  auto scan_chunk = [&](int c) {
+    const int k = c * 32 + lane;
+    const int oi = perm[k];
+    const float dx = __fsub_rn(qx, rb[k * 3 + 0]);
+    const float dy = __fsub_rn(qy, rb[k * 3 + 1]);
+    const float dz = __fsub_rn(qz, rb[k * 3 + 2]);
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    float thr_d = __shfl_sync(0xffffffffu, best_d, 31);
+    int thr_i = __shfl_sync(0xffffffffu, best_i, 31);
+    unsigned cand = __ballot_sync(0xffffffffu, d < thr_d || (d == thr_d && oi < thr_i));
+    while (cand) {
+      const int src = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float cd = __shfl_sync(0xffffffffu, d, src);
+      const int ci = __shfl_sync(0xffffffffu, oi, src);
+      if (cd < thr_d || (cd == thr_d && ci < thr_i)) {   // warp-uniform
+        const unsigned before = __ballot_sync(0xffffffffu, best_d < cd || (best_d == cd && best_i < ci));
+        const int pos = __popc(before);
+        const float up_d = __shfl_up_sync(0xffffffffu, best_d, 1);
+        const int up_i = __shfl_up_sync(0xffffffffu, best_i, 1);
+        if (lane > pos) {
+          best_d = up_d;
+          best_i = up_i;
+        } else if (lane == pos) {
+          best_d = cd;
+          best_i = ci;
+        }
+        thr_d = __shfl_sync(0xffffffffu, best_d, 31);
+        thr_i = __shfl_sync(0xffffffffu, best_i, 31);
+      }
+    }
+  };
+
+  // start with the chunk whose box is closest to the query: it fills the list with nearby points
+  float mn = fminf(fminf(lb[0], lb[1]), fminf(lb[2], lb[3]));
+  int arg = (mn == lb[0]) ? lane : (mn == lb[1]) ? 32 + lane : (mn == lb[2]) ? 64 + lane : 96 + lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mn, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om < mn || (om == mn && oa < arg)) {
+      mn = om;
+      arg = oa;
+    }
+  }
+  const int first = arg;
+  scan_chunk(first);
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    float thr = __shfl_sync(0xffffffffu, best_d, 31);
+    unsigned todo = __ballot_sync(0xffffffffu, lb[s] <= thr && (s * 32 + lane) != first && (s * 32 + lane) < n_chunks);
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      thr = __shfl_sync(0xffffffffu, best_d, 31);
+      const float l_lb = __shfl_sync(0xffffffffu, lb[s], l);
+      if (l_lb <= thr) scan_chunk(s * 32 + l);      // warp-uniform re-check against the tightened threshold
+    }
+  }
+  idx_out[(size_t)qi * 32 + lane] = best_i;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Vector attention (Point-Transformer layer) glue, un-fused variant (token tensors in HBM):
 //   tokens t = (b, i, j), j < 32 neighbours.  reference: point_transformers.py:86-95,139-151
 // ------------------------------------------------------------------------------------------------
@@ -427,7 +526,8 @@ __global__ void reg_out_kernel(const __nv_bfloat16* __restrict__ h, const float*
 // (ptEmb_head.py:808,896-897,933-934)
 __global__ void normalise_points_kernel(const float* __restrict__ bps, const float* __restrict__ templ,
                                         const float* __restrict__ centre, float* __restrict__ pt_xyz,
-                                        float* __restrict__ q_xyz, int P, int Q, float radius, int B) {
+                                        float* __restrict__ q_xyz, int P, int Q, float radius, int B,
+                                        const int* __restrict__ perm, float* __restrict__ pt_xyz_sorted) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = (P + Q) * 3;
   if (gid >= B * per) return;
@@ -435,6 +535,11 @@ __global__ void normalise_points_kernel(const float* __restrict__ bps, const flo
   if (r < P * 3) {
     const float c = centre[b * 3 + r % 3];
     pt_xyz[(size_t)b * P * 3 + r] = __fdiv_rn(__fsub_rn(__fadd_rn(bps[r], c), c), radius);
+    if (perm != nullptr) {   // the same value of point perm[k], stored at chunk-order position k (32-NN pruning)
+      const int k = r / 3, a = r - k * 3;
+      const float cc = centre[b * 3 + a];
+      pt_xyz_sorted[(size_t)b * P * 3 + r] = __fdiv_rn(__fsub_rn(__fadd_rn(bps[perm[k] * 3 + a], cc), cc), radius);
+    }
   } else {
     const int k = r - P * 3;
     const float c = centre[b * 3 + k % 3];

@@ -42,6 +42,29 @@ def sine_pos_3d(n_views, h, w, num_feats, normalize=True, temperature=10000.0, s
     return out
 
 
+def bps_spatial_chunks(bps, radius, grow=1e-4):
+    """k-d partition of the basis points into compact 32-point chunks: returns the permutation (chunk-major order,
+    int32 [P]) and each chunk's bounding box (fp32 [P/32, 6] = min xyz, max xyz; normalised units, grown by `grow` to
+    absorb the per-sample rounding of ((bps + c) - c) / r).  P must be 32 * 2^k."""
+    x = bps.detach().cpu().double() / radius
+    order = torch.arange(x.shape[0])
+
+    def split(idx):
+        if idx.numel() <= 32:
+            return [idx]
+        pts = x[idx]
+        axis = int((pts.max(dim=0).values - pts.min(dim=0).values).argmax())
+        srt = idx[torch.argsort(pts[:, axis], stable=True)]
+        half = srt.numel() // 2
+        return split(srt[:half]) + split(srt[half:])
+    leaves = split(order)
+    assert all(l.numel() == 32 for l in leaves), "basis point count must be 32 * 2^k"
+    perm = torch.cat(leaves)
+    pts = x[perm].reshape(-1, 32, 3)
+    boxes = torch.cat([pts.min(dim=1).values - grow, pts.max(dim=1).values + grow], dim=1)
+    return perm.to(torch.int32), boxes.float()
+
+
 class PackedWeights:
     """Owns the device tensors referenced by the ctypes `PoemWeights` struct."""
 
@@ -67,6 +90,9 @@ class PackedWeights:
         W.anchor_idx = self._i32(anchor_idx.reshape(-1))
         assert template_xyz.shape == (dims.n_query, 3)
         W.template_xyz = self._f32(template_xyz)
+        perm, boxes = bps_spatial_chunks(bps.reshape(-1, 3), dims.radius)
+        W.bps_perm = self._i32(perm)
+        W.bps_chunk_box = self._f32(boxes)
         for i in range(dims.n_blocks):
             self._pack_block(W.blocks[i], f64, f"transformer.pt_metro_encoder.{i}.")
 

@@ -115,6 +115,35 @@ def test_knn32_bit_exact(lib, B, Lq, Lr):
     assert torch.equal(idx.cpu().long(), want)               # index work: bit-exact, order included
 
 
+@pytest.mark.parametrize("case", ["bps", "random_with_ties", "far_queries"])
+def test_knn32_bps_pruned_matches_brute_force(lib, case):
+    """The spatially pruned kernel (Morton chunks + bounding boxes) must return exactly what the oracle returns."""
+    from poem_v2_b200.pack import bps_spatial_chunks
+    g = torch.Generator().manual_seed(11)
+    B, Lq, Lr = 3, 799, 4096
+    bps, _, _ = synth.load_assets()
+    if case == "random_with_ties":
+        base = torch.rand(Lr, 3, generator=g) * 2 - 1
+        base[7] = base[3]
+        base[4000] = base[3]
+        perm, boxes = bps_spatial_chunks(base, 1.0)
+        ref = base[None].repeat(B, 1, 1)
+        qry = base[None, :Lq].repeat(B, 1, 1).clone()
+        qry[1] += 0.01 * torch.randn(Lq, 3, generator=g)
+    else:
+        perm, boxes = bps_spatial_chunks(bps, 0.1)
+        centre = torch.tensor([[0.01, -0.02, 0.6], [0.3, 0.2, 0.55], [-0.1, 0.05, 0.7]])
+        ref = ((bps[None] + centre[:, None]) - centre[:, None]) / 0.1          # per-sample rounding, as in the head
+        scale = 0.5 if case == "bps" else 3.0                                  # far: most queries outside the ball
+        qry = torch.randn(B, Lq, 3, generator=g) * scale
+    idx = torch.full((B, Lq, 32), -7, dtype=torch.int32, device="cuda")
+    ref_sorted = ref[:, perm.long()].contiguous()                               # chunk order, per sample
+    dv = [qry.cuda(), ref_sorted.cuda(), perm.cuda(), boxes.cuda()]
+    nat.check(lib.poem_knn32_bps(_p(dv[0]), _p(dv[1]), _p(dv[2]), _p(dv[3]), _p(idx), B, Lq, Lr, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu().long(), orc.knn(qry, ref, 32))
+
+
 # ------------------------------------------------------------------------------------------ sampler
 @pytest.mark.parametrize("D,views", [(128, [2]), (256, [3, 1, 2]), (512, [1])])
 def test_project_sample(lib, D, views):
