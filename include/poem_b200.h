@@ -198,10 +198,10 @@ int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const 
                 int act, const float* residual, int ld_res, float* out_f32, int ld_f32, poem_bf16* out_bf16,
                 int ld_bf16, void* stream);
 
-/* softmax(Q K^T / sqrt(hd)) V per head, no mask.  Q bf16 [B*Lq, ldq], K bf16 [B*Lk, ldk],
- * Vt bf16 [B, D, Lk] (value projection stored transposed), ctx bf16 [B*Lq, ld_ctx].  Lk % 128 == 0.
+/* softmax(Q K^T / sqrt(hd)) V per head, no mask.  Q bf16 [B*Lq, ldq], K bf16 [B*Lk, ldk], V bf16 [B*Lk, ldv] (all
+ * row-major, head h in columns [h*hd, (h+1)*hd)), ctx bf16 [B*Lq, ld_ctx].  Lk % 128 == 0.
  * Replaces HF BertSelfAttention's matmul-softmax-matmul (pt_metro_transformer.py:57-72). */
-int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* Vt, poem_bf16* ctx,
+int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* V, int ldv, poem_bf16* ctx,
              int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream);
 
 /* idx int32 [B, Lq, 32]: 32 nearest reference points, ascending squared-L2, lower index wins ties.

@@ -150,7 +150,7 @@ def load():
     lib.poem_linear.restype = i
     lib.poem_linear.argtypes = [vp, i, vp, i, vp, i, i, i, i, vp, i, vp, i, vp, i, vp]
     lib.poem_mha.restype = i
-    lib.poem_mha.argtypes = [vp, i, vp, i, vp, vp, i, i, i, i, i, i, vp]
+    lib.poem_mha.argtypes = [vp, i, vp, i, vp, i, vp, i, i, i, i, i, i, vp]
     lib.poem_knn32_bps.restype = i
     lib.poem_knn32_bps.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
     lib.poem_knn32.restype = i

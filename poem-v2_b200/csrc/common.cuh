@@ -143,8 +143,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // Instruction descriptor for kind::f16 with BF16 A/B, FP32 accumulator, K-major A and B.
 //   bits [4,6) c_format=1 (F32); [7,10) a_format=1 (BF16); [10,13) b_format=1 (BF16);
 //   bit 15 a_major=0 (K), bit 16 b_major=0 (K); [17,23) N>>3; [24,29) M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Shared-memory descriptor of an MN-major operand tile stored as [K rows x kRowBytes] (each K row holds kRowBytes/2
+// consecutive MN elements; 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), rows packed back to back:
+//   canonical layout ((8 x16B, n), (8, k)) : ((1, LBO), (kRowBytes/16, SBO))  ->  SBO = 8 rows, LBO = next MN atom.
+template <uint32_t kRowBytes>
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  static_assert(kRowBytes == 128 || kRowBytes == 64, "row must be one swizzle atom wide");
+  constexpr uint64_t layout = (kRowBytes == 128) ? 2ull : 4ull;
+  constexpr uint64_t sbo = (8u * kRowBytes) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (sbo << 32) |
+         (1ull << 46) | (layout << 61);
 }
 
 // Shared-memory matrix descriptor, K-major operand, dense rows of `kRowBytes` (128 -> SWIZZLE_128B,

@@ -9,7 +9,8 @@
 //   S(j) buffer, so 256 TMEM columns hold two S buffers and the P·V result (2 CTAs per SM for HD <= 64)
 //   O_blk(j) is folded into the register accumulator (online-softmax rescale) one iteration later, while the
 //   tensor core already works on S(j+2) / P·V(j+1): the softmax warps never wait for an MMA in steady state.
-// Q/K tiles [rows x HD] and V^T tiles [HD x 64 keys] are staged by TMA; K and V rings are 2 deep.
+// Q/K/V tiles [rows x HD] are staged by TMA as they lie in memory; V is consumed as an MN-major B operand (no
+// transposed copy of the value projection is needed); K and V rings are 2 deep.
 // warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = softmax + output.
 #pragma once
 #include "common.cuh"
@@ -26,7 +27,7 @@ struct MhaCfg {
   static constexpr int kKBlocks = (HD * 2) / kRowBytes;          // 64-element K blocks of the head dim (1 or 2)
   static constexpr int kQBytes = MHA_BQ * HD * 2;
   static constexpr int kKBytes = MHA_BKEY * HD * 2;
-  static constexpr int kVBytes = HD * MHA_BKEY * 2;              // two [HD x 64 keys] SWIZZLE_128B tiles
+  static constexpr int kVBytes = MHA_BKEY * HD * 2;              // kKBlocks tiles of [128 keys x kRowBytes]
   static constexpr int kPBytes = MHA_BQ * MHA_BKEY * 2;          // two [128 x 64 keys] SWIZZLE_128B tiles
   static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 256;
   static constexpr int kTmemCols = 256;                          // two S buffers; O_blk aliases the consumed one
@@ -36,9 +37,9 @@ template <int HD>
 __global__ void __launch_bounds__(MHA_THREADS, (HD <= 64) ? 2 : 1)
 mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, ldq] bf16, box [HD(or 64) x 128]
                   const __grid_constant__ CUtensorMap tmap_k,   // [B*Lk rows, ldk] bf16, box [HD(or 64) x 128]
-                  const __grid_constant__ CUtensorMap tmap_vt,  // [B*vt_batch_rows, Lk] bf16, box [64 keys x HD]
-                  __nv_bfloat16* __restrict__ ctx, int ld_ctx, int Lq, int Lk, int vt_batch_rows, int q_col0,
-                  int k_col0, int vt_row0, float scale_log2e) {
+                  const __grid_constant__ CUtensorMap tmap_v,   // [B*Lk rows, ldv] bf16, box [HD(or 64) x 128]
+                  __nv_bfloat16* __restrict__ ctx, int ld_ctx, int Lq, int Lk, int q_col0, int k_col0, int v_col0,
+                  float scale_log2e) {
   using Cfg = MhaCfg<HD>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -69,7 +70,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_vt);
+    tma_prefetch_desc(&tmap_v);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -110,16 +111,16 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
                       k_col0 + head * HD + kb * 64, b * Lk + j * MHA_BKEY);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], Cfg::kVBytes);
-        for (int kb = 0; kb < 2; ++kb)
-          tma_load_2d(sV + st * Cfg::kVBytes + kb * (HD * 128), &tmap_vt, &v_full[st], j * MHA_BKEY + kb * 64,
-                      vt_row0 + b * vt_batch_rows + head * HD);
+        for (int kb = 0; kb < Cfg::kKBlocks; ++kb)
+          tma_load_2d(sV + st * Cfg::kVBytes + kb * (MHA_BKEY * Cfg::kRowBytes), &tmap_v, &v_full[st],
+                      v_col0 + head * HD + kb * 64, b * Lk + j * MHA_BKEY);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(MHA_BQ, MHA_BKEY);
-      constexpr uint32_t idesc_o = make_idesc_bf16(MHA_BQ, HD);
+      constexpr uint32_t idesc_o = make_idesc_bf16(MHA_BQ, HD, /*b_mn_major=*/1);
       auto issue_S = [&](int j) {   // S(j) -> TMEM buffer j%2, from K stage j%2
         const int st = j & 1;
         mbar_wait(&k_full[st], (uint32_t)(j >> 1) & 1);
@@ -146,12 +147,13 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         mbar_wait(&v_full[st], ph);
         tc_fence_after_sync();
         const uint32_t v_addr = smem_u32(sV + st * Cfg::kVBytes);
+        // O_blk[128 x HD] = P[128 x 128 keys] (K-major) · V[128 keys x HD] (MN-major: each key row holds HD values)
+        const uint64_t dv0 = make_mnmajor_desc<Cfg::kRowBytes>(v_addr, MHA_BKEY * Cfg::kRowBytes);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t dp = make_kmajor_desc<128>(smem_u32(sP) + kb * (MHA_BQ * 128));
-          const uint64_t dv = make_kmajor_desc<128>(v_addr + kb * (HD * 128));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + st * 128, dp + 2 * k, dv + 2 * k, idesc_o, (kb | k) != 0);
+        for (int ks = 0; ks < MHA_BKEY / 16; ++ks) {     // 16 keys per MMA
+          const uint64_t dp = make_kmajor_desc<128>(smem_u32(sP) + (ks >> 2) * (MHA_BQ * 128)) + 2 * (ks & 3);
+          const uint64_t dv = dv0 + (uint64_t)((ks * 16 * Cfg::kRowBytes) >> 4);
+          umma_bf16(tmem_base + st * 128, dp, dv, idesc_o, ks != 0);
         }
         umma_commit(&o_full[st]);
         umma_commit(&v_empty[st]);

@@ -448,8 +448,8 @@ extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int 
 // ------------------------------------------------------------------------------------------------
 template <int HD>
 static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, __nv_bfloat16* ctx,
-                         int ld_ctx, int B, int Lq, int Lk, int n_heads, int vt_batch_rows, int q_col0, int k_col0,
-                         int vt_row0, cudaStream_t st) {
+                         int ld_ctx, int B, int Lq, int Lk, int n_heads, int q_col0, int k_col0, int v_col0,
+                         cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(mha_fwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -459,17 +459,16 @@ static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   dim3 grid((Lq + MHA_BQ - 1) / MHA_BQ, n_heads, B);
   const float scale_log2e = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
   prof_begin(st);
-  mha_fwd_tc_kernel<HD><<<grid, MHA_THREADS, MhaCfg<HD>::kSmemBytes, st>>>(tq, tk, tv, ctx, ld_ctx, Lq, Lk,
-                                                                           vt_batch_rows, q_col0, k_col0, vt_row0,
-                                                                           scale_log2e);
+  mha_fwd_tc_kernel<HD><<<grid, MHA_THREADS, MhaCfg<HD>::kSmemBytes, st>>>(tq, tk, tv, ctx, ld_ctx, Lq, Lk, q_col0,
+                                                                           k_col0, v_col0, scale_log2e);
   LAUNCH_CHECK("mha_fwd_tc_kernel");
   return POEM_OK;
 }
 
-// Q [B*Lq, ldq] (columns q_col0..), K [B*Lk, ldk] (columns k_col0..), Vt [B*vt_batch_rows, Lk] (rows vt_row0.. per batch)
+// Q [B*Lq, ldq] (columns q_col0..), K [B*Lk, ldk] (columns k_col0..), V [B*Lk, ldv] (columns v_col0..); all row-major
 static int launch_mha(const __nv_bfloat16* Q, int ldq, int q_col0, const __nv_bfloat16* K, int ldk, int k_col0,
-                      const __nv_bfloat16* Vt, int vt_batch_rows, int vt_row0, __nv_bfloat16* ctx, int ld_ctx, int B,
-                      int Lq, int Lk, int D, int n_heads, cudaStream_t st) {
+                      const __nv_bfloat16* V, int ldv, int v_col0, __nv_bfloat16* ctx, int ld_ctx, int B, int Lq,
+                      int Lk, int D, int n_heads, cudaStream_t st) {
   if (D % n_heads) return fail(POEM_E_BADDIM, "mha: D %% heads != 0");
   const int hd = D / n_heads;
   if (Lk % MHA_BKEY) return fail(POEM_E_BADDIM, "mha: Lk=%d must be a multiple of %d", Lk, MHA_BKEY);
@@ -478,20 +477,20 @@ static int launch_mha(const __nv_bfloat16* Q, int ldq, int q_col0, const __nv_bf
   CUtensorMap tq, tk, tv;
   POEM_TRY(make_tmap_bf16(&tq, Q, (uint64_t)B * Lq, (uint64_t)ldq, (uint64_t)ldq, boxc, MHA_BQ));
   POEM_TRY(make_tmap_bf16(&tk, K, (uint64_t)B * Lk, (uint64_t)ldk, (uint64_t)ldk, boxc, MHA_BKEY));
-  POEM_TRY(make_tmap_bf16(&tv, Vt, (uint64_t)B * vt_batch_rows, (uint64_t)Lk, (uint64_t)Lk, 64, (uint32_t)hd));
+  POEM_TRY(make_tmap_bf16(&tv, V, (uint64_t)B * Lk, (uint64_t)ldv, (uint64_t)ldv, boxc, MHA_BKEY));
   switch (hd) {
-    case 32: return launch_mha_hd<32>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, vt_batch_rows, q_col0, k_col0, vt_row0, st);
-    case 64: return launch_mha_hd<64>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, vt_batch_rows, q_col0, k_col0, vt_row0, st);
-    case 128: return launch_mha_hd<128>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, vt_batch_rows, q_col0, k_col0, vt_row0, st);
+    case 32: return launch_mha_hd<32>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, q_col0, k_col0, v_col0, st);
+    case 64: return launch_mha_hd<64>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, q_col0, k_col0, v_col0, st);
+    case 128: return launch_mha_hd<128>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, q_col0, k_col0, v_col0, st);
     default: return fail(POEM_E_BADDIM, "mha: head dim %d unsupported (32, 64, 128)", hd);
   }
 }
 
-extern "C" int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* Vt, poem_bf16* ctx,
-                        int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream) {
-  if (!Q || !K || !Vt || !ctx) return fail(POEM_E_NULL, "mha: null pointer");
+extern "C" int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* V, int ldv,
+                        poem_bf16* ctx, int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream) {
+  if (!Q || !K || !V || !ctx) return fail(POEM_E_NULL, "mha: null pointer");
   return launch_mha(reinterpret_cast<const __nv_bfloat16*>(Q), ldq, 0, reinterpret_cast<const __nv_bfloat16*>(K), ldk,
-                    0, reinterpret_cast<const __nv_bfloat16*>(Vt), D, 0, reinterpret_cast<__nv_bfloat16*>(ctx), ld_ctx,
+                    0, reinterpret_cast<const __nv_bfloat16*>(V), ldv, 0, reinterpret_cast<__nv_bfloat16*>(ctx), ld_ctx,
                     B, Lq, Lk, D, n_heads, (cudaStream_t)stream);
 }
 
@@ -747,7 +746,7 @@ extern "C" int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, i
 // ------------------------------------------------------------------------------------------------
 struct BlockPlan {   // decoder blocks (PtEmbedTRv4)
   float *pt_xyz, *pt_xyz_sorted, *xyz;  // xyz: (NB+1) buffers of B*Q*3; pt_xyz_sorted: BPS in k-d chunk order
-  __nv_bfloat16 *ptf, *KK, *VT;
+  __nv_bfloat16 *ptf, *KK;   // KK: (B*P, 6D) = K1 | K2 | kt_cross | v_cross | V1 | V2
   float *qf32, *qe32, *tmp32, *a1_32, *a2_32, *f1_32, *f2_32;
   __nv_bfloat16 *qf16, *qe16, *qp16, *ctx16, *a1_16, *a2_16, *qkv16, *res16, *f1_16, *qc16, *f2_16, *r1_16, *ffn16;
   int *idx_self, *idx_cross;
@@ -782,8 +781,7 @@ static void plan_blocks(const PoemDims* d, int B, Bump& b, BlockPlan* p) {
   p->pt_xyz_sorted = b.take<float>(BP * 3);
   p->xyz = b.take<float>((size_t)(d->n_blocks + 1) * BQ * 3);
   p->ptf = b.take<__nv_bfloat16>(BP * D);
-  p->KK = b.take<__nv_bfloat16>(BP * 4 * D);
-  p->VT = b.take<__nv_bfloat16>(BP * 2 * D);
+  p->KK = b.take<__nv_bfloat16>(BP * 6 * D);
   p->qf32 = b.take<float>(BQ * D);
   p->qe32 = b.take<float>(BQ * D);
   p->tmp32 = b.take<float>(BQ * D);
@@ -874,29 +872,20 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
     const PoemBlock& k = w->blocks[i];
     float* xyz_in = p.xyz + (size_t)i * BQ * 3;
     float* xyz_out = p.xyz + (size_t)(i + 1) * BQ * 3;
-    // BPS-token projections: K1 | K2 | k' | v' row-major, V1 | V2 transposed per sample
+    // BPS-token projections in one GEMM: K1 | K2 | kt_cross | v_cross | V1 | V2, all row-major
     {
-      if (!k.pt_proj.w) return fail(POEM_E_NULL, "block %d: pt_proj missing", i);
-      GemmEpilogue e = epi_default(6 * D);
-      e.bias = k.pt_proj.b;
-      e.out_bf16 = p.KK;
-      e.ld_bf16 = 4 * D;
-      e.trans_from = 4 * D;
-      e.t_rows = P;
-      e.t_group_stride = (long long)2 * D * P;
-      e.out_t_bf16 = p.VT;
       TagScope ts("pt_proj");
-      POEM_TRY(launch_gemm(p.ptf, D, W16(k.pt_proj), D, BP, 6 * D, D, e, st));
+      POEM_TRY(linear("pt_proj", p.ptf, D, k.pt_proj, BP, 6 * D, D, ACT_NONE, nullptr, nullptr, p.KK, st));
     }
     POEM_TRY(linear("q_embed", p.qf16, D, k.embedding, BQ, D, D, ACT_NONE, nullptr, p.qe32, p.qe16, st));
     // MHA 1
     POEM_TRY(linear("mha_q", p.qe16, D, k.q1, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
-    POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 4 * D, 0, p.VT, 2 * D, 0, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
+    POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 6 * D, 0, p.KK, 6 * D, 4 * D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
     POEM_TRY(linear("mha_out", p.ctx16, D, k.o1, BQ, D, D, ACT_NONE, p.qe32, p.tmp32, nullptr, st));
     POEM_TRY(launch_layernorm(p.tmp32, k.ln1_g, k.ln1_b, p.a1_32, p.a1_16, BQ, D, st));
     // MHA 2
     POEM_TRY(linear("mha_q", p.a1_16, D, k.q2, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
-    POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 4 * D, D, p.VT, 2 * D, D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
+    POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 6 * D, D, p.KK, 6 * D, 5 * D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
     POEM_TRY(linear("mha_out", p.ctx16, D, k.o2, BQ, D, D, ACT_NONE, p.a1_32, p.tmp32, nullptr, st));
     POEM_TRY(launch_layernorm(p.tmp32, k.ln2_g, k.ln2_b, p.a2_32, p.a2_16, BQ, D, st));
     // vector self-attention
@@ -915,7 +904,7 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
       else
         POEM_TRY(launch_knn(xyz_in, p.pt_xyz, p.idx_cross, B, Q, P, st));
     }
-    POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 4 * D, p.KK + 3 * D, 4 * D, xyz_in,
+    POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 6 * D, p.KK + 3 * D, 6 * D, xyz_in,
                                      p.pt_xyz, anchors ? nullptr : p.idx_cross, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, P, D, p.res16, p.t0, p.t1, p.t2, st));
     POEM_TRY(linear("va_fc2", p.res16, D, k.cross_attn.fc2, BQ, D, D, ACT_NONE, p.f1_32, p.f2_32, p.f2_16, st));

@@ -83,9 +83,8 @@ def test_mha(lib, D, B, Lq, Lk):
     Q = torch.randn(B * Lq, D, device="cuda", generator=g).bfloat16()
     K = torch.randn(B * Lk, D, device="cuda", generator=g).bfloat16()
     V = torch.randn(B, Lk, D, device="cuda", generator=g).bfloat16()
-    Vt = V.transpose(1, 2).contiguous()                      # (B, D, Lk)
     ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
-    nat.check(lib.poem_mha(_p(Q), D, _p(K), D, _p(Vt), _p(ctx), D, B, Lq, Lk, D, h, _stream()))
+    nat.check(lib.poem_mha(_p(Q), D, _p(K), D, _p(V), D, _p(ctx), D, B, Lq, Lk, D, h, _stream()))
     torch.cuda.synchronize()
     q = Q.float().view(B, Lq, h, hd).transpose(1, 2)
     k = K.float().view(B, Lk, h, hd).transpose(1, 2)
