@@ -2,6 +2,9 @@
 //   A, W : bf16, K-major (row-major with K contiguous), staged by TMA (SWIZZLE_128B, 64-element K blocks)
 //   accumulate fp32 in TMEM (two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
 //   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two per TMEM lane quarter)
+//   W-stationary mode (whenever the [BN x K] weight slab fits in smem): every CTA keeps ONE n-tile for its whole
+//   life, loads its weight slab once and streams only A tiles through the ring -> L2->smem traffic per tile drops
+//   from (A + W) to A (the skinny-K GEMMs of this path are L2/HBM-bound, not MMA-bound).
 // Every Linear / 1x1-conv of the decoder path runs through this kernel (reference call sites: cuBLAS GEMMs
 // behind nn.Linear / nn.Conv2d(k=1) in lib/models/heads/ptEmb_head.py:94,755,760 and
 // lib/models/bricks/pt_metro_transformer.py:180-181, point_transformers.py:86-95,139-151).
@@ -31,6 +34,14 @@ struct ConvOperand {
   int stride;    // 1 or 2
   int cblocks;   // padded input channels / 64
   int Hout, Wout;
+};
+
+constexpr int GEMM_MAX_STAGES = 8;
+
+// Launch-time shape of the pipeline (computed on the host from the smem budget).
+struct GemmPipe {
+  int w_stationary;   // 1: weight slab resident in smem, ring holds A tiles only
+  int n_stages;       // ring depth (<= GEMM_MAX_STAGES)
 };
 
 struct GemmEpilogue {
@@ -71,7 +82,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kWBytes;
   static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_STAGE_LD * 4;   // per-epilogue-warp transpose tile
   static constexpr int kBiasBytes = 2 * BN * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 256 /*barriers*/;
+  static constexpr int kTailBytes = kStagingBytes + kBiasBytes + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;   // streaming mode
+  static constexpr int kSmemMax = 232448;                                 // 227 KB per CTA
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -80,26 +93,39 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
-                    int N, int K, GemmEpilogue ep, ConvOperand conv) {
+                    int N, int K, GemmEpilogue ep, ConvOperand conv, GemmPipe pipe) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
-  float* s_stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  float* s_bias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kBiasBytes);
-  uint64_t* full_bar = bars;                         // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;     // [2]
-  uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  // smem: [resident W slab (stationary mode)] [ring] [epilogue staging] [bias] [barriers]
+  const bool wst = pipe.w_stationary != 0;
+  const int n_stages = pipe.n_stages;
+  const int ring_stage_bytes = wst ? Cfg::kABytes : Cfg::kStageBytes;
+  uint8_t* s_wres = smem;
+  uint8_t* s_ring = smem + (wst ? k_blocks * Cfg::kWBytes : 0);
+  uint8_t* s_tail = s_ring + n_stages * ring_stage_bytes;
+  float* s_stage = reinterpret_cast<float*>(s_tail);
+  float* s_bias = reinterpret_cast<float*>(s_tail + Cfg::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + Cfg::kStagingBytes + Cfg::kBiasBytes);
+  uint64_t* full_bar = bars;                               // [GEMM_MAX_STAGES]
+  uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [GEMM_MAX_STAGES]
+  uint64_t* tmem_full = bars + 2 * GEMM_MAX_STAGES;        // [2]
+  uint64_t* tmem_empty = bars + 2 * GEMM_MAX_STAGES + 2;   // [2]
+  uint64_t* wres_full = bars + 2 * GEMM_MAX_STAGES + 4;    // resident weight slab landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 5);
+  // tile schedule. streaming: tile = blockIdx.x + i * gridDim.x over all (m, n) tiles, n fastest.
+  // stationary: this CTA owns n-tile blockIdx.x % tiles_n and walks m-tiles blockIdx.x / tiles_n + i * (gridDim.x / tiles_n)
+  const int it0 = wst ? (int)blockIdx.x / tiles_n : (int)blockIdx.x;
+  const int it_step = wst ? (int)gridDim.x / tiles_n : (int)gridDim.x;
+  const int it_end = wst ? tiles_m : num_tiles;
+  const int my_n_tile = (int)blockIdx.x % tiles_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -107,10 +133,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::kStages; ++s) {
+      for (int s = 0; s < n_stages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
+      mbar_init(wres_full, 1);
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full[s], 1);
         mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);  // one arrive per epilogue warp
@@ -130,14 +157,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * GEMM_BM;
-        const int n0 = (tile % tiles_n) * BN;
+      if (wst) {   // the whole [BN x K] weight slab of this CTA's n-tile, once
+        mbar_expect_tx(wres_full, (uint32_t)(k_blocks * Cfg::kWBytes));
+        for (int kb = 0; kb < k_blocks; ++kb)
+          tma_load_2d(s_wres + kb * Cfg::kWBytes, &tmap_w, wres_full, kb * GEMM_BK, my_n_tile * BN);
+      }
+      for (int it = it0; it < it_end; it += it_step) {
+        const int m0 = (wst ? it : it / tiles_n) * GEMM_BM;
+        const int n0 = (wst ? my_n_tile : it % tiles_n) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sa = s_ring + stage * ring_stage_bytes;
           uint8_t* sw = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)ring_stage_bytes);
           if (conv.enabled) {
             const int tap = kb / conv.cblocks, cc = kb - tap * conv.cblocks;
             const int ky = tap / conv.ksize, kx = tap - ky * conv.ksize;
@@ -147,8 +179,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
           }
-          tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0);
-          if (++stage == Cfg::kStages) {
+          if (!wst) tma_load_2d(sw, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0);
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -163,15 +195,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (wst) mbar_wait(wres_full, 0);
+      for (int it = it0; it < it_end; it += it_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sw = sa + Cfg::kABytes;
+          const uint32_t sa = smem_u32(s_ring + stage * ring_stage_bytes);
+          const uint32_t sw = wst ? smem_u32(s_wres + kb * Cfg::kWBytes) : sa + Cfg::kABytes;
           const uint64_t da = make_kmajor_desc<128>(sa);
           const uint64_t dw = make_kmajor_desc<128>(sw);
 #pragma unroll
@@ -180,7 +213,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             umma_bf16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == Cfg::kStages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -206,9 +239,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int cg = (lane & 3) * 8;     // first of this lane's 8 columns inside a 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * GEMM_BM;
-      const int n0 = (tile % tiles_n) * BN;
+    for (int it = it0; it < it_end; it += it_step) {
+      const int m0 = (wst ? it : it / tiles_n) * GEMM_BM;
+      const int n0 = (wst ? my_n_tile : it % tiles_n) * BN;
       // bias of this tile's columns -> smem (double buffered by accumulator stage)
       float* sb = s_bias + acc * BN;
       for (int j = threadIdx.x - 64; j < BN; j += 32 * GEMM_EPI_WARPS)

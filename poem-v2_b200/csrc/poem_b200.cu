@@ -195,16 +195,35 @@ struct Bump {
 template <int BN>
 static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, int N, int K, const GemmEpilogue& ep,
                           const ConvOperand& conv, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  GemmCfg<BN>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
     configured = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + BN - 1) / BN;
+  const int tiles = tiles_m * tiles_n;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  // W-stationary when the [BN x K] slab plus >= 3 A stages fit next to the epilogue staging, and every CTA gets
+  // at least two M tiles (otherwise the slab load is not amortised)
+  GemmPipe pipe;
+  const long long w_slab = (long long)k_blocks * Cfg::kWBytes;
+  const long long room = (long long)Cfg::kSmemMax - Cfg::kTailBytes - w_slab;
+  int grid, smem;
+  if (room >= 3 * Cfg::kABytes && tiles_n <= num_sms() && tiles_m >= 2 * (num_sms() / tiles_n)) {
+    pipe.w_stationary = 1;
+    pipe.n_stages = (int)(room / Cfg::kABytes);
+    if (pipe.n_stages > GEMM_MAX_STAGES) pipe.n_stages = GEMM_MAX_STAGES;
+    grid = (num_sms() / tiles_n) * tiles_n;
+    smem = (int)w_slab + pipe.n_stages * Cfg::kABytes + Cfg::kTailBytes;
+  } else {
+    pipe.w_stationary = 0;
+    pipe.n_stages = Cfg::kStages;
+    grid = tiles < num_sms() ? tiles : num_sms();
+    smem = Cfg::kSmemBytes;
+  }
   prof_begin(st);
-  gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, st>>>(ta, tw, M, N, K, ep, conv);
+  gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
   LAUNCH_CHECK("gemm_bf16_tc_kernel");
   return POEM_OK;
 }
