@@ -705,7 +705,8 @@ static int launch_vecattn_fused(const PoemVecAttn* w, const VaParams& prm, cudaS
   POEM_TRY(make_tmap_bf16(&t2, w->gamma1_delta2.w, D, D, D, 64, 128));
   POEM_TRY(make_tmap_bf16(&t3, w->gamma2.w, D, D, D, 64, 128));
   const int tiles = (prm.n_query + Cfg::QT - 1) / Cfg::QT;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int slots = num_sms() * Cfg::CTAS_PER_SM;
+  const int grid = tiles < slots ? tiles : slots;
   prof_begin(st);
   va_fused_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t1, t2, t3, prm);
   LAUNCH_CHECK("va_fused_kernel");

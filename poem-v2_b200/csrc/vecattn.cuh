@@ -35,13 +35,20 @@ template <int D>
 struct VaCfg {
   static constexpr int MT = D / 128;                 // accumulator tiles along the channel (M) axis
   static constexpr int KB = D / 64;                  // 64-wide K blocks
-  static constexpr int NT = (D <= 256) ? 128 : 64;   // tokens per tile (TMEM: 2 * MT * NT <= 512 columns)
+#ifndef POEM_VA_TWO_CTA
+#define POEM_VA_TWO_CTA 0   // measured on B200 (medium): 0.618 ms vs 0.534 ms per launch — the 2-stage weight ring starves the MMAs
+#endif
+  // D <= 256: two CTAs per SM, each on its own 64-token tiles (one CTA's MMAs overlap the other's epilogues);
+  // otherwise one CTA per SM with two channel-thread sets on 128-token tiles.
+  static constexpr bool TWO = (POEM_VA_TWO_CTA != 0) && (D <= 256);
+  static constexpr int CTAS_PER_SM = TWO ? 2 : 1;
+  static constexpr int NT = (D <= 256 && !TWO) ? 128 : 64;   // tokens per tile (TMEM: 2 * MT * NT columns)
   static constexpr int QT = NT / 32;                 // queries per tile
-  static constexpr int SETS = (D <= 256) ? 2 : 1;    // channel-thread sets; each set owns QT/SETS queries of a tile
+  static constexpr int SETS = (D <= 256 && !TWO) ? 2 : 1;    // channel-thread sets; each set owns QT/SETS queries
   static constexpr int QPS = QT / SETS;              // queries per thread and tile (== 2 for every supported D)
   static constexpr int EP = MT * 128 * SETS;         // channel threads
   static constexpr int THREADS = 64 + EP;
-  static constexpr int W_STAGES = 5;
+  static constexpr int W_STAGES = TWO ? 2 : 5;
   static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] bf16
   static constexpr int ACT_BYTES = NT * D * 2;       // KB blocks of [NT tokens x 64 k] bf16
   static constexpr int TMEM_COLS = (2 * MT * NT <= 256) ? 256 : 512;
@@ -75,7 +82,7 @@ struct VaParams {
 };
 
 template <int D>
-__global__ void __launch_bounds__(VaCfg<D>::THREADS, 1)
+__global__ void __launch_bounds__(VaCfg<D>::THREADS, VaCfg<D>::CTAS_PER_SM)
 va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_constant__ CUtensorMap tmap_wg1,   // wg1 = W_g1 W_d2
                 const __grid_constant__ CUtensorMap tmap_wg2, VaParams p) {
   using Cfg = VaCfg<D>;
