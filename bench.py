@@ -123,6 +123,40 @@ def emit(line):
 _REAL_STDOUT = os.dup(1)
 
 
+def torch_cuda_reference_pass(size, V, B, steps, warmup, dev, tf32):
+    """The reference's eager-PyTorch ops (oracle port) on the SAME GPU: the 'reference PyTorch-CUDA' figure the north
+    star's >= 10x target is quoted against (fp32, TF32 off/on, no CUDA_LAUNCH_BLOCKING)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import poem_oracle as orc
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    dims = release_dims(size)
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(dims, 0).items()}
+    feat, metas, ref_j = synth.make_inputs(dims, B, V, 1)
+    metas = dict(metas)
+    metas["cam_intr"], metas["cam_extr"] = metas["cam_intr"].to(dev), metas["cam_extr"].to(dev)
+    feat, ref_j = feat.to(dev), ref_j.to(dev)
+    bps, a_xyz, a_idx = [t.to(dev) for t in synth.load_assets()]
+    tmpl = synth.standin_template().to(dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = bool(tf32)
+    try:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            for _ in range(warmup):
+                orc.head_forward(sd, dims, feat, metas, ref_j, tmpl, bps, a_xyz, a_idx)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                orc.head_forward(sd, dims, feat, metas, ref_j, tmpl, bps, a_xyz, a_idx)
+            e1.record()
+            torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    ms = e0.elapsed_time(e1) / steps
+    return B / ms * 1e3, ms
+
+
 def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
@@ -133,6 +167,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-cuda-baseline", action="store_true",
+                    help="also time the reference's eager PyTorch ops (oracle port) on this GPU")
     args = ap.parse_args()
     size, V, B = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -314,13 +350,22 @@ def main():
         cpu = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"oracle port (fp32 torch CPU) on {sb} samples x {V} views, 3 passes, {sec:.2f} s/pass"}
 
+    torch_cuda = None
+    if args.torch_cuda_baseline and n_gpus == 1:
+        head._ws = None
+        torch.cuda.empty_cache()
+        torch_cuda = {}
+        for tf32 in (False, True):
+            sps, ms = torch_cuda_reference_pass(size, V, B, 3, 1, dev, tf32)
+            torch_cuda["tf32" if tf32 else "fp32"] = {"samples_per_s": sps, "ms_per_step": ms}
+        torch_cuda["note"] = "oracle port of the reference's eager ops on the same B200, same batch; reported context"
     line = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "path_roofline": path,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "torch_cuda_eager": torch_cuda,
             "kernel_breakdown_ms_per_step": {k: [round(v["ms"] / prof_steps, 4), v["n"] // prof_steps] for k, v in by_kernel}}
     emit(line)
     if world > 1:

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 
 # ------------------------------------------------------------------------------------------ a2
-def sine_pos_3d(n_views, h, w, num_feats, normalize=True, temperature=10000.0, scale=2 * math.pi, eps=1e-6):
+def sine_pos_3d(n_views, h, w, num_feats, normalize=True, temperature=10000.0, scale=2 * math.pi, eps=1e-6):  # CPU
     """`SinePositionalEncoding3D.forward` on an all-false mask (lib/models/layers/petr_transformer.py:434-469).
     Returns (n_views, 3*num_feats, h, w); channel order [view, y, x]."""
     ones = torch.ones(1, n_views, h, w, dtype=torch.float32)
@@ -214,7 +214,7 @@ def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anc
     views = [int(v) for v in img_metas["cam_view_num"]]
     B = len(views)
     inp_w, inp_h = img_metas["inp_img_shape"]
-    inp_res = torch.tensor([float(inp_w), float(inp_h)])
+    inp_res = torch.tensor([float(inp_w), float(inp_h)], device=feat.device)
     x = feature_volume(sd, feat, views, dims)
     centre = reference_joints[:, dims.center_idx]                   # (B,3)
     bps_world = bps[None] + centre[:, None]
