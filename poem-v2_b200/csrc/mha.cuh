@@ -11,7 +11,7 @@
 //   tensor core already works on S(j+2) / P·V(j+1): the softmax warps never wait for an MMA in steady state.
 // Q/K/V tiles [rows x HD] are staged by TMA as they lie in memory; V is consumed as an MN-major B operand (no
 // transposed copy of the value projection is needed); K and V rings are 2 deep.
-// warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = softmax + output.
+// warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = softmax + output (two threads per row).
 #pragma once
 #include "common.cuh"
 
@@ -19,7 +19,7 @@ namespace poem {
 
 constexpr int MHA_BQ = 128;    // queries per CTA
 constexpr int MHA_BKEY = 128;  // keys per block
-constexpr int MHA_THREADS = 192;
+constexpr int MHA_THREADS = 64 + 256;   // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 
 template <int HD>
 struct MhaCfg {
@@ -29,7 +29,8 @@ struct MhaCfg {
   static constexpr int kKBytes = MHA_BKEY * HD * 2;
   static constexpr int kVBytes = MHA_BKEY * HD * 2;              // kKBlocks tiles of [128 keys x kRowBytes]
   static constexpr int kPBytes = MHA_BQ * MHA_BKEY * 2;          // two [128 x 64 keys] SWIZZLE_128B tiles
-  static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + 256;
+  static constexpr int kXchgBytes = 2 * 128 * 2;                // bf16 row-max exchange between the two row halves
+  static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + kXchgBytes + 160;   // 2 CTAs/SM at HD=64
   static constexpr int kTmemCols = 256;                          // two S buffers; O_blk aliases the consumed one
 };
 
@@ -48,7 +49,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   uint8_t* sK = sQ + Cfg::kQBytes;               // 2 stages
   uint8_t* sV = sK + 2 * Cfg::kKBytes;           // 2 stages
   uint8_t* sP = sV + 2 * Cfg::kVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  __nv_bfloat16* s_xchg = reinterpret_cast<__nv_bfloat16*>(sP + Cfg::kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes + Cfg::kXchgBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;       // [2] TMA -> MMA
   uint64_t* k_empty = bars + 3;      // [2] MMA -> TMA (S(j) retired)
@@ -56,8 +58,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   uint64_t* v_empty = bars + 7;      // [2] (P·V(j) retired)
   uint64_t* s_full = bars + 9;       // [2] MMA -> softmax: S(j) in TMEM buffer j%2
   uint64_t* o_full = bars + 11;      // [2] MMA -> softmax: O_blk(j) in TMEM buffer j%2 (and P smem tile free)
-  uint64_t* o_done = bars + 13;      // [2] softmax -> MMA: O_blk(j) folded, buffer j%2 may take S(j+2)   (count 128)
-  uint64_t* p_full = bars + 15;      //     softmax -> MMA: P(j) in smem, S(j) consumed                   (count 128)
+  uint64_t* o_done = bars + 13;      // [2] softmax -> MMA: O_blk(j) folded, buffer j%2 may take S(j+2)   (count 256)
+  uint64_t* p_full = bars + 15;      //     softmax -> MMA: P(j) in smem, S(j) consumed                   (count 256)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
@@ -82,9 +84,9 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         mbar_init(&v_empty[s], 1);
         mbar_init(&s_full[s], 1);
         mbar_init(&o_full[s], 1);
-        mbar_init(&o_done[s], 128);
+        mbar_init(&o_done[s], 256);
       }
-      mbar_init(p_full, 128);
+      mbar_init(p_full, 256);
       fence_mbar_init();
     }
     __syncwarp();
@@ -166,27 +168,41 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     }
   } else {
     // ===================== softmax + output warps =====================
+    // 8 warps: two threads per query row (warps w and w+4 share a TMEM lane quarter); `half` selects which 64 of the
+    // 128 S columns / which HD/2 of the O columns a thread owns.  The row maximum is exchanged through smem once per
+    // key block, the row sums once at the end.
+    constexpr int HH = HD / 2;
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float o_acc[HD];
+    float o_acc[HH];
 #pragma unroll
-    for (int c = 0; c < HD; ++c) o_acc[c] = 0.f;
-    float m_run = -INFINITY;   // running max of raw scores
-    float l_run = 0.f;         // running sum of exp
+    for (int c = 0; c < HH; ++c) o_acc[c] = 0.f;
+    float m_run = -INFINITY;   // running max of raw scores (whole row)
+    float l_run = 0.f;         // running sum of exp over this thread's columns
     float alpha_prev = 0.f;    // rescale that belongs to the not-yet-folded O_blk(j-1)
 
-    auto fold_o = [&](int j, float alpha) {         // o_acc = o_acc * alpha + O_blk(j)
+    auto fold_o = [&](int j, float alpha) {         // o_acc = o_acc * alpha + O_blk(j)[:, half*HH .. +HH)
       const int st = j & 1;
       mbar_wait(&o_full[st], (uint32_t)(j >> 1) & 1);
       tc_fence_after_sync();
-#pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + lane_off + st * 128 + c0, r);
+      const uint32_t base = tmem_base + lane_off + st * 128 + half * HH;
+      if constexpr (HH == 16) {
+        uint32_t r[16];
+        tmem_ld16(base, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(r[i]);
+        for (int i = 0; i < 16; ++i) o_acc[i] = o_acc[i] * alpha + __uint_as_float(r[i]);
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(base + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c0 + i] = o_acc[c0 + i] * alpha + __uint_as_float(r[i]);
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(&o_done[st]);
@@ -194,29 +210,38 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
 
     for (int j = 0; j < n_kblocks; ++j) {
       const int st = j & 1;
-      const uint32_t tmem_S = tmem_base + lane_off + st * 128;
+      const uint32_t tmem_S = tmem_base + lane_off + st * 128 + half * 64;
       mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1);
       tc_fence_after_sync();
-      // pass A: block max
+      // pass A: max over this thread's 64 columns, then over the row via the partner thread
       float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < MHA_BKEY; c0 += 32) {
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_S + c0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
       }
+      // Exchange the half-row maxima as bf16 (any common reference value works for the softmax; both threads of a row
+      // use the same rounded pair).  Single buffer: the partner can only write its block j+1 value after S(j+1) was
+      // issued, which (for j >= 1) waits for o_done(j-1), i.e. for every thread's read below; block 0 syncs again.
+      const __nv_bfloat16 m_mine = __float2bfloat16(m_blk);
+      s_xchg[half * 128 + row] = m_mine;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m_blk = fmaxf(__bfloat162float(m_mine), __bfloat162float(s_xchg[(half ^ 1) * 128 + row]));
+      if (j == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
       const float m_scaled = m_new * scale_log2e;
       // fold the previous block's P·V (finished long ago) — this also guarantees the P tile is free again
       if (j > 0) fold_o(j - 1, alpha_prev);
       alpha_prev = alpha;
-      // pass B: probabilities -> bf16 -> swizzled smem (A operand of P·V)
+      // pass B: probabilities -> bf16 -> swizzled smem (A operand of P·V); this thread fills K block `half`
       float l_blk = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < MHA_BKEY; c0 += 32) {
+      uint8_t* tile = sP + half * (MHA_BQ * 128);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_S + c0, r);
         tmem_ld_wait();
@@ -228,8 +253,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
           l_blk += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
-        uint8_t* tile = sP + (c0 >> 6) * (MHA_BQ * 128);
-        const int chunk0 = (c0 & 63) >> 3;
+        const int chunk0 = c0 >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 v = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -243,13 +267,19 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       mbar_arrive(p_full);
     }
     fold_o(n_kblocks - 1, alpha_prev);
+    // row sum = both halves
+    // (every P·V has retired: the P tile is free and serves as the fp32 exchange buffer)
+    float* lbuf = reinterpret_cast<float*>(sP);
+    lbuf[half * 128 + row] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_row = l_run + lbuf[(half ^ 1) * 128 + row];
 
     const int q = q0 + row;
     if (q < Lq) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* o = ctx + (size_t)(b * Lq + q) * ld_ctx + head * HD;
+      const float inv = 1.0f / l_row;
+      __nv_bfloat16* o = ctx + (size_t)(b * Lq + q) * ld_ctx + head * HD + half * HH;
 #pragma unroll
-      for (int c = 0; c < HD; c += 8) {
+      for (int c = 0; c < HH; c += 8) {
         uint4 pk;
         pk.x = pack_bf16x2(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
         pk.y = pack_bf16x2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
