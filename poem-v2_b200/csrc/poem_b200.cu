@@ -244,7 +244,11 @@ static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   if ((ep.out_f32 && (ep.ld_f32 % 4)) || (ep.out_bf16 && (ep.ld_bf16 % 8)) ||
       (ep.res_mode == RES_F32 && (ep.res_ld % 4)))
     return fail(POEM_E_ALIGN, "gemm: output/residual leading dimensions must keep rows 16-byte aligned");
-  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+  // widest tile that divides N, narrowed while the grid would be under ~2 waves (small-M GEMMs of the query stream:
+  // more, smaller tiles keep the TMEM double buffering and the TMA ring busy instead of one serial tile per CTA)
+  int BN = (N % 256 == 0) ? 256 : (N % 128 == 0) ? 128 : 64;
+  const int tiles_m_ = (M + GEMM_BM - 1) / GEMM_BM;
+  while (BN > 64 && tiles_m_ * (N / BN) < 3 * num_sms()) BN >>= 1;
   CUtensorMap ta, tw;
   POEM_TRY(make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM));
   POEM_TRY(make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, GEMM_BK, (uint32_t)BN));
