@@ -1052,8 +1052,13 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
   {
     const int threads = 256;
     prof_begin(st);
-    merge_reduce_kernel<<<(unsigned)(((size_t)BP * 32 + threads - 1) / threads), threads, 0, st>>>(
-        h.Mm, vt.sample_rowbase, vt.sample_views, h.S, H, P, BP);
+    const unsigned blocks = (unsigned)(((size_t)BP * 32 + threads - 1) / threads);
+    switch (H) {
+      case 64: merge_reduce_kernel<2><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
+      case 128: merge_reduce_kernel<4><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
+      case 256: merge_reduce_kernel<8><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
+      default: merge_reduce_kernel<16><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
+    }
     LAUNCH_CHECK("merge_reduce_kernel");
   }
   POEM_TRY(linear("merge1a", h.S, H, w->merge1a, BP, H, H, ACT_RELU, nullptr, nullptr, h.H2, st));

@@ -170,34 +170,57 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
 //   N  > 1 : w_n = <m_n, m_0>, s = sum_{n>=1} w_n m_n
 // one warp per token.
 // ------------------------------------------------------------------------------------------------
+template <int PER>   // bf16 values per lane: H = 32 * PER, lane owns columns [lane*PER, lane*PER + PER)
 __global__ void merge_reduce_kernel(const __nv_bfloat16* __restrict__ m, const int* __restrict__ sample_rowbase,
-                                    const int* __restrict__ sample_views, __nv_bfloat16* __restrict__ s, int H, int P,
+                                    const int* __restrict__ sample_views, __nv_bfloat16* __restrict__ s, int P,
                                     int n_tokens) {
+  constexpr int H = 32 * PER;
+  constexpr int WORDS = PER / 2;   // 32-bit words (bf16 pairs) per lane
   const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= n_tokens) return;
   const int b = tok / P, pp = tok - b * P;
   const int N = sample_views[b];
-  const __nv_bfloat16* base = m + ((size_t)sample_rowbase[b] + (size_t)pp * N) * H;
-  const int per = H / 32;  // H in {64,128,256,512}: 2..16 values per lane
-  float m0[16], acc[16];
-  for (int i = 0; i < per; ++i) {
-    m0[i] = __bfloat162float(base[lane + 32 * i]);
-    acc[i] = (N == 1) ? m0[i] : 0.f;
-  }
-  for (int nn = 1; nn < N; ++nn) {
-    const __nv_bfloat16* r = base + (size_t)nn * H;
-    float mv[16];
-    float dot = 0.f;
-    for (int i = 0; i < per; ++i) {
-      mv[i] = __bfloat162float(r[lane + 32 * i]);
-      dot += mv[i] * m0[i];
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(m + ((size_t)sample_rowbase[b] + (size_t)pp * N) * H) + lane * WORDS;
+  auto load_row = [&](int nn, float (&v)[PER]) {
+    uint32_t w[WORDS];
+    const uint32_t* r = base + (size_t)nn * (H / 2);
+    if constexpr (WORDS == 1) {
+      w[0] = __ldg(r);
+    } else if constexpr (WORDS == 2) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(r));
+      w[0] = t.x, w[1] = t.y;
+    } else {
+#pragma unroll
+      for (int q = 0; q < WORDS / 4; ++q) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + q);
+        w[4 * q] = t.x, w[4 * q + 1] = t.y, w[4 * q + 2] = t.z, w[4 * q + 3] = t.w;
+      }
     }
 #pragma unroll
+    for (int i = 0; i < WORDS; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  };
+  float m0[PER], acc[PER];
+  load_row(0, m0);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) acc[i] = (N == 1) ? m0[i] : 0.f;
+  for (int nn = 1; nn < N; ++nn) {
+    float mv[PER];
+    load_row(nn, mv);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) dot += mv[i] * m0[i];
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    for (int i = 0; i < per; ++i) acc[i] += dot * mv[i];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) acc[i] += dot * mv[i];
   }
-  for (int i = 0; i < per; ++i) s[(size_t)tok * H + lane + 32 * i] = __float2bfloat16(acc[i]);
+  uint32_t* out = reinterpret_cast<uint32_t*>(s + (size_t)tok * H) + lane * WORDS;
+#pragma unroll
+  for (int i = 0; i < WORDS; ++i) out[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
 }
 
 // ------------------------------------------------------------------------------------------------
