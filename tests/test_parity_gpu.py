@@ -92,6 +92,21 @@ def test_head_matches_oracle_and_golden(name):
         assert num / den <= (1e-2 if meta["mode"] == "init" else 5e-2)
 
 
+@pytest.mark.parametrize("size,views", [("small", [10]), ("small", [1]), ("medium", [1, 10, 5, 7]), ("small", [6, 9, 3])])
+def test_view_count_edge_cases_match_oracle(size, views):
+    """1 view (single-view merge path), the maximum of 10 views and view counts that do not divide 128 (ragged rows
+    of the merge GEMMs), checked against the pinned oracle."""
+    dims = release_dims(size)
+    sd = synth.make_state_dict(dims, 21, "init")
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 5)
+    bps, a_xyz, a_idx = synth.load_assets()
+    with torch.no_grad():
+        want = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx)
+    head = build_head(dims, sd)
+    got = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
+    check_coords(got, want, f"{size} views={views}", 0.1)
+
+
 def test_transformer_module_matches_oracle():
     dims = release_dims("small")
     sd = synth.make_state_dict(dims, 11)
