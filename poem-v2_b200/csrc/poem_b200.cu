@@ -886,12 +886,43 @@ static int linear(const char* tag, const __nv_bfloat16* A, int lda, const PoemLi
   return launch_gemm(A, lda, W16(l), K, M, N, K, e, st);
 }
 
+// Side stream for the 32-NN searches: they only depend on the coordinates regressed by the previous block, are
+// latency-bound and tiny in registers/smem, so they run concurrently with the next block's attention GEMMs instead of
+// in front of its vector attention.  Fork/join with events keeps the call asynchronous on the caller's stream.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork[POEM_MAX_BLOCKS], join[POEM_MAX_BLOCKS];
+  bool ok = false;
+};
+static SideStream& side_stream() {
+  static thread_local SideStream s;
+  if (!s.ok) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess) {
+      s.ok = true;
+      for (int i = 0; i < POEM_MAX_BLOCKS; ++i)
+        s.ok = s.ok && cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  return s;
+}
+
+static int launch_block_knn(const PoemWeights* w, int B, int Q, int P, const BlockPlan& p, const float* xyz,
+                            bool pt_is_bps, cudaStream_t st) {
+  POEM_TRY(launch_knn(xyz, xyz, p.idx_self, B, Q, Q, st));
+  if (pt_is_bps && w->bps_perm && w->bps_chunk_box)
+    return launch_knn_bps(xyz, p.pt_xyz_sorted, w->bps_perm, w->bps_chunk_box, p.idx_cross, B, Q, P, st);
+  return launch_knn(xyz, p.pt_xyz, p.idx_cross, B, Q, P, st);
+}
+
 // a8-a13: the NB decoder blocks. Expects p.ptf (bf16 BPS features), p.pt_xyz, p.xyz[0], p.qf32/p.qf16 filled.
 // coords_out[i] = nan_to_num(xyz_i) * radius + centre when centre != NULL, else the raw normalised xyz_i.
 static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const BlockPlan& p, const float* centre,
                       float* coords_out, float* out_feats, bool pt_is_bps, cudaStream_t st) {
   const int D = dims->embed_dims, P = dims->n_sample, Q = dims->n_query, NB = dims->n_blocks;
   const int BQ = B * Q, BP = B * P;
+  SideStream& side = side_stream();
+  const bool knn_on_side = side.ok && !g_prof_on;   // per-launch event timing assumes one stream
   for (int i = 0; i < NB; ++i) {
     const PoemBlock& k = w->blocks[i];
     float* xyz_in = p.xyz + (size_t)i * BQ * 3;
@@ -915,19 +946,16 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
     // vector self-attention
     POEM_TRY(linear("va_self_qkv", p.a2_16, D, k.self_qkv, BQ, 3 * D, D, ACT_NONE, nullptr, nullptr, p.qkv16, st));
     const bool anchors = (i == 0);
-    if (!anchors) POEM_TRY(launch_knn(xyz_in, xyz_in, p.idx_self, B, Q, Q, st));
+    if (!anchors) {   // neighbour indices of this block: computed on the side stream since the previous block ended
+      if (knn_on_side) CUDA_TRY(cudaStreamWaitEvent(st, side.join[i], 0));
+      else POEM_TRY(launch_block_knn(w, B, Q, P, p, xyz_in, pt_is_bps, st));
+    }
     POEM_TRY(launch_vector_attention(&k.self_attn, p.qkv16, 3 * D, p.qkv16 + D, 3 * D, p.qkv16 + 2 * D, 3 * D, xyz_in,
                                      xyz_in, anchors ? nullptr : p.idx_self, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, Q, D, p.res16, p.t0, p.t1, p.t2, st));
     POEM_TRY(linear("va_fc2", p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
     // vector cross-attention (queries <- BPS tokens)
     POEM_TRY(linear("va_cross_q", p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
-    if (!anchors) {
-      if (pt_is_bps && w->bps_perm && w->bps_chunk_box)
-        POEM_TRY(launch_knn_bps(xyz_in, p.pt_xyz_sorted, w->bps_perm, w->bps_chunk_box, p.idx_cross, B, Q, P, st));
-      else
-        POEM_TRY(launch_knn(xyz_in, p.pt_xyz, p.idx_cross, B, Q, P, st));
-    }
     POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 6 * D, p.KK + 3 * D, 6 * D, xyz_in,
                                      p.pt_xyz, anchors ? nullptr : p.idx_cross, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, P, D, p.res16, p.t0, p.t1, p.t2, st));
@@ -942,6 +970,12 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
           p.r1_16, k.reg2_w, k.reg2_b, xyz_in, xyz_out, coords_out + (size_t)i * BQ * 3, centre, dims->radius, Q, D,
           BQ);
       LAUNCH_CHECK("reg_out_kernel");
+    }
+    if (knn_on_side && i + 1 < NB) {   // fork: 32-NN of block i+1 on the side stream, overlapping FFN / MHA of the main one
+      CUDA_TRY(cudaEventRecord(side.fork[i + 1], st));
+      CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork[i + 1], 0));
+      POEM_TRY(launch_block_knn(w, B, Q, P, p, xyz_out, pt_is_bps, side.stream));
+      CUDA_TRY(cudaEventRecord(side.join[i + 1], side.stream));
     }
     // feed-forward (its output only feeds the next block)
     const bool last = (i == NB - 1);
