@@ -318,7 +318,9 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   ConvOperand cv;
   cv.enabled = 1, cv.ksize = ksize, cv.pad = ksize / 2, cv.stride = stride, cv.cblocks = cblocks, cv.Hout = Hout,
   cv.Wout = Wout;
-  TagScope ts(ksize == 3 ? (stride == 1 ? "conv3x3" : "conv3x3s2") : "conv1x1");
+  char tag[48];
+  snprintf(tag, sizeof(tag), "conv%dx%d%s_c%d_to_%d", ksize, ksize, stride == 2 ? "s2" : "", Cin_p, Cout_p);
+  TagScope ts(tag);
   switch (BN) {
     case 64: return launch_gemm_bn<64>(ta, tw, M, Cout_p, K, e, cv, st);
     case 128: return launch_gemm_bn<128>(ta, tw, M, Cout_p, K, e, cv, st);
