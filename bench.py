@@ -333,7 +333,17 @@ def main():
                              "frac": ach / peaks["bf16_tflops"], "algorithmic_flops_per_launch": flops})
     else:
         roofline.update({"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None})
-    roofline["traffic"] = None      # dram bytes per launch from the ncu --set full capture: see profiles/
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu --set full capture
+    roofline["traffic"] = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)
+        if args.workload == "medium_v8_b32" and (top_name in tr or key in tr):
+            ent = tr.get(top_name, tr.get(key))
+            roofline["traffic"] = ent["dram_bytes_per_launch"]
+            roofline["traffic_source"] = ent["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline["peak_source"] = peaks["source"]
     # whole-path roofline: the decoder is tensor-bound at stage-boundary traffic
     t_tc = flops_s / (peaks["bf16_tflops"] * 1e12)
