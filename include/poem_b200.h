@@ -184,6 +184,33 @@ size_t poem_hrnet_stage4_workspace_bytes(const PoemHRStage4* w, int n_images, in
 int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, int base_res, const float* const* in,
                               float* const* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- whole HRNet-W40 backbone (reference lib/models/backbones/hrnet.py:240-420): stem (two
+ * stride-2 3x3 convs), layer1 (4 Bottlenecks), transitions 1-3, stage 2 (1 module, 2 branches), stage 3 (4 modules,
+ * 3 branches), stage 4 (3 modules, 4 branches).  Same weight conventions as stage 4; the first convolution (3 input
+ * channels) keeps fp32 weights [64, 27] with k = (ky*3 + kx)*3 + c. */
+typedef struct PoemBottleneck {
+  PoemLinear c1, c2, c3;   /* 1x1 in->64, 3x3 64->64, 1x1 64->256 (BN folded) */
+  PoemLinear ds;           /* 1x1 in->256 downsample of the identity path, w == NULL when absent */
+} PoemBottleneck;
+typedef struct PoemHRNet {
+  const float* stem1_w;
+  const float* stem1_b;
+  PoemLinear stem2;
+  PoemBottleneck layer1[4];
+  PoemLinear trans1[2];    /* 3x3 256->40 ; 3x3 stride-2 256->80 */
+  PoemLinear trans2;       /* 3x3 stride-2 80->160 */
+  PoemLinear trans3;       /* 3x3 stride-2 160->320 */
+  int32_t channels[4];
+  PoemHRModule stage2[1];
+  PoemHRModule stage3[4];
+  PoemHRModule stage4[3];
+} PoemHRNet;
+size_t poem_hrnet_workspace_bytes(const PoemHRNet* w, int n_images, int img_res);
+/* images: fp32 NCHW (n_images, 3, 256, 256); out[b]: fp32 NCHW (n_images, channels[b], 64 >> b, 64 >> b).
+ * Replaces `HighResolutionNet.forward` (hrnet.py:385-420) as called at lib/models/POEM.py:262. */
+int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res, const float* images, float* const* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
  * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
  * Replaces nn.Conv2d + nn.BatchNorm2d(eval) (+ReLU, + identity) of hrnet.py:38-67,177-207. */

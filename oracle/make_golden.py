@@ -60,8 +60,7 @@ def run_reference(size, views, wseed, iseed, mode):
     return cap
 
 
-def run_reference_stage4(n_images, wseed, iseed):
-    """The real reference `HighResolutionModule` x3 (= `HighResolutionNet.stage4`, hrnet.py:272-277) on CPU."""
+def _import_reference_hrnet():
     ref_shim.install(synth.standin_template)
     import lib.external.metro.hrnet  # noqa: F401  (bare package; the backbone imports its config from there)
     import types
@@ -71,6 +70,27 @@ def run_reference_stage4(n_images, wseed, iseed):
     sys.modules.setdefault("lib.external.metro.hrnet", types.ModuleType("lib.external.metro.hrnet"))
     sys.modules.setdefault("lib.external.metro.hrnet.config", cfgmod)
     import lib.models.backbones.hrnet as hr
+    return hr
+
+
+def run_reference_backbone(n_images, wseed, iseed):
+    """The real reference `HighResolutionNet` (hrnet.py:239-420) built from its own W40 yaml, on CPU, eval mode."""
+    import yaml
+    hr = _import_reference_hrnet()
+    with open(os.path.join(ref_shim.REF_ROOT, "config/backbone/cls_hrnet_w40_sgd_lr5e-2_wd1e-4_bs32_x100.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    net = hr.HighResolutionNet(cfg).eval()
+    sd = synth.make_backbone_state_dict(wseed)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    dead = ("incre_modules.", "downsamp_modules.", "final_layer.", "classifier.")
+    assert not unexpected and all(k.startswith(dead) for k in missing), (missing[:5], unexpected[:5])
+    with torch.no_grad():
+        return net(synth.make_images(n_images, 256, iseed))
+
+
+def run_reference_stage4(n_images, wseed, iseed):
+    """The real reference `HighResolutionModule` x3 (= `HighResolutionNet.stage4`, hrnet.py:272-277) on CPU."""
+    hr = _import_reference_hrnet()
     ch = [40, 80, 160, 320]
     mods = torch.nn.Sequential(*[hr.HighResolutionModule(4, hr.BasicBlock, [4] * 4, list(ch), list(ch), "SUM", True)
                                  for _ in range(3)]).eval()
@@ -84,6 +104,14 @@ def run_reference_stage4(n_images, wseed, iseed):
 
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    ys = run_reference_backbone(1, 0, 1)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hrnet_w40_n1.npz"),
+                        meta=np.array(repr(dict(kind="hrnet_w40", n_images=1, wseed=0, iseed=1, stride=4))),
+                        y0=ys[0][:, :, ::4, ::4].numpy(), y1=ys[1][:, :, ::2, ::2].numpy(), y2=ys[2].numpy(),
+                        y3=ys[3].numpy())
+    print("hrnet_w40_n1", [tuple(y.shape) for y in ys], [float(y.abs().mean()) for y in ys])
+    if "--only-hrnet" in sys.argv:
+        return
     ys = run_reference_stage4(2, 0, 1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hrnet_stage4_n2.npz"),
                         meta=np.array(repr(dict(kind="hrnet_stage4", n_images=2, wseed=0, iseed=1, stride=4))),

@@ -247,12 +247,13 @@ def _conv_bn(sd, conv_key, bn_key, x, stride=1, relu=False):
     return F.relu(y) if relu else y
 
 
-def hrnet_stage4(sd, x_list, n_modules=3):
+def hrnet_stage4(sd, x_list, n_modules=3, prefix=""):
     """`HighResolutionNet.stage4` = n_modules x `HighResolutionModule.forward`
     (lib/models/backbones/hrnet.py:217-234; BasicBlock :38-67; fuse layers :177-207). sd keys relative to `stage4.`"""
     xs = list(x_list)
     nb = len(xs)
     for m in range(n_modules):
+        m = f"{prefix}{m}"
         for b in range(nb):
             x = xs[b]
             for k in range(4):
@@ -277,3 +278,24 @@ def hrnet_stage4(sd, x_list, n_modules=3):
             fused.append(F.relu(y))
         xs = fused
     return xs
+
+
+def hrnet_forward(sd, img):
+    """Whole `HighResolutionNet.forward` for the W40 yaml (lib/models/backbones/hrnet.py:385-420): stem :388-393,
+    layer1 = 4 Bottlenecks :70-104, transitions :318-342, stages 2/3/4 with 1/4/3 modules. BatchNorm in eval mode."""
+    x = _conv_bn(sd, "conv1", "bn1", img, stride=2, relu=True)
+    x = _conv_bn(sd, "conv2", "bn2", x, stride=2, relu=True)
+    for k in range(4):
+        p = f"layer1.{k}."
+        t = _conv_bn(sd, p + "conv1", p + "bn1", x, relu=True)
+        t = _conv_bn(sd, p + "conv2", p + "bn2", t, relu=True)
+        t = _conv_bn(sd, p + "conv3", p + "bn3", t)
+        res = _conv_bn(sd, p + "downsample.0", p + "downsample.1", x) if (p + "downsample.0.weight") in sd else x
+        x = F.relu(t + res)
+    xs = [_conv_bn(sd, "transition1.0.0", "transition1.0.1", x, relu=True),
+          _conv_bn(sd, "transition1.1.0.0", "transition1.1.0.1", x, stride=2, relu=True)]
+    ys = hrnet_stage4(sd, xs, 1, prefix="stage2.")
+    xs = ys + [_conv_bn(sd, "transition2.2.0.0", "transition2.2.0.1", ys[-1], stride=2, relu=True)]
+    ys = hrnet_stage4(sd, xs, 4, prefix="stage3.")
+    xs = ys + [_conv_bn(sd, "transition3.3.0.0", "transition3.3.0.1", ys[-1], stride=2, relu=True)]
+    return hrnet_stage4(sd, xs, 3, prefix="stage4.")

@@ -92,6 +92,17 @@ class PoemHRStage4(C.Structure):
     _fields_ = [("n_modules", C.c_int32), ("channels", C.c_int32 * 4), ("modules", PoemHRModule * POEM_HR_MAX_MODULES)]
 
 
+class PoemBottleneck(C.Structure):
+    _fields_ = [("c1", PoemLinear), ("c2", PoemLinear), ("c3", PoemLinear), ("ds", PoemLinear)]
+
+
+class PoemHRNet(C.Structure):
+    _fields_ = [("stem1_w", C.c_void_p), ("stem1_b", C.c_void_p), ("stem2", PoemLinear),
+                ("layer1", PoemBottleneck * 4), ("trans1", PoemLinear * 2), ("trans2", PoemLinear),
+                ("trans3", PoemLinear), ("channels", C.c_int32 * 4), ("stage2", PoemHRModule * 1),
+                ("stage3", PoemHRModule * 4), ("stage4", PoemHRModule * 3)]
+
+
 class PoemInputs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_images", C.c_int32), ("view_counts", C.c_void_p), ("mlvl_feat", C.c_void_p),
                 ("cam_intr", C.c_void_p), ("cam_extr", C.c_void_p), ("reference_joints", C.c_void_p),
@@ -101,7 +112,7 @@ class PoemInputs(C.Structure):
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
            "poem_profile_summary", "poem_debug_force_unfused", "poem_hrnet_stage4_workspace_bytes",
-           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
@@ -166,6 +177,10 @@ def load():
     lib.poem_hrnet_stage4_workspace_bytes.argtypes = [C.POINTER(PoemHRStage4), i, i]
     lib.poem_hrnet_stage4_forward.restype = i
     lib.poem_hrnet_stage4_forward.argtypes = [C.POINTER(PoemHRStage4), i, i, C.POINTER(vp), C.POINTER(vp), vp, sz, vp]
+    lib.poem_hrnet_workspace_bytes.restype = sz
+    lib.poem_hrnet_workspace_bytes.argtypes = [C.POINTER(PoemHRNet), i, i]
+    lib.poem_hrnet_forward.restype = i
+    lib.poem_hrnet_forward.argtypes = [C.POINTER(PoemHRNet), i, i, vp, C.POINTER(vp), vp, sz, vp]
     lib.poem_conv_nhwc.restype = i
     lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp]
     lib.poem_layernorm.restype = i

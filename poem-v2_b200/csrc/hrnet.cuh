@@ -43,6 +43,55 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ i
   }
 }
 
+// Stem conv1 (hrnet.py:245-246, 388-390): 3x3 stride-2 convolution 3 -> 64 channels on the NCHW fp32 image, BatchNorm
+// folded, ReLU; writes NHWC bf16 (64 channels = one swizzle atom) for the implicit-GEMM convolutions that follow.
+// K = 27 is far too small for the tensor core: one thread per output pixel, weights broadcast from smem.
+//   w: fp32 [64][27] with k = (ky*3 + kx)*3 + c ; b: fp32 [64]
+__global__ void __launch_bounds__(128)
+stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
+                  __nv_bfloat16* __restrict__ out, int N, int H, int W) {
+  __shared__ float sw[64 * 27];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (size_t)N * Ho * Wo) return;
+  const int xo = (int)(pix % Wo);
+  const int yo = (int)((pix / Wo) % Ho);
+  const size_t n = pix / ((size_t)Wo * Ho);
+  float in[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int y = 2 * yo + ky - 1, x = 2 * xo + kx - 1;
+      const bool ok = (y >= 0 && y < H && x >= 0 && x < W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) in[(ky * 3 + kx) * 3 + c] = ok ? img[((n * 3 + c) * H + y) * W + x] : 0.f;
+    }
+  __nv_bfloat16* o = out + pix * 64;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = sb[c0 + j];
+      const float* wr = sw + (c0 + j) * 27;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) a = fmaf(wr[k], in[k], a);
+      acc[j] = fmaxf(a, 0.f);
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(acc[0], acc[1]);
+    pk.y = pack_bf16x2(acc[2], acc[3]);
+    pk.z = pack_bf16x2(acc[4], acc[5]);
+    pk.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(o + c0) = pk;
+  }
+}
+
 // Fuse layer sum (hrnet.py:225-233): out[n,y,x,c] = relu(sum_j in_j[n, y >> s_j, x >> s_j, c]); in_j has resolution
 // (H >> s_j, W >> s_j) — nearest-neighbour upsampling by 2^s_j of the 1x1-conv terms, s_j = 0 for the others.
 struct FuseSumArgs {

@@ -371,33 +371,13 @@ extern "C" size_t poem_hrnet_stage4_workspace_bytes(const PoemHRStage4* w, int n
   return hr_plan(n_images, base_res, w->channels, nullptr, &p);
 }
 
-extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, int base_res, const float* const* in,
-                                         float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!w || !in || !out || !workspace) return fail(POEM_E_NULL, "hrnet_stage4: null pointer");
-  if (w->n_modules < 1 || w->n_modules > POEM_HR_MAX_MODULES) return fail(POEM_E_BADDIM, "n_modules=%d", w->n_modules);
-  if (base_res != 64 && base_res != 32 && base_res != 128) return fail(POEM_E_BADDIM, "base_res=%d", base_res);
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
-  const int N = n_images, R0 = base_res;
-  const int* ch = w->channels;
-  cudaStream_t st = (cudaStream_t)stream;
-  HrPlan p;
-  const size_t need = hr_plan(N, R0, ch, reinterpret_cast<uint8_t*>(workspace), &p);
-  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
-  int Cp[4], R[4];
-  for (int i = 0; i < 4; ++i) {
-    Cp[i] = pad64(ch[i]);
-    R[i] = R0 >> i;
-    if (!in[i] || !out[i]) return fail(POEM_E_NULL, "hrnet_stage4: branch %d pointer missing", i);
-    dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
-    prof_begin(st);
-    nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], Cp[i], R[i] * R[i]);
-    LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
-  }
-  int cur[4] = {0, 0, 0, 0};   // index of the buffer holding the branch's current activation
-  for (int m = 0; m < w->n_modules; ++m) {
-    const PoemHRModule& mod = w->modules[m];
+// n_modules HighResolutionModules over the first nb branches (hrnet.py:217-234); cur[b] = live buffer of branch b
+static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N, const int* R, const int* Cp,
+                          const HrPlan& p, int* cur, cudaStream_t st) {
+  for (int m = 0; m < n_modules; ++m) {
+    const PoemHRModule& mod = mods[m];
     // ---- branches: 4 BasicBlocks each (hrnet.py:38-67)
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < nb; ++b) {
       for (int k = 0; k < 4; ++k) {
         __nv_bfloat16* x = p.x[b][cur[b]];
         __nv_bfloat16* t = p.x[b][(cur[b] + 1) % 3];
@@ -408,10 +388,10 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
       }
     }
     // ---- fuse layers (hrnet.py:177-207, 225-233)
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < nb; ++i) {
       FuseSumArgs fa;
       fa.n_in = 0;
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < nb; ++j) {
         const __nv_bfloat16* xj = p.x[j][cur[j]];
         if (j == i) {
           fa.in[fa.n_in] = xj, fa.shift[fa.n_in] = 0;
@@ -438,8 +418,13 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
       fuse_sum_relu_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cp[i], total8);
       LAUNCH_CHECK("fuse_sum_relu_kernel");
     }
-    for (int i = 0; i < 4; ++i) cur[i] = (cur[i] + 1) % 3;
+    for (int i = 0; i < nb; ++i) cur[i] = (cur[i] + 1) % 3;
   }
+  return POEM_OK;
+}
+
+static int hr_export(const HrPlan& p, const int* cur, const int* ch, const int* Cp, const int* R, int N,
+                     float* const* out, cudaStream_t st) {
   for (int i = 0; i < 4; ++i) {
     dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
     prof_begin(st);
@@ -447,6 +432,118 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
     LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
   }
   return POEM_OK;
+}
+
+extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, int base_res, const float* const* in,
+                                         float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !in || !out || !workspace) return fail(POEM_E_NULL, "hrnet_stage4: null pointer");
+  if (w->n_modules < 1 || w->n_modules > POEM_HR_MAX_MODULES) return fail(POEM_E_BADDIM, "n_modules=%d", w->n_modules);
+  if (base_res != 64 && base_res != 32 && base_res != 128) return fail(POEM_E_BADDIM, "base_res=%d", base_res);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  const int N = n_images, R0 = base_res;
+  const int* ch = w->channels;
+  cudaStream_t st = (cudaStream_t)stream;
+  HrPlan p;
+  const size_t need = hr_plan(N, R0, ch, reinterpret_cast<uint8_t*>(workspace), &p);
+  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  int Cp[4], R[4];
+  for (int i = 0; i < 4; ++i) {
+    Cp[i] = pad64(ch[i]);
+    R[i] = R0 >> i;
+    if (!in[i] || !out[i]) return fail(POEM_E_NULL, "hrnet_stage4: branch %d pointer missing", i);
+    dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
+    prof_begin(st);
+    nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], Cp[i], R[i] * R[i]);
+    LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+  }
+  int cur[4] = {0, 0, 0, 0};   // index of the buffer holding the branch's current activation
+  POEM_TRY(run_hr_modules(w->modules, w->n_modules, 4, N, R, Cp, p, cur, st));
+  return hr_export(p, cur, ch, Cp, R, N, out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole HRNet-W40 backbone (hrnet.py:385-420): stem, layer1 (4 Bottlenecks), transitions, stages 2-4
+// ------------------------------------------------------------------------------------------------
+struct HrNetPlan {
+  __nv_bfloat16 *s1, *s2;        // stem outputs: (N,R/2,R/2,64), (N,R/4,R/4,64)
+  __nv_bfloat16 *l256[3], *l64[2];   // layer1 activations at R/4: 256 and 64 channels
+  HrPlan hr;
+};
+static size_t hrnet_plan(int N, int img_res, const int* ch, uint8_t* base, HrNetPlan* p) {
+  Bump b{base, 0};
+  const size_t r2 = (size_t)(img_res / 2) * (img_res / 2), r4 = (size_t)(img_res / 4) * (img_res / 4);
+  p->s1 = b.take<__nv_bfloat16>((size_t)N * r2 * 64);
+  p->s2 = b.take<__nv_bfloat16>((size_t)N * r4 * 64);
+  for (int k = 0; k < 3; ++k) p->l256[k] = b.take<__nv_bfloat16>((size_t)N * r4 * 256);
+  for (int k = 0; k < 2; ++k) p->l64[k] = b.take<__nv_bfloat16>((size_t)N * r4 * 64);
+  const size_t off = (b.off + 1023) & ~size_t(1023);
+  const size_t hr = hr_plan(N, img_res / 4, ch, base ? base + off : nullptr, &p->hr);
+  return off + hr;
+}
+extern "C" size_t poem_hrnet_workspace_bytes(const PoemHRNet* w, int n_images, int img_res) {
+  if (!w || n_images < 1 || img_res < 64 || img_res % 32) return 0;
+  HrNetPlan p;
+  return hrnet_plan(n_images, img_res, w->channels, nullptr, &p);
+}
+
+extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res, const float* images,
+                                  float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !images || !out || !workspace) return fail(POEM_E_NULL, "hrnet: null pointer");
+  if (img_res != 256) return fail(POEM_E_BADDIM, "hrnet: img_res=%d (256 supported)", img_res);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  if (!w->stem1_w || !w->stem1_b) return fail(POEM_E_NULL, "hrnet: stem weights missing");
+  const int N = n_images;
+  const int* ch = w->channels;
+  cudaStream_t st = (cudaStream_t)stream;
+  HrNetPlan p;
+  const size_t need = hrnet_plan(N, img_res, ch, reinterpret_cast<uint8_t*>(workspace), &p);
+  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  const int R2 = img_res / 2, R4 = img_res / 4;
+  // stem: conv1 3->64 s2 (direct, fp32 weights) ; conv2 64->64 s2
+  {
+    const size_t pixels = (size_t)N * R2 * R2;
+    prof_begin(st);
+    stem_conv1_kernel<<<(unsigned)((pixels + 127) / 128), 128, 0, st>>>(images, w->stem1_w, w->stem1_b, p.s1, N, img_res,
+                                                                      img_res);
+    LAUNCH_CHECK("stem_conv1_kernel");
+  }
+  POEM_TRY(launch_conv(p.s1, N, R2, R2, 64, w->stem2, 64, 3, 2, true, nullptr, p.s2, st));
+  // layer1: Bottleneck x4 (hrnet.py:70-104, 254-257)
+  const __nv_bfloat16* x = p.s2;
+  int x_ch = 64;
+  for (int k = 0; k < 4; ++k) {
+    const PoemBottleneck& bt = w->layer1[k];
+    POEM_TRY(launch_conv(x, N, R4, R4, x_ch, bt.c1, 64, 1, 1, true, nullptr, p.l64[0], st));
+    POEM_TRY(launch_conv(p.l64[0], N, R4, R4, 64, bt.c2, 64, 3, 1, true, nullptr, p.l64[1], st));
+    const __nv_bfloat16* res = x;
+    __nv_bfloat16* y = p.l256[k % 2];
+    if (bt.ds.w) {
+      POEM_TRY(launch_conv(x, N, R4, R4, x_ch, bt.ds, 256, 1, 1, false, nullptr, p.l256[2], st));
+      res = p.l256[2];
+    } else if (x_ch != 256) {
+      return fail(POEM_E_BADDIM, "hrnet: layer1 block %d needs a downsample", k);
+    }
+    POEM_TRY(launch_conv(p.l64[1], N, R4, R4, 64, bt.c3, 256, 1, 1, true, res, y, st));
+    x = y;
+    x_ch = 256;
+  }
+  int Cp[4], R[4], cur[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    Cp[i] = pad64(ch[i]);
+    R[i] = R4 >> i;
+    if (!out[i]) return fail(POEM_E_NULL, "hrnet: output %d missing", i);
+  }
+  // transition1 (hrnet.py:318-342): 3x3 256->40 ; 3x3 s2 256->80
+  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st));
+  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[1], Cp[1], 3, 2, true, nullptr, p.hr.x[1][0], st));
+  POEM_TRY(run_hr_modules(w->stage2, 1, 2, N, R, Cp, p.hr, cur, st));
+  // transition2: new branch from the lowest-resolution output, 3x3 s2 80->160
+  POEM_TRY(launch_conv(p.hr.x[1][cur[1]], N, R[1], R[1], Cp[1], w->trans2, Cp[2], 3, 2, true, nullptr, p.hr.x[2][0], st));
+  POEM_TRY(run_hr_modules(w->stage3, 4, 3, N, R, Cp, p.hr, cur, st));
+  // transition3: 3x3 s2 160->320
+  POEM_TRY(launch_conv(p.hr.x[2][cur[2]], N, R[2], R[2], Cp[2], w->trans3, Cp[3], 3, 2, true, nullptr, p.hr.x[3][0], st));
+  POEM_TRY(run_hr_modules(w->stage4, 3, 4, N, R, Cp, p.hr, cur, st));
+  return hr_export(p.hr, cur, ch, Cp, R, N, out, st);
 }
 
 extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N,

@@ -1,5 +1,10 @@
-"""Host-side mirror of HRNet-W40 **stage 4** (reference lib/models/backbones/hrnet.py:272-277): the three
-`HighResolutionModule`s (`hrnet.py:108-234`) that turn [40@64², 80@32², 160@16², 320@8²] into the same four maps.
+"""Host-side mirror of the HRNet-W40 backbone (reference lib/models/backbones/hrnet.py).
+
+`HRNetStage4` is **stage 4** alone (`hrnet.py:272-277`): the three `HighResolutionModule`s (`hrnet.py:108-234`) that
+turn [40@64², 80@32², 160@16², 320@8²] into the same four maps.  `HRNetW40` is the whole `HighResolutionNet.forward`
+(`hrnet.py:385-420`): image (N,3,256,256) -> the same four maps, with the reference's parameter names from `conv1.` to
+`stage4.` (the dead classification-head keys `incre_modules.* / downsamp_modules.* / final_layer.* / classifier.*`
+are accepted and dropped).
 
 `HRNetStage4` keeps the reference's parameter names (`{m}.branches.{b}.{k}.conv1.weight`, `...bn1.running_mean`,
 `{m}.fuse_layers.{i}.{j}...` — the `stage4.` prefix of `HighResolutionNet`) so a backbone checkpoint loads unchanged;
@@ -154,3 +159,193 @@ class HRNetStage4(nn.Module):
         nat.check(lib.poem_hrnet_stage4_forward(C.byref(st), n, base, ins_p, outs_p, self._ws.data_ptr() + off,
                                                 self._ws.numel() - off, torch.cuda.current_stream(dev).cuda_stream))
         return outs
+
+
+# ------------------------------------------------------------------------------------------------ whole backbone
+STAGE_MODULES = {2: 1, 3: 4, 4: 3}          # config/backbone/cls_hrnet_w40_*.yaml: NUM_MODULES of stages 2-4
+_DEAD_PREFIXES = ("incre_modules.", "downsamp_modules.", "final_layer.", "classifier.")
+
+
+def backbone_param_shapes(channels=CHANNELS):
+    """name -> shape of every live parameter/buffer of reference `HighResolutionNet` (W40 yaml)."""
+    s = {}
+
+    def bn(prefix, c):
+        s[prefix + ".weight"] = (c,)
+        s[prefix + ".bias"] = (c,)
+        s[prefix + ".running_mean"] = (c,)
+        s[prefix + ".running_var"] = (c,)
+        s[prefix + ".num_batches_tracked"] = ()
+    s["conv1.weight"] = (64, 3, 3, 3)
+    bn("bn1", 64)
+    s["conv2.weight"] = (64, 64, 3, 3)
+    bn("bn2", 64)
+    for k in range(4):                       # layer1: Bottleneck(inplanes, 64) x4, expansion 4 (hrnet.py:70-104)
+        cin = 64 if k == 0 else 256
+        p = f"layer1.{k}."
+        s[p + "conv1.weight"] = (64, cin, 1, 1)
+        bn(p + "bn1", 64)
+        s[p + "conv2.weight"] = (64, 64, 3, 3)
+        bn(p + "bn2", 64)
+        s[p + "conv3.weight"] = (256, 64, 1, 1)
+        bn(p + "bn3", 256)
+        if k == 0:
+            s[p + "downsample.0.weight"] = (256, 64, 1, 1)
+            bn(p + "downsample.1", 256)
+    # transitions (hrnet.py:318-342)
+    s["transition1.0.0.weight"] = (channels[0], 256, 3, 3)
+    bn("transition1.0.1", channels[0])
+    s["transition1.1.0.0.weight"] = (channels[1], 256, 3, 3)
+    bn("transition1.1.0.1", channels[1])
+    s["transition2.2.0.0.weight"] = (channels[2], channels[1], 3, 3)
+    bn("transition2.2.0.1", channels[2])
+    s["transition3.3.0.0.weight"] = (channels[3], channels[2], 3, 3)
+    bn("transition3.3.0.1", channels[3])
+    for stage, n_mod in STAGE_MODULES.items():
+        for k, v in stage4_param_shapes(n_mod, channels[:stage]).items():
+            s[f"stage{stage}.{k}"] = v
+    return s
+
+
+def _fold_stem(sd):
+    """conv1 + bn1 -> fp32 [64, 27] with k = (ky*3 + kx)*3 + c, and fp32 bias [64]."""
+    w = sd["conv1.weight"].double()
+    scale = sd["bn1.weight"].double() / torch.sqrt(sd["bn1.running_var"].double() + BN_EPS)
+    w = (w * scale[:, None, None, None]).permute(0, 2, 3, 1).reshape(64, 27)
+    b = sd["bn1.bias"].double() - sd["bn1.running_mean"].double() * scale
+    return w.float(), b.float()
+
+
+class HRNetW40(nn.Module):
+    """Drop-in for `HighResolutionNet` / `HRNet` (`hrnet.py:239-420,439-449`): `forward(img) -> [y0, y1, y2, y3]`."""
+
+    def __init__(self, cfg=None, channels=CHANNELS):
+        super().__init__()
+        self.channels = tuple(channels)
+        self.name = "HRNet"
+        self._names = []
+        for name, shape in backbone_param_shapes(channels).items():
+            t = torch.zeros(shape, dtype=torch.long if name.endswith("num_batches_tracked") else torch.float32)
+            if name.endswith("running_var") or (name.endswith(".weight") and len(shape) == 1):
+                t = torch.ones(shape)
+            self.register_buffer(name.replace(".", "__"), t)
+            self._names.append(name)
+        self._packed = None
+        self._ws = None
+
+    def state_dict(self, *a, prefix="", **k):
+        return {prefix + n: getattr(self, n.replace(".", "__")) for n in self._names}
+
+    def load_state_dict(self, sd, strict=True):
+        live = set(self._names)
+        missing = [n for n in self._names if n not in sd]
+        unexpected = [n for n in sd if n not in live and not n.startswith(_DEAD_PREFIXES)]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"HRNetW40: missing keys {missing[:4]}, unexpected keys {unexpected[:4]}")
+        for n in self._names:
+            if n in sd:
+                getattr(self, n.replace(".", "__")).copy_(sd[n])
+        self._packed = None
+
+    def _pack(self, device):
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        net = nat.PoemHRNet()
+        keep = []
+
+        def lin(w, b):
+            wt = w.to(torch.bfloat16).contiguous().to(device)
+            bt = b.to(torch.float32).contiguous().to(device)
+            keep.extend([wt, bt])
+            return nat.PoemLinear(wt.data_ptr(), bt.data_ptr())
+        ch = self.channels
+        cp = [_pad64(c) for c in ch]
+        for i, c in enumerate(ch):
+            net.channels[i] = c
+        w1, b1 = _fold_stem(sd)
+        w1, b1 = w1.contiguous().to(device), b1.contiguous().to(device)
+        keep.extend([w1, b1])
+        net.stem1_w, net.stem1_b = w1.data_ptr(), b1.data_ptr()
+        net.stem2 = lin(*_fold(sd, "conv2", "bn2", 64, 64))
+        for k in range(4):
+            p = f"layer1.{k}."
+            cin = 64 if k == 0 else 256
+            bt = net.layer1[k]
+            bt.c1 = lin(*_fold(sd, p + "conv1", p + "bn1", cin, 64))
+            bt.c2 = lin(*_fold(sd, p + "conv2", p + "bn2", 64, 64))
+            bt.c3 = lin(*_fold(sd, p + "conv3", p + "bn3", 64, 256))
+            if k == 0:
+                bt.ds = lin(*_fold(sd, p + "downsample.0", p + "downsample.1", 64, 256))
+        net.trans1[0] = lin(*_fold(sd, "transition1.0.0", "transition1.0.1", 256, cp[0]))
+        net.trans1[1] = lin(*_fold(sd, "transition1.1.0.0", "transition1.1.0.1", 256, cp[1]))
+        net.trans2 = lin(*_fold(sd, "transition2.2.0.0", "transition2.2.0.1", cp[1], cp[2]))
+        net.trans3 = lin(*_fold(sd, "transition3.3.0.0", "transition3.3.0.1", cp[2], cp[3]))
+        for stage, n_mod in STAGE_MODULES.items():
+            mods = getattr(net, f"stage{stage}")
+            for m in range(n_mod):
+                mod = mods[m]
+                for b in range(stage):
+                    for k in range(4):
+                        p = f"stage{stage}.{m}.branches.{b}.{k}."
+                        mod.branch[b][k][0] = lin(*_fold(sd, p + "conv1", p + "bn1", cp[b], cp[b]))
+                        mod.branch[b][k][1] = lin(*_fold(sd, p + "conv2", p + "bn2", cp[b], cp[b]))
+                for i in range(stage):
+                    for j in range(stage):
+                        p = f"stage{stage}.{m}.fuse_layers.{i}.{j}."
+                        if j > i:
+                            mod.fuse[i][j][0] = lin(*_fold(sd, p + "0", p + "1", cp[j], cp[i]))
+                        elif j < i:
+                            for k in range(i - j):
+                                co = cp[i] if k == i - j - 1 else cp[j]
+                                mod.fuse[i][j][k] = lin(*_fold(sd, p + f"{k}.0", p + f"{k}.1", cp[j], co))
+        self._packed = (net, keep, str(device))
+        return net
+
+    @torch.no_grad()
+    def forward(self, x):
+        if not x.is_cuda:
+            raise nat.PoemError("HRNetW40 input must be a CUDA tensor: there is no CPU implementation")
+        dev = x.device
+        x = x.contiguous().float()
+        n, c, h, w = x.shape
+        assert c == 3 and h == w, tuple(x.shape)
+        lib = nat.load()
+        net = self._packed[0] if self._packed is not None and self._packed[2] == str(dev) else self._pack(dev)
+        need = lib.poem_hrnet_workspace_bytes(C.byref(net), n, h)
+        if need == 0:
+            raise nat.PoemError(f"HRNetW40: unsupported image size {h}")
+        if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+        off = (-self._ws.data_ptr()) % 1024
+        outs = [torch.empty(n, ch, (h // 4) >> b, (h // 4) >> b, device=dev) for b, ch in enumerate(self.channels)]
+        outs_p = (C.c_void_p * 4)(*[o.data_ptr() for o in outs])
+        nat.check(lib.poem_hrnet_forward(C.byref(net), n, h, x.data_ptr(), outs_p, self._ws.data_ptr() + off,
+                                         self._ws.numel() - off, torch.cuda.current_stream(dev).cuda_stream))
+        return outs
+
+
+def backbone_flops_per_image(img_res=256, channels=CHANNELS):
+    """Nominal multiply-add FLOPs (2 * Cout * Cin * k^2 * Hout * Wout, real channel counts) of one image, by section."""
+    base = img_res // 4
+    out = {}
+
+    def res_of(name):
+        t = name.split(".")
+        if t[0] == "conv1":
+            return img_res // 2
+        if t[0] in ("conv2", "layer1"):
+            return base
+        if t[0].startswith("transition"):
+            return base >> int(t[1])
+        if t[2] == "branches":
+            return base >> int(t[3])
+        i, j = int(t[3]), int(t[4])
+        return base >> j if j > i else base >> (j + int(t[5]) + 1)
+    for name, shape in backbone_param_shapes(channels).items():
+        if len(shape) != 4:
+            continue
+        r = res_of(name)
+        sec = name.split(".")[0]
+        sec = "stem" if sec in ("conv1", "conv2") else ("transitions" if sec.startswith("transition") else sec)
+        out[sec] = out.get(sec, 0.0) + 2.0 * shape[0] * shape[1] * shape[2] * shape[3] * r * r
+    return out

@@ -195,6 +195,34 @@ def make_stage4_state_dict(seed: int = 0, n_modules: int = 3):
     return sd
 
 
+def make_backbone_state_dict(seed: int = 0):
+    """Seeded weights for the whole HRNet-W40 backbone under the reference key names (same recipe as stage 4)."""
+    from .hrnet import backbone_param_shapes
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in backbone_param_shapes().items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(100)
+        elif name.endswith("running_var"):
+            sd[name] = 0.5 + torch.rand(shape, generator=g)
+        elif name.endswith("running_mean") or name.endswith(".bias"):
+            sd[name] = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[name] = 0.6 + 0.2 * torch.rand(shape, generator=g)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[name] = torch.randn(shape, generator=g) * math.sqrt(1.0 / fan_in)
+    return sd
+
+
+def make_images(n_images: int, res: int = 256, seed: int = 1):
+    """ImageNet-normalised-looking images: smooth low-frequency content plus pixel noise, roughly unit variance."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.randn(n_images, 3, res // 16, res // 16, generator=g)
+    img = torch.nn.functional.interpolate(low, size=(res, res), mode="bilinear", align_corners=False)
+    return img + 0.3 * torch.randn(n_images, 3, res, res, generator=g)
+
+
 def make_stage4_inputs(n_images: int, base_res: int = 64, seed: int = 1):
     g = torch.Generator().manual_seed(seed)
     return [torch.relu(torch.randn(n_images, c, base_res >> b, base_res >> b, generator=g))

@@ -169,6 +169,27 @@ def test_registers_under_reference_names():
     assert "REGISTERED-OK" in r.stdout, r.stdout + r.stderr
 
 
+def test_backbone_keeps_reference_state_dict_keys():
+    """HRNetW40 exposes the live keys of reference `HighResolutionNet` (hrnet.py:239-283): 1/4/3 modules in stages
+    2/3/4, Bottleneck layer1 with a downsample in block 0 only, transitions that only add the new branch."""
+    from poem_v2_b200.hrnet import HRNetW40, backbone_param_shapes
+    shapes = backbone_param_shapes()
+    m = HRNetW40()
+    assert set(m.state_dict()) == set(shapes)
+    convs = [k for k, v in shapes.items() if len(v) == 4]
+    assert len(convs) == 2 + 13 + 4 + (16 + 2) + 4 * (24 + 3 + 4) + 3 * (32 + 6 + 10)   # 305 convolutions
+    assert shapes["layer1.0.downsample.0.weight"] == (256, 64, 1, 1) and "layer1.1.downsample.0.weight" not in shapes
+    assert shapes["transition1.1.0.0.weight"] == (80, 256, 3, 3)
+    assert shapes["transition3.3.0.0.weight"] == (320, 160, 3, 3) and "transition3.0.0.weight" not in shapes
+    assert shapes["stage3.3.fuse_layers.2.0.1.0.weight"] == (160, 40, 3, 3)
+    sd = synth.make_backbone_state_dict(0)
+    sd["final_layer.0.weight"] = torch.zeros(2048, 1024, 1, 1)   # dead classification head: dropped
+    m.load_state_dict(sd, strict=True)
+    assert torch.equal(m.state_dict()["stage2.0.branches.1.3.bn2.running_var"], sd["stage2.0.branches.1.3.bn2.running_var"])
+    with pytest.raises(nat.PoemError, match="no CPU implementation"):
+        m(torch.zeros(1, 3, 256, 256))
+
+
 def test_shard_bounds_cover_and_balance():
     for views, world in [([8] * 32, 8), ([8] * 32, 2), ([1, 8, 2, 2, 7, 3], 2), ([4, 4, 4], 4), ([2] * 5, 4)]:
         b = shard.shard_bounds(views, world)

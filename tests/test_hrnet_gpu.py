@@ -99,3 +99,71 @@ def test_stage4_matches_reference_golden():
     sub = [got[0][:, :, ::4, ::4], got[1][:, :, ::2, ::2], got[2], got[3]]
     for g_, w_ in zip(sub, want):
         assert (g_ - w_).abs().max().item() <= 3e-2 * w_.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ whole backbone (f1)
+def _check_maps(got, want, label, max_frac=5e-2, mean_frac=5e-3):
+    for b, (g_, w_) in enumerate(zip(got, want)):
+        assert g_.shape == w_.shape and torch.isfinite(g_).all()
+        err = (g_ - w_).abs()
+        scale = w_.abs().max().item()
+        rel_l2 = ((g_ - w_).norm() / w_.norm()).item()
+        print(f"{label} branch {b}: max err {err.max().item():.4f} mean err {err.mean().item():.5f} rel-L2 {rel_l2:.2e} "
+              f"(|ref| max {scale:.2f}, mean {w_.abs().mean().item():.3f})")
+        # ~150 bf16 convolutions deep with bf16 activations in between
+        assert err.max().item() <= max_frac * scale
+        assert err.mean().item() <= mean_frac * scale
+        assert rel_l2 <= 2e-2
+
+
+@pytest.mark.parametrize("N", [1, 3])
+def test_backbone_matches_oracle(N):
+    from poem_v2_b200.hrnet import HRNetW40
+    sd = synth.make_backbone_state_dict(0)
+    img = synth.make_images(N, 256, 1)
+    with torch.no_grad():
+        want = orc.hrnet_forward(sd, img)
+    m = HRNetW40()
+    m.load_state_dict(sd, strict=True)
+    got = [g.cpu() for g in m(img.cuda())]
+    _check_maps(got, want, f"backbone N={N}")
+
+
+def test_backbone_matches_reference_golden():
+    import ast
+    import os
+    import numpy as np
+    from poem_v2_b200.hrnet import HRNetW40
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hrnet_w40_n1.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    sd = synth.make_backbone_state_dict(meta["wseed"])
+    sd["classifier.weight"] = torch.zeros(1000, 2048)        # dead classification-head key: accepted and dropped
+    m = HRNetW40()
+    m.load_state_dict(sd, strict=True)
+    got = [g.cpu() for g in m(synth.make_images(meta["n_images"], 256, meta["iseed"]).cuda())]
+    want = [torch.from_numpy(z[f"y{b}"]) for b in range(4)]
+    sub = [got[0][:, :, ::4, ::4], got[1][:, :, ::2, ::2], got[2], got[3]]
+    _check_maps(sub, want, "backbone golden")
+
+
+def test_backbone_deterministic():
+    from poem_v2_b200.hrnet import HRNetW40
+    sd = synth.make_backbone_state_dict(3)
+    m = HRNetW40()
+    m.load_state_dict(sd, strict=True)
+    img = synth.make_images(2, 256, 5).cuda()
+    a = m(img)
+    b = m(img)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)          # deterministic
+
+
+def test_backbone_rejects_bad_input():
+    from poem_v2_b200.hrnet import HRNetW40
+    m = HRNetW40()
+    with pytest.raises(nat.PoemError):
+        m(torch.zeros(1, 3, 256, 256))                  # CPU tensor: no CPU implementation
+    with pytest.raises(nat.PoemError):
+        m(torch.zeros(1, 3, 224, 224, device="cuda"))   # only the 256x256 release resolution
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({"conv1.weight": torch.zeros(64, 3, 3, 3)}, strict=True)
