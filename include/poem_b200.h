@@ -137,6 +137,9 @@ size_t poem_profile_summary(char* buf, size_t cap);
 /* Test hook: route poem_vector_attention through the un-fused composition (token tensors in HBM) so the fused
  * kernel can be checked against it on the device.  Not used by the product path. */
 void poem_debug_force_unfused(int on);
+/* Test hook: 0 = 3x3 stride-1 C->C convolutions use the halo-reuse kernel (default); 2 = every convolution takes the
+ * generic implicit-GEMM path (so the two can be compared on the device). */
+void poem_debug_conv_mode(int mode);
 
 /* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
 size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);

@@ -111,7 +111,7 @@ class PoemInputs(C.Structure):
 
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
-           "poem_profile_summary", "poem_debug_force_unfused", "poem_hrnet_stage4_workspace_bytes",
+           "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_hrnet_stage4_workspace_bytes",
            "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",

@@ -1,0 +1,289 @@
+// 3x3 stride-1 convolution with halo reuse (the BasicBlock convolutions of HRNet, reference
+// lib/models/backbones/hrnet.py:38-67 — 212 of the backbone's 305 convolutions and 85 % of its FLOPs).
+//
+// The generic implicit-GEMM path (gemm.cuh, ConvOperand) re-fetches every input pixel once per filter tap: 9 x the
+// activation bytes travel L2 -> smem and that, not the tensor core, bounds it.  Here a CTA owns a 16x16 output patch
+// and fetches its 18x18 input halo ONCE per 64-channel block with one 4-D TMA box (64 ch, 18 px, 18 rows; zero fill
+// outside the image = padding).  The nine taps are then nine *shifted views* of that smem patch:
+//   * an MMA M-tile is 16 image rows x 8 pixels, so an 8-row core-matrix group = 8 consecutive pixels of one image row
+//     (128 B each, SWIZZLE_128B) and the stride between groups (SBO) is the uniform smem row pitch 18 x 128 B;
+//   * tap (ky, kx) of sub-tile s starts at pixel (ky, kx + 8 s) of the patch: a 128-byte-granular start address that
+//     is NOT 1024-byte aligned.  Measured on B200 (scripts/exp_halo.py): the tensor core applies the 128-byte swizzle
+//     XOR to the bits of the final shared-memory address, exactly like TMA does when it writes the box, so any
+//     128-byte-aligned start and any SBO address the TMA-written patch correctly with descriptor base offset 0
+//     (setting base offset = (start >> 7) & 7 gives wrong results).
+// Two sub-tiles (left / right 8 columns) share the patch and every weight tile -> L2 -> smem traffic per output pixel
+// drops from 9 x 128 B (+ weights per 128 px) to 1.27 x 128 B (+ weights per 256 px; resident in smem when C = 64).
+// What bounds the kernel after that is shared-memory bandwidth: an SS-mode MMA reads 128 x 32 B of A and C x 32 B of B
+// per K = 16 step (C = 64: 192 B/clk against the 128 B/clk the SM delivers), so the epilogue keeps out of smem:
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue straight from the TMEM layout
+//   (lane = pixel, 32 channels = 64 contiguous bytes: 256-bit shortcut loads and stores, bias broadcast from smem);
+//   accumulators double-buffered in TMEM when 4 x C columns fit (C <= 128).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace poem {
+
+template <int CP>
+struct HaloCfg {
+  static_assert(CP == 64 || CP == 128 || CP == 192, "padded channel count");
+  static constexpr int kCB = CP / 64;                  // 64-channel blocks (K blocks per tap)
+  static constexpr int kPitch = 18;                    // patch pixels per smem row
+  static constexpr int kRows = 18;
+  static constexpr int kABytes = kRows * kPitch * 128; // 41,472 bytes landed per patch
+  static constexpr int kAStride = (kABytes + 1023) / 1024 * 1024;
+  static constexpr int kAStages = 3;
+  static constexpr int kBBytes = CP * 128;             // [CP out-channel rows][64 k] bf16
+  static constexpr bool kBResident = (CP == 64);       // all nine weight tiles stay in smem
+  static constexpr int kBStages = kBResident ? 9 : (CP == 128 ? 6 : 4);
+  static constexpr int kAccPairs = (4 * CP <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = (2 * kAccPairs * CP <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kAStages * kAStride + kBStages * kBBytes + CP * 4 + 256;
+};
+
+constexpr int HALO_THREADS = 64 + 32 * 8;
+
+struct HaloArgs {
+  int n_images, R;                  // square maps, R % 16 == 0
+  const float* bias;                // [CP]
+  int relu;                         // ReLU after bias (+ residual)
+  const __nv_bfloat16* res;         // NHWC identity shortcut or nullptr
+  __nv_bfloat16* out;               // NHWC
+};
+
+// K-major SWIZZLE_128B descriptor with explicit group stride and base offset (bits [49,52))
+__device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
+}
+
+// 256-bit global accesses (sm_100: LDG.256 / STG.256), one full 32-byte sector per lane
+__device__ __forceinline__ void ldg_nc_256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+template <int CP>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, HaloArgs a) {
+  using Cfg = HaloCfg<CP>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* s_a = smem;                                        // [kAStages][kAStride]
+  uint8_t* s_b = smem + Cfg::kAStages * Cfg::kAStride;        // [kBStages][kBBytes]
+  float* s_bias = reinterpret_cast<float*>(s_b + Cfg::kBStages * Cfg::kBBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + CP);
+  uint64_t* a_full = bars;            // [3]
+  uint64_t* a_empty = bars + 3;       // [3]
+  uint64_t* b_full = bars + 6;        // [9]  (resident mode: b_full[0] only)
+  uint64_t* b_empty = bars + 15;      // [9]
+  uint64_t* tmem_full = bars + 24;    // [2]
+  uint64_t* tmem_empty = bars + 26;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int tiles_x = a.R / 16;
+  const int tiles_per_img = tiles_x * tiles_x;
+  const int num_tiles = a.n_images * tiles_per_img;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kAStages; ++s) {
+        mbar_init(&a_full[s], 1);
+        mbar_init(&a_empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full[s], 1);
+        mbar_init(&tmem_empty[s], 8);
+      }
+      for (int s = 0; s < 9; ++s) {
+        mbar_init(&b_full[s], 1);
+        mbar_init(&b_empty[s], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  for (int j = threadIdx.x; j < CP; j += HALO_THREADS) s_bias[j] = a.bias ? __ldg(a.bias + j) : 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (Cfg::kBResident) {
+        mbar_expect_tx(&b_full[0], 9u * Cfg::kBBytes);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_b + tap * Cfg::kBBytes, &tmap_w, &b_full[0], tap * CP, 0);
+      }
+      const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int steps = my_tiles * Cfg::kCB;   // (tile, channel block) pairs, in order
+      auto load_patch = [&](int step) {
+        const int tile = (int)blockIdx.x + (step / Cfg::kCB) * (int)gridDim.x;
+        const int cb = step % Cfg::kCB;
+        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
+        const int st = step % Cfg::kAStages;
+        mbar_wait(&a_empty[st], ((step / Cfg::kAStages) & 1) ^ 1);
+        mbar_expect_tx(&a_full[st], (uint32_t)Cfg::kABytes);
+        tma_load_4d(s_a + st * Cfg::kAStride, &tmap_x, &a_full[st], cb * 64, x0 - 1, y0 - 1, n);
+      };
+      int bs = 0;
+      uint32_t bphase = 0;
+      for (int step = 0; step < Cfg::kAStages - 1 && step < steps; ++step) load_patch(step);
+      for (int step = 0; step < steps; ++step) {
+        // the patch two steps ahead goes out before this block's weight tiles
+        if (step + Cfg::kAStages - 1 < steps) load_patch(step + Cfg::kAStages - 1);
+        if (!Cfg::kBResident) {
+          const int cb = step % Cfg::kCB;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bphase ^ 1);
+            mbar_expect_tx(&b_full[bs], (uint32_t)Cfg::kBBytes);
+            tma_load_2d(s_b + bs * Cfg::kBBytes, &tmap_w, &b_full[bs], tap * CP + cb * 64, 0);
+            if (++bs == Cfg::kBStages) {
+              bs = 0;
+              bphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, CP);
+      int step = 0, bs = 0, acc = 0;
+      uint32_t bphase = 0, acc_phase = 0;
+      if (Cfg::kBResident) mbar_wait(&b_full[0], 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2) * CP;
+        for (int cb = 0; cb < Cfg::kCB; ++cb, ++step) {
+          const int st = step % Cfg::kAStages;
+          mbar_wait(&a_full[st], (step / Cfg::kAStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t pa = smem_u32(s_a + st * Cfg::kAStride);
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t pb;
+            if (Cfg::kBResident) {
+              pb = smem_u32(s_b + tap * Cfg::kBBytes);
+            } else {
+              mbar_wait(&b_full[bs], bphase);
+              tc_fence_after_sync();
+              pb = smem_u32(s_b + bs * Cfg::kBBytes);
+            }
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            const uint64_t db = make_kmajor_desc<128>(pb);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint32_t start = pa + (uint32_t)((ky * Cfg::kPitch + kx + 8 * sub) * 128);
+              const uint64_t da = make_kmajor_desc_ex(start, Cfg::kPitch * 128, 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d0 + sub * CP, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+            }
+            if (!Cfg::kBResident) {
+              umma_commit(&b_empty[bs]);
+              if (++bs == Cfg::kBStages) {
+                bs = 0;
+                bphase ^= 1;
+              }
+            }
+          }
+          umma_commit(&a_empty[st]);
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == Cfg::kAccPairs) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9) =====================
+    // TMEM lane m = 32 q + lane is the pixel (row y0 + m / 8, column x0 + 8 sub + m % 8); a 32-channel chunk of it is 64
+    // contiguous bytes of the NHWC tensor, moved as two 256-bit accesses.  Warps q and q + 4 split the chunks by parity.
+    const int quarter = warp & 3;
+    const int par = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const size_t off = (((size_t)n * a.R + (y0 + quarter * 4 + (lane >> 3))) * a.R + (x0 + sub * 8 + (lane & 7))) * CP;
+        uint32_t rres[Cfg::kCB][16];
+        if (a.res != nullptr) {   // every shortcut load of this sub-tile is in flight before the accumulator is awaited
+#pragma unroll
+          for (int j = 0; j < Cfg::kCB; ++j) {
+            const __nv_bfloat16* rp = a.res + off + (2 * j + par) * 32;
+            ldg_nc_256(rp, &rres[j][0]);
+            ldg_nc_256(rp + 16, &rres[j][8]);
+          }
+        }
+        if (sub == 0) {
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int j = 0; j < Cfg::kCB; ++j) {
+          const int c0 = (2 * j + par) * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub) * CP + c0), r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+            float v0 = __uint_as_float(r[4 * q]) + b4.x, v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
+            float v2 = __uint_as_float(r[4 * q + 2]) + b4.z, v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
+            if (a.res != nullptr) {
+              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j][2 * q]));
+              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j][2 * q + 1]));
+              v0 += f0.x, v1 += f0.y, v2 += f1.x, v3 += f1.y;
+            }
+            if (a.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+            pk[2 * q] = pack_bf16x2(v0, v1);
+            pk[2 * q + 1] = pack_bf16x2(v2, v3);
+          }
+          __nv_bfloat16* op = a.out + off + c0;
+          stg_256(op, &pk[0]);
+          stg_256(op + 16, &pk[8]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == Cfg::kAccPairs) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace poem

@@ -11,6 +11,7 @@
 
 #include "../../include/poem_b200.h"
 #include "gemm.cuh"
+#include "conv3x3.cuh"
 #include "mha.cuh"
 #include "hrnet.cuh"
 #include "simt.cuh"
@@ -280,6 +281,44 @@ static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W
   return POEM_OK;
 }
 
+// 3x3 stride-1 C -> C convolution with halo reuse (conv3x3.cuh)
+static int g_conv_mode = 0;   // 0: halo-reuse kernel where it applies; 2: every convolution on the generic path
+extern "C" void poem_debug_conv_mode(int mode) { g_conv_mode = mode; }
+
+template <int CP>
+static int launch_conv3x3_halo_cp(const CUtensorMap& tx, const CUtensorMap& tw, const HaloArgs& a, cudaStream_t st) {
+  using Cfg = HaloCfg<CP>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = a.n_images * (a.R / 16) * (a.R / 16);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  prof_begin(st);
+  conv3x3_halo_kernel<CP><<<grid, HALO_THREADS, Cfg::kSmemBytes, st>>>(tx, tw, a);
+  LAUNCH_CHECK("conv3x3_halo_kernel");
+  return POEM_OK;
+}
+
+static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cp, const PoemLinear& wt, bool relu,
+                               const __nv_bfloat16* res, __nv_bfloat16* out, cudaStream_t st) {
+  CUtensorMap tx, tw;
+  POEM_TRY(make_tmap_nhwc(&tx, in, N, R, R, Cp, HaloCfg<64>::kPitch, HaloCfg<64>::kRows, 1, 1));
+  POEM_TRY(make_tmap_bf16(&tw, wt.w, (uint64_t)Cp, (uint64_t)9 * Cp, (uint64_t)9 * Cp, 64, (uint32_t)Cp));
+  HaloArgs a;
+  a.n_images = N, a.R = R, a.bias = wt.b, a.relu = relu ? 1 : 0, a.res = res, a.out = out;
+  char tag[48];
+  snprintf(tag, sizeof(tag), "conv3x3halo_c%d_r%d", Cp, R);
+  TagScope ts(tag);
+  switch (Cp) {
+    case 64: return launch_conv3x3_halo_cp<64>(tx, tw, a, st);
+    case 128: return launch_conv3x3_halo_cp<128>(tx, tw, a, st);
+    case 192: return launch_conv3x3_halo_cp<192>(tx, tw, a, st);
+  }
+  return fail(POEM_E_BADDIM, "conv3x3 halo: C=%d", Cp);
+}
+
 // out[N, Hout, Wout, Cout_p] = act(conv(in[N, Hin, Win, Cin_p], w[Cout_p, k*k*Cin_p]) + b) (+ res)
 static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
                        int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
@@ -287,6 +326,9 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   if (!wt.w || !wt.b) return fail(POEM_E_NULL, "conv: weight pointer missing");
   if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
     return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
+  if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Cin_p == Cout_p && Hin == Win && Hin % 16 == 0 &&
+      (Cin_p == 64 || Cin_p == 128 || Cin_p == 192))
+    return launch_conv3x3_halo(in, N, Hin, Cin_p, wt, relu, res, out, st);
   const int Hout = Hin / stride, Wout = Win / stride;
   if (Wout < 1 || 128 % Wout || Wout > 128 || Cin_p % 64 || Cout_p % 32)
     return fail(POEM_E_BADDIM, "conv: unsupported shape %dx%d C %d -> %d", Hin, Win, Cin_p, Cout_p);
