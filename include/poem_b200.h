@@ -137,8 +137,9 @@ size_t poem_profile_summary(char* buf, size_t cap);
 /* Test hook: route poem_vector_attention through the un-fused composition (token tensors in HBM) so the fused
  * kernel can be checked against it on the device.  Not used by the product path. */
 void poem_debug_force_unfused(int on);
-/* Test hook: 0 = 3x3 stride-1 C->C convolutions use the halo-reuse kernel (default); 2 = every convolution takes the
- * generic implicit-GEMM path (so the two can be compared on the device). */
+/* Test hook: 0 = 3x3 stride-1 C->C convolutions use the halo-reuse kernel on the live channels (default); 1 = halo
+ * kernel on all padded channels; 2 = every convolution takes the generic implicit-GEMM path (so the variants can be
+ * compared on the device). */
 void poem_debug_conv_mode(int mode);
 
 /* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
@@ -216,9 +217,12 @@ int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res, const floa
 
 /* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
  * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
+ * c_live > 0 promises that only the first c_live input AND output channels are non-zero (the rest of the padded
+ * tensors, weights and bias is zero padding), which lets the 3x3 stride-1 kernel skip the padding; 0 = no promise.
  * Replaces nn.Conv2d + nn.BatchNorm2d(eval) (+ReLU, + identity) of hrnet.py:38-67,177-207. */
 int poem_conv_nhwc(const poem_bf16* in, int n_images, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
-                   int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out, void* stream);
+                   int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out, int c_live,
+                   void* stream);
 
 /* ---- stage-level entry points (unit-testable building blocks; same kernels the whole path uses) ---- */
 

@@ -182,7 +182,9 @@ def load():
     lib.poem_hrnet_forward.restype = i
     lib.poem_hrnet_forward.argtypes = [C.POINTER(PoemHRNet), i, i, vp, C.POINTER(vp), vp, sz, vp]
     lib.poem_conv_nhwc.restype = i
-    lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp]
+    lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, i, vp]
+    lib.poem_debug_conv_mode.restype = None
+    lib.poem_debug_conv_mode.argtypes = [i]
     lib.poem_layernorm.restype = i
     lib.poem_layernorm.argtypes = [vp, vp, vp, vp, vp, i, i, vp]
     _lib = lib

@@ -19,6 +19,11 @@
 //   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue straight from the TMEM layout
 //   (lane = pixel, 32 channels = 64 contiguous bytes: 256-bit shortcut loads and stores, bias broadcast from smem);
 //   accumulators double-buffered in TMEM when 4 x C columns fit (C <= 128).
+// Real channel counts: HRNet-W40 has 40 / 80 / 160 channels stored padded to 64 / 128 / 192.  Multiplying the padding
+// costs 2.6x / 2.6x / 1.4x the useful MMA work, so the K and N extents follow CR = the real count rounded up to 16:
+// K is cut into blocks of 64 channels (SWIZZLE_128B), then 32 (SWIZZLE_64B), then 16 (SWIZZLE_32B) — each block is its
+// own TMA box of the same padded NHWC tensor with the matching swizzle and smem descriptor — and N = CR.  The epilogue
+// writes the CP - CR padding channels as zeros so every consumer still sees a clean padded tensor.
 #pragma once
 #include <cuda.h>
 
@@ -26,21 +31,35 @@
 
 namespace poem {
 
-template <int CP>
+// K blocks of a CR-channel operand: CR / 64 blocks of 64 channels, then the remainder as 32 and / or 16 channels
+template <int CR>
+struct HaloBlocks {
+  static_assert(CR % 16 == 0 && CR >= 16, "real channel count is rounded up to 16");
+  static constexpr int n64 = CR / 64;
+  static constexpr int tail = CR % 64;   // 0, 16, 32 or 48
+  static constexpr int n = n64 + (tail == 48 ? 2 : (tail ? 1 : 0));
+  __host__ __device__ static constexpr int ch0(int b) { return b <= n64 ? 64 * b : 64 * n64 + 32; }
+  __host__ __device__ static constexpr int nch(int b) { return b < n64 ? 64 : (b == n64 ? (tail == 16 ? 16 : 32) : 16); }
+};
+
+template <int CP, int CR>
 struct HaloCfg {
   static_assert(CP == 64 || CP == 128 || CP == 192, "padded channel count");
-  static constexpr int kCB = CP / 64;                  // 64-channel blocks (K blocks per tap)
+  static_assert(CR <= CP && CR > CP - 64, "CR is the real channel count rounded up to 16");
+  using Blk = HaloBlocks<CR>;
+  static constexpr int kNB = Blk::n;                   // K blocks per tap
   static constexpr int kPitch = 18;                    // patch pixels per smem row
   static constexpr int kRows = 18;
-  static constexpr int kABytes = kRows * kPitch * 128; // 41,472 bytes landed per patch
-  static constexpr int kAStride = (kABytes + 1023) / 1024 * 1024;
+  static constexpr int kAStride = (kRows * kPitch * 128 + 1023) / 1024 * 1024;   // room for a 64-channel patch
   static constexpr int kAStages = 3;
-  static constexpr int kBBytes = CP * 128;             // [CP out-channel rows][64 k] bf16
-  static constexpr bool kBResident = (CP == 64);       // all nine weight tiles stay in smem
-  static constexpr int kBStages = kBResident ? 9 : (CP == 128 ? 6 : 4);
+  static constexpr int kBStride = CR * 128;            // room for a [CR out-channel rows][64 k] tile
+  static constexpr int kTapBytes = CR * CR * 2;        // resident mode: the kNB tiles of one tap, packed
+  static constexpr bool kBResident = (CP == 64);       // all nine taps' weight tiles stay in smem
+  static constexpr int kBStages = CP == 128 ? 6 : 4;   // streaming mode ring depth
+  static constexpr int kBBytesTotal = kBResident ? 9 * kTapBytes : kBStages * kBStride;
   static constexpr int kAccPairs = (4 * CP <= 512) ? 2 : 1;
   static constexpr int kTmemCols = (2 * kAccPairs * CP <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kAStages * kAStride + kBStages * kBBytes + CP * 4 + 256;
+  static constexpr int kSmemBytes = kAStages * kAStride + (kBBytesTotal + 1023) / 1024 * 1024 + CP * 4 + 256;
 };
 
 constexpr int HALO_THREADS = 64 + 32 * 8;
@@ -53,11 +72,19 @@ struct HaloArgs {
   __nv_bfloat16* out;               // NHWC
 };
 
-// K-major SWIZZLE_128B descriptor with explicit group stride and base offset (bits [49,52))
-__device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+// K-major descriptor for rows of `row_bytes` (128 / 64 / 32 -> SWIZZLE_128B / 64B / 32B) with an explicit stride
+// between 8-row groups; base offset stays 0 (see above).
+__device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
-         ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
+         (layout << 61);
 }
+
+struct HaloMaps {
+  CUtensorMap x[3];   // activation boxes of 64 / 32 / 16 channels (SWIZZLE_128B / 64B / 32B)
+  CUtensorMap w[3];   // weight boxes [CR rows][64 / 32 / 16 k]
+};
+__host__ __device__ constexpr int halo_map_index(int nch) { return nch == 64 ? 0 : (nch == 32 ? 1 : 2); }
 
 // 256-bit global accesses (sm_100: LDG.256 / STG.256), one full 32-byte sector per lane
 __device__ __forceinline__ void ldg_nc_256(const void* p, uint32_t* r) {
@@ -71,18 +98,19 @@ __device__ __forceinline__ void stg_256(void* p, const uint32_t* r) {
                : "memory");
 }
 
-template <int CP>
+template <int CP, int CR>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, HaloArgs a) {
-  using Cfg = HaloCfg<CP>;
+conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
+  using Cfg = HaloCfg<CP, CR>;
+  using Blk = typename Cfg::Blk;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* s_a = smem;                                        // [kAStages][kAStride]
-  uint8_t* s_b = smem + Cfg::kAStages * Cfg::kAStride;        // [kBStages][kBBytes]
-  float* s_bias = reinterpret_cast<float*>(s_b + Cfg::kBStages * Cfg::kBBytes);
+  uint8_t* s_b = smem + Cfg::kAStages * Cfg::kAStride;        // [kBStages][kBStride] or [9][kTapBytes]
+  float* s_bias = reinterpret_cast<float*>(s_b + (Cfg::kBBytesTotal + 1023) / 1024 * 1024);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + CP);
   uint64_t* a_full = bars;            // [3]
   uint64_t* a_empty = bars + 3;       // [3]
@@ -97,8 +125,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int num_tiles = a.n_images * tiles_per_img;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_x);
-    tma_prefetch_desc(&tmap_w);
+    for (int b = 0; b < Cfg::kNB; ++b) {
+      tma_prefetch_desc(&maps.x[halo_map_index(Blk::nch(b))]);
+      tma_prefetch_desc(&maps.w[halo_map_index(Blk::nch(b))]);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -129,20 +159,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       if (Cfg::kBResident) {
-        mbar_expect_tx(&b_full[0], 9u * Cfg::kBBytes);
-        for (int tap = 0; tap < 9; ++tap) tma_load_2d(s_b + tap * Cfg::kBBytes, &tmap_w, &b_full[0], tap * CP, 0);
+        mbar_expect_tx(&b_full[0], 9u * Cfg::kTapBytes);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int b = 0; b < Cfg::kNB; ++b)
+            tma_load_2d(s_b + tap * Cfg::kTapBytes + CR * Blk::ch0(b) * 2, &maps.w[halo_map_index(Blk::nch(b))], &b_full[0],
+                        tap * CP + Blk::ch0(b), 0);
       }
       const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-      const int steps = my_tiles * Cfg::kCB;   // (tile, channel block) pairs, in order
+      const int steps = my_tiles * Cfg::kNB;   // (tile, K block) pairs, in order
       auto load_patch = [&](int step) {
-        const int tile = (int)blockIdx.x + (step / Cfg::kCB) * (int)gridDim.x;
-        const int cb = step % Cfg::kCB;
+        const int tile = (int)blockIdx.x + (step / Cfg::kNB) * (int)gridDim.x;
+        const int b = step % Cfg::kNB;
         const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
         const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
         const int st = step % Cfg::kAStages;
         mbar_wait(&a_empty[st], ((step / Cfg::kAStages) & 1) ^ 1);
-        mbar_expect_tx(&a_full[st], (uint32_t)Cfg::kABytes);
-        tma_load_4d(s_a + st * Cfg::kAStride, &tmap_x, &a_full[st], cb * 64, x0 - 1, y0 - 1, n);
+        mbar_expect_tx(&a_full[st], (uint32_t)(Cfg::kRows * Cfg::kPitch * Blk::nch(b) * 2));
+        tma_load_4d(s_a + st * Cfg::kAStride, &maps.x[halo_map_index(Blk::nch(b))], &a_full[st], Blk::ch0(b), x0 - 1, y0 - 1, n);
       };
       int bs = 0;
       uint32_t bphase = 0;
@@ -151,11 +184,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         // the patch two steps ahead goes out before this block's weight tiles
         if (step + Cfg::kAStages - 1 < steps) load_patch(step + Cfg::kAStages - 1);
         if (!Cfg::kBResident) {
-          const int cb = step % Cfg::kCB;
+          const int b = step % Cfg::kNB;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bs], bphase ^ 1);
-            mbar_expect_tx(&b_full[bs], (uint32_t)Cfg::kBBytes);
-            tma_load_2d(s_b + bs * Cfg::kBBytes, &tmap_w, &b_full[bs], tap * CP + cb * 64, 0);
+            mbar_expect_tx(&b_full[bs], (uint32_t)(CR * Blk::nch(b) * 2));
+            tma_load_2d(s_b + bs * Cfg::kBStride, &maps.w[halo_map_index(Blk::nch(b))], &b_full[bs], tap * CP + Blk::ch0(b), 0);
             if (++bs == Cfg::kBStages) {
               bs = 0;
               bphase ^= 1;
@@ -167,7 +200,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, CP);
+      constexpr uint32_t idesc = make_idesc_bf16(128, CR);
       int step = 0, bs = 0, acc = 0;
       uint32_t bphase = 0, acc_phase = 0;
       if (Cfg::kBResident) mbar_wait(&b_full[0], 0);
@@ -175,7 +208,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 2) * CP;
-        for (int cb = 0; cb < Cfg::kCB; ++cb, ++step) {
+#pragma unroll
+        for (int b = 0; b < Cfg::kNB; ++b, ++step) {
+          const int nch = Blk::nch(b);
+          const uint32_t row_bytes = (uint32_t)nch * 2;
           const int st = step % Cfg::kAStages;
           mbar_wait(&a_full[st], (step / Cfg::kAStages) & 1);
           tc_fence_after_sync();
@@ -183,20 +219,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           for (int tap = 0; tap < 9; ++tap) {
             uint32_t pb;
             if (Cfg::kBResident) {
-              pb = smem_u32(s_b + tap * Cfg::kBBytes);
+              pb = smem_u32(s_b + tap * Cfg::kTapBytes + CR * Blk::ch0(b) * 2);
             } else {
               mbar_wait(&b_full[bs], bphase);
               tc_fence_after_sync();
-              pb = smem_u32(s_b + bs * Cfg::kBBytes);
+              pb = smem_u32(s_b + bs * Cfg::kBStride);
             }
             const int ky = tap / 3, kx = tap - 3 * ky;
-            const uint64_t db = make_kmajor_desc<128>(pb);
+            const uint64_t db = make_kmajor_desc_ex(pb, 8 * row_bytes, row_bytes);
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
-              const uint32_t start = pa + (uint32_t)((ky * Cfg::kPitch + kx + 8 * sub) * 128);
-              const uint64_t da = make_kmajor_desc_ex(start, Cfg::kPitch * 128, 0u);
+              const uint32_t start = pa + (uint32_t)(ky * Cfg::kPitch + kx + 8 * sub) * row_bytes;
+              const uint64_t da = make_kmajor_desc_ex(start, Cfg::kPitch * row_bytes, row_bytes);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(d0 + sub * CP, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                if (k < nch / 16) umma_bf16(d0 + sub * CP, da + 2 * k, db + 2 * k, idesc, (b | tap | k) != 0);
             }
             if (!Cfg::kBResident) {
               umma_commit(&b_empty[bs]);
@@ -221,6 +258,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // contiguous bytes of the NHWC tensor, moved as two 256-bit accesses.  Warps q and q + 4 split the chunks by parity.
     const int quarter = warp & 3;
     const int par = (warp - 2) >> 2;
+    constexpr int kChunks = CP / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -229,13 +267,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
         const size_t off = (((size_t)n * a.R + (y0 + quarter * 4 + (lane >> 3))) * a.R + (x0 + sub * 8 + (lane & 7))) * CP;
-        uint32_t rres[Cfg::kCB][16];
+        // this warp's chunks are 2 j + par; chunk c covers channels [32 c, 32 c + 32): real below CR, zero padding above
+        uint32_t rres[kChunks][16];
         if (a.res != nullptr) {   // every shortcut load of this sub-tile is in flight before the accumulator is awaited
 #pragma unroll
-          for (int j = 0; j < Cfg::kCB; ++j) {
-            const __nv_bfloat16* rp = a.res + off + (2 * j + par) * 32;
-            ldg_nc_256(rp, &rres[j][0]);
-            ldg_nc_256(rp + 16, &rres[j][8]);
+          for (int j = 0; j < kChunks; ++j) {
+            const int c0 = (2 * j + par) * 32;
+            if (c0 < CR) {
+              const __nv_bfloat16* rp = a.res + off + c0;
+              ldg_nc_256(rp, &rres[j][0]);
+              ldg_nc_256(rp + 16, &rres[j][8]);
+            }
           }
         }
         if (sub == 0) {
@@ -243,14 +285,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           tc_fence_after_sync();
         }
 #pragma unroll
-        for (int j = 0; j < Cfg::kCB; ++j) {
+        for (int j = 0; j < kChunks; ++j) {
           const int c0 = (2 * j + par) * 32;
+          __nv_bfloat16* op = a.out + off + c0;
+          uint32_t pk[16];
+          if (c0 >= CR) {   // pure padding chunk (warp-uniform)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) pk[q] = 0u;
+            stg_256(op, &pk[0]);
+            stg_256(op + 16, &pk[8]);
+            continue;
+          }
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub) * CP + c0), r);
           tmem_ld_wait();
-          uint32_t pk[16];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
+            if (c0 + 4 * q >= CR) {   // columns past N = CR were never written by the MMA
+              pk[2 * q] = 0u;
+              pk[2 * q + 1] = 0u;
+              continue;
+            }
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
             float v0 = __uint_as_float(r[4 * q]) + b4.x, v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
             float v2 = __uint_as_float(r[4 * q + 2]) + b4.z, v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
@@ -263,7 +318,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             pk[2 * q] = pack_bf16x2(v0, v1);
             pk[2 * q + 1] = pack_bf16x2(v2, v3);
           }
-          __nv_bfloat16* op = a.out + off + c0;
           stg_256(op, &pk[0]);
           stg_256(op + 16, &pk[8]);
         }

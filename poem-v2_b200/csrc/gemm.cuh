@@ -90,7 +90,9 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+// kRes: the epilogue has a residual operand (ep.res_mode != RES_NONE).  Compile-time so that the residual-free
+// instantiation carries none of the prefetch registers / branches.
+template <int BN, bool kRes>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
                     int N, int K, GemmEpilogue ep, ConvOperand conv, GemmPipe pipe) {
@@ -239,6 +241,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int cg = (lane & 3) * 8;     // first of this lane's 8 columns inside a 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
+    // residual row of output row m: fp32 or bf16 pointer (nullptr when absent / out of range) and the RES_MERGE scale
+    auto res_row = [&](int m, const float*& pf, const __nv_bfloat16*& pb, float& scale) {
+      pf = nullptr;
+      pb = nullptr;
+      scale = 1.0f;
+      if (!kRes || m >= M) return;
+      if (ep.res_mode == RES_F32) {
+        pf = ep.res_f32 + (size_t)m * ep.res_ld;
+      } else if (ep.res_mode == RES_POSADD) {
+        pf = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
+      } else if (ep.res_mode == RES_BF16) {
+        pb = ep.res_bf16 + (size_t)m * ep.res_ld;
+      } else if (ep.res_mode == RES_MERGE) {
+        const int g = m / ep.rows_per_group;
+        const int cnt = ep.row_cnt[g];
+        scale = 1.0f / (float)cnt;
+        pb = ep.res_bf16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+      }
+    };
     for (int it = it0; it < it_end; it += it_step) {
       const int m0 = (wst ? it : it / tiles_n) * GEMM_BM;
       const int n0 = (wst ? my_n_tile : it % tiles_n) * BN;
@@ -257,23 +278,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int mrow[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = m0 + quarter * 32 + 8 * i + sr;
-        mrow[i] = m;
-        resf[i] = nullptr;
-        resb[i] = nullptr;
-        rscale[i] = 1.0f;
-        if (m < M) {
-          if (ep.res_mode == RES_F32) {
-            resf[i] = ep.res_f32 + (size_t)m * ep.res_ld;
-          } else if (ep.res_mode == RES_POSADD) {
-            resf[i] = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
-          } else if (ep.res_mode == RES_BF16) {
-            resb[i] = ep.res_bf16 + (size_t)m * ep.res_ld;
-          } else if (ep.res_mode == RES_MERGE) {
-            const int g = m / ep.rows_per_group;
-            const int cnt = ep.row_cnt[g];
-            rscale[i] = 1.0f / (float)cnt;
-            resb[i] = ep.res_bf16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+        mrow[i] = m0 + quarter * 32 + 8 * i + sr;
+        res_row(mrow[i], resf[i], resb[i], rscale[i]);
+      }
+      // the residual rows of this CTA's NEXT tile start travelling HBM -> L2 now (the epilogue of a skinny-K GEMM is
+      // otherwise bound by the latency of these loads, not by bandwidth)
+      if (kRes && it + it_step < it_end) {
+        const int itn = it + it_step;
+        const int m0n = (wst ? itn : itn / tiles_n) * GEMM_BM;
+        const int n0n = (wst ? my_n_tile : itn % tiles_n) * BN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* pf;
+          const __nv_bfloat16* pb;
+          float sc;
+          res_row(m0n + quarter * 32 + 8 * i + sr, pf, pb, sc);
+          for (int c0 = chunk_par * 32; c0 < BN && n0n + c0 < N && n0n + c0 < ep.trans_from; c0 += 64) {
+            if (pf != nullptr) prefetch_l2(pf + n0n + c0 + cg);
+            if (pb != nullptr && (lane & 1) == 0) prefetch_l2(pb + n0n + c0 + cg);
           }
         }
       }
@@ -289,6 +311,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
         const int n = n0 + c0;
         if (n >= N) break;   // warp-uniform
+        // this chunk's residual values: all loads in flight before the accumulator chunk is read and staged
+        float4 pf0[4], pf1[4];
+        uint4 pbv[4];
+        if (kRes && n < ep.trans_from) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (resf[i] != nullptr) {
+              pf0[i] = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg));
+              pf1[i] = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg + 4));
+            } else if (resb[i] != nullptr) {
+              pbv[i] = __ldg(reinterpret_cast<const uint4*>(resb[i] + n + cg));
+            }
+          }
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
         tmem_ld_wait();
@@ -311,7 +347,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
             }
-            if (ep.res_mode == RES_F32 || ep.res_mode == RES_POSADD) {
+            if (kRes && (ep.res_mode == RES_F32 || ep.res_mode == RES_POSADD)) {
               const float* rp = (ep.res_mode == RES_F32)
                                     ? ep.res_f32 + (size_t)mt_row * ep.res_ld
                                     : ep.res_f32 + ((size_t)ep.row_tab[mt_row >> 8] * 256 + (mt_row & 255)) * ep.res_ld;
@@ -358,14 +394,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
             }
-            if (resf[i] != nullptr) {
-              const float4 t0 = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg));
-              const float4 t1 = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg + 4));
+            if (kRes && resf[i] != nullptr) {
+              const float4 t0 = pf0[i], t1 = pf1[i];
               v[0] += t0.x, v[1] += t0.y, v[2] += t0.z, v[3] += t0.w;
               v[4] += t1.x, v[5] += t1.y, v[6] += t1.z, v[7] += t1.w;
-            } else if (resb[i] != nullptr) {
-              const uint4 t = __ldg(reinterpret_cast<const uint4*>(resb[i] + n + cg));
-              const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+            } else if (kRes && resb[i] != nullptr) {
+              const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&pbv[i]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = __bfloat1622float2(t2[j]);

@@ -155,6 +155,7 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = (box_cols * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
                           : (box_cols * 2 == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : (box_cols * 2 == 32) ? CU_TENSOR_MAP_SWIZZLE_32B
                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
   if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return fail(POEM_E_BADDIM, "unsupported TMA box width %u", box_cols);
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -199,7 +200,8 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
     configured = true;
   }
   const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + BN - 1) / BN;
@@ -224,7 +226,10 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
     smem = Cfg::kSmemBytes;
   }
   prof_begin(st);
-  gemm_bf16_tc_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
+  if (ep.res_mode != RES_NONE)
+    gemm_bf16_tc_kernel<BN, true><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
+  else
+    gemm_bf16_tc_kernel<BN, false><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
   LAUNCH_CHECK("gemm_bf16_tc_kernel");
   return POEM_OK;
 }
@@ -266,69 +271,88 @@ static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
 // 4-D bf16 tensor map over an NHWC activation tensor: dims (C, W, H, N); box (64, bw*stride, bh*stride, bn) with
 // traversal stride `stride` along W and H, SWIZZLE_128B, zero fill outside (= convolution padding).
 static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int Cp, int bw, int bh, int bn,
-                          int stride) {
+                          int stride, int box_c = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (Cp % 64)) return fail(POEM_E_ALIGN, "conv: bad activation tensor");
   cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstride[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+  const CUtensorMapSwizzle swz = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d)", (int)r);
   return POEM_OK;
 }
 
 // 3x3 stride-1 C -> C convolution with halo reuse (conv3x3.cuh)
-static int g_conv_mode = 0;   // 0: halo-reuse kernel where it applies; 2: every convolution on the generic path
+static int g_conv_mode = 0;   // 0: halo-reuse kernel, live channels only; 1: halo-reuse, all padded channels; 2: generic path
 extern "C" void poem_debug_conv_mode(int mode) { g_conv_mode = mode; }
 
-template <int CP>
-static int launch_conv3x3_halo_cp(const CUtensorMap& tx, const CUtensorMap& tw, const HaloArgs& a, cudaStream_t st) {
-  using Cfg = HaloCfg<CP>;
+template <int CP, int CR>
+static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, const PoemLinear& wt, const HaloArgs& a,
+                                  cudaStream_t st) {
+  using Cfg = HaloCfg<CP, CR>;
+  using Blk = typename Cfg::Blk;
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<CP, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int tiles = a.n_images * (a.R / 16) * (a.R / 16);
+  HaloMaps maps;
+  bool have[3] = {false, false, false};
+  for (int b = 0; b < Cfg::kNB; ++b) {
+    const int nch = Blk::nch(b), mi = halo_map_index(nch);
+    if (have[mi]) continue;
+    POEM_TRY(make_tmap_nhwc(&maps.x[mi], in, N, R, R, CP, Cfg::kPitch, Cfg::kRows, 1, 1, nch));
+    POEM_TRY(make_tmap_bf16(&maps.w[mi], wt.w, (uint64_t)CR, (uint64_t)9 * CP, (uint64_t)9 * CP, (uint32_t)nch, (uint32_t)CR));
+    have[mi] = true;
+  }
+  int first = have[0] ? 0 : (have[1] ? 1 : 2);
+  for (int mi = 0; mi < 3; ++mi)
+    if (!have[mi]) maps.x[mi] = maps.x[first], maps.w[mi] = maps.w[first];
+  const int tiles = N * (R / 16) * (R / 16);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_begin(st);
-  conv3x3_halo_kernel<CP><<<grid, HALO_THREADS, Cfg::kSmemBytes, st>>>(tx, tw, a);
+  conv3x3_halo_kernel<CP, CR><<<grid, HALO_THREADS, Cfg::kSmemBytes, st>>>(maps, a);
   LAUNCH_CHECK("conv3x3_halo_kernel");
   return POEM_OK;
 }
 
-static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cp, const PoemLinear& wt, bool relu,
+// c_real: number of live channels (the rest of Cp is zero padding); 0 = treat all Cp channels as live
+static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cp, int c_real, const PoemLinear& wt, bool relu,
                                const __nv_bfloat16* res, __nv_bfloat16* out, cudaStream_t st) {
-  CUtensorMap tx, tw;
-  POEM_TRY(make_tmap_nhwc(&tx, in, N, R, R, Cp, HaloCfg<64>::kPitch, HaloCfg<64>::kRows, 1, 1));
-  POEM_TRY(make_tmap_bf16(&tw, wt.w, (uint64_t)Cp, (uint64_t)9 * Cp, (uint64_t)9 * Cp, 64, (uint32_t)Cp));
   HaloArgs a;
   a.n_images = N, a.R = R, a.bias = wt.b, a.relu = relu ? 1 : 0, a.res = res, a.out = out;
+  int cr = (c_real > 0 && g_conv_mode != 1) ? (c_real + 15) / 16 * 16 : Cp;
+  if (!((Cp == 64 && cr == 48) || (Cp == 128 && cr == 80) || (Cp == 192 && cr == 160))) cr = Cp;
   char tag[48];
-  snprintf(tag, sizeof(tag), "conv3x3halo_c%d_r%d", Cp, R);
+  snprintf(tag, sizeof(tag), "conv3x3halo_c%d_of_%d_r%d", cr, Cp, R);
   TagScope ts(tag);
-  switch (Cp) {
-    case 64: return launch_conv3x3_halo_cp<64>(tx, tw, a, st);
-    case 128: return launch_conv3x3_halo_cp<128>(tx, tw, a, st);
-    case 192: return launch_conv3x3_halo_cp<192>(tx, tw, a, st);
+  switch (Cp * 1000 + cr) {
+    case 64048: return launch_conv3x3_halo_cp<64, 48>(in, N, R, wt, a, st);
+    case 64064: return launch_conv3x3_halo_cp<64, 64>(in, N, R, wt, a, st);
+    case 128080: return launch_conv3x3_halo_cp<128, 80>(in, N, R, wt, a, st);
+    case 128128: return launch_conv3x3_halo_cp<128, 128>(in, N, R, wt, a, st);
+    case 192160: return launch_conv3x3_halo_cp<192, 160>(in, N, R, wt, a, st);
+    case 192192: return launch_conv3x3_halo_cp<192, 192>(in, N, R, wt, a, st);
   }
-  return fail(POEM_E_BADDIM, "conv3x3 halo: C=%d", Cp);
+  return fail(POEM_E_BADDIM, "conv3x3 halo: C=%d (%d live)", Cp, cr);
 }
 
 // out[N, Hout, Wout, Cout_p] = act(conv(in[N, Hin, Win, Cin_p], w[Cout_p, k*k*Cin_p]) + b) (+ res)
 static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
                        int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
-                       cudaStream_t st) {
+                       cudaStream_t st, int c_real = 0) {
   if (!wt.w || !wt.b) return fail(POEM_E_NULL, "conv: weight pointer missing");
   if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
     return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
   if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Cin_p == Cout_p && Hin == Win && Hin % 16 == 0 &&
       (Cin_p == 64 || Cin_p == 128 || Cin_p == 192))
-    return launch_conv3x3_halo(in, N, Hin, Cin_p, wt, relu, res, out, st);
+    return launch_conv3x3_halo(in, N, Hin, Cin_p, c_real, wt, relu, res, out, st);
   const int Hout = Hin / stride, Wout = Win / stride;
   if (Wout < 1 || 128 % Wout || Wout > 128 || Cin_p % 64 || Cout_p % 32)
     return fail(POEM_E_BADDIM, "conv: unsupported shape %dx%d C %d -> %d", Hin, Win, Cin_p, Cout_p);
@@ -374,14 +398,15 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
 
 extern "C" int poem_conv_nhwc(const poem_bf16* in, int N, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
                               int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out,
-                              void* stream) {
+                              int c_live, void* stream) {
   if (!in || !out) return fail(POEM_E_NULL, "conv: null pointer");
+  if (c_live < 0 || c_live > Cin_p || c_live > Cout_p) return fail(POEM_E_BADDIM, "conv: c_live=%d", c_live);
   PoemLinear wt;
   wt.w = w;
   wt.b = b;
   return launch_conv(reinterpret_cast<const __nv_bfloat16*>(in), N, H, W, Cin_p, wt, Cout_p, ksize, stride, relu != 0,
                      reinterpret_cast<const __nv_bfloat16*>(res), reinterpret_cast<__nv_bfloat16*>(out),
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, c_live);
 }
 
 static inline int pad64(int c) { return (c + 63) / 64 * 64; }
@@ -415,7 +440,7 @@ extern "C" size_t poem_hrnet_stage4_workspace_bytes(const PoemHRStage4* w, int n
 
 // n_modules HighResolutionModules over the first nb branches (hrnet.py:217-234); cur[b] = live buffer of branch b
 static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N, const int* R, const int* Cp,
-                          const HrPlan& p, int* cur, cudaStream_t st) {
+                          const int* ch, const HrPlan& p, int* cur, cudaStream_t st) {
   for (int m = 0; m < n_modules; ++m) {
     const PoemHRModule& mod = mods[m];
     // ---- branches: 4 BasicBlocks each (hrnet.py:38-67)
@@ -424,8 +449,8 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
         __nv_bfloat16* x = p.x[b][cur[b]];
         __nv_bfloat16* t = p.x[b][(cur[b] + 1) % 3];
         __nv_bfloat16* y = p.x[b][(cur[b] + 2) % 3];
-        POEM_TRY(launch_conv(x, N, R[b], R[b], Cp[b], mod.branch[b][k][0], Cp[b], 3, 1, true, nullptr, t, st));
-        POEM_TRY(launch_conv(t, N, R[b], R[b], Cp[b], mod.branch[b][k][1], Cp[b], 3, 1, true, x, y, st));
+        POEM_TRY(launch_conv(x, N, R[b], R[b], Cp[b], mod.branch[b][k][0], Cp[b], 3, 1, true, nullptr, t, st, ch[b]));
+        POEM_TRY(launch_conv(t, N, R[b], R[b], Cp[b], mod.branch[b][k][1], Cp[b], 3, 1, true, x, y, st, ch[b]));
         cur[b] = (cur[b] + 2) % 3;
       }
     }
@@ -499,7 +524,7 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
     LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
   }
   int cur[4] = {0, 0, 0, 0};   // index of the buffer holding the branch's current activation
-  POEM_TRY(run_hr_modules(w->modules, w->n_modules, 4, N, R, Cp, p, cur, st));
+  POEM_TRY(run_hr_modules(w->modules, w->n_modules, 4, N, R, Cp, ch, p, cur, st));
   return hr_export(p, cur, ch, Cp, R, N, out, st);
 }
 
@@ -578,13 +603,13 @@ extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res,
   // transition1 (hrnet.py:318-342): 3x3 256->40 ; 3x3 s2 256->80
   POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st));
   POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[1], Cp[1], 3, 2, true, nullptr, p.hr.x[1][0], st));
-  POEM_TRY(run_hr_modules(w->stage2, 1, 2, N, R, Cp, p.hr, cur, st));
+  POEM_TRY(run_hr_modules(w->stage2, 1, 2, N, R, Cp, ch, p.hr, cur, st));
   // transition2: new branch from the lowest-resolution output, 3x3 s2 80->160
   POEM_TRY(launch_conv(p.hr.x[1][cur[1]], N, R[1], R[1], Cp[1], w->trans2, Cp[2], 3, 2, true, nullptr, p.hr.x[2][0], st));
-  POEM_TRY(run_hr_modules(w->stage3, 4, 3, N, R, Cp, p.hr, cur, st));
+  POEM_TRY(run_hr_modules(w->stage3, 4, 3, N, R, Cp, ch, p.hr, cur, st));
   // transition3: 3x3 s2 160->320
   POEM_TRY(launch_conv(p.hr.x[2][cur[2]], N, R[2], R[2], Cp[2], w->trans3, Cp[3], 3, 2, true, nullptr, p.hr.x[3][0], st));
-  POEM_TRY(run_hr_modules(w->stage4, 3, 4, N, R, Cp, p.hr, cur, st));
+  POEM_TRY(run_hr_modules(w->stage4, 3, 4, N, R, Cp, ch, p.hr, cur, st));
   return hr_export(p.hr, cur, ch, Cp, R, N, out, st);
 }
 

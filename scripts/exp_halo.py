@@ -9,7 +9,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from poem_v2_b200 import _native as nat  # noqa: E402
 
 lib = nat.load()
-lib.poem_debug_conv_mode.argtypes = [__import__("ctypes").c_int]
 
 
 def run(N, R, c, cp, relu, res, mode, timing=False):
@@ -37,7 +36,7 @@ def run(N, R, c, cp, relu, res, mode, timing=False):
 
     def call():
         nat.check(lib.poem_conv_nhwc(xd.data_ptr(), N, R, R, cp, wd.data_ptr(), bd.data_ptr(), cp, 3, 1, int(relu),
-                                     rd.data_ptr() if res else None, out.data_ptr(), st))
+                                     rd.data_ptr() if res else None, out.data_ptr(), c, st))
     call()
     torch.cuda.synchronize()
     ms = None
@@ -65,11 +64,11 @@ def run(N, R, c, cp, relu, res, mode, timing=False):
 
 
 for (R, c, cp) in [(64, 40, 64), (32, 80, 128), (16, 160, 192), (32, 40, 64), (16, 80, 128)]:
-    for mode in (0, 2):
+    for mode in (0, 1, 2):
         e, _ = run(3, R, c, cp, True, True, mode)
         print(f"R={R} C={c}->{cp} mode {mode}: rel err {e:.3e}", flush=True)
 for (R, c, cp) in [(64, 40, 64), (32, 80, 128), (16, 160, 192)]:
-    for mode in (0, 2):
+    for mode in (0, 1, 2):
         for res in (False, True):
             _, ms = run(256, R, c, cp, True, res, mode, timing=True)
             print(f"N=256 R={R} Cp={cp} mode {mode} res={res}: {ms * 1e3:.1f} us", flush=True)

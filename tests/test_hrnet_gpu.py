@@ -15,6 +15,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+@pytest.mark.parametrize("live", [False, True])
 @pytest.mark.parametrize("N,R,cin,cout,k,stride,relu,res", [
     (2, 64, 40, 40, 3, 1, True, False),
     (2, 32, 80, 80, 3, 1, True, True),
@@ -25,8 +26,13 @@ def _p(t):
     (2, 16, 160, 320, 3, 2, False, False),
     (2, 8, 320, 40, 1, 1, False, False),     # fuse-layer 1x1 (upsampled later)
     (2, 32, 80, 40, 1, 1, False, False),
+    (3, 32, 40, 40, 3, 1, True, True),       # halo kernel, other map sizes / channel splits
+    (2, 16, 80, 80, 3, 1, False, True),
+    (1, 16, 33, 33, 3, 1, True, False),      # 33 live channels -> 48 (32 + 16) of 64
+    (2, 32, 150, 150, 3, 1, True, True),     # 150 -> 160 (64 + 64 + 32) of 192
+    (2, 16, 128, 128, 3, 1, True, True),     # no padding at all
 ])
-def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res):
+def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res, live):
     lib = nat.load()
     g = torch.Generator().manual_seed(R * 7 + cin + cout + k)
     cin_p, cout_p = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
@@ -48,8 +54,12 @@ def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res):
     d = [t.bfloat16().contiguous().cuda() if t is not None else None for t in (xp, wp.reshape(cout_p, -1), rp)]
     bd = bp.cuda()
     out = torch.full((N, Ro, Ro, cout_p), float("nan"), device="cuda", dtype=torch.bfloat16)
+    if live and cin != cout:
+        pytest.skip("c_live describes a C -> C convolution")
+    # live=True promises that channels >= cin are zero padding: the 3x3 stride-1 kernel then multiplies only the live
+    # channels (mixed 128/64/32-byte swizzle K blocks) and writes the padding as zeros
     nat.check(lib.poem_conv_nhwc(_p(d[0]), N, R, R, cin_p, _p(d[1]), _p(bd), cout_p, k, stride, int(relu), _p(d[2]),
-                                 _p(out), torch.cuda.current_stream().cuda_stream))
+                                 _p(out), cin if live else 0, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = F.conv2d(x, w, b, stride=stride, padding=k // 2)
     if res:
