@@ -50,16 +50,33 @@ struct HaloCfg {
   static constexpr int kNB = Blk::n;                   // K blocks per tap
   static constexpr int kPitch = 18;                    // patch pixels per smem row
   static constexpr int kRows = 18;
-  static constexpr int kAStride = (kRows * kPitch * 128 + 1023) / 1024 * 1024;   // room for a 64-channel patch
-  static constexpr int kAStages = 3;
+  // patch ring: T tile slots, each holding the kNB K-block patches of one tile at fixed (1024-aligned) offsets, one
+  // full/empty barrier pair per (slot, block) -> stage = step % (T * kNB)
+  __host__ __device__ static constexpr int blk_bytes(int b) { return kRows * kPitch * Blk::nch(b) * 2; }
+  __host__ __device__ static constexpr int blk_off(int b) {
+    int off = 0;
+    for (int i = 0; i < b; ++i) off += (blk_bytes(i) + 1023) / 1024 * 1024;
+    return off;
+  }
+  static constexpr int kSlotBytes = blk_off(kNB);
+  static constexpr int kTailBytes = CP * 4 + 512;      // bias + barriers
+  static constexpr int kBudget = 232448 - 1024 - kTailBytes;
+  // weights: all nine taps stay resident in smem when they leave room for two tile slots (CR <= 80); otherwise the
+  // [CR x nch] tiles stream through a ring that takes whatever one tile slot leaves (an MMA consumes a tile in
+  // ~0.3 us, an L2 round trip is ~1 us: a shallow ring starves the tensor core)
+  static constexpr int kTapBytes = CR * CR * 2;        // the kNB tiles of one tap, packed
+  static constexpr bool kBResident = (kBudget - 9 * kTapBytes) >= 2 * kSlotBytes;
   static constexpr int kBStride = CR * 128;            // room for a [CR out-channel rows][64 k] tile
-  static constexpr int kTapBytes = CR * CR * 2;        // resident mode: the kNB tiles of one tap, packed
-  static constexpr bool kBResident = (CP == 64);       // all nine taps' weight tiles stay in smem
-  static constexpr int kBStages = CP == 128 ? 6 : 4;   // streaming mode ring depth
-  static constexpr int kBBytesTotal = kBResident ? 9 * kTapBytes : kBStages * kBStride;
+  static constexpr int kBStagesRoom = (kBudget - kSlotBytes) / kBStride;
+  static constexpr int kBStages = kBStagesRoom > 8 ? 8 : kBStagesRoom;
+  static constexpr int kBBytesTotal = ((kBResident ? 9 * kTapBytes : kBStages * kBStride) + 1023) / 1024 * 1024;
+  static constexpr int kSlotsRoom = (kBudget - kBBytesTotal) / kSlotBytes;
+  static constexpr int kSlots = kSlotsRoom > 4 ? 4 : kSlotsRoom;
+  static constexpr int kAStages = kSlots * kNB;
+  static_assert(kSlots >= 1 && kAStages <= 12 && (kBResident || kBStages >= 3), "smem plan");
   static constexpr int kAccPairs = (4 * CP <= 512) ? 2 : 1;
   static constexpr int kTmemCols = (2 * kAccPairs * CP <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kAStages * kAStride + (kBBytesTotal + 1023) / 1024 * 1024 + CP * 4 + 256;
+  static constexpr int kSmemBytes = kSlots * kSlotBytes + kBBytesTotal + kTailBytes;
 };
 
 constexpr int HALO_THREADS = 64 + 32 * 8;
@@ -108,17 +125,17 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  uint8_t* s_a = smem;                                        // [kAStages][kAStride]
-  uint8_t* s_b = smem + Cfg::kAStages * Cfg::kAStride;        // [kBStages][kBStride] or [9][kTapBytes]
-  float* s_bias = reinterpret_cast<float*>(s_b + (Cfg::kBBytesTotal + 1023) / 1024 * 1024);
+  uint8_t* s_a = smem;                                        // [kSlots][kSlotBytes]
+  uint8_t* s_b = smem + Cfg::kSlots * Cfg::kSlotBytes;        // [kBStages][kBStride] or [9][kTapBytes]
+  float* s_bias = reinterpret_cast<float*>(s_b + Cfg::kBBytesTotal);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + CP);
-  uint64_t* a_full = bars;            // [3]
-  uint64_t* a_empty = bars + 3;       // [3]
-  uint64_t* b_full = bars + 6;        // [9]  (resident mode: b_full[0] only)
-  uint64_t* b_empty = bars + 15;      // [9]
-  uint64_t* tmem_full = bars + 24;    // [2]
-  uint64_t* tmem_empty = bars + 26;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* a_full = bars;            // [12]
+  uint64_t* a_empty = bars + 12;      // [12]
+  uint64_t* b_full = bars + 24;       // [9]  (resident mode: b_full[0] only)
+  uint64_t* b_empty = bars + 33;      // [9]
+  uint64_t* tmem_full = bars + 42;    // [2]
+  uint64_t* tmem_empty = bars + 44;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 46);
 
   const int tiles_x = a.R / 16;
   const int tiles_per_img = tiles_x * tiles_x;
@@ -167,34 +184,37 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
       }
       const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
       const int steps = my_tiles * Cfg::kNB;   // (tile, K block) pairs, in order
-      auto load_patch = [&](int step) {
-        const int tile = (int)blockIdx.x + (step / Cfg::kNB) * (int)gridDim.x;
-        const int b = step % Cfg::kNB;
-        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-        const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
-        const int st = step % Cfg::kAStages;
-        mbar_wait(&a_empty[st], ((step / Cfg::kAStages) & 1) ^ 1);
-        mbar_expect_tx(&a_full[st], (uint32_t)(Cfg::kRows * Cfg::kPitch * Blk::nch(b) * 2));
-        tma_load_4d(s_a + st * Cfg::kAStride, &maps.x[halo_map_index(Blk::nch(b))], &a_full[st], Blk::ch0(b), x0 - 1, y0 - 1, n);
-      };
-      int bs = 0;
-      uint32_t bphase = 0;
-      for (int step = 0; step < Cfg::kAStages - 1 && step < steps; ++step) load_patch(step);
-      for (int step = 0; step < steps; ++step) {
-        // the patch two steps ahead goes out before this block's weight tiles
-        if (step + Cfg::kAStages - 1 < steps) load_patch(step + Cfg::kAStages - 1);
-        if (!Cfg::kBResident) {
-          const int b = step % Cfg::kNB;
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_empty[bs], bphase ^ 1);
-            mbar_expect_tx(&b_full[bs], (uint32_t)(CR * Blk::nch(b) * 2));
-            tma_load_2d(s_b + bs * Cfg::kBStride, &maps.w[halo_map_index(Blk::nch(b))], &b_full[bs], tap * CP + Blk::ch0(b), 0);
-            if (++bs == Cfg::kBStages) {
-              bs = 0;
-              bphase ^= 1;
-            }
+      // One thread feeds two independent rings (patches, weight tiles): it probes both "slot free" barriers without
+      // blocking, so a full patch ring never delays the weight tiles of the step in flight (and vice versa).
+      const int b_total = Cfg::kBResident ? 0 : steps * 9;
+      int a_next = 0, b_next = 0;
+      while (a_next < steps || b_next < b_total) {
+        bool progress = false;
+        if (a_next < steps) {
+          const int st = a_next % Cfg::kAStages;
+          if (mbar_test_wait(&a_empty[st], ((a_next / Cfg::kAStages) & 1) ^ 1)) {
+            const int tile = (int)blockIdx.x + (a_next / Cfg::kNB) * (int)gridDim.x;
+            const int b = a_next % Cfg::kNB;
+            const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+            const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
+            mbar_expect_tx(&a_full[st], (uint32_t)Cfg::blk_bytes(b));
+            tma_load_4d(s_a + (st / Cfg::kNB) * Cfg::kSlotBytes + Cfg::blk_off(b), &maps.x[halo_map_index(Blk::nch(b))],
+                        &a_full[st], Blk::ch0(b), x0 - 1, y0 - 1, n);
+            ++a_next;
+            progress = true;
           }
         }
+        if (b_next < b_total) {
+          const int bs = b_next % Cfg::kBStages;
+          if (mbar_test_wait(&b_empty[bs], ((b_next / Cfg::kBStages) & 1) ^ 1)) {
+            const int b = (b_next / 9) % Cfg::kNB, tap = b_next % 9;
+            mbar_expect_tx(&b_full[bs], (uint32_t)(CR * Blk::nch(b) * 2));
+            tma_load_2d(s_b + bs * Cfg::kBStride, &maps.w[halo_map_index(Blk::nch(b))], &b_full[bs], tap * CP + Blk::ch0(b), 0);
+            ++b_next;
+            progress = true;
+          }
+        }
+        if (!progress) __nanosleep(64);
       }
     }
   } else if (warp == 1) {
@@ -215,7 +235,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
           const int st = step % Cfg::kAStages;
           mbar_wait(&a_full[st], (step / Cfg::kAStages) & 1);
           tc_fence_after_sync();
-          const uint32_t pa = smem_u32(s_a + st * Cfg::kAStride);
+          const uint32_t pa = smem_u32(s_a + (st / Cfg::kNB) * Cfg::kSlotBytes + Cfg::blk_off(b));
           for (int tap = 0; tap < 9; ++tap) {
             uint32_t pb;
             if (Cfg::kBResident) {
@@ -264,6 +284,19 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
       const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
+      if (a.res != nullptr && tile + (int)gridDim.x < num_tiles) {
+        // the shortcut pixels of this CTA's NEXT tile start travelling HBM -> L2 now
+        const int tn = tile + (int)gridDim.x;
+        const int nn = tn / tiles_per_img, remn = tn - nn * tiles_per_img;
+        const int yn = (remn / tiles_x) * 16 + quarter * 4 + (lane >> 3), xn = (remn % tiles_x) * 16 + (lane & 7);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const __nv_bfloat16* rp = a.res + (((size_t)nn * a.R + yn) * a.R + xn + sub * 8) * CP;
+#pragma unroll
+          for (int j = 0; j < kChunks; ++j)
+            if ((2 * j + par) * 32 < CR) prefetch_l2(rp + (2 * j + par) * 32);
+        }
+      }
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
         const size_t off = (((size_t)n * a.R + (y0 + quarter * 4 + (lane >> 3))) * a.R + (x0 + sub * 8 + (lane & 7))) * CP;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (one kernel launch) into a short markdown table: python scripts/ncu_summary.py rep [out.md]"""
+"""Summarise an .ncu-rep (every kernel launch in it) into a short markdown table: python scripts/ncu_summary.py rep [out.md]"""
 import csv
 import io
 import subprocess
@@ -21,21 +21,29 @@ KEYS = [
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum",
 ]
 
 
-def raw(rep):
+def raw_all(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, vals = rows[0], rows[1], rows[-1]
-    return {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    hdr, units = rows[0], rows[1]
+    return [{h: (v, u) for h, u, v in zip(hdr, units, vals)} for vals in rows[2:]]
 
 
 def main():
     rep = sys.argv[1]
-    m = raw(rep)
+    text = "\n".join(one(rep, m) for m in raw_all(rep))
+    if len(sys.argv) > 2:
+        open(sys.argv[2], "w").write(text)
+    print(text)
+
+
+def one(rep, m):
     lines = [f"# ncu --set full: `{m.get('Kernel Name', ('?', ''))[0][:90]}`", "", f"report: `{rep}`", "",
              "| metric | value | unit |", "|---|---|---|"]
     for k in KEYS:
@@ -47,10 +55,7 @@ def main():
     lines += ["", "Top warp stall reasons (avg warps stalled per issue-active cycle):", ""]
     for val, k in stalls:
         lines.append(f"- {k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}: {val:.2f}")
-    text = "\n".join(lines) + "\n"
-    if len(sys.argv) > 2:
-        open(sys.argv[2], "w").write(text)
-    print(text)
+    return "\n".join(lines) + "\n"
 
 
 if __name__ == "__main__":
