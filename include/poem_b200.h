@@ -215,6 +215,20 @@ size_t poem_hrnet_workspace_bytes(const PoemHRNet* w, int n_images, int img_res)
 int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res, const float* images, float* const* out,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- images -> mlvl_feat: backbone + `feat_decode` (reference lib/models/POEM.py:189-203, 255-265, HRNet branch):
+ * x = f0; x = ConvBlock_i(x) + f_{i+1} for the three stride-2 ConvBlocks (3x3 conv with bias + BN + ReLU, folded);
+ * bilinear x2 upsampling of the 8x8 map; 1x1 convolution 320 -> out_channels (bias, no norm). */
+typedef struct PoemFeatDecode {
+  PoemLinear delayer[3];   /* 3x3 stride-2: 40->80, 80->160, 160->320 (padded to 64; BN and conv bias folded) */
+  PoemLinear feat_in;      /* 1x1 320 -> out_channels (padded to 64) */
+  int32_t out_channels;    /* 160 */
+} PoemFeatDecode;
+size_t poem_image_features_workspace_bytes(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images, int img_res);
+/* images fp32 NCHW (n_images, 3, 256, 256) -> mlvl_feat fp32 NCHW (n_images, out_channels, 16, 16), the tensor
+ * poem_head_forward takes; maps: optional four fp32 NCHW backbone outputs (NULL to skip the export). */
+int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images, int img_res, const float* images,
+                        float* mlvl_feat, float* const* maps, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
  * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
  * c_live > 0 promises that only the first c_live input AND output channels are non-zero (the rest of the padded

@@ -88,6 +88,41 @@ def run_reference_backbone(n_images, wseed, iseed):
         return net(synth.make_images(n_images, 256, iseed))
 
 
+def run_reference_image_stage(n_images, wseed, iseed):
+    """Real reference backbone (`HighResolutionNet`, W40 yaml) followed by the real `feat_decode` method of
+    `PtEmbedMultiviewStereoV2` (lib/models/POEM.py:189-203) bound to real `ConvBlock`s, on CPU in eval mode."""
+    import yaml
+    hr = _import_reference_hrnet()
+    # POEM.py imports the two builders from packages the stub layer keeps bare (their __init__ would pull every head)
+    from lib.utils.builder import BACKBONE, HEAD, build_from_cfg
+    sys.modules["lib.models.heads"].build_head = lambda cfg, **kw: build_from_cfg(cfg, HEAD, **kw)
+    bb = sys.modules.get("lib.models.backbones")
+    if bb is not None and not hasattr(bb, "build_backbone"):
+        bb.build_backbone = lambda cfg, **kw: build_from_cfg(cfg, BACKBONE, **kw)
+    import lib.models.POEM as poem_mod
+    from lib.models.bricks.conv import ConvBlock
+    with open(os.path.join(ref_shim.REF_ROOT, "config/backbone/cls_hrnet_w40_sgd_lr5e-2_wd1e-4_bs32_x100.yaml")) as f:
+        cfg = yaml.safe_load(f)
+
+    class Shell(torch.nn.Module):       # the attributes feat_decode touches, built as POEM.py:169-181 builds them
+        def __init__(self):
+            super().__init__()
+            fs = (40, 80, 160, 320)
+            self.img_backbone = hr.HighResolutionNet(cfg)
+            self.feat_delayer = torch.nn.ModuleList([ConvBlock(fs[i], fs[i + 1], kernel_size=3, stride=2, relu=True, norm="bn")
+                                                     for i in range(3)])
+            self.feat_in = ConvBlock(fs[3], fs[2], kernel_size=1, padding=0, relu=False, norm=None)
+    shell = Shell().eval()
+    sd = synth.make_image_stage_state_dict(wseed)
+    missing, unexpected = shell.load_state_dict(sd, strict=False)
+    dead = ("img_backbone.incre_modules.", "img_backbone.downsamp_modules.", "img_backbone.final_layer.",
+            "img_backbone.classifier.")
+    assert not unexpected and all(k.startswith(dead) for k in missing), (missing[:5], unexpected[:5])
+    with torch.no_grad():
+        feats = shell.img_backbone(synth.make_images(n_images, 256, iseed))
+        return poem_mod.PtEmbedMultiviewStereoV2.feat_decode(shell, feats, "HRNet"), feats
+
+
 def run_reference_stage4(n_images, wseed, iseed):
     """The real reference `HighResolutionModule` x3 (= `HighResolutionNet.stage4`, hrnet.py:272-277) on CPU."""
     hr = _import_reference_hrnet()
@@ -110,6 +145,10 @@ def main():
                         y0=ys[0][:, :, ::4, ::4].numpy(), y1=ys[1][:, :, ::2, ::2].numpy(), y2=ys[2].numpy(),
                         y3=ys[3].numpy())
     print("hrnet_w40_n1", [tuple(y.shape) for y in ys], [float(y.abs().mean()) for y in ys])
+    mf, _ = run_reference_image_stage(1, 0, 1)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "image_stage_n1.npz"),
+                        meta=np.array(repr(dict(kind="image_stage", n_images=1, wseed=0, iseed=1))), mlvl_feat=mf.numpy())
+    print("image_stage_n1", tuple(mf.shape), float(mf.abs().mean()))
     if "--only-hrnet" in sys.argv:
         return
     ys = run_reference_stage4(2, 0, 1)

@@ -239,11 +239,12 @@ def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anc
 
 # ------------------------------------------------------------------------------------------ a17
 def _conv_bn(sd, conv_key, bn_key, x, stride=1, relu=False):
-    """Conv2d(bias=False) + BatchNorm2d in eval mode (+ ReLU)."""
+    """Conv2d (+ bias when the checkpoint has one) + BatchNorm2d in eval mode when bn_key is given (+ ReLU)."""
     w = sd[conv_key + ".weight"]
-    y = F.conv2d(x, w, None, stride=stride, padding=w.shape[-1] // 2)
-    y = F.batch_norm(y, sd[bn_key + ".running_mean"], sd[bn_key + ".running_var"], sd[bn_key + ".weight"],
-                     sd[bn_key + ".bias"], training=False, eps=1e-5)
+    y = F.conv2d(x, w, sd.get(conv_key + ".bias"), stride=stride, padding=w.shape[-1] // 2)
+    if bn_key is not None:
+        y = F.batch_norm(y, sd[bn_key + ".running_mean"], sd[bn_key + ".running_var"], sd[bn_key + ".weight"],
+                         sd[bn_key + ".bias"], training=False, eps=1e-5)
     return F.relu(y) if relu else y
 
 
@@ -299,3 +300,20 @@ def hrnet_forward(sd, img):
     ys = hrnet_stage4(sd, xs, 4, prefix="stage3.")
     xs = ys + [_conv_bn(sd, "transition3.3.0.0", "transition3.3.0.1", ys[-1], stride=2, relu=True)]
     return hrnet_stage4(sd, xs, 3, prefix="stage4.")
+
+
+def feat_decode(sd, feats):
+    """`PtEmbedMultiviewStereoV2.feat_decode`, HRNet branch (lib/models/POEM.py:189-203): ConvBlocks are
+    conv(bias) + BN + ReLU (lib/models/bricks/conv.py:4-44); `feat_in` is a bare 1x1 convolution."""
+    x = feats[0]
+    for i in range(3):
+        p = f"feat_delayer.{i}."
+        x = _conv_bn(sd, p + "conv", p + "norm", x, stride=2, relu=True) + feats[i + 1]
+    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    return _conv_bn(sd, "feat_in.conv", None, x)
+
+
+def image_features(sd, img):
+    """images -> mlvl_feat: `extract_img_feat` + `feat_decode` (POEM.py:255-265); sd holds full-model keys."""
+    feats = hrnet_forward({k[len("img_backbone."):]: v for k, v in sd.items() if k.startswith("img_backbone.")}, img)
+    return feat_decode(sd, feats), feats

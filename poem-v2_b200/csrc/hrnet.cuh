@@ -92,6 +92,27 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ w, co
   }
 }
 
+// F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) of an fp32 NHWC map (padded channels) written as
+// the fp32 NCHW tensor (N, C, 2H, 2W) the head consumes (POEM.py:200).  Source index = (dst + 0.5) / 2 - 0.5 clamped at 0.
+__global__ void upsample2x_nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W,
+                                               int Cp, int C) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Ho = 2 * H, Wo = 2 * W;
+  if (gid >= (size_t)N * C * Ho * Wo) return;
+  const int x = (int)(gid % Wo);
+  const int y = (int)((gid / Wo) % Ho);
+  const int c = (int)((gid / ((size_t)Wo * Ho)) % C);
+  const size_t n = gid / ((size_t)Wo * Ho * C);
+  const float sy = fmaxf((y + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((x + 0.5f) * 0.5f - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float* b = in + n * H * W * Cp + c;
+  const float v00 = b[((size_t)y0 * W + x0) * Cp], v01 = b[((size_t)y0 * W + x1) * Cp];
+  const float v10 = b[((size_t)y1 * W + x0) * Cp], v11 = b[((size_t)y1 * W + x1) * Cp];
+  out[gid] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+
 // Fuse layer sum (hrnet.py:225-233): out[n,y,x,c] = relu(sum_j in_j[n, y >> s_j, x >> s_j, c]); in_j has resolution
 // (H >> s_j, W >> s_j) — nearest-neighbour upsampling by 2^s_j of the 1x1-conv terms, s_j = 0 for the others.
 struct FuseSumArgs {

@@ -346,12 +346,12 @@ static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cp, in
 // out[N, Hout, Wout, Cout_p] = act(conv(in[N, Hin, Win, Cin_p], w[Cout_p, k*k*Cin_p]) + b) (+ res)
 static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
                        int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
-                       cudaStream_t st, int c_real = 0) {
+                       cudaStream_t st, int c_real = 0, bool relu_before_res = false, float* out_f32 = nullptr) {
   if (!wt.w || !wt.b) return fail(POEM_E_NULL, "conv: weight pointer missing");
   if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
     return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
   if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Cin_p == Cout_p && Hin == Win && Hin % 16 == 0 &&
-      (Cin_p == 64 || Cin_p == 128 || Cin_p == 192))
+      (Cin_p == 64 || Cin_p == 128 || Cin_p == 192) && !relu_before_res && out != nullptr && out_f32 == nullptr)
     return launch_conv3x3_halo(in, N, Hin, Cin_p, c_real, wt, relu, res, out, st);
   const int Hout = Hin / stride, Wout = Win / stride;
   if (Wout < 1 || 128 % Wout || Wout > 128 || Cin_p % 64 || Cout_p % 32)
@@ -372,8 +372,8 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   POEM_TRY(make_tmap_bf16(&tw, wt.w, (uint64_t)Cout_p, (uint64_t)K, (uint64_t)K, GEMM_BK, (uint32_t)BN));
   GemmEpilogue e = epi_default(Cout_p);
   e.bias = wt.b;
-  e.act = (relu && !res) ? ACT_RELU : ACT_NONE;
-  e.act_after_res = (relu && res) ? ACT_RELU : ACT_NONE;
+  e.act = (relu && (!res || relu_before_res)) ? ACT_RELU : ACT_NONE;
+  e.act_after_res = (relu && res && !relu_before_res) ? ACT_RELU : ACT_NONE;
   if (res) {
     e.res_mode = RES_BF16;
     e.res_bf16 = res;
@@ -381,6 +381,8 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   }
   e.out_bf16 = out;
   e.ld_bf16 = Cout_p;
+  e.out_f32 = out_f32;
+  e.ld_f32 = Cout_p;
   ConvOperand cv;
   cv.enabled = 1, cv.ksize = ksize, cv.pad = ksize / 2, cv.stride = stride, cv.cblocks = cblocks, cv.Hout = Hout,
   cv.Wout = Wout;
@@ -553,18 +555,10 @@ extern "C" size_t poem_hrnet_workspace_bytes(const PoemHRNet* w, int n_images, i
   return hrnet_plan(n_images, img_res, w->channels, nullptr, &p);
 }
 
-extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res, const float* images,
-                                  float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!w || !images || !out || !workspace) return fail(POEM_E_NULL, "hrnet: null pointer");
-  if (img_res != 256) return fail(POEM_E_BADDIM, "hrnet: img_res=%d (256 supported)", img_res);
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
-  if (!w->stem1_w || !w->stem1_b) return fail(POEM_E_NULL, "hrnet: stem weights missing");
-  const int N = n_images;
+// stem .. stage 4 on the planned workspace; leaves branch b's map in p.hr.x[b][cur[b]] (NHWC bf16, padded channels)
+static int hrnet_run(const PoemHRNet* w, int N, int img_res, const float* images, const HrNetPlan& p, int* cur,
+                     cudaStream_t st) {
   const int* ch = w->channels;
-  cudaStream_t st = (cudaStream_t)stream;
-  HrNetPlan p;
-  const size_t need = hrnet_plan(N, img_res, ch, reinterpret_cast<uint8_t*>(workspace), &p);
-  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
   const int R2 = img_res / 2, R4 = img_res / 4;
   // stem: conv1 3->64 s2 (direct, fp32 weights) ; conv2 64->64 s2
   {
@@ -594,11 +588,11 @@ extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res,
     x = y;
     x_ch = 256;
   }
-  int Cp[4], R[4], cur[4] = {0, 0, 0, 0};
+  int Cp[4], R[4];
   for (int i = 0; i < 4; ++i) {
     Cp[i] = pad64(ch[i]);
     R[i] = R4 >> i;
-    if (!out[i]) return fail(POEM_E_NULL, "hrnet: output %d missing", i);
+    cur[i] = 0;
   }
   // transition1 (hrnet.py:318-342): 3x3 256->40 ; 3x3 s2 256->80
   POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st));
@@ -609,8 +603,108 @@ extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res,
   POEM_TRY(run_hr_modules(w->stage3, 4, 3, N, R, Cp, ch, p.hr, cur, st));
   // transition3: 3x3 s2 160->320
   POEM_TRY(launch_conv(p.hr.x[2][cur[2]], N, R[2], R[2], Cp[2], w->trans3, Cp[3], 3, 2, true, nullptr, p.hr.x[3][0], st));
-  POEM_TRY(run_hr_modules(w->stage4, 3, 4, N, R, Cp, ch, p.hr, cur, st));
-  return hr_export(p.hr, cur, ch, Cp, R, N, out, st);
+  return run_hr_modules(w->stage4, 3, 4, N, R, Cp, ch, p.hr, cur, st);
+}
+
+static int hrnet_check(const PoemHRNet* w, int img_res, const void* images, const void* workspace) {
+  if (!w || !images || !workspace) return fail(POEM_E_NULL, "hrnet: null pointer");
+  if (img_res != 256) return fail(POEM_E_BADDIM, "hrnet: img_res=%d (256 supported)", img_res);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  if (!w->stem1_w || !w->stem1_b) return fail(POEM_E_NULL, "hrnet: stem weights missing");
+  return POEM_OK;
+}
+
+extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res, const float* images,
+                                  float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
+  POEM_TRY(hrnet_check(w, img_res, images, workspace));
+  if (!out) return fail(POEM_E_NULL, "hrnet: null pointer");
+  const int N = n_images;
+  cudaStream_t st = (cudaStream_t)stream;
+  HrNetPlan p;
+  const size_t need = hrnet_plan(N, img_res, w->channels, reinterpret_cast<uint8_t*>(workspace), &p);
+  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  int Cp[4], R[4], cur[4];
+  for (int i = 0; i < 4; ++i) {
+    Cp[i] = pad64(w->channels[i]);
+    R[i] = (img_res / 4) >> i;
+    if (!out[i]) return fail(POEM_E_NULL, "hrnet: output %d missing", i);
+  }
+  POEM_TRY(hrnet_run(w, N, img_res, images, p, cur, st));
+  return hr_export(p.hr, cur, w->channels, Cp, R, N, out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// images -> mlvl_feat: backbone + feat_decode (reference lib/models/POEM.py:255-265 `extract_img_feat` + `feat_decode`,
+// HRNet branch :189-203): three stride-2 ConvBlocks chained down the pyramid with the backbone maps added after the
+// ReLU, bilinear x2 upsampling of the 8x8 map, 1x1 convolution 320 -> 160
+// ------------------------------------------------------------------------------------------------
+struct FeatPlan {
+  HrNetPlan net;
+  __nv_bfloat16* d[3];   // pyramid sums at R/8, R/16, R/32
+  float* f8;             // feat_in output at R/32, fp32 NHWC (padded channels)
+};
+static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, uint8_t* base, FeatPlan* p) {
+  const size_t net = hrnet_plan(N, img_res, ch, base, &p->net);
+  Bump b{base ? base + ((net + 1023) & ~size_t(1023)) : nullptr, 0};
+  for (int i = 0; i < 3; ++i) {
+    const size_t r = (size_t)(img_res / 8) >> i;
+    p->d[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad64(ch[i + 1]));
+  }
+  const size_t r8 = (size_t)img_res / 32;
+  p->f8 = b.take<float>((size_t)N * r8 * r8 * pad64(out_ch));
+  return ((net + 1023) & ~size_t(1023)) + b.off;
+}
+extern "C" size_t poem_image_features_workspace_bytes(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images,
+                                                      int img_res) {
+  if (!w || !fd || n_images < 1 || img_res < 64 || img_res % 32) return 0;
+  FeatPlan p;
+  return feat_plan(n_images, img_res, w->channels, fd->out_channels, nullptr, &p);
+}
+
+extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images, int img_res,
+                                   const float* images, float* mlvl_feat, float* const* maps, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  POEM_TRY(hrnet_check(w, img_res, images, workspace));
+  if (!fd || !mlvl_feat) return fail(POEM_E_NULL, "image_features: null pointer");
+  if (fd->out_channels < 1 || fd->out_channels > 256) return fail(POEM_E_BADDIM, "out_channels=%d", fd->out_channels);
+  const int N = n_images;
+  const int* ch = w->channels;
+  cudaStream_t st = (cudaStream_t)stream;
+  FeatPlan p;
+  const size_t need = feat_plan(N, img_res, ch, fd->out_channels, reinterpret_cast<uint8_t*>(workspace), &p);
+  if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  int Cp[4], R[4], cur[4];
+  for (int i = 0; i < 4; ++i) {
+    Cp[i] = pad64(ch[i]);
+    R[i] = (img_res / 4) >> i;
+  }
+  POEM_TRY(hrnet_run(w, N, img_res, images, p.net, cur, st));
+  if (maps) {
+    for (int i = 0; i < 4; ++i)
+      if (!maps[i]) return fail(POEM_E_NULL, "image_features: map %d missing", i);
+    POEM_TRY(hr_export(p.net.hr, cur, ch, Cp, R, N, maps, st));
+  }
+  // x = f0 ; x = relu(bn(conv3x3 s2(x))) + f_{i+1}
+  const __nv_bfloat16* x = p.net.hr.x[0][cur[0]];
+  for (int i = 0; i < 3; ++i) {
+    POEM_TRY(launch_conv(x, N, R[i], R[i], Cp[i], fd->delayer[i], Cp[i + 1], 3, 2, true, p.net.hr.x[i + 1][cur[i + 1]],
+                         p.d[i], st, 0, /*relu_before_res=*/true));
+    x = p.d[i];
+  }
+  // feat_in is a 1x1 convolution without norm / activation: it commutes with the bilinear upsampling (whose weights
+  // sum to one, so the bias passes through), so it runs on the 8x8 map (4x fewer MACs) and the upsampling kernel
+  // interpolates its fp32 output straight into the NCHW tensor the head consumes
+  const int Co_p = pad64(fd->out_channels);
+  POEM_TRY(launch_conv(x, N, R[3], R[3], Cp[3], fd->feat_in, Co_p, 1, 1, false, nullptr, nullptr, st, 0, false, p.f8));
+  {
+    const int Ro = 2 * R[3];
+    const size_t total = (size_t)N * fd->out_channels * Ro * Ro;
+    prof_begin(st);
+    upsample2x_nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.f8, mlvl_feat, N, R[3], R[3], Co_p,
+                                                                                  fd->out_channels);
+    LAUNCH_CHECK("upsample2x_nhwc_to_nchw_kernel");
+  }
+  return POEM_OK;
 }
 
 extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N,

@@ -59,13 +59,15 @@ def stage4_param_shapes(n_modules=3, channels=CHANNELS):
 
 
 def _fold(sd, conv_key, bn_key, cin_p, cout_p):
-    """conv (no bias) + eval BatchNorm -> bf16 [Cout_p, k*k*Cin_p] (K ordered ky, kx, c) and fp32 bias [Cout_p]."""
+    """conv (+ optional bias) + optional eval BatchNorm -> [Cout_p, k*k*Cin_p] (K ordered ky, kx, c), bias [Cout_p]."""
     w = sd[conv_key + ".weight"].double()
-    g, b = sd[bn_key + ".weight"].double(), sd[bn_key + ".bias"].double()
-    mu, var = sd[bn_key + ".running_mean"].double(), sd[bn_key + ".running_var"].double()
-    scale = g / torch.sqrt(var + BN_EPS)
-    w = w * scale[:, None, None, None]
-    bias = b - mu * scale
+    bias = sd[conv_key + ".bias"].double() if (conv_key + ".bias") in sd else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn_key is not None:
+        g, b = sd[bn_key + ".weight"].double(), sd[bn_key + ".bias"].double()
+        mu, var = sd[bn_key + ".running_mean"].double(), sd[bn_key + ".running_var"].double()
+        scale = g / torch.sqrt(var + BN_EPS)
+        w = w * scale[:, None, None, None]
+        bias = (bias - mu) * scale + b
     co, ci, kh, kw = w.shape
     wp = torch.zeros(cout_p, kh, kw, cin_p, dtype=torch.float64)
     wp[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
@@ -349,3 +351,111 @@ def backbone_flops_per_image(img_res=256, channels=CHANNELS):
         sec = "stem" if sec in ("conv1", "conv2") else ("transitions" if sec.startswith("transition") else sec)
         out[sec] = out.get(sec, 0.0) + 2.0 * shape[0] * shape[1] * shape[2] * shape[3] * r * r
     return out
+
+
+# ------------------------------------------------------------------------------------------------ images -> mlvl_feat
+FEAT_OUT = 160
+_OTHER_MODEL_PREFIXES = ("uv_delayer.", "uv_out.", "uv_in.", "ptEmb_head.", "mano_layer.", "img_backbone.incre_modules.",
+                         "img_backbone.downsamp_modules.", "img_backbone.final_layer.", "img_backbone.classifier.")
+
+
+def image_stage_param_shapes(channels=CHANNELS, out_channels=FEAT_OUT):
+    """Live keys of the image half of reference `PtEmbedMultiviewStereoV2` (lib/models/POEM.py:100-105,169-181):
+    `img_backbone.*` (HRNet), `feat_delayer.{0,1,2}.{conv,norm}.*`, `feat_in.conv.*`."""
+    s = {"img_backbone." + k: v for k, v in backbone_param_shapes(channels).items()}
+    for i in range(3):
+        p = f"feat_delayer.{i}."
+        s[p + "conv.weight"] = (channels[i + 1], channels[i], 3, 3)
+        s[p + "conv.bias"] = (channels[i + 1],)
+        for k, shp in (("weight", (channels[i + 1],)), ("bias", (channels[i + 1],)), ("running_mean", (channels[i + 1],)),
+                       ("running_var", (channels[i + 1],)), ("num_batches_tracked", ())):
+            s[p + "norm." + k] = shp
+    s["feat_in.conv.weight"] = (out_channels, channels[3], 1, 1)
+    s["feat_in.conv.bias"] = (out_channels,)
+    return s
+
+
+class ImageStage(nn.Module):
+    """`extract_img_feat` + `feat_decode` of the reference model (POEM.py:189-203, 255-265): images (BN,3,256,256) ->
+    `mlvl_feat` (BN,160,16,16), the tensor `POEM_Generalized_Head.forward` takes.  Keys as in the full-model
+    checkpoint; keys of the other halves of the model (`ptEmb_head.*`, `uv_*`, ...) are accepted and ignored."""
+
+    def __init__(self, channels=CHANNELS, out_channels=FEAT_OUT):
+        super().__init__()
+        self.channels, self.out_channels = tuple(channels), out_channels
+        self._names = []
+        for name, shape in image_stage_param_shapes(channels, out_channels).items():
+            t = torch.zeros(shape, dtype=torch.long if name.endswith("num_batches_tracked") else torch.float32)
+            if name.endswith("running_var") or (name.endswith(".weight") and len(shape) == 1):
+                t = torch.ones(shape)
+            self.register_buffer(name.replace(".", "__"), t)
+            self._names.append(name)
+        self._backbone = HRNetW40(channels=channels)
+        self._packed = None
+        self._ws = None
+
+    def state_dict(self, *a, prefix="", **k):
+        return {prefix + n: getattr(self, n.replace(".", "__")) for n in self._names}
+
+    def load_state_dict(self, sd, strict=True):
+        live = set(self._names)
+        missing = [n for n in self._names if n not in sd]
+        unexpected = [n for n in sd if n not in live and not n.startswith(_OTHER_MODEL_PREFIXES)]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"ImageStage: missing keys {missing[:4]}, unexpected keys {unexpected[:4]}")
+        for n in self._names:
+            if n in sd:
+                getattr(self, n.replace(".", "__")).copy_(sd[n])
+        self._packed = None
+
+    def _pack(self, device):
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        self._backbone.load_state_dict({k[len("img_backbone."):]: v for k, v in sd.items()
+                                        if k.startswith("img_backbone.")}, strict=True)
+        net = self._backbone._pack(device)
+        fd = nat.PoemFeatDecode()
+        keep = []
+
+        def lin(w, b):
+            wt = w.to(torch.bfloat16).contiguous().to(device)
+            bt = b.to(torch.float32).contiguous().to(device)
+            keep.extend([wt, bt])
+            return nat.PoemLinear(wt.data_ptr(), bt.data_ptr())
+        cp = [_pad64(c) for c in self.channels]
+        for i in range(3):
+            p = f"feat_delayer.{i}."
+            fd.delayer[i] = lin(*_fold(sd, p + "conv", p + "norm", cp[i], cp[i + 1]))
+        fd.feat_in = lin(*_fold(sd, "feat_in.conv", None, cp[3], _pad64(self.out_channels)))
+        fd.out_channels = self.out_channels
+        self._packed = (net, fd, keep, str(device))
+        return net, fd
+
+    @torch.no_grad()
+    def forward(self, img, return_maps=False):
+        if not img.is_cuda:
+            raise nat.PoemError("ImageStage input must be a CUDA tensor: there is no CPU implementation")
+        dev = img.device
+        img = img.reshape(-1, *img.shape[-3:]).contiguous().float()
+        n, c, h, w = img.shape
+        assert c == 3 and h == w, tuple(img.shape)
+        lib = nat.load()
+        if self._packed is not None and self._packed[3] == str(dev):
+            net, fd = self._packed[0], self._packed[1]
+        else:
+            net, fd = self._pack(dev)
+        need = lib.poem_image_features_workspace_bytes(C.byref(net), C.byref(fd), n, h)
+        if need == 0:
+            raise nat.PoemError(f"ImageStage: unsupported image size {h}")
+        if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+        off = (-self._ws.data_ptr()) % 1024
+        feat = torch.empty(n, self.out_channels, h // 16, h // 16, device=dev)
+        maps, maps_p = None, None
+        if return_maps:
+            maps = [torch.empty(n, ch, (h // 4) >> b, (h // 4) >> b, device=dev) for b, ch in enumerate(self.channels)]
+            maps_p = (C.c_void_p * 4)(*[o.data_ptr() for o in maps])
+        nat.check(lib.poem_image_features(C.byref(net), C.byref(fd), n, h, img.data_ptr(), feat.data_ptr(), maps_p,
+                                          self._ws.data_ptr() + off, self._ws.numel() - off,
+                                          torch.cuda.current_stream(dev).cuda_stream))
+        return (feat, maps) if return_maps else feat

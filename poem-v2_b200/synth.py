@@ -215,6 +215,27 @@ def make_backbone_state_dict(seed: int = 0):
     return sd
 
 
+def make_image_stage_state_dict(seed: int = 0):
+    """Seeded weights for backbone + feat_decode under the full-model key names (`img_backbone.*`, `feat_delayer.*`,
+    `feat_in.*`)."""
+    from .hrnet import image_stage_param_shapes
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in image_stage_param_shapes().items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(100)
+        elif name.endswith("running_var"):
+            sd[name] = 0.5 + torch.rand(shape, generator=g)
+        elif name.endswith("running_mean") or name.endswith(".bias"):
+            sd[name] = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[name] = 0.6 + 0.2 * torch.rand(shape, generator=g)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[name] = torch.randn(shape, generator=g) * math.sqrt(1.0 / fan_in)
+    return sd
+
+
 def make_images(n_images: int, res: int = 256, seed: int = 1):
     """ImageNet-normalised-looking images: smooth low-frequency content plus pixel noise, roughly unit variance."""
     g = torch.Generator().manual_seed(seed)

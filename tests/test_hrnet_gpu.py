@@ -177,3 +177,67 @@ def test_backbone_rejects_bad_input():
         m(torch.zeros(1, 3, 224, 224, device="cuda"))   # only the 256x256 release resolution
     with pytest.raises(RuntimeError):
         m.load_state_dict({"conv1.weight": torch.zeros(64, 3, 3, 3)}, strict=True)
+
+
+# ------------------------------------------------------------------------------------------------ images -> mlvl_feat
+@pytest.mark.parametrize("N", [1, 4])
+def test_image_stage_matches_oracle(N):
+    from poem_v2_b200.hrnet import ImageStage
+    sd = synth.make_image_stage_state_dict(0)
+    img = synth.make_images(N, 256, 1)
+    with torch.no_grad():
+        want, want_maps = orc.image_features(sd, img)
+    m = ImageStage()
+    m.load_state_dict(sd, strict=True)
+    got, maps = m(img.cuda(), return_maps=True)
+    _check_maps([got.cpu()], [want], f"mlvl_feat N={N}")
+    _check_maps([x.cpu() for x in maps], want_maps, f"image stage maps N={N}")
+    again = m(img.cuda())                       # without the map export: same features
+    assert torch.equal(again, got)
+
+
+def test_image_stage_matches_reference_golden():
+    import ast
+    import os
+    import numpy as np
+    from poem_v2_b200.hrnet import ImageStage
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "image_stage_n1.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    sd = synth.make_image_stage_state_dict(meta["wseed"])
+    sd["ptEmb_head.input_proj.weight"] = torch.zeros(4)       # other halves of the full-model checkpoint: ignored
+    sd["uv_out.conv.bias"] = torch.zeros(21)
+    m = ImageStage()
+    m.load_state_dict(sd, strict=True)
+    got = m(synth.make_images(meta["n_images"], 256, meta["iseed"]).cuda()).cpu()
+    _check_maps([got], [torch.from_numpy(z["mlvl_feat"])], "mlvl_feat golden")
+
+
+def test_images_to_mesh_pipeline():
+    """ImageStage -> POEM_Generalized_Head on the device, against oracle.image_features -> oracle.head_forward."""
+    from poem_v2_b200.config import release_dims
+    from poem_v2_b200.head import POEM_Generalized_Head
+    from poem_v2_b200.hrnet import ImageStage
+    dims = release_dims("small")
+    B, V = 1, 2
+    sd_img = synth.make_image_stage_state_dict(0)
+    sd_img["feat_in.conv.weight"] *= 0.1      # unit-scale mlvl_feat, the range the synthetic head weights are made for
+    sd_img["feat_in.conv.bias"] *= 0.1
+    sd_head = synth.make_state_dict(dims, 0)
+    _, metas, ref_j = synth.make_inputs(dims, B, [V], 1)
+    img = synth.make_images(B * V, 256, 2)
+    bps, a_xyz, a_idx = synth.load_assets()
+    with torch.no_grad():
+        feat_ref, _ = orc.image_features(sd_img, img)
+        want = orc.head_forward(sd_head, dims, feat_ref, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx)
+    stage = ImageStage()
+    stage.load_state_dict(sd_img, strict=True)
+    head = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    head.load_state_dict(sd_head, strict=True)
+    head = head.cuda().eval()
+    m = dict(metas)
+    m["cam_intr"], m["cam_extr"] = metas["cam_intr"].cuda(), metas["cam_extr"].cuda()
+    feat = stage(img.cuda())
+    got = head(mlvl_feat=feat, img_metas=m, reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
+    err = (got - want).norm(dim=-1)
+    print(f"images->mesh: mean |ours - oracle| = {err.mean().item() * 1e3:.4f} mm, max {err.max().item() * 1e3:.3f} mm")
+    assert torch.isfinite(got).all() and err.mean().item() * 1e3 <= 1.0
