@@ -223,11 +223,29 @@ typedef struct PoemFeatDecode {
   PoemLinear feat_in;      /* 1x1 320 -> out_channels (padded to 64) */
   int32_t out_channels;    /* 160 */
 } PoemFeatDecode;
-size_t poem_image_features_workspace_bytes(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images, int img_res);
+/* `uv_decode` + `heatmap_stage` (POEM.py:205-229, HRNet branch): x = f3; x = ConvBlock_i(cat(bilinear x2(x), f_{2-i}))
+ * for i = 0..2 (3x3 conv + bias + BN + ReLU: 480->160, 240->80, 120->40); 2x2 max-pool; 1x1 conv 40 -> n_joints +
+ * sigmoid; pdf normalisation and integral soft-argmax (lib/models/integal_pose.py:196-220) scaled to pixels. */
+typedef struct PoemUVDecode {
+  PoemLinear delayer[3];   /* input channels ordered (upsampled, skip) as torch.cat does, then zero-padded to 64 */
+  const float* out_w;      /* fp32 [n_joints, 40] */
+  const float* out_b;      /* fp32 [n_joints] */
+  int32_t n_joints;        /* 21 */
+} PoemUVDecode;
+size_t poem_image_features_workspace_bytes(const PoemHRNet* w, const PoemFeatDecode* fd, const PoemUVDecode* uv,
+                                           int n_images, int img_res);
 /* images fp32 NCHW (n_images, 3, 256, 256) -> mlvl_feat fp32 NCHW (n_images, out_channels, 16, 16), the tensor
- * poem_head_forward takes; maps: optional four fp32 NCHW backbone outputs (NULL to skip the export). */
-int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images, int img_res, const float* images,
-                        float* mlvl_feat, float* const* maps, void* workspace, size_t workspace_bytes, void* stream);
+ * poem_head_forward takes.  uv != NULL additionally runs the heatmap branch: uv_px fp32 (n_images, n_joints, 2) in
+ * pixels (`pred_joints_uv`, POEM.py:331) and, if heatmap != NULL, the sigmoid maps fp32 (n_images, n_joints, 32, 32).
+ * maps: optional four fp32 NCHW backbone outputs (NULL to skip the export). */
+int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, const PoemUVDecode* uv, int n_images, int img_res,
+                        const float* images, float* mlvl_feat, float* uv_px, float* heatmap, float* const* maps,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* Batched DLT triangulation (lib/utils/triangulation.py:5-45 in the per-sample loop of POEM.py:284-299): uv_px
+ * (n_images, n_joints, 2), cam_intr (n_images, 3, 3), cam_extr (n_images, 4, 4) camera-to-master, view_counts int32
+ * [batch] -> ref_joints fp32 (batch, n_joints, 3).  All device pointers. */
+int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, const float* cam_extr, const int32_t* view_counts,
+                         int batch, int n_joints, float* ref_joints, void* stream);
 
 /* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
  * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.

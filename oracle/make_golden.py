@@ -112,15 +112,30 @@ def run_reference_image_stage(n_images, wseed, iseed):
             self.feat_delayer = torch.nn.ModuleList([ConvBlock(fs[i], fs[i + 1], kernel_size=3, stride=2, relu=True, norm="bn")
                                                      for i in range(3)])
             self.feat_in = ConvBlock(fs[3], fs[2], kernel_size=1, padding=0, relu=False, norm=None)
+            self.num_joints = 21
+            self.uv_delayer = torch.nn.ModuleList([ConvBlock(fs[3 - i] + fs[2 - i], fs[2 - i], kernel_size=3, relu=True,
+                                                             norm="bn") for i in range(3)])
+            self.uv_out = ConvBlock(fs[0], 21, kernel_size=1, padding=0, relu=False, norm=None)
+            self.uv_in = ConvBlock(21, fs[1], kernel_size=1, padding=0, relu=True, norm="bn")
+
+        def uv_decode(self, feats):
+            return poem_mod.PtEmbedMultiviewStereoV2.uv_decode(self, feats)
     shell = Shell().eval()
     sd = synth.make_image_stage_state_dict(wseed)
     missing, unexpected = shell.load_state_dict(sd, strict=False)
     dead = ("img_backbone.incre_modules.", "img_backbone.downsamp_modules.", "img_backbone.final_layer.",
-            "img_backbone.classifier.")
+            "img_backbone.classifier.", "uv_in.")
     assert not unexpected and all(k.startswith(dead) for k in missing), (missing[:5], unexpected[:5])
+    from lib.utils.triangulation import batch_triangulate_dlt_torch
     with torch.no_grad():
         feats = shell.img_backbone(synth.make_images(n_images, 256, iseed))
-        return poem_mod.PtEmbedMultiviewStereoV2.feat_decode(shell, feats, "HRNet"), feats
+        mlvl = poem_mod.PtEmbedMultiviewStereoV2.feat_decode(shell, feats, "HRNet")
+        uv = poem_mod.PtEmbedMultiviewStereoV2.heatmap_stage(shell, feats, 256, 256)
+        # the per-sample DLT loop of POEM.py:284-299 on the reference function, all images as the views of one sample
+        intr, extr = synth.make_cameras(1, [n_images], iseed)
+        K, T = intr.view(-1, 3, 3), torch.linalg.inv(extr.view(-1, 4, 4))
+        ref_j = batch_triangulate_dlt_torch(uv.unsqueeze(0), K.unsqueeze(0), T.unsqueeze(0))
+    return mlvl, feats, uv, ref_j
 
 
 def run_reference_stage4(n_images, wseed, iseed):
@@ -145,10 +160,11 @@ def main():
                         y0=ys[0][:, :, ::4, ::4].numpy(), y1=ys[1][:, :, ::2, ::2].numpy(), y2=ys[2].numpy(),
                         y3=ys[3].numpy())
     print("hrnet_w40_n1", [tuple(y.shape) for y in ys], [float(y.abs().mean()) for y in ys])
-    mf, _ = run_reference_image_stage(1, 0, 1)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "image_stage_n1.npz"),
-                        meta=np.array(repr(dict(kind="image_stage", n_images=1, wseed=0, iseed=1))), mlvl_feat=mf.numpy())
-    print("image_stage_n1", tuple(mf.shape), float(mf.abs().mean()))
+    mf, _, uv, rj = run_reference_image_stage(3, 0, 1)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "image_stage_n3.npz"),
+                        meta=np.array(repr(dict(kind="image_stage", n_images=3, wseed=0, iseed=1))), mlvl_feat=mf.numpy(),
+                        pred_joints_uv=uv.numpy(), ref_joints=rj.numpy())
+    print("image_stage_n3", tuple(mf.shape), float(mf.abs().mean()), tuple(uv.shape), tuple(rj.shape), rj[0, :2])
     if "--only-hrnet" in sys.argv:
         return
     ys = run_reference_stage4(2, 0, 1)

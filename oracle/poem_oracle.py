@@ -317,3 +317,41 @@ def image_features(sd, img):
     """images -> mlvl_feat: `extract_img_feat` + `feat_decode` (POEM.py:255-265); sd holds full-model keys."""
     feats = hrnet_forward({k[len("img_backbone."):]: v for k, v in sd.items() if k.startswith("img_backbone.")}, img)
     return feat_decode(sd, feats), feats
+
+
+def uv_decode_heatmap(sd, feats, img_w=256, img_h=256):
+    """`uv_decode` + `heatmap_stage`, HRNet branch (lib/models/POEM.py:205-229) with `integral_heatmap2d`
+    (lib/models/integal_pose.py:196-220).  Returns (uv_px (BN,21,2), uv_hmap (BN,21,32,32))."""
+    rev = list(reversed(feats))
+    x = rev[0]
+    for i in range(3):
+        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        x = torch.cat((x, rev[i + 1]), dim=1)
+        p = f"uv_delayer.{i}."
+        x = _conv_bn(sd, p + "conv", p + "norm", x, relu=True)
+    x = F.max_pool2d(x, kernel_size=2, stride=2)
+    hmap = torch.sigmoid(_conv_bn(sd, "uv_out.conv", None, x))
+    pdf = hmap.reshape(*hmap.shape[:2], -1)
+    pdf = (pdf / (pdf.sum(dim=-1, keepdim=True) + 1e-6)).view_as(hmap)
+    v_accu, u_accu = pdf.sum(dim=3), pdf.sum(dim=2)
+    wv = torch.arange(v_accu.shape[-1], dtype=pdf.dtype) / v_accu.shape[-1]
+    wu = torch.arange(u_accu.shape[-1], dtype=pdf.dtype) / u_accu.shape[-1]
+    uv = torch.cat([(u_accu * wu).sum(-1, keepdim=True), (v_accu * wv).sum(-1, keepdim=True)], dim=-1)
+    return uv * torch.tensor([float(img_w), float(img_h)]), hmap
+
+
+def triangulate_dlt(uv_px, cam_intr, cam_extr, view_counts):
+    """Reference joints by DLT, per sample over its own views (POEM.py:284-299 calling
+    lib/utils/triangulation.py:5-45): M = K * inv(cam_extr)[:3]; A rows u*M[2]-M[0], v*M[2]-M[1]; X = last row of VT."""
+    out = []
+    T = torch.linalg.inv(cam_extr.view(-1, 4, 4))
+    K = cam_intr.view(-1, 3, 3)
+    start = 0
+    for n in view_counts:
+        M = torch.matmul(K[start:start + n], T[start:start + n, :3, :])          # (n,3,4)
+        kp = uv_px[start:start + n].permute(1, 0, 2).unsqueeze(3)                 # (J,n,2,1)
+        A = (kp * M[None, :, 2:3, :] - M[None, :, :2, :]).reshape(kp.shape[0], -1, 4)
+        VT = torch.linalg.svd(A)[2]
+        out.append(VT[:, -1, :3] / (VT[:, -1, 3:] + 1e-7))
+        start += n
+    return torch.stack(out)

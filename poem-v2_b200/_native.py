@@ -107,6 +107,10 @@ class PoemFeatDecode(C.Structure):
     _fields_ = [("delayer", PoemLinear * 3), ("feat_in", PoemLinear), ("out_channels", C.c_int32)]
 
 
+class PoemUVDecode(C.Structure):
+    _fields_ = [("delayer", PoemLinear * 3), ("out_w", C.c_void_p), ("out_b", C.c_void_p), ("n_joints", C.c_int32)]
+
+
 class PoemInputs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_images", C.c_int32), ("view_counts", C.c_void_p), ("mlvl_feat", C.c_void_p),
                 ("cam_intr", C.c_void_p), ("cam_extr", C.c_void_p), ("reference_joints", C.c_void_p),
@@ -116,7 +120,7 @@ class PoemInputs(C.Structure):
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
            "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_hrnet_stage4_workspace_bytes",
-           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_triangulate_dlt", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
@@ -186,9 +190,13 @@ def load():
     lib.poem_hrnet_forward.restype = i
     lib.poem_hrnet_forward.argtypes = [C.POINTER(PoemHRNet), i, i, vp, C.POINTER(vp), vp, sz, vp]
     lib.poem_image_features_workspace_bytes.restype = sz
-    lib.poem_image_features_workspace_bytes.argtypes = [C.POINTER(PoemHRNet), C.POINTER(PoemFeatDecode), i, i]
+    lib.poem_image_features_workspace_bytes.argtypes = [C.POINTER(PoemHRNet), C.POINTER(PoemFeatDecode),
+                                                        C.POINTER(PoemUVDecode), i, i]
     lib.poem_image_features.restype = i
-    lib.poem_image_features.argtypes = [C.POINTER(PoemHRNet), C.POINTER(PoemFeatDecode), i, i, vp, vp, C.POINTER(vp), vp, sz, vp]
+    lib.poem_image_features.argtypes = [C.POINTER(PoemHRNet), C.POINTER(PoemFeatDecode), C.POINTER(PoemUVDecode), i, i, vp,
+                                        vp, vp, vp, C.POINTER(vp), vp, sz, vp]
+    lib.poem_triangulate_dlt.restype = i
+    lib.poem_triangulate_dlt.argtypes = [vp, vp, vp, vp, i, i, vp, vp]
     lib.poem_conv_nhwc.restype = i
     lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, i, vp]
     lib.poem_debug_conv_mode.restype = None

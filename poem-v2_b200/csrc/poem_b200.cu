@@ -640,10 +640,12 @@ extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res,
 // ------------------------------------------------------------------------------------------------
 struct FeatPlan {
   HrNetPlan net;
-  __nv_bfloat16* d[3];   // pyramid sums at R/8, R/16, R/32
-  float* f8;             // feat_in output at R/32, fp32 NHWC (padded channels)
+  __nv_bfloat16* d[3];     // pyramid sums at R/8, R/16, R/32
+  float* f8;               // feat_in output at R/32, fp32 NHWC (padded channels)
+  __nv_bfloat16* cat[3];   // uv_decode: cat(upsampled, skip) at R/16, R/8, R/4
+  __nv_bfloat16* u[3];     // uv_decode: ConvBlock outputs at R/16, R/8, R/4
 };
-static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, uint8_t* base, FeatPlan* p) {
+static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, bool with_uv, uint8_t* base, FeatPlan* p) {
   const size_t net = hrnet_plan(N, img_res, ch, base, &p->net);
   Bump b{base ? base + ((net + 1023) & ~size_t(1023)) : nullptr, 0};
   for (int i = 0; i < 3; ++i) {
@@ -652,31 +654,41 @@ static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, uint8_t* 
   }
   const size_t r8 = (size_t)img_res / 32;
   p->f8 = b.take<float>((size_t)N * r8 * r8 * pad64(out_ch));
+  for (int i = 0; i < 3; ++i) {
+    p->cat[i] = p->u[i] = nullptr;
+    if (!with_uv) continue;
+    const size_t r = (size_t)(img_res / 16) << i;    // R/16, R/8, R/4
+    p->cat[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad64(ch[3 - i] + ch[2 - i]));
+    p->u[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad64(ch[2 - i]));
+  }
   return ((net + 1023) & ~size_t(1023)) + b.off;
 }
-extern "C" size_t poem_image_features_workspace_bytes(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images,
-                                                      int img_res) {
+extern "C" size_t poem_image_features_workspace_bytes(const PoemHRNet* w, const PoemFeatDecode* fd, const PoemUVDecode* uv,
+                                                      int n_images, int img_res) {
   if (!w || !fd || n_images < 1 || img_res < 64 || img_res % 32) return 0;
   FeatPlan p;
-  return feat_plan(n_images, img_res, w->channels, fd->out_channels, nullptr, &p);
+  return feat_plan(n_images, img_res, w->channels, fd->out_channels, uv != nullptr, nullptr, &p);
 }
 
-extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, int n_images, int img_res,
-                                   const float* images, float* mlvl_feat, float* const* maps, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, const PoemUVDecode* uv, int n_images,
+                                   int img_res, const float* images, float* mlvl_feat, float* uv_px, float* heatmap,
+                                   float* const* maps, void* workspace, size_t workspace_bytes, void* stream) {
   POEM_TRY(hrnet_check(w, img_res, images, workspace));
   if (!fd || !mlvl_feat) return fail(POEM_E_NULL, "image_features: null pointer");
   if (fd->out_channels < 1 || fd->out_channels > 256) return fail(POEM_E_BADDIM, "out_channels=%d", fd->out_channels);
+  if (uv && (!uv_px || !uv->out_w || !uv->out_b)) return fail(POEM_E_NULL, "image_features: uv pointers missing");
+  if (uv && (uv->n_joints < 1 || uv->n_joints > HEAT_MAX_J)) return fail(POEM_E_BADDIM, "n_joints=%d", uv->n_joints);
   const int N = n_images;
   const int* ch = w->channels;
   cudaStream_t st = (cudaStream_t)stream;
   FeatPlan p;
-  const size_t need = feat_plan(N, img_res, ch, fd->out_channels, reinterpret_cast<uint8_t*>(workspace), &p);
+  const size_t need = feat_plan(N, img_res, ch, fd->out_channels, uv != nullptr, reinterpret_cast<uint8_t*>(workspace), &p);
   if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
   int Cp[4], R[4], cur[4];
   for (int i = 0; i < 4; ++i) {
     Cp[i] = pad64(ch[i]);
     R[i] = (img_res / 4) >> i;
+    if (uv && ch[i] % 8) return fail(POEM_E_BADDIM, "uv_decode needs channel counts that are multiples of 8");
   }
   POEM_TRY(hrnet_run(w, N, img_res, images, p.net, cur, st));
   if (maps) {
@@ -684,7 +696,7 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
       if (!maps[i]) return fail(POEM_E_NULL, "image_features: map %d missing", i);
     POEM_TRY(hr_export(p.net.hr, cur, ch, Cp, R, N, maps, st));
   }
-  // x = f0 ; x = relu(bn(conv3x3 s2(x))) + f_{i+1}
+  // ---- feat_decode: x = f0 ; x = relu(bn(conv3x3 s2(x))) + f_{i+1}
   const __nv_bfloat16* x = p.net.hr.x[0][cur[0]];
   for (int i = 0; i < 3; ++i) {
     POEM_TRY(launch_conv(x, N, R[i], R[i], Cp[i], fd->delayer[i], Cp[i + 1], 3, 2, true, p.net.hr.x[i + 1][cur[i + 1]],
@@ -704,6 +716,43 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
                                                                                   fd->out_channels);
     LAUNCH_CHECK("upsample2x_nhwc_to_nchw_kernel");
   }
+  if (!uv) return POEM_OK;
+  // ---- uv_decode + heatmap_stage (POEM.py:205-229): x = f3; x = ConvBlock_i(cat(up2(x), f_{2-i})); max-pool; 1x1 +
+  // sigmoid; soft-argmax
+  const __nv_bfloat16* h = p.net.hr.x[3][cur[3]];
+  int h_cp = Cp[3], h_c = ch[3];
+  for (int i = 0; i < 3; ++i) {
+    const int lo = 2 - i;                      // skip branch, resolution R[lo]
+    const int cat_cp = pad64(h_c + ch[lo]);
+    const size_t total8 = (size_t)N * R[lo] * R[lo] * cat_cp / 8;
+    prof_begin(st);
+    upsample2x_concat_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+        h, p.net.hr.x[lo][cur[lo]], p.cat[i], R[lo] / 2, R[lo] / 2, h_cp, h_c, Cp[lo], ch[lo], cat_cp, total8);
+    LAUNCH_CHECK("upsample2x_concat_kernel");
+    POEM_TRY(launch_conv(p.cat[i], N, R[lo], R[lo], cat_cp, uv->delayer[i], Cp[lo], 3, 1, true, nullptr, p.u[i], st));
+    h = p.u[i];
+    h_cp = Cp[lo];
+    h_c = ch[lo];
+  }
+  {
+    const int J = uv->n_joints, Rp = R[0] / 2;
+    const size_t smem = (size_t)(J * ch[0] + J + 8 * J * 3) * sizeof(float);
+    prof_begin(st);
+    heatmap_uv_kernel<<<N, 256, smem, st>>>(h, uv->out_w, uv->out_b, uv_px, heatmap, Rp, Cp[0], ch[0], J, (float)img_res,
+                                           (float)img_res);
+    LAUNCH_CHECK("heatmap_uv_kernel");
+  }
+  return POEM_OK;
+}
+
+extern "C" int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, const float* cam_extr,
+                                    const int32_t* view_counts, int batch, int n_joints, float* ref_joints, void* stream) {
+  if (!uv_px || !cam_intr || !cam_extr || !view_counts || !ref_joints) return fail(POEM_E_NULL, "triangulate: null pointer");
+  if (batch < 1 || n_joints < 1 || n_joints > 32) return fail(POEM_E_BADDIM, "triangulate: batch=%d joints=%d", batch, n_joints);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  dlt_triangulate_kernel<<<batch, 32, 0, st>>>(uv_px, cam_intr, cam_extr, view_counts, ref_joints, n_joints);
+  LAUNCH_CHECK("dlt_triangulate_kernel");
   return POEM_OK;
 }
 

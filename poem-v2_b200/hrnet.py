@@ -355,13 +355,15 @@ def backbone_flops_per_image(img_res=256, channels=CHANNELS):
 
 # ------------------------------------------------------------------------------------------------ images -> mlvl_feat
 FEAT_OUT = 160
-_OTHER_MODEL_PREFIXES = ("uv_delayer.", "uv_out.", "uv_in.", "ptEmb_head.", "mano_layer.", "img_backbone.incre_modules.",
+N_JOINTS = 21
+_OTHER_MODEL_PREFIXES = ("uv_in.", "ptEmb_head.", "mano_layer.", "img_backbone.incre_modules.",
                          "img_backbone.downsamp_modules.", "img_backbone.final_layer.", "img_backbone.classifier.")
 
 
 def image_stage_param_shapes(channels=CHANNELS, out_channels=FEAT_OUT):
-    """Live keys of the image half of reference `PtEmbedMultiviewStereoV2` (lib/models/POEM.py:100-105,169-181):
-    `img_backbone.*` (HRNet), `feat_delayer.{0,1,2}.{conv,norm}.*`, `feat_in.conv.*`."""
+    """Live keys of the image half of reference `PtEmbedMultiviewStereoV2` (lib/models/POEM.py:100-105,169-194):
+    `img_backbone.*` (HRNet), `feat_delayer.{0,1,2}.{conv,norm}.*`, `feat_in.conv.*`, `uv_delayer.*`, `uv_out.conv.*`
+    (`uv_in.*` only produces `uv_feat`, which inference discards: dead)."""
     s = {"img_backbone." + k: v for k, v in backbone_param_shapes(channels).items()}
     for i in range(3):
         p = f"feat_delayer.{i}."
@@ -372,13 +374,25 @@ def image_stage_param_shapes(channels=CHANNELS, out_channels=FEAT_OUT):
             s[p + "norm." + k] = shp
     s["feat_in.conv.weight"] = (out_channels, channels[3], 1, 1)
     s["feat_in.conv.bias"] = (out_channels,)
+    for i in range(3):                       # uv_delayer (POEM.py:184-191): cat(up(x), skip) -> skip's channel count
+        cin, cout = channels[3 - i] + channels[2 - i], channels[2 - i]
+        p = f"uv_delayer.{i}."
+        s[p + "conv.weight"] = (cout, cin, 3, 3)
+        s[p + "conv.bias"] = (cout,)
+        for k, shp in (("weight", (cout,)), ("bias", (cout,)), ("running_mean", (cout,)), ("running_var", (cout,)),
+                       ("num_batches_tracked", ())):
+            s[p + "norm." + k] = shp
+    s["uv_out.conv.weight"] = (N_JOINTS, channels[0], 1, 1)
+    s["uv_out.conv.bias"] = (N_JOINTS,)
     return s
 
 
 class ImageStage(nn.Module):
-    """`extract_img_feat` + `feat_decode` of the reference model (POEM.py:189-203, 255-265): images (BN,3,256,256) ->
-    `mlvl_feat` (BN,160,16,16), the tensor `POEM_Generalized_Head.forward` takes.  Keys as in the full-model
-    checkpoint; keys of the other halves of the model (`ptEmb_head.*`, `uv_*`, ...) are accepted and ignored."""
+    """`extract_img_feat` + `feat_decode` + `heatmap_stage` of the reference model (POEM.py:189-229, 255-268): images
+    (BN,3,256,256) -> `mlvl_feat` (BN,160,16,16), the tensor `POEM_Generalized_Head.forward` takes, and the 2-D joint
+    estimates `pred_joints_uv` (BN,21,2); `triangulate` turns those into `reference_joints` (POEM.py:284-299).  Keys
+    as in the full-model checkpoint; keys of the other parts of the model (`ptEmb_head.*`, `uv_in.*`, `mano_layer.*`)
+    are accepted and ignored."""
 
     def __init__(self, channels=CHANNELS, out_channels=FEAT_OUT):
         super().__init__()
@@ -427,11 +441,38 @@ class ImageStage(nn.Module):
             fd.delayer[i] = lin(*_fold(sd, p + "conv", p + "norm", cp[i], cp[i + 1]))
         fd.feat_in = lin(*_fold(sd, "feat_in.conv", None, cp[3], _pad64(self.out_channels)))
         fd.out_channels = self.out_channels
-        self._packed = (net, fd, keep, str(device))
-        return net, fd
+        uv = nat.PoemUVDecode()
+        ch = self.channels
+        for i in range(3):
+            p = f"uv_delayer.{i}."
+            uv.delayer[i] = lin(*_fold(sd, p + "conv", p + "norm", _pad64(ch[3 - i] + ch[2 - i]), cp[2 - i]))
+        ow = sd["uv_out.conv.weight"].reshape(N_JOINTS, ch[0]).float().contiguous().to(device)
+        ob = sd["uv_out.conv.bias"].float().contiguous().to(device)
+        keep.extend([ow, ob])
+        uv.out_w, uv.out_b, uv.n_joints = ow.data_ptr(), ob.data_ptr(), N_JOINTS
+        self._packed = (net, fd, keep, str(device), uv)
+        return net, fd, uv
+
+    @staticmethod
+    @torch.no_grad()
+    def triangulate(uv_px, cam_intr, cam_extr, cam_view_num):
+        """`reference_joints` (B,21,3) from the 2-D estimates of each sample's views (POEM.py:284-299)."""
+        if not uv_px.is_cuda:
+            raise nat.PoemError("triangulate inputs must be CUDA tensors: there is no CPU implementation")
+        dev = uv_px.device
+        counts = torch.as_tensor([int(v) for v in cam_view_num], dtype=torch.int32, device=dev)
+        n = int(counts.sum().item())
+        uv = uv_px.reshape(n, -1, 2).contiguous().float()
+        k = cam_intr.reshape(n, 3, 3).to(dev).contiguous().float()
+        e = cam_extr.reshape(n, 4, 4).to(dev).contiguous().float()
+        out = torch.empty(len(counts), uv.shape[1], 3, device=dev)
+        nat.check(nat.load().poem_triangulate_dlt(uv.data_ptr(), k.data_ptr(), e.data_ptr(), counts.data_ptr(),
+                                                  len(counts), uv.shape[1], out.data_ptr(),
+                                                  torch.cuda.current_stream(dev).cuda_stream))
+        return out
 
     @torch.no_grad()
-    def forward(self, img, return_maps=False):
+    def forward(self, img, return_maps=False, return_uv=False, return_heatmap=False):
         if not img.is_cuda:
             raise nat.PoemError("ImageStage input must be a CUDA tensor: there is no CPU implementation")
         dev = img.device
@@ -440,10 +481,12 @@ class ImageStage(nn.Module):
         assert c == 3 and h == w, tuple(img.shape)
         lib = nat.load()
         if self._packed is not None and self._packed[3] == str(dev):
-            net, fd = self._packed[0], self._packed[1]
+            net, fd, uv = self._packed[0], self._packed[1], self._packed[4]
         else:
-            net, fd = self._pack(dev)
-        need = lib.poem_image_features_workspace_bytes(C.byref(net), C.byref(fd), n, h)
+            net, fd, uv = self._pack(dev)
+        want_uv = return_uv or return_heatmap
+        uv_ref = C.byref(uv) if want_uv else None
+        need = lib.poem_image_features_workspace_bytes(C.byref(net), C.byref(fd), uv_ref, n, h)
         if need == 0:
             raise nat.PoemError(f"ImageStage: unsupported image size {h}")
         if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
@@ -455,7 +498,20 @@ class ImageStage(nn.Module):
         if return_maps:
             maps = [torch.empty(n, ch, (h // 4) >> b, (h // 4) >> b, device=dev) for b, ch in enumerate(self.channels)]
             maps_p = (C.c_void_p * 4)(*[o.data_ptr() for o in maps])
-        nat.check(lib.poem_image_features(C.byref(net), C.byref(fd), n, h, img.data_ptr(), feat.data_ptr(), maps_p,
+        uv_px = torch.empty(n, N_JOINTS, 2, device=dev) if want_uv else None
+        heat = torch.empty(n, N_JOINTS, h // 8, h // 8, device=dev) if return_heatmap else None
+        nat.check(lib.poem_image_features(C.byref(net), C.byref(fd), uv_ref, n, h, img.data_ptr(), feat.data_ptr(),
+                                          uv_px.data_ptr() if want_uv else None,
+                                          heat.data_ptr() if return_heatmap else None, maps_p,
                                           self._ws.data_ptr() + off, self._ws.numel() - off,
                                           torch.cuda.current_stream(dev).cuda_stream))
-        return (feat, maps) if return_maps else feat
+        if not (return_maps or want_uv):
+            return feat
+        out = {"mlvl_feat": feat}
+        if return_maps:
+            out["img_feats"] = maps
+        if want_uv:
+            out["pred_joints_uv"] = uv_px
+        if return_heatmap:
+            out["uv_hmap"] = heat
+        return out

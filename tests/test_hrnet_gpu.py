@@ -189,7 +189,8 @@ def test_image_stage_matches_oracle(N):
         want, want_maps = orc.image_features(sd, img)
     m = ImageStage()
     m.load_state_dict(sd, strict=True)
-    got, maps = m(img.cuda(), return_maps=True)
+    res = m(img.cuda(), return_maps=True)
+    got, maps = res["mlvl_feat"], res["img_feats"]
     _check_maps([got.cpu()], [want], f"mlvl_feat N={N}")
     _check_maps([x.cpu() for x in maps], want_maps, f"image stage maps N={N}")
     again = m(img.cuda())                       # without the map export: same features
@@ -201,15 +202,68 @@ def test_image_stage_matches_reference_golden():
     import os
     import numpy as np
     from poem_v2_b200.hrnet import ImageStage
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "image_stage_n1.npz"))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "image_stage_n3.npz"))
     meta = ast.literal_eval(str(z["meta"]))
+    n = meta["n_images"]
     sd = synth.make_image_stage_state_dict(meta["wseed"])
-    sd["ptEmb_head.input_proj.weight"] = torch.zeros(4)       # other halves of the full-model checkpoint: ignored
-    sd["uv_out.conv.bias"] = torch.zeros(21)
+    sd["ptEmb_head.input_proj.weight"] = torch.zeros(4)       # other parts of the full-model checkpoint: ignored
+    sd["uv_in.conv.bias"] = torch.zeros(80)
     m = ImageStage()
     m.load_state_dict(sd, strict=True)
-    got = m(synth.make_images(meta["n_images"], 256, meta["iseed"]).cuda()).cpu()
-    _check_maps([got], [torch.from_numpy(z["mlvl_feat"])], "mlvl_feat golden")
+    res = m(synth.make_images(n, 256, meta["iseed"]).cuda(), return_uv=True)
+    _check_maps([res["mlvl_feat"].cpu()], [torch.from_numpy(z["mlvl_feat"])], "mlvl_feat golden")
+    uv = res["pred_joints_uv"].cpu()
+    duv = (uv - torch.from_numpy(z["pred_joints_uv"])).abs()
+    print(f"pred_joints_uv golden: max |d| {duv.max().item():.4f} px, mean {duv.mean().item():.4f} px")
+    assert duv.max().item() <= 1.0 and duv.mean().item() <= 0.25          # 256-px image, bf16 conv stack
+    intr, extr = synth.make_cameras(1, [n], meta["iseed"])
+    rj = ImageStage.triangulate(res["pred_joints_uv"], intr, extr, [n]).cpu()
+    drj = (rj - torch.from_numpy(z["ref_joints"])).norm(dim=-1)
+    print(f"ref_joints golden: max {drj.max().item() * 1e3:.4f} mm")
+    assert drj.max().item() <= 1e-3                                       # 1 px at 0.6 m and f = 900 is 0.67 mm
+
+
+@pytest.mark.parametrize("views", [[2], [1, 3, 8], [10, 2]])
+def test_triangulate_dlt_matches_oracle(views):
+    """Jacobi-SVD DLT kernel vs the oracle's torch.linalg.svd on projections of known joints (+ pixel noise)."""
+    from poem_v2_b200.hrnet import ImageStage
+    g = torch.Generator().manual_seed(sum(views))
+    B = len(views)
+    intr, extr = synth.make_cameras(B, views, 3)
+    joints = torch.tensor([0.0, 0.0, 0.6]) + 0.05 * torch.randn(B, 21, 3, generator=g)
+    T = torch.linalg.inv(extr)
+    uv, start = [], 0
+    for b, v in enumerate(views):
+        for i in range(start, start + v):
+            pc = joints[b] @ T[i, :3, :3].T + T[i, :3, 3]
+            px = pc @ intr[i].T
+            uv.append(px[:, :2] / px[:, 2:3])
+        start += v
+    uv = torch.stack(uv) + 0.5 * torch.randn(sum(views), 21, 2, generator=g)
+    want = orc.triangulate_dlt(uv, intr, extr, views)
+    got = ImageStage.triangulate(uv.cuda(), intr.cuda(), extr.cuda(), views).cpu()
+    err = (got - want).norm(dim=-1).max().item()
+    print(f"DLT views={views}: max |ours - svd| = {err * 1e3:.5f} mm; |svd - truth| = {(want - joints).norm(dim=-1).max().item() * 1e3:.3f} mm")
+    assert err <= 2e-5          # fp32 SVD in the oracle vs fp64 Jacobi here: 0.02 mm
+
+
+@pytest.mark.parametrize("N", [2])
+def test_heatmap_stage_matches_oracle(N):
+    from poem_v2_b200.hrnet import ImageStage
+    sd = synth.make_image_stage_state_dict(1)
+    sd["uv_out.conv.weight"] *= 0.2            # unsaturated heatmaps
+    img = synth.make_images(N, 256, 4)
+    with torch.no_grad():
+        _, maps = orc.image_features(sd, img)
+        want_uv, want_h = orc.uv_decode_heatmap(sd, maps)
+    m = ImageStage()
+    m.load_state_dict(sd, strict=True)
+    res = m(img.cuda(), return_uv=True, return_heatmap=True)
+    dh = (res["uv_hmap"].cpu() - want_h).abs()
+    duv = (res["pred_joints_uv"].cpu() - want_uv).abs()
+    print(f"heatmap N={N}: max |dh| {dh.max().item():.4f} mean {dh.mean().item():.5f}; uv max {duv.max().item():.4f} px")
+    assert dh.mean().item() <= 1e-2 and dh.max().item() <= 0.15
+    assert duv.max().item() <= 0.5
 
 
 def test_images_to_mesh_pipeline():
