@@ -355,3 +355,27 @@ def triangulate_dlt(uv_px, cam_intr, cam_extr, view_counts):
         out.append(VT[:, -1, :3] / (VT[:, -1, 3:] + 1e-7))
         start += n
     return torch.stack(out)
+
+
+def model_forward(sd, dims, batch, template, bps, anchor_xyz, anchor_idx):
+    """`PtEmbedMultiviewStereoV2._forward_impl(mode="test")` (lib/models/POEM.py:251-333) on full-model keys:
+    backbone -> feat_decode -> heatmap_stage -> per-sample DLT (or the given joints when every sample is single-view)
+    -> head.  Returns the reference's prediction dict (evaluation keys)."""
+    img = batch["image"].reshape(-1, *batch["image"].shape[-3:])
+    views = [int(v) for v in batch["cam_view_num"]]
+    H, W = img.shape[-2:]
+    mlvl_feat, feats = image_features(sd, img)
+    uv, _ = uv_decode_heatmap(sd, feats, W, H)
+    intr, extr = batch["target_cam_intr"].reshape(-1, 3, 3), batch["target_cam_extr"].reshape(-1, 4, 4)
+    if img.shape[0] == len(views):
+        ref_joints = batch["master_joints_3d"].reshape(-1, 21, 3)
+    else:
+        ref_joints = triangulate_dlt(uv, intr, extr, views)
+    metas = {"inp_img_shape": (H, W), "cam_intr": intr, "cam_extr": extr, "master_id": batch["master_id"],
+             "cam_view_num": views}
+    head_sd = {k[len("ptEmb_head."):]: v for k, v in sd.items() if k.startswith("ptEmb_head.")}
+    coords = head_forward(head_sd, dims, mlvl_feat, metas, ref_joints, template, bps, anchor_xyz, anchor_idx)
+    pj, pv = coords[-1, :, :21], coords[-1, :, 21:]
+    c = pj[:, dims.center_idx].unsqueeze(1)
+    return {"all_coords_preds": coords, "pred_joints_3d": pj, "pred_verts_3d": pv, "pred_joints_3d_rel": pj - c,
+            "pred_verts_3d_rel": pv - c, "pred_joints_uv": uv, "pred_ref_joints_3d": ref_joints}

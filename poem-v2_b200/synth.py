@@ -248,3 +248,26 @@ def make_stage4_inputs(n_images: int, base_res: int = 64, seed: int = 1):
     g = torch.Generator().manual_seed(seed)
     return [torch.relu(torch.randn(n_images, c, base_res >> b, base_res >> b, generator=g))
             for b, c in enumerate((40, 80, 160, 320))]
+
+
+def make_model_state_dict(dims: HeadDims, seed: int = 0):
+    """Full-model checkpoint keys (reference `PtEmbedMultiviewStereoV2.state_dict()` minus dead weights): image half +
+    `ptEmb_head.*`.  `feat_in` is scaled so that `mlvl_feat` has unit scale, the range the synthetic head weights are
+    made for; `uv_out` is scaled so that the heatmaps are not saturated."""
+    sd = make_image_stage_state_dict(seed)
+    sd["feat_in.conv.weight"] = sd["feat_in.conv.weight"] * 0.1
+    sd["feat_in.conv.bias"] = sd["feat_in.conv.bias"] * 0.1
+    sd["uv_out.conv.weight"] = sd["uv_out.conv.weight"] * 0.2
+    sd.update({"ptEmb_head." + k: v for k, v in make_state_dict(dims, seed).items()})
+    return sd
+
+
+def make_batch(B: int, V, seed: int = 1):
+    """A reference-style evaluation batch (POEM.py:251-315): images, cameras, view counts, master ids (+ the GT joints the
+    reference falls back to when every sample is single-view)."""
+    views = _view_list(B, V)
+    intr, extr = make_cameras(B, V, seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    return {"image": make_images(sum(views), 256, seed), "cam_view_num": np.array(views), "target_cam_intr": intr,
+            "target_cam_extr": extr, "master_id": [0] * B,
+            "master_joints_3d": torch.tensor([0.0, 0.0, 0.6]) + 0.03 * torch.randn(B, 21, 3, generator=g)}

@@ -190,6 +190,30 @@ def test_backbone_keeps_reference_state_dict_keys():
         m(torch.zeros(1, 3, 256, 256))
 
 
+def test_model_keeps_reference_checkpoint_keys():
+    """The inference model exposes the reference's flat checkpoint key space (POEM.py:100-194): `img_backbone.*`,
+    `feat_delayer.*`, `feat_in.*`, `uv_delayer.*`, `uv_out.*`, `ptEmb_head.*`; dead keys are dropped on load."""
+    from poem_v2_b200.model import PtEmbedMultiviewStereoV2
+    dims = release_dims("small")
+    m = PtEmbedMultiviewStereoV2(dims, template_mesh=synth.standin_template())
+    sd = synth.make_model_state_dict(dims, 0)
+    extra = dict(sd)
+    extra["uv_in.conv.weight"] = torch.zeros(80, 21, 1, 1)               # only feeds the unused uv_feat
+    extra["mano_layer.th_betas"] = torch.zeros(1, 10)
+    extra["img_backbone.classifier.bias"] = torch.zeros(1000)
+    extra["ptEmb_head.center_shift_layer.0.weight"] = torch.zeros(799, 799)
+    m.load_state_dict({"module." + k: v for k, v in extra.items()}, strict=True)   # DDP prefix as in net_utils.py
+    own = m.state_dict()
+    assert set(own) == set(sd)
+    assert own["uv_delayer.0.conv.weight"].shape == (160, 480, 3, 3)
+    assert own["feat_delayer.2.conv.weight"].shape == (320, 160, 3, 3) and own["feat_in.conv.weight"].shape == (160, 320, 1, 1)
+    assert torch.equal(own["ptEmb_head.input_proj.weight"], sd["ptEmb_head.input_proj.weight"])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({**sd, "bogus.weight": torch.zeros(1)}, strict=True)
+    with pytest.raises(NotImplementedError):
+        m(synth.make_batch(1, [2], 1), mode="train")
+
+
 def test_shard_bounds_cover_and_balance():
     for views, world in [([8] * 32, 8), ([8] * 32, 2), ([1, 8, 2, 2, 7, 3], 2), ([4, 4, 4], 4), ([2] * 5, 4)]:
         b = shard.shard_bounds(views, world)

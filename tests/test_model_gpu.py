@@ -1,0 +1,49 @@
+"""Whole inference model (reference `PtEmbedMultiviewStereoV2._forward_impl(mode="test")`, lib/models/POEM.py:251-333):
+images -> backbone -> feat_decode / heatmap -> DLT -> decoder head, against the fp32 oracle composition."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import poem_oracle as orc  # noqa: E402
+from poem_v2_b200 import synth  # noqa: E402
+from poem_v2_b200.config import release_dims  # noqa: E402
+from poem_v2_b200.model import PtEmbedMultiviewStereoV2  # noqa: E402
+
+
+def _to_cuda(batch):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("views", [[3], [2, 4], [1, 1]])
+def test_model_matches_oracle(views):
+    dims = release_dims("small")
+    sd = synth.make_model_state_dict(dims, 0)
+    batch = synth.make_batch(len(views), views, 2)
+    bps, a_xyz, a_idx = synth.load_assets()
+    with torch.no_grad():
+        want = orc.model_forward(sd, dims, batch, synth.standin_template(), bps, a_xyz, a_idx)
+    model = PtEmbedMultiviewStereoV2(dims, template_mesh=synth.standin_template())
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    got = model(_to_cuda(batch), mode="test")
+    assert set(want) <= set(got)
+    duv = (got["pred_joints_uv"].cpu() - want["pred_joints_uv"]).abs().max().item()
+    drj = (got["pred_ref_joints_3d"].cpu() - want["pred_ref_joints_3d"]).norm(dim=-1).max().item() * 1e3
+    err = (got["all_coords_preds"].cpu() - want["all_coords_preds"]).norm(dim=-1)
+    print(f"model views={views}: uv max {duv:.3f} px, ref joints max {drj:.3f} mm, mesh mean {err.mean().item() * 1e3:.3f} mm "
+          f"max {err.max().item() * 1e3:.2f} mm")
+    assert duv <= 0.5 and drj <= 0.5
+    assert torch.isfinite(got["all_coords_preds"]).all() and err.mean().item() * 1e3 <= 1.0
+    for k in ("pred_joints_3d", "pred_verts_3d", "pred_joints_3d_rel", "pred_verts_3d_rel"):
+        assert got[k].shape == want[k].shape
+    assert torch.equal(got["pred_joints_3d"], got["all_coords_preds"][-1, :, :21])
+
+
+def test_model_errors():
+    dims = release_dims("small")
+    model = PtEmbedMultiviewStereoV2(dims, template_mesh=synth.standin_template())
+    with pytest.raises(NotImplementedError):
+        model(synth.make_batch(1, [2], 1), mode="train")
+    with pytest.raises(Exception, match="CUDA"):
+        model(synth.make_batch(1, [2], 1), mode="test")        # CPU tensors: no CPU implementation
