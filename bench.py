@@ -157,6 +157,53 @@ def torch_cuda_reference_pass(size, V, B, steps, warmup, dev, tf32):
     return B / ms * 1e3, ms
 
 
+def images_to_mesh_pass(size, V, B, dev, cpu_views, steps=10, warmup=3):
+    """SURVEY §8d metric (ii): samples/s of the whole evaluation forward (`PtEmbedMultiviewStereoV2._forward_impl`,
+    POEM.py:251-333) from images resident in HBM (two image sets alternated, each >> L2), and the oracle port of the
+    same forward on the host cores for ONE sample (bounded: the fp32 backbone costs ~30 GFLOP per image)."""
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    from poem_v2_b200.model import PtEmbedMultiviewStereoV2
+    dims = release_dims(size)
+    sd = synth.make_model_state_dict(dims, 0)
+    model = PtEmbedMultiviewStereoV2(dims, template_mesh=synth.standin_template())
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    batches = []
+    for s_ in range(2):
+        b = synth.make_batch(B, V, s_ + 1)
+        batches.append({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()})
+    for i in range(warmup):
+        model(batches[i & 1], mode="test")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = model(batches[i & 1], mode="test")["all_coords_preds"]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    res = {"value": B / ms * 1e3, "unit": "samples/s", "images_per_s": B * V / ms * 1e3, "ms_per_step": ms,
+           "workload": f"POEM-{size}: {B} samples x {V} views of 3x256x256 -> mesh (backbone + feat_decode + heatmap + "
+                       f"DLT + decoder)", "finite": bool(torch.isfinite(out).all())}
+    del model, batches
+    torch.cuda.empty_cache()
+    if cpu_views:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import poem_oracle as orc
+        torch.set_num_threads(os.cpu_count() or 1)
+        b1 = synth.make_batch(1, cpu_views, 1)
+        bps, a_xyz, a_idx = synth.load_assets()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            orc.model_forward(sd, dims, b1, synth.standin_template(), bps, a_xyz, a_idx)
+            sec = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 1.0 / sec, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"oracle port (fp32 torch CPU) of the same forward on 1 sample x {cpu_views} views, "
+                                         f"1 pass, {sec:.2f} s"}
+    return res
+
+
 def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
@@ -169,6 +216,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-cuda-baseline", action="store_true",
                     help="also time the reference's eager PyTorch ops (oracle port) on this GPU")
+    ap.add_argument("--images-to-mesh", action="store_true",
+                    help="also report SURVEY §8d metric (ii): the whole evaluation forward from images (backbone, "
+                         "feat_decode, heatmap stage, DLT, decoder), with its own CPU baseline")
     args = ap.parse_args()
     size, V, B = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -369,13 +419,21 @@ def main():
             sps, ms = torch_cuda_reference_pass(size, V, B, 3, 1, dev, tf32)
             torch_cuda["tf32" if tf32 else "fp32"] = {"samples_per_s": sps, "ms_per_step": ms}
         torch_cuda["note"] = "oracle port of the reference's eager ops on the same B200, same batch; reported context"
+    images = None
+    if args.images_to_mesh and n_gpus == 1:
+        try:
+            head._ws = None
+            torch.cuda.empty_cache()
+            images = images_to_mesh_pass(size, V, B, dev, cpu_views=V if not args.no_cpu_baseline else 0)
+        except Exception as e:  # noqa: BLE001
+            images = {"error": repr(e)[:300]}
     line = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "path_roofline": path,
-            "cpu_baseline": cpu, "torch_cuda_eager": torch_cuda,
+            "cpu_baseline": cpu, "torch_cuda_eager": torch_cuda, "images_to_mesh": images,
             "kernel_breakdown_ms_per_step": {k: [round(v["ms"] / prof_steps, 4), v["n"] // prof_steps] for k, v in by_kernel}}
     emit(line)
     if world > 1:
