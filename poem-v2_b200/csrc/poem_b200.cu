@@ -906,7 +906,17 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
     if (rb > 0x7fffffffLL) return fail(POEM_E_BADDIM, "too many merge rows");
   }
   if (img != NV) return fail(POEM_E_BADDIM, "sum(view_counts)=%d != n_images=%d", img, NV);
-  CUDA_TRY(cudaMemcpyAsync(dev, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (B <= VIEW_PARAM_MAX) {
+    // the view counts travel as kernel parameters and the tables are rebuilt on the device: no host-to-device copy, so
+    // the whole forward can be captured into a CUDA graph (a memcpy node would keep a pointer to this stack frame)
+    ViewCountsParam vp;
+    for (int b = 0; b < B; ++b) vp.n[b] = host_views[b];
+    prof_begin(st);
+    view_tables_kernel<<<1, 256, 0, st>>>(vp, B, NV, P, dev);
+    LAUNCH_CHECK("view_tables_kernel");
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(dev, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   vt->img_sample = dev;
   vt->img_view = dev + NV;
   vt->img_posrow = dev + 2 * NV;

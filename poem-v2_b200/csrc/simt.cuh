@@ -592,4 +592,25 @@ __global__ void broadcast_queries_kernel(const float* __restrict__ table, float*
   out_bf16[gid] = __float2bfloat16(v);
 }
 
+// Per-image / per-sample index tables from the per-sample view counts (passed by value):
+//   dev = [img_sample (NV) | img_view (NV) | img_posrow (NV) | sample_rowbase (B) | sample_views (B)]
+constexpr int VIEW_PARAM_MAX = 256;
+struct ViewCountsParam {
+  int n[VIEW_PARAM_MAX];
+};
+__global__ void view_tables_kernel(ViewCountsParam vc, int B, int NV, int P, int* __restrict__ dev) {
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int first = 0;
+    for (int i = 0; i < b; ++i) first += vc.n[i];
+    const int n = vc.n[b];
+    dev[3 * NV + b] = first * P;
+    dev[3 * NV + B + b] = n;
+    for (int v = 0; v < n; ++v) {
+      dev[first + v] = b;
+      dev[NV + first + v] = v;
+      dev[2 * NV + first + v] = n * (n - 1) / 2 + v;
+    }
+  }
+}
+
 }  // namespace poem

@@ -148,7 +148,8 @@ class POEM_Generalized_Head(_NativeDecoder):
         assert len(views) == B and int(views.sum()) == mlvl_feat.shape[0]
         assert mlvl_feat.shape[1] == d.in_channels and tuple(mlvl_feat.shape[-2:]) == (d.feat_hw, d.feat_hw)
         inp_w, inp_h = img_metas["inp_img_shape"]   # the reference unpacks (H,W) as (w,h) (ptEmb_head.py:831)
-        img_metas["inp_res"] = torch.tensor([inp_w, inp_h], dtype=torch.float32, device=dev)
+        if not torch.cuda.is_current_stream_capturing():   # mirrors the reference's mutation; a host->device copy
+            img_metas["inp_res"] = torch.tensor([inp_w, inp_h], dtype=torch.float32, device=dev)
         feat = mlvl_feat.contiguous().float()
         intr = img_metas["cam_intr"].to(dev, torch.float32).contiguous()
         extr = img_metas["cam_extr"].to(dev, torch.float32).contiguous()

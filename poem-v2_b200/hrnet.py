@@ -387,6 +387,9 @@ def image_stage_param_shapes(channels=CHANNELS, out_channels=FEAT_OUT):
     return s
 
 
+_COUNTS_CACHE = {}
+
+
 class ImageStage(nn.Module):
     """`extract_img_feat` + `feat_decode` + `heatmap_stage` of the reference model (POEM.py:189-229, 255-268): images
     (BN,3,256,256) -> `mlvl_feat` (BN,160,16,16), the tensor `POEM_Generalized_Head.forward` takes, and the 2-D joint
@@ -460,8 +463,11 @@ class ImageStage(nn.Module):
         if not uv_px.is_cuda:
             raise nat.PoemError("triangulate inputs must be CUDA tensors: there is no CPU implementation")
         dev = uv_px.device
-        counts = torch.as_tensor([int(v) for v in cam_view_num], dtype=torch.int32, device=dev)
-        n = int(counts.sum().item())
+        key = (tuple(int(v) for v in cam_view_num), str(dev))
+        counts = _COUNTS_CACHE.get(key)
+        if counts is None:          # cached so that a captured forward (poem_v2_b200.graph) performs no host->device copy
+            counts = _COUNTS_CACHE[key] = torch.tensor(key[0], dtype=torch.int32, device=dev)
+        n = sum(key[0])
         uv = uv_px.reshape(n, -1, 2).contiguous().float()
         k = cam_intr.reshape(n, 3, 3).to(dev).contiguous().float()
         e = cam_extr.reshape(n, 4, 4).to(dev).contiguous().float()

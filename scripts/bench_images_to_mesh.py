@@ -56,6 +56,17 @@ step(0)
 torch.cuda.synchronize()
 prof = nat.profile_summary()
 lib.poem_profile_enable(0)
+from poem_v2_b200.graph import graph_model  # noqa: E402
+g = graph_model(model, batches[0])
+for i in range(3):
+    g(batches[i & 1])
+torch.cuda.synchronize()
+e0.record()
+for i in range(K):
+    g(batches[i & 1])
+e1.record()
+torch.cuda.synchronize()
+ms_graph = e0.elapsed_time(e1) / K
 ms_img = sorted(t_img)[len(t_img) // 2]
 gflop_img = sum(backbone_flops_per_image().values()) / 1e9
 groups = {}
@@ -66,7 +77,8 @@ for k, v in prof.items():
     g[1] += v["n"]
 print(json.dumps({
     "workload": f"images -> mesh, POEM-{size}, {B} samples x {V} views (3x256x256), heatmap + DLT reference joints",
-    "ms_per_step": ms, "samples_per_s": B / ms * 1e3, "images_per_s": B * V / ms * 1e3,
+    "ms_per_step": ms, "ms_per_step_cuda_graph": ms_graph, "samples_per_s": B / ms * 1e3,
+    "samples_per_s_cuda_graph": B / ms_graph * 1e3, "images_per_s": B * V / ms * 1e3,
     "image_stage_ms": ms_img, "decoder_and_dlt_ms": ms - ms_img, "image_stage_images_per_s": B * V / ms_img * 1e3,
     "backbone_nominal_tflops": gflop_img * B * V / ms_img, "finite": bool(torch.isfinite(out).all()),
     "kernel_groups_ms": {k: [round(v[0], 3), v[1]] for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])}}))

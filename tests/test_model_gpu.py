@@ -47,3 +47,24 @@ def test_model_errors():
         model(synth.make_batch(1, [2], 1), mode="train")
     with pytest.raises(Exception, match="CUDA"):
         model(synth.make_batch(1, [2], 1), mode="test")        # CPU tensors: no CPU implementation
+
+
+@pytest.mark.parametrize("views", [[2], [1, 3]])
+def test_graph_replay_matches_eager(views):
+    """The captured forward (poem_v2_b200.graph) replays bit-identically to the eager call, also on new inputs."""
+    from poem_v2_b200.graph import graph_model
+    dims = release_dims("small")
+    model = PtEmbedMultiviewStereoV2(dims, template_mesh=synth.standin_template())
+    model.load_state_dict(synth.make_model_state_dict(dims, 0), strict=True)
+    model = model.cuda().eval()
+    b1, b2 = _to_cuda(synth.make_batch(len(views), views, 2)), _to_cuda(synth.make_batch(len(views), views, 5))
+    eager1 = {k: v.clone() for k, v in model(b1, mode="test").items()}
+    eager2 = {k: v.clone() for k, v in model(b2, mode="test").items()}
+    g = graph_model(model, b1)
+    r1 = {k: v.clone() for k, v in g(b1).items()}
+    r2 = {k: v.clone() for k, v in g(b2).items()}
+    for k in ("all_coords_preds", "pred_joints_uv", "pred_ref_joints_3d"):
+        assert torch.equal(r1[k], eager1[k]) and torch.equal(r2[k], eager2[k]), k
+    assert not torch.equal(r1["all_coords_preds"], r2["all_coords_preds"])
+    with pytest.raises(ValueError):
+        g(_to_cuda(synth.make_batch(len(views), [v + 1 for v in views], 2)))     # other view counts: must re-capture
