@@ -60,6 +60,11 @@ class GraphedForward:
         self.graph.replay()
         return self.outputs
 
+    def replay(self):
+        """Replay on the inputs already held by the captured buffers."""
+        self.graph.replay()
+        return self.outputs
+
 
 def graph_model(model, batch, mode="test"):
     """`PtEmbedMultiviewStereoV2` forward as a graph: `g = graph_model(model, batch); preds = g(batch)`."""
@@ -72,6 +77,9 @@ def graph_head(head, mlvl_feat, img_metas, reference_joints):
     metas = {k: v for k, v in img_metas.items() if k != "inp_res"}
     g = GraphedForward(lambda **kw: head(**kw), {"mlvl_feat": mlvl_feat, "img_metas": metas,
                                                    "reference_joints": reference_joints})
-    return lambda mlvl_feat, img_metas, reference_joints, **_: g(
-        mlvl_feat=mlvl_feat, img_metas={k: v for k, v in img_metas.items() if k != "inp_res"},
-        reference_joints=reference_joints)
+
+    def call(mlvl_feat, img_metas, reference_joints, **_):
+        return g(mlvl_feat=mlvl_feat, img_metas={k: v for k, v in img_metas.items() if k != "inp_res"},
+                 reference_joints=reference_joints)
+    call.replay = g.replay
+    return call
