@@ -103,18 +103,6 @@ struct HaloMaps {
 };
 __host__ __device__ constexpr int halo_map_index(int nch) { return nch == 64 ? 0 : (nch == 32 ? 1 : 2); }
 
-// 256-bit global accesses (sm_100: LDG.256 / STG.256), one full 32-byte sector per lane
-__device__ __forceinline__ void ldg_nc_256(const void* p, uint32_t* r) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg_256(void* p, const uint32_t* r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-
 template <int CP, int CR>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {

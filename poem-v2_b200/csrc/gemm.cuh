@@ -72,19 +72,18 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, interleaved over the 32-column chunks
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
-constexpr int GEMM_STAGE_LD = 36;   // floats per staging row (32 + 4 pad: conflict-free 128-bit accesses)
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 3 : 4;   // 227 KB smem: 3 x 48 KB stages + 36 KB epilogue staging
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kWBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_STAGE_LD * 4;   // per-epilogue-warp transpose tile
   static constexpr int kBiasBytes = 2 * BN * 4;
-  static constexpr int kTailBytes = kStagingBytes + kBiasBytes + 256 /*barriers*/;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;   // streaming mode
+  static constexpr int kTailBytes = kBiasBytes + 256 /*barriers*/;
   static constexpr int kSmemMax = 232448;                                 // 227 KB per CTA
+  static constexpr int kStagesRoom = (kSmemMax - 1024 - kTailBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRoom > 6 ? 6 : kStagesRoom;       // BN = 256: 4 x 48 KB
+  static constexpr int kSmemBytes = kStages * kStageBytes + kTailBytes;   // streaming mode
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -106,16 +105,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  // smem: [resident W slab (stationary mode)] [ring] [epilogue staging] [bias] [barriers]
+  // smem: [resident W slab (stationary mode)] [ring] [bias] [barriers]
   const bool wst = pipe.w_stationary != 0;
   const int n_stages = pipe.n_stages;
   const int ring_stage_bytes = wst ? Cfg::kABytes : Cfg::kStageBytes;
   uint8_t* s_wres = smem;
   uint8_t* s_ring = smem + (wst ? k_blocks * Cfg::kWBytes : 0);
   uint8_t* s_tail = s_ring + n_stages * ring_stage_bytes;
-  float* s_stage = reinterpret_cast<float*>(s_tail);
-  float* s_bias = reinterpret_cast<float*>(s_tail + Cfg::kStagingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + Cfg::kStagingBytes + Cfg::kBiasBytes);
+  float* s_bias = reinterpret_cast<float*>(s_tail);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + Cfg::kBiasBytes);
   uint64_t* full_bar = bars;                               // [GEMM_MAX_STAGES]
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;            // [GEMM_MAX_STAGES]
   uint64_t* tmem_full = bars + 2 * GEMM_MAX_STAGES;        // [2]
@@ -229,16 +227,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
-    // TMEM hands each lane one accumulator ROW (32 columns at a time).  Row-major outputs are re-distributed
-    // through a per-warp smem staging tile so that 4 lanes cover 32 consecutive columns of one row (full 32-byte
-    // sectors, bias/residual as vector loads); transposed outputs keep the TMEM layout (lanes = consecutive rows =
-    // consecutive addresses).
+    // TMEM hands each lane one accumulator ROW (32 columns at a time) and the epilogue keeps that layout: a lane's 32
+    // columns are 128 (fp32) / 64 (bf16) contiguous bytes of its output row, moved with 256-bit accesses (one full
+    // 32-byte sector per lane and instruction), bias broadcast from smem.  No shared-memory transpose: with SS-mode
+    // MMAs the operand reads already take most of the SM's shared-memory bandwidth, and a staged epilogue was what
+    // bounded the skinny-K GEMMs of this path.
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
     const int ew = warp - 2;       // 0..7
     const int chunk_par = ew >> 2; // this warp handles 32-column chunks with (chunk index & 1) == chunk_par
-    float* stage = s_stage + ew * (32 * GEMM_STAGE_LD);
-    const int sr = lane >> 2;          // sub-row 0..7 in the row-major phase
-    const int cg = (lane & 3) * 8;     // first of this lane's 8 columns inside a 32-column chunk
     int acc = 0;
     uint32_t acc_phase = 0;
     // residual row of output row m: fp32 or bf16 pointer (nullptr when absent / out of range) and the RES_MERGE scale
@@ -268,39 +264,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int j = threadIdx.x - 64; j < BN; j += 32 * GEMM_EPI_WARPS)
         sb[j] = (ep.bias != nullptr && n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after_sync();
 
-      // row-major phase: this lane handles rows rr[i] = quarter*32 + 8*i + sr, columns cg..cg+7 of every chunk
-      const float* resf[4];
-      const __nv_bfloat16* resb[4];
-      float rscale[4];
-      int mrow[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        mrow[i] = m0 + quarter * 32 + 8 * i + sr;
-        res_row(mrow[i], resf[i], resb[i], rscale[i]);
-      }
+      const int mt_row = m0 + quarter * 32 + lane;   // this lane's output row
+      const float* resf;
+      const __nv_bfloat16* resb;
+      float rscale;
+      res_row(mt_row, resf, resb, rscale);
       // the residual rows of this CTA's NEXT tile start travelling HBM -> L2 now (the epilogue of a skinny-K GEMM is
       // otherwise bound by the latency of these loads, not by bandwidth)
       if (kRes && it + it_step < it_end) {
         const int itn = it + it_step;
         const int m0n = (wst ? itn : itn / tiles_n) * GEMM_BM;
         const int n0n = (wst ? my_n_tile : itn % tiles_n) * BN;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float* pf;
-          const __nv_bfloat16* pb;
-          float sc;
-          res_row(m0n + quarter * 32 + 8 * i + sr, pf, pb, sc);
-          for (int c0 = chunk_par * 32; c0 < BN && n0n + c0 < N && n0n + c0 < ep.trans_from; c0 += 64) {
-            if (pf != nullptr) prefetch_l2(pf + n0n + c0 + cg);
-            if (pb != nullptr && (lane & 1) == 0) prefetch_l2(pb + n0n + c0 + cg);
-          }
+        const float* pf;
+        const __nv_bfloat16* pb;
+        float sc;
+        res_row(m0n + quarter * 32 + lane, pf, pb, sc);
+        for (int c0 = chunk_par * 32; c0 < BN && n0n + c0 < N && n0n + c0 < ep.trans_from; c0 += 64) {
+          if (pf != nullptr) prefetch_l2(pf + n0n + c0);
+          if (pb != nullptr) prefetch_l2(pb + n0n + c0);
         }
       }
-      // transposed phase: this lane handles row quarter*32 + lane
-      const int mt_row = m0 + quarter * 32 + lane;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+
       size_t t_base = 0;
       if (ep.trans_from < N && mt_row < M) {
         const int g = mt_row / ep.t_rows;
@@ -311,121 +298,91 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
         const int n = n0 + c0;
         if (n >= N) break;   // warp-uniform
-        // this chunk's residual values: all loads in flight before the accumulator chunk is read and staged
-        float4 pf0[4], pf1[4];
-        uint4 pbv[4];
+        // this chunk's residual values: in flight before the accumulator chunk is read
+        uint32_t rr[32];
         if (kRes && n < ep.trans_from) {
+          if (resf != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (resf[i] != nullptr) {
-              pf0[i] = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg));
-              pf1[i] = __ldg(reinterpret_cast<const float4*>(resf[i] + n + cg + 4));
-            } else if (resb[i] != nullptr) {
-              pbv[i] = __ldg(reinterpret_cast<const uint4*>(resb[i] + n + cg));
-            }
+            for (int j = 0; j < 4; ++j) ldg_nc_256(resf + n + 8 * j, &rr[8 * j]);
+          } else if (resb != nullptr) {
+            ldg_nc_256(resb + n, &rr[0]);
+            ldg_nc_256(resb + n + 16, &rr[8]);
           }
         }
         uint32_t r[32];
+        __syncwarp();   // lanes past the last row skip the stores below: reconverge before the aligned TMEM load
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
         tmem_ld_wait();
+        if (mt_row < M) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+        }
+        if (ep.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (ep.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
         if (n >= ep.trans_from) {
-          // ---------------- transposed store (lane = row) ----------------
-          if (mt_row < M) {
-            float v[32];
+          // ---------------- transposed store (consecutive lanes = consecutive addresses) ----------------
+          if (kRes && (ep.res_mode == RES_F32 || ep.res_mode == RES_POSADD)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
-              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
-              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+              const float4 t = __ldg(reinterpret_cast<const float4*>(resf + n) + j);
+              v[4 * j + 0] += t.x;
+              v[4 * j + 1] += t.y;
+              v[4 * j + 2] += t.z;
+              v[4 * j + 3] += t.w;
             }
-            if (ep.act == ACT_RELU) {
+          }
+          const int tc = n - ep.trans_from;
+          if (ep.out_t_bf16 != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (ep.act == ACT_GELU) {
+            for (int j = 0; j < 32; ++j) ep.out_t_bf16[t_base + (size_t)(tc + j) * ep.t_rows] = __float2bfloat16(v[j]);
+          }
+          if (ep.out_t_f32 != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-            }
-            if (kRes && (ep.res_mode == RES_F32 || ep.res_mode == RES_POSADD)) {
-              const float* rp = (ep.res_mode == RES_F32)
-                                    ? ep.res_f32 + (size_t)mt_row * ep.res_ld
-                                    : ep.res_f32 + ((size_t)ep.row_tab[mt_row >> 8] * 256 + (mt_row & 255)) * ep.res_ld;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(rp + n) + j);
-                v[4 * j + 0] += t.x;
-                v[4 * j + 1] += t.y;
-                v[4 * j + 2] += t.z;
-                v[4 * j + 3] += t.w;
-              }
-            }
-            const int tc = n - ep.trans_from;
-            if (ep.out_t_bf16 != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ep.out_t_bf16[t_base + (size_t)(tc + j) * ep.t_rows] = __float2bfloat16(v[j]);
-            }
-            if (ep.out_t_f32 != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) ep.out_t_f32[t_base + (size_t)(tc + j) * ep.t_rows] = v[j];
-            }
+            for (int j = 0; j < 32; ++j) ep.out_t_f32[t_base + (size_t)(tc + j) * ep.t_rows] = v[j];
           }
         } else {
-          // ---------------- row-major store through the staging tile ----------------
-          __syncwarp();   // previous chunk's reads of the staging tile are done
+        // ---------------- row-major store ----------------
+        if (kRes && resf != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stage + lane * GEMM_STAGE_LD + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + cg);
-          const float4 b1 = *reinterpret_cast<const float4*>(sb + c0 + cg + 4);
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
+        } else if (kRes && resb != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (mrow[i] >= M) continue;
-            const float* sp = stage + (8 * i + sr) * GEMM_STAGE_LD + cg;
-            const float4 x0 = *reinterpret_cast<const float4*>(sp);
-            const float4 x1 = *reinterpret_cast<const float4*>(sp + 4);
-            float v[8] = {x0.x + b0.x, x0.y + b0.y, x0.z + b0.z, x0.w + b0.w,
-                          x1.x + b1.x, x1.y + b1.y, x1.z + b1.z, x1.w + b1.w};
-            if (ep.act == ACT_RELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (ep.act == ACT_GELU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-            }
-            if (kRes && resf[i] != nullptr) {
-              const float4 t0 = pf0[i], t1 = pf1[i];
-              v[0] += t0.x, v[1] += t0.y, v[2] += t0.z, v[3] += t0.w;
-              v[4] += t1.x, v[5] += t1.y, v[6] += t1.z, v[7] += t1.w;
-            } else if (kRes && resb[i] != nullptr) {
-              const __nv_bfloat162* t2 = reinterpret_cast<const __nv_bfloat162*>(&pbv[i]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(t2[j]);
-                v[2 * j] = v[2 * j] * rscale[i] + f.x;
-                v[2 * j + 1] = v[2 * j + 1] * rscale[i] + f.y;
-              }
-            }
-            if (ep.act_after_res == ACT_RELU) {   // BasicBlock: relu(bn2(conv2(.)) + identity)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (ep.out_f32 != nullptr) {
-              float4* o = reinterpret_cast<float4*>(ep.out_f32 + (size_t)mrow[i] * ep.ld_f32 + n + cg);
-              o[0] = make_float4(v[0], v[1], v[2], v[3]);
-              o[1] = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (ep.out_bf16 != nullptr) {
-              uint4 pk;
-              pk.x = pack_bf16x2(v[0], v[1]);
-              pk.y = pack_bf16x2(v[2], v[3]);
-              pk.z = pack_bf16x2(v[4], v[5]);
-              pk.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(ep.out_bf16 + (size_t)mrow[i] * ep.ld_bf16 + n + cg) = pk;
-            }
+          for (int j = 0; j < 16; ++j) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[j]));
+            v[2 * j] = v[2 * j] * rscale + f.x;
+            v[2 * j + 1] = v[2 * j + 1] * rscale + f.y;
           }
         }
+        if (ep.act_after_res == ACT_RELU) {   // BasicBlock: relu(bn2(conv2(.)) + identity)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.out_f32 != nullptr) {
+          float* o = ep.out_f32 + (size_t)mt_row * ep.ld_f32 + n;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) stg_256(o + 8 * j, reinterpret_cast<const uint32_t*>(&v[8 * j]));
+        }
+        if (ep.out_bf16 != nullptr) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          __nv_bfloat16* o = ep.out_bf16 + (size_t)mt_row * ep.ld_bf16 + n;
+          stg_256(o, &pk[0]);
+          stg_256(o + 16, &pk[8]);
+        }
+        }   // row-major
+        }   // mt_row < M
       }
       // all TMEM reads of this warp are complete (wait::ld above) -> hand the accumulator back
       tc_fence_before_sync();

@@ -204,10 +204,17 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
     CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
     configured = true;
   }
+  // the epilogue moves 32-column chunks of a row with 256-bit accesses
+  auto misaligned = [](const void* p, int ld, int elem) {
+    return p != nullptr && ((reinterpret_cast<uintptr_t>(p) & 31) || ((size_t)ld * elem) % 32);
+  };
+  if (N % 32 || misaligned(ep.out_f32, ep.ld_f32, 4) || misaligned(ep.out_bf16, ep.ld_bf16, 2) ||
+      (ep.res_mode != RES_NONE && (misaligned(ep.res_f32, ep.res_ld, 4) || misaligned(ep.res_bf16, ep.res_ld, 2))))
+    return fail(POEM_E_ALIGN, "gemm: N %% 32 == 0 and 32-byte aligned output / residual rows required (N=%d)", N);
   const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + BN - 1) / BN;
   const int tiles = tiles_m * tiles_n;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  // W-stationary when the [BN x K] slab plus >= 3 A stages fit next to the epilogue staging, and every CTA gets
+  // W-stationary when the [BN x K] slab plus >= 3 A stages fit, and every CTA gets
   // at least two M tiles (otherwise the slab load is not amortised)
   GemmPipe pipe;
   const long long w_slab = (long long)k_blocks * Cfg::kWBytes;

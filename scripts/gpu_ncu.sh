@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu --set full captures of the hot kernels (one launch each), reports into gpurun_out/
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph"
 cap() { # name regex skip
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/$1 $CMD > gpurun_out/ncu_$1.log 2>&1
   echo "== ncu $1 exit $? =="; ls -la gpurun_out/$1.ncu-rep 2>/dev/null
