@@ -249,12 +249,13 @@ int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, const float*
 
 /* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
  * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
- * c_live > 0 promises that only the first c_live input AND output channels are non-zero (the rest of the padded
- * tensors, weights and bias is zero padding), which lets the 3x3 stride-1 kernel skip the padding; 0 = no promise.
+ * c_live_in / c_live_out > 0 promise that only the first c_live_in input / c_live_out output channels are non-zero
+ * (the rest of the padded tensors, weights and bias is zero padding), which lets the 3x3 stride-1 kernel skip the
+ * padding; 0 = no promise.
  * Replaces nn.Conv2d + nn.BatchNorm2d(eval) (+ReLU, + identity) of hrnet.py:38-67,177-207. */
 int poem_conv_nhwc(const poem_bf16* in, int n_images, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
-                   int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out, int c_live,
-                   void* stream);
+                   int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out, int c_live_in,
+                   int c_live_out, void* stream);
 
 /* ---- stage-level entry points (unit-testable building blocks; same kernels the whole path uses) ---- */
 

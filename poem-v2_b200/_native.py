@@ -198,7 +198,7 @@ def load():
     lib.poem_triangulate_dlt.restype = i
     lib.poem_triangulate_dlt.argtypes = [vp, vp, vp, vp, i, i, vp, vp]
     lib.poem_conv_nhwc.restype = i
-    lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, i, vp]
+    lib.poem_conv_nhwc.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, i, i, vp]
     lib.poem_debug_conv_mode.restype = None
     lib.poem_debug_conv_mode.argtypes = [i]
     lib.poem_layernorm.restype = i

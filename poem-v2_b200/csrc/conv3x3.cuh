@@ -42,11 +42,12 @@ struct HaloBlocks {
   __host__ __device__ static constexpr int nch(int b) { return b < n64 ? 64 : (b == n64 ? (tail == 16 ? 16 : 32) : 16); }
 };
 
-template <int CP, int CR>
+// CIP / CIR: padded / live input channels; CP / CR: padded / live output channels (live counts rounded up to 16)
+template <int CIP, int CIR, int CP, int CR>
 struct HaloCfg {
-  static_assert(CP == 64 || CP == 128 || CP == 192, "padded channel count");
-  static_assert(CR <= CP && CR > CP - 64, "CR is the real channel count rounded up to 16");
-  using Blk = HaloBlocks<CR>;
+  static_assert(CP % 64 == 0 && CP <= 256 && CIP % 64 == 0, "padded channel counts");
+  static_assert(CR <= CP && CR > CP - 64 && CIR <= CIP && CIR > CIP - 64, "live counts are rounded up to 16");
+  using Blk = HaloBlocks<CIR>;
   static constexpr int kNB = Blk::n;                   // K blocks per tap
   static constexpr int kPitch = 18;                    // patch pixels per smem row
   static constexpr int kRows = 18;
@@ -64,7 +65,7 @@ struct HaloCfg {
   // weights: all nine taps stay resident in smem when they leave room for two tile slots (CR <= 80); otherwise the
   // [CR x nch] tiles stream through a ring that takes whatever one tile slot leaves (an MMA consumes a tile in
   // ~0.3 us, an L2 round trip is ~1 us: a shallow ring starves the tensor core)
-  static constexpr int kTapBytes = CR * CR * 2;        // the kNB tiles of one tap, packed
+  static constexpr int kTapBytes = CR * CIR * 2;       // the kNB tiles of one tap, packed
   static constexpr bool kBResident = (kBudget - 9 * kTapBytes) >= 2 * kSlotBytes;
   static constexpr int kBStride = CR * 128;            // room for a [CR out-channel rows][64 k] tile
   static constexpr int kBStagesRoom = (kBudget - kSlotBytes) / kBStride;
@@ -103,10 +104,10 @@ struct HaloMaps {
 };
 __host__ __device__ constexpr int halo_map_index(int nch) { return nch == 64 ? 0 : (nch == 32 ? 1 : 2); }
 
-template <int CP, int CR>
+template <int CIP, int CIR, int CP, int CR>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
-  using Cfg = HaloCfg<CP, CR>;
+  using Cfg = HaloCfg<CIP, CIR, CP, CR>;
   using Blk = typename Cfg::Blk;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -168,7 +169,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
         for (int tap = 0; tap < 9; ++tap)
           for (int b = 0; b < Cfg::kNB; ++b)
             tma_load_2d(s_b + tap * Cfg::kTapBytes + CR * Blk::ch0(b) * 2, &maps.w[halo_map_index(Blk::nch(b))], &b_full[0],
-                        tap * CP + Blk::ch0(b), 0);
+                        tap * CIP + Blk::ch0(b), 0);
       }
       const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
       const int steps = my_tiles * Cfg::kNB;   // (tile, K block) pairs, in order
@@ -197,7 +198,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
           if (mbar_test_wait(&b_empty[bs], ((b_next / Cfg::kBStages) & 1) ^ 1)) {
             const int b = (b_next / 9) % Cfg::kNB, tap = b_next % 9;
             mbar_expect_tx(&b_full[bs], (uint32_t)(CR * Blk::nch(b) * 2));
-            tma_load_2d(s_b + bs * Cfg::kBStride, &maps.w[halo_map_index(Blk::nch(b))], &b_full[bs], tap * CP + Blk::ch0(b), 0);
+            tma_load_2d(s_b + bs * Cfg::kBStride, &maps.w[halo_map_index(Blk::nch(b))], &b_full[bs], tap * CIP + Blk::ch0(b), 0);
             ++b_next;
             progress = true;
           }

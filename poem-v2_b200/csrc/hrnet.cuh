@@ -348,37 +348,45 @@ struct FuseSumArgs {
   int shift[4];
   int n_in;
 };
-__global__ void fuse_sum_relu_kernel(FuseSumArgs a, __nv_bfloat16* __restrict__ out, int H, int W, int Cp, size_t total8) {
+// 16 channels (one 256-bit access per term) per thread
+__global__ void __launch_bounds__(256)
+fuse_sum_relu_kernel(FuseSumArgs a, __nv_bfloat16* __restrict__ out, int H, int W, int Cp, size_t total16) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total8) return;
-  const int c8 = Cp / 8;
-  const int c = (int)(gid % c8) * 8;
-  size_t pix = gid / c8;
+  if (gid >= total16) return;
+  const int c16 = Cp / 16;
+  const int c = (int)(gid % c16) * 16;
+  size_t pix = gid / c16;
   const int x = (int)(pix % W);
   pix /= W;
   const int y = (int)(pix % H);
   const size_t n = pix / H;
-  float acc[8];
+  uint32_t v[4][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int j = 0; j < a.n_in; ++j) {
-    const int s = a.shift[j];
-    const int hj = H >> s, wj = W >> s;
-    const uint4 v = *reinterpret_cast<const uint4*>(a.in[j] + ((n * hj + (y >> s)) * wj + (x >> s)) * Cp + c);
-    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(v2[i]);
-      acc[2 * i] += f.x;
-      acc[2 * i + 1] += f.y;
+  for (int j = 0; j < 4; ++j) {   // all loads in flight before the first use
+    if (j < a.n_in) {
+      const int s = a.shift[j];
+      const int hj = H >> s, wj = W >> s;
+      ldg_nc_256(a.in[j] + ((n * hj + (y >> s)) * wj + (x >> s)) * Cp + c, v[j]);
     }
   }
-  uint4 o;
-  o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-  o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-  o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-  o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-  *reinterpret_cast<uint4*>(out + gid * 8) = o;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < a.n_in) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[j][i]));
+        acc[2 * i] += f.x;
+        acc[2 * i + 1] += f.y;
+      }
+    }
+  }
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
+  stg_256(out + gid * 16, o);
 }
 
 }  // namespace poem

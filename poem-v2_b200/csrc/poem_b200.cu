@@ -299,14 +299,15 @@ static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W
 static int g_conv_mode = 0;   // 0: halo-reuse kernel, live channels only; 1: halo-reuse, all padded channels; 2: generic path
 extern "C" void poem_debug_conv_mode(int mode) { g_conv_mode = mode; }
 
-template <int CP, int CR>
+template <int CIP, int CIR, int CP, int CR>
 static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, const PoemLinear& wt, const HaloArgs& a,
                                   cudaStream_t st) {
-  using Cfg = HaloCfg<CP, CR>;
+  using Cfg = HaloCfg<CIP, CIR, CP, CR>;
   using Blk = typename Cfg::Blk;
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<CP, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(conv3x3_halo_kernel<CIP, CIR, CP, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
     attr_done = true;
   }
   HaloMaps maps;
@@ -314,8 +315,8 @@ static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, const P
   for (int b = 0; b < Cfg::kNB; ++b) {
     const int nch = Blk::nch(b), mi = halo_map_index(nch);
     if (have[mi]) continue;
-    POEM_TRY(make_tmap_nhwc(&maps.x[mi], in, N, R, R, CP, Cfg::kPitch, Cfg::kRows, 1, 1, nch));
-    POEM_TRY(make_tmap_bf16(&maps.w[mi], wt.w, (uint64_t)CR, (uint64_t)9 * CP, (uint64_t)9 * CP, (uint32_t)nch, (uint32_t)CR));
+    POEM_TRY(make_tmap_nhwc(&maps.x[mi], in, N, R, R, CIP, Cfg::kPitch, Cfg::kRows, 1, 1, nch));
+    POEM_TRY(make_tmap_bf16(&maps.w[mi], wt.w, (uint64_t)CR, (uint64_t)9 * CIP, (uint64_t)9 * CIP, (uint32_t)nch, (uint32_t)CR));
     have[mi] = true;
   }
   int first = have[0] ? 0 : (have[1] ? 1 : 2);
@@ -324,42 +325,68 @@ static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, const P
   const int tiles = N * (R / 16) * (R / 16);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_begin(st);
-  conv3x3_halo_kernel<CP, CR><<<grid, HALO_THREADS, Cfg::kSmemBytes, st>>>(maps, a);
+  conv3x3_halo_kernel<CIP, CIR, CP, CR><<<grid, HALO_THREADS, Cfg::kSmemBytes, st>>>(maps, a);
   LAUNCH_CHECK("conv3x3_halo_kernel");
   return POEM_OK;
 }
 
-// c_real: number of live channels (the rest of Cp is zero padding); 0 = treat all Cp channels as live
-static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cp, int c_real, const PoemLinear& wt, bool relu,
-                               const __nv_bfloat16* res, __nv_bfloat16* out, cudaStream_t st) {
+// Shapes the halo-reuse kernel is instantiated for: (padded in, live in, padded out, live out), live counts rounded to 16
+static bool halo_supported(int cip, int cir, int cop, int cor) {
+  const long long key = ((long long)cip << 48) | ((long long)cir << 32) | ((long long)cop << 16) | cor;
+  auto k = [](long long a, long long b, long long c, long long d) { return (a << 48) | (b << 32) | (c << 16) | d; };
+  return key == k(64, 48, 64, 48) || key == k(64, 64, 64, 64) || key == k(128, 80, 128, 80) ||
+         key == k(128, 128, 128, 128) || key == k(192, 160, 192, 160) || key == k(192, 192, 192, 192) ||
+         key == k(256, 256, 64, 48) || key == k(256, 240, 128, 80) || key == k(128, 128, 64, 48);
+}
+
+// ci_live / co_live: live channels of the input / output (the rest of the padded count is zero); 0 = all live
+static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cip, int ci_live, int Cop, int co_live,
+                               const PoemLinear& wt, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
+                               cudaStream_t st, bool* handled) {
+  const bool live = (g_conv_mode != 1);
+  int cir = (ci_live > 0 && live) ? (ci_live + 15) / 16 * 16 : Cip;
+  int cor = (co_live > 0 && live) ? (co_live + 15) / 16 * 16 : Cop;
+  if (!halo_supported(Cip, cir, Cop, cor)) cir = Cip, cor = Cop;
+  *handled = halo_supported(Cip, cir, Cop, cor);
+  if (!*handled) return POEM_OK;
   HaloArgs a;
   a.n_images = N, a.R = R, a.bias = wt.b, a.relu = relu ? 1 : 0, a.res = res, a.out = out;
-  int cr = (c_real > 0 && g_conv_mode != 1) ? (c_real + 15) / 16 * 16 : Cp;
-  if (!((Cp == 64 && cr == 48) || (Cp == 128 && cr == 80) || (Cp == 192 && cr == 160))) cr = Cp;
-  char tag[48];
-  snprintf(tag, sizeof(tag), "conv3x3halo_c%d_of_%d_r%d", cr, Cp, R);
+  char tag[64];
+  snprintf(tag, sizeof(tag), "conv3x3halo_c%d_of_%d_to_c%d_of_%d_r%d", cir, Cip, cor, Cop, R);
   TagScope ts(tag);
-  switch (Cp * 1000 + cr) {
-    case 64048: return launch_conv3x3_halo_cp<64, 48>(in, N, R, wt, a, st);
-    case 64064: return launch_conv3x3_halo_cp<64, 64>(in, N, R, wt, a, st);
-    case 128080: return launch_conv3x3_halo_cp<128, 80>(in, N, R, wt, a, st);
-    case 128128: return launch_conv3x3_halo_cp<128, 128>(in, N, R, wt, a, st);
-    case 192160: return launch_conv3x3_halo_cp<192, 160>(in, N, R, wt, a, st);
-    case 192192: return launch_conv3x3_halo_cp<192, 192>(in, N, R, wt, a, st);
-  }
-  return fail(POEM_E_BADDIM, "conv3x3 halo: C=%d (%d live)", Cp, cr);
+  const long long key = ((long long)Cip << 48) | ((long long)cir << 32) | ((long long)Cop << 16) | cor;
+#define HALO_CASE(a_, b_, c_, d_)                                                             \
+  if (key == (((long long)(a_) << 48) | ((long long)(b_) << 32) | ((long long)(c_) << 16) | (d_))) \
+    return launch_conv3x3_halo_cp<a_, b_, c_, d_>(in, N, R, wt, a, st);
+  HALO_CASE(64, 48, 64, 48)
+  HALO_CASE(64, 64, 64, 64)
+  HALO_CASE(128, 80, 128, 80)
+  HALO_CASE(128, 128, 128, 128)
+  HALO_CASE(192, 160, 192, 160)
+  HALO_CASE(192, 192, 192, 192)
+  HALO_CASE(256, 256, 64, 48)
+  HALO_CASE(256, 240, 128, 80)
+  HALO_CASE(128, 128, 64, 48)
+#undef HALO_CASE
+  return fail(POEM_E_BADDIM, "conv3x3 halo: no instantiation");
 }
 
 // out[N, Hout, Wout, Cout_p] = act(conv(in[N, Hin, Win, Cin_p], w[Cout_p, k*k*Cin_p]) + b) (+ res)
 static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
                        int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
-                       cudaStream_t st, int c_real = 0, bool relu_before_res = false, float* out_f32 = nullptr) {
+                       cudaStream_t st, int c_real = 0, bool relu_before_res = false, float* out_f32 = nullptr,
+                       int c_real_in = -1) {
   if (!wt.w || !wt.b) return fail(POEM_E_NULL, "conv: weight pointer missing");
   if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
     return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
-  if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Cin_p == Cout_p && Hin == Win && Hin % 16 == 0 &&
-      (Cin_p == 64 || Cin_p == 128 || Cin_p == 192) && !relu_before_res && out != nullptr && out_f32 == nullptr)
-    return launch_conv3x3_halo(in, N, Hin, Cin_p, c_real, wt, relu, res, out, st);
+  // c_real: live output channels; c_real_in: live input channels (defaults to c_real, the C -> C BasicBlock case)
+  if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Hin == Win && Hin % 16 == 0 && !relu_before_res &&
+      out != nullptr && out_f32 == nullptr) {
+    bool handled = false;
+    POEM_TRY(launch_conv3x3_halo(in, N, Hin, Cin_p, c_real_in >= 0 ? c_real_in : c_real, Cout_p, c_real, wt, relu, res, out,
+                                 st, &handled));
+    if (handled) return POEM_OK;
+  }
   const int Hout = Hin / stride, Wout = Win / stride;
   if (Wout < 1 || 128 % Wout || Wout > 128 || Cin_p % 64 || Cout_p % 32)
     return fail(POEM_E_BADDIM, "conv: unsupported shape %dx%d C %d -> %d", Hin, Win, Cin_p, Cout_p);
@@ -407,15 +434,16 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
 
 extern "C" int poem_conv_nhwc(const poem_bf16* in, int N, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
                               int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out,
-                              int c_live, void* stream) {
+                              int c_live_in, int c_live_out, void* stream) {
   if (!in || !out) return fail(POEM_E_NULL, "conv: null pointer");
-  if (c_live < 0 || c_live > Cin_p || c_live > Cout_p) return fail(POEM_E_BADDIM, "conv: c_live=%d", c_live);
+  if (c_live_in < 0 || c_live_in > Cin_p || c_live_out < 0 || c_live_out > Cout_p)
+    return fail(POEM_E_BADDIM, "conv: c_live=%d/%d", c_live_in, c_live_out);
   PoemLinear wt;
   wt.w = w;
   wt.b = b;
   return launch_conv(reinterpret_cast<const __nv_bfloat16*>(in), N, H, W, Cin_p, wt, Cout_p, ksize, stride, relu != 0,
                      reinterpret_cast<const __nv_bfloat16*>(res), reinterpret_cast<__nv_bfloat16*>(out),
-                     (cudaStream_t)stream, c_live);
+                     (cudaStream_t)stream, c_live_out, false, nullptr, c_live_in);
 }
 
 static inline int pad64(int c) { return (c + 63) / 64 * 64; }
@@ -489,9 +517,9 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
         ++fa.n_in;
       }
       __nv_bfloat16* dst = p.x[i][(cur[i] + 1) % 3];
-      const size_t total8 = (size_t)N * R[i] * R[i] * Cp[i] / 8;
+      const size_t total16 = (size_t)N * R[i] * R[i] * Cp[i] / 16;
       prof_begin(st);
-      fuse_sum_relu_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cp[i], total8);
+      fuse_sum_relu_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cp[i], total16);
       LAUNCH_CHECK("fuse_sum_relu_kernel");
     }
     for (int i = 0; i < nb; ++i) cur[i] = (cur[i] + 1) % 3;
@@ -602,7 +630,7 @@ static int hrnet_run(const PoemHRNet* w, int N, int img_res, const float* images
     cur[i] = 0;
   }
   // transition1 (hrnet.py:318-342): 3x3 256->40 ; 3x3 s2 256->80
-  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st));
+  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st, ch[0], false, nullptr, 256));
   POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[1], Cp[1], 3, 2, true, nullptr, p.hr.x[1][0], st));
   POEM_TRY(run_hr_modules(w->stage2, 1, 2, N, R, Cp, ch, p.hr, cur, st));
   // transition2: new branch from the lowest-resolution output, 3x3 s2 80->160
@@ -736,7 +764,8 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
     upsample2x_concat_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
         h, p.net.hr.x[lo][cur[lo]], p.cat[i], R[lo] / 2, R[lo] / 2, h_cp, h_c, Cp[lo], ch[lo], cat_cp, total8);
     LAUNCH_CHECK("upsample2x_concat_kernel");
-    POEM_TRY(launch_conv(p.cat[i], N, R[lo], R[lo], cat_cp, uv->delayer[i], Cp[lo], 3, 1, true, nullptr, p.u[i], st));
+    POEM_TRY(launch_conv(p.cat[i], N, R[lo], R[lo], cat_cp, uv->delayer[i], Cp[lo], 3, 1, true, nullptr, p.u[i], st, ch[lo], false,
+                         nullptr, h_c + ch[lo]));
     h = p.u[i];
     h_cp = Cp[lo];
     h_c = ch[lo];

@@ -36,7 +36,7 @@ def run(N, R, c, cp, relu, res, mode, timing=False):
 
     def call():
         nat.check(lib.poem_conv_nhwc(xd.data_ptr(), N, R, R, cp, wd.data_ptr(), bd.data_ptr(), cp, 3, 1, int(relu),
-                                     rd.data_ptr() if res else None, out.data_ptr(), c, st))
+                                     rd.data_ptr() if res else None, out.data_ptr(), c, c, st))
     call()
     torch.cuda.synchronize()
     ms = None

@@ -25,7 +25,7 @@ for (R, c, cp) in [(64, 40, 64), (32, 80, 128), (16, 160, 192)]:
 
     def call():
         nat.check(lib.poem_conv_nhwc(x.data_ptr(), N, R, R, cp, w.data_ptr(), b.data_ptr(), cp, 3, 1, 1, r.data_ptr(),
-                                     out.data_ptr(), c, st))
+                                     out.data_ptr(), c, c, st))
     for _ in range(3):
         call()
     torch.cuda.synchronize()

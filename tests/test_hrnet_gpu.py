@@ -31,6 +31,9 @@ def _p(t):
     (1, 16, 33, 33, 3, 1, True, False),      # 33 live channels -> 48 (32 + 16) of 64
     (2, 32, 150, 150, 3, 1, True, True),     # 150 -> 160 (64 + 64 + 32) of 192
     (2, 16, 128, 128, 3, 1, True, True),     # no padding at all
+    (2, 32, 256, 40, 3, 1, True, False),     # transition1: 256 -> 40 (Cin != Cout on the halo kernel)
+    (2, 32, 240, 80, 3, 1, True, False),     # uv_decode: cat(160, 80) -> 80
+    (3, 16, 120, 40, 3, 1, True, False),     # uv_decode: cat(80, 40) -> 40
 ])
 def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res, live):
     lib = nat.load()
@@ -54,12 +57,11 @@ def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res, live):
     d = [t.bfloat16().contiguous().cuda() if t is not None else None for t in (xp, wp.reshape(cout_p, -1), rp)]
     bd = bp.cuda()
     out = torch.full((N, Ro, Ro, cout_p), float("nan"), device="cuda", dtype=torch.bfloat16)
-    if live and cin != cout:
-        pytest.skip("c_live describes a C -> C convolution")
-    # live=True promises that channels >= cin are zero padding: the 3x3 stride-1 kernel then multiplies only the live
-    # channels (mixed 128/64/32-byte swizzle K blocks) and writes the padding as zeros
+    # live=True promises that channels >= cin / cout are zero padding: the 3x3 stride-1 kernel then multiplies only
+    # the live channels (mixed 128/64/32-byte swizzle K blocks) and writes the padding as zeros
     nat.check(lib.poem_conv_nhwc(_p(d[0]), N, R, R, cin_p, _p(d[1]), _p(bd), cout_p, k, stride, int(relu), _p(d[2]),
-                                 _p(out), cin if live else 0, torch.cuda.current_stream().cuda_stream))
+                                 _p(out), cin if live else 0, cout if live else 0,
+                                 torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = F.conv2d(x, w, b, stride=stride, padding=k // 2)
     if res:
