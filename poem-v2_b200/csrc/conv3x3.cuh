@@ -88,6 +88,7 @@ struct HaloArgs {
   int relu;                         // ReLU after bias (+ residual)
   const __nv_bfloat16* res;         // NHWC identity shortcut or nullptr
   __nv_bfloat16* out;               // NHWC
+  int cout_s;                       // channels per pixel of out / res in memory (multiple of 16, >= CR, <= CP)
 };
 
 // K-major descriptor for rows of `row_bytes` (128 / 64 / 32 -> SWIZZLE_128B / 64B / 32B) with an explicit stride
@@ -280,7 +281,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
         const int yn = (remn / tiles_x) * 16 + quarter * 4 + (lane >> 3), xn = (remn % tiles_x) * 16 + (lane & 7);
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
-          const __nv_bfloat16* rp = a.res + (((size_t)nn * a.R + yn) * a.R + xn + sub * 8) * CP;
+          const __nv_bfloat16* rp = a.res + (((size_t)nn * a.R + yn) * a.R + xn + sub * 8) * a.cout_s;
 #pragma unroll
           for (int j = 0; j < kChunks; ++j)
             if ((2 * j + par) * 32 < CR) prefetch_l2(rp + (2 * j + par) * 32);
@@ -288,7 +289,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
       }
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
-        const size_t off = (((size_t)n * a.R + (y0 + quarter * 4 + (lane >> 3))) * a.R + (x0 + sub * 8 + (lane & 7))) * CP;
+        const size_t off = (((size_t)n * a.R + (y0 + quarter * 4 + (lane >> 3))) * a.R + (x0 + sub * 8 + (lane & 7))) * a.cout_s;
         // this warp's chunks are 2 j + par; chunk c covers channels [32 c, 32 c + 32): real below CR, zero padding above
         uint32_t rres[kChunks][16];
         if (a.res != nullptr) {   // every shortcut load of this sub-tile is in flight before the accumulator is awaited
@@ -298,7 +299,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
             if (c0 < CR) {
               const __nv_bfloat16* rp = a.res + off + c0;
               ldg_nc_256(rp, &rres[j][0]);
-              ldg_nc_256(rp + 16, &rres[j][8]);
+              if (c0 + 16 < a.cout_s) ldg_nc_256(rp + 16, &rres[j][8]);
             }
           }
         }
@@ -309,13 +310,14 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
           const int c0 = (2 * j + par) * 32;
+          if (c0 >= a.cout_s) continue;   // these channels do not exist in memory (compact storage)
           __nv_bfloat16* op = a.out + off + c0;
           uint32_t pk[16];
           if (c0 >= CR) {   // pure padding chunk (warp-uniform)
 #pragma unroll
             for (int q = 0; q < 16; ++q) pk[q] = 0u;
             stg_256(op, &pk[0]);
-            stg_256(op + 16, &pk[8]);
+            if (c0 + 16 < a.cout_s) stg_256(op + 16, &pk[8]);
             continue;
           }
           uint32_t r[32];
@@ -331,7 +333,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
             float v0 = __uint_as_float(r[4 * q]) + b4.x, v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
             float v2 = __uint_as_float(r[4 * q + 2]) + b4.z, v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
-            if (a.res != nullptr) {
+            if (a.res != nullptr && c0 + 4 * q < a.cout_s) {
               const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j][2 * q]));
               const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j][2 * q + 1]));
               v0 += f0.x, v1 += f0.y, v2 += f1.x, v3 += f1.y;
@@ -341,7 +343,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
             pk[2 * q + 1] = pack_bf16x2(v2, v3);
           }
           stg_256(op, &pk[0]);
-          stg_256(op + 16, &pk[8]);
+          if (c0 + 16 < a.cout_s) stg_256(op + 16, &pk[8]);
         }
       }
       tc_fence_before_sync();

@@ -59,6 +59,7 @@ struct GemmEpilogue {
   int ld_f32;
   __nv_bfloat16* out_bf16; // row-major [M, ld_bf16] or nullptr
   int ld_bf16;
+  int n_store;             // row-major outputs / residuals only exist for columns < n_store (multiple of 16; = N normally)
   // columns >= trans_from go to a per-group transposed buffer:
   //   out_t[(m / t_rows) * t_group_stride + (n - trans_from) * t_rows + (m % t_rows)]
   int trans_from;          // = N when unused
@@ -300,13 +301,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (n >= N) break;   // warp-uniform
         // this chunk's residual values: in flight before the accumulator chunk is read
         uint32_t rr[32];
+        const int valid = ep.n_store - n;   // row-major columns of this chunk that exist in memory: >= 32, 16 or <= 0
+        if (n < ep.trans_from && valid <= 0) continue;   // warp-uniform: nothing of this chunk is stored
         if (kRes && n < ep.trans_from) {
           if (resf != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ldg_nc_256(resf + n + 8 * j, &rr[8 * j]);
+            for (int j = 0; j < 4; ++j)
+              if (valid >= 8 * (j + 1)) ldg_nc_256(resf + n + 8 * j, &rr[8 * j]);
           } else if (resb != nullptr) {
             ldg_nc_256(resb + n, &rr[0]);
-            ldg_nc_256(resb + n + 16, &rr[8]);
+            if (valid >= 32) ldg_nc_256(resb + n + 16, &rr[8]);
           }
         }
         uint32_t r[32];
@@ -371,7 +375,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (ep.out_f32 != nullptr) {
           float* o = ep.out_f32 + (size_t)mt_row * ep.ld_f32 + n;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) stg_256(o + 8 * j, reinterpret_cast<const uint32_t*>(&v[8 * j]));
+          for (int j = 0; j < 4; ++j)
+            if (valid >= 8 * (j + 1)) stg_256(o + 8 * j, reinterpret_cast<const uint32_t*>(&v[8 * j]));
         }
         if (ep.out_bf16 != nullptr) {
           uint32_t pk[16];
@@ -379,7 +384,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           __nv_bfloat16* o = ep.out_bf16 + (size_t)mt_row * ep.ld_bf16 + n;
           stg_256(o, &pk[0]);
-          stg_256(o + 16, &pk[8]);
+          if (valid >= 32) stg_256(o + 16, &pk[8]);
         }
         }   // row-major
         }   // mt_row < M

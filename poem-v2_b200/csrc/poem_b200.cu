@@ -246,6 +246,7 @@ static GemmEpilogue epi_default(int N) {
   memset(&e, 0, sizeof(e));
   e.trans_from = N;
   e.t_rows = 1;
+  e.n_store = N;
   return e;
 }
 
@@ -281,7 +282,7 @@ static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W
                           int stride, int box_c = 64) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled unavailable");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (Cp % 64)) return fail(POEM_E_ALIGN, "conv: bad activation tensor");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (Cp % 8)) return fail(POEM_E_ALIGN, "conv: bad activation tensor");
   cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstride[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
@@ -300,7 +301,7 @@ static int g_conv_mode = 0;   // 0: halo-reuse kernel, live channels only; 1: ha
 extern "C" void poem_debug_conv_mode(int mode) { g_conv_mode = mode; }
 
 template <int CIP, int CIR, int CP, int CR>
-static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, const PoemLinear& wt, const HaloArgs& a,
+static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, int cin_s, const PoemLinear& wt, const HaloArgs& a,
                                   cudaStream_t st) {
   using Cfg = HaloCfg<CIP, CIR, CP, CR>;
   using Blk = typename Cfg::Blk;
@@ -315,7 +316,7 @@ static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, const P
   for (int b = 0; b < Cfg::kNB; ++b) {
     const int nch = Blk::nch(b), mi = halo_map_index(nch);
     if (have[mi]) continue;
-    POEM_TRY(make_tmap_nhwc(&maps.x[mi], in, N, R, R, CIP, Cfg::kPitch, Cfg::kRows, 1, 1, nch));
+    POEM_TRY(make_tmap_nhwc(&maps.x[mi], in, N, R, R, cin_s, Cfg::kPitch, Cfg::kRows, 1, 1, nch));
     POEM_TRY(make_tmap_bf16(&maps.w[mi], wt.w, (uint64_t)CR, (uint64_t)9 * CIP, (uint64_t)9 * CIP, (uint32_t)nch, (uint32_t)CR));
     have[mi] = true;
   }
@@ -342,22 +343,23 @@ static bool halo_supported(int cip, int cir, int cop, int cor) {
 // ci_live / co_live: live channels of the input / output (the rest of the padded count is zero); 0 = all live
 static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cip, int ci_live, int Cop, int co_live,
                                const PoemLinear& wt, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
-                               cudaStream_t st, bool* handled) {
+                               cudaStream_t st, bool* handled, int cin_s, int cout_s) {
   const bool live = (g_conv_mode != 1);
   int cir = (ci_live > 0 && live) ? (ci_live + 15) / 16 * 16 : Cip;
   int cor = (co_live > 0 && live) ? (co_live + 15) / 16 * 16 : Cop;
   if (!halo_supported(Cip, cir, Cop, cor)) cir = Cip, cor = Cop;
-  *handled = halo_supported(Cip, cir, Cop, cor);
+  // compact storage keeps only the live channels (rounded to 16) of every pixel: the kernel must not touch more
+  *handled = halo_supported(Cip, cir, Cop, cor) && cir <= cin_s && cor <= cout_s;
   if (!*handled) return POEM_OK;
   HaloArgs a;
-  a.n_images = N, a.R = R, a.bias = wt.b, a.relu = relu ? 1 : 0, a.res = res, a.out = out;
+  a.n_images = N, a.R = R, a.bias = wt.b, a.relu = relu ? 1 : 0, a.res = res, a.out = out, a.cout_s = cout_s;
   char tag[64];
   snprintf(tag, sizeof(tag), "conv3x3halo_c%d_of_%d_to_c%d_of_%d_r%d", cir, Cip, cor, Cop, R);
   TagScope ts(tag);
   const long long key = ((long long)Cip << 48) | ((long long)cir << 32) | ((long long)Cop << 16) | cor;
 #define HALO_CASE(a_, b_, c_, d_)                                                             \
   if (key == (((long long)(a_) << 48) | ((long long)(b_) << 32) | ((long long)(c_) << 16) | (d_))) \
-    return launch_conv3x3_halo_cp<a_, b_, c_, d_>(in, N, R, wt, a, st);
+    return launch_conv3x3_halo_cp<a_, b_, c_, d_>(in, N, R, cin_s, wt, a, st);
   HALO_CASE(64, 48, 64, 48)
   HALO_CASE(64, 64, 64, 64)
   HALO_CASE(128, 80, 128, 80)
@@ -375,7 +377,13 @@ static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cip, i
 static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
                        int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
                        cudaStream_t st, int c_real = 0, bool relu_before_res = false, float* out_f32 = nullptr,
-                       int c_real_in = -1) {
+                       int c_real_in = -1, int cin_s = 0, int cout_s = 0) {
+  // cin_s / cout_s: channels per pixel of the tensors in memory (multiples of 16; 0 = the padded counts).  With
+  // compact storage a 64-channel TMA box simply runs past the pixel's channels and the hardware zero-fills the rest.
+  if (cin_s <= 0) cin_s = Cin_p;
+  if (cout_s <= 0) cout_s = Cout_p;
+  if (cin_s % 16 || cout_s % 16 || cin_s > Cin_p || cout_s > Cout_p)
+    return fail(POEM_E_BADDIM, "conv: storage channels %d/%d for padded %d/%d", cin_s, cout_s, Cin_p, Cout_p);
   if (!wt.w || !wt.b) return fail(POEM_E_NULL, "conv: weight pointer missing");
   if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
     return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
@@ -384,7 +392,7 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
       out != nullptr && out_f32 == nullptr) {
     bool handled = false;
     POEM_TRY(launch_conv3x3_halo(in, N, Hin, Cin_p, c_real_in >= 0 ? c_real_in : c_real, Cout_p, c_real, wt, relu, res, out,
-                                 st, &handled));
+                                 st, &handled, cin_s, cout_s));
     if (handled) return POEM_OK;
   }
   const int Hout = Hin / stride, Wout = Win / stride;
@@ -399,7 +407,7 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   const int taps = ksize * ksize, cblocks = Cin_p / 64;
   const int M = N * Hout * Wout, K = taps * Cin_p;
   CUtensorMap ta, tw;
-  POEM_TRY(make_tmap_nhwc(&ta, in, N, Hin, Win, Cin_p, Wout, bh, bn, stride));
+  POEM_TRY(make_tmap_nhwc(&ta, in, N, Hin, Win, cin_s, Wout, bh, bn, stride));
   const int BN = (Cout_p <= 256) ? Cout_p : 160;
   if (!(BN == 64 || BN == 128 || BN == 160 || BN == 192 || BN == 256) || Cout_p % BN)
     return fail(POEM_E_BADDIM, "conv: Cout_p=%d has no tile", Cout_p);
@@ -411,10 +419,11 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   if (res) {
     e.res_mode = RES_BF16;
     e.res_bf16 = res;
-    e.res_ld = Cout_p;
+    e.res_ld = cout_s;
   }
   e.out_bf16 = out;
-  e.ld_bf16 = Cout_p;
+  e.ld_bf16 = cout_s;
+  e.n_store = out_f32 ? Cout_p : cout_s;   // the fp32 output (feat_in) keeps the padded row
   e.out_f32 = out_f32;
   e.ld_f32 = Cout_p;
   ConvOperand cv;
@@ -446,7 +455,8 @@ extern "C" int poem_conv_nhwc(const poem_bf16* in, int N, int H, int W, int Cin_
                      (cudaStream_t)stream, c_live_out, false, nullptr, c_live_in);
 }
 
-static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }   // weight / K-block padding
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }   // channels per pixel kept in memory
 
 struct HrPlan {
   __nv_bfloat16* x[4][3];     // per branch: current / scratch / next
@@ -457,11 +467,13 @@ static size_t hr_plan(int N, int R0, const int* ch, uint8_t* base, HrPlan* p) {
   Bump b{base, 0};
   size_t chain_max = 0;
   for (int i = 0; i < 4; ++i) {
-    const size_t n = (size_t)N * (R0 >> i) * (R0 >> i) * pad64(ch[i]);
+    const size_t n = (size_t)N * (R0 >> i) * (R0 >> i) * pad16(ch[i]);
     for (int k = 0; k < 3; ++k) p->x[i][k] = b.take<__nv_bfloat16>(n);
     for (int j = 0; j < 4; ++j) p->term[i][j] = (j == i) ? nullptr : b.take<__nv_bfloat16>(n);
     if (i >= 1 && i <= 2) {
-      const size_t c = (size_t)N * (R0 >> i) * (R0 >> i) * pad64(ch[0]);   // largest chain intermediate at this res
+      int cmax = 0;   // chain intermediates at this resolution keep the source branch's channel count (j < i)
+      for (int j = 0; j < i; ++j) cmax = ch[j] > cmax ? ch[j] : cmax;
+      const size_t c = (size_t)N * (R0 >> i) * (R0 >> i) * pad16(cmax);
       chain_max = c > chain_max ? c : chain_max;
     }
   }
@@ -476,8 +488,11 @@ extern "C" size_t poem_hrnet_stage4_workspace_bytes(const PoemHRStage4* w, int n
 }
 
 // n_modules HighResolutionModules over the first nb branches (hrnet.py:217-234); cur[b] = live buffer of branch b
-static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N, const int* R, const int* Cp,
+// Cw: channel counts padded to 64 (weight layout, K blocks); Cs: channels per pixel in memory (padded to 16)
+static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N, const int* R, const int* Cw,
                           const int* ch, const HrPlan& p, int* cur, cudaStream_t st) {
+  int Cs[4];
+  for (int i = 0; i < 4; ++i) Cs[i] = pad16(ch[i]);
   for (int m = 0; m < n_modules; ++m) {
     const PoemHRModule& mod = mods[m];
     // ---- branches: 4 BasicBlocks each (hrnet.py:38-67)
@@ -486,8 +501,10 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
         __nv_bfloat16* x = p.x[b][cur[b]];
         __nv_bfloat16* t = p.x[b][(cur[b] + 1) % 3];
         __nv_bfloat16* y = p.x[b][(cur[b] + 2) % 3];
-        POEM_TRY(launch_conv(x, N, R[b], R[b], Cp[b], mod.branch[b][k][0], Cp[b], 3, 1, true, nullptr, t, st, ch[b]));
-        POEM_TRY(launch_conv(t, N, R[b], R[b], Cp[b], mod.branch[b][k][1], Cp[b], 3, 1, true, x, y, st, ch[b]));
+        POEM_TRY(launch_conv(x, N, R[b], R[b], Cw[b], mod.branch[b][k][0], Cw[b], 3, 1, true, nullptr, t, st, ch[b], false, nullptr, -1,
+                             Cs[b], Cs[b]));
+        POEM_TRY(launch_conv(t, N, R[b], R[b], Cw[b], mod.branch[b][k][1], Cw[b], 3, 1, true, x, y, st, ch[b], false, nullptr, -1,
+                             Cs[b], Cs[b]));
         cur[b] = (cur[b] + 2) % 3;
       }
     }
@@ -500,7 +517,8 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
         if (j == i) {
           fa.in[fa.n_in] = xj, fa.shift[fa.n_in] = 0;
         } else if (j > i) {   // 1x1 conv + BN at the low resolution, upsampled by the sum kernel
-          POEM_TRY(launch_conv(xj, N, R[j], R[j], Cp[j], mod.fuse[i][j][0], Cp[i], 1, 1, false, nullptr, p.term[i][j], st));
+          POEM_TRY(launch_conv(xj, N, R[j], R[j], Cw[j], mod.fuse[i][j][0], Cw[i], 1, 1, false, nullptr, p.term[i][j], st, 0, false,
+                               nullptr, -1, Cs[j], Cs[i]));
           fa.in[fa.n_in] = p.term[i][j], fa.shift[fa.n_in] = j - i;
         } else {              // chain of (i - j) stride-2 3x3 convs; all but the last keep C_j channels and ReLU
           const __nv_bfloat16* src = xj;
@@ -508,7 +526,8 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
           for (int k = 0; k < i - j; ++k) {
             const bool last = (k == i - j - 1);
             __nv_bfloat16* dst = last ? p.term[i][j] : p.chain[k & 1];
-            POEM_TRY(launch_conv(src, N, r, r, Cp[j], mod.fuse[i][j][k], last ? Cp[i] : Cp[j], 3, 2, !last, nullptr, dst, st));
+            POEM_TRY(launch_conv(src, N, r, r, Cw[j], mod.fuse[i][j][k], last ? Cw[i] : Cw[j], 3, 2, !last, nullptr, dst, st, 0, false,
+                                 nullptr, -1, Cs[j], last ? Cs[i] : Cs[j]));
             src = dst;
             r >>= 1;
           }
@@ -517,9 +536,9 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
         ++fa.n_in;
       }
       __nv_bfloat16* dst = p.x[i][(cur[i] + 1) % 3];
-      const size_t total16 = (size_t)N * R[i] * R[i] * Cp[i] / 16;
+      const size_t total16 = (size_t)N * R[i] * R[i] * Cs[i] / 16;
       prof_begin(st);
-      fuse_sum_relu_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cp[i], total16);
+      fuse_sum_relu_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cs[i], total16);
       LAUNCH_CHECK("fuse_sum_relu_kernel");
     }
     for (int i = 0; i < nb; ++i) cur[i] = (cur[i] + 1) % 3;
@@ -527,12 +546,13 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
   return POEM_OK;
 }
 
-static int hr_export(const HrPlan& p, const int* cur, const int* ch, const int* Cp, const int* R, int N,
-                     float* const* out, cudaStream_t st) {
+static int hr_export(const HrPlan& p, const int* cur, const int* ch, const int* R, int N, float* const* out,
+                     cudaStream_t st) {
   for (int i = 0; i < 4; ++i) {
-    dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
+    const int cs = pad16(ch[i]);
+    dim3 grid((R[i] * R[i] + 31) / 32, (cs + 31) / 32, N), block(32, 8);
     prof_begin(st);
-    nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, st>>>(p.x[i][cur[i]], out[i], ch[i], Cp[i], R[i] * R[i]);
+    nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, st>>>(p.x[i][cur[i]], out[i], ch[i], cs, R[i] * R[i]);
     LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
   }
   return POEM_OK;
@@ -555,14 +575,15 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
     Cp[i] = pad64(ch[i]);
     R[i] = R0 >> i;
     if (!in[i] || !out[i]) return fail(POEM_E_NULL, "hrnet_stage4: branch %d pointer missing", i);
-    dim3 grid((R[i] * R[i] + 31) / 32, (Cp[i] + 31) / 32, N), block(32, 8);
+    const int cs = pad16(ch[i]);
+    dim3 grid((R[i] * R[i] + 31) / 32, (cs + 31) / 32, N), block(32, 8);
     prof_begin(st);
-    nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], Cp[i], R[i] * R[i]);
+    nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], cs, R[i] * R[i]);
     LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
   }
   int cur[4] = {0, 0, 0, 0};   // index of the buffer holding the branch's current activation
   POEM_TRY(run_hr_modules(w->modules, w->n_modules, 4, N, R, Cp, ch, p, cur, st));
-  return hr_export(p, cur, ch, Cp, R, N, out, st);
+  return hr_export(p, cur, ch, R, N, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,14 +651,18 @@ static int hrnet_run(const PoemHRNet* w, int N, int img_res, const float* images
     cur[i] = 0;
   }
   // transition1 (hrnet.py:318-342): 3x3 256->40 ; 3x3 s2 256->80
-  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st, ch[0], false, nullptr, 256));
-  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[1], Cp[1], 3, 2, true, nullptr, p.hr.x[1][0], st));
+  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[0], Cp[0], 3, 1, true, nullptr, p.hr.x[0][0], st, ch[0], false, nullptr, 256, 256,
+                       pad16(ch[0])));
+  POEM_TRY(launch_conv(x, N, R4, R4, 256, w->trans1[1], Cp[1], 3, 2, true, nullptr, p.hr.x[1][0], st, 0, false, nullptr, -1, 256,
+                       pad16(ch[1])));
   POEM_TRY(run_hr_modules(w->stage2, 1, 2, N, R, Cp, ch, p.hr, cur, st));
   // transition2: new branch from the lowest-resolution output, 3x3 s2 80->160
-  POEM_TRY(launch_conv(p.hr.x[1][cur[1]], N, R[1], R[1], Cp[1], w->trans2, Cp[2], 3, 2, true, nullptr, p.hr.x[2][0], st));
+  POEM_TRY(launch_conv(p.hr.x[1][cur[1]], N, R[1], R[1], Cp[1], w->trans2, Cp[2], 3, 2, true, nullptr, p.hr.x[2][0], st, 0, false,
+                       nullptr, -1, pad16(ch[1]), pad16(ch[2])));
   POEM_TRY(run_hr_modules(w->stage3, 4, 3, N, R, Cp, ch, p.hr, cur, st));
   // transition3: 3x3 s2 160->320
-  POEM_TRY(launch_conv(p.hr.x[2][cur[2]], N, R[2], R[2], Cp[2], w->trans3, Cp[3], 3, 2, true, nullptr, p.hr.x[3][0], st));
+  POEM_TRY(launch_conv(p.hr.x[2][cur[2]], N, R[2], R[2], Cp[2], w->trans3, Cp[3], 3, 2, true, nullptr, p.hr.x[3][0], st, 0, false,
+                       nullptr, -1, pad16(ch[2]), pad16(ch[3])));
   return run_hr_modules(w->stage4, 3, 4, N, R, Cp, ch, p.hr, cur, st);
 }
 
@@ -658,14 +683,13 @@ extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res,
   HrNetPlan p;
   const size_t need = hrnet_plan(N, img_res, w->channels, reinterpret_cast<uint8_t*>(workspace), &p);
   if (need > workspace_bytes) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
-  int Cp[4], R[4], cur[4];
+  int R[4], cur[4];
   for (int i = 0; i < 4; ++i) {
-    Cp[i] = pad64(w->channels[i]);
     R[i] = (img_res / 4) >> i;
     if (!out[i]) return fail(POEM_E_NULL, "hrnet: output %d missing", i);
   }
   POEM_TRY(hrnet_run(w, N, img_res, images, p, cur, st));
-  return hr_export(p.hr, cur, w->channels, Cp, R, N, out, st);
+  return hr_export(p.hr, cur, w->channels, R, N, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,7 +709,7 @@ static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, bool with
   Bump b{base ? base + ((net + 1023) & ~size_t(1023)) : nullptr, 0};
   for (int i = 0; i < 3; ++i) {
     const size_t r = (size_t)(img_res / 8) >> i;
-    p->d[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad64(ch[i + 1]));
+    p->d[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad16(ch[i + 1]));
   }
   const size_t r8 = (size_t)img_res / 32;
   p->f8 = b.take<float>((size_t)N * r8 * r8 * pad64(out_ch));
@@ -693,8 +717,8 @@ static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, bool with
     p->cat[i] = p->u[i] = nullptr;
     if (!with_uv) continue;
     const size_t r = (size_t)(img_res / 16) << i;    // R/16, R/8, R/4
-    p->cat[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad64(ch[3 - i] + ch[2 - i]));
-    p->u[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad64(ch[2 - i]));
+    p->cat[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad16(ch[3 - i] + ch[2 - i]));
+    p->u[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad16(ch[2 - i]));
   }
   return ((net + 1023) & ~size_t(1023)) + b.off;
 }
@@ -729,20 +753,21 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
   if (maps) {
     for (int i = 0; i < 4; ++i)
       if (!maps[i]) return fail(POEM_E_NULL, "image_features: map %d missing", i);
-    POEM_TRY(hr_export(p.net.hr, cur, ch, Cp, R, N, maps, st));
+    POEM_TRY(hr_export(p.net.hr, cur, ch, R, N, maps, st));
   }
   // ---- feat_decode: x = f0 ; x = relu(bn(conv3x3 s2(x))) + f_{i+1}
   const __nv_bfloat16* x = p.net.hr.x[0][cur[0]];
   for (int i = 0; i < 3; ++i) {
     POEM_TRY(launch_conv(x, N, R[i], R[i], Cp[i], fd->delayer[i], Cp[i + 1], 3, 2, true, p.net.hr.x[i + 1][cur[i + 1]],
-                         p.d[i], st, 0, /*relu_before_res=*/true));
+                         p.d[i], st, 0, /*relu_before_res=*/true, nullptr, -1, pad16(ch[i]), pad16(ch[i + 1])));
     x = p.d[i];
   }
   // feat_in is a 1x1 convolution without norm / activation: it commutes with the bilinear upsampling (whose weights
   // sum to one, so the bias passes through), so it runs on the 8x8 map (4x fewer MACs) and the upsampling kernel
   // interpolates its fp32 output straight into the NCHW tensor the head consumes
   const int Co_p = pad64(fd->out_channels);
-  POEM_TRY(launch_conv(x, N, R[3], R[3], Cp[3], fd->feat_in, Co_p, 1, 1, false, nullptr, nullptr, st, 0, false, p.f8));
+  POEM_TRY(launch_conv(x, N, R[3], R[3], Cp[3], fd->feat_in, Co_p, 1, 1, false, nullptr, nullptr, st, 0, false, p.f8, -1,
+                       pad16(ch[3]), Co_p));
   {
     const int Ro = 2 * R[3];
     const size_t total = (size_t)N * fd->out_channels * Ro * Ro;
@@ -755,26 +780,26 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
   // ---- uv_decode + heatmap_stage (POEM.py:205-229): x = f3; x = ConvBlock_i(cat(up2(x), f_{2-i})); max-pool; 1x1 +
   // sigmoid; soft-argmax
   const __nv_bfloat16* h = p.net.hr.x[3][cur[3]];
-  int h_cp = Cp[3], h_c = ch[3];
+  int h_cs = pad16(ch[3]), h_c = ch[3];
   for (int i = 0; i < 3; ++i) {
     const int lo = 2 - i;                      // skip branch, resolution R[lo]
-    const int cat_cp = pad64(h_c + ch[lo]);
-    const size_t total8 = (size_t)N * R[lo] * R[lo] * cat_cp / 8;
+    const int cat_cp = pad64(h_c + ch[lo]), cat_cs = pad16(h_c + ch[lo]);
+    const size_t total8 = (size_t)N * R[lo] * R[lo] * cat_cs / 8;
     prof_begin(st);
     upsample2x_concat_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
-        h, p.net.hr.x[lo][cur[lo]], p.cat[i], R[lo] / 2, R[lo] / 2, h_cp, h_c, Cp[lo], ch[lo], cat_cp, total8);
+        h, p.net.hr.x[lo][cur[lo]], p.cat[i], R[lo] / 2, R[lo] / 2, h_cs, h_c, pad16(ch[lo]), ch[lo], cat_cs, total8);
     LAUNCH_CHECK("upsample2x_concat_kernel");
     POEM_TRY(launch_conv(p.cat[i], N, R[lo], R[lo], cat_cp, uv->delayer[i], Cp[lo], 3, 1, true, nullptr, p.u[i], st, ch[lo], false,
-                         nullptr, h_c + ch[lo]));
+                         nullptr, h_c + ch[lo], cat_cs, pad16(ch[lo])));
     h = p.u[i];
-    h_cp = Cp[lo];
+    h_cs = pad16(ch[lo]);
     h_c = ch[lo];
   }
   {
     const int J = uv->n_joints, Rp = R[0] / 2;
     const size_t smem = (size_t)(J * ch[0] + J + 8 * J * 3) * sizeof(float);
     prof_begin(st);
-    heatmap_uv_kernel<<<N, 256, smem, st>>>(h, uv->out_w, uv->out_b, uv_px, heatmap, Rp, Cp[0], ch[0], J, (float)img_res,
+    heatmap_uv_kernel<<<N, 256, smem, st>>>(h, uv->out_w, uv->out_b, uv_px, heatmap, Rp, pad16(ch[0]), ch[0], J, (float)img_res,
                                            (float)img_res);
     LAUNCH_CHECK("heatmap_uv_kernel");
   }
