@@ -75,7 +75,7 @@ struct HaloCfg {
   static constexpr int kSlots = kSlotsRoom > 4 ? 4 : kSlotsRoom;
   static constexpr int kAStages = kSlots * kNB;
   static_assert(kSlots >= 1 && kAStages <= 12 && (kBResident || kBStages >= 3), "smem plan");
-  static constexpr int kAccPairs = (4 * CP <= 512) ? 2 : 1;
+  static constexpr int kAccPairs = 512 / (2 * CP) >= 4 ? 4 : (512 / (2 * CP) >= 2 ? 2 : 1);   // accumulator stages in TMEM
   static constexpr int kTmemCols = (2 * kAccPairs * CP <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kSlots * kSlotBytes + kBBytesTotal + kTailBytes;
 };
@@ -123,9 +123,9 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
   uint64_t* a_empty = bars + 12;      // [12]
   uint64_t* b_full = bars + 24;       // [9]  (resident mode: b_full[0] only)
   uint64_t* b_empty = bars + 33;      // [9]
-  uint64_t* tmem_full = bars + 42;    // [2]
-  uint64_t* tmem_empty = bars + 44;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 46);
+  uint64_t* tmem_full = bars + 42;    // [4]
+  uint64_t* tmem_empty = bars + 46;   // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 50);
 
   const int tiles_x = a.R / 16;
   const int tiles_per_img = tiles_x * tiles_x;
@@ -143,7 +143,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
         mbar_init(&a_full[s], 1);
         mbar_init(&a_empty[s], 1);
       }
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < Cfg::kAccPairs; ++s) {
         mbar_init(&tmem_full[s], 1);
         mbar_init(&tmem_empty[s], 8);
       }
@@ -164,7 +164,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       if (Cfg::kBResident) {
         mbar_expect_tx(&b_full[0], 9u * Cfg::kTapBytes);
         for (int tap = 0; tap < 9; ++tap)
@@ -209,7 +209,10 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): ptxas then knows the region is single-threaded and issues each UTCHMMA directly
+    // instead of wrapping it in a per-instruction elect / branch loop (~40 cycles per MMA, which at N = 48 — 24 tensor
+    // cycles per MMA — left the tensor pipe half idle)
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, CR);
       int step = 0, bs = 0, acc = 0;
       uint32_t bphase = 0, acc_phase = 0;

@@ -155,7 +155,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       int stage = 0;
       uint32_t phase = 0;
       if (wst) {   // the whole [BN x K] weight slab of this CTA's n-tile, once
@@ -190,7 +190,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0;

@@ -99,7 +99,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       mbar_expect_tx(q_full, Cfg::kQBytes);
       for (int kb = 0; kb < Cfg::kKBlocks; ++kb)
         tma_load_2d(sQ + kb * (MHA_BQ * Cfg::kRowBytes), &tmap_q, q_full, q_col0 + head * HD + kb * 64, b * Lq + q0);
@@ -120,7 +120,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       constexpr uint32_t idesc_s = make_idesc_bf16(MHA_BQ, MHA_BKEY);
       constexpr uint32_t idesc_o = make_idesc_bf16(MHA_BQ, HD, /*b_mn_major=*/1);
       auto issue_S = [&](int j) {   // S(j) -> TMEM buffer j%2, from K stage j%2

@@ -136,7 +136,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA weight producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -161,7 +161,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
       constexpr uint32_t idesc = make_idesc_bf16(128, NT);
       int stage = 0;
       uint32_t phase = 0;
