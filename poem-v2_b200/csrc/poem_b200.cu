@@ -994,7 +994,7 @@ static int launch_project_sample(const float* xmap, const float* intr, const flo
   prof_begin(st);
   camera_prep_kernel<<<(NV + 63) / 64, 64, 0, st>>>(intr, extr, proj, NV);
   LAUNCH_CHECK("camera_prep_kernel");
-  const size_t smem = (size_t)SAMPLE_CH * fh * fw * sizeof(float);
+  const size_t smem = (size_t)SAMPLE_PITCH * fh * fw * sizeof(float);
   if (smem > 48 * 1024) return fail(POEM_E_BADDIM, "feature map %dx%d too large for the sampler", fh, fw);
   dim3 grid(D / SAMPLE_CH, NV);
   prof_begin(st);

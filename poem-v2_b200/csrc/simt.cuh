@@ -82,6 +82,7 @@ __global__ void camera_prep_kernel(const float* __restrict__ intr, const float* 
 //            F.grid_sample(bilinear, zeros, align_corners=False) ptEmb_head.py:900-901
 // ------------------------------------------------------------------------------------------------
 constexpr int SAMPLE_CH = 32;
+constexpr int SAMPLE_PITCH = SAMPLE_CH + 4;   // floats per pixel in smem
 constexpr int SAMPLE_THREADS = 512;
 
 __global__ void __launch_bounds__(SAMPLE_THREADS)
@@ -90,14 +91,20 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
                       const int* __restrict__ img_sample, const int* __restrict__ img_view,
                       const int* __restrict__ sample_rowbase, __nv_bfloat16* __restrict__ X, int D, int P, int FH,
                       int FW, float inv_w, float inv_h) {
-  extern __shared__ float planes[];  // [SAMPLE_CH][FH*FW]
+  // Pixel-major copy of this block's 32 channels: pix[pixel][SAMPLE_PITCH], 36 floats per pixel (32 channels + pad).
+  // A tap is then read as 8 x LDS.128 (4 channels each) instead of 32 scalar loads, and with the 144-byte pitch the
+  // 16-byte bank group of a lane is (pixel + channel group) % 8, so random pixels spread over all banks (the
+  // channel-planar layout had every lane of a warp gathering from the same 1 KB plane: 66 M bank conflicts per call).
+  extern __shared__ __align__(16) float pix[];
   const int img = blockIdx.y;
   const int d0 = blockIdx.x * SAMPLE_CH;
   const int F = FH * FW;
   const int b = img_sample[img];
   const int n = img_view[img];
-  for (int i = threadIdx.x; i < SAMPLE_CH * F; i += SAMPLE_THREADS)
-    planes[i] = xmap[((size_t)img * D + d0) * F + i];
+  for (int i = threadIdx.x; i < SAMPLE_CH * F; i += SAMPLE_THREADS) {
+    const int ch = i / F, px = i - ch * F;
+    pix[px * SAMPLE_PITCH + ch] = xmap[((size_t)img * D + d0) * F + i];
+  }
   const float* pm = proj + img * 24;
   const float cx = centre[b * 3 + 0], cy = centre[b * 3 + 1], cz = centre[b * 3 + 2];
   constexpr int PTS = 8;
@@ -141,25 +148,32 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
   const int chunks = P / D;  // rows per (view, channel)
   const size_t row0 = (size_t)sample_rowbase[b] + (size_t)n * P;
   const int p0 = threadIdx.x * PTS;
-  for (int dd = 0; dd < SAMPLE_CH; ++dd) {
-    const float* pl = planes + dd * F;
-    const size_t rbase = row0 + (size_t)(d0 + dd) * chunks;
-    float v[PTS];
+#pragma unroll 1
+  for (int cg = 0; cg < SAMPLE_CH / 4; ++cg) {
+    float v[4][PTS];
 #pragma unroll
     for (int j = 0; j < PTS; ++j) {
       // ATen accumulates the four taps in the order nw, ne, sw, se
-      float t = pl[o00[j]] * w00[j];
-      t += pl[o01[j]] * w01[j];
-      t += pl[o10[j]] * w10[j];
-      t += pl[o11[j]] * w11[j];
-      v[j] = t;
+      const float4 a = *reinterpret_cast<const float4*>(pix + o00[j] * SAMPLE_PITCH + 4 * cg);
+      const float4 bq = *reinterpret_cast<const float4*>(pix + o01[j] * SAMPLE_PITCH + 4 * cg);
+      const float4 c = *reinterpret_cast<const float4*>(pix + o10[j] * SAMPLE_PITCH + 4 * cg);
+      const float4 d = *reinterpret_cast<const float4*>(pix + o11[j] * SAMPLE_PITCH + 4 * cg);
+      float t;
+      t = a.x * w00[j], t += bq.x * w01[j], t += c.x * w10[j], t += d.x * w11[j], v[0][j] = t;
+      t = a.y * w00[j], t += bq.y * w01[j], t += c.y * w10[j], t += d.y * w11[j], v[1][j] = t;
+      t = a.z * w00[j], t += bq.z * w01[j], t += c.z * w10[j], t += d.z * w11[j], v[2][j] = t;
+      t = a.w * w00[j], t += bq.w * w01[j], t += c.w * w10[j], t += d.w * w11[j], v[3][j] = t;
     }
-    uint4 pk;
-    pk.x = pack_bf16x2(v[0], v[1]);
-    pk.y = pack_bf16x2(v[2], v[3]);
-    pk.z = pack_bf16x2(v[4], v[5]);
-    pk.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(X + (rbase + p0 / D) * D + (p0 % D)) = pk;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const size_t rbase = row0 + (size_t)(d0 + 4 * cg + q) * chunks;
+      uint4 pk;
+      pk.x = pack_bf16x2(v[q][0], v[q][1]);
+      pk.y = pack_bf16x2(v[q][2], v[q][3]);
+      pk.z = pack_bf16x2(v[q][4], v[q][5]);
+      pk.w = pack_bf16x2(v[q][6], v[q][7]);
+      *reinterpret_cast<uint4*>(X + (rbase + p0 / D) * D + (p0 % D)) = pk;
+    }
   }
 }
 
