@@ -157,7 +157,7 @@ def torch_cuda_reference_pass(size, V, B, steps, warmup, dev, tf32):
     return B / ms * 1e3, ms
 
 
-def images_to_mesh_pass(size, V, B, dev, cpu_views, steps=10, warmup=3):
+def images_to_mesh_pass(size, V, B, dev, cpu_views, steps=10, warmup=3, eager=False):
     """SURVEY §8d metric (ii): samples/s of the whole evaluation forward (`PtEmbedMultiviewStereoV2._forward_impl`,
     POEM.py:251-333) from images resident in HBM (two image sets alternated, each >> L2), and the oracle port of the
     same forward on the host cores for ONE sample (bounded: the fp32 backbone costs ~30 GFLOP per image)."""
@@ -186,7 +186,33 @@ def images_to_mesh_pass(size, V, B, dev, cpu_views, steps=10, warmup=3):
     res = {"value": B / ms * 1e3, "unit": "samples/s", "images_per_s": B * V / ms * 1e3, "ms_per_step": ms,
            "workload": f"POEM-{size}: {B} samples x {V} views of 3x256x256 -> mesh (backbone + feat_decode + heatmap + "
                        f"DLT + decoder)", "finite": bool(torch.isfinite(out).all())}
-    del model, batches
+    del model
+    torch.cuda.empty_cache()
+    if eager:   # the reference's eager PyTorch ops (oracle port) for the same forward on this GPU: reported context
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import poem_oracle as orc
+        sd_dev = {k: v.to(dev) for k, v in sd.items()}
+        assets = [t.to(dev) for t in synth.load_assets()]
+        tmpl = synth.standin_template().to(dev)
+        res["torch_cuda_eager"] = {}
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        try:
+            for tf32 in (False, True):
+                torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+                with torch.no_grad():
+                    orc.model_forward(sd_dev, dims, batches[0], tmpl, *assets)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for i in range(3):
+                        orc.model_forward(sd_dev, dims, batches[i & 1], tmpl, *assets)
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms_e = e0.elapsed_time(e1) / 3
+                res["torch_cuda_eager"]["tf32" if tf32 else "fp32"] = {"samples_per_s": B / ms_e * 1e3, "ms_per_step": ms_e}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        del sd_dev
+    del batches
     torch.cuda.empty_cache()
     if cpu_views:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -447,7 +473,8 @@ def main():
         try:
             head._ws = None
             torch.cuda.empty_cache()
-            images = images_to_mesh_pass(size, V, B, dev, cpu_views=V if not args.no_cpu_baseline else 0)
+            images = images_to_mesh_pass(size, V, B, dev, cpu_views=V if not args.no_cpu_baseline else 0,
+                                         eager=args.torch_cuda_baseline)
         except Exception as e:  # noqa: BLE001
             images = {"error": repr(e)[:300]}
     line = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps,

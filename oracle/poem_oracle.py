@@ -334,10 +334,10 @@ def uv_decode_heatmap(sd, feats, img_w=256, img_h=256):
     pdf = hmap.reshape(*hmap.shape[:2], -1)
     pdf = (pdf / (pdf.sum(dim=-1, keepdim=True) + 1e-6)).view_as(hmap)
     v_accu, u_accu = pdf.sum(dim=3), pdf.sum(dim=2)
-    wv = torch.arange(v_accu.shape[-1], dtype=pdf.dtype) / v_accu.shape[-1]
-    wu = torch.arange(u_accu.shape[-1], dtype=pdf.dtype) / u_accu.shape[-1]
+    wv = torch.arange(v_accu.shape[-1], dtype=pdf.dtype, device=pdf.device) / v_accu.shape[-1]
+    wu = torch.arange(u_accu.shape[-1], dtype=pdf.dtype, device=pdf.device) / u_accu.shape[-1]
     uv = torch.cat([(u_accu * wu).sum(-1, keepdim=True), (v_accu * wv).sum(-1, keepdim=True)], dim=-1)
-    return uv * torch.tensor([float(img_w), float(img_h)]), hmap
+    return uv * torch.tensor([float(img_w), float(img_h)], device=uv.device), hmap
 
 
 def triangulate_dlt(uv_px, cam_intr, cam_extr, view_counts):
