@@ -79,7 +79,8 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kWBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kBiasBytes = 2 * BN * 4;
+  static constexpr int kBiasMax = 4096;                                   // the whole bias vector lives in smem up to this N
+  static constexpr int kBiasBytes = kBiasMax * 4;
   static constexpr int kTailBytes = kBiasBytes + 256 /*barriers*/;
   static constexpr int kSmemMax = 232448;                                 // 227 KB per CTA
   static constexpr int kStagesRoom = (kSmemMax - 1024 - kTailBytes) / kStageBytes;
@@ -148,6 +149,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncwarp();
     tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
+  // the bias vector goes to smem once (a per-tile global load + named barrier sat on the epilogue's critical path)
+  const bool bias_resident = (N <= Cfg::kBiasMax);
+  if (bias_resident)
+    for (int j = threadIdx.x; j < N; j += GEMM_THREADS) s_bias[j] = ep.bias != nullptr ? __ldg(ep.bias + j) : 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -260,11 +265,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int it = it0; it < it_end; it += it_step) {
       const int m0 = (wst ? it : it / tiles_n) * GEMM_BM;
       const int n0 = (wst ? my_n_tile : it % tiles_n) * BN;
-      // bias of this tile's columns -> smem (double buffered by accumulator stage)
-      float* sb = s_bias + acc * BN;
-      for (int j = threadIdx.x - 64; j < BN; j += 32 * GEMM_EPI_WARPS)
-        sb[j] = (ep.bias != nullptr && n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+      float* sb = s_bias + n0;
+      if (!bias_resident) {   // very wide outputs: this tile's columns, double buffered by accumulator stage
+        sb = s_bias + acc * BN;
+        for (int j = threadIdx.x - 64; j < BN; j += 32 * GEMM_EPI_WARPS)
+          sb[j] = (ep.bias != nullptr && n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+      }
 
       const int mt_row = m0 + quarter * 32 + lane;   // this lane's output row
       const float* resf;
@@ -295,28 +302,45 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         t_base = (size_t)g * ep.t_group_stride + (size_t)(mt_row - g * ep.t_rows);
       }
 
-#pragma unroll 1
-      for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
+      // This warp's chunks are c0 = 32 * chunk_par + 64 * j.  The active ones form a prefix (columns < N that exist in
+      // memory), so without a residual operand the TMEM load of chunk j + 1 is issued before chunk j is processed.
+      constexpr int kChunksPerWarp = (BN / 32 + 1) / 2;
+      constexpr int kRegSets = kRes ? 1 : 2;
+      auto chunk_active = [&](int j) {
+        const int c0 = chunk_par * 32 + 64 * j, n = n0 + c0;
+        return c0 < BN && n < N && !(n < ep.trans_from && ep.n_store - n <= 0);
+      };
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk_par * 32;
+      uint32_t rbuf[kRegSets][32];
+      if (!kRes && chunk_active(0)) tmem_ld32(tmem_acc, rbuf[0]);
+#pragma unroll
+      for (int j = 0; j < kChunksPerWarp; ++j) {
+        if (!chunk_active(j)) break;   // warp-uniform
+        const int c0 = chunk_par * 32 + 64 * j;
         const int n = n0 + c0;
-        if (n >= N) break;   // warp-uniform
         // this chunk's residual values: in flight before the accumulator chunk is read
         uint32_t rr[32];
-        const int valid = ep.n_store - n;   // row-major columns of this chunk that exist in memory: >= 32, 16 or <= 0
-        if (n < ep.trans_from && valid <= 0) continue;   // warp-uniform: nothing of this chunk is stored
+        const int valid = ep.n_store - n;   // row-major columns of this chunk that exist in memory: >= 32 or 16
         if (kRes && n < ep.trans_from) {
           if (resf != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (valid >= 8 * (j + 1)) ldg_nc_256(resf + n + 8 * j, &rr[8 * j]);
+            for (int q = 0; q < 4; ++q)
+              if (valid >= 8 * (q + 1)) ldg_nc_256(resf + n + 8 * q, &rr[8 * q]);
           } else if (resb != nullptr) {
             ldg_nc_256(resb + n, &rr[0]);
             if (valid >= 32) ldg_nc_256(resb + n + 16, &rr[8]);
           }
         }
-        uint32_t r[32];
-        __syncwarp();   // lanes past the last row skip the stores below: reconverge before the aligned TMEM load
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c0, r);
+        uint32_t (&r)[32] = rbuf[kRes ? 0 : (j & 1)];
+        if (kRes) {
+          __syncwarp();   // lanes past the last row skip the stores below: reconverge before the aligned TMEM load
+          tmem_ld32(tmem_acc + 64 * j, r);
+        }
         tmem_ld_wait();
+        if (!kRes && j + 1 < kChunksPerWarp && chunk_active(j + 1)) {
+          __syncwarp();
+          tmem_ld32(tmem_acc + 64 * (j + 1), rbuf[(j + 1) & 1]);
+        }
         if (mt_row < M) {
         float v[32];
 #pragma unroll
