@@ -247,6 +247,13 @@ int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd, const Poem
 int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, const float* cam_extr, const int32_t* view_counts,
                          int batch, int n_joints, float* ref_joints, void* stream);
 
+/* Evaluation metrics on the device (reference lib/metrics/pa_eval.py:41-124 `PAEval.feed` /
+ * `align_w_scale`, lib/metrics/mean_epe.py:23-33): per sample the Procrustes-aligned and the raw mean point distance.
+ * gt, pred: fp32 (batch, n_points, 3); out: fp32 (batch, 2) = [aligned, raw]; aligned: optional fp32 (batch, n_points, 3)
+ * aligned prediction.  Replaces the per-sample host loop around scipy.linalg.orthogonal_procrustes. */
+int poem_pa_metrics(const float* gt, const float* pred, int batch, int n_points, float* out, float* aligned,
+                    void* stream);
+
 /* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
  * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
  * c_live_in / c_live_out > 0 promise that only the first c_live_in input / c_live_out output channels are non-zero

@@ -138,6 +138,29 @@ def run_reference_image_stage(n_images, wseed, iseed):
     return mlvl, feats, uv, ref_j
 
 
+def run_reference_pa_metrics(seed):
+    """The real `PAEval` (lib/metrics/pa_eval.py) fed with seeded joints / vertices; returns inputs and its measures."""
+    ref_shim.install(synth.standin_template)
+    from lib.metrics.pa_eval import PAEval
+    g = torch.Generator().manual_seed(seed)
+    gt_j = torch.tensor([0.0, 0.0, 0.6]) + 0.05 * torch.randn(5, 21, 3, generator=g)
+    gt_v = torch.tensor([0.0, 0.0, 0.6]) + 0.05 * torch.randn(5, 778, 3, generator=g)
+    # predictions: a similarity transform of the ground truth (rotation, scale, shift) plus noise
+    ang = 0.3 * torch.randn(5, 3, generator=g)
+    Rm = torch.linalg.matrix_exp(torch.stack([torch.tensor([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]]) for a in ang]))
+    sc = 1.0 + 0.1 * torch.randn(5, 1, 1, generator=g)
+    sh = 0.02 * torch.randn(5, 1, 3, generator=g)
+    pr_j = (gt_j - gt_j.mean(1, keepdim=True)) @ Rm.transpose(1, 2) * sc + gt_j.mean(1, keepdim=True) + sh \
+        + 0.004 * torch.randn(5, 21, 3, generator=g)
+    pr_v = (gt_v - gt_v.mean(1, keepdim=True)) @ Rm.transpose(1, 2) * sc + gt_v.mean(1, keepdim=True) + sh \
+        + 0.004 * torch.randn(5, 778, 3, generator=g)
+    ev = PAEval(None, mesh_score=True)
+    ev.feed(pr_j, gt_j, pr_v, gt_v)
+    al_j = np.stack([PAEval.align_w_scale(gt_j[i].numpy().copy(), pr_j[i].numpy().copy())[0] for i in range(5)])
+    return dict(gt_j=gt_j.numpy(), gt_v=gt_v.numpy(), pr_j=pr_j.numpy(), pr_v=pr_v.numpy(), aligned_j=al_j,
+                measures=np.array([ev.get_measures()[k] for k in ("pa_mpjpe", "mpjpe", "pa_mpvpe", "mpvpe")]))
+
+
 def run_reference_stage4(n_images, wseed, iseed):
     """The real reference `HighResolutionModule` x3 (= `HighResolutionNet.stage4`, hrnet.py:272-277) on CPU."""
     hr = _import_reference_hrnet()
@@ -165,6 +188,9 @@ def main():
                         meta=np.array(repr(dict(kind="image_stage", n_images=3, wseed=0, iseed=1))), mlvl_feat=mf.numpy(),
                         pred_joints_uv=uv.numpy(), ref_joints=rj.numpy())
     print("image_stage_n3", tuple(mf.shape), float(mf.abs().mean()), tuple(uv.shape), tuple(rj.shape), rj[0, :2])
+    pm = run_reference_pa_metrics(3)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics_pa.npz"), **pm)
+    print("metrics_pa", pm["measures"])
     if "--only-hrnet" in sys.argv:
         return
     ys = run_reference_stage4(2, 0, 1)

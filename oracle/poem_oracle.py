@@ -379,3 +379,28 @@ def model_forward(sd, dims, batch, template, bps, anchor_xyz, anchor_idx):
     c = pj[:, dims.center_idx].unsqueeze(1)
     return {"all_coords_preds": coords, "pred_joints_3d": pj, "pred_verts_3d": pv, "pred_joints_3d_rel": pj - c,
             "pred_verts_3d_rel": pv - c, "pred_joints_uv": uv, "pred_ref_joints_3d": ref_joints}
+
+
+def pa_align(gt, pred):
+    """`PAEval.align_w_scale` (lib/metrics/pa_eval.py:103-124) for one sample, numpy fp32 like the reference; the
+    orthogonal Procrustes step is scipy's published algorithm (scipy.linalg.orthogonal_procrustes: u, w, vt =
+    svd(A^T B); R = u vt; scale = sum(w))."""
+    import numpy as np
+    mtx1, mtx2 = np.asarray(gt, dtype=np.float32), np.asarray(pred, dtype=np.float32)
+    t1, t2 = mtx1.mean(0), mtx2.mean(0)
+    a, b = mtx1 - t1, mtx2 - t2
+    s1 = np.linalg.norm(a) + 1e-8
+    a = a / s1
+    s2 = np.linalg.norm(b) + 1e-8
+    b = b / s2
+    u, w, vt = np.linalg.svd(a.T.dot(b))
+    R, s = u.dot(vt), w.sum()
+    return np.dot(b, R.T) * s * s1 + t1
+
+
+def pa_distances(gt, pred):
+    """(B,N,3) x2 -> (B,2): [aligned mean distance, raw mean distance] as `PAEval.feed` / `get_dist` (pa_eval.py:41-66)."""
+    import numpy as np
+    gt, pred = np.asarray(gt, dtype=np.float32), np.asarray(pred, dtype=np.float32)
+    al = np.stack([pa_align(g, p) for g, p in zip(gt, pred)])
+    return np.stack([np.linalg.norm(al - gt, axis=2).mean(1), np.linalg.norm(pred - gt, axis=2).mean(1)], axis=1)

@@ -120,7 +120,7 @@ class PoemInputs(C.Structure):
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
            "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_hrnet_stage4_workspace_bytes",
-           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_triangulate_dlt", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
+           "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_triangulate_dlt", "poem_pa_metrics", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm"]
@@ -195,6 +195,8 @@ def load():
     lib.poem_image_features.restype = i
     lib.poem_image_features.argtypes = [C.POINTER(PoemHRNet), C.POINTER(PoemFeatDecode), C.POINTER(PoemUVDecode), i, i, vp,
                                         vp, vp, vp, C.POINTER(vp), vp, sz, vp]
+    lib.poem_pa_metrics.restype = i
+    lib.poem_pa_metrics.argtypes = [vp, vp, i, i, vp, vp, vp]
     lib.poem_triangulate_dlt.restype = i
     lib.poem_triangulate_dlt.argtypes = [vp, vp, vp, vp, i, i, vp, vp]
     lib.poem_conv_nhwc.restype = i

@@ -806,6 +806,17 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
   return POEM_OK;
 }
 
+extern "C" int poem_pa_metrics(const float* gt, const float* pred, int batch, int n_points, float* out, float* aligned,
+                               void* stream) {
+  if (!gt || !pred || !out) return fail(POEM_E_NULL, "pa_metrics: null pointer");
+  if (batch < 1 || n_points < 3) return fail(POEM_E_BADDIM, "pa_metrics: batch=%d points=%d", batch, n_points);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  pa_metrics_kernel<<<batch, PA_THREADS, 0, st>>>(gt, pred, n_points, out, aligned);
+  LAUNCH_CHECK("pa_metrics_kernel");
+  return POEM_OK;
+}
+
 extern "C" int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, const float* cam_extr,
                                     const int32_t* view_counts, int batch, int n_joints, float* ref_joints, void* stream) {
   if (!uv_px || !cam_intr || !cam_extr || !view_counts || !ref_joints) return fail(POEM_E_NULL, "triangulate: null pointer");

@@ -627,4 +627,119 @@ __global__ void view_tables_kernel(ViewCountsParam vc, int B, int NV, int P, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Evaluation metrics on the device (reference lib/metrics/pa_eval.py:41-124, mean_epe.py:23-33): per sample the mean
+// point distance and the Procrustes-aligned mean point distance (`PAEval.align_w_scale`: centre both sets, scale each
+// to unit Frobenius norm (+1e-8), orthogonal Procrustes R = U V^T of M = A^T B = U S V^T with scale sum(S), map the
+// prediction back with the ground truth's scale and centre).  The reference loops over samples around SciPy on the
+// host; here one block per sample, sums in fp64, the 3x3 SVD by one-sided Jacobi in fp64.
+//   gt, pred: (batch, n, 3) fp32;  out: (batch, 2) = [aligned mean distance, raw mean distance];  aligned: optional
+// ------------------------------------------------------------------------------------------------
+constexpr int PA_THREADS = 128;
+__device__ __forceinline__ double block_sum_128(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+__global__ void __launch_bounds__(PA_THREADS)
+pa_metrics_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int n, float* __restrict__ out,
+                  float* __restrict__ aligned) {
+  __shared__ double red[4];
+  __shared__ double sR[9];
+  __shared__ double sScale;
+  const float* a = gt + (size_t)blockIdx.x * n * 3;
+  const float* b = pred + (size_t)blockIdx.x * n * 3;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += PA_THREADS)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += (double)a[i * 3 + c], acc[3 + c] += (double)b[i * 3 + c];
+  float t1[3], t2[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    t1[c] = (float)(block_sum_128(acc[c], red) / n);       // the reference works in fp32 (numpy arrays of the tensors)
+    t2[c] = (float)(block_sum_128(acc[3 + c], red) / n);
+  }
+  double n1 = 0, n2 = 0, m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += PA_THREADS) {
+    float x[3], y[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = a[i * 3 + c] - t1[c], y[c] = b[i * 3 + c] - t2[c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      n1 += (double)x[r] * x[r];
+      n2 += (double)y[r] * y[r];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m[r * 3 + c] += (double)x[r] * y[c];
+    }
+  }
+  const float s1 = (float)sqrt(block_sum_128(n1, red)) + 1e-8f;
+  const float s2 = (float)sqrt(block_sum_128(n2, red)) + 1e-8f;
+  double M[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = block_sum_128(m[k], red) / ((double)s1 * (double)s2);
+  if (threadIdx.x == 0) {
+    // one-sided Jacobi: rotate column pairs of W = M V until orthogonal; then W = U S
+    double W[3][3], V[3][3];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) W[r][c] = M[r * 3 + c], V[r][c] = (r == c) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+      double off = 0.0;
+      for (int p = 0; p < 2; ++p)
+        for (int q = p + 1; q < 3; ++q) {
+          double al = 0, be = 0, ga = 0;
+          for (int r = 0; r < 3; ++r) al += W[r][p] * W[r][p], be += W[r][q] * W[r][q], ga += W[r][p] * W[r][q];
+          if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+          off = fmax(off, fabs(ga) / sqrt(al * be));
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          for (int r = 0; r < 3; ++r) {
+            const double x = W[r][p], y = W[r][q];
+            W[r][p] = cs * x - sn * y, W[r][q] = sn * x + cs * y;
+            const double vx = V[r][p], vy = V[r][q];
+            V[r][p] = cs * vx - sn * vy, V[r][q] = sn * vx + cs * vy;
+          }
+        }
+      if (off < 1e-15) break;
+    }
+    double sig[3], scale = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      sig[c] = sqrt(W[0][c] * W[0][c] + W[1][c] * W[1][c] + W[2][c] * W[2][c]);
+      scale += sig[c];
+    }
+    // R = U V^T with U = W / sigma (a vanishing singular value leaves that column of U free: degenerate input)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double v = 0.0;
+        for (int k = 0; k < 3; ++k) v += (sig[k] > 0.0 ? W[r][k] / sig[k] : 0.0) * V[c][k];
+        sR[r * 3 + c] = v;
+      }
+    sScale = scale;
+  }
+  __syncthreads();
+  double d_al = 0.0, d_raw = 0.0;
+  const float sc = (float)sScale;
+  for (int i = threadIdx.x; i < n; i += PA_THREADS) {
+    float y[3], z[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = (b[i * 3 + c] - t2[c]) / s2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)   // (pred_t . R^T) * s, then the ground truth's scale and centre
+      z[r] = ((float)sR[r * 3 + 0] * y[0] + (float)sR[r * 3 + 1] * y[1] + (float)sR[r * 3 + 2] * y[2]) * sc * s1 + t1[r];
+    float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float da = z[c] - a[i * 3 + c], dr = b[i * 3 + c] - a[i * 3 + c];
+      e0 += da * da, e1 += dr * dr;
+      if (aligned != nullptr) aligned[((size_t)blockIdx.x * n + i) * 3 + c] = z[c];
+    }
+    d_al += (double)sqrtf(e0), d_raw += (double)sqrtf(e1);
+  }
+  const double sa = block_sum_128(d_al, red), sr = block_sum_128(d_raw, red);
+  if (threadIdx.x == 0) out[blockIdx.x * 2] = (float)(sa / n), out[blockIdx.x * 2 + 1] = (float)(sr / n);
+}
+
 }  // namespace poem

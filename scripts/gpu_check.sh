@@ -15,3 +15,4 @@ run vecattn 300 tests/test_kernels_gpu.py -k "vector_attention"
 run parity 900 tests/test_parity_gpu.py
 run hrnet 400 tests/test_hrnet_gpu.py
 run model 400 tests/test_model_gpu.py
+run metrics 200 tests/test_metrics_gpu.py
