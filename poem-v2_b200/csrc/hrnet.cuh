@@ -1,7 +1,9 @@
-// HRNet-W40 stage 4 glue kernels (reference lib/models/backbones/hrnet.py:38-67,217-234,272-277).
-// Activations live as NHWC bf16 with the channel count padded to a multiple of 64 (one SWIZZLE_128B atom), so
-// every 3x3 / 1x1 convolution is an implicit GEMM of gemm_bf16_tc_kernel (TMA gathers the shifted image rows, zero
-// fill = padding); BatchNorm (eval) is folded into the weights/bias at pack time.
+// HRNet-W40 glue kernels (reference lib/models/backbones/hrnet.py, lib/models/POEM.py:189-229): layout changes, stem,
+// fuse-layer sums, upsampling / concat, heatmap soft-argmax, DLT triangulation.
+// Activations live as NHWC bf16.  Inside the image half a pixel keeps only its live channels rounded up to 16
+// (48 / 80 / 160 / 320: "compact storage"); every convolution is a tcgen05 GEMM whose A operand TMA gathers (conv3x3.cuh
+// for 3x3 stride 1, the ConvOperand mode of gemm.cuh otherwise) — a 64-channel box that runs past a pixel's channels is
+// zero-filled by the hardware; BatchNorm (eval) and conv biases are folded into the weights at pack time.
 #pragma once
 #include "common.cuh"
 
