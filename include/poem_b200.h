@@ -161,12 +161,15 @@ int poem_transformer_forward(const PoemDims* dims, const PoemWeights* w, int bat
                              const float* query_feat, const float* pt_xyz, const float* pt_feats, float* out_xyz,
                              float* out_feats, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same call with HOST input/output buffers (pinned memory recommended): copies inputs to the staging area at
- * the head of `workspace`, runs, copies `all_coords_preds` back.  Weights and workspace stay on the device.
- * workspace must hold poem_workspace_bytes() + poem_staging_bytes(). */
+/* Same call with HOST input/output buffers (pinned memory recommended): copies the inputs into `staging`, runs,
+ * copies `all_coords_preds` back.  Weights, staging and workspace stay on the device.  `staging` (poem_staging_bytes(),
+ * 1024-byte aligned) is private to this entry point: it has two slots and the inputs travel on an internal copy stream,
+ * so the host->device transfer of call i + 1 overlaps the kernels of call i; nothing else may use it while calls are
+ * in flight.  `workspace` (poem_workspace_bytes()) is only touched on `stream` and may be shared with other calls on
+ * that stream.  The host buffers of a call must stay valid until `stream` has reached the end of that call. */
 size_t poem_staging_bytes(const PoemDims* dims, int batch, int n_images);
-int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* host_in,
-                           float* host_out_coords, void* workspace, size_t workspace_bytes, void* stream);
+int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* host_in, float* host_out,
+                           void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- HRNet-W40 stage 4 (reference lib/models/backbones/hrnet.py:272-277: 3 HighResolutionModules of 4 branches x
  * 4 BasicBlocks + all-to-all fuse layers).  Convolution weights have eval-mode BatchNorm folded in and are stored as

@@ -160,7 +160,7 @@ def load():
                                       sz, vp]
     lib.poem_head_forward_host.restype = i
     lib.poem_head_forward_host.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), C.POINTER(PoemInputs), vp, vp,
-                                           sz, vp]
+                                           sz, vp, sz, vp]
     lib.poem_transformer_workspace_bytes.restype = sz
     lib.poem_transformer_workspace_bytes.argtypes = [C.POINTER(PoemDims), i]
     lib.poem_transformer_forward.restype = i

@@ -1518,22 +1518,57 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
 // host-buffer variant
 // ------------------------------------------------------------------------------------------------
 static size_t align1k(size_t x) { return (x + 1023) & ~size_t(1023); }
-extern "C" size_t poem_staging_bytes(const PoemDims* d, int B, int NV) {
-  if (check_dims(d) != POEM_OK) return 0;
+static size_t staging_slot_bytes(const PoemDims* d, int B, int NV) {
   return align1k((size_t)NV * d->in_channels * 256 * 4) + align1k((size_t)NV * 9 * 4) + align1k((size_t)NV * 16 * 4) +
          align1k((size_t)B * 63 * 4) + align1k((size_t)d->n_blocks * B * d->n_query * 3 * 4) + 1024;
 }
+// two staging slots: the host->device copy of call i + 1 overlaps the kernels of call i
+extern "C" size_t poem_staging_bytes(const PoemDims* d, int B, int NV) {
+  if (check_dims(d) != POEM_OK) return 0;
+  return 2 * staging_slot_bytes(d, B, NV);
+}
+
+// copy stream + events of the host-buffer entry point (per host thread)
+struct HostPipe {
+  cudaStream_t copy = nullptr;
+  cudaEvent_t h2d_done[2], slot_free[2];
+  int next = 0;
+  bool ok = false;
+};
+static HostPipe& host_pipe() {
+  static thread_local HostPipe p;
+  if (!p.ok && cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking) == cudaSuccess) {
+    p.ok = true;
+    for (int i = 0; i < 2; ++i)
+      p.ok = p.ok && cudaEventCreateWithFlags(&p.h2d_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p.slot_free[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  return p;
+}
 
 extern "C" int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* hin,
-                                      float* host_out, void* workspace, size_t workspace_bytes, void* stream) {
+                                      float* host_out, void* staging, size_t staging_bytes, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   POEM_TRY(check_dims(dims));
-  if (!hin || !host_out || !workspace) return fail(POEM_E_NULL, "head_forward_host: null pointer");
+  if (!hin || !host_out || !workspace || !staging) return fail(POEM_E_NULL, "head_forward_host: null pointer");
+  if (reinterpret_cast<uintptr_t>(staging) & 1023) return fail(POEM_E_ALIGN, "staging must be 1024-byte aligned");
   const int B = hin->batch, NV = hin->n_images;
-  const size_t stage = poem_staging_bytes(dims, B, NV);
-  const size_t need = stage + poem_workspace_bytes(dims, B, NV);
-  if (workspace_bytes < need) return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, need);
+  const size_t slot_bytes = staging_slot_bytes(dims, B, NV);
+  if (staging_bytes < 2 * slot_bytes) return fail(POEM_E_WORKSPACE, "staging %zu < required %zu", staging_bytes, 2 * slot_bytes);
+  if (workspace_bytes < poem_workspace_bytes(dims, B, NV))
+    return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, poem_workspace_bytes(dims, B, NV));
   cudaStream_t st = (cudaStream_t)stream;
-  Bump b{reinterpret_cast<uint8_t*>(workspace), 0};
+  // Inputs travel on a copy stream into one of two staging slots, so the transfer of the next call overlaps the
+  // kernels of this one; a slot is reused only after the call that read it has finished (slot_free).  A capturing
+  // stream (CUDA graph) or a failed stream creation falls back to copying on the compute stream.
+  HostPipe& hp = host_pipe();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const bool piped = hp.ok && cap == cudaStreamCaptureStatusNone && !g_prof_on;
+  const int slot = piped ? hp.next : 0;
+  if (piped) hp.next ^= 1;
+  cudaStream_t cs = piped ? hp.copy : st;
+  Bump b{reinterpret_cast<uint8_t*>(staging) + (size_t)slot * slot_bytes, 0};
   const size_t n_feat = (size_t)NV * dims->in_channels * 256;
   float* d_feat = b.take<float>(n_feat);
   float* d_intr = b.take<float>((size_t)NV * 9);
@@ -1541,17 +1576,22 @@ extern "C" int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w
   float* d_ref = b.take<float>((size_t)B * 63);
   const size_t n_out = (size_t)dims->n_blocks * B * dims->n_query * 3;
   float* d_out = b.take<float>(n_out);
-  CUDA_TRY(cudaMemcpyAsync(d_feat, hin->mlvl_feat, n_feat * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_intr, hin->cam_intr, (size_t)NV * 9 * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_extr, hin->cam_extr, (size_t)NV * 16 * 4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(d_ref, hin->reference_joints, (size_t)B * 63 * 4, cudaMemcpyHostToDevice, st));
+  if (piped) CUDA_TRY(cudaStreamWaitEvent(cs, hp.slot_free[slot], 0));   // no-op until the slot has been used once
+  CUDA_TRY(cudaMemcpyAsync(d_feat, hin->mlvl_feat, n_feat * 4, cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(cudaMemcpyAsync(d_intr, hin->cam_intr, (size_t)NV * 9 * 4, cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(cudaMemcpyAsync(d_extr, hin->cam_extr, (size_t)NV * 16 * 4, cudaMemcpyHostToDevice, cs));
+  CUDA_TRY(cudaMemcpyAsync(d_ref, hin->reference_joints, (size_t)B * 63 * 4, cudaMemcpyHostToDevice, cs));
+  if (piped) {
+    CUDA_TRY(cudaEventRecord(hp.h2d_done[slot], cs));
+    CUDA_TRY(cudaStreamWaitEvent(st, hp.h2d_done[slot], 0));
+  }
   PoemInputs din = *hin;
   din.mlvl_feat = d_feat;
   din.cam_intr = d_intr;
   din.cam_extr = d_extr;
   din.reference_joints = d_ref;
-  POEM_TRY(poem_head_forward(dims, w, &din, d_out, nullptr, reinterpret_cast<uint8_t*>(workspace) + stage,
-                             workspace_bytes - stage, stream));
+  POEM_TRY(poem_head_forward(dims, w, &din, d_out, nullptr, workspace, workspace_bytes, stream));
   CUDA_TRY(cudaMemcpyAsync(host_out, d_out, n_out * 4, cudaMemcpyDeviceToHost, st));
+  if (piped) CUDA_TRY(cudaEventRecord(hp.slot_free[slot], st));
   return POEM_OK;
 }

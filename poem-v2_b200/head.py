@@ -181,8 +181,12 @@ class POEM_Generalized_Head(_NativeDecoder):
         lib = nat.load()
         pw = self.packed(dev)
         cd = nat.make_dims(d, MAX_VIEWS)
-        need = lib.poem_workspace_bytes(C.byref(cd), B, NV) + lib.poem_staging_bytes(C.byref(cd), B, NV)
-        ws_ptr, ws_bytes = self.workspace(need, dev)
+        ws_ptr, ws_bytes = self.workspace(lib.poem_workspace_bytes(C.byref(cd), B, NV), dev)
+        # staging is private to the host entry point (its copy stream writes it while earlier calls still compute)
+        st_need = lib.poem_staging_bytes(C.byref(cd), B, NV)
+        if getattr(self, "_stage", None) is None or self._stage.numel() < st_need + 1024 or self._stage.device != torch.device(dev):
+            self._stage = torch.empty(st_need + 1024, dtype=torch.uint8, device=dev)
+        st_off = (-self._stage.data_ptr()) % 1024
         if out is None:
             out = torch.empty(d.n_blocks, B, d.n_query, 3, dtype=torch.float32).pin_memory()
         inp_w, inp_h = img_metas["inp_img_shape"]
@@ -191,7 +195,8 @@ class POEM_Generalized_Head(_NativeDecoder):
         inp = nat.PoemInputs(B, NV, views.ctypes.data, mlvl_feat.data_ptr(), img_metas["cam_intr"].data_ptr(),
                              img_metas["cam_extr"].data_ptr(), reference_joints.data_ptr(), float(inp_w), float(inp_h))
         stream = torch.cuda.current_stream(dev).cuda_stream
-        nat.check(lib.poem_head_forward_host(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), ws_ptr,
+        nat.check(lib.poem_head_forward_host(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(),
+                                             self._stage.data_ptr() + st_off, self._stage.numel() - st_off, ws_ptr,
                                              ws_bytes, stream))
         return out
 
