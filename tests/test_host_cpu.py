@@ -42,6 +42,31 @@ def test_workspace_query_and_dim_validation_need_no_gpu():
     assert b"embed_dims" in lib.poem_last_error()
 
 
+def test_image_half_workspace_queries_need_no_gpu():
+    """Workspace planning of the image half is host arithmetic: compact storage (48 / 80 / 160 / 320 channels per
+    pixel) sizes it, the heatmap branch adds its concat buffers, bad arguments return 0."""
+    import ctypes as C
+    lib = nat.load()
+    net, fd, uv = nat.PoemHRNet(), nat.PoemFeatDecode(), nat.PoemUVDecode()
+    for i, c in enumerate((40, 80, 160, 320)):
+        net.channels[i] = c
+    fd.out_channels, uv.n_joints = 160, 21
+    n256 = lib.poem_hrnet_workspace_bytes(C.byref(net), 256, 256)
+    assert 3.0e9 < n256 < 4.5e9
+    assert abs(lib.poem_hrnet_workspace_bytes(C.byref(net), 128, 256) * 2 - n256) < 1 << 20      # linear in the image count
+    f = lib.poem_image_features_workspace_bytes(C.byref(net), C.byref(fd), None, 256, 256)
+    fu = lib.poem_image_features_workspace_bytes(C.byref(net), C.byref(fd), C.byref(uv), 256, 256)
+    assert n256 < f < fu < n256 + (2 << 30)
+    assert lib.poem_hrnet_workspace_bytes(C.byref(net), 0, 256) == 0
+    assert lib.poem_hrnet_workspace_bytes(C.byref(net), 4, 250) == 0                            # not a multiple of 32
+    st = nat.PoemHRStage4()
+    st.n_modules = 3
+    for i, c in enumerate((40, 80, 160, 320)):
+        st.channels[i] = c
+    s4 = lib.poem_hrnet_stage4_workspace_bytes(C.byref(st), 256, 64)
+    assert 0 < s4 < n256
+
+
 def test_sine_table_matches_oracle():
     for n, f in [(1, 64), (3, 128), (8, 256)]:
         a = pack.sine_pos_3d(n, 16, 16, f)
