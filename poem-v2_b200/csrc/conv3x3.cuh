@@ -27,6 +27,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace poem {
@@ -269,94 +271,133 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
     // ===================== epilogue warps (2..9) =====================
     // TMEM lane m = 32 q + lane is the pixel (row y0 + m / 8, column x0 + 8 sub + m % 8); a 32-channel chunk of it is 64
     // contiguous bytes of the NHWC tensor, moved as two 256-bit accesses.  Warps q and q + 4 split the chunks by parity.
+    // With two warps per scheduler the epilogue is bound by the length of its own dependent instruction stream (an
+    // "empty" kernel — no loads, MMAs or stores — ran at 2/3 of the full one), so the stream is kept short: the chunk
+    // parity is a compile-time constant (channel masks fold away), tile -> pixel arithmetic is shifts on 32-bit values
+    // (the map is a power of two wide), ReLU rides on the bf16 conversion (cvt.rn.relu), and for C <= 64 the bias sits
+    // in registers and both sub-tiles' TMEM loads are in flight together.
     const int quarter = warp & 3;
-    const int par = (warp - 2) >> 2;
     constexpr int kChunks = CP / 64;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-      const int y0 = (rem / tiles_x) * 16, x0 = (rem % tiles_x) * 16;
-      if (a.res != nullptr && tile + (int)gridDim.x < num_tiles) {
-        // the shortcut pixels of this CTA's NEXT tile start travelling HBM -> L2 now
-        const int tn = tile + (int)gridDim.x;
-        const int nn = tn / tiles_per_img, remn = tn - nn * tiles_per_img;
-        const int yn = (remn / tiles_x) * 16 + quarter * 4 + (lane >> 3), xn = (remn % tiles_x) * 16 + (lane & 7);
+    const int tx_log2 = 31 - __clz(tiles_x);                  // R / 16 is 1, 2, 4, ...
+    const uint32_t lane_pix = (uint32_t)((quarter * 4 + (lane >> 3)) * a.R + (lane & 7));
+    auto tile_pix = [&](int tile) -> uint32_t {               // pixel index of the tile's first pixel
+      const int n = tile >> (2 * tx_log2), rem = tile & (tiles_per_img - 1);
+      return (uint32_t)((n * a.R + ((rem >> tx_log2) << 4)) * a.R + ((rem & (tiles_x - 1)) << 4));
+    };
+    auto body = [&](auto par_c) {
+      constexpr int par = decltype(par_c)::value;
+      constexpr bool kRegBias = (kChunks == 1);
+      constexpr bool kBothSubs = (kChunks == 1);              // 2 x 32 accumulator registers
+      float bias_r[kRegBias ? 32 : 1];
+      if constexpr (kRegBias) {
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const __nv_bfloat16* rp = a.res + (((size_t)nn * a.R + yn) * a.R + xn + sub * 8) * a.cout_s;
-#pragma unroll
-          for (int j = 0; j < kChunks; ++j)
-            if ((2 * j + par) * 32 < CR) prefetch_l2(rp + (2 * j + par) * 32);
-        }
+        for (int q = 0; q < 32; ++q) bias_r[q] = (par * 32 + q < CR) ? s_bias[par * 32 + q] : 0.f;
       }
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const size_t off = (((size_t)n * a.R + (y0 + quarter * 4 + (lane >> 3))) * a.R + (x0 + sub * 8 + (lane & 7))) * a.cout_s;
-        // this warp's chunks are 2 j + par; chunk c covers channels [32 c, 32 c + 32): real below CR, zero padding above
-        uint32_t rres[kChunks][16];
-        if (a.res != nullptr) {   // every shortcut load of this sub-tile is in flight before the accumulator is awaited
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t pix0 = tile_pix(tile) + lane_pix;
+        if (a.res != nullptr && tile + (int)gridDim.x < num_tiles) {
+          // the shortcut pixels of this CTA's NEXT tile start travelling HBM -> L2 now
+          const __nv_bfloat16* rp = a.res + (size_t)(tile_pix(tile + (int)gridDim.x) + lane_pix) * a.cout_s;
 #pragma unroll
-          for (int j = 0; j < kChunks; ++j) {
-            const int c0 = (2 * j + par) * 32;
-            if (c0 < CR) {
-              const __nv_bfloat16* rp = a.res + off + c0;
-              ldg_nc_256(rp, &rres[j][0]);
-              if (c0 + 16 < a.cout_s) ldg_nc_256(rp + 16, &rres[j][8]);
-            }
-          }
-        }
-        if (sub == 0) {
-          mbar_wait(&tmem_full[acc], acc_phase);
-          tc_fence_after_sync();
-        }
+          for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
-        for (int j = 0; j < kChunks; ++j) {
+            for (int j = 0; j < kChunks; ++j)
+              if ((2 * j + par) * 32 < CR) prefetch_l2(rp + (size_t)(sub * 8) * a.cout_s + (2 * j + par) * 32);
+        }
+        auto finish = [&](int sub, int j, const uint32_t (&r)[32], const uint32_t (&rr)[16]) {
           const int c0 = (2 * j + par) * 32;
-          if (c0 >= a.cout_s) continue;   // these channels do not exist in memory (compact storage)
-          __nv_bfloat16* op = a.out + off + c0;
+          __nv_bfloat16* op = a.out + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
           uint32_t pk[16];
-          if (c0 >= CR) {   // pure padding chunk (warp-uniform)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) pk[q] = 0u;
-            stg_256(op, &pk[0]);
-            if (c0 + 16 < a.cout_s) stg_256(op + 16, &pk[8]);
-            continue;
-          }
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub) * CP + c0), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (c0 + 4 * q >= CR) {   // columns past N = CR were never written by the MMA
-              pk[2 * q] = 0u;
-              pk[2 * q + 1] = 0u;
+          for (int q = 0; q < 16; ++q) {
+            const int c = c0 + 2 * q;
+            if (c >= CR) {   // columns past N = CR were never written by the MMA (compile-time for a given chunk)
+              pk[q] = 0u;
               continue;
             }
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
-            float v0 = __uint_as_float(r[4 * q]) + b4.x, v1 = __uint_as_float(r[4 * q + 1]) + b4.y;
-            float v2 = __uint_as_float(r[4 * q + 2]) + b4.z, v3 = __uint_as_float(r[4 * q + 3]) + b4.w;
-            if (a.res != nullptr && c0 + 4 * q < a.cout_s) {
-              const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j][2 * q]));
-              const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[j][2 * q + 1]));
-              v0 += f0.x, v1 += f0.y, v2 += f1.x, v3 += f1.y;
+            float v0 = __uint_as_float(r[2 * q]), v1 = __uint_as_float(r[2 * q + 1]);
+            if constexpr (kRegBias) {
+              v0 += bias_r[2 * q], v1 += bias_r[2 * q + 1];
+            } else {
+              const float2 b2 = *reinterpret_cast<const float2*>(s_bias + c);
+              v0 += b2.x, v1 += b2.y;
             }
-            if (a.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
-            pk[2 * q] = pack_bf16x2(v0, v1);
-            pk[2 * q + 1] = pack_bf16x2(v2, v3);
+            if (a.res != nullptr) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[q]));
+              v0 += f.x, v1 += f.y;
+            }
+            pk[q] = a.relu ? pack_bf16x2_relu(v0, v1) : pack_bf16x2(v0, v1);
           }
           stg_256(op, &pk[0]);
           if (c0 + 16 < a.cout_s) stg_256(op + 16, &pk[8]);
+        };
+        auto load_res = [&](int sub, int j, uint32_t (&rr)[16]) {
+          const int c0 = (2 * j + par) * 32;
+          const __nv_bfloat16* rp = a.res + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
+          ldg_nc_256(rp, &rr[0]);
+          if (c0 + 16 < a.cout_s) ldg_nc_256(rp + 16, &rr[8]);
+        };
+        auto zero_chunk = [&](int sub, int j) {   // pure padding chunk inside the stored channels
+          const int c0 = (2 * j + par) * 32;
+          __nv_bfloat16* op = a.out + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
+          uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          stg_256(op, z);
+          if (c0 + 16 < a.cout_s) stg_256(op + 16, z);
+        };
+        const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 2 * CP + par * 32);
+        if constexpr (kBothSubs) {
+          uint32_t rr[2][16], r[2][32];
+          if (a.res != nullptr) {
+            load_res(0, 0, rr[0]);
+            load_res(1, 0, rr[1]);
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after_sync();
+          tmem_ld32(tm, r[0]);
+          tmem_ld32(tm + CP, r[1]);
+          tmem_ld_wait();
+          finish(0, 0, r[0], rr[0]);
+          finish(1, 0, r[1], rr[1]);
+        } else {
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t rr[kChunks][16];
+            if (a.res != nullptr) {   // every shortcut load of this sub-tile is in flight before the accumulator is read
+#pragma unroll
+              for (int j = 0; j < kChunks; ++j)
+                if ((2 * j + par) * 32 < CR) load_res(sub, j, rr[j]);
+            }
+            if (sub == 0) {
+              mbar_wait(&tmem_full[acc], acc_phase);
+              tc_fence_after_sync();
+            }
+#pragma unroll
+            for (int j = 0; j < kChunks; ++j) {
+              const int c0 = (2 * j + par) * 32;
+              if (c0 >= CR) {
+                if (c0 < a.cout_s) zero_chunk(sub, j);
+                continue;
+              }
+              uint32_t r[32];
+              tmem_ld32(tm + (uint32_t)(sub * CP + 64 * j), r);
+              tmem_ld_wait();
+              finish(sub, j, r, rr[j]);
+            }
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == Cfg::kAccPairs) {
+          acc = 0;
+          acc_phase ^= 1;
         }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == Cfg::kAccPairs) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
+    };
+    if (((warp - 2) >> 2) == 0) body(std::integral_constant<int, 0>{});
+    else body(std::integral_constant<int, 1>{});
   }
 
   tc_fence_before_sync();

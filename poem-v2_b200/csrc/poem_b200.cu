@@ -388,7 +388,8 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2) || (ksize == 1 && stride != 1))
     return fail(POEM_E_BADDIM, "conv: unsupported kernel %d / stride %d", ksize, stride);
   // c_real: live output channels; c_real_in: live input channels (defaults to c_real, the C -> C BasicBlock case)
-  if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Hin == Win && Hin % 16 == 0 && !relu_before_res &&
+  if (g_conv_mode != 2 && ksize == 3 && stride == 1 && Hin == Win && Hin % 16 == 0 && ((Hin / 16) & (Hin / 16 - 1)) == 0 &&
+      !relu_before_res &&
       out != nullptr && out_f32 == nullptr) {
     bool handled = false;
     POEM_TRY(launch_conv3x3_halo(in, N, Hin, Cin_p, c_real_in >= 0 ? c_real_in : c_real, Cout_p, c_real, wt, relu, res, out,
