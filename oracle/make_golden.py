@@ -60,6 +60,52 @@ def run_reference(size, views, wseed, iseed, mode):
     return cap
 
 
+def run_reference_parametric(views, wseed, iseed, mseed=11):
+    """The real reference head built from config/release/train_medium_MANO.yaml (PARAMETRIC_OUTPUT): its own
+    `get_parametric_output` (pt_metro_transformer.py:139-151), `rot6d_to_aa` (utils/transform.py:448-466) and head
+    epilogue (ptEmb_head.py:950-963) run on the stub layer's restated third-party pieces (pytorch3d.transforms,
+    manotorch LBS on `synth.synthetic_mano()` stand-in parameters)."""
+    dims = release_dims("medium_MANO")
+    ref_shim.MANO_PARAMS = synth.synthetic_mano(mseed)
+    try:
+        head, _ = ref_shim.build_reference_head("medium_MANO", template_fn=synth.standin_template)
+        sd = synth.make_state_dict(dims, wseed, "stress")
+        ref_sd = dict(sd)
+        for i in range(dims.n_blocks - 1):       # the reference owns the tail layers in every block; only the last runs
+            for n in ("flat_verts.weight", "flat_verts.bias", "mano_linear.weight", "mano_linear.bias"):
+                ref_sd.setdefault(f"transformer.pt_metro_encoder.{i}.{n}",
+                                  torch.zeros_like(sd[f"transformer.pt_metro_encoder.{dims.n_blocks - 1}.{n}"]))
+        missing, unexpected = head.load_state_dict(ref_sd, strict=False)
+        assert not unexpected, unexpected
+        assert set(ref_sd).isdisjoint(missing)
+        feat, metas, ref_j = synth.make_inputs(dims, len(views), views, iseed)
+        cap = {}
+        last = head.transformer.pt_metro_encoder[dims.n_blocks - 1]
+        orig = last.get_parametric_output
+
+        def spy(verts_feat, verts):
+            cap["tail_feats"] = verts_feat.detach().clone()
+            cap["tail_xyz_in"] = verts.detach().clone()
+            return orig(verts_feat, verts)
+        last.get_parametric_output = spy
+        with torch.no_grad():
+            res = head(mlvl_feat=feat, img_metas=metas, reference_joints=ref_j, debug_metas=None)
+        cap.update(all_coords_preds=res["all_coords_preds"].detach().clone(), pred_pose=res["pred_pose"].detach().clone(),
+                   pred_shape=res["pred_shape"].detach().clone())
+        return cap
+    finally:
+        ref_shim.MANO_PARAMS = None
+
+
+def write_parametric_golden():
+    views, wseed, iseed, mseed = [2, 3], 2, 5, 11
+    cap = run_reference_parametric(views, wseed, iseed, mseed)
+    meta = dict(size="medium_MANO", views=views, wseed=wseed, iseed=iseed, mseed=mseed, mode="stress")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mano_medium_b2.npz"), meta=np.array(repr(meta)),
+                        **{k: v.numpy() for k, v in cap.items()})
+    print("mano_medium_b2", {k: tuple(v.shape) for k, v in cap.items()}, cap["pred_pose"][0, :2], cap["pred_shape"][0, :3])
+
+
 def _import_reference_hrnet():
     ref_shim.install(synth.standin_template)
     import lib.external.metro.hrnet  # noqa: F401  (bare package; the backbone imports its config from there)
@@ -177,6 +223,8 @@ def run_reference_stage4(n_images, wseed, iseed):
 
 def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "--only-mano" in sys.argv:
+        return write_parametric_golden()
     ys = run_reference_backbone(1, 0, 1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hrnet_w40_n1.npz"),
                         meta=np.array(repr(dict(kind="hrnet_w40", n_images=1, wseed=0, iseed=1, stride=4))),
@@ -199,6 +247,7 @@ def main():
                         y0=ys[0][:, :, ::4, ::4].numpy(), y1=ys[1][:, :, ::2, ::2].numpy(), y2=ys[2].numpy(),
                         y3=ys[3].numpy())
     print("hrnet_stage4_n2", [tuple(y.shape) for y in ys])
+    write_parametric_golden()
     for name, (size, views, wseed, iseed, mode) in CASES.items():
         cap = run_reference(size, views, wseed, iseed, mode)
         out = {

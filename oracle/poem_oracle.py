@@ -207,10 +207,130 @@ def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=N
     return out, xyz
 
 
+# ------------------------------------------------------------------------------------------ a16
+def rotation_6d_to_matrix(d6):
+    """pytorch3d v0.7.2 `transforms.rotation_6d_to_matrix` (third-party, absent offline — published algorithm of
+    Zhou et al. 2019): Gram-Schmidt on the two 3-vectors, rows (b1, b2, b1 x b2)."""
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = F.normalize(a1, dim=-1)
+    b2 = a2 - (b1 * a2).sum(-1, keepdim=True) * b1
+    b2 = F.normalize(b2, dim=-1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    return torch.stack((b1, b2, b3), dim=-2)
+
+
+def matrix_to_quaternion(m):
+    """pytorch3d v0.7.2 `transforms.matrix_to_quaternion` (real part first): four candidate quaternions, the one
+    with the largest denominator is taken (no sign standardisation in this version)."""
+    batch = m.shape[:-2]
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = torch.unbind(m.reshape(batch + (9,)), dim=-1)
+    pos = torch.stack([1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22, 1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22],
+                      dim=-1)
+    q_abs = torch.where(pos > 0, torch.sqrt(pos.clamp_min(0)), torch.zeros_like(pos))
+    cand = torch.stack([
+        torch.stack([q_abs[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01], dim=-1),
+        torch.stack([m21 - m12, q_abs[..., 1] ** 2, m10 + m01, m02 + m20], dim=-1),
+        torch.stack([m02 - m20, m10 + m01, q_abs[..., 2] ** 2, m12 + m21], dim=-1),
+        torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[..., 3] ** 2], dim=-1)], dim=-2)
+    cand = cand / (2.0 * q_abs[..., None].clamp_min(0.1))
+    pick = q_abs.argmax(dim=-1)
+    return torch.gather(cand, -2, pick[..., None, None].expand(batch + (1, 4))).squeeze(-2)
+
+
+def quaternion_to_axis_angle(q):
+    """pytorch3d v0.7.2 `transforms.quaternion_to_axis_angle`."""
+    norms = torch.norm(q[..., 1:], p=2, dim=-1, keepdim=True)
+    half = torch.atan2(norms, q[..., :1])
+    ang = 2 * half
+    small = ang.abs() < 1e-6
+    k = torch.empty_like(ang)
+    k[~small] = torch.sin(half[~small]) / ang[~small]
+    k[small] = 0.5 - (ang[small] * ang[small]) / 48
+    return q[..., 1:] / k
+
+
+def rot6d_to_aa(r6):
+    """lib/utils/transform.py:448-466: Compose([rotation_6d_to_matrix, matrix_to_quaternion,
+    quaternion_to_axis_angle])."""
+    return quaternion_to_axis_angle(matrix_to_quaternion(rotation_6d_to_matrix(r6)))
+
+
+def axis_angle_to_rotmat(aa):
+    """Rodrigues through a unit quaternion, as manopth/manotorch do (`batch_rodrigues`: norm of aa + 1e-8, half
+    angle, quaternion -> matrix).  Third-party (manotorch v0.0.2), restated from the published algorithm."""
+    ang = torch.norm(aa + 1e-8, p=2, dim=-1, keepdim=True)
+    axis = aa / ang
+    q = torch.cat([torch.cos(0.5 * ang), torch.sin(0.5 * ang) * axis], dim=-1)
+    q = q / q.norm(p=2, dim=-1, keepdim=True)
+    w, x, y, z = q.unbind(-1)
+    w2, x2, y2, z2 = w * w, x * x, y * y, z * z
+    wx, wy, wz, xy, xz, yz = w * x, w * y, w * z, x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=-1).reshape(aa.shape[:-1] + (3, 3))
+
+
+def mano_forward(mano, pose_aa, betas, center_idx=None):
+    """manotorch v0.0.2 `ManoLayer(rot_mode="axisang", use_pca=False, flat_hand_mean=True, center_idx=...)` —
+    the MANO linear-blend-skinning forward (Romero et al. 2017; third-party, absent offline, restated):
+    shape blend -> joints -> pose blend -> kinematic chain -> skinning -> 16 joints + 5 tip vertices reordered to
+    the 21-joint convention -> optional root-centring.  `mano`: dict of `synth.synthetic_mano()` roles.
+    Returns verts (B,778,3), joints (B,21,3)."""
+    from poem_v2_b200.synth import MANO_JOINT_ORDER, MANO_PARENTS, MANO_TIP_VERTS
+    B = pose_aa.shape[0]
+    R = axis_angle_to_rotmat(pose_aa.reshape(B, 16, 3))                         # (B,16,3,3)
+    pose_map = (R[:, 1:] - torch.eye(3, dtype=R.dtype)).reshape(B, 135)
+    v_shaped = mano["v_template"][None] + torch.einsum("vck,bk->bvc", mano["shapedirs"], betas)
+    J = torch.einsum("jv,bvc->bjc", mano["J_regressor"], v_shaped)              # (B,16,3)
+    v_posed = v_shaped + torch.einsum("vck,bk->bvc", mano["posedirs"], pose_map)
+    G = [None] * 16
+    for j in range(16):
+        T = torch.zeros(B, 4, 4, dtype=R.dtype)
+        T[:, :3, :3] = R[:, j]
+        T[:, 3, 3] = 1.0
+        par = MANO_PARENTS[j]
+        if par < 0:
+            T[:, :3, 3] = J[:, j]
+            G[j] = T
+        else:
+            T[:, :3, 3] = J[:, j] - J[:, par]
+            G[j] = G[par] @ T
+    G = torch.stack(G, dim=1)                                                   # (B,16,4,4)
+    A = G.clone()
+    A[..., :3, 3] = G[..., :3, 3] - torch.einsum("bjrc,bjc->bjr", G[..., :3, :3], J)   # remove the rest pose
+    Tv = torch.einsum("vj,bjrc->bvrc", mano["weights"], A)                      # (B,778,4,4)
+    vh = torch.cat([v_posed, torch.ones(B, 778, 1, dtype=R.dtype)], dim=-1)
+    verts = torch.einsum("bvrc,bvc->bvr", Tv, vh)[..., :3]
+    jtr = torch.cat([G[..., :3, 3], verts[:, list(MANO_TIP_VERTS)]], dim=1)[:, list(MANO_JOINT_ORDER)]
+    if center_idx is not None:
+        c = jtr[:, center_idx:center_idx + 1]
+        jtr, verts = jtr - c, verts - c
+    return verts, jtr
+
+
+def parametric_tail(sd, i, dims, feats, xyz, mano):
+    """`point_METRO_block.get_parametric_output` (lib/models/bricks/pt_metro_transformer.py:139-151): the
+    (B,799,D) features are RE-INTERPRETED as (B*D,799) rows (not transposed), Linear(799,1), Linear(D,106),
+    16 x 6-D rotations -> axis-angle, MANO forward; joints and vertices of `xyz` are overwritten."""
+    p = f"transformer.pt_metro_encoder.{i}."
+    D = dims.embed_dims
+    flat = F.linear(feats.reshape(-1, dims.n_query), sd[p + "flat_verts.weight"], sd[p + "flat_verts.bias"])
+    par = F.linear(flat.reshape(-1, D), sd[p + "mano_linear.weight"], sd[p + "mano_linear.bias"])
+    pose = rot6d_to_aa(par[:, :96].reshape(-1, 16, 6)).reshape(-1, 48)
+    betas = par[:, 96:]
+    verts, joints = mano_forward(mano, pose, betas, dims.center_idx)
+    xyz = xyz.clone()
+    xyz[:, 21:] = verts
+    xyz[:, :21] = joints
+    return xyz, pose, betas
+
+
 # ------------------------------------------------------------------------------------------ a1
-def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anchor_xyz, anchor_idx, stages=None):
-    """`POEM_Generalized_Head.forward` (lib/models/heads/ptEmb_head.py:825-964), non-parametric output.
-    Returns all_coords_preds (NB,B,799,3) in metres."""
+def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anchor_xyz, anchor_idx, stages=None,
+                 mano=None):
+    """`POEM_Generalized_Head.forward` (lib/models/heads/ptEmb_head.py:825-964).
+    Returns all_coords_preds (NB,B,799,3) in metres; with `dims.parametric` (medium_MANO) the last block goes
+    through the MANO tail and (coords, pred_pose (B,16,3), pred_shape (B,10)) is returned."""
     views = [int(v) for v in img_metas["cam_view_num"]]
     B = len(views)
     inp_w, inp_h = img_metas["inp_img_shape"]
@@ -230,11 +350,19 @@ def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anc
     xyz_all = []
     for i in range(dims.n_blocks):
         q_feats, q_xyz = metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages)
+        if dims.parametric and i == dims.n_blocks - 1:          # pt_metro_transformer.py:194-195
+            if stages is not None:
+                stages["tail.feats"], stages["tail.xyz_in"] = q_feats, q_xyz
+            q_xyz, pose, betas = parametric_tail(sd, i, dims, q_feats, q_xyz, mano)
         xyz_all.append(q_xyz)
     coords = torch.nan_to_num(torch.stack(xyz_all))
     if stages is not None:
         stages["xyz_norm"] = coords
-    return coords * dims.radius + centre[None, :, None, :]
+    if not dims.parametric:
+        return coords * dims.radius + centre[None, :, None, :]
+    # ptEmb_head.py:950-963: the MANO output of the last block is metric already, only the offset is added
+    out = torch.cat([coords[:-1] * dims.radius, coords[-1:]]) + centre[None, :, None, :]
+    return out, pose.reshape(-1, 16, 3), betas.reshape(-1, 10)
 
 
 # ------------------------------------------------------------------------------------------ a17

@@ -11,7 +11,10 @@ where stated):
   * pytorch3d.ops.knn_points  : squared-L2 + topk(smallest, sorted) restatement (third-party,
     pytorch3d v0.7.2 `knn_points`, not vendored by the reference) — ARITHMETIC, unpinned
   * manotorch.ManoLayer       : returns the seeded stand-in template (MANO assets are licensed
-    and absent) — parity with real MANO is unpinned
+    and absent) — parity with real MANO is unpinned; for the parametric tail (medium_MANO) it runs
+    the restated LBS forward on seeded stand-in parameters (`MANO_PARAMS`)
+  * pytorch3d.transforms      : rotation_6d_to_matrix / matrix_to_quaternion / quaternion_to_axis_angle
+    restated (v0.7.2, third-party) — ARITHMETIC, unpinned; cross-checked against SciPy in tests
   * transformers 5.x -> 4.x   : BertAttention adapter that restores 4.x cross-attention
     semantics (`encoder_hidden_states` => K/V source, no mask)
 
@@ -130,6 +133,7 @@ def _knn_points(p1, p2, K=1, return_nn=False, **kw):
 
 
 _installed = False
+MANO_PARAMS = None   # set to a `synth.synthetic_mano()` dict to make the stub ManoLayer a real LBS forward
 
 
 def install(template_fn=None):
@@ -162,11 +166,21 @@ def install(template_fn=None):
               "matrix_to_quaternion", "matrix_to_rotation_6d", "quaternion_to_axis_angle", "quaternion_to_matrix",
               "rotation_6d_to_matrix"]:
         setattr(p3t, n, _raise)
+    # the three the parametric tail composes (lib/utils/transform.py:448-466): restated in poem_oracle (third-party
+    # arithmetic, pytorch3d v0.7.2, unpinned) — the reference's own `rot6d_to_aa` / `get_parametric_output` run on them
+    import poem_oracle as _orc
+    p3t.rotation_6d_to_matrix = _orc.rotation_6d_to_matrix
+    p3t.matrix_to_quaternion = _orc.matrix_to_quaternion
+    p3t.quaternion_to_axis_angle = _orc.quaternion_to_axis_angle
 
     # manotorch
     import manotorch.manolayer as ml
 
     class ManoLayer(torch.nn.Module):
+        """Without MANO_PARAMS: returns the fixed seeded template.  With MANO_PARAMS (a `synth.synthetic_mano()`
+        dict): the restated manotorch forward (`poem_oracle.mano_forward`) on those stand-in parameters, so the
+        reference's parametric tail runs end to end."""
+
         def __init__(self, *a, **k):
             super().__init__()
             t = template_fn() if template_fn is not None else torch.zeros(799, 3)
@@ -174,9 +188,15 @@ def install(template_fn=None):
             self.register_buffer("_verts", t[None, 21:].clone(), persistent=False)
             self.th_faces = torch.zeros(1538, 3, dtype=torch.long)
             self.th_J_regressor = torch.zeros(16, 778)
+            self.center_idx = k.get("center_idx")
 
         def forward(self, pose, betas=None, **k):
             n = pose.shape[0]
+            if MANO_PARAMS is not None:
+                if betas is None:
+                    betas = torch.zeros(n, 10)
+                v, j = _orc.mano_forward(MANO_PARAMS, pose, betas, self.center_idx)
+                return types.SimpleNamespace(verts=v, joints=j)
             return types.SimpleNamespace(verts=self._verts.repeat(n, 1, 1), joints=self._joints.repeat(n, 1, 1))
     ml.ManoLayer = ManoLayer
 

@@ -35,6 +35,29 @@ def standin_template(seed: int = 7) -> torch.Tensor:
     return t - t[9:10]
 
 
+# MANO kinematic tree (parent of each of the 16 joints) and the fingertip vertices manotorch appends for a right hand
+MANO_PARENTS = (-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14)
+MANO_TIP_VERTS = (745, 317, 444, 556, 673)
+# manotorch's 16 joints + 5 tips -> the 21-joint hand order
+MANO_JOINT_ORDER = (0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20)
+
+
+def synthetic_mano(seed: int = 11):
+    """Seeded stand-in for the MANO model parameters (the licensed `assets/mano_v1_2` pickles are absent offline):
+    same tensor shapes and roles as manotorch's `th_*` buffers, hand-sized magnitudes (metres).  Used by BOTH the
+    reference run that writes the parametric golden and by our head, so the parametric tail
+    is exercised end to end; parity with the real MANO data is unpinned."""
+    g = torch.Generator().manual_seed(seed)
+    v = 0.05 * torch.randn(778, 3, generator=g)
+    return {
+        "v_template": v.contiguous(),
+        "shapedirs": (0.004 * torch.randn(778, 3, 10, generator=g)).contiguous(),
+        "posedirs": (0.002 * torch.randn(778, 3, 135, generator=g)).contiguous(),
+        "J_regressor": torch.softmax(3.0 * torch.randn(16, 778, generator=g), dim=1).contiguous(),
+        "weights": torch.softmax(4.0 * torch.randn(778, 16, generator=g), dim=1).contiguous(),
+    }
+
+
 def _view_list(B, V):
     return [int(V)] * B if isinstance(V, (int, np.integer)) else [int(v) for v in V]
 
