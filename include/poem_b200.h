@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define POEM_ABI_VERSION 1
+#define POEM_ABI_VERSION 2
 
 #define POEM_OK 0
 #define POEM_E_BADDIM (-1)      /* unsupported / inconsistent dimensions */
@@ -151,6 +151,42 @@ size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);
  *   out_feats  : optional fp32 [B, Q, D] output of the last block's FFN (needs dims->run_last_ffn) or NULL */
 int poem_head_forward(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
                       float* out_feats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Parametric output (config/release/train_medium_MANO.yaml: TRANSFORMER.PARAMETRIC_OUTPUT), SURVEY §8a row a16.
+ * Replaces point_METRO_block.get_parametric_output (pt_metro_transformer.py:139-151) of the LAST block, rot6d_to_aa
+ * (utils/transform.py:448-466) and the manotorch ManoLayer forward it calls (axis-angle, no PCA, flat hand mean,
+ * centred on joint dims->center_idx).  All tensors fp32 on the device; the MANO model parameters are the layer's
+ * `th_*` buffers re-laid so that the blend loops read consecutive vertices:
+ *   shapedirs [10, 778*3]  (= th_shapedirs (778,3,10) with the coefficient axis first),
+ *   posedirs  [135, 778*3] (= th_posedirs (778,3,135) likewise). */
+typedef struct PoemManoTail {
+  const float* flat_w;        /* flat_verts.weight [Q] */
+  const float* flat_b;        /* flat_verts.bias   [1] */
+  const float* lin_w;         /* mano_linear.weight [106, D] */
+  const float* lin_b;         /* mano_linear.bias   [106] */
+  const float* v_template;    /* [778, 3] */
+  const float* shapedirs;     /* [10, 778*3] */
+  const float* posedirs;      /* [135, 778*3] */
+  const float* j_regressor;   /* [16, 778] */
+  const float* skin_weights;  /* [778, 16] */
+} PoemManoTail;
+
+/* Stage-level: query_feats [B,Q,D] (output of the last block, re-interpreted as (B*D, Q) rows like the reference) ->
+ *   coords     [B,Q,3]: 21 MANO joints then 778 vertices, centred on joint center_idx, nan_to_num'd, plus
+ *                       reference_joints[b, center_idx] when `reference_joints` ([B,21,3]) is not NULL;
+ *   pred_pose  [B,48] axis-angle, pred_shape [B,10].
+ * workspace: poem_parametric_tail_workspace_bytes(dims, batch) bytes. */
+size_t poem_parametric_tail_workspace_bytes(const PoemDims* dims, int batch);
+int poem_parametric_tail(const PoemDims* dims, const PoemManoTail* mano, int batch, const float* query_feats,
+                         const float* reference_joints, float* coords, float* pred_pose, float* pred_shape,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* poem_head_forward for a PARAMETRIC_OUTPUT head (ptEmb_head.py:950-963): blocks 0..NB-2 give xyz*radius + centre, the
+ * last block's joints/vertices come from the MANO tail (+ centre, not scaled).  Same workspace as poem_head_forward.
+ * out_coords [NB,B,Q,3]; pred_pose [B,48] (`pred_pose` reshaped (B,16,3)); pred_shape [B,10]. */
+int poem_head_forward_parametric(const PoemDims* dims, const PoemWeights* w, const PoemManoTail* mano,
+                                 const PoemInputs* in, float* out_coords, float* pred_pose, float* pred_shape,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Decoder blocks only.  Replaces PtEmbedTRv4.forward(query_xyz, query_feat, pt_xyz, pt_feats)
  * (ptEmb_transformer.py:371-376): all inputs fp32 device buffers in normalised (radius) units,

@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpoem_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["poem_b200.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh", "hrnet.cuh"]
+HEADERS = ["common.cuh", "gemm.cuh", "conv3x3.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh", "hrnet.cuh", "mano.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 
@@ -81,6 +81,12 @@ class PoemWeights(C.Structure):
                 ("blocks", PoemBlock * POEM_MAX_BLOCKS)]
 
 
+class PoemManoTail(C.Structure):
+    _fields_ = [("flat_w", C.c_void_p), ("flat_b", C.c_void_p), ("lin_w", C.c_void_p), ("lin_b", C.c_void_p),
+                ("v_template", C.c_void_p), ("shapedirs", C.c_void_p), ("posedirs", C.c_void_p),
+                ("j_regressor", C.c_void_p), ("skin_weights", C.c_void_p)]
+
+
 POEM_HR_MAX_MODULES = 4
 
 
@@ -123,7 +129,8 @@ EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_
            "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_triangulate_dlt", "poem_pa_metrics", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
-           "poem_vector_attention_workspace_bytes", "poem_layernorm"]
+           "poem_vector_attention_workspace_bytes", "poem_layernorm", "poem_parametric_tail_workspace_bytes",
+           "poem_parametric_tail", "poem_head_forward_parametric"]
 
 _lib = None
 
@@ -161,6 +168,13 @@ def load():
     lib.poem_head_forward_host.restype = i
     lib.poem_head_forward_host.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), C.POINTER(PoemInputs), vp, vp,
                                            sz, vp, sz, vp]
+    lib.poem_parametric_tail_workspace_bytes.restype = sz
+    lib.poem_parametric_tail_workspace_bytes.argtypes = [C.POINTER(PoemDims), i]
+    lib.poem_parametric_tail.restype = i
+    lib.poem_parametric_tail.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemManoTail), i, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.poem_head_forward_parametric.restype = i
+    lib.poem_head_forward_parametric.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), C.POINTER(PoemManoTail),
+                                                 C.POINTER(PoemInputs), vp, vp, vp, vp, sz, vp]
     lib.poem_transformer_workspace_bytes.restype = sz
     lib.poem_transformer_workspace_bytes.argtypes = [C.POINTER(PoemDims), i]
     lib.poem_transformer_forward.restype = i

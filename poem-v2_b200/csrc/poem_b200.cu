@@ -16,6 +16,7 @@
 #include "hrnet.cuh"
 #include "simt.cuh"
 #include "vecattn.cuh"
+#include "mano.cuh"
 
 using namespace poem;
 
@@ -1409,8 +1410,75 @@ extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights*
   return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, /*pt_is_bps=*/false, st);
 }
 
+// a16: flat_verts + mano_linear + rot6d -> axis-angle + MANO forward; `flat` is B*D floats of scratch.
+static int launch_parametric_tail(const PoemDims* dims, const PoemManoTail* m, int B, const float* feats,
+                                  const float* ref_joints, float* coords, float* pose, float* shape, float* flat,
+                                  cudaStream_t st) {
+  if (!m->flat_w || !m->flat_b || !m->lin_w || !m->lin_b || !m->v_template || !m->shapedirs || !m->posedirs ||
+      !m->j_regressor || !m->skin_weights)
+    return fail(POEM_E_NULL, "parametric tail: null weight / MANO parameter");
+  if (dims->n_query != 21 + kManoVerts) return fail(POEM_E_BADDIM, "parametric tail needs n_query = 799");
+  if (dims->center_idx < 0 || dims->center_idx >= 21) return fail(POEM_E_BADDIM, "center_idx=%d", dims->center_idx);
+  const int rows = B * dims->embed_dims;
+  prof_begin(st);
+  flat_verts_kernel<<<(unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, st>>>(feats, m->flat_w, m->flat_b, flat,
+                                                                                 dims->n_query, rows);
+  LAUNCH_CHECK("flat_verts_kernel");
+  ManoTailArgs a;
+  a.lin_w = m->lin_w, a.lin_b = m->lin_b;
+  a.v_template = m->v_template, a.shapedirs = m->shapedirs, a.posedirs = m->posedirs;
+  a.j_regressor = m->j_regressor, a.skin_weights = m->skin_weights;
+  a.flat = flat, a.ref_joints = ref_joints;
+  a.coords = coords, a.pose_out = pose, a.shape_out = shape;
+  a.D = dims->embed_dims, a.center_idx = dims->center_idx;
+  prof_begin(st);
+  mano_tail_kernel<<<B, 256, 0, st>>>(a);
+  LAUNCH_CHECK("mano_tail_kernel");
+  return POEM_OK;
+}
+
+extern "C" size_t poem_parametric_tail_workspace_bytes(const PoemDims* dims, int batch) {
+  if (check_dims(dims) != POEM_OK || batch < 1) return 0;
+  return (size_t)batch * dims->embed_dims * sizeof(float) + 1024;
+}
+
+extern "C" int poem_parametric_tail(const PoemDims* dims, const PoemManoTail* mano, int batch, const float* query_feats,
+                                    const float* reference_joints, float* coords, float* pred_pose, float* pred_shape,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  POEM_TRY(check_dims(dims));
+  if (!mano || !query_feats || !coords || !pred_pose || !pred_shape || !workspace)
+    return fail(POEM_E_NULL, "parametric_tail: null pointer");
+  if (batch < 1) return fail(POEM_E_BADDIM, "batch=%d", batch);
+  if (workspace_bytes < (size_t)batch * dims->embed_dims * sizeof(float))
+    return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes,
+                (size_t)batch * dims->embed_dims * sizeof(float));
+  return launch_parametric_tail(dims, mano, batch, query_feats, reference_joints, coords, pred_pose, pred_shape,
+                                reinterpret_cast<float*>(workspace), (cudaStream_t)stream);
+}
+
+static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
+                             float* out_feats, const PoemManoTail* mano, float* pred_pose, float* pred_shape,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
                                  float* out_feats, void* workspace, size_t workspace_bytes, void* stream) {
+  return head_forward_impl(dims, w, in, out_coords, out_feats, nullptr, nullptr, nullptr, workspace, workspace_bytes,
+                           stream);
+}
+
+extern "C" int poem_head_forward_parametric(const PoemDims* dims, const PoemWeights* w, const PoemManoTail* mano,
+                                            const PoemInputs* in, float* out_coords, float* pred_pose,
+                                            float* pred_shape, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dims || !mano || !pred_pose || !pred_shape) return fail(POEM_E_NULL, "head_forward_parametric: null pointer");
+  PoemDims d = *dims;
+  d.run_last_ffn = 1;   // the tail reads the last block's feed-forward output
+  return head_forward_impl(&d, w, in, out_coords, nullptr, mano, pred_pose, pred_shape, workspace, workspace_bytes,
+                           stream);
+}
+
+static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const PoemInputs* in, float* out_coords,
+                             float* out_feats, const PoemManoTail* mano, float* pred_pose, float* pred_shape,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   POEM_TRY(check_dims(dims));
   if (!w || !in || !out_coords || !workspace) return fail(POEM_E_NULL, "head_forward: null pointer");
   if (!in->view_counts || !in->mlvl_feat || !in->cam_intr || !in->cam_extr || !in->reference_joints)
@@ -1512,7 +1580,13 @@ extern "C" int poem_head_forward(const PoemDims* dims, const PoemWeights* w, con
     LAUNCH_CHECK("broadcast_queries_kernel");
   }
   // ---- a8-a15
-  return run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, /*pt_is_bps=*/true, st);
+  POEM_TRY(run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, /*pt_is_bps=*/true, st));
+  // ---- a16: the last block's joints / vertices are replaced by the MANO output (tmp32 is free after the last LayerNorm)
+  if (mano)
+    POEM_TRY(launch_parametric_tail(dims, mano, B, out_feats ? out_feats : p.qf32, in->reference_joints,
+                                    out_coords + (size_t)(dims->n_blocks - 1) * BQ * 3, pred_pose, pred_shape, p.tmp32,
+                                    st));
+  return POEM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ import torch.nn as nn
 from . import _native as nat
 from . import synth
 from .config import HeadDims, dims_from_cfg
-from .pack import PackedWeights
+from .pack import MANO_KEYS, PackedManoTail, PackedWeights, mano_zero_pose_template
 
 MAX_VIEWS = 10   # reference README: evaluated with 1..8 (up to 10 in the view sweep) cameras per sample
 
@@ -33,27 +33,53 @@ class _Tree(nn.Module):
         self._modules[head].add(rest, tensor)
 
 
+def _manotorch_layer(dims):
+    from manotorch.manolayer import ManoLayer  # type: ignore
+    return ManoLayer(joint_rot_mode="axisang", use_pca=False, mano_assets_root="assets/mano_v1_2",
+                     center_idx=dims.center_idx, flat_hand_mean=True)
+
+
 def _resolve_template(dims, template):
     if template is not None:
         t = torch.as_tensor(template, dtype=torch.float32).reshape(dims.n_query, 3)
         return t
     try:  # the reference builds it from manotorch on every forward (ptEmb_head.py:886-894)
-        from manotorch.manolayer import ManoLayer  # type: ignore
-        layer = ManoLayer(joint_rot_mode="axisang", use_pca=False, mano_assets_root="assets/mano_v1_2",
-                          center_idx=dims.center_idx, flat_hand_mean=True)
-        out = layer(torch.zeros(1, 48), torch.zeros(1, 10))
+        out = _manotorch_layer(dims)(torch.zeros(1, 48), torch.zeros(1, 10))
         return torch.cat([out.joints, out.verts], dim=1)[0].float()
     except Exception as e:  # noqa: BLE001
         raise RuntimeError("MANO template unavailable (manotorch / assets/mano_v1_2 missing): pass "
                            "`template_mesh=(799,3)` to the head or call `set_template()`") from e
 
 
+def _resolve_mano(dims, mano):
+    """MANO model parameters for the parametric tail: a dict with MANO_KEYS (roles of manotorch's `th_*` buffers),
+    else the buffers of an installed manotorch layer."""
+    if mano is None:
+        try:
+            layer = _manotorch_layer(dims)
+            mano = {k: getattr(layer, "th_" + k) for k in MANO_KEYS}
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError("MANO parameters unavailable (manotorch / assets/mano_v1_2 missing): pass `mano_params=` "
+                               "(dict with v_template, shapedirs, posedirs, J_regressor, weights), call `set_mano()`, "
+                               "or load a checkpoint that carries the `mano_layer.th_*` buffers") from e
+    missing = [k for k in MANO_KEYS if k not in mano]
+    if missing:
+        raise KeyError(f"mano_params lacks {missing}")
+    out = {k: torch.as_tensor(mano[k], dtype=torch.float32) for k in MANO_KEYS}
+    assert out["v_template"].numel() == 778 * 3 and out["shapedirs"].numel() == 778 * 3 * 10
+    assert out["posedirs"].numel() == 778 * 3 * 135 and out["J_regressor"].numel() == 16 * 778
+    assert out["weights"].numel() == 778 * 16
+    return out
+
+
 class _NativeDecoder(nn.Module):
     """Parameters under the reference's names + lazily packed kernel weights + workspace cache."""
 
-    def __init__(self, dims: HeadDims, key_prefix: str, template_mesh=None):
+    def __init__(self, dims: HeadDims, key_prefix: str, template_mesh=None, mano_params=None):
         super().__init__()
         self.dims = dims
+        self._mano = None if mano_params is None else _resolve_mano(dims, mano_params)
+        self._packed_mano = None
         self._key_prefix = key_prefix           # "" for the head, "transformer." stripped for PtEmbedTRv4
         shapes = synth.live_param_shapes(dims)
         self._live = []
@@ -85,6 +111,11 @@ class _NativeDecoder(nn.Module):
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
                               error_msgs):
         live = {prefix + k for k in self._live}
+        if self.dims.parametric and self._mano is None:    # a reference checkpoint carries the MANO layer's buffers
+            tag = f"pt_metro_encoder.{self.dims.n_blocks - 1}.mano_layer.th_"
+            found = {k.rsplit("th_", 1)[1]: v for k, v in state_dict.items() if k.startswith(prefix) and tag in k}
+            if all(k in found for k in MANO_KEYS):
+                self.set_mano(found)
         for k in [k for k in state_dict if k.startswith(prefix) and k not in live]:
             del state_dict[k]
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
@@ -94,6 +125,20 @@ class _NativeDecoder(nn.Module):
         self._template = _resolve_template(self.dims, template_mesh)
         self._packed = None
 
+    def set_mano(self, mano_params):
+        """MANO model parameters of the parametric tail (roles of manotorch's `th_*` buffers)."""
+        self._mano = _resolve_mano(self.dims, mano_params)
+        self._packed = self._packed_mano = None
+
+    def packed_mano(self, device):
+        self.packed(device)                                  # refreshes the cache key
+        if self._packed_mano is None:
+            if self._mano is None:
+                self._mano = _resolve_mano(self.dims, None)
+            sd = {self._key_prefix + k: v for k, v in self.state_dict().items()}
+            self._packed_mano = PackedManoTail(sd, self.dims, self._mano, device)
+        return self._packed_mano
+
     def live_state(self):
         sd = self.state_dict()
         return {self._key_prefix + k: sd[k] for k in self._live}
@@ -102,8 +147,12 @@ class _NativeDecoder(nn.Module):
         params = [p for p in self.parameters()]
         key = (str(device), tuple((p.data_ptr(), p._version) for p in params))
         if self._packed is None or self._packed_key != key:
+            self._packed_mano = None
             if self._template is None:
-                self._template = _resolve_template(self.dims, None)
+                if self.dims.parametric and self._mano is not None:
+                    self._template = mano_zero_pose_template(self._mano, self.dims.center_idx)
+                else:
+                    self._template = _resolve_template(self.dims, None)
             full = {}
             for name, shape in synth.live_param_shapes(self.dims).items():   # head-only keys absent for the TR class
                 full[name] = torch.zeros(shape)
@@ -129,13 +178,11 @@ class POEM_Generalized_Head(_NativeDecoder):
     """Drop-in for the reference head: `forward(mlvl_feat, img_metas, reference_joints, **kwargs)` ->
     {"all_coords_preds": (NB,B,799,3) metres}."""
 
-    def __init__(self, cfg, template_mesh=None):
+    def __init__(self, cfg, template_mesh=None, mano_params=None):
         dims = cfg if isinstance(cfg, HeadDims) else dims_from_cfg(cfg)
-        super().__init__(dims, "", template_mesh)
+        super().__init__(dims, "", template_mesh, mano_params)
         self.num_preds = dims.n_blocks            # read by the model shell (reference POEM.py:115)
         self.parametric_output = dims.parametric
-        if dims.parametric:
-            raise NotImplementedError("PARAMETRIC_OUTPUT (medium_MANO tail) is not built yet: needs the MANO layer")
 
     @torch.no_grad()
     def forward(self, mlvl_feat, img_metas, reference_joints, **kwargs):
@@ -167,9 +214,18 @@ class POEM_Generalized_Head(_NativeDecoder):
         inp = nat.PoemInputs(B, NV, views.ctypes.data, feat.data_ptr(), intr.data_ptr(), extr.data_ptr(),
                              refj.data_ptr(), float(inp_w), float(inp_h))
         stream = torch.cuda.current_stream(dev).cuda_stream
-        nat.check(lib.poem_head_forward(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), None, ws_ptr,
-                                        ws_bytes, stream))
-        return {"all_coords_preds": out}
+        if not d.parametric:
+            nat.check(lib.poem_head_forward(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), None, ws_ptr,
+                                            ws_bytes, stream))
+            return {"all_coords_preds": out}
+        # medium_MANO: the last block's joints / vertices come from the MANO tail (ptEmb_head.py:950-963)
+        pm = self.packed_mano(dev)
+        pose = torch.empty(B, 16, 3, dtype=torch.float32, device=dev)
+        shape = torch.empty(B, 10, dtype=torch.float32, device=dev)
+        nat.check(lib.poem_head_forward_parametric(C.byref(cd), C.byref(pw.struct), C.byref(pm.struct), C.byref(inp),
+                                                   out.data_ptr(), pose.data_ptr(), shape.data_ptr(), ws_ptr, ws_bytes,
+                                                   stream))
+        return {"all_coords_preds": out, "pred_pose": pose, "pred_shape": shape}
 
     @torch.no_grad()
     def forward_host(self, mlvl_feat, img_metas, reference_joints, out=None):
@@ -205,7 +261,7 @@ class PtEmbedTRv4(_NativeDecoder):
     """Drop-in for the reference transformer: `forward(query_xyz, query_feat, pt_xyz, pt_feats)` ->
     (xyz (NB,B,799,3) normalised, pred_pose None, pred_shape None)."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, mano_params=None):
         if isinstance(cfg, HeadDims):
             dims = cfg
         else:
@@ -214,10 +270,8 @@ class PtEmbedTRv4(_NativeDecoder):
                             n_heads=int(g("NUM_ATTENTION_HEADS")), n_sample=int(g("BPS_FEAT_DIM")),
                             n_neighbor=int(g("N_NEIGHBOR")), parametric=bool(g("PARAMETRIC_OUTPUT", False)),
                             center_idx=int(g("TRANSFORMER_CENTER_IDX", 9)))
-        super().__init__(dims, "transformer.", template_mesh=torch.zeros(dims.n_query, 3))
+        super().__init__(dims, "transformer.", template_mesh=torch.zeros(dims.n_query, 3), mano_params=mano_params)
         self.name = type(self).__name__
-        if dims.parametric:
-            raise NotImplementedError("PARAMETRIC_OUTPUT is not built yet")
 
     @torch.no_grad()
     def forward(self, query_xyz, query_feat, pt_xyz, pt_feats):
@@ -227,16 +281,27 @@ class PtEmbedTRv4(_NativeDecoder):
         B = query_feat.shape[0]
         lib = nat.load()
         pw = self.packed(dev)
-        cd = nat.make_dims(d, MAX_VIEWS)
+        cd = nat.make_dims(d, MAX_VIEWS, run_last_ffn=d.parametric)
         need = lib.poem_transformer_workspace_bytes(C.byref(cd), B)
         ws_ptr, ws_bytes = self.workspace(need, dev)
         args = [t.to(dev, torch.float32).contiguous() for t in (query_xyz, query_feat.expand(B, -1, -1), pt_xyz, pt_feats)]
         out = torch.empty(d.n_blocks, B, d.n_query, 3, dtype=torch.float32, device=dev)
+        feats = torch.empty(B, d.n_query, d.embed_dims, dtype=torch.float32, device=dev) if d.parametric else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         nat.check(lib.poem_transformer_forward(C.byref(cd), C.byref(pw.struct), B, args[0].data_ptr(),
                                                args[1].data_ptr(), args[2].data_ptr(), args[3].data_ptr(),
-                                               out.data_ptr(), None, ws_ptr, ws_bytes, stream))
-        return out, None, None
+                                               out.data_ptr(), None if feats is None else feats.data_ptr(), ws_ptr,
+                                               ws_bytes, stream))
+        if not d.parametric:
+            return out, None, None
+        # pt_metro_transformer.py:194-195: the last block's xyz is overwritten by the (root-centred, metric) MANO output
+        pm = self.packed_mano(dev)
+        pose = torch.empty(B, 48, dtype=torch.float32, device=dev)
+        shape = torch.empty(B, 10, dtype=torch.float32, device=dev)
+        nat.check(lib.poem_parametric_tail(C.byref(cd), C.byref(pm.struct), B, feats.data_ptr(), None,
+                                           out[-1].data_ptr(), pose.data_ptr(), shape.data_ptr(), ws_ptr, ws_bytes,
+                                           stream))
+        return out, pose, shape
 
 
 def register_into(head_registry=None, transformer_registry=None):

@@ -19,7 +19,7 @@ _IMAGE_PREFIXES = ("img_backbone.", "feat_delayer.", "feat_in.", "uv_delayer.", 
 
 
 class PtEmbedMultiviewStereoV2(nn.Module):
-    def __init__(self, cfg, template_mesh=None, **kwargs):
+    def __init__(self, cfg, template_mesh=None, mano_params=None, **kwargs):
         super().__init__()
         self.name = type(self).__name__
         head_cfg = cfg if isinstance(cfg, HeadDims) else cfg.HEAD
@@ -27,7 +27,7 @@ class PtEmbedMultiviewStereoV2(nn.Module):
             bb = cfg.BACKBONE.TYPE
             if bb != "HRNet":
                 raise NotImplementedError(f"backbone {bb}: only the HRNet-W40 release configuration is built")
-        self.ptEmb_head = POEM_Generalized_Head(head_cfg, template_mesh=template_mesh)
+        self.ptEmb_head = POEM_Generalized_Head(head_cfg, template_mesh=template_mesh, mano_params=mano_params)
         self.image_stage = ImageStage()
         self.num_joints = 21
         self.center_idx = self.ptEmb_head.dims.center_idx

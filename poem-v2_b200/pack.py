@@ -182,3 +182,44 @@ class PackedWeights:
         blk.ffn2 = self._linear(f64[e + "output.dense.weight"], f64[e + "output.dense.bias"])
         blk.ln3_g = self._f32(f64[e + "output.LayerNorm.weight"])
         blk.ln3_b = self._f32(f64[e + "output.LayerNorm.bias"])
+
+
+MANO_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "weights")
+
+
+def mano_zero_pose_template(mano, center_idx=9):
+    """(799,3) joints ‖ vertices of the MANO layer at zero pose / zero shape, centred on joint `center_idx` — what the
+    reference head recomputes on every forward (ptEmb_head.py:885-891).  At zero pose the skinning is the identity:
+    vertices = v_template, the 16 joints = J_regressor · v_template, plus the 5 fingertip vertices, re-ordered."""
+    from .synth import MANO_JOINT_ORDER, MANO_TIP_VERTS
+    v = mano["v_template"].detach().to("cpu", torch.float64).reshape(778, 3)
+    j16 = mano["J_regressor"].detach().to("cpu", torch.float64).reshape(16, 778) @ v
+    j21 = torch.cat([j16, v[list(MANO_TIP_VERTS)]])[list(MANO_JOINT_ORDER)]
+    c = j21[center_idx:center_idx + 1]
+    return torch.cat([j21 - c, v - c]).float()
+
+
+class PackedManoTail:
+    """Device tensors behind the ctypes `PoemManoTail` struct: the last block's `flat_verts` / `mano_linear` (fp32, as
+    in the reference) and the MANO model parameters with the blend-coefficient axis first."""
+
+    def __init__(self, sd, dims: HeadDims, mano, device):
+        self._keep = []
+        p = f"transformer.pt_metro_encoder.{dims.n_blocks - 1}."
+        dev = torch.device(device)
+
+        def f32(t):
+            t = t.detach().to(torch.float32).contiguous().to(dev)
+            self._keep.append(t)
+            return t.data_ptr()
+        m = nat.PoemManoTail()
+        m.flat_w = f32(sd[p + "flat_verts.weight"].reshape(-1))
+        m.flat_b = f32(sd[p + "flat_verts.bias"].reshape(-1))
+        m.lin_w = f32(sd[p + "mano_linear.weight"].reshape(106, dims.embed_dims))
+        m.lin_b = f32(sd[p + "mano_linear.bias"].reshape(-1))
+        m.v_template = f32(mano["v_template"].reshape(778, 3))
+        m.shapedirs = f32(mano["shapedirs"].reshape(778 * 3, 10).t())
+        m.posedirs = f32(mano["posedirs"].reshape(778 * 3, 135).t())
+        m.j_regressor = f32(mano["J_regressor"].reshape(16, 778))
+        m.skin_weights = f32(mano["weights"].reshape(778, 16))
+        self.struct = m

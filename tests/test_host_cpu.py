@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = nat.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.poem_abi_version() == 1
+    assert lib.poem_abi_version() == 2
 
 
 def test_workspace_query_and_dim_validation_need_no_gpu():
@@ -150,6 +150,48 @@ def test_module_keeps_reference_state_dict_keys():
     shell.load_state_dict({"ptEmb_head." + k: v for k, v in sd.items()}, strict=True)
     tr = PtEmbedTRv4(dims)
     tr.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=True)
+
+
+def test_parametric_head_host_side():
+    """medium_MANO: reference key names, MANO parameters from the constructor or from the
+    `mano_layer.th_*` buffers a reference checkpoint carries, zero-pose template = the oracle's MANO forward."""
+    dims = release_dims("medium_MANO")
+    assert dims.parametric and dims.embed_dims == 256
+    mano = synth.synthetic_mano(11)
+    sd = synth.make_state_dict(dims, 2)
+    last = f"transformer.pt_metro_encoder.{dims.n_blocks - 1}."
+    assert sd[last + "flat_verts.weight"].shape == (1, 799) and sd[last + "mano_linear.weight"].shape == (106, 256)
+    head = POEM_Generalized_Head(dims, mano_params=mano)
+    head.load_state_dict(sd, strict=True)
+    assert head.parametric_output
+    v, j = orc.mano_forward(mano, torch.zeros(1, 48), torch.zeros(1, 10), dims.center_idx)
+    want = torch.cat([j, v], dim=1)[0]
+    assert (pack.mano_zero_pose_template(mano, dims.center_idx) - want).abs().max().item() <= 1e-7
+    # a reference checkpoint: MANO buffers ride along under the last block's mano_layer
+    ck = dict(sd)
+    shapes = {"v_template": (1, 778, 3), "shapedirs": (778, 3, 10), "posedirs": (778, 3, 135),
+              "J_regressor": (16, 778), "weights": (778, 16)}
+    for k, shp in shapes.items():
+        ck[last + "mano_layer.th_" + k] = mano[k].reshape(shp)
+    ck[last + "mano_layer.th_faces"] = torch.zeros(1538, 3, dtype=torch.long)
+    h2 = POEM_Generalized_Head(dims)
+    h2.load_state_dict(ck, strict=True)
+    for k in shapes:
+        assert torch.equal(h2._mano[k].reshape(-1), mano[k].reshape(-1))
+    # without parameters the parametric head fails loudly when it has to pack them
+    h3 = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    h3.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError, match="MANO parameters unavailable"):
+        h3.packed_mano("cpu")
+    with pytest.raises(KeyError):
+        POEM_Generalized_Head(dims, mano_params={"v_template": mano["v_template"]})
+    # C-ABI: workspace query of the stage-level entry point is host arithmetic
+    import ctypes as C
+    lib = nat.load()
+    d = nat.make_dims(dims)
+    assert lib.poem_parametric_tail_workspace_bytes(C.byref(d), 32) == 32 * 256 * 4 + 1024
+    assert lib.poem_parametric_tail_workspace_bytes(C.byref(d), 0) == 0
+    assert lib.poem_parametric_tail(C.byref(d), None, 1, None, None, None, None, None, None, 0, None) == -2
 
 
 def test_module_reads_reference_config_and_fails_loudly_without_gpu():
