@@ -40,7 +40,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
                   const __grid_constant__ CUtensorMap tmap_k,   // [B*Lk rows, ldk] bf16, box [HD(or 64) x 128]
                   const __grid_constant__ CUtensorMap tmap_v,   // [B*Lk rows, ldv] bf16, box [HD(or 64) x 128]
                   __nv_bfloat16* __restrict__ ctx, int ld_ctx, int Lq, int Lk, int q_col0, int k_col0, int v_col0,
-                  float scale_log2e) {
+                  float scale_log2e, int n_heads) {
   using Cfg = MhaCfg<HD>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -64,9 +64,22 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * MHA_BQ;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
+  // 1-D grid, full 128-query tiles first, the partial tile of every (sample, head) last: Lq = 799 leaves a 31-row
+  // tile whose idle softmax warps skip their work (below), so those CTAs are short and fill the last wave
+  // (7 x 4 x 32 = 896 equal CTAs on 296 slots took four waves for 3.03 waves of work).
+  const int n_full = Lq / MHA_BQ;
+  const int full_ctas = n_full * (int)(gridDim.x / (n_full + ((Lq % MHA_BQ) ? 1 : 0)));
+  int tile, group;
+  if ((int)blockIdx.x < full_ctas) {
+    tile = (int)blockIdx.x % n_full;
+    group = (int)blockIdx.x / n_full;
+  } else {
+    tile = n_full;
+    group = (int)blockIdx.x - full_ctas;
+  }
+  const int q0 = tile * MHA_BQ;
+  const int head = group % n_heads;
+  const int b = group / n_heads;
   const int n_kblocks = Lk / MHA_BKEY;
 
   if (warp == 0 && lane == 0) {
@@ -176,6 +189,19 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    if (q0 + quarter * 32 >= Lq) {
+      // No valid query row in this warp (and in its partner warp): keep the barrier protocol, skip the arithmetic.
+      // The named barrier keeps these warps in step with the working ones, so every mbarrier phase still sees
+      // exactly one arrival per thread.
+      for (int j = 0; j < n_kblocks; ++j) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (j == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (j > 0) mbar_arrive(&o_done[(j - 1) & 1]);
+        mbar_arrive(p_full);
+      }
+      mbar_arrive(&o_done[(n_kblocks - 1) & 1]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else {
     float o_acc[HH];
 #pragma unroll
     for (int c = 0; c < HH; ++c) o_acc[c] = 0.f;
@@ -287,6 +313,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         pk.w = pack_bf16x2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
         *reinterpret_cast<uint4*>(o + c) = pk;
       }
+    }
     }
   }
 

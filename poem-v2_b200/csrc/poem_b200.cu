@@ -862,11 +862,11 @@ static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
                                   MhaCfg<HD>::kSmemBytes));
     configured = true;
   }
-  dim3 grid((Lq + MHA_BQ - 1) / MHA_BQ, n_heads, B);
+  dim3 grid((unsigned)(((Lq + MHA_BQ - 1) / MHA_BQ) * n_heads * B));   // full tiles first, partial tiles last
   const float scale_log2e = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
   prof_begin(st);
   mha_fwd_tc_kernel<HD><<<grid, MHA_THREADS, MhaCfg<HD>::kSmemBytes, st>>>(tq, tk, tv, ctx, ld_ctx, Lq, Lk, q_col0,
-                                                                           k_col0, v_col0, scale_log2e);
+                                                                           k_col0, v_col0, scale_log2e, n_heads);
   LAUNCH_CHECK("mha_fwd_tc_kernel");
   return POEM_OK;
 }
