@@ -43,9 +43,10 @@ __device__ __forceinline__ float nan_to_num_f(float v) {   // torch.nan_to_num (
 }
 
 constexpr int kManoVerts = 778, kManoJoints = 16, kManoV3 = kManoVerts * 3;
+constexpr int kManoThreads = 1024, kManoWarps = kManoThreads / 32;   // one block per sample: wide, so the blend loops keep many loads in flight
 
-// One block (256 threads) per sample.
-__global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
+// One block per sample.
+__global__ void __launch_bounds__(kManoThreads) mano_tail_kernel(const ManoTailArgs a) {
   __shared__ float par[106];
   __shared__ float R[kManoJoints][9];
   __shared__ float pm[135];
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
 
   // ---- mano_linear: (D) -> 106 = 16 x 6-D rotations | 10 betas
   const float* f = a.flat + (size_t)b * D;
-  for (int o = warp; o < 106; o += 8) {
+  for (int o = warp; o < 106; o += kManoWarps) {
     const float* w = a.lin_w + (size_t)o * D;
     float acc = 0.f;
     for (int c = lane; c < D; c += 32) acc += f[c] * w[c];
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
   if (tid < 135) pm[tid] = R[1 + tid / 9][tid % 9] - ((tid % 9) % 4 == 0 ? 1.f : 0.f);
 
   // ---- shape blend: v_shaped = v_template + shapedirs . betas   (shapedirs stored [10][778*3])
-  for (int i = tid; i < kManoV3; i += 256) {
+  for (int i = tid; i < kManoV3; i += kManoThreads) {
     float v = a.v_template[i];
 #pragma unroll
     for (int k = 0; k < 10; ++k) v += a.shapedirs[k * kManoV3 + i] * par[96 + k];
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
   }
   __syncthreads();
   // ---- joints of the shaped mesh: J = J_regressor . v_shaped
-  for (int o = warp; o < kManoJoints * 3; o += 8) {
+  for (int o = warp; o < kManoJoints * 3; o += kManoWarps) {
     const int j = o / 3, c = o % 3;
     float acc = 0.f;
     for (int v = lane; v < kManoVerts; v += 32) acc += a.j_regressor[j * kManoVerts + v] * vs[v * 3 + c];
@@ -142,9 +143,10 @@ __global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
   }
   __syncthreads();
   // ---- pose blend: v_posed = v_shaped + posedirs . (R[1:] - I)   (posedirs stored [135][778*3])
-  for (int i = tid; i < kManoV3; i += 256) {
+  for (int i = tid; i < kManoV3; i += kManoThreads) {
     float v = 0.f;
-    for (int k = 0; k < 135; ++k) v += a.posedirs[k * kManoV3 + i] * pm[k];
+#pragma unroll 15
+    for (int k = 0; k < 135; ++k) v += a.posedirs[k * kManoV3 + i] * pm[k];   // 15 independent L2 loads in flight
     vs[i] += v;
   }
   // ---- kinematic chain (MANO tree: joint j hangs on j-1, except 1,4,7,10,13 which hang on the root): thread per finger
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
   }
   __syncthreads();
   // ---- skinning: thread per vertex, in place
-  for (int v = tid; v < kManoVerts; v += 256) {
+  for (int v = tid; v < kManoVerts; v += kManoThreads) {
     float T[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) T[e] = 0.f;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(256) mano_tail_kernel(const ManoTailArgs a) {
     ox = c[0], oy = c[1], oz = c[2];
   }
   float* out = a.coords + (size_t)b * (21 + kManoVerts) * 3;
-  for (int i = tid; i < (21 + kManoVerts) * 3; i += 256) {
+  for (int i = tid; i < (21 + kManoVerts) * 3; i += kManoThreads) {
     const int c = i % 3;
     const float v = i < 63 ? jt[i / 3][c] : vs[i - 63];
     out[i] = nan_to_num_f(v - (c == 0 ? cx : c == 1 ? cy : cz)) + (c == 0 ? ox : c == 1 ? oy : oz);

@@ -1432,7 +1432,7 @@ static int launch_parametric_tail(const PoemDims* dims, const PoemManoTail* m, i
   a.coords = coords, a.pose_out = pose, a.shape_out = shape;
   a.D = dims->embed_dims, a.center_idx = dims->center_idx;
   prof_begin(st);
-  mano_tail_kernel<<<B, 256, 0, st>>>(a);
+  mano_tail_kernel<<<B, kManoThreads, 0, st>>>(a);
   LAUNCH_CHECK("mano_tail_kernel");
   return POEM_OK;
 }

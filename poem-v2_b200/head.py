@@ -131,7 +131,9 @@ class _NativeDecoder(nn.Module):
         self._packed = self._packed_mano = None
 
     def packed_mano(self, device):
-        self.packed(device)                                  # refreshes the cache key
+        """Call after `packed(device)`: a re-pack of the weights drops this cache too."""
+        if self._packed is None:
+            self.packed(device)
         if self._packed_mano is None:
             if self._mano is None:
                 self._mano = _resolve_mano(self.dims, None)
