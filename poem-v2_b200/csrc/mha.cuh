@@ -190,18 +190,17 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     const int row = quarter * 32 + lane;            // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     if (q0 + quarter * 32 >= Lq) {
-      // No valid query row in this warp (and in its partner warp): keep the barrier protocol, skip the arithmetic.
-      // The named barrier keeps these warps in step with the working ones, so every mbarrier phase still sees
-      // exactly one arrival per thread.
+      // No valid query row in this warp (and in its partner warp): keep the mbarrier protocol, skip the arithmetic.
       for (int j = 0; j < n_kblocks; ++j) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (j == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
         if (j > 0) mbar_arrive(&o_done[(j - 1) & 1]);
         mbar_arrive(p_full);
+        mbar_wait(p_full, (uint32_t)j & 1);   // stay in step with the working warps: one arrival per thread and phase
       }
       mbar_arrive(&o_done[(n_kblocks - 1) & 1]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     } else {
+    // the two warps that share a lane quarter only ever exchange with each other: named barrier 1 + quarter, 64 threads
+    // (a CTA-wide barrier here kept all eight warps in lock step once per key block)
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
     float o_acc[HH];
 #pragma unroll
     for (int c = 0; c < HH; ++c) o_acc[c] = 0.f;
@@ -254,9 +253,9 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       // issued, which (for j >= 1) waits for o_done(j-1), i.e. for every thread's read below; block 0 syncs again.
       const __nv_bfloat16 m_mine = __float2bfloat16(m_blk);
       s_xchg[half * 128 + row] = m_mine;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      pair_sync();
       m_blk = fmaxf(__bfloat162float(m_mine), __bfloat162float(s_xchg[(half ^ 1) * 128 + row]));
-      if (j == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (j == 0) pair_sync();
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
       const float m_scaled = m_new * scale_log2e;
@@ -297,7 +296,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     // (every P·V has retired: the P tile is free and serves as the fp32 exchange buffer)
     float* lbuf = reinterpret_cast<float*>(sP);
     lbuf[half * 128 + row] = l_run;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    pair_sync();
     const float l_row = l_run + lbuf[(half ^ 1) * 128 + row];
 
     const int q = q0 + row;
