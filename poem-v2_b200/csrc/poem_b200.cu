@@ -1118,7 +1118,9 @@ static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q,
   if ((idx == nullptr) == (anchor_idx == nullptr)) return fail(POEM_E_NULL, "vector_attention: give idx XOR anchors");
   if (anchor_idx && !anchor_xyz) return fail(POEM_E_NULL, "vector_attention: anchor_xyz missing");
   if (D % 32) return fail(POEM_E_BADDIM, "vector_attention: D=%d", D);
-  if (!g_force_unfused && (D == 128 || D == 256 || D == 512) && ldk == ldv &&
+  // the fused kernel gathers kt / v as 4-byte words (two channels): even leading dimension, 4-byte aligned tables
+  if (!g_force_unfused && (D == 128 || D == 256 || D == 512) && ldk == ldv && (ldk % 2) == 0 &&
+      ((reinterpret_cast<uintptr_t>(ktab) | reinterpret_cast<uintptr_t>(vtab)) & 3) == 0 &&
       (long long)B * Lr * ldk < 0x7fffffffLL) {
     if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->delta2.b || !w->gamma1_delta2.w || !w->gamma2.w)
       return fail(POEM_E_NULL, "vector_attention: weight pointer missing");

@@ -215,17 +215,30 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     const uint32_t act_byte = (uint32_t)(c & 7) * 2;
     uint32_t acc_phase = 0;
 
-    // 32 bf16 values of column c from the gather rows of one query, packed two per register
+    // 32 bf16 values of column c from the gather rows of one query, packed two per register (rows 2i | 2i+1).
+    // Lanes 2k / 2k+1 own channels c / c+1 of the same 4-byte word: the even lane fetches that word for the even rows,
+    // the odd lane for the odd rows (16 loads of 4 bytes instead of 32 of 2, half the registers in flight), then one
+    // shuffle per word swaps them and a byte permute keeps this thread's half of both.
+    const uint32_t odd = (uint32_t)lane & 1u;
+    const uint32_t prmt_sel = odd ? 0x3276u : 0x5410u;   // (own, partner) -> odd: partner.hi | own.hi << 16; even: own.lo | partner.lo << 16
     auto gather32 = [&](const __nv_bfloat16* tab, int qi, uint32_t(&out)[16]) {
-      const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tab) + c;
-      const int4* rows4 = reinterpret_cast<const int4*>(s_rows + qi * 32);   // s_rows = row * ld (elements)
+      const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tab + (c & ~1));
+      // s_rows (element offsets row * ld) holds the even neighbours of a query first, then the odd ones
+      const int4* rows4 = reinterpret_cast<const int4*>(s_rows + qi * 32 + odd * 16);
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
+      for (int j4 = 0; j4 < 4; ++j4) {
         const int4 o = rows4[j4];
-        const uint32_t a0 = __ldg(t16 + (uint32_t)o.x), a1 = __ldg(t16 + (uint32_t)o.y);
-        const uint32_t a2 = __ldg(t16 + (uint32_t)o.z), a3 = __ldg(t16 + (uint32_t)o.w);
-        out[2 * j4] = a0 | (a1 << 16);
-        out[2 * j4 + 1] = a2 | (a3 << 16);
+        out[4 * j4 + 0] = __ldg(t32 + ((uint32_t)o.x >> 1));
+        out[4 * j4 + 1] = __ldg(t32 + ((uint32_t)o.y >> 1));
+        out[4 * j4 + 2] = __ldg(t32 + ((uint32_t)o.z >> 1));
+        out[4 * j4 + 3] = __ldg(t32 + ((uint32_t)o.w >> 1));
+      }
+    };
+    auto exchange32 = [&](uint32_t(&w)[16]) {   // call once the words are needed: own word + partner's word -> rows 2i | 2i+1
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, w[i], 1);
+        w[i] = __byte_perm(w[i], other, prmt_sel);
       }
     };
     auto bf_lo = [](uint32_t x) { return __uint_as_float(x << 16); };
@@ -254,7 +267,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           ry = p.q_xyz[(size_t)qg * 3 + 1] - ny;
           rz = p.q_xyz[(size_t)qg * 3 + 2] - nz;
         }
-        s_rows[et] = row * p.ldk;   // element offset of the gather row (ldk == ldv, checked on the host)
+        // element offset of the gather row (ldk == ldv and even, checked on the host); even neighbours first
+        s_rows[(et & ~31) + (j & 1) * 16 + (j >> 1)] = row * p.ldk;
         s_rel[et] = make_float4(rx, ry, rz, 0.f);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
@@ -300,6 +314,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
+        exchange32(kk[0]);
+        exchange32(kk[1]);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
 #pragma unroll
@@ -333,6 +349,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
+        exchange32(vv[0]);
+        exchange32(vv[1]);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int qg = q_first + qi0 + u;
