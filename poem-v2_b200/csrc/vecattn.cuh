@@ -140,22 +140,21 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // order = consumption order of the MMA issuer: per round, per channel tile mt, per GEMM g, per K block
-        for (int round = 0; round < 2; ++round) {
-          const int g_first = (round == 0) ? 0 : 2, g_last = (round == 0) ? 1 : 2;
-          for (int mt = 0; mt < MT; ++mt)
-            for (int g = g_first; g <= g_last; ++g) {
-              const CUtensorMap* tm = (g == 0) ? &tmap_wd2 : (g == 1) ? &tmap_wg1 : &tmap_wg2;
-              for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(&w_empty[stage], phase ^ 1);
-                mbar_expect_tx(&w_full[stage], Cfg::W_TILE_BYTES);
-                tma_load_2d(s_w + stage * Cfg::W_TILE_BYTES, tm, &w_full[stage], kb * 64, mt * 128);
-                if (++stage == Cfg::W_STAGES) {
-                  stage = 0;
-                  phase ^= 1;
-                }
-              }
+        // order = consumption order of the MMA issuer: gamma1 (g = 1) of every channel tile, then pos (g = 0) of every
+        // channel tile, then the logits (g = 2) of every channel tile; K blocks innermost
+        for (int step = 0; step < 3 * MT; ++step) {
+          const int g = (step < MT) ? 1 : (step < 2 * MT) ? 0 : 2;
+          const int mt = step % MT;
+          const CUtensorMap* tm = (g == 0) ? &tmap_wd2 : (g == 1) ? &tmap_wg1 : &tmap_wg2;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&w_empty[stage], phase ^ 1);
+            mbar_expect_tx(&w_full[stage], Cfg::W_TILE_BYTES);
+            tma_load_2d(s_w + stage * Cfg::W_TILE_BYTES, tm, &w_full[stage], kb * 64, mt * 128);
+            if (++stage == Cfg::W_STAGES) {
+              stage = 0;
+              phase ^= 1;
             }
+          }
         }
       }
     }
@@ -167,33 +166,34 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       uint32_t phase = 0;
       uint32_t act_phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int round = 0; round < 2; ++round) {
-          mbar_wait(act_full, act_phase);
-          act_phase ^= 1;
-          tc_fence_after_sync();
-          // round 0: pos = W_d2 h  and  gamma1_pre = (W_g1 W_d2) h   (same B operand); round 1: logits = W_g2 relu(.)
-          // Channel tile mt is finished (and committed to its own barrier) before mt+1 starts, so the channel warps
-          // of tile mt run their epilogue while the tensor core works on the next tile.
-          const int g_first = (round == 0) ? 0 : 2, g_last = (round == 0) ? 1 : 2;
-          for (int mt = 0; mt < MT; ++mt) {
-            for (int g = g_first; g <= g_last; ++g) {
-              const uint32_t acc = ((g == 0) ? tmem_pos : tmem_h) + mt * NT;
-              for (int kb = 0; kb < KB; ++kb) {
-                const uint64_t db = make_kmajor_desc<128>(smem_u32(round == 0 ? s_act : s_act1) + kb * (NT * 128));
-                mbar_wait(&w_full[stage], phase);
-                tc_fence_after_sync();
-                const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                umma_commit(&w_empty[stage]);
-                if (++stage == Cfg::W_STAGES) {
-                  stage = 0;
-                  phase ^= 1;
-                }
-              }
-            }
-            umma_commit(&acc_full[mt]);
+        // Round 0 (B operand h): gamma1_pre = (W_g1 W_d2) h of every channel tile first — each committed to its own
+        // barrier, so the channel warps of tile mt start epilogue 2 as early as possible — then pos = W_d2 h, which only
+        // epilogue 3 reads and which therefore runs on the tensor core WHILE the channel warps are in epilogue 2.
+        // Round 1 (B operand relu(gamma1)): logits = W_g2 relu(.), committed per channel tile; MMAs retire in order,
+        // so that commit also covers the tile's pos accumulators.
+        for (int step = 0; step < 3 * MT; ++step) {
+          const int g = (step < MT) ? 1 : (step < 2 * MT) ? 0 : 2;
+          const int mt = step % MT;
+          if (step == 0 || step == 2 * MT) {
+            mbar_wait(act_full, act_phase);
+            act_phase ^= 1;
+            tc_fence_after_sync();
           }
+          const uint32_t acc = ((g == 0) ? tmem_pos : tmem_h) + mt * NT;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t db = make_kmajor_desc<128>(smem_u32(g == 2 ? s_act1 : s_act) + kb * (NT * 128));
+            mbar_wait(&w_full[stage], phase);
+            tc_fence_after_sync();
+            const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&w_empty[stage]);
+            if (++stage == Cfg::W_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (g != 0) umma_commit(&acc_full[mt]);
         }
       }
     }
