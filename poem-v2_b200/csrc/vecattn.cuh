@@ -52,8 +52,6 @@ struct VaCfg {
   static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] bf16
   static constexpr int ACT_BYTES = NT * D * 2;       // KB blocks of [NT tokens x 64 k] bf16
   static constexpr int TMEM_COLS = (2 * MT * NT <= 256) ? 256 : 512;
-  static constexpr int GROUPS = EP / NT;             // stage-A: thread groups per token
-  static constexpr int CPT = D / GROUPS;             // stage-A: channels per thread
   // smem: act0 (h) | act1 (relu gamma1) | weight ring | wd1 (float4 per channel) | token rows | token rel xyz | barriers
   static constexpr int OFF_W = 2 * ACT_BYTES;
   static constexpr int OFF_WD1 = OFF_W + W_STAGES * W_TILE_BYTES;
@@ -273,25 +271,32 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
 
-      // ---- stage A: h = relu(W_d1 rel + b_d1) -> activation tile (B operand of the pos and gamma1 GEMMs)
+      // ---- stage A: h = relu(W_d1 rel + b_d1) -> activation tile (B operand of the pos and gamma1 GEMMs).
+      //      A thread owns 8 channels x 8 tokens: the 8 weight rows stay in registers, so the tile costs 16 LDS.128 per
+      //      thread (8 weight rows + 8 token offsets) instead of one per output channel (64).
       {
-        const int t = et % NT;
-        const int c_first = (et / NT) * Cfg::CPT;
-        const float4 rel = s_rel[t];
-#pragma unroll 4
-        for (int cc = 0; cc < Cfg::CPT; cc += 8) {
+        constexpr int TG = NT / 8;               // token groups; thread = (token group, 8-channel group)
+        static_assert(TG * (D / 8) == EP, "stage A mapping: 8 tokens x 8 channels per channel thread");
+        const int tg = et % TG;
+        const int ch = (et / TG) * 8;
+        float4 wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = s_wd1[ch + i];
+        uint8_t* blk = s_act + (ch >> 6) * (NT * 128);
+        const uint32_t chunk = (uint32_t)(ch & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int t = tg + TG * i;
+          const float4 rel = s_rel[t];
           uint32_t pk[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 w0 = s_wd1[c_first + cc + 2 * i];
-            const float4 w1 = s_wd1[c_first + cc + 2 * i + 1];
+          for (int k = 0; k < 4; ++k) {
+            const float4 w0 = wv[2 * k], w1 = wv[2 * k + 1];
             const float h0 = fmaxf(fmaf(w0.x, rel.x, fmaf(w0.y, rel.y, fmaf(w0.z, rel.z, w0.w))), 0.f);
             const float h1 = fmaxf(fmaf(w1.x, rel.x, fmaf(w1.y, rel.y, fmaf(w1.z, rel.z, w1.w))), 0.f);
-            pk[i] = pack_bf16x2(h0, h1);
+            pk[k] = pack_bf16x2(h0, h1);
           }
-          const int ch = c_first + cc;
-          uint8_t* dst = s_act + (ch >> 6) * (NT * 128) + sw128_offset(t, (ch & 63) >> 3);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(blk + sw128_offset(t, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       fence_proxy_async_smem();
