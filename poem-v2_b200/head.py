@@ -197,8 +197,14 @@ class POEM_Generalized_Head(_NativeDecoder):
         assert len(views) == B and int(views.sum()) == mlvl_feat.shape[0]
         assert mlvl_feat.shape[1] == d.in_channels and tuple(mlvl_feat.shape[-2:]) == (d.feat_hw, d.feat_hw)
         inp_w, inp_h = img_metas["inp_img_shape"]   # the reference unpacks (H,W) as (w,h) (ptEmb_head.py:831)
-        if not torch.cuda.is_current_stream_capturing():   # mirrors the reference's mutation; a host->device copy
-            img_metas["inp_res"] = torch.tensor([inp_w, inp_h], dtype=torch.float32, device=dev)
+        # mirrors the reference's mutation of img_metas (ptEmb_head.py:833).  The tensor is cached: building it per call
+        # is a pageable host->device copy that synchronises the stream and serialises consecutive forwards
+        # (measured: 6.3 ms of CPU time per call instead of 1.9 ms, scripts/exp_host_enqueue.py).
+        key = (str(dev), float(inp_w), float(inp_h))
+        if getattr(self, "_inp_res_key", None) != key and not torch.cuda.is_current_stream_capturing():
+            self._inp_res, self._inp_res_key = torch.tensor([inp_w, inp_h], dtype=torch.float32, device=dev), key
+        if getattr(self, "_inp_res_key", None) == key:
+            img_metas["inp_res"] = self._inp_res
         feat = mlvl_feat.contiguous().float()
         intr = img_metas["cam_intr"].to(dev, torch.float32).contiguous()
         extr = img_metas["cam_extr"].to(dev, torch.float32).contiguous()
