@@ -75,7 +75,10 @@ def test_linear_rejects_bad_arguments(lib):
 
 
 # ------------------------------------------------------------------------------------------ MHA
-@pytest.mark.parametrize("D,B,Lq,Lk", [(128, 2, 799, 512), (256, 2, 799, 4096), (512, 1, 799, 1024), (256, 3, 130, 256)])
+# query counts: 799 = 6 full 128-row tiles + a 31-row tile whose idle warps skip; 130 = 1 + a 2-row tile; 100 = only a
+# partial tile (three idle warp pairs); 256 / 384 = full tiles only; 97 rows reach into the fourth warp of the tile
+@pytest.mark.parametrize("D,B,Lq,Lk", [(128, 2, 799, 512), (256, 2, 799, 4096), (512, 1, 799, 1024), (256, 3, 130, 256),
+                                       (256, 2, 100, 384), (256, 2, 256, 128), (128, 1, 384, 256), (256, 5, 97, 256)])
 def test_mha(lib, D, B, Lq, Lk):
     h = 4
     hd = D // h

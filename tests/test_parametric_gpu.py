@@ -235,3 +235,28 @@ def test_parametric_properties_at_benchmark_size():
     ms["master_id"], ms["cam_view_num"] = [0] * sub, np.array([V] * sub)
     o3 = head(mlvl_feat=feat[:sub * V].cuda(), img_metas=ms, reference_joints=ref_j[:sub].cuda())
     assert torch.equal(o3["all_coords_preds"].cpu(), c1[:, :sub]) and torch.equal(o3["pred_pose"].cpu(), o1["pred_pose"].cpu()[:sub])
+
+
+def test_parametric_head_graph_replay_is_identical():
+    """The parametric forward is capture-safe like the plain one: CUDA-graph replay == eager, on new inputs too."""
+    from poem_v2_b200.graph import graph_head
+    dims = release_dims("medium_MANO")
+    mano = synth.synthetic_mano(11)
+    head = POEM_Generalized_Head(dims, mano_params=mano)
+    head.load_state_dict(synth.make_state_dict(dims, 0), strict=True)
+    head = head.cuda().eval()
+
+    def inputs(seed):
+        feat, metas, ref_j = synth.make_inputs(dims, 2, [3, 2], seed)
+        m = dict(metas)
+        m["cam_intr"], m["cam_extr"] = metas["cam_intr"].cuda(), metas["cam_extr"].cuda()
+        return feat.cuda(), m, ref_j.cuda()
+    g = graph_head(head, *inputs(1))
+    for seed in (1, 2):
+        f, m, r = inputs(seed)
+        eager = {k: v.clone() for k, v in head(mlvl_feat=f, img_metas=m, reference_joints=r).items()}
+        got = g(mlvl_feat=f, img_metas=m, reference_joints=r)
+        torch.cuda.synchronize()
+        assert set(got) == {"all_coords_preds", "pred_pose", "pred_shape"}
+        for k in eager:
+            assert torch.equal(got[k], eager[k]), k
