@@ -33,6 +33,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes for -126 <= x <= ~1: x = n + f with n = rint(x) taken from the low mantissa bits of
+// x + 1.5 * 2^23, a degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16
+// rounding of the probabilities it feeds), n added to the exponent field.  Used for a fraction of the softmax
+// exponentials of the attention kernel, whose MUFU.EX2 issue rate (16 / clk / SM) is the measured limiter
+// (profiles/r1_ncu_mha.md: 26 % of the warp samples sit on ex2 with stall reason mio_throttle).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.0551716648042202f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // 256-bit global accesses (sm_100: LDG.256 / STG.256), one full 32-byte sector per lane
 __device__ __forceinline__ void ldg_nc_256(const void* p, uint32_t* r) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
