@@ -188,6 +188,13 @@ int poem_head_forward_parametric(const PoemDims* dims, const PoemWeights* w, con
                                  const PoemInputs* in, float* out_coords, float* pred_pose, float* pred_shape,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with HOST buffers (see poem_head_forward_host): host_pose [B,48], host_shape [B,10] are copied back with
+ * the coordinates. */
+int poem_head_forward_parametric_host(const PoemDims* dims, const PoemWeights* w, const PoemManoTail* mano,
+                                      const PoemInputs* host_in, float* host_out, float* host_pose, float* host_shape,
+                                      void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* Decoder blocks only.  Replaces PtEmbedTRv4.forward(query_xyz, query_feat, pt_xyz, pt_feats)
  * (ptEmb_transformer.py:371-376): all inputs fp32 device buffers in normalised (radius) units,
  *   query_xyz [B,Q,3], query_feat [B,Q,D], pt_xyz [B,P,3], pt_feats [B,P,D];

@@ -130,7 +130,7 @@ EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm", "poem_parametric_tail_workspace_bytes",
-           "poem_parametric_tail", "poem_head_forward_parametric"]
+           "poem_parametric_tail", "poem_head_forward_parametric", "poem_head_forward_parametric_host"]
 
 _lib = None
 
@@ -175,6 +175,10 @@ def load():
     lib.poem_head_forward_parametric.restype = i
     lib.poem_head_forward_parametric.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights), C.POINTER(PoemManoTail),
                                                  C.POINTER(PoemInputs), vp, vp, vp, vp, sz, vp]
+    lib.poem_head_forward_parametric_host.restype = i
+    lib.poem_head_forward_parametric_host.argtypes = [C.POINTER(PoemDims), C.POINTER(PoemWeights),
+                                                      C.POINTER(PoemManoTail), C.POINTER(PoemInputs), vp, vp, vp, vp, sz,
+                                                      vp, sz, vp]
     lib.poem_transformer_workspace_bytes.restype = sz
     lib.poem_transformer_workspace_bytes.argtypes = [C.POINTER(PoemDims), i]
     lib.poem_transformer_forward.restype = i

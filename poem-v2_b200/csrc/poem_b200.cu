@@ -1597,7 +1597,8 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
 static size_t align1k(size_t x) { return (x + 1023) & ~size_t(1023); }
 static size_t staging_slot_bytes(const PoemDims* d, int B, int NV) {
   return align1k((size_t)NV * d->in_channels * 256 * 4) + align1k((size_t)NV * 9 * 4) + align1k((size_t)NV * 16 * 4) +
-         align1k((size_t)B * 63 * 4) + align1k((size_t)d->n_blocks * B * d->n_query * 3 * 4) + 1024;
+         align1k((size_t)B * 63 * 4) + align1k((size_t)d->n_blocks * B * d->n_query * 3 * 4) +
+         align1k((size_t)B * 58 * 4) /* pred_pose | pred_shape of a parametric head */ + 1024;
 }
 // two staging slots: the host->device copy of call i + 1 overlaps the kernels of call i
 extern "C" size_t poem_staging_bytes(const PoemDims* d, int B, int NV) {
@@ -1623,9 +1624,31 @@ static HostPipe& host_pipe() {
   return p;
 }
 
+static int head_forward_host_impl(const PoemDims* dims, const PoemWeights* w, const PoemManoTail* mano,
+                                  const PoemInputs* hin, float* host_out, float* host_pose, float* host_shape,
+                                  void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
 extern "C" int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const PoemInputs* hin,
                                       float* host_out, void* staging, size_t staging_bytes, void* workspace,
                                       size_t workspace_bytes, void* stream) {
+  return head_forward_host_impl(dims, w, nullptr, hin, host_out, nullptr, nullptr, staging, staging_bytes, workspace,
+                                workspace_bytes, stream);
+}
+
+extern "C" int poem_head_forward_parametric_host(const PoemDims* dims, const PoemWeights* w, const PoemManoTail* mano,
+                                                 const PoemInputs* hin, float* host_out, float* host_pose,
+                                                 float* host_shape, void* staging, size_t staging_bytes,
+                                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!mano || !host_pose || !host_shape) return fail(POEM_E_NULL, "head_forward_parametric_host: null pointer");
+  return head_forward_host_impl(dims, w, mano, hin, host_out, host_pose, host_shape, staging, staging_bytes, workspace,
+                                workspace_bytes, stream);
+}
+
+static int head_forward_host_impl(const PoemDims* dims, const PoemWeights* w, const PoemManoTail* mano,
+                                  const PoemInputs* hin, float* host_out, float* host_pose, float* host_shape,
+                                  void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   POEM_TRY(check_dims(dims));
   if (!hin || !host_out || !workspace || !staging) return fail(POEM_E_NULL, "head_forward_host: null pointer");
   if (reinterpret_cast<uintptr_t>(staging) & 1023) return fail(POEM_E_ALIGN, "staging must be 1024-byte aligned");
@@ -1653,6 +1676,8 @@ extern "C" int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w
   float* d_ref = b.take<float>((size_t)B * 63);
   const size_t n_out = (size_t)dims->n_blocks * B * dims->n_query * 3;
   float* d_out = b.take<float>(n_out);
+  float* d_pose = b.take<float>((size_t)B * 58);   // pred_pose (B,48) then pred_shape (B,10)
+  float* d_shape = d_pose + (size_t)B * 48;
   if (piped) CUDA_TRY(cudaStreamWaitEvent(cs, hp.slot_free[slot], 0));   // no-op until the slot has been used once
   CUDA_TRY(cudaMemcpyAsync(d_feat, hin->mlvl_feat, n_feat * 4, cudaMemcpyHostToDevice, cs));
   CUDA_TRY(cudaMemcpyAsync(d_intr, hin->cam_intr, (size_t)NV * 9 * 4, cudaMemcpyHostToDevice, cs));
@@ -1667,7 +1692,13 @@ extern "C" int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w
   din.cam_intr = d_intr;
   din.cam_extr = d_extr;
   din.reference_joints = d_ref;
-  POEM_TRY(poem_head_forward(dims, w, &din, d_out, nullptr, workspace, workspace_bytes, stream));
+  if (mano) {
+    POEM_TRY(poem_head_forward_parametric(dims, w, mano, &din, d_out, d_pose, d_shape, workspace, workspace_bytes, stream));
+    CUDA_TRY(cudaMemcpyAsync(host_pose, d_pose, (size_t)B * 48 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(host_shape, d_shape, (size_t)B * 10 * 4, cudaMemcpyDeviceToHost, st));
+  } else {
+    POEM_TRY(poem_head_forward(dims, w, &din, d_out, nullptr, workspace, workspace_bytes, stream));
+  }
   CUDA_TRY(cudaMemcpyAsync(host_out, d_out, n_out * 4, cudaMemcpyDeviceToHost, st));
   if (piped) CUDA_TRY(cudaEventRecord(hp.slot_free[slot], st));
   return POEM_OK;

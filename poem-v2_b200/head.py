@@ -259,6 +259,16 @@ class POEM_Generalized_Head(_NativeDecoder):
         inp = nat.PoemInputs(B, NV, views.ctypes.data, mlvl_feat.data_ptr(), img_metas["cam_intr"].data_ptr(),
                              img_metas["cam_extr"].data_ptr(), reference_joints.data_ptr(), float(inp_w), float(inp_h))
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if d.parametric:      # returns (coords, pred_pose (B,16,3), pred_shape (B,10)), all in pinned host memory
+            pm = self.packed_mano(dev)
+            if getattr(self, "_host_pose", None) is None or self._host_pose.shape[0] != B:
+                self._host_pose = torch.empty(B, 16, 3, dtype=torch.float32).pin_memory()
+                self._host_shape = torch.empty(B, 10, dtype=torch.float32).pin_memory()
+            nat.check(lib.poem_head_forward_parametric_host(C.byref(cd), C.byref(pw.struct), C.byref(pm.struct),
+                                                            C.byref(inp), out.data_ptr(), self._host_pose.data_ptr(),
+                                                            self._host_shape.data_ptr(), self._stage.data_ptr() + st_off,
+                                                            self._stage.numel() - st_off, ws_ptr, ws_bytes, stream))
+            return out, self._host_pose, self._host_shape
         nat.check(lib.poem_head_forward_host(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(),
                                              self._stage.data_ptr() + st_off, self._stage.numel() - st_off, ws_ptr,
                                              ws_bytes, stream))

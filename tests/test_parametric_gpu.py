@@ -260,3 +260,24 @@ def test_parametric_head_graph_replay_is_identical():
         assert set(got) == {"all_coords_preds", "pred_pose", "pred_shape"}
         for k in eager:
             assert torch.equal(got[k], eager[k]), k
+
+
+def test_parametric_host_buffer_entry_point():
+    """`poem_head_forward_parametric_host` (host inputs / outputs, copies inside the call) == the device entry point."""
+    dims = release_dims("medium_MANO")
+    mano = synth.synthetic_mano(11)
+    head = POEM_Generalized_Head(dims, mano_params=mano)
+    head.load_state_dict(synth.make_state_dict(dims, 0), strict=True)
+    head = head.cuda().eval()
+    for seed in (1, 2, 3):                       # three calls: both staging slots and a reused one
+        feat, metas, ref_j = synth.make_inputs(dims, 2, [2, 3], seed)
+        hm = dict(metas)
+        hm["cam_intr"], hm["cam_extr"] = metas["cam_intr"].pin_memory(), metas["cam_extr"].pin_memory()
+        coords, pose, shape = head.forward_host(feat.pin_memory(), hm, ref_j.pin_memory())
+        torch.cuda.synchronize()
+        coords, pose, shape = coords.clone(), pose.clone(), shape.clone()
+        dm = dict(metas)
+        dm["cam_intr"], dm["cam_extr"] = metas["cam_intr"].cuda(), metas["cam_extr"].cuda()
+        want = head(mlvl_feat=feat.cuda(), img_metas=dm, reference_joints=ref_j.cuda())
+        assert torch.equal(coords, want["all_coords_preds"].cpu())
+        assert torch.equal(pose, want["pred_pose"].cpu()) and torch.equal(shape, want["pred_shape"].cpu())
