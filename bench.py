@@ -482,7 +482,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches) * n_gpus, "clocks": clk,   # whole job, like `value` (every rank launches the same) "roofline": roofline, "path_roofline": path,
+            # launches of the whole job, like `value` (every rank launches the same kernels)
+            "gpu_launches": int(launches) * n_gpus, "clocks": clk, "roofline": roofline, "path_roofline": path,
             "cpu_baseline": cpu, "torch_cuda_eager": torch_cuda, "images_to_mesh": images,
             "kernel_breakdown_ms_per_step": {k: [round(v["ms"] / prof_steps, 4), v["n"] // prof_steps] for k, v in by_kernel}}
     emit(line)
