@@ -77,6 +77,7 @@ def graph_head(head, mlvl_feat, img_metas, reference_joints):
     metas = {k: v for k, v in img_metas.items() if k != "inp_res"}
     g = GraphedForward(lambda **kw: head(**kw), {"mlvl_feat": mlvl_feat, "img_metas": metas,
                                                    "reference_joints": reference_joints})
+    g._static["img_metas"].pop("inp_res", None)   # added by the head itself (reference ptEmb_head.py:833), not an input
 
     def call(mlvl_feat, img_metas, reference_joints, **_):
         return g(mlvl_feat=mlvl_feat, img_metas={k: v for k, v in img_metas.items() if k != "inp_res"},
