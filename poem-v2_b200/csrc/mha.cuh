@@ -25,6 +25,10 @@ constexpr int MHA_THREADS = 64 + 256;   // TMA warp, MMA warp, 8 softmax warps (
                                         // Measured per launch (medium, B = 32): 0 -> 209.0 us, 12.5 % -> 201.6, 25 % -> 201.6, 50 % -> 223.7
 #endif
 constexpr int MHA_POLY_EVERY = POEM_MHA_POLY_EVERY;
+#ifndef POEM_MHA_BUNDLE
+#define POEM_MHA_BUNDLE 16
+#endif
+constexpr int MHA_BUNDLE = POEM_MHA_BUNDLE;   // (sample, head) groups scheduled together (1 MB of K / V each at head dim 64)
 
 template <int HD>
 struct MhaCfg {
@@ -69,18 +73,23 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 1-D grid, full 128-query tiles first, the partial tile of every (sample, head) last: Lq = 799 leaves a 31-row
-  // tile whose idle softmax warps skip their work (below), so those CTAs are short and fill the last wave
-  // (7 x 4 x 32 = 896 equal CTAs on 296 slots took four waves for 3.03 waves of work).
+  // 1-D grid over (sample, head) groups in bundles of MHA_BUNDLE: the bundle's full 128-query tiles first, then its
+  // partial tiles (Lq = 799 leaves a 31-row tile whose idle softmax warps skip their work, so those CTAs are short).
+  // Bundling keeps the K / V slices of a group in L2 between its full and partial tiles: with all partial tiles at
+  // the end of the grid every K / V byte was fetched from HBM twice (ncu: 253 MB per launch for 134 MB of K / V).
   const int n_full = Lq / MHA_BQ;
-  const int full_ctas = n_full * (int)(gridDim.x / (n_full + ((Lq % MHA_BQ) ? 1 : 0)));
+  const int per_group = n_full + ((Lq % MHA_BQ) ? 1 : 0);
+  const int n_groups = (int)gridDim.x / per_group;
+  const int bundle0 = ((int)blockIdx.x / (MHA_BUNDLE * per_group)) * MHA_BUNDLE;   // first group of this bundle
+  const int in_bundle = min(MHA_BUNDLE, n_groups - bundle0);                        // groups in it (last one may be short)
+  const int r = (int)blockIdx.x - bundle0 * per_group;                              // index inside the bundle
   int tile, group;
-  if ((int)blockIdx.x < full_ctas) {
-    tile = (int)blockIdx.x % n_full;
-    group = (int)blockIdx.x / n_full;
+  if (r < in_bundle * n_full) {
+    tile = r % n_full;
+    group = bundle0 + r / n_full;
   } else {
     tile = n_full;
-    group = (int)blockIdx.x - full_ctas;
+    group = bundle0 + (r - in_bundle * n_full);
   }
   const int q0 = tile * MHA_BQ;
   const int head = group % n_heads;
