@@ -56,8 +56,8 @@ struct VaCfg {
   static constexpr int OFF_W = 2 * ACT_BYTES;
   static constexpr int OFF_WD1 = OFF_W + W_STAGES * W_TILE_BYTES;
   static constexpr int OFF_ROWS = OFF_WD1 + D * 16;
-  static constexpr int OFF_REL = OFF_ROWS + NT * 4;
-  static constexpr int OFF_BARS = OFF_REL + NT * 16;
+  static constexpr int OFF_REL = OFF_ROWS + 2 * NT * 4;      // token rows and rel xyz are double buffered (tile parity)
+  static constexpr int OFF_BARS = OFF_REL + 2 * NT * 16;
   static constexpr int SMEM_BYTES = OFF_BARS + 256;
 };
 
@@ -91,8 +91,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   uint8_t* s_act1 = smem + Cfg::ACT_BYTES;     // B operand of the logits GEMM (epilogue 2 output)
   uint8_t* s_w = smem + Cfg::OFF_W;
   float4* s_wd1 = reinterpret_cast<float4*>(smem + Cfg::OFF_WD1);
-  int* s_rows = reinterpret_cast<int*>(smem + Cfg::OFF_ROWS);
-  float4* s_rel = reinterpret_cast<float4*>(smem + Cfg::OFF_REL);
+  int* s_rows_base = reinterpret_cast<int*>(smem + Cfg::OFF_ROWS);
+  float4* s_rel_base = reinterpret_cast<float4*>(smem + Cfg::OFF_REL);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
   uint64_t* w_full = bars;                        // [W_STAGES]
   uint64_t* w_empty = bars + Cfg::W_STAGES;       // [W_STAGES]
@@ -217,6 +217,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     // Lanes 2k / 2k+1 own channels c / c+1 of the same 4-byte word: the even lane fetches that word for the even rows,
     // the odd lane for the odd rows (16 loads of 4 bytes instead of 32 of 2, half the registers in flight), then one
     // shuffle per word swaps them and a byte permute keeps this thread's half of both.
+    int* s_rows = s_rows_base;        // buffers of the current tile (switched at the end of every tile)
+    float4* s_rel = s_rel_base;
     const uint32_t odd = (uint32_t)lane & 1u;
     const uint32_t prmt_sel = odd ? 0x3276u : 0x5410u;   // (own, partner) -> odd: partner.hi | own.hi << 16; even: own.lo | partner.lo << 16
     auto gather32 = [&](const __nv_bfloat16* tab, int qi, uint32_t(&out)[16]) {
@@ -242,34 +244,49 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     auto bf_lo = [](uint32_t x) { return __uint_as_float(x << 16); };
     auto bf_hi = [](uint32_t x) { return __uint_as_float(x & 0xffff0000u); };
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int q_first = tile * QT;
-      // ---- tile metadata: gather row + relative position of every token
-      if (et < NT) {
-        const int qg = q_first + (et >> 5);
-        const int j = et & 31;
-        int row = 0;
-        float rx = 0.f, ry = 0.f, rz = 0.f;
-        if (qg < p.n_query) {
-          const int b = qg / p.Lq;
-          float nx, ny, nz;
-          if (p.anchor_idx != nullptr) {
-            row = b * p.Lr + p.anchor_idx[j];
-            nx = p.anchor_xyz[j * 3 + 0], ny = p.anchor_xyz[j * 3 + 1], nz = p.anchor_xyz[j * 3 + 2];
-          } else {
-            row = b * p.Lr + p.idx[(size_t)qg * 32 + j];
-            const float* rp = p.ref_xyz + (size_t)row * 3;
-            nx = rp[0], ny = rp[1], nz = rp[2];
-          }
-          rx = p.q_xyz[(size_t)qg * 3 + 0] - nx;
-          ry = p.q_xyz[(size_t)qg * 3 + 1] - ny;
-          rz = p.q_xyz[(size_t)qg * 3 + 2] - nz;
+    // ---- tile metadata: gather row + relative position of every token, written by the first NT channel threads into
+    //      the buffers of tile parity `buf`.  The metadata of tile i + 1 is produced at the END of tile i (its index
+    //      load is issued even earlier), so the two dependent global loads (neighbour index -> neighbour xyz) are off
+    //      the critical path and one CTA-wide barrier per tile is enough.
+    auto load_index = [&](int q_first_) -> int {          // neighbour row of token `et` (element offset / ldk)
+      const int qg = q_first_ + (et >> 5);
+      const int j = et & 31;
+      if (qg >= p.n_query) return 0;
+      const int b = qg / p.Lq;
+      return b * p.Lr + (p.anchor_idx != nullptr ? p.anchor_idx[j] : p.idx[(size_t)qg * 32 + j]);
+    };
+    auto write_meta = [&](int q_first_, int row, int buf) {
+      const int qg = q_first_ + (et >> 5);
+      const int j = et & 31;
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (qg < p.n_query) {
+        float nx, ny, nz;
+        if (p.anchor_idx != nullptr) {
+          nx = p.anchor_xyz[j * 3 + 0], ny = p.anchor_xyz[j * 3 + 1], nz = p.anchor_xyz[j * 3 + 2];
+        } else {
+          const float* rp = p.ref_xyz + (size_t)row * 3;
+          nx = rp[0], ny = rp[1], nz = rp[2];
         }
-        // element offset of the gather row (ldk == ldv and even, checked on the host); even neighbours first
-        s_rows[(et & ~31) + (j & 1) * 16 + (j >> 1)] = row * p.ldk;
-        s_rel[et] = make_float4(rx, ry, rz, 0.f);
+        rx = p.q_xyz[(size_t)qg * 3 + 0] - nx;
+        ry = p.q_xyz[(size_t)qg * 3 + 1] - ny;
+        rz = p.q_xyz[(size_t)qg * 3 + 2] - nz;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+      // element offset of the gather row (ldk == ldv and even, checked on the host); even neighbours first
+      s_rows_base[buf * NT + (et & ~31) + (j & 1) * 16 + (j >> 1)] = row * p.ldk;
+      s_rel_base[buf * NT + et] = make_float4(rx, ry, rz, 0.f);
+    };
+    if (et < NT && (int)blockIdx.x < n_tiles) write_meta(blockIdx.x * QT, load_index(blockIdx.x * QT), 0);
+    asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+      const int q_first = tile * QT;
+      s_rows = s_rows_base + buf * NT;
+      s_rel = s_rel_base + buf * NT;
+      const int next_q_first = (tile + (int)gridDim.x) * QT;
+      const bool has_next = tile + (int)gridDim.x < n_tiles;
+      int next_row = 0;
+      if (et < NT && has_next) next_row = load_index(next_q_first);   // in flight during the whole tile
 
       // ---- stage A: h = relu(W_d1 rel + b_d1) -> activation tile (B operand of the pos and gamma1 GEMMs).
       //      A thread owns 8 channels x 8 tokens: the 8 weight rows stay in registers, so the tile costs 16 LDS.128 per
@@ -392,7 +409,9 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         }
       }
       tc_fence_before_sync();
-      // the next tile's metadata overwrite s_rows/s_rel: every channel thread must be done reading them
+      // next tile's metadata into the other buffers (free since the end of the previous tile), then the only CTA-wide
+      // barrier of the tile: publishes them and ends every thread's reads of this tile's buffers
+      if (et < NT && has_next) write_meta(next_q_first, next_row, buf ^ 1);
       asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
     }
   }
