@@ -56,8 +56,8 @@ struct VaCfg {
   static constexpr int OFF_W = 2 * ACT_BYTES;
   static constexpr int OFF_WD1 = OFF_W + W_STAGES * W_TILE_BYTES;
   static constexpr int OFF_ROWS = OFF_WD1 + D * 16;
-  static constexpr int OFF_REL = OFF_ROWS + 2 * NT * 4;      // token rows and rel xyz are double buffered (tile parity)
-  static constexpr int OFF_BARS = OFF_REL + 2 * NT * 16;
+  static constexpr int OFF_REL = OFF_ROWS + 3 * NT * 4;      // token rows and rel xyz: three buffers (tile index mod 3)
+  static constexpr int OFF_BARS = OFF_REL + 3 * NT * 16;
   static constexpr int SMEM_BYTES = OFF_BARS + 256;
 };
 
@@ -98,7 +98,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   uint64_t* w_empty = bars + Cfg::W_STAGES;       // [W_STAGES]
   uint64_t* act_full = bars + 2 * Cfg::W_STAGES;  // channel threads -> MMA: B operand ready (count EP)
   uint64_t* acc_full = act_full + 1;              // [MT] MMA -> channel threads of tile mt: accumulators ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + MT);
+  uint64_t* pos_done = acc_full + MT;             // MMA -> channel threads: every round-0 MMA has read the h tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pos_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,6 +118,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       }
       mbar_init(act_full, EP);
       for (int m = 0; m < MT; ++m) mbar_init(&acc_full[m], 1);
+      mbar_init(pos_done, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -192,6 +194,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
             }
           }
           if (g != 0) umma_commit(&acc_full[mt]);
+          if (step == 2 * MT - 1) umma_commit(pos_done);   // the h tile may be overwritten by the next tile's stage A
         }
       }
     }
@@ -217,8 +220,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     // Lanes 2k / 2k+1 own channels c / c+1 of the same 4-byte word: the even lane fetches that word for the even rows,
     // the odd lane for the odd rows (16 loads of 4 bytes instead of 32 of 2, half the registers in flight), then one
     // shuffle per word swaps them and a byte permute keeps this thread's half of both.
-    int* s_rows = s_rows_base;        // buffers of the current tile (switched at the end of every tile)
-    float4* s_rel = s_rel_base;
+    int* s_rows = s_rows_base;        // gather rows of the current tile (one of three buffers)
     const uint32_t odd = (uint32_t)lane & 1u;
     const uint32_t prmt_sel = odd ? 0x3276u : 0x5410u;   // (own, partner) -> odd: partner.hi | own.hi << 16; even: own.lo | partner.lo << 16
     auto gather32 = [&](const __nv_bfloat16* tab, int qi, uint32_t(&out)[16]) {
@@ -245,9 +247,13 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     auto bf_hi = [](uint32_t x) { return __uint_as_float(x & 0xffff0000u); };
 
     // ---- tile metadata: gather row + relative position of every token, written by the first NT channel threads into
-    //      the buffers of tile parity `buf`.  The metadata of tile i + 1 is produced at the END of tile i (its index
-    //      load is issued even earlier), so the two dependent global loads (neighbour index -> neighbour xyz) are off
-    //      the critical path and one CTA-wide barrier per tile is enough.
+    //      one of three buffers (tile index mod 3).
+    // Software pipeline over the tiles of this CTA: while the tensor core computes the logits of tile i the channel
+    // warps already build the h tile of tile i + 1 (stage A), so at the end of tile i they only have to arrive and the
+    // round-0 MMAs of tile i + 1 start at once.  That needs the metadata of tile i + 1 in the middle of tile i: its
+    // neighbour indices are loaded one tile ahead (register), the dependent xyz loads are issued at the top of tile i
+    // behind the kt gathers, and the single CTA-wide barrier of the tile (after epilogue 2, where every warp has to
+    // wait for the logits anyway) publishes them.  Three buffers: the one being written was last read two barriers ago.
     auto load_index = [&](int q_first_) -> int {          // neighbour row of token `et` (element offset / ldk)
       const int qg = q_first_ + (et >> 5);
       const int j = et & 31;
@@ -255,7 +261,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       const int b = qg / p.Lq;
       return b * p.Lr + (p.anchor_idx != nullptr ? p.anchor_idx[j] : p.idx[(size_t)qg * 32 + j]);
     };
-    auto write_meta = [&](int q_first_, int row, int buf) {
+    auto write_meta = [&](int q_first_, int row, int mb) {
       const int qg = q_first_ + (et >> 5);
       const int j = et & 31;
       float rx = 0.f, ry = 0.f, rz = 0.f;
@@ -272,52 +278,58 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         rz = p.q_xyz[(size_t)qg * 3 + 2] - nz;
       }
       // element offset of the gather row (ldk == ldv and even, checked on the host); even neighbours first
-      s_rows_base[buf * NT + (et & ~31) + (j & 1) * 16 + (j >> 1)] = row * p.ldk;
-      s_rel_base[buf * NT + et] = make_float4(rx, ry, rz, 0.f);
+      s_rows_base[mb * NT + (et & ~31) + (j & 1) * 16 + (j >> 1)] = row * p.ldk;
+      s_rel_base[mb * NT + et] = make_float4(rx, ry, rz, 0.f);
     };
-    if (et < NT && (int)blockIdx.x < n_tiles) write_meta(blockIdx.x * QT, load_index(blockIdx.x * QT), 0);
-    asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
-
-    int buf = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-      const int q_first = tile * QT;
-      s_rows = s_rows_base + buf * NT;
-      s_rel = s_rel_base + buf * NT;
-      const int next_q_first = (tile + (int)gridDim.x) * QT;
-      const bool has_next = tile + (int)gridDim.x < n_tiles;
-      int next_row = 0;
-      if (et < NT && has_next) next_row = load_index(next_q_first);   // in flight during the whole tile
-
-      // ---- stage A: h = relu(W_d1 rel + b_d1) -> activation tile (B operand of the pos and gamma1 GEMMs).
-      //      A thread owns 8 channels x 8 tokens: the 8 weight rows stay in registers, so the tile costs 16 LDS.128 per
-      //      thread (8 weight rows + 8 token offsets) instead of one per output channel (64).
-      {
-        constexpr int TG = NT / 8;               // token groups; thread = (token group, 8-channel group)
-        static_assert(TG * (D / 8) == EP, "stage A mapping: 8 tokens x 8 channels per channel thread");
-        const int tg = et % TG;
-        const int ch = (et / TG) * 8;
-        float4 wv[8];
+    // ---- stage A: h = relu(W_d1 rel + b_d1) -> activation tile (B operand of the pos and gamma1 GEMMs).
+    //      A thread owns 8 channels x 8 tokens: the 8 weight rows stay in registers, so the tile costs 16 LDS.128 per
+    //      thread (8 weight rows + 8 token offsets) instead of one per output channel (64).
+    auto stage_a = [&](const float4* rel_buf) {
+      constexpr int TG = NT / 8;               // token groups; thread = (token group, 8-channel group)
+      static_assert(TG * (D / 8) == EP, "stage A mapping: 8 tokens x 8 channels per channel thread");
+      const int tg = et % TG;
+      const int ch = (et / TG) * 8;
+      float4 wv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) wv[i] = s_wd1[ch + i];
-        uint8_t* blk = s_act + (ch >> 6) * (NT * 128);
-        const uint32_t chunk = (uint32_t)(ch & 63) >> 3;
+      for (int i = 0; i < 8; ++i) wv[i] = s_wd1[ch + i];
+      uint8_t* blk = s_act + (ch >> 6) * (NT * 128);
+      const uint32_t chunk = (uint32_t)(ch & 63) >> 3;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int t = tg + TG * i;
-          const float4 rel = s_rel[t];
-          uint32_t pk[4];
+      for (int i = 0; i < 8; ++i) {
+        const int t = tg + TG * i;
+        const float4 rel = rel_buf[t];
+        uint32_t pk[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4 w0 = wv[2 * k], w1 = wv[2 * k + 1];
-            const float h0 = fmaxf(fmaf(w0.x, rel.x, fmaf(w0.y, rel.y, fmaf(w0.z, rel.z, w0.w))), 0.f);
-            const float h1 = fmaxf(fmaf(w1.x, rel.x, fmaf(w1.y, rel.y, fmaf(w1.z, rel.z, w1.w))), 0.f);
-            pk[k] = pack_bf16x2(h0, h1);
-          }
-          *reinterpret_cast<uint4*>(blk + sw128_offset(t, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int k = 0; k < 4; ++k) {
+          const float4 w0 = wv[2 * k], w1 = wv[2 * k + 1];
+          const float h0 = fmaxf(fmaf(w0.x, rel.x, fmaf(w0.y, rel.y, fmaf(w0.z, rel.z, w0.w))), 0.f);
+          const float h1 = fmaxf(fmaf(w1.x, rel.x, fmaf(w1.y, rel.y, fmaf(w1.z, rel.z, w1.w))), 0.f);
+          pk[k] = pack_bf16x2(h0, h1);
         }
+        *reinterpret_cast<uint4*>(blk + sw128_offset(t, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();
+    };
+
+    // prologue: metadata and h tile of this CTA's first tile, neighbour indices of its second one
+    const int tile_step = (int)gridDim.x;
+    int next_row = 0;
+    if ((int)blockIdx.x < n_tiles) {
+      if (et < NT) {
+        write_meta(blockIdx.x * QT, load_index(blockIdx.x * QT), 0);
+        if ((int)blockIdx.x + tile_step < n_tiles) next_row = load_index((blockIdx.x + tile_step) * QT);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+      stage_a(s_rel_base);
       mbar_arrive(act_full);
+    }
+    uint32_t pos_phase = 0;
+    int mb = 0;                                                 // metadata buffer of the current tile
+    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step) {
+      const int q_first = tile * QT;
+      const int mb_next = (mb == 2) ? 0 : mb + 1;
+      s_rows = s_rows_base + mb * NT;
+      const bool has_next = tile + tile_step < n_tiles;
 
       // ---- epilogue 2: relu((W_g1 W_d2) h + qt_i - kt_j) -> activation tile (B operand of the logits GEMM).
       //      All kt gathers of this thread's two queries are in flight before it waits for the accumulators.
@@ -332,6 +344,12 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           const int qg = q_first + qi0 + u;
           qv[u] = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
           act1_q[u] = smem_u32(s_act1) + act_blk + (act_chunk << 4) + act_byte + (uint32_t)(qi0 + u) * (32 * 128);
+        }
+        // metadata of the next tile (its xyz loads queue up behind the kt gathers, all of it under the gamma1 GEMMs),
+        // neighbour indices of the tile after it
+        if (et < NT && has_next) {
+          write_meta((tile + tile_step) * QT, next_row, mb_next);
+          if (tile + 2 * tile_step < n_tiles) next_row = load_index((tile + 2 * tile_step) * QT);
         }
         mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
@@ -366,8 +384,23 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       //      softmax((a + b_g2) / sqrt(D)): the bias is constant over the neighbours and cancels.
       {
         uint32_t vv[2][16];
-        gather32(p.vtab, qi0, vv[0]);
-        gather32(p.vtab, qi0 + 1, vv[1]);
+#ifndef POEM_VA_V_EARLY
+#define POEM_VA_V_EARLY 1   // v gathers of how many of the thread's two queries are issued before stage A of the next tile
+                            // (measured, medium: 0 -> 0.3668 ms per launch, 1 -> 0.3655, 2 -> 0.3771 with 44 bytes of spills)
+#endif
+        if (POEM_VA_V_EARLY >= 1) gather32(p.vtab, qi0, vv[0]);
+        if (POEM_VA_V_EARLY >= 2) gather32(p.vtab, qi0 + 1, vv[1]);
+        // the only CTA-wide barrier of the tile: every warp is past epilogue 2 (the logits GEMM cannot start earlier
+        // anyway) and the next tile's metadata is visible.  Then the h tile of the next tile, while the tensor core
+        // computes this tile's logits; the round-0 MMAs of this tile must have read the old h tile (pos_done).
+        asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+        if (has_next) {
+          mbar_wait(pos_done, pos_phase);
+          stage_a(s_rel_base + mb_next * NT);
+        }
+        if (POEM_VA_V_EARLY < 1) gather32(p.vtab, qi0, vv[0]);
+        if (POEM_VA_V_EARLY < 2) gather32(p.vtab, qi0 + 1, vv[1]);
+        pos_phase ^= 1;
         mbar_wait(&acc_full[mt], acc_phase);
         acc_phase ^= 1;
         tc_fence_after_sync();
@@ -409,10 +442,9 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         }
       }
       tc_fence_before_sync();
-      // next tile's metadata into the other buffers (free since the end of the previous tile), then the only CTA-wide
-      // barrier of the tile: publishes them and ends every thread's reads of this tile's buffers
-      if (et < NT && has_next) write_meta(next_q_first, next_row, buf ^ 1);
-      asm volatile("bar.sync 1, %0;" ::"n"(EP) : "memory");
+      // this thread's TMEM reads of the tile are done and its part of the next h tile is written (fenced in stage_a)
+      if (has_next) mbar_arrive(act_full);
+      mb = mb_next;
     }
   }
 
