@@ -21,6 +21,8 @@
 //     shuffles, no smem round trip.
 //   * pos stays in TMEM (first MT*NT columns) until the final reduction; the gamma hidden layer / logits reuse the
 //     other MT*NT columns.
+//   * software pipeline over the tiles of a CTA: the h tile of tile i + 1 is built while the tensor core computes the
+//     logits of tile i; GEMM order per tile is gamma1 -> pos -> logits so the pos GEMMs run under epilogue 2.
 // warp 0 = TMA weight producer, warp 1 = MMA issuer (+TMEM alloc), warps 2.. = SETS*MT*4 "channel" warps
 // (two sets of channel warps share the TMEM lanes and split the tile's queries, doubling the warps that hide the
 // neighbour-gather latency).
