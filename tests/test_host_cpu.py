@@ -319,3 +319,35 @@ def test_two_rank_sharding_and_gather_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_bench_line_contract_keys():
+    """bench.py's JSON line must carry every key of the measurement contract (a stray comment once swallowed
+    `roofline`): checked on the source without a GPU, and the CPU reference arm is run for real."""
+    import ast
+    import json
+    import subprocess
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    dicts = [n.value for n in ast.walk(tree) if isinstance(n, ast.Assign) and isinstance(n.value, ast.Dict)
+             and any(isinstance(t, ast.Name) and t.id == "line" for t in n.targets)]
+    assert len(dicts) == 2                                   # the reference arm's line and ours
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "cpu_baseline"}
+    for d in dicts:
+        keys = {k.value for k in d.keys if isinstance(k, ast.Constant)}
+        assert need <= keys, need - keys
+    ours = max(dicts, key=lambda d: len(d.keys))
+    keys = {k.value for k in ours.keys if isinstance(k, ast.Constant)}
+    assert {"roofline", "path_roofline", "clocks", "kernel_breakdown_ms_per_step"} <= keys
+    # the reference arm is CPU-only: one bounded step of the small workload, one JSON line on stdout
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small_v4_b8",
+                          "--steps", "1", "--warmup", "1", "--cpu-sample-batch", "1"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
