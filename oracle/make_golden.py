@@ -106,6 +106,50 @@ def write_parametric_golden():
     print("mano_medium_b2", {k: tuple(v.shape) for k, v in cap.items()}, cap["pred_pose"][0, :2], cap["pred_shape"][0, :3])
 
 
+LOSS_WEIGHTS = {"HEATMAP_JOINTS_WEIGHT": 10.0, "JOINTS_LOSS_WEIGHT": 1.0, "VERTICES_LOSS_WEIGHT": 1.0,
+                "JOINTS_2D_LOSS_WEIGHT": 1.0, "VERTICES_2D_LOSS_WEIGHT": 0.5}   # release weights; 2-D vertex term switched on
+
+
+def run_reference_loss(B, V, seed, parametric):
+    """The real `PtEmbedMultiviewStereoV2.compute_loss` (lib/models/POEM.py:363-466) called on a shell object that
+    carries exactly the attributes the method reads (criteria as POEM.py:133-144 builds them for the release loss types)."""
+    ref_shim.install(synth.standin_template)
+    import types
+    from lib.utils.builder import BACKBONE, HEAD, build_from_cfg
+    sys.modules["lib.models.heads"].build_head = lambda cfg, **kw: build_from_cfg(cfg, HEAD, **kw)
+    bb = sys.modules.get("lib.models.backbones")
+    if bb is None:
+        _import_reference_hrnet()
+        bb = sys.modules.get("lib.models.backbones")
+    if bb is not None and not hasattr(bb, "build_backbone"):
+        bb.build_backbone = lambda cfg, **kw: build_from_cfg(cfg, BACKBONE, **kw)
+    import lib.models.POEM as poem_mod
+    cls = poem_mod.PtEmbedMultiviewStereoV2
+    mano = synth.synthetic_mano(11)
+    shell = types.SimpleNamespace(
+        heatmap_joints_weights=LOSS_WEIGHTS["HEATMAP_JOINTS_WEIGHT"], joints_weight=LOSS_WEIGHTS["JOINTS_LOSS_WEIGHT"],
+        vertices_weight=LOSS_WEIGHTS["VERTICES_LOSS_WEIGHT"], joints_2d_weight=LOSS_WEIGHTS["JOINTS_2D_LOSS_WEIGHT"],
+        vertices_2d_weight=LOSS_WEIGHTS["VERTICES_2D_LOSS_WEIGHT"], pose_weight=0.001, shape_weight=0.0005, num_joints=21,
+        mano_layer=types.SimpleNamespace(th_J_regressor=mano["J_regressor"]), parametric_output=parametric,
+        transformer_center_idx=9, criterion_joints=torch.nn.MSELoss(), criterion_vertices=torch.nn.L1Loss(),
+        criterion_parameters=torch.nn.MSELoss(), loss_proj_to_multicam=cls.loss_proj_to_multicam)
+    preds, gt = synth.make_loss_case(B, V, seed, parametric)
+    with torch.no_grad():
+        loss, ld = cls.compute_loss(shell, preds, gt)
+    assert torch.equal(loss, ld["loss"])
+    return {k: float(v) for k, v in ld.items()}
+
+
+def write_loss_golden():
+    cases = {"plain_ragged": (3, [2, 1, 3], 5, False), "parametric_v4": (2, 4, 6, True)}
+    out = {}
+    for name, (B, V, seed, par) in cases.items():
+        ld = run_reference_loss(B, V, seed, par)
+        out[name] = dict(B=B, V=V, seed=seed, parametric=par, losses=ld)
+        print("loss", name, ld)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "loss_cases.npz"), meta=np.array(repr(out)))
+
+
 def _import_reference_hrnet():
     ref_shim.install(synth.standin_template)
     import lib.external.metro.hrnet  # noqa: F401  (bare package; the backbone imports its config from there)
@@ -225,6 +269,8 @@ def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     if "--only-mano" in sys.argv:
         return write_parametric_golden()
+    if "--only-loss" in sys.argv:
+        return write_loss_golden()
     ys = run_reference_backbone(1, 0, 1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hrnet_w40_n1.npz"),
                         meta=np.array(repr(dict(kind="hrnet_w40", n_images=1, wseed=0, iseed=1, stride=4))),
@@ -248,6 +294,7 @@ def main():
                         y3=ys[3].numpy())
     print("hrnet_stage4_n2", [tuple(y.shape) for y in ys])
     write_parametric_golden()
+    write_loss_golden()
     for name, (size, views, wseed, iseed, mode) in CASES.items():
         cap = run_reference(size, views, wseed, iseed, mode)
         out = {

@@ -532,3 +532,77 @@ def pa_distances(gt, pred):
     gt, pred = np.asarray(gt, dtype=np.float32), np.asarray(pred, dtype=np.float32)
     al = np.stack([pa_align(g, p) for g, p in zip(gt, pred)])
     return np.stack([np.linalg.norm(al - gt, axis=2).mean(1), np.linalg.norm(pred - gt, axis=2).mean(1)], axis=1)
+
+
+# ------------------------------------------------------------------------------------------ f3 (training loss; groundwork)
+OPENPOSE_TIP_VERTS = (744, 320, 443, 555, 672)      # lib/utils/misc.py:76-82 (CONST.MANO_KPID_2_VERTICES)
+OPENPOSE_ORDER = (0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20)
+
+
+def mano_to_openpose(j_regressor, verts):
+    """lib/utils/transform.py:836-872: 16 regressed joints + the reference's own 5 tip vertices, re-ordered."""
+    j = torch.matmul(j_regressor, verts)
+    return torch.cat([j, verts[:, list(OPENPOSE_TIP_VERTS)]], dim=1)[:, list(OPENPOSE_ORDER)]
+
+
+def _project_to_views(points, T_m2c, K, view_counts):
+    """`batch_cam_extr_transf` + `batch_cam_intr_projection` (lib/utils/transform.py:898-930) of each sample's master-frame
+    points into all of its views: (B,P,3) -> (sum V, P, 2)."""
+    out, start = [], 0
+    for b, n in enumerate(view_counts):
+        T, Kb = T_m2c[start:start + n], K[start:start + n]
+        pc = torch.einsum("nrc,pc->npr", T[:, :3, :3], points[b]) + T[:, None, :3, 3]
+        q = torch.einsum("nrc,npc->npr", Kb, pc)
+        z = q[..., 2:]
+        z = torch.where(z.abs() < 1e-7, torch.full_like(z, 1e-7), z)
+        out.append(q[..., :2] / z)
+        start += n
+    return torch.cat(out)
+
+
+def compute_loss(preds, gt, weights, j_regressor, parametric=False, transformer_center_idx=9, num_joints=21):
+    """`PtEmbedMultiviewStereoV2.compute_loss` (lib/models/POEM.py:363-466) with the release loss types (joints l2,
+    vertices l1, parameters l2; config/release/train_*.yaml LOSS).  `weights`: dict with the cfg.LOSS weights.
+    Groundwork for SURVEY §8f row f3 (training path): pinned against the reference method in tests/golden/loss_*.npz;
+    no product kernel consumes it yet."""
+    coords = preds["all_coords_preds"]
+    views = [int(v) for v in gt["cam_view_num"]]
+    H, W = gt["image"].shape[-2:]
+    img_scale = math.sqrt(float(W ** 2 + H ** 2))
+    jg, vg = gt["master_joints_3d"].reshape(-1, 21, 3), gt["master_verts_3d"].reshape(-1, 778, 3)
+    out = {}
+    d = (preds["pred_joints_uv"] - gt["target_joints_2d"]) / img_scale
+    out["loss_heatmap_joints"] = (d ** 2).sum(2).mean()
+    loss = weights["HEATMAP_JOINTS_WEIGHT"] * out["loss_heatmap_joints"]
+    T = torch.linalg.inv(gt["target_cam_extr"].reshape(-1, 4, 4))
+    K = gt["target_cam_intr"].reshape(-1, 3, 3)
+    pj, pv = coords[-1, :, :num_joints], coords[-1, :, num_joints:]
+    out["loss_3d_joints_from_mesh"] = F.mse_loss(mano_to_openpose(j_regressor, pv), mano_to_openpose(j_regressor, vg))
+    out["loss_3d_joints"] = F.mse_loss(pj, jg)
+    recon = weights["JOINTS_LOSS_WEIGHT"] * (out["loss_3d_joints"] + out["loss_3d_joints_from_mesh"])
+    if parametric:
+        c = jg[:, transformer_center_idx:transformer_center_idx + 1]
+        out["loss_3d_verts"] = F.l1_loss(pv - c, vg - c)
+    else:
+        out["loss_3d_verts"] = F.l1_loss(pv, vg)
+    recon = recon + weights["VERTICES_LOSS_WEIGHT"] * out["loss_3d_verts"]
+
+    def proj_loss(points, target_2d):                      # loss_proj_to_multicam, POEM.py:335-361
+        off = torch.clamp(_project_to_views(points, T, K, views) - target_2d, min=-0.5 * img_scale,
+                          max=0.5 * img_scale) / img_scale
+        return (off ** 2).sum(2).mean()
+    if weights.get("JOINTS_2D_LOSS_WEIGHT", 0.0) != 0:
+        out["loss_2d_joints"] = proj_loss(pj, gt["target_joints_2d"])
+        recon = recon + weights["JOINTS_2D_LOSS_WEIGHT"] * out["loss_2d_joints"]
+    if weights.get("VERTICES_2D_LOSS_WEIGHT", 0.0) != 0:
+        out["loss_2d_verts"] = proj_loss(pv, _project_to_views(vg, T, K, views))
+        recon = recon + weights["VERTICES_2D_LOSS_WEIGHT"] * out["loss_2d_verts"]
+    if parametric:
+        first = [sum(views[:j]) for j in range(len(views))]
+        out["loss_pose"] = F.mse_loss(preds["pred_pose"], gt["mano_pose"][first])
+        out["loss_shape"] = F.mse_loss(preds["pred_shape"], gt["mano_shape"][first])
+        recon = recon + weights.get("POSE_LOSS_WEIGHT", 0.001) * out["loss_pose"] \
+            + weights.get("SHAPE_LOSS_WEIGHT", 0.0005) * out["loss_shape"]
+    out["loss_recon"] = recon
+    out["loss"] = loss + recon
+    return out

@@ -294,3 +294,26 @@ def make_batch(B: int, V, seed: int = 1):
     return {"image": make_images(sum(views), 256, seed), "cam_view_num": np.array(views), "target_cam_intr": intr,
             "target_cam_extr": extr, "master_id": [0] * B,
             "master_joints_3d": torch.tensor([0.0, 0.0, 0.6]) + 0.03 * torch.randn(B, 21, 3, generator=g)}
+
+
+def make_loss_case(B: int, V, seed: int = 1, parametric: bool = False, n_blocks: int = 3):
+    """Seeded (preds, gt) pair for the training loss (reference POEM.py:363-466): predictions a few mm / px away from
+    the ground truth, ragged view counts allowed."""
+    views = _view_list(B, V)
+    nv = sum(views)
+    intr, extr = make_cameras(B, V, seed)
+    g = torch.Generator().manual_seed(seed + 31)
+    c0 = torch.tensor([0.0, 0.0, 0.6])
+    jg = c0 + 0.03 * torch.randn(B, 21, 3, generator=g)
+    vg = c0 + 0.03 * torch.randn(B, 778, 3, generator=g)
+    gt = {"image": torch.zeros(nv, 3, 256, 256), "cam_view_num": np.array(views), "target_cam_intr": intr,
+          "target_cam_extr": extr, "master_joints_3d": jg, "master_verts_3d": vg,
+          "target_joints_2d": 128.0 + 60.0 * torch.randn(nv, 21, 2, generator=g)}
+    coords = torch.cat([jg, vg], dim=1)[None] + 0.004 * torch.randn(n_blocks, B, 799, 3, generator=g)
+    preds = {"all_coords_preds": coords, "pred_joints_uv": gt["target_joints_2d"] + 3.0 * torch.randn(nv, 21, 2, generator=g)}
+    if parametric:
+        gt["mano_pose"] = 0.3 * torch.randn(nv, 16, 3, generator=g)
+        gt["mano_shape"] = torch.randn(nv, 10, generator=g)
+        preds["pred_pose"] = 0.3 * torch.randn(B, 16, 3, generator=g)
+        preds["pred_shape"] = torch.randn(B, 10, generator=g)
+    return preds, gt
