@@ -150,6 +150,55 @@ def write_loss_golden():
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "loss_cases.npz"), meta=np.array(repr(out)))
 
 
+GRAD_KEYS = ["input_proj.weight", "adapt_pos3d.bias", "merge_net_feature.0.2.weight", "merge_net_feature.1.2.bias",
+             "query_feat_embedding.weight", "transformer.pt_metro_encoder.0.embedding.weight",
+             "transformer.pt_metro_encoder.0.encoder.attn.self.key.weight",
+             "transformer.pt_metro_encoder.1.encoder.cross_attn.output.LayerNorm.weight",
+             "transformer.pt_metro_encoder.1.encoder.vec_attn.query_self_attn.fc_gamma.0.weight",
+             "transformer.pt_metro_encoder.2.encoder.vec_attn.query_cross_attn.fc_delta.0.weight",
+             "transformer.pt_metro_encoder.2.encoder.vec_attn.query_cross_attn.w_vs.weight",
+             "transformer.pt_metro_encoder.2.encoder.vec_attn.reg_branch.2.weight",
+             "transformer.pt_metro_encoder.0.encoder.output.dense.weight"]
+
+
+def grad_loss(coords, seed):
+    """Scalar used for the gradient golden: squared distance (mm^2) of every block's prediction to a seeded target."""
+    g = torch.Generator().manual_seed(seed + 77)
+    target = coords.detach() + 0.005 * torch.randn(coords.shape, generator=g)
+    return ((coords - target) * 1e3).pow(2).mean()
+
+
+def run_reference_grads(size, views, wseed, iseed):
+    """Autograd of the real reference head (eval mode: dropout off; the 32-NN indices are constants of the graph)."""
+    dims = release_dims(size)
+    head, _ = ref_shim.build_reference_head(size, template_fn=synth.standin_template)
+    sd = synth.make_state_dict(dims, wseed, "stress")
+    head.load_state_dict(sd, strict=False)
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, iseed)
+    params = dict(head.named_parameters())
+    for p_ in params.values():
+        p_.requires_grad_(False)
+    for k in GRAD_KEYS:
+        params[k].requires_grad_(True)
+    res = head(mlvl_feat=feat, img_metas=metas, reference_joints=ref_j, debug_metas=None)
+    loss = grad_loss(res["all_coords_preds"], iseed)
+    loss.backward()
+    out = {"loss": np.array(loss.item())}
+    for k in GRAD_KEYS:
+        g = params[k].grad.detach().reshape(-1)
+        out["norm:" + k] = np.array(float(g.norm()))
+        out["head:" + k] = g[:: max(1, g.numel() // 64)][:64].numpy().copy()
+    return out
+
+
+def write_grad_golden():
+    size, views, wseed, iseed = "small", [2, 1], 1, 3
+    out = run_reference_grads(size, views, wseed, iseed)
+    meta = dict(size=size, views=views, wseed=wseed, iseed=iseed, keys=GRAD_KEYS)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "grad_small_b2.npz"), meta=np.array(repr(meta)), **out)
+    print("grad_small_b2 loss", float(out["loss"]), {k[5:]: float(out[k]) for k in out if k.startswith("norm:")})
+
+
 def _import_reference_hrnet():
     ref_shim.install(synth.standin_template)
     import lib.external.metro.hrnet  # noqa: F401  (bare package; the backbone imports its config from there)
@@ -271,6 +320,8 @@ def main():
         return write_parametric_golden()
     if "--only-loss" in sys.argv:
         return write_loss_golden()
+    if "--only-grad" in sys.argv:
+        return write_grad_golden()
     ys = run_reference_backbone(1, 0, 1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "hrnet_w40_n1.npz"),
                         meta=np.array(repr(dict(kind="hrnet_w40", n_images=1, wseed=0, iseed=1, stride=4))),
@@ -295,6 +346,7 @@ def main():
     print("hrnet_stage4_n2", [tuple(y.shape) for y in ys])
     write_parametric_golden()
     write_loss_golden()
+    write_grad_golden()
     for name, (size, views, wseed, iseed, mode) in CASES.items():
         cap = run_reference(size, views, wseed, iseed, mode)
         out = {

@@ -9,7 +9,7 @@ from poem_v2_b200 import synth
 from poem_v2_b200.config import release_dims
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("hrnet", "image_stage", "metrics", "mano", "loss")))
+CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("hrnet", "image_stage", "metrics", "mano", "loss", "grad")))
 
 
 def load_case(name):
