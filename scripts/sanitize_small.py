@@ -1,0 +1,19 @@
+"""Tiny decoder forwards for compute-sanitizer (memcheck): POEM-small head (B=2, ragged views) and the medium_MANO head."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from poem_v2_b200 import synth
+from poem_v2_b200.config import release_dims
+from poem_v2_b200.head import POEM_Generalized_Head
+
+for size, mano in (("small", None), ("medium_MANO", synth.synthetic_mano(11))):
+    dims = release_dims(size)
+    head = POEM_Generalized_Head(dims, template_mesh=None if mano else synth.standin_template(), mano_params=mano)
+    head.load_state_dict(synth.make_state_dict(dims, 0), strict=True)
+    head = head.cuda().eval()
+    feat, metas, ref_j = synth.make_inputs(dims, 2, [2, 1], 1)
+    m = dict(metas)
+    m["cam_intr"], m["cam_extr"] = metas["cam_intr"].cuda(), metas["cam_extr"].cuda()
+    out = head(mlvl_feat=feat.cuda(), img_metas=m, reference_joints=ref_j.cuda())
+    torch.cuda.synchronize()
+    print(size, {k: tuple(v.shape) for k, v in out.items()}, "finite", bool(torch.isfinite(out["all_coords_preds"]).all()))
