@@ -351,3 +351,53 @@ def test_bench_line_contract_keys():
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def _ragged_samples(seed=0):
+    rng = np.random.default_rng(seed)
+    samples = []
+    for v in (3, 1, 2):
+        samples.append({"image": rng.standard_normal((v, 3, 8, 8)).astype(np.float32),
+                        "target_joints_3d": rng.standard_normal((v, 21, 3)).astype(np.float32),
+                        "target_cam_intr": rng.standard_normal((v, 3, 3)).astype(np.float32),
+                        "target_cam_extr": rng.standard_normal((v, 4, 4)).astype(np.float64),
+                        "master_joints_3d": rng.standard_normal((1, 21, 3)).astype(np.float32),
+                        "image_path": np.array([f"cam{i}.png" for i in range(v)]),
+                        "master_id": 0, "sample_idx": [int(rng.integers(100)) for _ in range(v)]})
+    return samples
+
+
+def test_collation_mirror():
+    """`collation_random_n_views` (reference lib/utils/collation.py:7-25): ragged view counts -> flat (sum V, ...)
+    float32 tensors + cam_view_num; non-numeric fields are listed per sample; a single sample is accepted."""
+    from poem_v2_b200.collation import collation_random_n_views
+    samples = _ragged_samples()
+    out = collation_random_n_views(samples)
+    assert out["cam_view_num"].tolist() == [3, 1, 2]
+    assert out["image"].shape == (6, 3, 8, 8) and out["image"].dtype == torch.float32
+    assert out["target_cam_extr"].dtype == torch.float32            # torch.Tensor(...) casts like the reference
+    assert out["master_joints_3d"].shape == (3, 21, 3)
+    assert torch.equal(out["target_joints_3d"][3:4], torch.from_numpy(samples[1]["target_joints_3d"]))
+    assert out["master_id"] == [0, 0, 0] and len(out["image_path"]) == 3 and list(out["image_path"][0]) == ["cam0.png", "cam1.png", "cam2.png"]
+    one = collation_random_n_views(samples[0])
+    assert one["cam_view_num"].tolist() == [3] and one["image"].shape == (3, 3, 8, 8)
+    if os.path.isdir("/root/reference/lib"):                         # against the reference function itself
+        import importlib.util
+        import types
+        pkg = types.ModuleType("_refcol"); pkg.__path__ = []
+        utils = types.ModuleType("_refcol.utils"); utils.__path__ = []
+        tr = types.ModuleType("_refcol.utils.transform")
+        tr.batch_cam_extr_transf = tr.batch_cam_intr_projection = None
+        sys.modules.update({"_refcol": pkg, "_refcol.utils": utils, "_refcol.utils.transform": tr})
+        spec = importlib.util.spec_from_file_location("_refcol.utils.collation", "/root/reference/lib/utils/collation.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        want = mod.collation_random_n_views(_ragged_samples())
+        assert set(want) == set(out)
+        for k, v in want.items():
+            if torch.is_tensor(v):
+                assert torch.equal(v, out[k]), k
+            elif isinstance(v, np.ndarray):
+                assert np.array_equal(v, out[k]), k
+            else:
+                assert all(np.array_equal(a, b) for a, b in zip(v, out[k])), k
