@@ -3,6 +3,12 @@
 Samples are independent units of the decoder path (all views of a sample stay together because the cross-view
 merge mixes them), so N ranks each run the whole path on a contiguous slice of the batch; there is no
 data-path collective.  The only optional exchange is an all_gather of the (NB, B/N, 799, 3) results.
+
+When there are fewer samples than GPUs (serving: one sample, eight views, eight GPUs) the image half is the part that
+still shards: the B*V images are split across the ranks (`image_bounds`), every rank runs backbone + feat_decode on its
+images and ONE all_gather exchanges the (., 160, 16, 16) feature maps (`gather_features`, 82 KB per image in bf16, 164
+KB in fp32) — the single real exchange step of the path; the decoder then runs on the sample-sharding
+above (ranks without a sample idle through it).
 """
 import numpy as np
 import torch
@@ -59,4 +65,30 @@ def gather_outputs(local_coords, batch_total, bounds, group=None):
     out = torch.empty(nb, batch_total, q, 3, dtype=local_coords.dtype, device=local_coords.device)
     for (s, e), part in zip(bounds, parts):
         out[:, s:e] = part[:, :e - s]
+    return out
+
+
+def image_bounds(n_images, world_size):
+    """Contiguous split of the flat image axis into `world_size` near-equal slices [(i0, i1), ...] (may be empty)."""
+    base, extra = divmod(int(n_images), world_size)
+    bounds, start = [], 0
+    for r in range(world_size):
+        end = start + base + (1 if r < extra else 0)
+        bounds.append((start, end))
+        start = end
+    return bounds
+
+
+def gather_features(local_feat, n_images, bounds, group=None):
+    """all_gather of the per-rank feature maps (n_r, C, h, w) into (n_images, C, h, w) on every rank: the exchange step
+    of the image-sharded mode.  Slices are padded to the widest one so a single fixed-size collective moves them."""
+    world = dist.get_world_size(group)
+    width = max(e - s for s, e in bounds)
+    pad = torch.zeros((width,) + tuple(local_feat.shape[1:]), dtype=local_feat.dtype, device=local_feat.device)
+    pad[:local_feat.shape[0]] = local_feat
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = torch.empty((int(n_images),) + tuple(local_feat.shape[1:]), dtype=local_feat.dtype, device=local_feat.device)
+    for (s, e), part in zip(bounds, parts):
+        out[s:e] = part[:e - s]
     return out

@@ -288,6 +288,8 @@ def test_shard_bounds_cover_and_balance():
         assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
         assert all(e >= s for s, e in b)
     assert shard.shard_bounds([8] * 32, 8) == [(4 * r, 4 * r + 4) for r in range(8)]
+    assert shard.image_bounds(8, 8) == [(r, r + 1) for r in range(8)]
+    assert shard.image_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)] and shard.image_bounds(2, 4)[2:] == [(2, 2), (2, 2)]
 
 
 def _gloo_worker(rank, world, port, q):
@@ -303,7 +305,14 @@ def _gloo_worker(rank, world, port, q):
     bounds = shard.shard_bounds(views, world)
     full = shard.gather_outputs(local, len(views), bounds)
     want = torch.stack([ref_j[:, :1, :].expand(-1, 799, -1) + i for i in range(3)])
-    q.put((rank, bool(torch.equal(full, want))))
+    ok = bool(torch.equal(full, want))
+    # image-sharded mode (fewer samples than ranks): every rank "extracts" the features of its images, one all_gather
+    n_img = feat.shape[0]
+    ib = shard.image_bounds(n_img, world)
+    i0, i1 = ib[rank]
+    gathered = shard.gather_features(feat[i0:i1] * 2.0, n_img, ib)
+    ok = ok and bool(torch.equal(gathered, feat * 2.0))
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
