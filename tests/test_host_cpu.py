@@ -410,3 +410,22 @@ def test_collation_mirror():
                 assert np.array_equal(v, out[k]), k
             else:
                 assert all(np.array_equal(a, b) for a, b in zip(v, out[k])), k
+
+
+def test_poly_exp2_constants_in_the_kernel_source():
+    """The FMA-pipe 2^x of the attention kernel (csrc/common.cuh `poly_exp2`): its constants are read from the source and
+    the same arithmetic is replayed in float32 — relative error <= 8e-5 on [-30, 0.5], far below the bf16 rounding of the
+    probabilities it produces."""
+    src = open(os.path.join(ROOT, "poem-v2_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float poly_exp2(float x)"):]
+    body = body[:body.index("return __int_as_float")]
+    c3, c2, c1, c0 = [np.float32(v) for v in re.findall(r"(\d\.\d+)f", body)][-4:]
+    assert "12582912.f" in body and "-126.f" in body
+    x = np.linspace(-30, 0.5, 400001).astype(np.float32)
+    t = (x + np.float32(12582912.0)).astype(np.float32)
+    f = (x - (t - np.float32(12582912.0))).astype(np.float32)
+    assert np.abs(f).max() <= 0.5
+    p = ((c3 * f + c2) * f + c1) * f + c0
+    got = (p.astype(np.float32).view(np.int32) + (t.view(np.int32) << 23)).view(np.float32)
+    ref = np.exp2(x.astype(np.float64))
+    assert np.max(np.abs(got / ref - 1.0)) <= 8e-5
