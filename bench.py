@@ -409,10 +409,10 @@ def main():
     R = B * V * dims.n_sample
     # algorithmic bytes / flops per launch for the launch classes that can dominate
     per_launch = {
-        "gemm_bf16_tc_kernel:va_token": ("hbm", T * D * 2 * 2 + D * D * 2, 2.0 * T * D * D),
-        "gemm_bf16_tc_kernel:merge0a": ("hbm", R * D * 2 * 2 + D * D * 2, 2.0 * R * D * D),
-        "gemm_bf16_tc_kernel:merge0b": ("hbm", R * D * 2 + R * D + D * D, 1.0 * R * D * D),
-        "gemm_bf16_tc_kernel:pt_proj": ("hbm", B * 4096 * D * 2 * 7 + 6 * D * D * 2, 2.0 * B * 4096 * D * 6 * D),
+        "gemm_op16_tc_kernel:va_token": ("hbm", T * D * 2 * 2 + D * D * 2, 2.0 * T * D * D),
+        "gemm_op16_tc_kernel:merge0a": ("hbm", R * D * 2 * 2 + D * D * 2, 2.0 * R * D * D),
+        "gemm_op16_tc_kernel:merge0b": ("hbm", R * D * 2 + R * D + D * D, 1.0 * R * D * D),
+        "gemm_op16_tc_kernel:pt_proj": ("hbm", B * 4096 * D * 2 * 7 + 6 * D * D * 2, 2.0 * B * 4096 * D * 6 * D),
         "mha_fwd_tc_kernel": ("tensor", 0, 4.0 * B * dims.n_query * 4096 * D),
         "va_fused_kernel": ("tensor", 0, 6.0 * T * D * D),
     }

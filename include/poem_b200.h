@@ -12,7 +12,7 @@
  *   - all device buffers are caller-allocated; the library allocates nothing and keeps no mutable global
  *     state besides the last-error string (thread local)
  *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*)
- *   - "bf16" buffers are raw 16-bit bfloat16 (uint16_t storage)
+ *   - "op16" buffers are raw 16-bit bfloat16 (uint16_t storage)
  */
 #ifndef POEM_B200_H
 #define POEM_B200_H
@@ -33,7 +33,7 @@ extern "C" {
 #define POEM_E_CUDA (-4)        /* CUDA runtime / driver error */
 #define POEM_E_ALIGN (-5)       /* pointer or leading dimension not 16-byte aligned */
 
-typedef uint16_t poem_bf16;
+typedef uint16_t poem_op16;
 
 /* Dimensions read from cfg.MODEL.HEAD (ptEmb_head.py:57-76,686-695; ptEmb_transformer.py:312-324). */
 typedef struct PoemDims {
@@ -52,9 +52,9 @@ typedef struct PoemDims {
   int32_t run_last_ffn; /* 1 if the last block's FFN output is needed (parametric tail) */
 } PoemDims;
 
-/* One Linear layer in kernel layout: weight bf16 [out, in] row-major (K-major), bias fp32 [out] or NULL. */
+/* One Linear layer in kernel layout: weight op16 [out, in] row-major (K-major), bias fp32 [out] or NULL. */
 typedef struct PoemLinear {
-  const poem_bf16* w;
+  const poem_op16* w;
   const float* b;
 } PoemLinear;
 
@@ -141,6 +141,12 @@ void poem_debug_force_unfused(int on);
  * kernel on all padded channels; 2 = every convolution takes the generic implicit-GEMM path (so the variants can be
  * compared on the device). */
 void poem_debug_conv_mode(int mode);
+/* Test hook: while `device_buf` is non-NULL, every whole-path / transformer call of this host thread copies the
+ * 32-NN index sets it used in blocks 1..NB-1 into it (device int32, layout [block - 1][0 = self, 1 = cross][B*Q*32];
+ * a call that needs more than `capacity` int32 fails with POEM_E_WORKSPACE).  32-NN selection is discontinuous in the
+ * regressed coordinates, so the parity tests compare against the oracle run on the SAME sets, and check the sets
+ * separately (bit-exact given the coordinates).  NULL disables.  Not used by the product path. */
+void poem_debug_export_neighbours(int32_t* device_buf, size_t capacity);
 
 /* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
 size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);
@@ -216,8 +222,8 @@ int poem_head_forward_host(const PoemDims* dims, const PoemWeights* w, const Poe
 
 /* ---- HRNet-W40 stage 4 (reference lib/models/backbones/hrnet.py:272-277: 3 HighResolutionModules of 4 branches x
  * 4 BasicBlocks + all-to-all fuse layers).  Convolution weights have eval-mode BatchNorm folded in and are stored as
- * bf16 [Cout_p, k*k*Cin_p] (K ordered (ky, kx, c); channel counts padded to multiples of 64 with zeros), bias fp32
- * [Cout_p].  Activations are converted NCHW fp32 <-> NHWC bf16 inside the call. */
+ * op16 [Cout_p, k*k*Cin_p] (K ordered (ky, kx, c); channel counts padded to multiples of 64 with zeros), bias fp32
+ * [Cout_p].  Activations are converted NCHW fp32 <-> NHWC op16 inside the call. */
 #define POEM_HR_MAX_MODULES 4
 typedef struct PoemHRModule {
   PoemLinear branch[4][4][2];   /* [branch][block][conv1 | conv2] */
@@ -300,28 +306,28 @@ int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, const float*
 int poem_pa_metrics(const float* gt, const float* pred, int batch, int n_points, float* out, float* aligned,
                     void* stream);
 
-/* One convolution of the stage (building block of the call above): NHWC bf16 in/out, channels padded to 64,
- * w bf16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
+/* One convolution of the stage (building block of the call above): NHWC op16 in/out, channels padded to 64,
+ * w op16 [Cout_p, k*k*Cin_p], b fp32 [Cout_p], ksize 1|3 (padding k/2), stride 1|2, optional ReLU and NHWC residual.
  * c_live_in / c_live_out > 0 promise that only the first c_live_in input / c_live_out output channels are non-zero
  * (the rest of the padded tensors, weights and bias is zero padding), which lets the 3x3 stride-1 kernel skip the
  * padding; 0 = no promise.
  * Replaces nn.Conv2d + nn.BatchNorm2d(eval) (+ReLU, + identity) of hrnet.py:38-67,177-207. */
-int poem_conv_nhwc(const poem_bf16* in, int n_images, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
-                   int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out, int c_live_in,
+int poem_conv_nhwc(const poem_op16* in, int n_images, int H, int W, int Cin_p, const poem_op16* w, const float* b,
+                   int Cout_p, int ksize, int stride, int relu, const poem_op16* res, poem_op16* out, int c_live_in,
                    int c_live_out, void* stream);
 
 /* ---- stage-level entry points (unit-testable building blocks; same kernels the whole path uses) ---- */
 
-/* C = act(A·W^T + bias) (+ residual); A bf16 [M,K] (lda), W bf16 [N,K] (ldw); outputs optional.
+/* C = act(A·W^T + bias) (+ residual); A op16 [M,K] (lda), W op16 [N,K] (ldw); outputs optional.
  * act: 0 none, 1 relu, 2 gelu(erf).  Replaces nn.Linear / 1x1 nn.Conv2d call sites (cuBLAS/cuDNN). */
-int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N, int K,
-                int act, const float* residual, int ld_res, float* out_f32, int ld_f32, poem_bf16* out_bf16,
-                int ld_bf16, void* stream);
+int poem_linear(const poem_op16* A, int lda, const poem_op16* W, int ldw, const float* bias, int M, int N, int K,
+                int act, const float* residual, int ld_res, float* out_f32, int ld_f32, poem_op16* out_op16,
+                int ld_op16, void* stream);
 
-/* softmax(Q K^T / sqrt(hd)) V per head, no mask.  Q bf16 [B*Lq, ldq], K bf16 [B*Lk, ldk], V bf16 [B*Lk, ldv] (all
- * row-major, head h in columns [h*hd, (h+1)*hd)), ctx bf16 [B*Lq, ld_ctx].  Lk % 128 == 0.
+/* softmax(Q K^T / sqrt(hd)) V per head, no mask.  Q op16 [B*Lq, ldq], K op16 [B*Lk, ldk], V op16 [B*Lk, ldv] (all
+ * row-major, head h in columns [h*hd, (h+1)*hd)), ctx op16 [B*Lq, ld_ctx].  Lk % 128 == 0.
  * Replaces HF BertSelfAttention's matmul-softmax-matmul (pt_metro_transformer.py:57-72). */
-int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* V, int ldv, poem_bf16* ctx,
+int poem_mha(const poem_op16* Q, int ldq, const poem_op16* K, int ldk, const poem_op16* V, int ldv, poem_op16* ctx,
              int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream);
 
 /* idx int32 [B, Lq, 32]: 32 nearest reference points, ascending squared-L2, lower index wins ties.
@@ -334,26 +340,26 @@ int poem_knn32_bps(const float* query_xyz, const float* ref_xyz_sorted, const in
                    int32_t* idx, int B, int Lq, int Lr, void* stream);
 
 /* Camera projection + bilinear sampling in the reference's reinterpreted (token, view, channel) row order.
- * xmap fp32 [n_images, D, fh*fw]; X bf16 [sum_views*P, D].  Replaces collation.py:48-65 + F.grid_sample +
+ * xmap fp32 [n_images, D, fh*fw]; X op16 [sum_views*P, D].  Replaces collation.py:48-65 + F.grid_sample +
  * the raw .view regroup (ptEmb_head.py:874-915). */
 int poem_project_sample(const float* xmap, const float* cam_intr, const float* cam_extr, const float* bps,
                         const float* centre, const int32_t* host_view_counts, int B, int n_images, int D, int P,
-                        int fh, int fw, float img_w, float img_h, poem_bf16* X, void* workspace,
+                        int fh, int fw, float img_w, float img_h, poem_op16* X, void* workspace,
                         size_t workspace_bytes, void* stream);
 
 /* Vector attention core: res[b,i,:] = sum_j softmax_j(gamma(q_i - k_j + pos_ij)/sqrt(D)) * (v_j + pos_ij),
  * pos_ij = delta(xyz_i - nbr_xyz_j), in the folded form documented at PoemVecAttn:
- * q = qt bf16 [B*Lq, ldq]; ktab = kt, vtab = v bf16 [B*Lr, ldk/ldv]; idx int32 [B*Lq*32]
- * (or NULL with anchors: anchor_idx int32[32], anchor_xyz fp32[32,3]); res bf16 [B*Lq, D].
+ * q = qt op16 [B*Lq, ldq]; ktab = kt, vtab = v op16 [B*Lr, ldk/ldv]; idx int32 [B*Lq*32]
+ * (or NULL with anchors: anchor_idx int32[32], anchor_xyz fp32[32,3]); res op16 [B*Lq, D].
  * Replaces point_transformers.py:86-94 / 139-150. */
-int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, int ldq, const poem_bf16* ktab, int ldk,
-                          const poem_bf16* vtab, int ldv, const float* q_xyz, const float* ref_xyz,
+int poem_vector_attention(const PoemVecAttn* w, const poem_op16* q, int ldq, const poem_op16* ktab, int ldk,
+                          const poem_op16* vtab, int ldv, const float* q_xyz, const float* ref_xyz,
                           const int32_t* idx, const int32_t* anchor_idx, const float* anchor_xyz, int B, int Lq,
-                          int Lr, int D, poem_bf16* res, void* workspace, size_t workspace_bytes, void* stream);
+                          int Lr, int D, poem_op16* res, void* workspace, size_t workspace_bytes, void* stream);
 size_t poem_vector_attention_workspace_bytes(int B, int Lq, int D);
 
 /* y = LayerNorm(x) over the last dim, eps 1e-12 (HF BertSelfOutput/BertOutput). */
-int poem_layernorm(const float* x, const float* gamma, const float* beta, float* y_f32, poem_bf16* y_bf16, int rows,
+int poem_layernorm(const float* x, const float* gamma, const float* beta, float* y_f32, poem_op16* y_op16, int rows,
                    int D, void* stream);
 
 #ifdef __cplusplus

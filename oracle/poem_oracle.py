@@ -144,15 +144,16 @@ def _vector_attention_core(sd, p, q, k, v, rel):
     return (a * (v + pos)).sum(dim=2)
 
 
-def vec_self_attention(sd, p, xyz, feats, K, anchors=None):
-    """`ptTransformerBlock._forward` (lib/models/bricks/point_transformers.py:70-96)."""
+def vec_self_attention(sd, p, xyz, feats, K, anchors=None, idx_forced=None):
+    """`ptTransformerBlock._forward` (lib/models/bricks/point_transformers.py:70-96).
+    `idx_forced` (test hook, not in the reference): use these neighbour indices instead of running `knn`."""
     B = xyz.shape[0]
     if anchors is not None:                                          # block 0: fixed anchors for every query
         a_xyz, a_idx = anchors
         idx = a_idx[None, None].expand(B, xyz.shape[1], -1)
         nbr_xyz = a_xyz[None, None].expand(B, xyz.shape[1], -1, -1)
     else:
-        idx = knn(xyz, xyz, K)
+        idx = knn(xyz, xyz, K) if idx_forced is None else idx_forced
         nbr_xyz = gather_rows(xyz, idx)
     x = F.linear(feats, sd[p + "fc1.weight"], sd[p + "fc1.bias"])
     q = F.linear(x, sd[p + "w_qs.weight"])
@@ -162,15 +163,16 @@ def vec_self_attention(sd, p, xyz, feats, K, anchors=None):
     return F.linear(res, sd[p + "fc2.weight"], sd[p + "fc2.bias"]) + feats, idx
 
 
-def vec_cross_attention(sd, p, pt_xyz, pt_feats, q_xyz, q_feats, K, anchors=None):
-    """`ptTransformerBlock_CrossAttn._forward` (lib/models/bricks/point_transformers.py:125-156)."""
+def vec_cross_attention(sd, p, pt_xyz, pt_feats, q_xyz, q_feats, K, anchors=None, idx_forced=None):
+    """`ptTransformerBlock_CrossAttn._forward` (lib/models/bricks/point_transformers.py:125-156).
+    `idx_forced`: see `vec_self_attention`."""
     B = q_xyz.shape[0]
     if anchors is not None:                                          # anchor idx gathers rows of the 4096-row table
         a_xyz, a_idx = anchors
         idx = a_idx[None, None].expand(B, q_xyz.shape[1], -1)
         nbr_xyz = a_xyz[None, None].expand(B, q_xyz.shape[1], -1, -1)
     else:
-        idx = knn(q_xyz, pt_xyz, K)
+        idx = knn(q_xyz, pt_xyz, K) if idx_forced is None else idx_forced
         nbr_xyz = gather_rows(pt_xyz, idx)
     nf = gather_rows(pt_feats, idx)
     q = F.linear(q_feats, sd[p + "w_qs.weight"])
@@ -182,7 +184,7 @@ def vec_cross_attention(sd, p, pt_xyz, pt_feats, q_xyz, q_feats, K, anchors=None
 
 
 # ------------------------------------------------------------------------------------------ a9-a11
-def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=None):
+def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=None, neighbours=None):
     """`point_METRO_block.forward` + `point_METRO_layer.forward` + `pointer_layer.forward`
     (lib/models/bricks/pt_metro_transformer.py:153-200, 56-91, 34-40); eval mode (dropout = identity)."""
     p = f"transformer.pt_metro_encoder.{i}."
@@ -192,9 +194,10 @@ def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=N
     a1 = bert_cross_attention(sd, p + "encoder.attn", qe, ke, dims.n_heads)
     a2 = bert_cross_attention(sd, p + "encoder.cross_attn", a1, ke, dims.n_heads)
     anc = anchors if i == 0 else None
-    f1, idx_s = vec_self_attention(sd, p + "encoder.vec_attn.query_self_attn.", q_xyz, a2, dims.n_neighbor, anc)
+    nb_s, nb_c = (None, None) if (neighbours is None or i == 0) else neighbours
+    f1, idx_s = vec_self_attention(sd, p + "encoder.vec_attn.query_self_attn.", q_xyz, a2, dims.n_neighbor, anc, nb_s)
     f2, idx_c = vec_cross_attention(sd, p + "encoder.vec_attn.query_cross_attn.", pt_xyz, ke, q_xyz, f1,
-                                    dims.n_neighbor, anc)
+                                    dims.n_neighbor, anc, nb_c)
     xyz = _mlp2(sd, p + "encoder.vec_attn.reg_branch", f2) + q_xyz
     h = F.gelu(F.linear(f2, sd[p + "encoder.intermediate.dense.weight"], sd[p + "encoder.intermediate.dense.bias"]))
     o = F.linear(h, sd[p + "encoder.output.dense.weight"], sd[p + "encoder.output.dense.bias"])
@@ -327,8 +330,11 @@ def parametric_tail(sd, i, dims, feats, xyz, mano):
 
 # ------------------------------------------------------------------------------------------ a1
 def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anchor_xyz, anchor_idx, stages=None,
-                 mano=None):
+                 mano=None, neighbours=None):
     """`POEM_Generalized_Head.forward` (lib/models/heads/ptEmb_head.py:825-964).
+    `neighbours` (test hook, not in the reference): (NB-1, 2, B, Q, K) int64 — the 32-NN index sets (self, cross) to use
+    in blocks 1..NB-1 instead of running `knn`, so that a device run and the oracle can be compared on the same sets
+    (32-NN selection is discontinuous in the coordinates).
     Returns all_coords_preds (NB,B,799,3) in metres; with `dims.parametric` (medium_MANO) the last block goes
     through the MANO tail and (coords, pred_pose (B,16,3), pred_shape (B,10)) is returned."""
     views = [int(v) for v in img_metas["cam_view_num"]]
@@ -336,7 +342,7 @@ def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anc
     inp_w, inp_h = img_metas["inp_img_shape"]
     inp_res = torch.tensor([float(inp_w), float(inp_h)], device=feat.device)
     x = feature_volume(sd, feat, views, dims)
-    centre = reference_joints[:, dims.center_idx]                   # (B,3)
+    centre = reference_joints[:, 9]                                 # (B,3)  ptEmb_head.py:873 (fixed joint 9)
     bps_world = bps[None] + centre[:, None]
     grid = project_bps(bps_world, img_metas["cam_intr"], img_metas["cam_extr"], views, inp_res)
     sampled = F.grid_sample(x, grid, align_corners=False).squeeze(-1)   # (BV,D,P)
@@ -349,7 +355,8 @@ def head_forward(sd, dims, feat, img_metas, reference_joints, template, bps, anc
     anchors = (anchor_xyz, anchor_idx)
     xyz_all = []
     for i in range(dims.n_blocks):
-        q_feats, q_xyz = metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages)
+        nb = None if (neighbours is None or i == 0) else (neighbours[i - 1][0], neighbours[i - 1][1])
+        q_feats, q_xyz = metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages, nb)
         if dims.parametric and i == dims.n_blocks - 1:          # pt_metro_transformer.py:194-195
             if stages is not None:
                 stages["tail.feats"], stages["tail.xyz_in"] = q_feats, q_xyz
@@ -485,7 +492,7 @@ def triangulate_dlt(uv_px, cam_intr, cam_extr, view_counts):
     return torch.stack(out)
 
 
-def model_forward(sd, dims, batch, template, bps, anchor_xyz, anchor_idx):
+def model_forward(sd, dims, batch, template, bps, anchor_xyz, anchor_idx, data_center_idx=0):
     """`PtEmbedMultiviewStereoV2._forward_impl(mode="test")` (lib/models/POEM.py:251-333) on full-model keys:
     backbone -> feat_decode -> heatmap_stage -> per-sample DLT (or the given joints when every sample is single-view)
     -> head.  Returns the reference's prediction dict (evaluation keys)."""
@@ -504,7 +511,7 @@ def model_forward(sd, dims, batch, template, bps, anchor_xyz, anchor_idx):
     head_sd = {k[len("ptEmb_head."):]: v for k, v in sd.items() if k.startswith("ptEmb_head.")}
     coords = head_forward(head_sd, dims, mlvl_feat, metas, ref_joints, template, bps, anchor_xyz, anchor_idx)
     pj, pv = coords[-1, :, :21], coords[-1, :, 21:]
-    c = pj[:, dims.center_idx].unsqueeze(1)
+    c = pj[:, data_center_idx].unsqueeze(1)                          # POEM.py:328 (DATA_PRESET.CENTER_IDX = 0)
     return {"all_coords_preds": coords, "pred_joints_3d": pj, "pred_verts_3d": pv, "pred_joints_3d_rel": pj - c,
             "pred_verts_3d_rel": pv - c, "pred_joints_uv": uv, "pred_ref_joints_3d": ref_joints}
 

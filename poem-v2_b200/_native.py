@@ -18,6 +18,21 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 POEM_MAX_BLOCKS = 8
 
 
+def op16_dtype():
+    """torch dtype of the library's 16-bit operand format `poem_op16` (IEEE fp16, csrc/common.cuh)."""
+    import torch
+    return torch.float16
+
+
+def to_op16(t):
+    """Round a weight / activation tensor to the operand format; raises on overflow (|x| > 65504 would become inf)."""
+    import torch
+    t = t.detach()
+    if t.numel() and float(t.abs().max()) > 65504.0:
+        raise ValueError("value outside the fp16 operand range (|x| > 65504); rescale the checkpoint")
+    return t.to(torch.float16)
+
+
 def _nvcc():
     for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
         if p and os.path.exists(p):
@@ -125,7 +140,7 @@ class PoemInputs(C.Structure):
 
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
-           "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_hrnet_stage4_workspace_bytes",
+           "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_debug_export_neighbours", "poem_hrnet_stage4_workspace_bytes",
            "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_triangulate_dlt", "poem_pa_metrics", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
            "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
@@ -156,6 +171,8 @@ def load():
     lib.poem_profile_enable.restype = None
     lib.poem_debug_force_unfused.argtypes = [i]
     lib.poem_debug_force_unfused.restype = None
+    lib.poem_debug_export_neighbours.argtypes = [vp, sz]
+    lib.poem_debug_export_neighbours.restype = None
     lib.poem_profile_summary.restype = sz
     lib.poem_profile_summary.argtypes = [C.c_char_p, sz]
     lib.poem_workspace_bytes.restype = sz

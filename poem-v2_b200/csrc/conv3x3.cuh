@@ -88,8 +88,8 @@ struct HaloArgs {
   int n_images, R;                  // square maps, R % 16 == 0
   const float* bias;                // [CP]
   int relu;                         // ReLU after bias (+ residual)
-  const __nv_bfloat16* res;         // NHWC identity shortcut or nullptr
-  __nv_bfloat16* out;               // NHWC
+  const op16* res;         // NHWC identity shortcut or nullptr
+  op16* out;               // NHWC
   int cout_s;                       // channels per pixel of out / res in memory (multiple of 16, >= CR, <= CP)
 };
 
@@ -215,7 +215,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
     // instead of wrapping it in a per-instruction elect / branch loop (~40 cycles per MMA, which at N = 48 — 24 tensor
     // cycles per MMA — left the tensor pipe half idle)
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, CR);
+      constexpr uint32_t idesc = make_idesc_op16(128, CR);
       int step = 0, bs = 0, acc = 0;
       uint32_t bphase = 0, acc_phase = 0;
       if (Cfg::kBResident) mbar_wait(&b_full[0], 0);
@@ -248,7 +248,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
               const uint64_t da = make_kmajor_desc_ex(start, Cfg::kPitch * row_bytes, row_bytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (k < nch / 16) umma_bf16(d0 + sub * CP, da + 2 * k, db + 2 * k, idesc, (b | tap | k) != 0);
+                if (k < nch / 16) umma_op16(d0 + sub * CP, da + 2 * k, db + 2 * k, idesc, (b | tap | k) != 0);
             }
             if (!Cfg::kBResident) {
               umma_commit(&b_empty[bs]);
@@ -274,7 +274,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
     // With two warps per scheduler the epilogue is bound by the length of its own dependent instruction stream (an
     // "empty" kernel — no loads, MMAs or stores — ran at 2/3 of the full one), so the stream is kept short: the chunk
     // parity is a compile-time constant (channel masks fold away), tile -> pixel arithmetic is shifts on 32-bit values
-    // (the map is a power of two wide), ReLU rides on the bf16 conversion (cvt.rn.relu), and for C <= 64 the bias sits
+    // (the map is a power of two wide), ReLU rides on the op16 conversion (cvt.rn.relu), and for C <= 64 the bias sits
     // in registers and both sub-tiles' TMEM loads are in flight together.
     const int quarter = warp & 3;
     constexpr int kChunks = CP / 64;
@@ -299,7 +299,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
         const uint32_t pix0 = tile_pix(tile) + lane_pix;
         if (a.res != nullptr && tile + (int)gridDim.x < num_tiles) {
           // the shortcut pixels of this CTA's NEXT tile start travelling HBM -> L2 now
-          const __nv_bfloat16* rp = a.res + (size_t)(tile_pix(tile + (int)gridDim.x) + lane_pix) * a.cout_s;
+          const op16* rp = a.res + (size_t)(tile_pix(tile + (int)gridDim.x) + lane_pix) * a.cout_s;
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
@@ -308,7 +308,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
         }
         auto finish = [&](int sub, int j, const uint32_t (&r)[32], const uint32_t (&rr)[16]) {
           const int c0 = (2 * j + par) * 32;
-          __nv_bfloat16* op = a.out + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
+          op16* op = a.out + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
           uint32_t pk[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
@@ -325,23 +325,23 @@ conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, HaloArgs a) {
               v0 += b2.x, v1 += b2.y;
             }
             if (a.res != nullptr) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[q]));
+              const float2 f = op16x2_to_f2(*reinterpret_cast<const op16x2*>(&rr[q]));
               v0 += f.x, v1 += f.y;
             }
-            pk[q] = a.relu ? pack_bf16x2_relu(v0, v1) : pack_bf16x2(v0, v1);
+            pk[q] = a.relu ? pack_op16x2_relu(v0, v1) : pack_op16x2(v0, v1);
           }
           stg_256(op, &pk[0]);
           if (c0 + 16 < a.cout_s) stg_256(op + 16, &pk[8]);
         };
         auto load_res = [&](int sub, int j, uint32_t (&rr)[16]) {
           const int c0 = (2 * j + par) * 32;
-          const __nv_bfloat16* rp = a.res + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
+          const op16* rp = a.res + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
           ldg_nc_256(rp, &rr[0]);
           if (c0 + 16 < a.cout_s) ldg_nc_256(rp + 16, &rr[8]);
         };
         auto zero_chunk = [&](int sub, int j) {   // pure padding chunk inside the stored channels
           const int c0 = (2 * j + par) * 32;
-          __nv_bfloat16* op = a.out + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
+          op16* op = a.out + (size_t)(pix0 + sub * 8) * a.cout_s + c0;
           uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           stg_256(op, z);
           if (c0 + 16 < a.cout_s) stg_256(op + 16, z);

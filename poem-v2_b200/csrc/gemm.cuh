@@ -1,5 +1,5 @@
 // Persistent warp-specialised tcgen05 GEMM:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
-//   A, W : bf16, K-major (row-major with K contiguous), staged by TMA (SWIZZLE_128B, 64-element K blocks)
+//   A, W : op16, K-major (row-major with K contiguous), staged by TMA (SWIZZLE_128B, 64-element K blocks)
 //   accumulate fp32 in TMEM (two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
 //   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (two per TMEM lane quarter)
 //   W-stationary mode (whenever the [BN x K] weight slab fits in smem): every CTA keeps ONE n-tile for its whole
@@ -20,8 +20,8 @@ enum GemmRes : int {
   RES_NONE = 0,
   RES_F32 = 1,      // out += res_f32[m * res_ld + n]
   RES_POSADD = 2,   // out += res_f32[(row_tab[m / 256] * 256 + m % 256) * res_ld + n]   (positional term per view)
-  RES_MERGE = 3,    // out = out * row_scale[m / P] + res_bf16[(row_base[m / P] + (m % P) * row_cnt[m / P]) * res_ld + n]
-  RES_BF16 = 4      // out += res_bf16[m * res_ld + n]   (BasicBlock identity shortcut, NHWC)
+  RES_MERGE = 3,    // out = out * row_scale[m / P] + res_op16[(row_base[m / P] + (m % P) * row_cnt[m / P]) * res_ld + n]
+  RES_BF16 = 4      // out += res_op16[m * res_ld + n]   (BasicBlock identity shortcut, NHWC)
 };
 
 // Implicit-GEMM convolution: the A operand is gathered by TMA straight from an NHWC activation tensor
@@ -50,22 +50,27 @@ struct GemmEpilogue {
   int act_after_res;   // applied after the residual (row-major path only)
   int res_mode;
   const float* res_f32;
-  const __nv_bfloat16* res_bf16;
+  const op16* res_op16;
   int res_ld;
   const int* row_tab;      // RES_POSADD: per-image row of the positional table; RES_MERGE: row_base per sample
   const int* row_cnt;      // RES_MERGE: views per sample
   int rows_per_group;      // RES_MERGE: P
+  // per-row power-of-two scale sigma[m] of a pre-scaled A operand (merge-net aggregate, see merge_reduce_kernel):
+  //   sigma_mode 1: out = act(acc + bias / sigma[m])   (the ReLU MLP layer computed on A / sigma: positively homogeneous)
+  //   sigma_mode 2: acc is multiplied by sigma[m] before the bias (undoes the scaling)
+  const float* row_sigma;  // nullptr = unused
+  int sigma_mode;
   float* out_f32;          // row-major [M, ld_f32] or nullptr
   int ld_f32;
-  __nv_bfloat16* out_bf16; // row-major [M, ld_bf16] or nullptr
-  int ld_bf16;
+  op16* out_op16; // row-major [M, ld_op16] or nullptr
+  int ld_op16;
   int n_store;             // row-major outputs / residuals only exist for columns < n_store (multiple of 16; = N normally)
   // columns >= trans_from go to a per-group transposed buffer:
   //   out_t[(m / t_rows) * t_group_stride + (n - trans_from) * t_rows + (m % t_rows)]
   int trans_from;          // = N when unused
   int t_rows;
   long long t_group_stride;
-  __nv_bfloat16* out_t_bf16;
+  op16* out_t_op16;
   float* out_t_f32;
 };
 
@@ -95,7 +100,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // instantiation carries none of the prefetch registers / branches.
 template <int BN, bool kRes>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
+gemm_op16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M,
                     int N, int K, GemmEpilogue ep, ConvOperand conv, GemmPipe pipe) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -196,7 +201,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+      constexpr uint32_t idesc = make_idesc_op16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -215,8 +220,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint64_t dw = make_kmajor_desc<128>(sw);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 bf16 (32 B) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
+            // advance 16 op16 (32 B) along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+            umma_op16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (++stage == n_stages) {
@@ -234,7 +239,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ===================== epilogue warps (2..9) =====================
     // TMEM hands each lane one accumulator ROW (32 columns at a time) and the epilogue keeps that layout: a lane's 32
-    // columns are 128 (fp32) / 64 (bf16) contiguous bytes of its output row, moved with 256-bit accesses (one full
+    // columns are 128 (fp32) / 64 (op16) contiguous bytes of its output row, moved with 256-bit accesses (one full
     // 32-byte sector per lane and instruction), bias broadcast from smem.  No shared-memory transpose: with SS-mode
     // MMAs the operand reads already take most of the SM's shared-memory bandwidth, and a staged epilogue was what
     // bounded the skinny-K GEMMs of this path.
@@ -243,8 +248,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int chunk_par = ew >> 2; // this warp handles 32-column chunks with (chunk index & 1) == chunk_par
     int acc = 0;
     uint32_t acc_phase = 0;
-    // residual row of output row m: fp32 or bf16 pointer (nullptr when absent / out of range) and the RES_MERGE scale
-    auto res_row = [&](int m, const float*& pf, const __nv_bfloat16*& pb, float& scale) {
+    // residual row of output row m: fp32 or op16 pointer (nullptr when absent / out of range) and the RES_MERGE scale
+    auto res_row = [&](int m, const float*& pf, const op16*& pb, float& scale) {
       pf = nullptr;
       pb = nullptr;
       scale = 1.0f;
@@ -254,12 +259,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       } else if (ep.res_mode == RES_POSADD) {
         pf = ep.res_f32 + ((size_t)ep.row_tab[m >> 8] * 256 + (m & 255)) * ep.res_ld;
       } else if (ep.res_mode == RES_BF16) {
-        pb = ep.res_bf16 + (size_t)m * ep.res_ld;
+        pb = ep.res_op16 + (size_t)m * ep.res_ld;
       } else if (ep.res_mode == RES_MERGE) {
         const int g = m / ep.rows_per_group;
         const int cnt = ep.row_cnt[g];
         scale = 1.0f / (float)cnt;
-        pb = ep.res_bf16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+        pb = ep.res_op16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
       }
     };
     for (int it = it0; it < it_end; it += it_step) {
@@ -275,9 +280,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       const int mt_row = m0 + quarter * 32 + lane;   // this lane's output row
       const float* resf;
-      const __nv_bfloat16* resb;
+      const op16* resb;
       float rscale;
       res_row(mt_row, resf, resb, rscale);
+      const float row_sig = (ep.row_sigma != nullptr && mt_row < M) ? __ldg(ep.row_sigma + mt_row) : 1.0f;
       // the residual rows of this CTA's NEXT tile start travelling HBM -> L2 now (the epilogue of a skinny-K GEMM is
       // otherwise bound by the latency of these loads, not by bandwidth)
       if (kRes && it + it_step < it_end) {
@@ -285,7 +291,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m0n = (wst ? itn : itn / tiles_n) * GEMM_BM;
         const int n0n = (wst ? my_n_tile : itn % tiles_n) * BN;
         const float* pf;
-        const __nv_bfloat16* pb;
+        const op16* pb;
         float sc;
         res_row(m0n + quarter * 32 + lane, pf, pb, sc);
         for (int c0 = chunk_par * 32; c0 < BN && n0n + c0 < N && n0n + c0 < ep.trans_from; c0 += 64) {
@@ -343,13 +349,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         if (mt_row < M) {
         float v[32];
+        if (ep.row_sigma == nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b4.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+          }
+        } else {
+          const float a_sc = (ep.sigma_mode == 2) ? row_sig : 1.0f;
+          const float b_sc = (ep.sigma_mode == 1) ? 1.0f / row_sig : 1.0f;   // sigma is a power of two: exact
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+            v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), a_sc, b4.x * b_sc);
+            v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), a_sc, b4.y * b_sc);
+            v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), a_sc, b4.z * b_sc);
+            v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), a_sc, b4.w * b_sc);
+          }
         }
         if (ep.act == ACT_RELU) {
 #pragma unroll
@@ -371,9 +390,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           const int tc = n - ep.trans_from;
-          if (ep.out_t_bf16 != nullptr) {
+          if (ep.out_t_op16 != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ep.out_t_bf16[t_base + (size_t)(tc + j) * ep.t_rows] = __float2bfloat16(v[j]);
+            for (int j = 0; j < 32; ++j) ep.out_t_op16[t_base + (size_t)(tc + j) * ep.t_rows] = f2op16(v[j]);
           }
           if (ep.out_t_f32 != nullptr) {
 #pragma unroll
@@ -387,7 +406,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         } else if (kRes && resb != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[j]));
+            const float2 f = op16x2_to_f2(*reinterpret_cast<const op16x2*>(&rr[j]));
             v[2 * j] = v[2 * j] * rscale + f.x;
             v[2 * j + 1] = v[2 * j + 1] * rscale + f.y;
           }
@@ -402,11 +421,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < 4; ++j)
             if (valid >= 8 * (j + 1)) stg_256(o + 8 * j, reinterpret_cast<const uint32_t*>(&v[8 * j]));
         }
-        if (ep.out_bf16 != nullptr) {
+        if (ep.out_op16 != nullptr) {
           uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          __nv_bfloat16* o = ep.out_bf16 + (size_t)mt_row * ep.ld_bf16 + n;
+          for (int j = 0; j < 16; ++j) pk[j] = pack_op16x2(v[2 * j], v[2 * j + 1]);
+          op16* o = ep.out_op16 + (size_t)mt_row * ep.ld_op16 + n;
           stg_256(o, &pk[0]);
           if (valid >= 32) stg_256(o + 16, &pk[8]);
         }

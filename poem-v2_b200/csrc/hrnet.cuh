@@ -1,6 +1,6 @@
 // HRNet-W40 glue kernels (reference lib/models/backbones/hrnet.py, lib/models/POEM.py:189-229): layout changes, stem,
 // fuse-layer sums, upsampling / concat, heatmap soft-argmax, DLT triangulation.
-// Activations live as NHWC bf16.  Inside the image half a pixel keeps only its live channels rounded up to 16
+// Activations live as NHWC op16.  Inside the image half a pixel keeps only its live channels rounded up to 16
 // (48 / 80 / 160 / 320: "compact storage"); every convolution is a tcgen05 GEMM whose A operand TMA gathers (conv3x3.cuh
 // for 3x3 stride 1, the ConvOperand mode of gemm.cuh otherwise) — a 64-channel box that runs past a pixel's channels is
 // zero-filled by the hardware; BatchNorm (eval) and conv biases are folded into the weights at pack time.
@@ -9,8 +9,8 @@
 
 namespace poem {
 
-// (N, C, H*W) fp32 -> (N, H*W, Cp) bf16, channels >= C zero-filled.  32x32 smem transpose tiles.
-__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Cp,
+// (N, C, H*W) fp32 -> (N, H*W, Cp) op16, channels >= C zero-filled.  32x32 smem transpose tiles.
+__global__ void nchw_f32_to_nhwc_op16_kernel(const float* __restrict__ in, op16* __restrict__ out, int C, int Cp,
                                              int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -23,12 +23,12 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
-    if (c < Cp && p < HW) out[((size_t)n * HW + p) * Cp + c] = __float2bfloat16(tile[tx][i]);
+    if (c < Cp && p < HW) out[((size_t)n * HW + p) * Cp + c] = f2op16(tile[tx][i]);
   }
 }
 
-// (N, H*W, Cp) bf16 -> (N, C, H*W) fp32 (only the C real channels)
-__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int Cp,
+// (N, H*W, Cp) op16 -> (N, C, H*W) fp32 (only the C real channels)
+__global__ void nhwc_op16_to_nchw_f32_kernel(const op16* __restrict__ in, float* __restrict__ out, int C, int Cp,
                                              int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -36,7 +36,7 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ i
   const int tx = threadIdx.x, ty = threadIdx.y;
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
-    tile[i][tx] = (c < Cp && p < HW) ? __bfloat162float(in[((size_t)n * HW + p) * Cp + c]) : 0.f;
+    tile[i][tx] = (c < Cp && p < HW) ? op16_to_f(in[((size_t)n * HW + p) * Cp + c]) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -46,12 +46,12 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ i
 }
 
 // Stem conv1 (hrnet.py:245-246, 388-390): 3x3 stride-2 convolution 3 -> 64 channels on the NCHW fp32 image, BatchNorm
-// folded, ReLU; writes NHWC bf16 (64 channels = one swizzle atom) for the implicit-GEMM convolutions that follow.
+// folded, ReLU; writes NHWC op16 (64 channels = one swizzle atom) for the implicit-GEMM convolutions that follow.
 // K = 27 is far too small for the tensor core: one thread per output pixel, weights broadcast from smem.
 //   w: fp32 [64][27] with k = (ky*3 + kx)*3 + c ; b: fp32 [64]
 __global__ void __launch_bounds__(128)
 stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ b,
-                  __nv_bfloat16* __restrict__ out, int N, int H, int W) {
+                  op16* __restrict__ out, int N, int H, int W) {
   __shared__ float sw[64 * 27];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) sw[i] = w[i];
@@ -73,7 +73,7 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ w, co
 #pragma unroll
       for (int c = 0; c < 3; ++c) in[(ky * 3 + kx) * 3 + c] = ok ? img[((n * 3 + c) * H + y) * W + x] : 0.f;
     }
-  __nv_bfloat16* o = out + pix * 64;
+  op16* o = out + pix * 64;
 #pragma unroll 1
   for (int c0 = 0; c0 < 64; c0 += 8) {
     float acc[8];
@@ -86,10 +86,10 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ w, co
       acc[j] = fmaxf(a, 0.f);
     }
     uint4 pk;
-    pk.x = pack_bf16x2(acc[0], acc[1]);
-    pk.y = pack_bf16x2(acc[2], acc[3]);
-    pk.z = pack_bf16x2(acc[4], acc[5]);
-    pk.w = pack_bf16x2(acc[6], acc[7]);
+    pk.x = pack_op16x2(acc[0], acc[1]);
+    pk.y = pack_op16x2(acc[2], acc[3]);
+    pk.z = pack_op16x2(acc[4], acc[5]);
+    pk.w = pack_op16x2(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(o + c0) = pk;
   }
 }
@@ -116,10 +116,10 @@ __global__ void upsample2x_nhwc_to_nchw_kernel(const float* __restrict__ in, flo
 }
 
 // uv_decode step input (POEM.py:208-210): cat(F.interpolate(hi, x2, bilinear, align_corners=False), lo) along channels,
-// NHWC bf16, written with the channel count padded to 64 (zeros).  C_hi and C_lo are multiples of 8, so an 8-channel
+// NHWC op16, written with the channel count padded to 64 (zeros).  C_hi and C_lo are multiples of 8, so an 8-channel
 // group never straddles the two sources.  hi: (N, H, W, Cp_hi), lo: (N, 2H, 2W, Cp_lo), out: (N, 2H, 2W, Cp_out).
-__global__ void upsample2x_concat_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                         __nv_bfloat16* __restrict__ out, int H, int W, int Cp_hi, int C_hi, int Cp_lo,
+__global__ void upsample2x_concat_kernel(const op16* __restrict__ hi, const op16* __restrict__ lo,
+                                         op16* __restrict__ out, int H, int W, int Cp_hi, int C_hi, int Cp_lo,
                                          int C_lo, int Cp_out, size_t total8) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total8) return;
@@ -137,23 +137,23 @@ __global__ void upsample2x_concat_kernel(const __nv_bfloat16* __restrict__ hi, c
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
     const float ly = sy - (float)y0, lx = sx - (float)x0;
-    const __nv_bfloat16* b = hi + n * H * W * Cp_hi + c;
+    const op16* b = hi + n * H * W * Cp_hi + c;
     const uint4 q00 = *reinterpret_cast<const uint4*>(b + ((size_t)y0 * W + x0) * Cp_hi);
     const uint4 q01 = *reinterpret_cast<const uint4*>(b + ((size_t)y0 * W + x1) * Cp_hi);
     const uint4 q10 = *reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x0) * Cp_hi);
     const uint4 q11 = *reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x1) * Cp_hi);
-    const __nv_bfloat162* p00 = reinterpret_cast<const __nv_bfloat162*>(&q00);
-    const __nv_bfloat162* p01 = reinterpret_cast<const __nv_bfloat162*>(&q01);
-    const __nv_bfloat162* p10 = reinterpret_cast<const __nv_bfloat162*>(&q10);
-    const __nv_bfloat162* p11 = reinterpret_cast<const __nv_bfloat162*>(&q11);
+    const op16x2* p00 = reinterpret_cast<const op16x2*>(&q00);
+    const op16x2* p01 = reinterpret_cast<const op16x2*>(&q01);
+    const op16x2* p10 = reinterpret_cast<const op16x2*>(&q10);
+    const op16x2* p11 = reinterpret_cast<const op16x2*>(&q11);
     uint32_t r[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 a = __bfloat1622float2(p00[i]), bq = __bfloat1622float2(p01[i]);
-      const float2 cq = __bfloat1622float2(p10[i]), d = __bfloat1622float2(p11[i]);
+      const float2 a = op16x2_to_f2(p00[i]), bq = op16x2_to_f2(p01[i]);
+      const float2 cq = op16x2_to_f2(p10[i]), d = op16x2_to_f2(p11[i]);
       const float vx = (1.f - ly) * ((1.f - lx) * a.x + lx * bq.x) + ly * ((1.f - lx) * cq.x + lx * d.x);
       const float vy = (1.f - ly) * ((1.f - lx) * a.y + lx * bq.y) + ly * ((1.f - lx) * cq.y + lx * d.y);
-      r[i] = pack_bf16x2(vx, vy);
+      r[i] = pack_op16x2(vx, vy);
     }
     o = make_uint4(r[0], r[1], r[2], r[3]);
   } else if (c < C_hi + C_lo) {
@@ -168,7 +168,7 @@ __global__ void upsample2x_concat_kernel(const __nv_bfloat16* __restrict__ hi, c
 //   w: fp32 [J][C], b: fp32 [J]; uv_px: (N, J, 2) = (u * img_w, v * img_h); heat: optional (N, J, R, R) fp32
 constexpr int HEAT_MAX_J = 24;
 __global__ void __launch_bounds__(256)
-heatmap_uv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+heatmap_uv_kernel(const op16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                   float* __restrict__ uv_px, float* __restrict__ heat, int R, int Cp, int C, int J, float img_w,
                   float img_h) {
   extern __shared__ float sm[];
@@ -188,16 +188,16 @@ heatmap_uv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
     float acc[HEAT_MAX_J];
 #pragma unroll
     for (int j = 0; j < HEAT_MAX_J; ++j) acc[j] = (j < J) ? sb[j] : 0.f;
-    const __nv_bfloat16* base = x + ((n * R2 + 2 * py) * R2 + 2 * px) * Cp;
+    const op16* base = x + ((n * R2 + 2 * py) * R2 + 2 * px) * Cp;
     for (int c = 0; c < C; c += 8) {
       float m[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint4 q = *reinterpret_cast<const uint4*>(base + ((size_t)(k >> 1) * R2 + (k & 1)) * Cp + c);
-        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+        const op16x2* q2 = reinterpret_cast<const op16x2*>(&q);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(q2[i]);
+          const float2 f = op16x2_to_f2(q2[i]);
           m[2 * i] = k ? fmaxf(m[2 * i], f.x) : f.x;
           m[2 * i + 1] = k ? fmaxf(m[2 * i + 1], f.y) : f.y;
         }
@@ -346,13 +346,13 @@ dlt_triangulate_kernel(const float* __restrict__ uv_px, const float* __restrict_
 // Fuse layer sum (hrnet.py:225-233): out[n,y,x,c] = relu(sum_j in_j[n, y >> s_j, x >> s_j, c]); in_j has resolution
 // (H >> s_j, W >> s_j) — nearest-neighbour upsampling by 2^s_j of the 1x1-conv terms, s_j = 0 for the others.
 struct FuseSumArgs {
-  const __nv_bfloat16* in[4];
+  const op16* in[4];
   int shift[4];
   int n_in;
 };
 // 16 channels (one 256-bit access per term) per thread
 __global__ void __launch_bounds__(256)
-fuse_sum_relu_kernel(FuseSumArgs a, __nv_bfloat16* __restrict__ out, int H, int W, int Cp, size_t total16) {
+fuse_sum_relu_kernel(FuseSumArgs a, op16* __restrict__ out, int H, int W, int Cp, size_t total16) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total16) return;
   const int c16 = Cp / 16;
@@ -379,7 +379,7 @@ fuse_sum_relu_kernel(FuseSumArgs a, __nv_bfloat16* __restrict__ out, int H, int 
     if (j < a.n_in) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[j][i]));
+        const float2 f = op16x2_to_f2(*reinterpret_cast<const op16x2*>(&v[j][i]));
         acc[2 * i] += f.x;
         acc[2 * i + 1] += f.y;
       }
@@ -387,7 +387,7 @@ fuse_sum_relu_kernel(FuseSumArgs a, __nv_bfloat16* __restrict__ out, int H, int 
   }
   uint32_t o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
+  for (int i = 0; i < 8; ++i) o[i] = pack_op16x2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
   stg_256(out + gid * 16, o);
 }
 

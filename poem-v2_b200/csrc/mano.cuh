@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kManoThreads) mano_tail_kernel(const ManoTailA
   if (a.center_idx >= 0) cx = jt[a.center_idx][0], cy = jt[a.center_idx][1], cz = jt[a.center_idx][2];
   float ox = 0.f, oy = 0.f, oz = 0.f;
   if (a.ref_joints) {
-    const float* c = a.ref_joints + ((size_t)b * 21 + a.center_idx) * 3;
+    const float* c = a.ref_joints + ((size_t)b * 21 + 9) * 3;   // hand centre: always joint 9 (ptEmb_head.py:873,958)
     ox = c[0], oy = c[1], oz = c[2];
   }
   float* out = a.coords + (size_t)b * (21 + kManoVerts) * 3;

@@ -3,7 +3,7 @@
 //
 // One CTA = 128 queries of one (sample, head). Per 128-key block j:
 //   S(j) = Q·K(j)^T     tcgen05.mma (M=128, N=128, K=HD) -> TMEM buffer j%2          (double buffered)
-//   softmax warps (thread == query row, no cross-lane traffic): pass A row max, pass B P = exp2(..) as bf16 into a
+//   softmax warps (thread == query row, no cross-lane traffic): pass A row max, pass B P = exp2(..) as op16 into a
 //   SWIZZLE_128B K-major smem tile
 //   O_blk(j) = P(j)·V(j) (M=128, N=HD, K=128) -> TMEM, written over the first HD columns of the ALREADY CONSUMED
 //   S(j) buffer, so 256 TMEM columns hold two S buffers and the P·V result (2 CTAs per SM for HD <= 64)
@@ -38,17 +38,17 @@ struct MhaCfg {
   static constexpr int kKBytes = MHA_BKEY * HD * 2;
   static constexpr int kVBytes = MHA_BKEY * HD * 2;              // kKBlocks tiles of [128 keys x kRowBytes]
   static constexpr int kPBytes = MHA_BQ * MHA_BKEY * 2;          // two [128 x 64 keys] SWIZZLE_128B tiles
-  static constexpr int kXchgBytes = 2 * 128 * 2;                // bf16 row-max exchange between the two row halves
+  static constexpr int kXchgBytes = 2 * 128 * 4;                // fp32 row-max exchange between the two row halves
   static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + kXchgBytes + 160;   // 2 CTAs/SM at HD=64
   static constexpr int kTmemCols = 256;                          // two S buffers; O_blk aliases the consumed one
 };
 
 template <int HD>
 __global__ void __launch_bounds__(MHA_THREADS, (HD <= 64) ? 2 : 1)
-mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, ldq] bf16, box [HD(or 64) x 128]
-                  const __grid_constant__ CUtensorMap tmap_k,   // [B*Lk rows, ldk] bf16, box [HD(or 64) x 128]
-                  const __grid_constant__ CUtensorMap tmap_v,   // [B*Lk rows, ldv] bf16, box [HD(or 64) x 128]
-                  __nv_bfloat16* __restrict__ ctx, int ld_ctx, int Lq, int Lk, int q_col0, int k_col0, int v_col0,
+mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, ldq] op16, box [HD(or 64) x 128]
+                  const __grid_constant__ CUtensorMap tmap_k,   // [B*Lk rows, ldk] op16, box [HD(or 64) x 128]
+                  const __grid_constant__ CUtensorMap tmap_v,   // [B*Lk rows, ldv] op16, box [HD(or 64) x 128]
+                  op16* __restrict__ ctx, int ld_ctx, int Lq, int Lk, int q_col0, int k_col0, int v_col0,
                   float scale_log2e, int n_heads) {
   using Cfg = MhaCfg<HD>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -58,7 +58,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   uint8_t* sK = sQ + Cfg::kQBytes;               // 2 stages
   uint8_t* sV = sK + 2 * Cfg::kKBytes;           // 2 stages
   uint8_t* sP = sV + 2 * Cfg::kVBytes;
-  __nv_bfloat16* s_xchg = reinterpret_cast<__nv_bfloat16*>(sP + Cfg::kPBytes);
+  float* s_xchg = reinterpret_cast<float*>(sP + Cfg::kPBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes + Cfg::kXchgBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;       // [2] TMA -> MMA
@@ -148,8 +148,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
-      constexpr uint32_t idesc_s = make_idesc_bf16(MHA_BQ, MHA_BKEY);
-      constexpr uint32_t idesc_o = make_idesc_bf16(MHA_BQ, HD, /*b_mn_major=*/1);
+      constexpr uint32_t idesc_s = make_idesc_op16(MHA_BQ, MHA_BKEY);
+      constexpr uint32_t idesc_o = make_idesc_op16(MHA_BQ, HD, /*b_mn_major=*/1);
       auto issue_S = [&](int j) {   // S(j) -> TMEM buffer j%2, from K stage j%2
         const int st = j & 1;
         mbar_wait(&k_full[st], (uint32_t)(j >> 1) & 1);
@@ -161,7 +161,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
           const uint64_t dk = make_kmajor_desc<Cfg::kRowBytes>(k_addr + kb * (MHA_BKEY * Cfg::kRowBytes));
 #pragma unroll
           for (int k = 0; k < Cfg::kRowBytes / 32; ++k)
-            umma_bf16(tmem_base + st * 128, dq + 2 * k, dk + 2 * k, idesc_s, (kb | k) != 0);
+            umma_op16(tmem_base + st * 128, dq + 2 * k, dk + 2 * k, idesc_s, (kb | k) != 0);
         }
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);
@@ -182,7 +182,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
         for (int ks = 0; ks < MHA_BKEY / 16; ++ks) {     // 16 keys per MMA
           const uint64_t dp = make_kmajor_desc<128>(smem_u32(sP) + (ks >> 2) * (MHA_BQ * 128)) + 2 * (ks & 3);
           const uint64_t dv = dv0 + (uint64_t)((ks * 16 * Cfg::kRowBytes) >> 4);
-          umma_bf16(tmem_base + st * 128, dp, dv, idesc_o, ks != 0);
+          umma_op16(tmem_base + st * 128, dp, dv, idesc_o, ks != 0);
         }
         umma_commit(&o_full[st]);
         umma_commit(&v_empty[st]);
@@ -262,13 +262,11 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
 #pragma unroll
         for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
       }
-      // Exchange the half-row maxima as bf16 (any common reference value works for the softmax; both threads of a row
-      // use the same rounded pair).  Single buffer: the partner can only write its block j+1 value after S(j+1) was
+      // Exchange the half-row maxima.  Single buffer: the partner can only write its block j+1 value after S(j+1) was
       // issued, which (for j >= 1) waits for o_done(j-1), i.e. for every thread's read below; block 0 syncs again.
-      const __nv_bfloat16 m_mine = __float2bfloat16(m_blk);
-      s_xchg[half * 128 + row] = m_mine;
+      s_xchg[half * 128 + row] = m_blk;
       pair_sync();
-      m_blk = fmaxf(__bfloat162float(m_mine), __bfloat162float(s_xchg[(half ^ 1) * 128 + row]));
+      m_blk = fmaxf(m_blk, s_xchg[(half ^ 1) * 128 + row]);
       if (j == 0) pair_sync();
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
@@ -276,7 +274,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       // fold the previous block's P·V (finished long ago) — this also guarantees the P tile is free again
       if (j > 0) fold_o(j - 1, alpha_prev);
       alpha_prev = alpha;
-      // pass B: probabilities -> bf16 -> swizzled smem (A operand of P·V); this thread fills K block `half`
+      // pass B: probabilities -> op16 -> swizzled smem (A operand of P·V); this thread fills K block `half`
       float l_blk = 0.f;
       uint8_t* tile = sP + half * (MHA_BQ * 128);
 #pragma unroll
@@ -293,7 +291,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
           // every MHA_POLY_EVERY-th pair takes its second exponential from the FMA pipes instead of the SFU
           const float p1 = (MHA_POLY_EVERY > 0 && (i % (MHA_POLY_EVERY > 0 ? MHA_POLY_EVERY : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1);
           l_blk += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          pk[i] = pack_op16x2(p0, p1);
         }
         const int chunk0 = c0 >> 3;
 #pragma unroll
@@ -319,14 +317,14 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
     const int q = q0 + row;
     if (q < Lq) {
       const float inv = 1.0f / l_row;
-      __nv_bfloat16* o = ctx + (size_t)(b * Lq + q) * ld_ctx + head * HD + half * HH;
+      op16* o = ctx + (size_t)(b * Lq + q) * ld_ctx + head * HD + half * HH;
 #pragma unroll
       for (int c = 0; c < HH; c += 8) {
         uint4 pk;
-        pk.x = pack_bf16x2(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
-        pk.y = pack_bf16x2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-        pk.z = pack_bf16x2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
-        pk.w = pack_bf16x2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+        pk.x = pack_op16x2(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
+        pk.y = pack_op16x2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+        pk.z = pack_op16x2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
+        pk.w = pack_op16x2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
         *reinterpret_cast<uint4*>(o + c) = pk;
       }
     }

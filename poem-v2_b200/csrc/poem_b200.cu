@@ -142,8 +142,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = [box_cols, box_rows]; swizzle by box width.
-static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+// 2-D op16 tensor [rows, cols] with row pitch ld (elements); box = [box_cols, box_rows]; swizzle by box width.
+static int make_tmap_op16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                           uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled unavailable");
@@ -159,7 +159,7 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
                           : (box_cols * 2 == 32) ? CU_TENSOR_MAP_SWIZZLE_32B
                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
   if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return fail(POEM_E_BADDIM, "unsupported TMA box width %u", box_cols);
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -167,14 +167,15 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
 }
 
 static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,16 +202,16 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_op16_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_op16_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemMax));
     configured = true;
   }
   // the epilogue moves 32-column chunks of a row with 256-bit accesses
   auto misaligned = [](const void* p, int ld, int elem) {
     return p != nullptr && ((reinterpret_cast<uintptr_t>(p) & 31) || ((size_t)ld * elem) % 32);
   };
-  if (N % 32 || misaligned(ep.out_f32, ep.ld_f32, 4) || misaligned(ep.out_bf16, ep.ld_bf16, 2) ||
-      (ep.res_mode != RES_NONE && (misaligned(ep.res_f32, ep.res_ld, 4) || misaligned(ep.res_bf16, ep.res_ld, 2))))
+  if (N % 32 || misaligned(ep.out_f32, ep.ld_f32, 4) || misaligned(ep.out_op16, ep.ld_op16, 2) ||
+      (ep.res_mode != RES_NONE && (misaligned(ep.res_f32, ep.res_ld, 4) || misaligned(ep.res_op16, ep.res_ld, 2))))
     return fail(POEM_E_ALIGN, "gemm: N %% 32 == 0 and 32-byte aligned output / residual rows required (N=%d)", N);
   const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + BN - 1) / BN;
   const int tiles = tiles_m * tiles_n;
@@ -235,10 +236,10 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
   }
   prof_begin(st);
   if (ep.res_mode != RES_NONE)
-    gemm_bf16_tc_kernel<BN, true><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
+    gemm_op16_tc_kernel<BN, true><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
   else
-    gemm_bf16_tc_kernel<BN, false><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
-  LAUNCH_CHECK("gemm_bf16_tc_kernel");
+    gemm_op16_tc_kernel<BN, false><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
+  LAUNCH_CHECK("gemm_op16_tc_kernel");
   return POEM_OK;
 }
 
@@ -251,12 +252,12 @@ static GemmEpilogue epi_default(int N) {
   return e;
 }
 
-static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K,
+static int launch_gemm(const op16* A, int lda, const op16* W, int ldw, int M, int N, int K,
                        const GemmEpilogue& ep, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(POEM_E_BADDIM, "gemm: bad shape %d %d %d", M, N, K);
   if (!A || !W) return fail(POEM_E_NULL, "gemm: null operand");
   if (N % 32) return fail(POEM_E_BADDIM, "gemm: N=%d must be a multiple of 32", N);
-  if ((ep.out_f32 && (ep.ld_f32 % 4)) || (ep.out_bf16 && (ep.ld_bf16 % 8)) ||
+  if ((ep.out_f32 && (ep.ld_f32 % 4)) || (ep.out_op16 && (ep.ld_op16 % 8)) ||
       (ep.res_mode == RES_F32 && (ep.res_ld % 4)))
     return fail(POEM_E_ALIGN, "gemm: output/residual leading dimensions must keep rows 16-byte aligned");
   // widest tile that divides N, narrowed while the grid would be under ~2 waves (small-M GEMMs of the query stream:
@@ -265,8 +266,8 @@ static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
   const int tiles_m_ = (M + GEMM_BM - 1) / GEMM_BM;
   while (BN > 64 && tiles_m_ * (N / BN) < 3 * num_sms()) BN >>= 1;
   CUtensorMap ta, tw;
-  POEM_TRY(make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM));
-  POEM_TRY(make_tmap_bf16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, GEMM_BK, (uint32_t)BN));
+  POEM_TRY(make_tmap_op16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM));
+  POEM_TRY(make_tmap_op16(&tw, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, GEMM_BK, (uint32_t)BN));
   ConvOperand none;
   memset(&none, 0, sizeof(none));
   if (BN == 256) return launch_gemm_bn<256>(ta, tw, M, N, K, ep, none, st);
@@ -275,9 +276,9 @@ static int launch_gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// implicit-GEMM convolution on NHWC bf16 (HRNet stage 4)
+// implicit-GEMM convolution on NHWC op16 (HRNet stage 4)
 // ------------------------------------------------------------------------------------------------
-// 4-D bf16 tensor map over an NHWC activation tensor: dims (C, W, H, N); box (64, bw*stride, bh*stride, bn) with
+// 4-D op16 tensor map over an NHWC activation tensor: dims (C, W, H, N); box (64, bw*stride, bh*stride, bn) with
 // traversal stride `stride` along W and H, SWIZZLE_128B, zero fill outside (= convolution padding).
 static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int Cp, int bw, int bh, int bn,
                           int stride, int box_c = 64) {
@@ -290,7 +291,7 @@ static int make_tmap_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W
   const CUtensorMapSwizzle swz = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(POEM_E_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d)", (int)r);
@@ -302,7 +303,7 @@ static int g_conv_mode = 0;   // 0: halo-reuse kernel, live channels only; 1: ha
 extern "C" void poem_debug_conv_mode(int mode) { g_conv_mode = mode; }
 
 template <int CIP, int CIR, int CP, int CR>
-static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, int cin_s, const PoemLinear& wt, const HaloArgs& a,
+static int launch_conv3x3_halo_cp(const op16* in, int N, int R, int cin_s, const PoemLinear& wt, const HaloArgs& a,
                                   cudaStream_t st) {
   using Cfg = HaloCfg<CIP, CIR, CP, CR>;
   using Blk = typename Cfg::Blk;
@@ -318,7 +319,7 @@ static int launch_conv3x3_halo_cp(const __nv_bfloat16* in, int N, int R, int cin
     const int nch = Blk::nch(b), mi = halo_map_index(nch);
     if (have[mi]) continue;
     POEM_TRY(make_tmap_nhwc(&maps.x[mi], in, N, R, R, cin_s, Cfg::kPitch, Cfg::kRows, 1, 1, nch));
-    POEM_TRY(make_tmap_bf16(&maps.w[mi], wt.w, (uint64_t)CR, (uint64_t)9 * CIP, (uint64_t)9 * CIP, (uint32_t)nch, (uint32_t)CR));
+    POEM_TRY(make_tmap_op16(&maps.w[mi], wt.w, (uint64_t)CR, (uint64_t)9 * CIP, (uint64_t)9 * CIP, (uint32_t)nch, (uint32_t)CR));
     have[mi] = true;
   }
   int first = have[0] ? 0 : (have[1] ? 1 : 2);
@@ -342,8 +343,8 @@ static bool halo_supported(int cip, int cir, int cop, int cor) {
 }
 
 // ci_live / co_live: live channels of the input / output (the rest of the padded count is zero); 0 = all live
-static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cip, int ci_live, int Cop, int co_live,
-                               const PoemLinear& wt, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
+static int launch_conv3x3_halo(const op16* in, int N, int R, int Cip, int ci_live, int Cop, int co_live,
+                               const PoemLinear& wt, bool relu, const op16* res, op16* out,
                                cudaStream_t st, bool* handled, int cin_s, int cout_s) {
   const bool live = (g_conv_mode != 1);
   int cir = (ci_live > 0 && live) ? (ci_live + 15) / 16 * 16 : Cip;
@@ -375,8 +376,8 @@ static int launch_conv3x3_halo(const __nv_bfloat16* in, int N, int R, int Cip, i
 }
 
 // out[N, Hout, Wout, Cout_p] = act(conv(in[N, Hin, Win, Cin_p], w[Cout_p, k*k*Cin_p]) + b) (+ res)
-static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
-                       int ksize, int stride, bool relu, const __nv_bfloat16* res, __nv_bfloat16* out,
+static int launch_conv(const op16* in, int N, int Hin, int Win, int Cin_p, const PoemLinear& wt, int Cout_p,
+                       int ksize, int stride, bool relu, const op16* res, op16* out,
                        cudaStream_t st, int c_real = 0, bool relu_before_res = false, float* out_f32 = nullptr,
                        int c_real_in = -1, int cin_s = 0, int cout_s = 0) {
   // cin_s / cout_s: channels per pixel of the tensors in memory (multiples of 16; 0 = the padded counts).  With
@@ -413,18 +414,18 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   const int BN = (Cout_p <= 256) ? Cout_p : 160;
   if (!(BN == 64 || BN == 128 || BN == 160 || BN == 192 || BN == 256) || Cout_p % BN)
     return fail(POEM_E_BADDIM, "conv: Cout_p=%d has no tile", Cout_p);
-  POEM_TRY(make_tmap_bf16(&tw, wt.w, (uint64_t)Cout_p, (uint64_t)K, (uint64_t)K, GEMM_BK, (uint32_t)BN));
+  POEM_TRY(make_tmap_op16(&tw, wt.w, (uint64_t)Cout_p, (uint64_t)K, (uint64_t)K, GEMM_BK, (uint32_t)BN));
   GemmEpilogue e = epi_default(Cout_p);
   e.bias = wt.b;
   e.act = (relu && (!res || relu_before_res)) ? ACT_RELU : ACT_NONE;
   e.act_after_res = (relu && res && !relu_before_res) ? ACT_RELU : ACT_NONE;
   if (res) {
     e.res_mode = RES_BF16;
-    e.res_bf16 = res;
+    e.res_op16 = res;
     e.res_ld = cout_s;
   }
-  e.out_bf16 = out;
-  e.ld_bf16 = cout_s;
+  e.out_op16 = out;
+  e.ld_op16 = cout_s;
   e.n_store = out_f32 ? Cout_p : cout_s;   // the fp32 output (feat_in) keeps the padded row
   e.out_f32 = out_f32;
   e.ld_f32 = Cout_p;
@@ -443,8 +444,8 @@ static int launch_conv(const __nv_bfloat16* in, int N, int Hin, int Win, int Cin
   }
 }
 
-extern "C" int poem_conv_nhwc(const poem_bf16* in, int N, int H, int W, int Cin_p, const poem_bf16* w, const float* b,
-                              int Cout_p, int ksize, int stride, int relu, const poem_bf16* res, poem_bf16* out,
+extern "C" int poem_conv_nhwc(const poem_op16* in, int N, int H, int W, int Cin_p, const poem_op16* w, const float* b,
+                              int Cout_p, int ksize, int stride, int relu, const poem_op16* res, poem_op16* out,
                               int c_live_in, int c_live_out, void* stream) {
   if (!in || !out) return fail(POEM_E_NULL, "conv: null pointer");
   if (c_live_in < 0 || c_live_in > Cin_p || c_live_out < 0 || c_live_out > Cout_p)
@@ -452,8 +453,8 @@ extern "C" int poem_conv_nhwc(const poem_bf16* in, int N, int H, int W, int Cin_
   PoemLinear wt;
   wt.w = w;
   wt.b = b;
-  return launch_conv(reinterpret_cast<const __nv_bfloat16*>(in), N, H, W, Cin_p, wt, Cout_p, ksize, stride, relu != 0,
-                     reinterpret_cast<const __nv_bfloat16*>(res), reinterpret_cast<__nv_bfloat16*>(out),
+  return launch_conv(reinterpret_cast<const op16*>(in), N, H, W, Cin_p, wt, Cout_p, ksize, stride, relu != 0,
+                     reinterpret_cast<const op16*>(res), reinterpret_cast<op16*>(out),
                      (cudaStream_t)stream, c_live_out, false, nullptr, c_live_in);
 }
 
@@ -461,17 +462,17 @@ static inline int pad64(int c) { return (c + 63) / 64 * 64; }   // weight / K-bl
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }   // channels per pixel kept in memory
 
 struct HrPlan {
-  __nv_bfloat16* x[4][3];     // per branch: current / scratch / next
-  __nv_bfloat16* term[4][4];  // fuse terms (i, j != i) at the size of branch i
-  __nv_bfloat16* chain[2];    // intermediates of the stride-2 chains
+  op16* x[4][3];     // per branch: current / scratch / next
+  op16* term[4][4];  // fuse terms (i, j != i) at the size of branch i
+  op16* chain[2];    // intermediates of the stride-2 chains
 };
 static size_t hr_plan(int N, int R0, const int* ch, uint8_t* base, HrPlan* p) {
   Bump b{base, 0};
   size_t chain_max = 0;
   for (int i = 0; i < 4; ++i) {
     const size_t n = (size_t)N * (R0 >> i) * (R0 >> i) * pad16(ch[i]);
-    for (int k = 0; k < 3; ++k) p->x[i][k] = b.take<__nv_bfloat16>(n);
-    for (int j = 0; j < 4; ++j) p->term[i][j] = (j == i) ? nullptr : b.take<__nv_bfloat16>(n);
+    for (int k = 0; k < 3; ++k) p->x[i][k] = b.take<op16>(n);
+    for (int j = 0; j < 4; ++j) p->term[i][j] = (j == i) ? nullptr : b.take<op16>(n);
     if (i >= 1 && i <= 2) {
       int cmax = 0;   // chain intermediates at this resolution keep the source branch's channel count (j < i)
       for (int j = 0; j < i; ++j) cmax = ch[j] > cmax ? ch[j] : cmax;
@@ -479,7 +480,7 @@ static size_t hr_plan(int N, int R0, const int* ch, uint8_t* base, HrPlan* p) {
       chain_max = c > chain_max ? c : chain_max;
     }
   }
-  for (int k = 0; k < 2; ++k) p->chain[k] = b.take<__nv_bfloat16>(chain_max > 0 ? chain_max : 64);
+  for (int k = 0; k < 2; ++k) p->chain[k] = b.take<op16>(chain_max > 0 ? chain_max : 64);
   return b.off + 1024;
 }
 
@@ -500,9 +501,9 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
     // ---- branches: 4 BasicBlocks each (hrnet.py:38-67)
     for (int b = 0; b < nb; ++b) {
       for (int k = 0; k < 4; ++k) {
-        __nv_bfloat16* x = p.x[b][cur[b]];
-        __nv_bfloat16* t = p.x[b][(cur[b] + 1) % 3];
-        __nv_bfloat16* y = p.x[b][(cur[b] + 2) % 3];
+        op16* x = p.x[b][cur[b]];
+        op16* t = p.x[b][(cur[b] + 1) % 3];
+        op16* y = p.x[b][(cur[b] + 2) % 3];
         POEM_TRY(launch_conv(x, N, R[b], R[b], Cw[b], mod.branch[b][k][0], Cw[b], 3, 1, true, nullptr, t, st, ch[b], false, nullptr, -1,
                              Cs[b], Cs[b]));
         POEM_TRY(launch_conv(t, N, R[b], R[b], Cw[b], mod.branch[b][k][1], Cw[b], 3, 1, true, x, y, st, ch[b], false, nullptr, -1,
@@ -515,7 +516,7 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
       FuseSumArgs fa;
       fa.n_in = 0;
       for (int j = 0; j < nb; ++j) {
-        const __nv_bfloat16* xj = p.x[j][cur[j]];
+        const op16* xj = p.x[j][cur[j]];
         if (j == i) {
           fa.in[fa.n_in] = xj, fa.shift[fa.n_in] = 0;
         } else if (j > i) {   // 1x1 conv + BN at the low resolution, upsampled by the sum kernel
@@ -523,11 +524,11 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
                                nullptr, -1, Cs[j], Cs[i]));
           fa.in[fa.n_in] = p.term[i][j], fa.shift[fa.n_in] = j - i;
         } else {              // chain of (i - j) stride-2 3x3 convs; all but the last keep C_j channels and ReLU
-          const __nv_bfloat16* src = xj;
+          const op16* src = xj;
           int r = R[j];
           for (int k = 0; k < i - j; ++k) {
             const bool last = (k == i - j - 1);
-            __nv_bfloat16* dst = last ? p.term[i][j] : p.chain[k & 1];
+            op16* dst = last ? p.term[i][j] : p.chain[k & 1];
             POEM_TRY(launch_conv(src, N, r, r, Cw[j], mod.fuse[i][j][k], last ? Cw[i] : Cw[j], 3, 2, !last, nullptr, dst, st, 0, false,
                                  nullptr, -1, Cs[j], last ? Cs[i] : Cs[j]));
             src = dst;
@@ -537,7 +538,7 @@ static int run_hr_modules(const PoemHRModule* mods, int n_modules, int nb, int N
         }
         ++fa.n_in;
       }
-      __nv_bfloat16* dst = p.x[i][(cur[i] + 1) % 3];
+      op16* dst = p.x[i][(cur[i] + 1) % 3];
       const size_t total16 = (size_t)N * R[i] * R[i] * Cs[i] / 16;
       prof_begin(st);
       fuse_sum_relu_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(fa, dst, R[i], R[i], Cs[i], total16);
@@ -554,8 +555,8 @@ static int hr_export(const HrPlan& p, const int* cur, const int* ch, const int* 
     const int cs = pad16(ch[i]);
     dim3 grid((R[i] * R[i] + 31) / 32, (cs + 31) / 32, N), block(32, 8);
     prof_begin(st);
-    nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, st>>>(p.x[i][cur[i]], out[i], ch[i], cs, R[i] * R[i]);
-    LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
+    nhwc_op16_to_nchw_f32_kernel<<<grid, block, 0, st>>>(p.x[i][cur[i]], out[i], ch[i], cs, R[i] * R[i]);
+    LAUNCH_CHECK("nhwc_op16_to_nchw_f32_kernel");
   }
   return POEM_OK;
 }
@@ -580,8 +581,8 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
     const int cs = pad16(ch[i]);
     dim3 grid((R[i] * R[i] + 31) / 32, (cs + 31) / 32, N), block(32, 8);
     prof_begin(st);
-    nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], cs, R[i] * R[i]);
-    LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+    nchw_f32_to_nhwc_op16_kernel<<<grid, block, 0, st>>>(in[i], p.x[i][0], ch[i], cs, R[i] * R[i]);
+    LAUNCH_CHECK("nchw_f32_to_nhwc_op16_kernel");
   }
   int cur[4] = {0, 0, 0, 0};   // index of the buffer holding the branch's current activation
   POEM_TRY(run_hr_modules(w->modules, w->n_modules, 4, N, R, Cp, ch, p, cur, st));
@@ -592,17 +593,17 @@ extern "C" int poem_hrnet_stage4_forward(const PoemHRStage4* w, int n_images, in
 // whole HRNet-W40 backbone (hrnet.py:385-420): stem, layer1 (4 Bottlenecks), transitions, stages 2-4
 // ------------------------------------------------------------------------------------------------
 struct HrNetPlan {
-  __nv_bfloat16 *s1, *s2;        // stem outputs: (N,R/2,R/2,64), (N,R/4,R/4,64)
-  __nv_bfloat16 *l256[3], *l64[2];   // layer1 activations at R/4: 256 and 64 channels
+  op16 *s1, *s2;        // stem outputs: (N,R/2,R/2,64), (N,R/4,R/4,64)
+  op16 *l256[3], *l64[2];   // layer1 activations at R/4: 256 and 64 channels
   HrPlan hr;
 };
 static size_t hrnet_plan(int N, int img_res, const int* ch, uint8_t* base, HrNetPlan* p) {
   Bump b{base, 0};
   const size_t r2 = (size_t)(img_res / 2) * (img_res / 2), r4 = (size_t)(img_res / 4) * (img_res / 4);
-  p->s1 = b.take<__nv_bfloat16>((size_t)N * r2 * 64);
-  p->s2 = b.take<__nv_bfloat16>((size_t)N * r4 * 64);
-  for (int k = 0; k < 3; ++k) p->l256[k] = b.take<__nv_bfloat16>((size_t)N * r4 * 256);
-  for (int k = 0; k < 2; ++k) p->l64[k] = b.take<__nv_bfloat16>((size_t)N * r4 * 64);
+  p->s1 = b.take<op16>((size_t)N * r2 * 64);
+  p->s2 = b.take<op16>((size_t)N * r4 * 64);
+  for (int k = 0; k < 3; ++k) p->l256[k] = b.take<op16>((size_t)N * r4 * 256);
+  for (int k = 0; k < 2; ++k) p->l64[k] = b.take<op16>((size_t)N * r4 * 64);
   const size_t off = (b.off + 1023) & ~size_t(1023);
   const size_t hr = hr_plan(N, img_res / 4, ch, base ? base + off : nullptr, &p->hr);
   return off + hr;
@@ -613,7 +614,7 @@ extern "C" size_t poem_hrnet_workspace_bytes(const PoemHRNet* w, int n_images, i
   return hrnet_plan(n_images, img_res, w->channels, nullptr, &p);
 }
 
-// stem .. stage 4 on the planned workspace; leaves branch b's map in p.hr.x[b][cur[b]] (NHWC bf16, padded channels)
+// stem .. stage 4 on the planned workspace; leaves branch b's map in p.hr.x[b][cur[b]] (NHWC op16, padded channels)
 static int hrnet_run(const PoemHRNet* w, int N, int img_res, const float* images, const HrNetPlan& p, int* cur,
                      cudaStream_t st) {
   const int* ch = w->channels;
@@ -628,14 +629,14 @@ static int hrnet_run(const PoemHRNet* w, int N, int img_res, const float* images
   }
   POEM_TRY(launch_conv(p.s1, N, R2, R2, 64, w->stem2, 64, 3, 2, true, nullptr, p.s2, st));
   // layer1: Bottleneck x4 (hrnet.py:70-104, 254-257)
-  const __nv_bfloat16* x = p.s2;
+  const op16* x = p.s2;
   int x_ch = 64;
   for (int k = 0; k < 4; ++k) {
     const PoemBottleneck& bt = w->layer1[k];
     POEM_TRY(launch_conv(x, N, R4, R4, x_ch, bt.c1, 64, 1, 1, true, nullptr, p.l64[0], st));
     POEM_TRY(launch_conv(p.l64[0], N, R4, R4, 64, bt.c2, 64, 3, 1, true, nullptr, p.l64[1], st));
-    const __nv_bfloat16* res = x;
-    __nv_bfloat16* y = p.l256[k % 2];
+    const op16* res = x;
+    op16* y = p.l256[k % 2];
     if (bt.ds.w) {
       POEM_TRY(launch_conv(x, N, R4, R4, x_ch, bt.ds, 256, 1, 1, false, nullptr, p.l256[2], st));
       res = p.l256[2];
@@ -701,17 +702,17 @@ extern "C" int poem_hrnet_forward(const PoemHRNet* w, int n_images, int img_res,
 // ------------------------------------------------------------------------------------------------
 struct FeatPlan {
   HrNetPlan net;
-  __nv_bfloat16* d[3];     // pyramid sums at R/8, R/16, R/32
+  op16* d[3];     // pyramid sums at R/8, R/16, R/32
   float* f8;               // feat_in output at R/32, fp32 NHWC (padded channels)
-  __nv_bfloat16* cat[3];   // uv_decode: cat(upsampled, skip) at R/16, R/8, R/4
-  __nv_bfloat16* u[3];     // uv_decode: ConvBlock outputs at R/16, R/8, R/4
+  op16* cat[3];   // uv_decode: cat(upsampled, skip) at R/16, R/8, R/4
+  op16* u[3];     // uv_decode: ConvBlock outputs at R/16, R/8, R/4
 };
 static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, bool with_uv, uint8_t* base, FeatPlan* p) {
   const size_t net = hrnet_plan(N, img_res, ch, base, &p->net);
   Bump b{base ? base + ((net + 1023) & ~size_t(1023)) : nullptr, 0};
   for (int i = 0; i < 3; ++i) {
     const size_t r = (size_t)(img_res / 8) >> i;
-    p->d[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad16(ch[i + 1]));
+    p->d[i] = b.take<op16>((size_t)N * r * r * pad16(ch[i + 1]));
   }
   const size_t r8 = (size_t)img_res / 32;
   p->f8 = b.take<float>((size_t)N * r8 * r8 * pad64(out_ch));
@@ -719,8 +720,8 @@ static size_t feat_plan(int N, int img_res, const int* ch, int out_ch, bool with
     p->cat[i] = p->u[i] = nullptr;
     if (!with_uv) continue;
     const size_t r = (size_t)(img_res / 16) << i;    // R/16, R/8, R/4
-    p->cat[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad16(ch[3 - i] + ch[2 - i]));
-    p->u[i] = b.take<__nv_bfloat16>((size_t)N * r * r * pad16(ch[2 - i]));
+    p->cat[i] = b.take<op16>((size_t)N * r * r * pad16(ch[3 - i] + ch[2 - i]));
+    p->u[i] = b.take<op16>((size_t)N * r * r * pad16(ch[2 - i]));
   }
   return ((net + 1023) & ~size_t(1023)) + b.off;
 }
@@ -758,7 +759,7 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
     POEM_TRY(hr_export(p.net.hr, cur, ch, R, N, maps, st));
   }
   // ---- feat_decode: x = f0 ; x = relu(bn(conv3x3 s2(x))) + f_{i+1}
-  const __nv_bfloat16* x = p.net.hr.x[0][cur[0]];
+  const op16* x = p.net.hr.x[0][cur[0]];
   for (int i = 0; i < 3; ++i) {
     POEM_TRY(launch_conv(x, N, R[i], R[i], Cp[i], fd->delayer[i], Cp[i + 1], 3, 2, true, p.net.hr.x[i + 1][cur[i + 1]],
                          p.d[i], st, 0, /*relu_before_res=*/true, nullptr, -1, pad16(ch[i]), pad16(ch[i + 1])));
@@ -781,7 +782,7 @@ extern "C" int poem_image_features(const PoemHRNet* w, const PoemFeatDecode* fd,
   if (!uv) return POEM_OK;
   // ---- uv_decode + heatmap_stage (POEM.py:205-229): x = f3; x = ConvBlock_i(cat(up2(x), f_{2-i})); max-pool; 1x1 +
   // sigmoid; soft-argmax
-  const __nv_bfloat16* h = p.net.hr.x[3][cur[3]];
+  const op16* h = p.net.hr.x[3][cur[3]];
   int h_cs = pad16(ch[3]), h_c = ch[3];
   for (int i = 0; i < 3; ++i) {
     const int lo = 2 - i;                      // skip branch, resolution R[lo]
@@ -830,9 +831,9 @@ extern "C" int poem_triangulate_dlt(const float* uv_px, const float* cam_intr, c
   return POEM_OK;
 }
 
-extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int ldw, const float* bias, int M, int N,
+extern "C" int poem_linear(const poem_op16* A, int lda, const poem_op16* W, int ldw, const float* bias, int M, int N,
                            int K, int act, const float* residual, int ld_res, float* out_f32, int ld_f32,
-                           poem_bf16* out_bf16, int ld_bf16, void* stream) {
+                           poem_op16* out_op16, int ld_op16, void* stream) {
   GemmEpilogue e = epi_default(N);
   e.bias = bias;
   e.act = act;
@@ -843,9 +844,9 @@ extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int 
   }
   e.out_f32 = out_f32;
   e.ld_f32 = ld_f32;
-  e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  e.ld_bf16 = ld_bf16;
-  return launch_gemm(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W), ldw, M,
+  e.out_op16 = reinterpret_cast<op16*>(out_op16);
+  e.ld_op16 = ld_op16;
+  return launch_gemm(reinterpret_cast<const op16*>(A), lda, reinterpret_cast<const op16*>(W), ldw, M,
                      N, K, e, (cudaStream_t)stream);
 }
 
@@ -853,7 +854,7 @@ extern "C" int poem_linear(const poem_bf16* A, int lda, const poem_bf16* W, int 
 // MHA launch
 // ------------------------------------------------------------------------------------------------
 template <int HD>
-static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, __nv_bfloat16* ctx,
+static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, op16* ctx,
                          int ld_ctx, int B, int Lq, int Lk, int n_heads, int q_col0, int k_col0, int v_col0,
                          cudaStream_t st) {
   static bool configured = false;
@@ -872,8 +873,8 @@ static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 }
 
 // Q [B*Lq, ldq] (columns q_col0..), K [B*Lk, ldk] (columns k_col0..), V [B*Lk, ldv] (columns v_col0..); all row-major
-static int launch_mha(const __nv_bfloat16* Q, int ldq, int q_col0, const __nv_bfloat16* K, int ldk, int k_col0,
-                      const __nv_bfloat16* V, int ldv, int v_col0, __nv_bfloat16* ctx, int ld_ctx, int B, int Lq,
+static int launch_mha(const op16* Q, int ldq, int q_col0, const op16* K, int ldk, int k_col0,
+                      const op16* V, int ldv, int v_col0, op16* ctx, int ld_ctx, int B, int Lq,
                       int Lk, int D, int n_heads, cudaStream_t st) {
   if (D % n_heads) return fail(POEM_E_BADDIM, "mha: D %% heads != 0");
   const int hd = D / n_heads;
@@ -881,9 +882,9 @@ static int launch_mha(const __nv_bfloat16* Q, int ldq, int q_col0, const __nv_bf
   if (ld_ctx % 8) return fail(POEM_E_ALIGN, "mha: ld_ctx must be a multiple of 8");
   const uint32_t boxc = hd < 64 ? (uint32_t)hd : 64u;
   CUtensorMap tq, tk, tv;
-  POEM_TRY(make_tmap_bf16(&tq, Q, (uint64_t)B * Lq, (uint64_t)ldq, (uint64_t)ldq, boxc, MHA_BQ));
-  POEM_TRY(make_tmap_bf16(&tk, K, (uint64_t)B * Lk, (uint64_t)ldk, (uint64_t)ldk, boxc, MHA_BKEY));
-  POEM_TRY(make_tmap_bf16(&tv, V, (uint64_t)B * Lk, (uint64_t)ldv, (uint64_t)ldv, boxc, MHA_BKEY));
+  POEM_TRY(make_tmap_op16(&tq, Q, (uint64_t)B * Lq, (uint64_t)ldq, (uint64_t)ldq, boxc, MHA_BQ));
+  POEM_TRY(make_tmap_op16(&tk, K, (uint64_t)B * Lk, (uint64_t)ldk, (uint64_t)ldk, boxc, MHA_BKEY));
+  POEM_TRY(make_tmap_op16(&tv, V, (uint64_t)B * Lk, (uint64_t)ldv, (uint64_t)ldv, boxc, MHA_BKEY));
   switch (hd) {
     case 32: return launch_mha_hd<32>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, q_col0, k_col0, v_col0, st);
     case 64: return launch_mha_hd<64>(tq, tk, tv, ctx, ld_ctx, B, Lq, Lk, n_heads, q_col0, k_col0, v_col0, st);
@@ -892,11 +893,11 @@ static int launch_mha(const __nv_bfloat16* Q, int ldq, int q_col0, const __nv_bf
   }
 }
 
-extern "C" int poem_mha(const poem_bf16* Q, int ldq, const poem_bf16* K, int ldk, const poem_bf16* V, int ldv,
-                        poem_bf16* ctx, int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream) {
+extern "C" int poem_mha(const poem_op16* Q, int ldq, const poem_op16* K, int ldk, const poem_op16* V, int ldv,
+                        poem_op16* ctx, int ld_ctx, int B, int Lq, int Lk, int D, int n_heads, void* stream) {
   if (!Q || !K || !V || !ctx) return fail(POEM_E_NULL, "mha: null pointer");
-  return launch_mha(reinterpret_cast<const __nv_bfloat16*>(Q), ldq, 0, reinterpret_cast<const __nv_bfloat16*>(K), ldk,
-                    0, reinterpret_cast<const __nv_bfloat16*>(V), ldv, 0, reinterpret_cast<__nv_bfloat16*>(ctx), ld_ctx,
+  return launch_mha(reinterpret_cast<const op16*>(Q), ldq, 0, reinterpret_cast<const op16*>(K), ldk,
+                    0, reinterpret_cast<const op16*>(V), ldv, 0, reinterpret_cast<op16*>(ctx), ld_ctx,
                     B, Lq, Lk, D, n_heads, (cudaStream_t)stream);
 }
 
@@ -934,7 +935,7 @@ extern "C" int poem_knn32(const float* query_xyz, const float* ref_xyz, int32_t*
   return launch_knn(query_xyz, ref_xyz, idx, B, Lq, Lr, (cudaStream_t)stream);
 }
 
-static int launch_layernorm(const float* x, const float* g, const float* b, float* y32, __nv_bfloat16* y16, int rows,
+static int launch_layernorm(const float* x, const float* g, const float* b, float* y32, op16* y16, int rows,
                             int D, cudaStream_t st) {
   if (D % 32 || D > 1024) return fail(POEM_E_BADDIM, "layernorm: D=%d", D);
   const int threads = 256;
@@ -943,10 +944,10 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
   LAUNCH_CHECK("layernorm_kernel");
   return POEM_OK;
 }
-extern "C" int poem_layernorm(const float* x, const float* gamma, const float* beta, float* y_f32, poem_bf16* y_bf16,
+extern "C" int poem_layernorm(const float* x, const float* gamma, const float* beta, float* y_f32, poem_op16* y_op16,
                               int rows, int D, void* stream) {
   if (!x || !gamma || !beta) return fail(POEM_E_NULL, "layernorm: null pointer");
-  return launch_layernorm(x, gamma, beta, y_f32, reinterpret_cast<__nv_bfloat16*>(y_bf16), rows, D,
+  return launch_layernorm(x, gamma, beta, y_f32, reinterpret_cast<op16*>(y_op16), rows, D,
                           (cudaStream_t)stream);
 }
 
@@ -989,7 +990,14 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
     view_tables_kernel<<<1, 256, 0, st>>>(vp, B, NV, P, dev);
     LAUNCH_CHECK("view_tables_kernel");
   } else {
+    // a memcpy node would keep a pointer into this stack frame: refuse to be captured into a CUDA graph
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(POEM_E_BADDIM, "batch %d > %d cannot be captured into a CUDA graph (view tables are copied from the host)", B,
+                  VIEW_PARAM_MAX);
     CUDA_TRY(cudaMemcpyAsync(dev, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // h dies with this frame
   }
   vt->img_sample = dev;
   vt->img_view = dev + NV;
@@ -1001,7 +1009,7 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
 
 static int launch_project_sample(const float* xmap, const float* intr, const float* extr, const float* bps,
                                  const float* centre, const ViewTables& vt, float* proj, int NV, int D, int P, int fh,
-                                 int fw, float img_w, float img_h, __nv_bfloat16* X, cudaStream_t st) {
+                                 int fw, float img_w, float img_h, op16* X, cudaStream_t st) {
   if (P != SAMPLE_THREADS * 8) return fail(POEM_E_BADDIM, "sampler is specialised for P=4096 (got %d)", P);
   if (D % SAMPLE_CH || P % D) return fail(POEM_E_BADDIM, "sampler: D=%d must divide P and be a multiple of 32", D);
   prof_begin(st);
@@ -1020,7 +1028,7 @@ static int launch_project_sample(const float* xmap, const float* intr, const flo
 
 extern "C" int poem_project_sample(const float* xmap, const float* cam_intr, const float* cam_extr, const float* bps,
                                    const float* centre, const int32_t* host_view_counts, int B, int n_images, int D,
-                                   int P, int fh, int fw, float img_w, float img_h, poem_bf16* X, void* workspace,
+                                   int P, int fh, int fw, float img_w, float img_h, poem_op16* X, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   if (!xmap || !cam_intr || !cam_extr || !bps || !centre || !host_view_counts || !X || !workspace)
     return fail(POEM_E_NULL, "project_sample: null pointer");
@@ -1031,7 +1039,7 @@ extern "C" int poem_project_sample(const float* xmap, const float* cam_intr, con
   ViewTables vt;
   POEM_TRY(upload_view_tables(host_view_counts, B, n_images, P, 64, tab, &vt, (cudaStream_t)stream));
   return launch_project_sample(xmap, cam_intr, cam_extr, bps, centre, vt, proj, n_images, D, P, fh, fw, img_w, img_h,
-                               reinterpret_cast<__nv_bfloat16*>(X), (cudaStream_t)stream);
+                               reinterpret_cast<op16*>(X), (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1043,10 +1051,10 @@ extern "C" size_t poem_vector_attention_workspace_bytes(int B, int Lq, int D) {
 
 // Un-fused composition of the same folded math: token tensors (B*Lq*32, D) live in HBM between the D x D GEMMs.
 //   t0: h -> logits ; t1: pos ; t2: gamma1_pre -> relu(gamma1_pre + qt_i - kt_j)
-static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* ktab, int ldk,
-                          const __nv_bfloat16* vtab, int ldv, const float* q_xyz, const float* ref_xyz, const int* idx,
+static int launch_vecattn(const PoemVecAttn* w, const op16* q, int ldq, const op16* ktab, int ldk,
+                          const op16* vtab, int ldv, const float* q_xyz, const float* ref_xyz, const int* idx,
                           const int* anchor_idx, const float* anchor_xyz, int B, int Lq, int Lr, int D,
-                          __nv_bfloat16* res, __nv_bfloat16* t0, __nv_bfloat16* t1, __nv_bfloat16* t2,
+                          op16* res, op16* t0, op16* t1, op16* t2,
                           cudaStream_t st) {
   if (!w->wd1 || !w->bd1 || !w->delta2.w || !w->gamma1_delta2.w || !w->gamma2.w)
     return fail(POEM_E_NULL, "vector_attention: weight pointer missing");
@@ -1057,13 +1065,13 @@ static int launch_vecattn(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq,
   va_hdelta_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(q_xyz, ref_xyz, idx, anchor_xyz, w->wd1, w->bd1, t0, Lq, Lr,
                                                           D, T);
   LAUNCH_CHECK("va_hdelta_kernel");
-  auto lin = [&](const __nv_bfloat16* A, const PoemLinear& l, bool bias, __nv_bfloat16* out) {
+  auto lin = [&](const op16* A, const PoemLinear& l, bool bias, op16* out) {
     TagScope ts("va_token");
     GemmEpilogue e = epi_default(D);
     e.bias = bias ? l.b : nullptr;
-    e.out_bf16 = out;
-    e.ld_bf16 = D;
-    return launch_gemm(A, D, reinterpret_cast<const __nv_bfloat16*>(l.w), D, (int)T, D, D, e, st);
+    e.out_op16 = out;
+    e.ld_op16 = D;
+    return launch_gemm(A, D, reinterpret_cast<const op16*>(l.w), D, (int)T, D, D, e, st);
   };
   POEM_TRY(lin(t0, w->delta2, true, t1));          // pos
   POEM_TRY(lin(t0, w->gamma1_delta2, false, t2));  // (W_g1 W_d2) h
@@ -1098,9 +1106,9 @@ static int launch_vecattn_fused(const PoemVecAttn* w, const VaParams& prm, cudaS
     configured = true;
   }
   CUtensorMap t1, t2, t3;
-  POEM_TRY(make_tmap_bf16(&t1, w->delta2.w, D, D, D, 64, 128));
-  POEM_TRY(make_tmap_bf16(&t2, w->gamma1_delta2.w, D, D, D, 64, 128));
-  POEM_TRY(make_tmap_bf16(&t3, w->gamma2.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_op16(&t1, w->delta2.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_op16(&t2, w->gamma1_delta2.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_op16(&t3, w->gamma2.w, D, D, D, 64, 128));
   const int tiles = (prm.n_query + Cfg::QT - 1) / Cfg::QT;
   const int slots = num_sms() * Cfg::CTAS_PER_SM;
   const int grid = tiles < slots ? tiles : slots;
@@ -1110,11 +1118,11 @@ static int launch_vecattn_fused(const PoemVecAttn* w, const VaParams& prm, cudaS
   return POEM_OK;
 }
 
-static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* ktab,
-                                   int ldk, const __nv_bfloat16* vtab, int ldv, const float* q_xyz,
+static int launch_vector_attention(const PoemVecAttn* w, const op16* q, int ldq, const op16* ktab,
+                                   int ldk, const op16* vtab, int ldv, const float* q_xyz,
                                    const float* ref_xyz, const int* idx, const int* anchor_idx,
-                                   const float* anchor_xyz, int B, int Lq, int Lr, int D, __nv_bfloat16* res,
-                                   __nv_bfloat16* t0, __nv_bfloat16* t1, __nv_bfloat16* t2, cudaStream_t st) {
+                                   const float* anchor_xyz, int B, int Lq, int Lr, int D, op16* res,
+                                   op16* t0, op16* t1, op16* t2, cudaStream_t st) {
   if ((idx == nullptr) == (anchor_idx == nullptr)) return fail(POEM_E_NULL, "vector_attention: give idx XOR anchors");
   if (anchor_idx && !anchor_xyz) return fail(POEM_E_NULL, "vector_attention: anchor_xyz missing");
   if (D % 32) return fail(POEM_E_BADDIM, "vector_attention: D=%d", D);
@@ -1140,23 +1148,23 @@ static int launch_vector_attention(const PoemVecAttn* w, const __nv_bfloat16* q,
                         res, t0, t1, t2, st);
 }
 
-extern "C" int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, int ldq, const poem_bf16* ktab, int ldk,
-                                     const poem_bf16* vtab, int ldv, const float* q_xyz, const float* ref_xyz,
+extern "C" int poem_vector_attention(const PoemVecAttn* w, const poem_op16* q, int ldq, const poem_op16* ktab, int ldk,
+                                     const poem_op16* vtab, int ldv, const float* q_xyz, const float* ref_xyz,
                                      const int32_t* idx, const int32_t* anchor_idx, const float* anchor_xyz, int B,
-                                     int Lq, int Lr, int D, poem_bf16* res, void* workspace, size_t workspace_bytes,
+                                     int Lq, int Lr, int D, poem_op16* res, void* workspace, size_t workspace_bytes,
                                      void* stream) {
   if (!w || !q || !ktab || !vtab || !q_xyz || !res || !workspace) return fail(POEM_E_NULL, "vector_attention: null");
   if (workspace_bytes < poem_vector_attention_workspace_bytes(B, Lq, D))
     return fail(POEM_E_WORKSPACE, "vector_attention: workspace too small");
   Bump bump{reinterpret_cast<uint8_t*>(workspace), 0};
   const size_t n = (size_t)B * Lq * 32 * D;
-  __nv_bfloat16* t0 = bump.take<__nv_bfloat16>(n);
-  __nv_bfloat16* t1 = bump.take<__nv_bfloat16>(n);
-  __nv_bfloat16* t2 = bump.take<__nv_bfloat16>(n);
-  return launch_vector_attention(w, reinterpret_cast<const __nv_bfloat16*>(q), ldq,
-                                 reinterpret_cast<const __nv_bfloat16*>(ktab), ldk,
-                                 reinterpret_cast<const __nv_bfloat16*>(vtab), ldv, q_xyz, ref_xyz, idx, anchor_idx,
-                                 anchor_xyz, B, Lq, Lr, D, reinterpret_cast<__nv_bfloat16*>(res), t0, t1, t2,
+  op16* t0 = bump.take<op16>(n);
+  op16* t1 = bump.take<op16>(n);
+  op16* t2 = bump.take<op16>(n);
+  return launch_vector_attention(w, reinterpret_cast<const op16*>(q), ldq,
+                                 reinterpret_cast<const op16*>(ktab), ldk,
+                                 reinterpret_cast<const op16*>(vtab), ldv, q_xyz, ref_xyz, idx, anchor_idx,
+                                 anchor_xyz, B, Lq, Lr, D, reinterpret_cast<op16*>(res), t0, t1, t2,
                                  (cudaStream_t)stream);
 }
 
@@ -1165,16 +1173,17 @@ extern "C" int poem_vector_attention(const PoemVecAttn* w, const poem_bf16* q, i
 // ------------------------------------------------------------------------------------------------
 struct BlockPlan {   // decoder blocks (PtEmbedTRv4)
   float *pt_xyz, *pt_xyz_sorted, *xyz;  // xyz: (NB+1) buffers of B*Q*3; pt_xyz_sorted: BPS in k-d chunk order
-  __nv_bfloat16 *ptf, *KK;   // KK: (B*P, 6D) = K1 | K2 | kt_cross | v_cross | V1 | V2
+  op16 *ptf, *KK;   // KK: (B*P, 6D) = K1 | K2 | kt_cross | v_cross | V1 | V2
   float *qf32, *qe32, *tmp32, *a1_32, *a2_32, *f1_32, *f2_32;
-  __nv_bfloat16 *qf16, *qe16, *qp16, *ctx16, *a1_16, *a2_16, *qkv16, *res16, *f1_16, *qc16, *f2_16, *r1_16, *ffn16;
+  op16 *qf16, *qe16, *qp16, *ctx16, *a1_16, *a2_16, *qkv16, *res16, *f1_16, *qc16, *f2_16, *r1_16, *ffn16;
   int *idx_self, *idx_cross;
-  __nv_bfloat16 *t0, *t1, *t2;
+  op16 *t0, *t1, *t2;
 };
 struct HeadPlan {    // everything in front of the blocks
   int* tables;
   float *proj, *centre, *xmap;
-  __nv_bfloat16 *featT, *X, *H1, *Mm, *S, *H2;
+  op16 *featT, *X, *H1, *Mm, *S, *H2;
+  float* sigma;   // per-token power-of-two scale of S (merge_reduce_kernel)
 };
 
 static int check_dims(const PoemDims* d) {
@@ -1199,8 +1208,8 @@ static void plan_blocks(const PoemDims* d, int B, Bump& b, BlockPlan* p) {
   p->pt_xyz = b.take<float>(BP * 3);
   p->pt_xyz_sorted = b.take<float>(BP * 3);
   p->xyz = b.take<float>((size_t)(d->n_blocks + 1) * BQ * 3);
-  p->ptf = b.take<__nv_bfloat16>(BP * D);
-  p->KK = b.take<__nv_bfloat16>(BP * 6 * D);
+  p->ptf = b.take<op16>(BP * D);
+  p->KK = b.take<op16>(BP * 6 * D);
   p->qf32 = b.take<float>(BQ * D);
   p->qe32 = b.take<float>(BQ * D);
   p->tmp32 = b.take<float>(BQ * D);
@@ -1208,24 +1217,24 @@ static void plan_blocks(const PoemDims* d, int B, Bump& b, BlockPlan* p) {
   p->a2_32 = b.take<float>(BQ * D);
   p->f1_32 = b.take<float>(BQ * D);
   p->f2_32 = b.take<float>(BQ * D);
-  p->qf16 = b.take<__nv_bfloat16>(BQ * D);
-  p->qe16 = b.take<__nv_bfloat16>(BQ * D);
-  p->qp16 = b.take<__nv_bfloat16>(BQ * D);
-  p->ctx16 = b.take<__nv_bfloat16>(BQ * D);
-  p->a1_16 = b.take<__nv_bfloat16>(BQ * D);
-  p->a2_16 = b.take<__nv_bfloat16>(BQ * D);
-  p->qkv16 = b.take<__nv_bfloat16>(BQ * 3 * D);
-  p->res16 = b.take<__nv_bfloat16>(BQ * D);
-  p->f1_16 = b.take<__nv_bfloat16>(BQ * D);
-  p->qc16 = b.take<__nv_bfloat16>(BQ * D);
-  p->f2_16 = b.take<__nv_bfloat16>(BQ * D);
-  p->r1_16 = b.take<__nv_bfloat16>(BQ * D);
-  p->ffn16 = b.take<__nv_bfloat16>(BQ * 4 * D);
+  p->qf16 = b.take<op16>(BQ * D);
+  p->qe16 = b.take<op16>(BQ * D);
+  p->qp16 = b.take<op16>(BQ * D);
+  p->ctx16 = b.take<op16>(BQ * D);
+  p->a1_16 = b.take<op16>(BQ * D);
+  p->a2_16 = b.take<op16>(BQ * D);
+  p->qkv16 = b.take<op16>(BQ * 3 * D);
+  p->res16 = b.take<op16>(BQ * D);
+  p->f1_16 = b.take<op16>(BQ * D);
+  p->qc16 = b.take<op16>(BQ * D);
+  p->f2_16 = b.take<op16>(BQ * D);
+  p->r1_16 = b.take<op16>(BQ * D);
+  p->ffn16 = b.take<op16>(BQ * 4 * D);
   p->idx_self = b.take<int>(T);
   p->idx_cross = b.take<int>(T);
-  p->t0 = b.take<__nv_bfloat16>(T * D);
-  p->t1 = b.take<__nv_bfloat16>(T * D);
-  p->t2 = b.take<__nv_bfloat16>(T * D);
+  p->t0 = b.take<op16>(T * D);
+  p->t1 = b.take<op16>(T * D);
+  p->t2 = b.take<op16>(T * D);
 }
 
 static void plan_head(const PoemDims* d, int B, int NV, Bump& b, HeadPlan* p) {
@@ -1234,13 +1243,14 @@ static void plan_head(const PoemDims* d, int B, int NV, Bump& b, HeadPlan* p) {
   p->tables = b.take<int>(view_tables_ints(B, NV));
   p->proj = b.take<float>((size_t)NV * 24);
   p->centre = b.take<float>((size_t)B * 3);
-  p->featT = b.take<__nv_bfloat16>((size_t)NV * F * C);
+  p->featT = b.take<op16>((size_t)NV * F * C);
   p->xmap = b.take<float>((size_t)NV * D * F);
-  p->X = b.take<__nv_bfloat16>(R * D);
-  p->H1 = b.take<__nv_bfloat16>(R * D);
-  p->Mm = b.take<__nv_bfloat16>(R * D / 2);
-  p->S = b.take<__nv_bfloat16>(BP * D / 2);
-  p->H2 = b.take<__nv_bfloat16>(BP * D / 2);
+  p->X = b.take<op16>(R * D);
+  p->H1 = b.take<op16>(R * D);
+  p->Mm = b.take<op16>(R * D / 2);
+  p->S = b.take<op16>(BP * D / 2);
+  p->H2 = b.take<op16>(BP * D / 2);
+  p->sigma = b.take<float>(BP);
 }
 
 extern "C" size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images) {
@@ -1260,10 +1270,12 @@ extern "C" size_t poem_transformer_workspace_bytes(const PoemDims* dims, int bat
   return b.off + 1024;
 }
 
-static inline const __nv_bfloat16* W16(const PoemLinear& l) { return reinterpret_cast<const __nv_bfloat16*>(l.w); }
+constexpr int kHandCentreJoint = 9;   // reference_joints[:, 9, :] (ptEmb_head.py:873)
 
-static int linear(const char* tag, const __nv_bfloat16* A, int lda, const PoemLinear& l, int M, int N, int K, int act,
-                  const float* res32, float* o32, __nv_bfloat16* o16, cudaStream_t st) {
+static inline const op16* W16(const PoemLinear& l) { return reinterpret_cast<const op16*>(l.w); }
+
+static int linear(const char* tag, const op16* A, int lda, const PoemLinear& l, int M, int N, int K, int act,
+                  const float* res32, float* o32, op16* o16, cudaStream_t st) {
   TagScope ts(tag);
   if (!l.w) return fail(POEM_E_NULL, "weight pointer missing");
   GemmEpilogue e = epi_default(N);
@@ -1276,8 +1288,8 @@ static int linear(const char* tag, const __nv_bfloat16* A, int lda, const PoemLi
   }
   e.out_f32 = o32;
   e.ld_f32 = N;
-  e.out_bf16 = o16;
-  e.ld_bf16 = N;
+  e.out_op16 = o16;
+  e.ld_op16 = N;
   return launch_gemm(A, lda, W16(l), K, M, N, K, e, st);
 }
 
@@ -1289,8 +1301,38 @@ struct SideStream {
   cudaEvent_t fork[POEM_MAX_BLOCKS], join[POEM_MAX_BLOCKS];
   bool ok = false;
 };
+constexpr int kMaxDevices = 32;
+// device a pointer lives on (-1 when it is not device memory); the streams / events below are created per device
+static int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (p == nullptr || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+// makes the device of the call's workspace current for the duration of an entry point (the caller's current device is
+// restored on return), so streams / events are created on, and kernels launched to, the device that owns the buffers
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(const void* device_ptr) {
+    dev = device_of(device_ptr);
+    cudaGetDevice(&prev);
+    if (dev >= 0 && dev != prev) cudaSetDevice(dev);
+    else if (dev < 0) dev = prev;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && dev != prev) cudaSetDevice(prev);
+  }
+};
+static int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
 static SideStream& side_stream() {
-  static thread_local SideStream s;
+  static thread_local SideStream per_dev[kMaxDevices];
+  SideStream& s = per_dev[current_device()];
   if (!s.ok) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess) {
       s.ok = true;
@@ -1302,6 +1344,13 @@ static SideStream& side_stream() {
   return s;
 }
 
+static thread_local int32_t* g_nbr_export = nullptr;
+static thread_local size_t g_nbr_capacity = 0;
+extern "C" void poem_debug_export_neighbours(int32_t* device_buf, size_t capacity) {
+  g_nbr_export = device_buf;
+  g_nbr_capacity = device_buf ? capacity : 0;
+}
+
 static int launch_block_knn(const PoemWeights* w, int B, int Q, int P, const BlockPlan& p, const float* xyz,
                             bool pt_is_bps, cudaStream_t st) {
   POEM_TRY(launch_knn(xyz, xyz, p.idx_self, B, Q, Q, st));
@@ -1310,7 +1359,7 @@ static int launch_block_knn(const PoemWeights* w, int B, int Q, int P, const Blo
   return launch_knn(xyz, p.pt_xyz, p.idx_cross, B, Q, P, st);
 }
 
-// a8-a13: the NB decoder blocks. Expects p.ptf (bf16 BPS features), p.pt_xyz, p.xyz[0], p.qf32/p.qf16 filled.
+// a8-a13: the NB decoder blocks. Expects p.ptf (op16 BPS features), p.pt_xyz, p.xyz[0], p.qf32/p.qf16 filled.
 // coords_out[i] = nan_to_num(xyz_i) * radius + centre when centre != NULL, else the raw normalised xyz_i.
 static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const BlockPlan& p, const float* centre,
                       float* coords_out, float* out_feats, bool pt_is_bps, cudaStream_t st) {
@@ -1344,6 +1393,13 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
     if (!anchors) {   // neighbour indices of this block: computed on the side stream since the previous block ended
       if (knn_on_side) CUDA_TRY(cudaStreamWaitEvent(st, side.join[i], 0));
       else POEM_TRY(launch_block_knn(w, B, Q, P, p, xyz_in, pt_is_bps, st));
+      if (g_nbr_export != nullptr) {   // test hook: the index sets this block is about to use
+        const size_t T = (size_t)BQ * 32;
+        if ((size_t)(NB - 1) * 2 * T > g_nbr_capacity) return fail(POEM_E_WORKSPACE, "neighbour export buffer too small");
+        int32_t* dst = g_nbr_export + (size_t)(i - 1) * 2 * T;
+        CUDA_TRY(cudaMemcpyAsync(dst, p.idx_self, T * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dst + T, p.idx_cross, T * 4, cudaMemcpyDeviceToDevice, st));
+      }
     }
     POEM_TRY(launch_vector_attention(&k.self_attn, p.qkv16, 3 * D, p.qkv16 + D, 3 * D, p.qkv16 + 2 * D, 3 * D, xyz_in,
                                      xyz_in, anchors ? nullptr : p.idx_self, anchors ? w->anchor_idx : nullptr,
@@ -1394,6 +1450,7 @@ extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights*
   if (B < 1) return fail(POEM_E_BADDIM, "batch=%d", B);
   if (out_feats && !dims->run_last_ffn) return fail(POEM_E_BADDIM, "out_feats needs dims->run_last_ffn");
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  DeviceGuard guard(workspace);
   cudaStream_t st = (cudaStream_t)stream;
   Bump b{reinterpret_cast<uint8_t*>(workspace), 0};
   BlockPlan p;
@@ -1404,11 +1461,11 @@ extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights*
   CUDA_TRY(cudaMemcpyAsync(p.xyz, query_xyz, BQ * 3 * 4, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(p.qf32, query_feat, BQ * D * 4, cudaMemcpyDeviceToDevice, st));
   prof_begin(st);
-  f32_to_bf16_kernel<<<(unsigned)((BQ * D + 255) / 256), 256, 0, st>>>(query_feat, p.qf16, BQ * D);
-  LAUNCH_CHECK("f32_to_bf16_kernel");
+  f32_to_op16_kernel<<<(unsigned)((BQ * D + 255) / 256), 256, 0, st>>>(query_feat, p.qf16, BQ * D);
+  LAUNCH_CHECK("f32_to_op16_kernel");
   prof_begin(st);
-  f32_to_bf16_kernel<<<(unsigned)((BP * D + 255) / 256), 256, 0, st>>>(pt_feats, p.ptf, BP * D);
-  LAUNCH_CHECK("f32_to_bf16_kernel");
+  f32_to_op16_kernel<<<(unsigned)((BP * D + 255) / 256), 256, 0, st>>>(pt_feats, p.ptf, BP * D);
+  LAUNCH_CHECK("f32_to_op16_kernel");
   return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, /*pt_is_bps=*/false, st);
 }
 
@@ -1497,6 +1554,7 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   if (R > 0x7fffffffLL || (long long)BQ * 32 > 0x7fffffffLL) return fail(POEM_E_BADDIM, "problem too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(POEM_E_ALIGN, "workspace must be 1024-byte aligned");
+  DeviceGuard guard(workspace);
   Bump bump{reinterpret_cast<uint8_t*>(workspace), 0};
   HeadPlan h;
   BlockPlan p;
@@ -1512,8 +1570,8 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   {
     dim3 grid((F + 31) / 32, (C + 31) / 32, NV), block(32, 8);
     prof_begin(st);
-    nchw_to_rows_bf16_kernel<<<grid, block, 0, st>>>(in->mlvl_feat, h.featT, C, F);
-    LAUNCH_CHECK("nchw_to_rows_bf16_kernel");
+    nchw_to_rows_op16_kernel<<<grid, block, 0, st>>>(in->mlvl_feat, h.featT, C, F);
+    LAUNCH_CHECK("nchw_to_rows_op16_kernel");
     GemmEpilogue e = epi_default(D);
     e.bias = w->input_proj.b;
     e.res_mode = RES_POSADD;
@@ -1529,7 +1587,8 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   }
   // ---- a3/a7: centre, normalised point sets
   prof_begin(st);
-  gather_centre_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(in->reference_joints, h.centre, dims->center_idx, B);
+  // the hand centre is ALWAYS joint 9 (ptEmb_head.py:873); dims->center_idx only roots the MANO layer (a16)
+  gather_centre_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(in->reference_joints, h.centre, kHandCentreJoint, B);
   LAUNCH_CHECK("gather_centre_kernel");
   {
     const int total = B * (P + Q) * 3;
@@ -1550,26 +1609,39 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
     prof_begin(st);
     const unsigned blocks = (unsigned)(((size_t)BP * 32 + threads - 1) / threads);
     switch (H) {
-      case 64: merge_reduce_kernel<2><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
-      case 128: merge_reduce_kernel<4><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
-      case 256: merge_reduce_kernel<8><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
-      default: merge_reduce_kernel<16><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, P, BP); break;
+      case 64: merge_reduce_kernel<2><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, h.sigma, P, BP); break;
+      case 128: merge_reduce_kernel<4><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, h.sigma, P, BP); break;
+      case 256: merge_reduce_kernel<8><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, h.sigma, P, BP); break;
+      default: merge_reduce_kernel<16><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, h.sigma, P, BP); break;
     }
     LAUNCH_CHECK("merge_reduce_kernel");
   }
-  POEM_TRY(linear("merge1a", h.S, H, w->merge1a, BP, H, H, ACT_RELU, nullptr, nullptr, h.H2, st));
+  {   // MLP1 hidden layer on S / sigma: relu(W s / sigma + b / sigma) = H2 / sigma
+    if (!w->merge1a.w) return fail(POEM_E_NULL, "merge_net_feature.1.0 missing");
+    GemmEpilogue e = epi_default(H);
+    e.bias = w->merge1a.b;
+    e.act = ACT_RELU;
+    e.row_sigma = h.sigma;
+    e.sigma_mode = 1;
+    e.out_op16 = h.H2;
+    e.ld_op16 = H;
+    TagScope ts("merge1a");
+    POEM_TRY(launch_gemm(h.S, H, W16(w->merge1a), H, BP, H, H, e, st));
+  }
   {
     if (!w->merge1b.w) return fail(POEM_E_NULL, "merge_net_feature.1.2 missing");
     GemmEpilogue e = epi_default(D);
     e.bias = w->merge1b.b;
     e.res_mode = RES_MERGE;
-    e.res_bf16 = h.X;
+    e.res_op16 = h.X;
     e.res_ld = D;
     e.row_tab = vt.sample_rowbase;
     e.row_cnt = vt.sample_views;
     e.rows_per_group = P;
-    e.out_bf16 = p.ptf;
-    e.ld_bf16 = D;
+    e.row_sigma = h.sigma;
+    e.sigma_mode = 2;
+    e.out_op16 = p.ptf;
+    e.ld_op16 = D;
     TagScope ts("merge1b");
     POEM_TRY(launch_gemm(h.H2, H, W16(w->merge1b), H, BP, D, H, e, st));
   }
@@ -1603,18 +1675,21 @@ static size_t staging_slot_bytes(const PoemDims* d, int B, int NV) {
 // two staging slots: the host->device copy of call i + 1 overlaps the kernels of call i
 extern "C" size_t poem_staging_bytes(const PoemDims* d, int B, int NV) {
   if (check_dims(d) != POEM_OK) return 0;
-  return 2 * staging_slot_bytes(d, B, NV);
+  return 2 * staging_slot_bytes(d, B, NV) + 2048;
 }
 
-// copy stream + events of the host-buffer entry point (per host thread)
+// copy stream + events of the host-buffer entry point (per host thread and device)
 struct HostPipe {
   cudaStream_t copy = nullptr;
   cudaEvent_t h2d_done[2], slot_free[2];
   int next = 0;
   bool ok = false;
+  const void* staging = nullptr;   // staging buffer of the previous call: a different one means the slots moved
+  size_t staging_bytes = 0;
 };
 static HostPipe& host_pipe() {
-  static thread_local HostPipe p;
+  static thread_local HostPipe per_dev[kMaxDevices];
+  HostPipe& p = per_dev[current_device()];
   if (!p.ok && cudaStreamCreateWithFlags(&p.copy, cudaStreamNonBlocking) == cudaSuccess) {
     p.ok = true;
     for (int i = 0; i < 2; ++i)
@@ -1654,7 +1729,12 @@ static int head_forward_host_impl(const PoemDims* dims, const PoemWeights* w, co
   if (reinterpret_cast<uintptr_t>(staging) & 1023) return fail(POEM_E_ALIGN, "staging must be 1024-byte aligned");
   const int B = hin->batch, NV = hin->n_images;
   const size_t slot_bytes = staging_slot_bytes(dims, B, NV);
-  if (staging_bytes < 2 * slot_bytes) return fail(POEM_E_WORKSPACE, "staging %zu < required %zu", staging_bytes, 2 * slot_bytes);
+  // the two slots sit at fixed offsets 0 and staging_bytes / 2, whatever the shape of this call: consecutive calls
+  // with different (batch, views) — the last partial batch of an epoch, ragged view counts — must not overlap the
+  // slot the previous call is still reading
+  const size_t slot_stride = (staging_bytes / 2) & ~size_t(1023);
+  if (slot_stride < slot_bytes) return fail(POEM_E_WORKSPACE, "staging %zu < required %zu", staging_bytes, 2 * slot_bytes + 2048);
+  DeviceGuard guard(workspace);
   if (workspace_bytes < poem_workspace_bytes(dims, B, NV))
     return fail(POEM_E_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, poem_workspace_bytes(dims, B, NV));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1668,7 +1748,13 @@ static int head_forward_host_impl(const PoemDims* dims, const PoemWeights* w, co
   const int slot = piped ? hp.next : 0;
   if (piped) hp.next ^= 1;
   cudaStream_t cs = piped ? hp.copy : st;
-  Bump b{reinterpret_cast<uint8_t*>(staging) + (size_t)slot * slot_bytes, 0};
+  if (piped && (hp.staging != staging || hp.staging_bytes != staging_bytes)) {
+    // another staging buffer (or size) than the previous call's: its slot layout is unrelated, wait for both slots
+    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamWaitEvent(cs, hp.slot_free[k], 0));
+    hp.staging = staging;
+    hp.staging_bytes = staging_bytes;
+  }
+  Bump b{reinterpret_cast<uint8_t*>(staging) + (size_t)slot * slot_stride, 0};
   const size_t n_feat = (size_t)NV * dims->in_channels * 256;
   float* d_feat = b.take<float>(n_feat);
   float* d_intr = b.take<float>((size_t)NV * 9);

@@ -6,10 +6,10 @@
 namespace poem {
 
 // ------------------------------------------------------------------------------------------------
-// (BV,C,256) f32 NCHW feature maps -> (BV*256, C) bf16 rows (K-major A operand of the input projection)
+// (BV,C,256) f32 NCHW feature maps -> (BV*256, C) op16 rows (K-major A operand of the input projection)
 // reference: input of nn.Conv2d(k=1) at lib/models/heads/ptEmb_head.py:835
 // ------------------------------------------------------------------------------------------------
-__global__ void nchw_to_rows_bf16_kernel(const float* __restrict__ feat, __nv_bfloat16* __restrict__ rows, int C,
+__global__ void nchw_to_rows_op16_kernel(const float* __restrict__ feat, op16* __restrict__ rows, int C,
                                          int HW) {
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
@@ -22,7 +22,7 @@ __global__ void nchw_to_rows_bf16_kernel(const float* __restrict__ feat, __nv_bf
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
-    if (c < C && p < HW) rows[((size_t)img * HW + p) * C + c] = __float2bfloat16(tile[tx][i]);
+    if (c < C && p < HW) rows[((size_t)img * HW + p) * C + c] = f2op16(tile[tx][i]);
   }
 }
 
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS)
 project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ proj,
                       const float* __restrict__ bps, const float* __restrict__ centre,
                       const int* __restrict__ img_sample, const int* __restrict__ img_view,
-                      const int* __restrict__ sample_rowbase, __nv_bfloat16* __restrict__ X, int D, int P, int FH,
+                      const int* __restrict__ sample_rowbase, op16* __restrict__ X, int D, int P, int FH,
                       int FW, float inv_w, float inv_h) {
   // Pixel-major copy of this block's 32 channels: pix[pixel][SAMPLE_PITCH], 36 floats per pixel (32 channels + pad).
   // A tap is then read as 8 x LDS.128 (4 channels each) instead of 32 scalar loads, and with the 144-byte pitch the
@@ -168,10 +168,10 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
     for (int q = 0; q < 4; ++q) {
       const size_t rbase = row0 + (size_t)(d0 + 4 * cg + q) * chunks;
       uint4 pk;
-      pk.x = pack_bf16x2(v[q][0], v[q][1]);
-      pk.y = pack_bf16x2(v[q][2], v[q][3]);
-      pk.z = pack_bf16x2(v[q][4], v[q][5]);
-      pk.w = pack_bf16x2(v[q][6], v[q][7]);
+      pk.x = pack_op16x2(v[q][0], v[q][1]);
+      pk.y = pack_op16x2(v[q][2], v[q][3]);
+      pk.z = pack_op16x2(v[q][4], v[q][5]);
+      pk.w = pack_op16x2(v[q][6], v[q][7]);
       *reinterpret_cast<uint4*>(X + (rbase + p0 / D) * D + (p0 % D)) = pk;
     }
   }
@@ -184,12 +184,12 @@ project_sample_kernel(const float* __restrict__ xmap, const float* __restrict__ 
 //   N  > 1 : w_n = <m_n, m_0>, s = sum_{n>=1} w_n m_n
 // one warp per token.
 // ------------------------------------------------------------------------------------------------
-template <int PER>   // bf16 values per lane: H = 32 * PER, lane owns columns [lane*PER, lane*PER + PER)
-__global__ void merge_reduce_kernel(const __nv_bfloat16* __restrict__ m, const int* __restrict__ sample_rowbase,
-                                    const int* __restrict__ sample_views, __nv_bfloat16* __restrict__ s, int P,
-                                    int n_tokens) {
+template <int PER>   // op16 values per lane: H = 32 * PER, lane owns columns [lane*PER, lane*PER + PER)
+__global__ void merge_reduce_kernel(const op16* __restrict__ m, const int* __restrict__ sample_rowbase,
+                                    const int* __restrict__ sample_views, op16* __restrict__ s,
+                                    float* __restrict__ sigma, int P, int n_tokens) {
   constexpr int H = 32 * PER;
-  constexpr int WORDS = PER / 2;   // 32-bit words (bf16 pairs) per lane
+  constexpr int WORDS = PER / 2;   // 32-bit words (op16 pairs) per lane
   const int tok = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tok >= n_tokens) return;
@@ -213,8 +213,8 @@ __global__ void merge_reduce_kernel(const __nv_bfloat16* __restrict__ m, const i
     }
 #pragma unroll
     for (int i = 0; i < WORDS; ++i) {
-      v[2 * i] = __uint_as_float(w[i] << 16);
-      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      v[2 * i] = op16_lo(w[i]);
+      v[2 * i + 1] = op16_hi(w[i]);
     }
   };
   float m0[PER], acc[PER];
@@ -232,18 +232,29 @@ __global__ void merge_reduce_kernel(const __nv_bfloat16* __restrict__ m, const i
 #pragma unroll
     for (int i = 0; i < PER; ++i) acc[i] += dot * mv[i];
   }
+  // s is cubic in the activations (<m_n, m_0> m_n): the row is stored as s / sigma with sigma = 2^floor(log2 max|s|)
+  // (exact), so the fp16 operand of MLP1 can neither overflow nor lose its small rows; the GEMM epilogues undo it.
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) mx = fmaxf(mx, fabsf(acc[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const uint32_t ebits = __float_as_uint(mx) & 0x7f800000u;
+  const float sig = (ebits == 0u || ebits == 0x7f800000u) ? 1.0f : __uint_as_float(ebits);
+  const float inv = 1.0f / sig;
+  if (lane == 0) sigma[tok] = sig;
   uint32_t* out = reinterpret_cast<uint32_t*>(s + (size_t)tok * H) + lane * WORDS;
 #pragma unroll
-  for (int i = 0; i < WORDS; ++i) out[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
+  for (int i = 0; i < WORDS; ++i) out[i] = pack_op16x2(acc[2 * i] * inv, acc[2 * i + 1] * inv);
 }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (eps 1e-12, biased variance) — HF BertSelfOutput / BertOutput.
-// one warp per row; writes fp32 and bf16 copies.
+// one warp per row; writes fp32 and op16 copies.
 // ------------------------------------------------------------------------------------------------
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ y_f32,
-                                 __nv_bfloat16* __restrict__ y_bf16, int rows, int D, float eps) {
+                                 op16* __restrict__ y_op16, int rows, int D, float eps) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -270,7 +281,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     const int c = lane + 32 * i;
     const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
     if (y_f32) y_f32[(size_t)row * D + c] = o;
-    if (y_bf16) y_bf16[(size_t)row * D + c] = __float2bfloat16(o);
+    if (y_op16) y_op16[(size_t)row * D + c] = f2op16(o);
   }
 }
 
@@ -433,7 +444,7 @@ __global__ void knn32_bps_kernel(const float* __restrict__ query, const float* _
 __global__ void va_hdelta_kernel(const float* __restrict__ q_xyz, const float* __restrict__ ref_xyz,
                                  const int* __restrict__ idx, const float* __restrict__ anchor_xyz,
                                  const float* __restrict__ wd1, const float* __restrict__ bd1,
-                                 __nv_bfloat16* __restrict__ hdelta, int Lq, int Lr, int D, size_t n_tokens) {
+                                 op16* __restrict__ hdelta, int Lq, int Lr, int D, size_t n_tokens) {
   const size_t t = blockIdx.x;  // one block per token group of 8
   const int sub = threadIdx.x / (blockDim.x / 8);
   const int tl = threadIdx.x % (blockDim.x / 8);
@@ -456,14 +467,14 @@ __global__ void va_hdelta_kernel(const float* __restrict__ q_xyz, const float* _
     v += wd1[c * 3 + 1] * ry;
     v += wd1[c * 3 + 2] * rz;
     v += bd1[c];
-    hdelta[tok * D + c] = __float2bfloat16(fmaxf(v, 0.f));
+    hdelta[tok * D + c] = f2op16(fmaxf(v, 0.f));
   }
 }
 
 // g[t, c] = relu(g[t, c] + qt[i, c] - kt[nbr_j, c])   (in place; g holds (W_g1 W_d2) h on entry)
-__global__ void va_gmix_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ ktab,
+__global__ void va_gmix_kernel(const op16* __restrict__ q, int ldq, const op16* __restrict__ ktab,
                                int ldk, const int* __restrict__ idx, const int* __restrict__ anchor_idx,
-                               __nv_bfloat16* __restrict__ g, int Lq, int Lr, int D, size_t n_tokens) {
+                               op16* __restrict__ g, int Lq, int Lr, int D, size_t n_tokens) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int vec = D / 8;
   const size_t tok = gid / vec;
@@ -476,23 +487,23 @@ __global__ void va_gmix_kernel(const __nv_bfloat16* __restrict__ q, int ldq, con
   const uint4 qv = *reinterpret_cast<const uint4*>(q + qi * ldq + c);
   const uint4 kv = *reinterpret_cast<const uint4*>(ktab + ((size_t)b * Lr + r) * ldk + c);
   const uint4 gv = *reinterpret_cast<const uint4*>(g + tok * D + c);
-  const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
-  const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
-  const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+  const op16x2* q2 = reinterpret_cast<const op16x2*>(&qv);
+  const op16x2* k2 = reinterpret_cast<const op16x2*>(&kv);
+  const op16x2* g2 = reinterpret_cast<const op16x2*>(&gv);
   uint4 ov;
   uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 a = __bfloat1622float2(q2[i]), bb = __bfloat1622float2(k2[i]), cc = __bfloat1622float2(g2[i]);
-    o[i] = pack_bf16x2(fmaxf(cc.x + (a.x - bb.x), 0.f), fmaxf(cc.y + (a.y - bb.y), 0.f));
+    const float2 a = op16x2_to_f2(q2[i]), bb = op16x2_to_f2(k2[i]), cc = op16x2_to_f2(g2[i]);
+    o[i] = pack_op16x2(fmaxf(cc.x + (a.x - bb.x), 0.f), fmaxf(cc.y + (a.y - bb.y), 0.f));
   }
   *reinterpret_cast<uint4*>(g + tok * D + c) = ov;
 }
 
 // res[i, c] = sum_j softmax_j(a[t, c] * inv_sqrt_d) * (v[nbr_j, c] + pos[t, c]);  one thread per (query, channel)
-__global__ void va_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ pos,
-                                 const __nv_bfloat16* __restrict__ vtab, int ldv, const int* __restrict__ idx,
-                                 const int* __restrict__ anchor_idx, __nv_bfloat16* __restrict__ res, int Lq, int Lr,
+__global__ void va_reduce_kernel(const op16* __restrict__ a, const op16* __restrict__ pos,
+                                 const op16* __restrict__ vtab, int ldv, const int* __restrict__ idx,
+                                 const int* __restrict__ anchor_idx, op16* __restrict__ res, int Lq, int Lr,
                                  int D, float inv_sqrt_d, size_t n_query) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t qi = gid / D;
@@ -503,7 +514,7 @@ __global__ void va_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    av[j] = __bfloat162float(a[(qi * 32 + j) * D + c]) * inv_sqrt_d;
+    av[j] = op16_to_f(a[(qi * 32 + j) * D + c]) * inv_sqrt_d;
     mx = fmaxf(mx, av[j]);
   }
   float sum = 0.f, acc = 0.f;
@@ -511,11 +522,11 @@ __global__ void va_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   for (int j = 0; j < 32; ++j) {
     const float e = __expf(av[j] - mx);
     const int r = (anchor_idx != nullptr) ? anchor_idx[j] : idx[qi * 32 + j];
-    const float val = __bfloat162float(vtab[((size_t)b * Lr + r) * ldv + c]) + __bfloat162float(pos[(qi * 32 + j) * D + c]);
+    const float val = op16_to_f(vtab[((size_t)b * Lr + r) * ldv + c]) + op16_to_f(pos[(qi * 32 + j) * D + c]);
     sum += e;
     acc += e * val;
   }
-  res[qi * D + c] = __float2bfloat16(acc / sum);
+  res[qi * D + c] = f2op16(acc / sum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,7 +534,7 @@ __global__ void va_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
 // Also writes the de-normalised prediction  out = nan_to_num(xyz') * r + centre  (ptEmb_head.py:944-948).
 // one warp per query.
 // ------------------------------------------------------------------------------------------------
-__global__ void reg_out_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ w2,
+__global__ void reg_out_kernel(const op16* __restrict__ h, const float* __restrict__ w2,
                                const float* __restrict__ b2, const float* __restrict__ xyz_in,
                                float* __restrict__ xyz_out, float* __restrict__ coords_out,
                                const float* __restrict__ centre, float radius, int Lq, int D, int n_query) {
@@ -532,7 +543,7 @@ __global__ void reg_out_kernel(const __nv_bfloat16* __restrict__ h, const float*
   if (qi >= n_query) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   for (int c = lane; c < D; c += 32) {
-    const float hv = __bfloat162float(h[(size_t)qi * D + c]);
+    const float hv = op16_to_f(h[(size_t)qi * D + c]);
     a0 += hv * w2[c];
     a1 += hv * w2[D + c];
     a2 += hv * w2[2 * D + c];
@@ -591,19 +602,19 @@ __global__ void gather_centre_kernel(const float* __restrict__ ref_joints, float
   if (i < B * 3) centre[i] = ref_joints[(i / 3) * 63 + centre_idx * 3 + (i % 3)];
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+__global__ void f32_to_op16_kernel(const float* __restrict__ x, op16* __restrict__ y, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = __float2bfloat16(x[i]);
+  if (i < n) y[i] = f2op16(x[i]);
 }
 
-// broadcast the (Q,D) query embedding table to (B*Q, D) fp32 + bf16
+// broadcast the (Q,D) query embedding table to (B*Q, D) fp32 + op16
 __global__ void broadcast_queries_kernel(const float* __restrict__ table, float* __restrict__ out_f32,
-                                         __nv_bfloat16* __restrict__ out_bf16, int QD, size_t total) {
+                                         op16* __restrict__ out_op16, int QD, size_t total) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const float v = table[gid % QD];
   out_f32[gid] = v;
-  out_bf16[gid] = __float2bfloat16(v);
+  out_op16[gid] = f2op16(v);
 }
 
 // Per-image / per-sample index tables from the per-sample view counts (passed by value):

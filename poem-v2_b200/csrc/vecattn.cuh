@@ -51,8 +51,8 @@ struct VaCfg {
   static constexpr int EP = MT * 128 * SETS;         // channel threads
   static constexpr int THREADS = 64 + EP;
   static constexpr int W_STAGES = TWO ? 2 : 5;
-  static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] bf16
-  static constexpr int ACT_BYTES = NT * D * 2;       // KB blocks of [NT tokens x 64 k] bf16
+  static constexpr int W_TILE_BYTES = 128 * 64 * 2;  // [128 channels x 64 k] op16
+  static constexpr int ACT_BYTES = NT * D * 2;       // KB blocks of [NT tokens x 64 k] op16
   static constexpr int TMEM_COLS = (2 * MT * NT <= 256) ? 256 : 512;
   // smem: act0 (h) | act1 (relu gamma1) | weight ring | wd1 (float4 per channel) | token rows | token rel xyz | barriers
   static constexpr int OFF_W = 2 * ACT_BYTES;
@@ -64,9 +64,9 @@ struct VaCfg {
 };
 
 struct VaParams {
-  const __nv_bfloat16* q;      // [n_query, ldq]  qt_i (gamma1-folded query term)
-  const __nv_bfloat16* ktab;   // [B*Lr, ldk]     kt_j (gamma1-folded key term)
-  const __nv_bfloat16* vtab;   // [B*Lr, ldv]
+  const op16* q;      // [n_query, ldq]  qt_i (gamma1-folded query term)
+  const op16* ktab;   // [B*Lr, ldk]     kt_j (gamma1-folded key term)
+  const op16* vtab;   // [B*Lr, ldv]
   int ldq, ldk, ldv;
   const float* q_xyz;          // [n_query, 3]
   const float* ref_xyz;        // [B*Lr, 3] (unused with anchors)
@@ -76,7 +76,7 @@ struct VaParams {
   const float* wd1;            // [D,3]
   const float* bd1;            // [D]
   const float* bd2;            // [D]
-  __nv_bfloat16* res;          // [n_query, D]
+  op16* res;          // [n_query, D]
   int Lq, Lr, n_query;
   float softmax_scale_log2e;   // log2(e) / sqrt(D)
 };
@@ -163,7 +163,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {   // elect.sync: ptxas knows the region is single-threaded (no per-instruction elect loop)
-      constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+      constexpr uint32_t idesc = make_idesc_op16(128, NT);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t act_phase = 0;
@@ -188,7 +188,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
             tc_fence_after_sync();
             const uint64_t da = make_kmajor_desc<128>(smem_u32(s_w) + stage * Cfg::W_TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_op16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             umma_commit(&w_empty[stage]);
             if (++stage == Cfg::W_STAGES) {
               stage = 0;
@@ -218,14 +218,14 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
     const uint32_t act_byte = (uint32_t)(c & 7) * 2;
     uint32_t acc_phase = 0;
 
-    // 32 bf16 values of column c from the gather rows of one query, packed two per register (rows 2i | 2i+1).
+    // 32 op16 values of column c from the gather rows of one query, packed two per register (rows 2i | 2i+1).
     // Lanes 2k / 2k+1 own channels c / c+1 of the same 4-byte word: the even lane fetches that word for the even rows,
     // the odd lane for the odd rows (16 loads of 4 bytes instead of 32 of 2, half the registers in flight), then one
     // shuffle per word swaps them and a byte permute keeps this thread's half of both.
     int* s_rows = s_rows_base;        // gather rows of the current tile (one of three buffers)
     const uint32_t odd = (uint32_t)lane & 1u;
     const uint32_t prmt_sel = odd ? 0x3276u : 0x5410u;   // (own, partner) -> odd: partner.hi | own.hi << 16; even: own.lo | partner.lo << 16
-    auto gather32 = [&](const __nv_bfloat16* tab, int qi, uint32_t(&out)[16]) {
+    auto gather32 = [&](const op16* tab, int qi, uint32_t(&out)[16]) {
       const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tab + (c & ~1));
       // s_rows (element offsets row * ld) holds the even neighbours of a query first, then the odd ones
       const int4* rows4 = reinterpret_cast<const int4*>(s_rows + qi * 32 + odd * 16);
@@ -245,8 +245,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         w[i] = __byte_perm(w[i], other, prmt_sel);
       }
     };
-    auto bf_lo = [](uint32_t x) { return __uint_as_float(x << 16); };
-    auto bf_hi = [](uint32_t x) { return __uint_as_float(x & 0xffff0000u); };
+    auto bf_lo = [](uint32_t x) { return op16_lo(x); };
+    auto bf_hi = [](uint32_t x) { return op16_hi(x); };
 
     // ---- tile metadata: gather row + relative position of every token, written by the first NT channel threads into
     //      one of three buffers (tile index mod 3).
@@ -306,7 +306,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           const float4 w0 = wv[2 * k], w1 = wv[2 * k + 1];
           const float h0 = fmaxf(fmaf(w0.x, rel.x, fmaf(w0.y, rel.y, fmaf(w0.z, rel.z, w0.w))), 0.f);
           const float h1 = fmaxf(fmaf(w1.x, rel.x, fmaf(w1.y, rel.y, fmaf(w1.z, rel.z, w1.w))), 0.f);
-          pk[k] = pack_bf16x2(h0, h1);
+          pk[k] = pack_op16x2(h0, h1);
         }
         *reinterpret_cast<uint4*>(blk + sw128_offset(t, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -344,7 +344,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int qg = q_first + qi0 + u;
-          qv[u] = (qg < p.n_query) ? __bfloat162float(p.q[(size_t)qg * p.ldq + c]) : 0.f;
+          qv[u] = (qg < p.n_query) ? op16_to_f(p.q[(size_t)qg * p.ldq + c]) : 0.f;
           act1_q[u] = smem_u32(s_act1) + act_blk + (act_chunk << 4) + act_byte + (uint32_t)(qi0 + u) * (32 * 128);
         }
         // metadata of the next tile (its xyz loads queue up behind the kt gathers, all of it under the gamma1 GEMMs),
@@ -440,7 +440,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
               acc = fmaf(e1, bf_hi(vp) + (__uint_as_float(ps[2 * j + 1]) + bd2), acc);
             }
           }
-          if (qg < p.n_query) p.res[(size_t)qg * D + c] = __float2bfloat16(acc / sum);
+          if (qg < p.n_query) p.res[(size_t)qg * D + c] = f2op16(acc / sum);
         }
       }
       tc_fence_before_sync();

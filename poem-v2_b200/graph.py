@@ -28,6 +28,28 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.outputs = fn(**self._static)
+        # The captured kernels hold raw pointers into the modules' workspaces and packed weights, which were allocated
+        # outside the graph pool during warm-up: keep them alive with the graph, and refuse to replay once the module
+        # has re-packed its weights (parameter update, set_template / set_mano) or grown its workspace.
+        self._pins = []
+        owner = getattr(fn, "__self__", None) or getattr(fn, "owner", None)
+        for m in self._modules_of(owner):
+            self._pins.append((m, {k: getattr(m, k, None) for k in self._PIN_ATTRS}))
+
+    _PIN_ATTRS = ("_ws", "_stage", "_packed", "_packed_mano", "_packed_hr", "_pack")
+
+    @staticmethod
+    def _modules_of(owner):
+        if owner is None or not hasattr(owner, "modules"):
+            return []
+        return [m for m in owner.modules() if any(hasattr(m, a) for a in GraphedForward._PIN_ATTRS)]
+
+    def _check_pins(self):
+        for m, held in self._pins:
+            for k, v in held.items():
+                if v is not None and getattr(m, k, None) is not v:
+                    raise RuntimeError(f"{type(m).__name__}.{k} changed after graph capture (weights re-packed or "
+                                       "workspace re-allocated): re-capture the graph")
 
     @staticmethod
     def _clone(d):
@@ -56,27 +78,32 @@ class GraphedForward:
                     raise ValueError(f"{path}{k} differs from the captured call: re-capture for new view counts / shapes")
 
     def __call__(self, **inputs):
+        self._check_pins()
         self._load(self._static, inputs)
         self.graph.replay()
         return self.outputs
 
     def replay(self):
         """Replay on the inputs already held by the captured buffers."""
+        self._check_pins()
         self.graph.replay()
         return self.outputs
 
 
 def graph_model(model, batch, mode="test"):
     """`PtEmbedMultiviewStereoV2` forward as a graph: `g = graph_model(model, batch); preds = g(batch)`."""
-    g = GraphedForward(lambda inputs: model(inputs, mode=mode), {"inputs": batch})
+    fn = lambda inputs: model(inputs, mode=mode)  # noqa: E731
+    fn.owner = model
+    g = GraphedForward(fn, {"inputs": batch})
     return lambda b: g(inputs=b)
 
 
 def graph_head(head, mlvl_feat, img_metas, reference_joints):
     """`POEM_Generalized_Head.forward` as a graph (same keyword call as the reference's, POEM.py:317-320)."""
     metas = {k: v for k, v in img_metas.items() if k != "inp_res"}
-    g = GraphedForward(lambda **kw: head(**kw), {"mlvl_feat": mlvl_feat, "img_metas": metas,
-                                                   "reference_joints": reference_joints})
+    fn = lambda **kw: head(**kw)  # noqa: E731
+    fn.owner = head
+    g = GraphedForward(fn, {"mlvl_feat": mlvl_feat, "img_metas": metas, "reference_joints": reference_joints})
     g._static["img_metas"].pop("inp_res", None)   # added by the head itself (reference ptEmb_head.py:833), not an input
 
     def call(mlvl_feat, img_metas, reference_joints, **_):

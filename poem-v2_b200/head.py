@@ -97,6 +97,8 @@ class _NativeDecoder(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = None
+        self.debug_export_neighbours = False    # test hook (poem_debug_export_neighbours): fills `last_neighbours`
+        self.last_neighbours = None
 
     def add_param(self, dotted, tensor):
         head, _, rest = dotted.partition(".")
@@ -222,18 +224,27 @@ class POEM_Generalized_Head(_NativeDecoder):
         inp = nat.PoemInputs(B, NV, views.ctypes.data, feat.data_ptr(), intr.data_ptr(), extr.data_ptr(),
                              refj.data_ptr(), float(inp_w), float(inp_h))
         stream = torch.cuda.current_stream(dev).cuda_stream
-        if not d.parametric:
-            nat.check(lib.poem_head_forward(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), None, ws_ptr,
-                                            ws_bytes, stream))
-            return {"all_coords_preds": out}
-        # medium_MANO: the last block's joints / vertices come from the MANO tail (ptEmb_head.py:950-963)
-        pm = self.packed_mano(dev)
-        pose = torch.empty(B, 16, 3, dtype=torch.float32, device=dev)
-        shape = torch.empty(B, 10, dtype=torch.float32, device=dev)
-        nat.check(lib.poem_head_forward_parametric(C.byref(cd), C.byref(pw.struct), C.byref(pm.struct), C.byref(inp),
-                                                   out.data_ptr(), pose.data_ptr(), shape.data_ptr(), ws_ptr, ws_bytes,
-                                                   stream))
-        return {"all_coords_preds": out, "pred_pose": pose, "pred_shape": shape}
+        nbr = None
+        if self.debug_export_neighbours and d.n_blocks > 1:      # test hook: the 32-NN sets the kernels used
+            nbr = torch.zeros(d.n_blocks - 1, 2, B, d.n_query, 32, dtype=torch.int32, device=dev)
+            lib.poem_debug_export_neighbours(nbr.data_ptr(), nbr.numel())
+        try:
+            if not d.parametric:
+                nat.check(lib.poem_head_forward(C.byref(cd), C.byref(pw.struct), C.byref(inp), out.data_ptr(), None,
+                                                ws_ptr, ws_bytes, stream))
+                return {"all_coords_preds": out}
+            # medium_MANO: the last block's joints / vertices come from the MANO tail (ptEmb_head.py:950-963)
+            pm = self.packed_mano(dev)
+            pose = torch.empty(B, 16, 3, dtype=torch.float32, device=dev)
+            shape = torch.empty(B, 10, dtype=torch.float32, device=dev)
+            nat.check(lib.poem_head_forward_parametric(C.byref(cd), C.byref(pw.struct), C.byref(pm.struct),
+                                                       C.byref(inp), out.data_ptr(), pose.data_ptr(), shape.data_ptr(),
+                                                       ws_ptr, ws_bytes, stream))
+            return {"all_coords_preds": out, "pred_pose": pose, "pred_shape": shape}
+        finally:
+            if nbr is not None:
+                lib.poem_debug_export_neighbours(None, 0)
+                self.last_neighbours = nbr
 
     @torch.no_grad()
     def forward_host(self, mlvl_feat, img_metas, reference_joints, out=None):
@@ -249,6 +260,8 @@ class POEM_Generalized_Head(_NativeDecoder):
         # staging is private to the host entry point (its copy stream writes it while earlier calls still compute)
         st_need = lib.poem_staging_bytes(C.byref(cd), B, NV)
         if getattr(self, "_stage", None) is None or self._stage.numel() < st_need + 1024 or self._stage.device != torch.device(dev):
+            if getattr(self, "_stage", None) is not None:
+                torch.cuda.synchronize(dev)    # the library's copy stream may still be writing the old buffer
             self._stage = torch.empty(st_need + 1024, dtype=torch.uint8, device=dev)
         st_off = (-self._stage.data_ptr()) % 1024
         if out is None:

@@ -9,7 +9,7 @@ are accepted and dropped).
 `HRNetStage4` keeps the reference's parameter names (`{m}.branches.{b}.{k}.conv1.weight`, `...bn1.running_mean`,
 `{m}.fuse_layers.{i}.{j}...` — the `stage4.` prefix of `HighResolutionNet`) so a backbone checkpoint loads unchanged;
 `forward(x_list)` has the signature of `self.stage4(x_list)` (`hrnet.py:417`).  BatchNorm runs in eval mode (the
-release configs freeze it: `FREEZE_BATCHNORM: true`) and is folded into the bf16 implicit-GEMM weights at pack time.
+release configs freeze it: `FREEZE_BATCHNORM: true`) and is folded into the fp16 implicit-GEMM weights at pack time.
 """
 import ctypes as C
 
@@ -111,7 +111,7 @@ class HRNetStage4(nn.Module):
         keep = []
 
         def lin(w, b):
-            wt = w.to(torch.bfloat16).contiguous().to(device)
+            wt = nat.to_op16(w).contiguous().to(device)
             bt = b.to(torch.float32).contiguous().to(device)
             keep.extend([wt, bt])
             return nat.PoemLinear(wt.data_ptr(), bt.data_ptr())
@@ -255,7 +255,7 @@ class HRNetW40(nn.Module):
         keep = []
 
         def lin(w, b):
-            wt = w.to(torch.bfloat16).contiguous().to(device)
+            wt = nat.to_op16(w).contiguous().to(device)
             bt = b.to(torch.float32).contiguous().to(device)
             keep.extend([wt, bt])
             return nat.PoemLinear(wt.data_ptr(), bt.data_ptr())
@@ -434,7 +434,7 @@ class ImageStage(nn.Module):
         keep = []
 
         def lin(w, b):
-            wt = w.to(torch.bfloat16).contiguous().to(device)
+            wt = nat.to_op16(w).contiguous().to(device)
             bt = b.to(torch.float32).contiguous().to(device)
             keep.extend([wt, bt])
             return nat.PoemLinear(wt.data_ptr(), bt.data_ptr())

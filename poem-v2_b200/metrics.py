@@ -34,6 +34,7 @@ class _DeviceMeter:
         self._sum, self.count = None, 0
 
     def update(self, total, n):
+        total = total.double()     # the reference's AverageMeter accumulates Python floats (float64)
         self._sum = total if self._sum is None else self._sum + total
         self.count += n
 

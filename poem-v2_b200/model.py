@@ -30,7 +30,12 @@ class PtEmbedMultiviewStereoV2(nn.Module):
         self.ptEmb_head = POEM_Generalized_Head(head_cfg, template_mesh=template_mesh, mano_params=mano_params)
         self.image_stage = ImageStage()
         self.num_joints = 21
-        self.center_idx = self.ptEmb_head.dims.center_idx
+        # POEM.py:40,328: the root joint of the *_rel outputs is DATA_PRESET.CENTER_IDX (0 in every release config) —
+        # NOT the transformer's TRANSFORMER_CENTER_IDX (9), which only centres the BPS / MANO layer (POEM.py:409)
+        preset = None if isinstance(cfg, HeadDims) else getattr(cfg, "DATA_PRESET", None)
+        if preset is None and kwargs.get("data_preset") is not None:
+            preset = kwargs["data_preset"]
+        self.center_idx = int(getattr(preset, "CENTER_IDX", 0)) if preset is not None else 0
         self.num_preds = self.ptEmb_head.num_preds
 
     # ---- checkpoint interface: the reference's flat key space (net_utils.py:200-231) ----

@@ -1,8 +1,8 @@
 """Weight packing: reference state dict -> kernel layout (`PoemWeights` of include/poem_b200.h).
 
 Host-side, one-off (re-run only when parameters change):
-  * matrices -> bf16 [out, in] row-major, biases / LayerNorm / tiny matrices -> fp32
-  * algebraic folds done in fp64 before rounding to bf16:
+  * matrices -> op16 (fp16) [out, in] row-major, biases / LayerNorm / tiny matrices -> fp32
+  * algebraic folds done in fp64 before rounding to fp16:
       - BPS-token projections: `embedding` composed into K/V of both BERT attentions and (through
         query_cross_attn.fc1) into k'/v' of the vector cross-attention, so the 4096 tokens are projected once
         per point instead of once per (query, neighbour) pair  (reference point_transformers.py:136-141,
@@ -108,11 +108,13 @@ class PackedWeights:
     def _i32(self, t):
         return self._dev(t, torch.int32)
 
-    def _bf16(self, t):
-        return self._dev(t, torch.bfloat16)
+    def _op16(self, t):
+        t = nat.to_op16(t).contiguous().to(self.device)
+        self._keep.append(t)
+        return t.data_ptr()
 
     def _linear(self, w, b=None):
-        return nat.PoemLinear(self._bf16(w), None if b is None else self._f32(b))
+        return nat.PoemLinear(self._op16(w), None if b is None else self._f32(b))
 
     @staticmethod
     def _pos_table(f64, dims, max_views):

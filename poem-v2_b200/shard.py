@@ -33,8 +33,12 @@ def shard_bounds(view_counts, world_size):
             # choose the closer of end-1 / end to the target
             if end > start and abs(cum[end - 1] - target) <= abs(cum[end] - target):
                 end -= 1
-            end = max(end, min(start + 1, B - (world_size - 1 - r)))  # leave at least one sample per later rank
-            end = min(end, B)
+            if B >= world_size:
+                # never empty when there are enough samples: at least one for this rank, and at least one left for
+                # every later rank (a rank with an empty slice would skip the head while the others wait in all_gather)
+                end = min(max(end, start + 1), B - (world_size - 1 - r))
+            else:
+                end = min(max(end, start), B)
         bounds.append((start, end))
         start = end
     return bounds

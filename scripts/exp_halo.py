@@ -13,10 +13,10 @@ lib = nat.load()
 
 def run(N, R, c, cp, relu, res, mode, timing=False):
     g = torch.Generator().manual_seed(R + c)
-    x = torch.randn(N, c, R, R, generator=g).bfloat16().float()
-    w = (torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).bfloat16().float()
+    x = torch.randn(N, c, R, R, generator=g).half().float()
+    w = (torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).half().float()
     b = 0.1 * torch.randn(c, generator=g)
-    r = torch.randn(N, c, R, R, generator=g).bfloat16().float() if res else None
+    r = torch.randn(N, c, R, R, generator=g).half().float() if res else None
     xp = torch.zeros(N, R, R, cp)
     xp[..., :c] = x.permute(0, 2, 3, 1)
     wp = torch.zeros(cp, 3, 3, cp)
@@ -27,10 +27,10 @@ def run(N, R, c, cp, relu, res, mode, timing=False):
     if res:
         rp = torch.zeros(N, R, R, cp)
         rp[..., :c] = r.permute(0, 2, 3, 1)
-    xd, wd = xp.bfloat16().cuda(), wp.reshape(cp, -1).bfloat16().contiguous().cuda()
-    rd = rp.bfloat16().cuda() if res else None
+    xd, wd = xp.half().cuda(), wp.reshape(cp, -1).half().contiguous().cuda()
+    rd = rp.half().cuda() if res else None
     bd = bp.cuda()
-    out = torch.full((N, R, R, cp), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((N, R, R, cp), float("nan"), device="cuda", dtype=torch.float16)
     lib.poem_debug_conv_mode(mode)
     st = torch.cuda.current_stream().cuda_stream
 

@@ -6,9 +6,9 @@ from poem_v2_b200 import _native as nat
 lib = nat.load()
 B, D, h, Lk, Lq = 32, 256, 4, 4096, 799
 g = torch.Generator(device="cuda").manual_seed(0)
-K = torch.randn(B * Lk, 6 * D, device="cuda", generator=g).bfloat16()      # strided like the KK table of the decoder
-Q = torch.randn(B * Lq, D, device="cuda", generator=g).bfloat16()
-ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+K = torch.randn(B * Lk, 6 * D, device="cuda", generator=g).half()      # strided like the KK table of the decoder
+Q = torch.randn(B * Lq, D, device="cuda", generator=g).half()
+ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.float16)
 st = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def run():

@@ -9,12 +9,12 @@ from poem_v2_b200 import _native as nat
 lib = nat.load()
 B, D, h, Lk = 32, 256, 4, 4096
 g = torch.Generator(device="cuda").manual_seed(0)
-K = torch.randn(B * Lk, D, device="cuda", generator=g).bfloat16()
-V = torch.randn(B * Lk, D, device="cuda", generator=g).bfloat16()
+K = torch.randn(B * Lk, D, device="cuda", generator=g).half()
+V = torch.randn(B * Lk, D, device="cuda", generator=g).half()
 st = torch.cuda.current_stream().cuda_stream
 for Lq in (512, 640, 768, 799, 896, 1024):
-    Q = torch.randn(B * Lq, D, device="cuda", generator=g).bfloat16()
-    ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+    Q = torch.randn(B * Lq, D, device="cuda", generator=g).half()
+    ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.float16)
     def run():
         nat.check(lib.poem_mha(Q.data_ptr(), D, K.data_ptr(), D, V.data_ptr(), D, ctx.data_ptr(), D, B, Lq, Lk, D, h, st))
     for _ in range(3):

@@ -10,8 +10,8 @@ for k in ${NCU_KERNELS:-va_fused mha}; do
   case $k in
     va_fused) cap va_fused va_fused 8;;
     mha) cap mha mha_fwd 6;;
-    merge0a) cap gemm_merge0a gemm_bf16 1;;
-    ptproj) cap gemm_ptproj gemm_bf16 5;;
+    merge0a) cap gemm_merge0a gemm_op16 1;;
+    ptproj) cap gemm_ptproj gemm_op16 5;;
     knn) cap knn knn32 5;;
     sample) cap sample project_sample 2;;
   esac

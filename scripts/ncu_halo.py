@@ -13,13 +13,13 @@ N = 256
 st = torch.cuda.current_stream().cuda_stream
 for (R, c, cp) in [(64, 40, 64), (32, 80, 128), (16, 160, 192)]:
     g = torch.Generator().manual_seed(R)
-    x = torch.randn(N, R, R, cp, generator=g).bfloat16().cuda()
+    x = torch.randn(N, R, R, cp, generator=g).half().cuda()
     x[..., c:] = 0
-    r = torch.randn(N, R, R, cp, generator=g).bfloat16().cuda()
+    r = torch.randn(N, R, R, cp, generator=g).half().cuda()
     r[..., c:] = 0
     w = torch.zeros(cp, 3, 3, cp)
     w[:c, :, :, :c] = torch.randn(c, 3, 3, c, generator=g) / (9 * c) ** 0.5
-    w = w.reshape(cp, -1).bfloat16().cuda()
+    w = w.reshape(cp, -1).half().cuda()
     b = torch.zeros(cp, device="cuda")
     out = torch.empty_like(x)
 

@@ -288,6 +288,14 @@ def test_shard_bounds_cover_and_balance():
         assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
         assert all(e >= s for s, e in b)
     assert shard.shard_bounds([8] * 32, 8) == [(4 * r, 4 * r + 4) for r in range(8)]
+    # skewed view counts: no rank may be left without a sample when B >= world — it would skip the head
+    # while the others wait in all_gather
+    for views, world in (([1, 1, 1, 10], 4), ([10, 1, 1, 1], 4), ([1, 10, 1, 1, 5, 5, 2], 3), ([1] * 7 + [10], 8),
+                         ([10] + [1] * 9, 8)):
+        b = shard.shard_bounds(views, world)
+        assert b[0][0] == 0 and b[-1][1] == len(views) and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(e > s_ for s_, e in b), (views, world, b)
+    assert [e - s_ for s_, e in shard.shard_bounds([3, 1], 4)].count(1) == 2          # B < world: two ranks idle
     assert shard.image_bounds(8, 8) == [(r, r + 1) for r in range(8)]
     assert shard.image_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)] and shard.image_bounds(2, 4)[2:] == [(2, 2), (2, 2)]
 

@@ -39,11 +39,11 @@ def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res, live):
     lib = nat.load()
     g = torch.Generator().manual_seed(R * 7 + cin + cout + k)
     cin_p, cout_p = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
-    x = torch.randn(N, cin, R, R, generator=g).bfloat16().float()
-    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    x = torch.randn(N, cin, R, R, generator=g).half().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).half().float()
     b = 0.1 * torch.randn(cout, generator=g)
     Ro = R // stride
-    r = torch.randn(N, cout, Ro, Ro, generator=g).bfloat16().float() if res else None
+    r = torch.randn(N, cout, Ro, Ro, generator=g).half().float() if res else None
     xp = torch.zeros(N, R, R, cin_p)
     xp[..., :cin] = x.permute(0, 2, 3, 1)
     wp = torch.zeros(cout_p, k, k, cin_p)
@@ -54,9 +54,9 @@ def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res, live):
     if res:
         rp = torch.zeros(N, Ro, Ro, cout_p)
         rp[..., :cout] = r.permute(0, 2, 3, 1)
-    d = [t.bfloat16().contiguous().cuda() if t is not None else None for t in (xp, wp.reshape(cout_p, -1), rp)]
+    d = [t.half().contiguous().cuda() if t is not None else None for t in (xp, wp.reshape(cout_p, -1), rp)]
     bd = bp.cuda()
-    out = torch.full((N, Ro, Ro, cout_p), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = torch.full((N, Ro, Ro, cout_p), float("nan"), device="cuda", dtype=torch.float16)
     # live=True promises that channels >= cin / cout are zero padding: the 3x3 stride-1 kernel then multiplies only
     # the live channels (mixed 128/64/32-byte swizzle K blocks) and writes the padding as zeros
     nat.check(lib.poem_conv_nhwc(_p(d[0]), N, R, R, cin_p, _p(d[1]), _p(bd), cout_p, k, stride, int(relu), _p(d[2]),

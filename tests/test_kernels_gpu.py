@@ -50,12 +50,12 @@ def _ws(nbytes):
 ])
 def test_linear(lib, M, N, K, act, res):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
-    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
     bias = torch.randn(N, device="cuda", generator=g)
     R = torch.randn(M, N, device="cuda", generator=g) if res else None
     o32 = torch.full((M, N), float("nan"), device="cuda")
-    o16 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    o16 = torch.zeros(M, N, device="cuda", dtype=torch.float16)
     nat.check(lib.poem_linear(_p(A), K, _p(W), K, _p(bias), M, N, K, act, _p(R), N, _p(o32), N, _p(o16), N, _stream()))
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t() + bias
@@ -68,7 +68,7 @@ def test_linear(lib, M, N, K, act, res):
 
 
 def test_linear_rejects_bad_arguments(lib):
-    A = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    A = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
     assert lib.poem_linear(_p(A), 64, _p(A), 64, None, 128, 100, 64, 0, None, 0, None, 0, _p(A), 100, _stream()) == -1
     assert lib.poem_linear(None, 64, _p(A), 64, None, 128, 128, 64, 0, None, 0, None, 0, _p(A), 128, _stream()) == -2
     assert b"null" in lib.poem_last_error()
@@ -83,10 +83,10 @@ def test_mha(lib, D, B, Lq, Lk):
     h = 4
     hd = D // h
     g = torch.Generator(device="cuda").manual_seed(D + Lk)
-    Q = torch.randn(B * Lq, D, device="cuda", generator=g).bfloat16()
-    K = torch.randn(B * Lk, D, device="cuda", generator=g).bfloat16()
-    V = torch.randn(B, Lk, D, device="cuda", generator=g).bfloat16()
-    ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+    Q = torch.randn(B * Lq, D, device="cuda", generator=g).half()
+    K = torch.randn(B * Lk, D, device="cuda", generator=g).half()
+    V = torch.randn(B, Lk, D, device="cuda", generator=g).half()
+    ctx = torch.zeros(B * Lq, D, device="cuda", dtype=torch.float16)
     nat.check(lib.poem_mha(_p(Q), D, _p(K), D, _p(V), D, _p(ctx), D, B, Lq, Lk, D, h, _stream()))
     torch.cuda.synchronize()
     q = Q.float().view(B, Lq, h, hd).transpose(1, 2)
@@ -158,7 +158,7 @@ def test_project_sample(lib, D, views):
     xmap = torch.randn(NV, D, 16, 16, generator=g)
     bps, _, _ = synth.load_assets()
     centre = refj[:, 9].contiguous()
-    X = torch.zeros(NV * P, D, device="cuda", dtype=torch.bfloat16)
+    X = torch.zeros(NV * P, D, device="cuda", dtype=torch.float16)
     wst, wsp, wsb = _ws(1 << 20)
     import numpy as np
     vc = np.asarray(views, dtype=np.int32)
@@ -205,9 +205,9 @@ def test_vector_attention(lib, D, B, Lq, Lr, anchors, unfused):
 def _check_vector_attention(lib, D, B, Lq, Lr, anchors):
     g = torch.Generator().manual_seed(D + Lr)
     sd = _vecattn_weights(D, g)
-    q = torch.randn(B * Lq, D, generator=g).bfloat16()
-    ktab = torch.randn(B * Lr, D, generator=g).bfloat16()
-    vtab = torch.randn(B * Lr, D, generator=g).bfloat16()
+    q = torch.randn(B * Lq, D, generator=g).half()
+    ktab = torch.randn(B * Lr, D, generator=g).half()
+    vtab = torch.randn(B * Lr, D, generator=g).half()
     q_xyz = torch.randn(B, Lq, 3, generator=g) * 0.5
     r_xyz = torch.randn(B, Lr, 3, generator=g) * 0.5
     _, a_xyz, a_idx = synth.load_assets()
@@ -227,14 +227,14 @@ def _check_vector_attention(lib, D, B, Lq, Lr, anchors):
     # the composed matrix W_g1 W_d2; built here in fp64 exactly like pack.py does
     Wg1, Wd2 = sd["fc_gamma.0.weight"].double(), sd["fc_delta.2.weight"].double()
     q_raw, k_raw = q, ktab                                  # bf16 un-folded inputs of the fp32 reference
-    q = (q_raw.double() @ Wg1.t() + Wg1 @ sd["fc_delta.2.bias"].double() + sd["fc_gamma.0.bias"].double()).bfloat16()
-    ktab = (k_raw.double() @ Wg1.t()).bfloat16()
+    q = (q_raw.double() @ Wg1.t() + Wg1 @ sd["fc_delta.2.bias"].double() + sd["fc_gamma.0.bias"].double()).half()
+    ktab = (k_raw.double() @ Wg1.t()).half()
     w = nat.PoemVecAttn(dev(sd["fc_delta.0.weight"], torch.float32), dev(sd["fc_delta.0.bias"], torch.float32),
-                        nat.PoemLinear(dev(sd["fc_delta.2.weight"], torch.bfloat16), dev(sd["fc_delta.2.bias"], torch.float32)),
-                        nat.PoemLinear(dev(Wg1 @ Wd2, torch.bfloat16), None),
-                        nat.PoemLinear(dev(sd["fc_gamma.2.weight"], torch.bfloat16), dev(sd["fc_gamma.2.bias"], torch.float32)),
+                        nat.PoemLinear(dev(sd["fc_delta.2.weight"], torch.float16), dev(sd["fc_delta.2.bias"], torch.float32)),
+                        nat.PoemLinear(dev(Wg1 @ Wd2, torch.float16), None),
+                        nat.PoemLinear(dev(sd["fc_gamma.2.weight"], torch.float16), dev(sd["fc_gamma.2.bias"], torch.float32)),
                         nat.PoemLinear(None, None))
-    res = torch.zeros(B * Lq, D, device="cuda", dtype=torch.bfloat16)
+    res = torch.zeros(B * Lq, D, device="cuda", dtype=torch.float16)
     nb = lib.poem_vector_attention_workspace_bytes(B, Lq, D)
     wst, wsp, wsb = _ws(nb)
     idx32 = idx.to(torch.int32).contiguous().cuda()
@@ -246,7 +246,7 @@ def _check_vector_attention(lib, D, B, Lq, Lr, anchors):
                                         _stream()))
     torch.cuda.synchronize()
     # fp32 reference on the bf16-rounded tables / weights
-    sdr = {k: (v.bfloat16().float() if k.endswith("weight") and v.shape[1] != 3 else v) for k, v in sd.items()}
+    sdr = {k: (v.half().float() if k.endswith("weight") and v.shape[1] != 3 else v) for k, v in sd.items()}
     k_g = orc.gather_rows(k_raw.float().view(B, Lr, D), idx)
     v_g = orc.gather_rows(vtab.float().view(B, Lr, D), idx)
     ref = orc._vector_attention_core(sdr, "", q_raw.float().view(B, Lq, D), k_g, v_g, q_xyz[:, :, None] - nbr)
@@ -264,7 +264,7 @@ def test_layernorm(lib, rows, D):
     gamma = torch.randn(D, device="cuda", generator=g)
     beta = torch.randn(D, device="cuda", generator=g)
     y = torch.empty_like(x)
-    y16 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    y16 = torch.empty(rows, D, device="cuda", dtype=torch.float16)
     nat.check(lib.poem_layernorm(_p(x), _p(gamma), _p(beta), _p(y), _p(y16), rows, D, _stream()))
     torch.cuda.synchronize()
     ref = torch.nn.functional.layer_norm(x, (D,), gamma, beta, eps=1e-12)

@@ -5,8 +5,18 @@
   * size-independent properties at the benchmark size (medium, 8 views, batch 32)
 
 Tolerances (north star): vertex coordinates within 1e-3 relative (fp32, metres), MPJPE against the reference
-within 0.1 mm.  The path computes its GEMMs in bf16 with fp32 accumulation; 32-NN selection is discontinuous, so a
-small fraction of queries whose 32nd/33rd neighbours are nearly equidistant may pick the other one — bounded below.
+within 0.1 mm.  The path computes its GEMMs with fp16 operands (11-bit significand, as TF32) and fp32 accumulation.
+
+32-NN selection (blocks 1..NB-1) is DISCONTINUOUS in the regressed coordinates: the goldens contain queries whose
+32nd / 33rd neighbours are equidistant to ~1e-6, and any implementation that is not bit-identical to the reference
+(including the reference itself on another device) picks the other one there.  The comparison is therefore split into
+the two statements that can be exact:
+  (A) coordinates: against the oracle run on the neighbour sets the kernels actually used (`neighbours=` hook of the
+      oracle, `poem_debug_export_neighbours` of the library): EVERY point within 1e-3 relative, no allowance;
+  (B) neighbour sets: each exported set is a valid 32-NN set of the coordinates it was computed from (bit-exactness of
+      the search itself on identical coordinates is tests/test_kernels_gpu.py::test_knn32_bit_exact);
+and against the un-forced oracle / reference golden every query whose sets agree with the reference's is held to the
+same 1e-3, while the queries whose set differs somewhere (reported) are bounded separately.
 """
 import numpy as np
 import pytest
@@ -21,6 +31,9 @@ from poem_v2_b200.config import release_dims  # noqa: E402
 from poem_v2_b200.head import POEM_Generalized_Head, PtEmbedTRv4  # noqa: E402
 
 MM = 1e-3  # metres
+REL_TOL = 1e-3          # north star: relative error of a regressed point, ||ours - ref|| / ||ref||
+FLIP_REL_TOL = 5e-3     # queries whose 32-NN set differs from the reference's (discontinuity), measured <= 1.7e-3
+FLIP_FRAC_MAX = 0.25    # cumulative over the four searches of blocks 1-2; measured 4-10 % with the stress weights
 
 
 def build_head(dims, sd):
@@ -36,60 +49,112 @@ def to_cuda(metas):
     return m
 
 
-def check_coords(ours, ref, label, mean_mm):
-    """ours/ref: (NB,B,799,3) metres.
+def run_with_neighbours(head, feat, metas, ref_j):
+    """-> (coords (NB,B,799,3) cpu, neighbour sets (NB-1, 2, B, 799, 32) int64 cpu) of one device run."""
+    head.debug_export_neighbours = True
+    try:
+        out = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda(), debug_metas=None)
+    finally:
+        head.debug_export_neighbours = False
+    got = out["all_coords_preds"]
+    assert got.dtype == torch.float32 and got.is_cuda
+    torch.cuda.synchronize()
+    return got.cpu(), head.last_neighbours.long().cpu(), out
 
-    Tolerances (north star: 1e-3 relative on fp32 vertex coordinates, MPJPE within 0.1 mm of the reference):
-      * per point ||ours - ref|| <= 1e-3 * ||ref|| (~0.6 mm at 0.6 m) for >= 95 % of the points (measured: 96.1 % for
-        POEM-large, >= 99.3 % for small/medium with stress weights, 100 % with reference-style initialisation); the
-        worst point (a query whose 32-NN set or near-one-hot softmax flipped) <= 1e-2 * ||ref||
-      * mean point error <= `mean_mm` (bf16 operands, fp32 accumulation; measured 0.05 mm with reference-style
-        initialisation, 0.10-0.28 mm with the O(1)-everywhere "stress" weights whose per-block updates are ~8 mm)
-      * MPJPE against a ground truth 5 mm away from the reference changes by <= 0.1 mm (what `MeanEPE` reports)
-    """
-    err = (ours - ref).norm(dim=-1)                    # per point, metres
-    rel = err / ref.norm(dim=-1)
-    mean_err = err.mean(dim=-1)                        # (NB,B)
+
+def d_mpjpe(ours, ref):
     g = torch.Generator().manual_seed(123)
     gt = ref + 5e-3 * torch.randn(ref.shape, generator=g) / 3 ** 0.5
     mpjpe_ours = (ours - gt).norm(dim=-1)[..., :21].mean(dim=-1)
     mpjpe_ref = (ref - gt).norm(dim=-1)[..., :21].mean(dim=-1)
-    d_mpjpe = (mpjpe_ours - mpjpe_ref).abs().max().item()
+    return (mpjpe_ours - mpjpe_ref).abs().max().item()
+
+
+def check_coords(ours, ref, label, mean_mm, flipped=None):
+    """ours/ref: (NB,B,799,3) metres.  Every point within REL_TOL of the reference (||ours - ref|| <= 1e-3 ||ref||, i.e.
+    ~0.6 mm at 0.6 m), no allowance.  `flipped` (NB,B,799) bool marks the queries whose 32-NN set differs from the
+    reference's in this or an earlier block: those are held to FLIP_REL_TOL instead and their fraction is bounded.
+    Also: mean point error <= `mean_mm`; MPJPE against a ground truth 5 mm away changes by <= 0.1 mm (`MeanEPE`)."""
+    err = (ours - ref).norm(dim=-1)                    # per point, metres
+    rel = err / ref.norm(dim=-1)
+    mean_err = err.mean(dim=-1)                        # (NB,B)
+    dm = d_mpjpe(ours, ref)
+    if flipped is None:
+        flipped = torch.zeros_like(rel, dtype=torch.bool)
+    keep = ~flipped
+    rel_same = rel[keep].max().item()
+    rel_flip = rel[flipped].max().item() if flipped.any() else 0.0
     print(f"{label}: mean |ours-ref| per block {[round(v, 4) for v in (mean_err.max(dim=1).values / MM).tolist()]} mm, "
-          f"worst point {err.max().item() / MM:.3f} mm, frac(rel>1e-3) {(rel > 1e-3).float().mean().item():.4f}, "
-          f"rel max {rel.max().item():.2e}, |dMPJPE vs GT| {d_mpjpe / MM:.4f} mm")
-    assert d_mpjpe <= 0.1 * MM
-    assert (rel > 1e-3).float().mean().item() <= 0.05
-    assert rel.max().item() <= 1e-2   # worst observed: 5.2e-3 (2.4 mm, POEM-large, one query whose 32-NN set flips)
+          f"worst point {err[keep].max().item() / MM:.3f} mm, rel max {rel_same:.2e}"
+          + (f" | queries with a different 32-NN set: {flipped[-1].float().mean().item():.4f}, their rel max {rel_flip:.2e}"
+             if flipped.any() else "") + f", |dMPJPE vs GT| {dm / MM:.4f} mm")
+    assert dm <= 0.1 * MM
+    assert rel_same <= REL_TOL
+    assert rel_flip <= FLIP_REL_TOL and flipped[-1].float().mean().item() <= FLIP_FRAC_MAX
     assert mean_err.max().item() <= mean_mm * MM
+
+
+def flipped_mask(nbr, stages, dims):
+    """(NB,B,799) bool: query's 32-NN set (self or cross) differs from the oracle's in block <= i."""
+    B = nbr.shape[2]
+    m = torch.zeros(dims.n_blocks, B, dims.n_query, dtype=torch.bool)
+    for i in range(1, dims.n_blocks):
+        for k, key in enumerate(("idx_self", "idx_cross")):
+            ref_sets = stages[f"b{i}.{key}"].sort(dim=-1).values
+            m[i] |= (nbr[i - 1, k].sort(dim=-1).values != ref_sets).any(dim=-1)
+        m[i] |= m[i - 1]
+    return m
+
+
+def check_neighbour_sets(nbr, got, ref_j, dims, pt_xyz):
+    """(B): every exported set holds the 32 nearest points of the coordinates the search saw — block i searches
+    around the coordinates block i-1 regressed (recovered from the metric output, hence the 1e-5 slack on d^2)."""
+    centre = ref_j[:, dims.center_idx][:, None]
+    for i in range(1, dims.n_blocks):
+        xyz = (got[i - 1] - centre) / dims.radius                      # (B,799,3) normalised
+        for k, ref in enumerate((xyz, pt_xyz)):
+            d = ((xyz[:, :, None, :] - ref[:, None, :, :]) ** 2).sum(-1)         # (B,799,Lr)
+            idx = nbr[i - 1, k]
+            assert idx.min() >= 0 and idx.max() < ref.shape[1]
+            assert (idx.sort(dim=-1).values.diff(dim=-1) > 0).all(), "duplicate neighbour"
+            sel = torch.gather(d, 2, idx)
+            assert (sel.diff(dim=-1) >= -1e-5).all(), "neighbours not in ascending distance order"
+            rest = d.scatter(2, idx, float("inf"))
+            assert (sel.max(dim=-1).values <= rest.min(dim=-1).values + 1e-5).all(), "not the 32 nearest"
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_head_matches_oracle_and_golden(name):
     meta, dims, sd, feat, metas, ref_j, gold = load_case(name)
     bps, a_xyz, a_idx = synth.load_assets()
-    st = {}
-    with torch.no_grad():
-        want = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx, stages=st)
+    tmpl = synth.standin_template()
     head = build_head(dims, sd)
-    out = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda(), debug_metas=None)
-    got = out["all_coords_preds"]
-    assert got.shape == want.shape and got.dtype == torch.float32 and got.is_cuda
-    got = got.cpu()
+    got, nbr, _ = run_with_neighbours(head, feat, metas, ref_j)
     assert torch.isfinite(got).all()
-    mean_mm = 0.1 if meta["mode"] == "init" else 0.35
-    check_coords(got, want, name + " vs oracle", mean_mm)
-    check_coords(got, gold["all_coords_preds"], name + " vs reference golden", mean_mm)
+    st, st_f = {}, {}
+    with torch.no_grad():
+        want = orc.head_forward(sd, dims, feat, metas, ref_j, tmpl, bps, a_xyz, a_idx, stages=st)
+        want_f = orc.head_forward(sd, dims, feat, metas, ref_j, tmpl, bps, a_xyz, a_idx, stages=st_f, neighbours=nbr)
+    assert got.shape == want.shape
+    mean_mm = 0.05
+    # (A) same neighbour sets: every point inside the north-star bound
+    check_coords(got, want_f, name + " vs oracle on the kernels' 32-NN sets", mean_mm)
+    # (B) the sets themselves
+    check_neighbour_sets(nbr, got, ref_j, dims, st["pt_xyz"])
+    # un-forced oracle and the reference's own output
+    flipped = flipped_mask(nbr, st, dims)
+    check_coords(got, want, name + " vs oracle", 0.1, flipped)
+    check_coords(got, gold["all_coords_preds"], name + " vs reference golden", 0.1, flipped)
     # normalised offsets from the template (what the decoder actually regresses): relative error of the update
-    tmpl = st["q_xyz"]
+    q0 = st_f["q_xyz"]
     for i in range(dims.n_blocks):
-        upd_ref = st[f"b{i}.xyz"] - tmpl
+        upd_ref = st_f[f"b{i}.xyz"] - q0
         centre = ref_j[:, dims.center_idx][:, None]
-        upd_got = (got[i] - centre) / dims.radius - tmpl
+        upd_got = (got[i] - centre) / dims.radius - q0
         num = (upd_got - upd_ref).norm(dim=-1).mean().item()
         den = upd_ref.norm(dim=-1).mean().item()
         print(f"{name} block {i}: mean |d_update| / mean |update| = {num / den:.3e}")
-        assert num / den <= (1e-2 if meta["mode"] == "init" else 5e-2)
+        assert num / den <= 5e-3
 
 
 @pytest.mark.parametrize("size,views", [("small", [10]), ("small", [1]), ("medium", [1, 10, 5, 7]), ("small", [6, 9, 3])])
@@ -100,11 +165,15 @@ def test_view_count_edge_cases_match_oracle(size, views):
     sd = synth.make_state_dict(dims, 21, "init")
     feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 5)
     bps, a_xyz, a_idx = synth.load_assets()
-    with torch.no_grad():
-        want = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx)
     head = build_head(dims, sd)
-    got = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
-    check_coords(got, want, f"{size} views={views}", 0.1)
+    got, nbr, _ = run_with_neighbours(head, feat, metas, ref_j)
+    with torch.no_grad():
+        want_f = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx, neighbours=nbr)
+    check_coords(got, want_f, f"{size} views={views} (kernels' 32-NN sets)", 0.05)
+    st = {}
+    with torch.no_grad():
+        want = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx, stages=st)
+    check_coords(got, want, f"{size} views={views}", 0.05, flipped_mask(nbr, st, dims))
 
 
 def test_transformer_module_matches_oracle():
@@ -146,6 +215,33 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     host_out = head.forward_host(pin(feat), hm, pin(ref_j))
     torch.cuda.synchronize()
     assert torch.equal(host_out, dev_out.cpu())          # same kernels, same order: bit-identical
+
+
+def test_host_entry_point_pipelines_calls_of_different_shapes():
+    """Consecutive host-buffer calls whose batch / view counts differ (last partial batch of an epoch, ragged views)
+    while the previous call is still running: the staging slots sit at shape-independent offsets, so no call may
+    overwrite the inputs of the one before it (slot 1 of a small call used to land inside slot 0 of a
+    large one)."""
+    dims = release_dims("small")
+    sd = synth.make_state_dict(dims, 0)
+    head = build_head(dims, sd)
+    pin = lambda t: t.contiguous().pin_memory()  # noqa: E731
+    shapes = [[4, 4, 4, 4], [2], [3, 1, 2], [1], [4, 4, 4, 4], [2, 2]]
+    calls = []
+    for i, views in enumerate(shapes):
+        feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 30 + i)
+        dev_out = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
+        hm = dict(metas)
+        hm["cam_intr"], hm["cam_extr"] = pin(metas["cam_intr"]), pin(metas["cam_extr"])
+        calls.append((pin(feat), hm, pin(ref_j), dev_out))
+    torch.cuda.synchronize()
+    head.forward_host(*calls[0][:3])          # sizes the staging buffer for the largest call
+    torch.cuda.synchronize()
+    for rep in range(3):                      # back to back, no synchronisation in between
+        outs = [head.forward_host(f, m, r) for f, m, r, _ in calls]
+        torch.cuda.synchronize()
+        for o, (_, _, _, want) in zip(outs, calls):
+            assert torch.equal(o, want)
 
 
 def test_deterministic_and_batch_independent():
