@@ -1,6 +1,7 @@
 // Shared device helpers for the sm_100a kernels: mbarrier, TMA, tcgen05 (UMMA/TMEM) wrappers.
 // Everything here is inline PTX for Blackwell (compile with -gencode arch=compute_100a,code=sm_100a).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

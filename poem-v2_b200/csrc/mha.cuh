@@ -38,7 +38,7 @@ struct MhaCfg {
   static constexpr int kKBytes = MHA_BKEY * HD * 2;
   static constexpr int kVBytes = MHA_BKEY * HD * 2;              // kKBlocks tiles of [128 keys x kRowBytes]
   static constexpr int kPBytes = MHA_BQ * MHA_BKEY * 2;          // two [128 x 64 keys] SWIZZLE_128B tiles
-  static constexpr int kXchgBytes = 2 * 128 * 4;                // fp32 row-max exchange between the two row halves
+  static constexpr int kXchgBytes = 2 * 128 * 2;                // bf16 row-max exchange between the two row halves (512 B: two CTAs of 113.6 KB still fit one SM)
   static constexpr int kSmemBytes = kQBytes + 2 * (kKBytes + kVBytes) + kPBytes + kXchgBytes + 160;   // 2 CTAs/SM at HD=64
   static constexpr int kTmemCols = 256;                          // two S buffers; O_blk aliases the consumed one
 };
@@ -58,7 +58,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   uint8_t* sK = sQ + Cfg::kQBytes;               // 2 stages
   uint8_t* sV = sK + 2 * Cfg::kKBytes;           // 2 stages
   uint8_t* sP = sV + 2 * Cfg::kVBytes;
-  float* s_xchg = reinterpret_cast<float*>(sP + Cfg::kPBytes);
+  __nv_bfloat16* s_xchg = reinterpret_cast<__nv_bfloat16*>(sP + Cfg::kPBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes + Cfg::kXchgBytes);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;       // [2] TMA -> MMA
@@ -262,11 +262,15 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
 #pragma unroll
         for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
       }
-      // Exchange the half-row maxima.  Single buffer: the partner can only write its block j+1 value after S(j+1) was
-      // issued, which (for j >= 1) waits for o_done(j-1), i.e. for every thread's read below; block 0 syncs again.
-      s_xchg[half * 128 + row] = m_blk;
+      // Exchange the half-row maxima as bfloat16 (fp32 range, so a large raw score cannot overflow; any common reference
+      // value works for the softmax and both threads of a row use the same rounded pair — the probabilities may exceed
+      // 1 by the rounding, < 2^(2^-8 |m| scale), harmless in fp16).  Single buffer: the partner can only write its block
+      // j+1 value after S(j+1) was issued, which (for j >= 1) waits for o_done(j-1), i.e. for every thread's read below;
+      // block 0 syncs again.
+      const __nv_bfloat16 m_mine = __float2bfloat16(m_blk);
+      s_xchg[half * 128 + row] = m_mine;
       pair_sync();
-      m_blk = fmaxf(m_blk, s_xchg[(half ^ 1) * 128 + row]);
+      m_blk = fmaxf(__bfloat162float(m_mine), __bfloat162float(s_xchg[(half ^ 1) * 128 + row]));
       if (j == 0) pair_sync();
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)

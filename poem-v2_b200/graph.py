@@ -36,7 +36,7 @@ class GraphedForward:
         for m in self._modules_of(owner):
             self._pins.append((m, {k: getattr(m, k, None) for k in self._PIN_ATTRS}))
 
-    _PIN_ATTRS = ("_ws", "_stage", "_packed", "_packed_mano", "_packed_hr", "_pack")
+    _PIN_ATTRS = ("_ws", "_stage", "_packed", "_packed_mano")
 
     @staticmethod
     def _modules_of(owner):
