@@ -264,7 +264,9 @@ gemm_op16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int g = m / ep.rows_per_group;
         const int cnt = ep.row_cnt[g];
         scale = 1.0f / (float)cnt;
-        pb = ep.res_op16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
+        // row_tab == nullptr: the token-first rows were gathered by the producer (fused sampler/merge kernel): row m
+        pb = (ep.row_tab == nullptr) ? ep.res_op16 + (size_t)m * ep.res_ld
+                                     : ep.res_op16 + ((size_t)ep.row_tab[g] + (size_t)(m - g * ep.rows_per_group) * cnt) * ep.res_ld;
       }
     };
     for (int it = it0; it < it_end; it += it_step) {

@@ -15,6 +15,7 @@
 #include "mha.cuh"
 #include "hrnet.cuh"
 #include "simt.cuh"
+#include "sample_merge.cuh"
 #include "vecattn.cuh"
 #include "mano.cuh"
 
@@ -953,9 +954,10 @@ extern "C" int poem_layernorm(const float* x, const float* gamma, const float* b
 
 // per-image / per-sample index tables derived from view_counts
 struct ViewTables {
-  int *img_sample, *img_view, *img_posrow, *sample_rowbase, *sample_views;
+  int *img_sample, *img_view, *img_posrow, *sample_rowbase, *sample_views, *tile_start;
+  int n_merge_tiles;   // row tiles of the fused sampler/merge kernel (tile_start[B])
 };
-static size_t view_tables_ints(int B, int NV) { return (size_t)3 * NV + 2 * B; }
+static size_t view_tables_ints(int B, int NV) { return (size_t)3 * NV + 3 * B + 1; }
 static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, int max_views, int* dev, ViewTables* vt,
                               cudaStream_t st) {
   std::vector<int> h(view_tables_ints(B, NV));
@@ -964,13 +966,16 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
   int* img_posrow = img_view + NV;
   int* rowbase = img_posrow + NV;
   int* views = rowbase + B;
-  int img = 0;
+  int* tile_start = views + B;
+  int img = 0, tiles = 0;
   long long rb = 0;
   for (int b = 0; b < B; ++b) {
     const int n = host_views[b];
     if (n < 1 || n > max_views) return fail(POEM_E_BADDIM, "view count %d of sample %d outside [1,%d]", n, b, max_views);
     rowbase[b] = (int)rb;
     views[b] = n;
+    tile_start[b] = tiles;
+    tiles += merge_tiles_of(n, P);
     for (int v = 0; v < n; ++v, ++img) {
       if (img >= NV) return fail(POEM_E_BADDIM, "sum(view_counts) exceeds n_images=%d", NV);
       img_sample[img] = b;
@@ -981,6 +986,8 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
     if (rb > 0x7fffffffLL) return fail(POEM_E_BADDIM, "too many merge rows");
   }
   if (img != NV) return fail(POEM_E_BADDIM, "sum(view_counts)=%d != n_images=%d", img, NV);
+  tile_start[B] = tiles;
+  vt->n_merge_tiles = tiles;
   if (B <= VIEW_PARAM_MAX) {
     // the view counts travel as kernel parameters and the tables are rebuilt on the device: no host-to-device copy, so
     // the whole forward can be captured into a CUDA graph (a memcpy node would keep a pointer to this stack frame)
@@ -1004,6 +1011,7 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
   vt->img_posrow = dev + 2 * NV;
   vt->sample_rowbase = dev + 3 * NV;
   vt->sample_views = dev + 3 * NV + B;
+  vt->tile_start = dev + 3 * NV + 2 * B;
   return POEM_OK;
 }
 
@@ -1089,6 +1097,24 @@ static int launch_vecattn(const PoemVecAttn* w, const op16* q, int ldq, const op
                                                                      1.0f / sqrtf((float)D), n_query);
     LAUNCH_CHECK("va_reduce_kernel");
   }
+  return POEM_OK;
+}
+
+template <int D>
+static int launch_sample_merge(const PoemWeights* w, const SmParams& sp, cudaStream_t st) {
+  using Cfg = SmCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(sample_merge_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  CUtensorMap t0a, t0b;
+  POEM_TRY(make_tmap_op16(&t0a, w->merge0a.w, D, D, D, 64, 128));
+  POEM_TRY(make_tmap_op16(&t0b, w->merge0b.w, D / 2, D, D, 64, (uint32_t)(D / 2 < 128 ? D / 2 : 128)));
+  const int grid = sp.n_tiles < num_sms() ? sp.n_tiles : num_sms();
+  prof_begin(st);
+  sample_merge_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t0a, t0b, sp);
+  LAUNCH_CHECK("sample_merge_kernel");
   return POEM_OK;
 }
 
@@ -1183,7 +1209,9 @@ struct HeadPlan {    // everything in front of the blocks
   int* tables;
   float *proj, *centre, *xmap;
   op16 *featT, *X, *H1, *Mm, *S, *H2;
-  float* sigma;   // per-token power-of-two scale of S (merge_reduce_kernel)
+  float* sigma;   // per-token power-of-two scale of S (merge_reduce_kernel / sample_merge_kernel)
+  uint32_t* taps; // bilinear taps of every (image, BPS point) (sample_taps_kernel)
+  op16* Q1;       // (B*P, D) token-first rows of X (fused path)
 };
 
 static int check_dims(const PoemDims* d) {
@@ -1251,6 +1279,8 @@ static void plan_head(const PoemDims* d, int B, int NV, Bump& b, HeadPlan* p) {
   p->S = b.take<op16>(BP * D / 2);
   p->H2 = b.take<op16>(BP * D / 2);
   p->sigma = b.take<float>(BP);
+  p->taps = b.take<uint32_t>((size_t)NV * (P / 4) * SM_TAP_WORDS);
+  p->Q1 = b.take<op16>(BP * D);
 }
 
 extern "C" size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images) {
@@ -1598,10 +1628,27 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
                                                                 p.pt_xyz_sorted);
     LAUNCH_CHECK("normalise_points_kernel");
   }
-  // ---- a4/a5 (+ the raw .view regroup of a6): X rows
+  // ---- a4/a5/a6: projection + bilinear sampling + merge MLP0 + cross-view reduce.  Fused kernel (sample_merge.cuh)
+  //      for D <= 256: nothing row-sized (X, H1, Mm) touches HBM; else (D = 512, or the test hook) the four-kernel chain.
+  const bool fused_merge = !g_force_unfused && (D == 128 || D == 256) && P == SM_P && dims->max_views <= 16;
+  if (fused_merge) {
+    if (!w->merge0a.w || !w->merge0a.b || !w->merge0b.w || !w->merge0b.b) return fail(POEM_E_NULL, "merge_net_feature.0 missing");
+    prof_begin(st);
+    camera_prep_kernel<<<(NV + 63) / 64, 64, 0, st>>>(in->cam_intr, in->cam_extr, h.proj, NV);
+    LAUNCH_CHECK("camera_prep_kernel");
+    prof_begin(st);
+    sample_taps_kernel<<<(unsigned)(((size_t)NV * P + 255) / 256), 256, 0, st>>>(h.proj, w->bps, h.centre, vt.img_sample, h.taps, NV,
+                                                                               dims->feat_h, dims->feat_w, 1.0f / in->inp_img_w,
+                                                                               1.0f / in->inp_img_h);
+    LAUNCH_CHECK("sample_taps_kernel");
+    SmParams sp;
+    sp.xmap = h.xmap, sp.taps = h.taps, sp.tile_start = vt.tile_start, sp.sample_views = vt.sample_views;
+    sp.sample_rowbase = vt.sample_rowbase, sp.b0a = w->merge0a.b, sp.b0b = w->merge0b.b;
+    sp.q1 = h.Q1, sp.s = h.S, sp.sigma = h.sigma, sp.n_samples = B, sp.n_tiles = vt.n_merge_tiles;
+    POEM_TRY(D == 128 ? launch_sample_merge<128>(w, sp, st) : launch_sample_merge<256>(w, sp, st));
+  } else {
   POEM_TRY(launch_project_sample(h.xmap, in->cam_intr, in->cam_extr, w->bps, h.centre, vt, h.proj, NV, D, P,
                                  dims->feat_h, dims->feat_w, in->inp_img_w, in->inp_img_h, h.X, st));
-  // ---- a6: merge network
   POEM_TRY(linear("merge0a", h.X, D, w->merge0a, (int)R, D, D, ACT_RELU, nullptr, nullptr, h.H1, st));
   POEM_TRY(linear("merge0b", h.H1, D, w->merge0b, (int)R, H, D, ACT_NONE, nullptr, nullptr, h.Mm, st));
   {
@@ -1615,6 +1662,7 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
       default: merge_reduce_kernel<16><<<blocks, threads, 0, st>>>(h.Mm, vt.sample_rowbase, vt.sample_views, h.S, h.sigma, P, BP); break;
     }
     LAUNCH_CHECK("merge_reduce_kernel");
+  }
   }
   {   // MLP1 hidden layer on S / sigma: relu(W s / sigma + b / sigma) = H2 / sigma
     if (!w->merge1a.w) return fail(POEM_E_NULL, "merge_net_feature.1.0 missing");
@@ -1633,9 +1681,9 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
     GemmEpilogue e = epi_default(D);
     e.bias = w->merge1b.b;
     e.res_mode = RES_MERGE;
-    e.res_op16 = h.X;
+    e.res_op16 = fused_merge ? h.Q1 : h.X;
     e.res_ld = D;
-    e.row_tab = vt.sample_rowbase;
+    e.row_tab = fused_merge ? nullptr : vt.sample_rowbase;   // fused path: the token-first rows are already gathered
     e.row_cnt = vt.sample_views;
     e.rows_per_group = P;
     e.row_sigma = h.sigma;

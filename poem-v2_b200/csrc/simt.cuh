@@ -618,18 +618,25 @@ __global__ void broadcast_queries_kernel(const float* __restrict__ table, float*
 }
 
 // Per-image / per-sample index tables from the per-sample view counts (passed by value):
-//   dev = [img_sample (NV) | img_view (NV) | img_posrow (NV) | sample_rowbase (B) | sample_views (B)]
+//   dev = [img_sample (NV) | img_view (NV) | img_posrow (NV) | sample_rowbase (B) | sample_views (B) | tile_start (B+1)]
+//   tile_start: first row tile of every sample in the fused sampler/merge kernel (tiles of floor(128 / n) tokens)
 constexpr int VIEW_PARAM_MAX = 256;
 struct ViewCountsParam {
   int n[VIEW_PARAM_MAX];
 };
+__host__ __device__ inline int merge_tiles_of(int n_views, int P) {
+  const int tok = 128 / n_views;
+  return (P + tok - 1) / tok;
+}
 __global__ void view_tables_kernel(ViewCountsParam vc, int B, int NV, int P, int* __restrict__ dev) {
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    int first = 0;
-    for (int i = 0; i < b; ++i) first += vc.n[i];
+    int first = 0, tiles = 0;
+    for (int i = 0; i < b; ++i) first += vc.n[i], tiles += merge_tiles_of(vc.n[i], P);
     const int n = vc.n[b];
     dev[3 * NV + b] = first * P;
     dev[3 * NV + B + b] = n;
+    dev[3 * NV + 2 * B + b] = tiles;
+    if (b == B - 1) dev[3 * NV + 2 * B + B] = tiles + merge_tiles_of(n, P);
     for (int v = 0; v < n; ++v) {
       dev[first + v] = b;
       dev[NV + first + v] = v;

@@ -244,6 +244,30 @@ def test_host_entry_point_pipelines_calls_of_different_shapes():
             assert torch.equal(o, want)
 
 
+@pytest.mark.parametrize("size,views", [("small", [1, 3, 7, 10, 8]), ("medium", [8, 8]), ("medium", [5, 1, 9])])
+def test_fused_sampler_merge_matches_the_unfused_chain(size, views):
+    """sample_merge_kernel (sampler + merge MLP0 + cross-view reduce in one kernel, row tiles of floor(128 / N) tokens,
+    tiles that straddle channel planes / views when N does not divide 128) against the four-kernel chain it replaces
+    (project_sample -> GEMM -> GEMM -> merge_reduce, `poem_debug_force_unfused`), on the device, whole path."""
+    from poem_v2_b200 import _native as nat
+    dims = release_dims(size)
+    sd = synth.make_state_dict(dims, 3, "stress")
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 11)
+    head = build_head(dims, sd)
+    lib = nat.load()
+    fused = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
+    lib.poem_debug_force_unfused(1)
+    try:
+        chain = head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
+    finally:
+        lib.poem_debug_force_unfused(0)
+    # block 0 has no 32-NN search: the two paths differ only by rounding (Mm stays fp32 in the fused kernel)
+    err0 = (fused[0] - chain[0]).norm(dim=-1)
+    print(f"{size} views={views}: block 0 fused vs chain: mean {err0.mean().item() * 1e3:.5f} mm, max {err0.max().item() * 1e3:.5f} mm")
+    assert torch.isfinite(fused).all()
+    assert err0.max().item() <= 0.1 * MM and err0.mean().item() <= 0.01 * MM
+
+
 def test_deterministic_and_batch_independent():
     """Samples are independent units: a sample's output must not depend on its batch neighbours."""
     dims = release_dims("small")
