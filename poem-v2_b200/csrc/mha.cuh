@@ -247,36 +247,31 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       mbar_arrive(&o_done[st]);
     };
 
-    // Software pipeline over the key blocks: the row maximum of block j + 1 ("pass A": TMEM read + FMNMX, no MUFU) is
-    // computed INSIDE the second half of block j's exponential pass ("pass B": MUFU-bound), so the SFU pipe and the
-    // ALU / TMEM-load work of one warp overlap instruction by instruction instead of alternating in phases (all eight
-    // warps of a CTA move in lock step through the barriers, so un-fused phases left the MUFU idle half of the time:
-    // 47 % MUFU, 37 % issue, 34 % tensor utilisation adding up to the launch time).  S(j+1) is issued by the MMA warp
-    // as soon as O_blk(j-1) has been folded at the top of iteration j, i.e. it lands during the first half of pass B.
-    auto pass_a16 = [&](uint32_t taddr, float& mx) {    // max over 16 more columns
-      uint32_t r[16];
-      tmem_ld16(taddr, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-    };
-    float m_blk = -INFINITY;   // this thread's half-row maximum of the block about to be processed
-    {
-      mbar_wait(&s_full[0], 0);
-      tc_fence_after_sync();
-      const uint32_t tmem_S0 = tmem_base + lane_off + half * 64;
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) pass_a16(tmem_S0 + c0, m_blk);
-    }
+    // Per key block: pass A (row maximum), pass B (probabilities -> P tile), and the fold of the PREVIOUS block's P·V.
+    // The fold sits in the MIDDLE of pass B: at the top of the iteration P·V(j-1) — issued only once the slowest thread
+    // had finished pass B(j-1) — is usually still in flight (ncu round 2: 16 % of all warp samples waited on o_full
+    // there).  The P tile is single-buffered and P·V(j-1) reads it until o_full, so the first half of the new
+    // probabilities waits in 16 registers and is stored after the fold.
     for (int j = 0; j < n_kblocks; ++j) {
       const int st = j & 1;
       const uint32_t tmem_S = tmem_base + lane_off + st * 128 + half * 64;
-      const uint32_t tmem_Sn = tmem_base + lane_off + (st ^ 1) * 128 + half * 64;
+      mbar_wait(&s_full[st], (uint32_t)(j >> 1) & 1);
+      tc_fence_after_sync();
+      // pass A: max over this thread's 64 columns, then over the row via the partner thread
+      float m_blk = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_S + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[i]));
+      }
       // Exchange the half-row maxima as bfloat16 (fp32 range, so a large raw score cannot overflow; any common reference
       // value works for the softmax and both threads of a row use the same rounded pair — the probabilities may exceed
-      // 1 by the rounding, < 2^(2^-8 |m| scale), harmless in fp16).  Single buffer: the partner can only compute its
-      // block j+1 value from S(j+1), which (for j >= 1) is issued after o_done(j-1), i.e. after every thread's read
-      // below (fold_o comes later in the iteration); S(0) and S(1) are issued up front, so block 0 syncs again.
+      // 1 by the rounding, < 2^(2^-8 |m| scale), harmless in fp16).  Single buffer: the partner can only write its block
+      // j+1 value after S(j+1) was issued, which (for j >= 1) waits for o_done(j-1), i.e. for every thread's fold below
+      // (after its read here); S(0) and S(1) are issued up front, so block 0 syncs again.
       const __nv_bfloat16 m_mine = __float2bfloat16(m_blk);
       s_xchg[half * 128 + row] = m_mine;
       pair_sync();
@@ -285,28 +280,15 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
       const float m_new = fmaxf(m_run, m_blk);
       const float alpha = fast_exp2((m_run - m_new) * scale_log2e);   // 0 on the first block (m_run = -inf)
       const float m_scaled = m_new * scale_log2e;
-      // fold the previous block's P·V (finished long ago) — this also guarantees the P tile is free again
-      if (j > 0) fold_o(j - 1, alpha_prev);
-      alpha_prev = alpha;
       // pass B: probabilities -> fp16 -> swizzled smem (A operand of P·V); this thread fills K block `half`
       float l_blk = 0.f;
-      float m_next = -INFINITY;
       uint8_t* tile = sP + half * (MHA_BQ * 128);
-      const bool has_next = j + 1 < n_kblocks;
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        if (c0 == 32 && has_next) {   // S(j+1) has landed by now in steady state
-          mbar_wait(&s_full[st ^ 1], (uint32_t)((j + 1) >> 1) & 1);
-          tc_fence_after_sync();
-        }
-        uint32_t r[16], ra[16];
-        const bool fuse = (c0 >= 32) && has_next;
-        tmem_ld16(tmem_S + c0, r);
-        if (fuse) tmem_ld16(tmem_Sn + (c0 - 32) * 2, ra);   // pass A of block j + 1: 32 of its 64 columns per chunk
+      auto pass_b32 = [&](int c0, uint32_t (&pk)[16]) {     // 32 columns -> 16 packed pairs
+        uint32_t r[32];
+        tmem_ld32(tmem_S + c0, r);
         tmem_ld_wait();
-        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float x0 = __uint_as_float(r[2 * i]) * scale_log2e - m_scaled;
           const float x1 = __uint_as_float(r[2 * i + 1]) * scale_log2e - m_scaled;
           const float p0 = fast_exp2(x0);
@@ -314,18 +296,26 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
           const float p1 = (MHA_POLY_EVERY > 0 && (i % (MHA_POLY_EVERY > 0 ? MHA_POLY_EVERY : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1);
           l_blk += p0 + p1;
           pk[i] = pack_op16x2(p0, p1);
-          if (fuse) m_next = fmaxf(m_next, fmaxf(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1])));
         }
-        if (fuse) pass_a16(tmem_Sn + (c0 - 32) * 2 + 16, m_next);
+      };
+      auto store_p32 = [&](int c0, const uint32_t (&pk)[16]) {
         const int chunk0 = c0 >> 3;
-        *reinterpret_cast<uint4*>(tile + sw128_offset(row, chunk0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(tile + sw128_offset(row, chunk0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(tile + sw128_offset(row, chunk0 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      };
+      uint32_t pk0[16], pk1[16];
+      pass_b32(0, pk0);
+      // fold the previous block's P·V: by now it has had pass A + half of pass B to finish; also frees the P tile
+      if (j > 0) fold_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
+      store_p32(0, pk0);
+      pass_b32(32, pk1);
+      store_p32(32, pk1);
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
-      m_blk = m_next;
       fence_proxy_async_smem();     // P visible to the tensor-core (async) proxy
-      tc_fence_before_sync();       // our TMEM reads of S(j) (and S(j+1)) are done before P·V(j) overwrites the buffer
+      tc_fence_before_sync();       // our TMEM reads of S(j) are done before P·V(j) overwrites the buffer
       mbar_arrive(p_full);
     }
     fold_o(n_kblocks - 1, alpha_prev);

@@ -1639,7 +1639,8 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
     prof_begin(st);
     sample_taps_kernel<<<(unsigned)(((size_t)NV * P + 255) / 256), 256, 0, st>>>(h.proj, w->bps, h.centre, vt.img_sample, h.taps, NV,
                                                                                dims->feat_h, dims->feat_w, 1.0f / in->inp_img_w,
-                                                                               1.0f / in->inp_img_h);
+                                                                               1.0f / in->inp_img_h,
+                                                                               (D == 128 ? SmCfg<128>::SLOTS : SmCfg<256>::SLOTS) * 4);
     LAUNCH_CHECK("sample_taps_kernel");
     SmParams sp;
     sp.xmap = h.xmap, sp.taps = h.taps, sp.tile_start = vt.tile_start, sp.sample_views = vt.sample_views;

@@ -29,7 +29,8 @@ namespace poem {
 
 constexpr int SM_P = 4096;         // BPS points
 constexpr int SM_F = 256;          // feature pixels
-constexpr int SM_TAP_WORDS = 20;   // per group of 4 points: w00[4] w01[4] w10[4] w11[4] (fp32) offs[4] (4 x u8 pixel index)
+constexpr int SM_TAP_WORDS = 24;   // per group of 4 points: w00[4] w01[4] w10[4] w11[4] (fp32), then per point two words
+                                   // = four u16 byte offsets (pixel index * slab pixel pitch) of the taps nw|ne, sw|se
 
 // ------------------------------------------------------------------------------------------------
 // taps[img][p / 4][20]: projection of BPS point p into image img + bilinear weights (zero padding folded into the
@@ -37,7 +38,8 @@ constexpr int SM_TAP_WORDS = 20;   // per group of 4 points: w00[4] w01[4] w10[4
 // ------------------------------------------------------------------------------------------------
 __global__ void sample_taps_kernel(const float* __restrict__ proj, const float* __restrict__ bps,
                                    const float* __restrict__ centre, const int* __restrict__ img_sample,
-                                   uint32_t* __restrict__ taps, int n_img, int FH, int FW, float inv_w, float inv_h) {
+                                   uint32_t* __restrict__ taps, int n_img, int FH, int FW, float inv_w, float inv_h,
+                                   int pixel_pitch_bytes) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_img * SM_P) return;
   const int img = idx / SM_P, p = idx - img * SM_P;
@@ -79,7 +81,10 @@ __global__ void sample_taps_kernel(const float* __restrict__ proj, const float* 
   t[4] = __float_as_uint(w01);
   t[8] = __float_as_uint(w10);
   t[12] = __float_as_uint(w11);
-  t[16] = o00 | (o01 << 8) | (o10 << 16) | (o11 << 24);
+  const uint32_t pb = (uint32_t)pixel_pitch_bytes;   // 255 * 48 < 65536
+  uint32_t* o = taps + ((size_t)img * (SM_P / 4) + (p >> 2)) * SM_TAP_WORDS + 16 + 2 * (p & 3);
+  o[0] = (o00 * pb) | ((o01 * pb) << 16);
+  o[1] = (o10 * pb) | ((o11 * pb) << 16);
 }
 
 template <int D>
@@ -101,7 +106,8 @@ struct SmCfg {
   static constexpr int OFF_W = 2 * X_BYTES;
   static constexpr int OFF_SLAB = OFF_W + W_STAGES * W_TILE_BYTES;  // two slabs
   static constexpr int OFF_BIAS = OFF_SLAB + 2 * SLAB_BYTES;        // b0a [D] | b0b [H]
-  static constexpr int OFF_BARS = OFF_BIAS + (D + H) * 4;
+  static constexpr int OFF_TOK = OFF_BIAS + (D + H) * 4;             // two tables of 128 ints (token of a tile row)
+  static constexpr int OFF_BARS = OFF_TOK + 2 * 128 * 4;
   static constexpr int SMEM_BYTES = OFF_BARS + 256;
   static constexpr int TMEM_COLS = (D + H <= 256) ? 256 : 512;
   static constexpr int W1_STEPS = KB * (D / 128);    // weight tiles of MLP0 layer 1 per row tile ([128 n] x [64 k])
@@ -125,11 +131,14 @@ struct SmParams {
 // tile -> sample lookup for a monotonically increasing tile sequence
 struct SmTileCursor {
   int b = 0, lo = 0, hi = 0;   // tiles [lo, hi) belong to sample b
+  int n_views = 1, img0 = 0;   // of sample b (re-read only when the sample changes)
   __device__ __forceinline__ void seek(const SmParams& p, int tile) {
     while (tile >= hi) {
       if (hi != 0) ++b;
       lo = p.tile_start[b];
       hi = p.tile_start[b + 1];
+      n_views = p.sample_views[b];
+      img0 = p.sample_rowbase[b] / SM_P;
     }
   }
 };
@@ -146,6 +155,7 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
   float* s_slab = reinterpret_cast<float*>(smem + Cfg::OFF_SLAB);
   float* s_b0a = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
   float* s_b0b = s_b0a + D;
+  int* s_tok = reinterpret_cast<int*>(smem + Cfg::OFF_TOK);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BARS);
   uint64_t* w_full = bars;                       // [W_STAGES]
   uint64_t* w_empty = bars + Cfg::W_STAGES;      // [W_STAGES]
@@ -274,7 +284,7 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
       const int buf = it & 1;
       uint8_t* xb = s_x + buf * Cfg::X_BYTES;
       cur.seek(p, tile);
-      const int N = p.sample_views[cur.b];
+      const int N = cur.n_views;
       const int TOK = 128 / N;
       const int tok0 = (tile - cur.lo) * TOK;
       const int ntok = min(TOK, SM_P - tok0);
@@ -289,8 +299,11 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_op16x2_relu(__uint_as_float(r[2 * i]) + s_b0a[c + 2 * i], __uint_as_float(r[2 * i + 1]) + s_b0a[c + 2 * i + 1]);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_b0a + c + 4 * i);
+          pk[2 * i] = pack_op16x2_relu(__uint_as_float(r[4 * i]) + b4.x, __uint_as_float(r[4 * i + 1]) + b4.y);
+          pk[2 * i + 1] = pack_op16x2_relu(__uint_as_float(r[4 * i + 2]) + b4.z, __uint_as_float(r[4 * i + 3]) + b4.w);
+        }
         uint8_t* blk = xb + (c >> 6) * (128 * 128);
         const uint32_t chunk0 = (uint32_t)(c & 63) >> 3;
 #pragma unroll
@@ -314,11 +327,12 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int c4 = (c >> 2) + q;           // 16-byte chunk (4 channels)
+          const float4 b4 = *reinterpret_cast<const float4*>(s_b0b + c + 4 * q);
           float4 v;
-          v.x = __uint_as_float(r[4 * q + 0]) + s_b0b[c + 4 * q + 0];
-          v.y = __uint_as_float(r[4 * q + 1]) + s_b0b[c + 4 * q + 1];
-          v.z = __uint_as_float(r[4 * q + 2]) + s_b0b[c + 4 * q + 2];
-          v.w = __uint_as_float(r[4 * q + 3]) + s_b0b[c + 4 * q + 3];
+          v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
+          v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
+          v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
+          v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
           *reinterpret_cast<float4*>(stg + (size_t)row * H + ((c4 ^ (row & 7)) << 2)) = v;
         }
       }
@@ -342,7 +356,23 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
         load_row(t * N, m0);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) acc[i] = (N == 1) ? m0[i] : 0.f;
-        for (int n = 1; n < N; ++n) {
+        int n = 1;
+        for (; n + 1 < N; n += 2) {                 // two views per step: the two shuffle reductions interleave
+          float ma[CPL], mb[CPL];
+          load_row(t * N + n, ma);
+          load_row(t * N + n + 1, mb);
+          float da = 0.f, db = 0.f;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) da += ma[i] * m0[i], db += mb[i] * m0[i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            da += __shfl_xor_sync(0xffffffffu, da, o);
+            db += __shfl_xor_sync(0xffffffffu, db, o);
+          }
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) acc[i] += da * ma[i], acc[i] += db * mb[i];
+        }
+        if (n < N) {
           float mv[CPL];
           load_row(t * N + n, mv);
           float dot = 0.f;
@@ -377,12 +407,12 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
     // slab loader: thread = (pixel px, slot group of 4): 4-byte cp.async per plane value, transposed into pixel-major
     auto load_slab = [&](int tile, SmTileCursor& c, int sbuf) {
       c.seek(p, tile);
-      const int N = p.sample_views[c.b];
+      const int N = c.n_views;
       const int TOK = 128 / N;
       const int r0 = (tile - c.lo) * TOK * N;
       const int L0 = r0 / G;
       const int planes = N * D;                        // planes of this sample
-      const float* base = p.xmap + ((size_t)(p.sample_rowbase[c.b] / SM_P) * D) * SM_F;
+      const float* base = p.xmap + ((size_t)c.img0 * D) * SM_F;
       float* dst = s_slab + sbuf * (Cfg::SLAB_BYTES / 4);
       for (int e = stid; e < SM_F * SLOTS; e += Cfg::N_SAMPLER) {
         const int slot = e / SM_F, px = e - slot * SM_F;
@@ -403,45 +433,111 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
       const float* slab = s_slab + buf * (Cfg::SLAB_BYTES / 4);
       cur.seek(p, tile);
       const int b = cur.b;
-      const int N = p.sample_views[b];
+      const int N = cur.n_views;
       const int TOK = 128 / N;
       const int tok0 = (tile - cur.lo) * TOK;
-      const int r0 = tok0 * N;                           // first row of the tile inside the sample
+      const int r0 = tok0 * N;                           // first row of the tile inside the sample (a multiple of N)
       const int rows_total = N * SM_P;
       const int Rb = (r0 / G) * G;                       // aligned base: item j owns rows Rb + j + G q
       const int L0 = Rb / G;
       const int QN = (Rb == r0) ? RPI : RPI + 1;
-      const int img0 = p.sample_rowbase[b] / SM_P;
+      const int img0 = cur.img0;
       // this tile's slab has landed (issued one tile ago); everyone has finished reading the other slab -> prefetch
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // token of every tile row that is the first row of a token (q1 of merge_features_mv), -1 otherwise:
+      // r = r0 + i with r0 a multiple of N, so r % N == i % N and r / N == tok0 + i / N  (one division per row and tile)
+      if (stid < 128) {
+        const int qd = stid / N;
+        s_tok[buf * 128 + stid] = (stid - qd * N == 0 && r0 + stid < rows_total) ? tok0 + qd : -1;
+      }
       asm volatile("bar.sync 3, %0;" ::"n"(Cfg::N_SAMPLER) : "memory");
       if (tile + (int)gridDim.x < p.n_tiles) load_slab(tile + gridDim.x, cur_next, buf ^ 1);
       // the X buffer must have been released by the epilogue of tile it - 2
       if (it >= 2) mbar_wait(&x_free[buf], (uint32_t)((it - 2) >> 1) & 1);
+      const int* tok_of = s_tok + buf * 128;
+      const bool fast = (Rb == r0) && (L0 % D) + RPI <= D && r0 + 128 <= rows_total;
+      if (fast) {
+        // ---- aligned tile (always the case when N divides 128): one view, slots 0 .. RPI-1, every row valid.
+        // Work item = (8-point group kc, row residue j): lane = (j & 3) * 8 + (kc & 7), so a warp's 8-byte A-tile
+        // stores cover four consecutive 128-byte rows (conflict-free); rows of one item are 16 apart, so the
+        // swizzle XOR (row & 7) is the same for all of them and the stores differ by immediate offsets.
+        const int n = L0 / D;
+        const int lane_s = stid & 31, wv = stid >> 5;
+        for (int wi = wv; wi < (G / 4) * (KC / 8); wi += Cfg::N_SAMPLER / 32) {
+          const int j = (wi % (G / 4)) * 4 + (lane_s >> 3);
+          const int kc = (wi / (G / 4)) * 8 + (lane_s & 7);
+          const uint32_t* tp = p.taps + ((size_t)(img0 + n) * (SM_P / 4) + (size_t)(j * D + kc * 8) / 4) * SM_TAP_WORDS;
+          uint8_t* arow = xb + (kc >> 3) * (128 * 128) + sw128_offset(j, kc & 7);    // row j + G q: + q * G * 128 bytes
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {               // points kc*8 + 4*hf .. + 3
+            uint4 T[6];
+#pragma unroll
+            for (int w = 0; w < 6; ++w) T[w] = __ldg(reinterpret_cast<const uint4*>(tp + hf * SM_TAP_WORDS) + w);
+            const float w00[4] = {__uint_as_float(T[0].x), __uint_as_float(T[0].y), __uint_as_float(T[0].z), __uint_as_float(T[0].w)};
+            const float w01[4] = {__uint_as_float(T[1].x), __uint_as_float(T[1].y), __uint_as_float(T[1].z), __uint_as_float(T[1].w)};
+            const float w10[4] = {__uint_as_float(T[2].x), __uint_as_float(T[2].y), __uint_as_float(T[2].z), __uint_as_float(T[2].w)};
+            const float w11[4] = {__uint_as_float(T[3].x), __uint_as_float(T[3].y), __uint_as_float(T[3].z), __uint_as_float(T[3].w)};
+            const uint32_t oa[4] = {T[4].x, T[4].z, T[5].x, T[5].z};     // nw | ne byte offsets of points 0..3
+            const uint32_t ob[4] = {T[4].y, T[4].w, T[5].y, T[5].w};     // sw | se
+            const char* sl8 = reinterpret_cast<const char*>(slab);
+#pragma unroll
+            for (int g4 = 0; g4 < RPI / 4; ++g4) {
+              float v[4][4];                             // [slot][point]
+#pragma unroll
+              for (int pt = 0; pt < 4; ++pt) {
+                // ATen accumulates the four taps in the order nw, ne, sw, se
+                const float4 a = *reinterpret_cast<const float4*>(sl8 + (oa[pt] & 0xffffu) + 16 * g4);
+                const float4 bq = *reinterpret_cast<const float4*>(sl8 + (oa[pt] >> 16) + 16 * g4);
+                const float4 c = *reinterpret_cast<const float4*>(sl8 + (ob[pt] & 0xffffu) + 16 * g4);
+                const float4 d = *reinterpret_cast<const float4*>(sl8 + (ob[pt] >> 16) + 16 * g4);
+                float t;
+                t = a.x * w00[pt], t += bq.x * w01[pt], t += c.x * w10[pt], t += d.x * w11[pt], v[0][pt] = t;
+                t = a.y * w00[pt], t += bq.y * w01[pt], t += c.y * w10[pt], t += d.y * w11[pt], v[1][pt] = t;
+                t = a.z * w00[pt], t += bq.z * w01[pt], t += c.z * w10[pt], t += d.z * w11[pt], v[2][pt] = t;
+                t = a.w * w00[pt], t += bq.w * w01[pt], t += c.w * w10[pt], t += d.w * w11[pt], v[3][pt] = t;
+              }
+#pragma unroll
+              for (int sl = 0; sl < 4; ++sl) {
+                const int q = 4 * g4 + sl;
+                const uint2 val = make_uint2(pack_op16x2(v[sl][0], v[sl][1]), pack_op16x2(v[sl][2], v[sl][3]));
+                *reinterpret_cast<uint2*>(arow + q * (G * 128) + hf * 8) = val;
+                const int tk = tok_of[j + G * q];
+                if (tk >= 0) *reinterpret_cast<uint2*>(p.q1 + ((size_t)b * SM_P + tk) * D + kc * 8 + hf * 4) = val;
+              }
+            }
+          }
+        }
+      } else {
+      // ---- generic tile (view counts that do not divide 128): the tile may start inside a channel plane and straddle
+      //      two views; slot groups of 4 are sampled per view and only the rows that belong to it are stored
       for (int item = stid; item < G * KC; item += Cfg::N_SAMPLER) {
         const int j = item / KC, kc = item - j * KC;     // chunk j (points j*D ..), 16-byte piece kc of the row
-        const int n_first = L0 / D, n_last = (L0 + QN - 1) / D;
+        // (the last tile of a sample may reach past its last view: those rows do not exist)
+        const int n_first = L0 / D, n_last = min((L0 + QN - 1) / D, N - 1);
         for (int n = n_first; n <= n_last; ++n) {
           const int q_lo = max(0, n * D - L0), q_hi = min(QN, (n + 1) * D - L0);
           const uint32_t* tp = p.taps + ((size_t)(img0 + n) * (SM_P / 4) + (size_t)(j * D + kc * 8) / 4) * SM_TAP_WORDS;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {               // points kc*8 + 4*hf .. + 3
             const uint4* t4 = reinterpret_cast<const uint4*>(tp + hf * SM_TAP_WORDS);
-            const uint4 W00 = __ldg(t4), W01 = __ldg(t4 + 1), W10 = __ldg(t4 + 2), W11 = __ldg(t4 + 3), OFF = __ldg(t4 + 4);
+            const uint4 W00 = __ldg(t4), W01 = __ldg(t4 + 1), W10 = __ldg(t4 + 2), W11 = __ldg(t4 + 3);
+            const uint4 OA = __ldg(t4 + 4), OB = __ldg(t4 + 5);
             const float w00[4] = {__uint_as_float(W00.x), __uint_as_float(W00.y), __uint_as_float(W00.z), __uint_as_float(W00.w)};
             const float w01[4] = {__uint_as_float(W01.x), __uint_as_float(W01.y), __uint_as_float(W01.z), __uint_as_float(W01.w)};
             const float w10[4] = {__uint_as_float(W10.x), __uint_as_float(W10.y), __uint_as_float(W10.z), __uint_as_float(W10.w)};
             const float w11[4] = {__uint_as_float(W11.x), __uint_as_float(W11.y), __uint_as_float(W11.z), __uint_as_float(W11.w)};
-            const uint32_t off[4] = {OFF.x, OFF.y, OFF.z, OFF.w};
+            const uint32_t oa[4] = {OA.x, OA.z, OB.x, OB.z};     // nw | ne byte offsets into the slab
+            const uint32_t ob[4] = {OA.y, OA.w, OB.y, OB.w};     // sw | se
+            const char* sl8 = reinterpret_cast<const char*>(slab);
             for (int g4 = q_lo / 4; 4 * g4 < q_hi; ++g4) {
               float v[4][4];                             // [slot][point]
 #pragma unroll
               for (int pt = 0; pt < 4; ++pt) {
                 // ATen accumulates the four taps in the order nw, ne, sw, se
-                const float4 a = *reinterpret_cast<const float4*>(slab + (off[pt] & 255u) * SLOTS + 4 * g4);
-                const float4 bq = *reinterpret_cast<const float4*>(slab + ((off[pt] >> 8) & 255u) * SLOTS + 4 * g4);
-                const float4 c = *reinterpret_cast<const float4*>(slab + ((off[pt] >> 16) & 255u) * SLOTS + 4 * g4);
-                const float4 d = *reinterpret_cast<const float4*>(slab + (off[pt] >> 24) * SLOTS + 4 * g4);
+                const float4 a = *reinterpret_cast<const float4*>(sl8 + (oa[pt] & 0xffffu) + 16 * g4);
+                const float4 bq = *reinterpret_cast<const float4*>(sl8 + (oa[pt] >> 16) + 16 * g4);
+                const float4 c = *reinterpret_cast<const float4*>(sl8 + (ob[pt] & 0xffffu) + 16 * g4);
+                const float4 d = *reinterpret_cast<const float4*>(sl8 + (ob[pt] >> 16) + 16 * g4);
                 float t;
                 t = a.x * w00[pt], t += bq.x * w01[pt], t += c.x * w10[pt], t += d.x * w11[pt], v[0][pt] = t;
                 t = a.y * w00[pt], t += bq.y * w01[pt], t += c.y * w10[pt], t += d.y * w11[pt], v[1][pt] = t;
@@ -458,13 +554,14 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
                   pk.x = pack_op16x2(v[sl][0], v[sl][1]);
                   pk.y = pack_op16x2(v[sl][2], v[sl][3]);
                   *reinterpret_cast<uint2*>(xb + (kc >> 3) * (128 * 128) + sw128_offset(i, kc & 7) + hf * 8) = pk;
-                  if (r % N == 0)                        // token-first row: q1 of merge_features_mv / q of _sv
-                    *reinterpret_cast<uint2*>(p.q1 + ((size_t)b * SM_P + r / N) * D + kc * 8 + hf * 4) = pk;
+                  const int tk = tok_of[i];              // token-first row: q1 of merge_features_mv / q of _sv
+                  if (tk >= 0) *reinterpret_cast<uint2*>(p.q1 + ((size_t)b * SM_P + tk) * D + kc * 8 + hf * 4) = pk;
                 }
               }
             }
           }
         }
+      }
       }
       fence_proxy_async_smem();      // A tile visible to the tensor-core (async) proxy
       mbar_arrive(&a_full[buf]);

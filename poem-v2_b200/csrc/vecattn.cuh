@@ -101,7 +101,8 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   uint64_t* act_full = bars + 2 * Cfg::W_STAGES;  // channel threads -> MMA: B operand ready (count EP)
   uint64_t* acc_full = act_full + 1;              // [MT] MMA -> channel threads of tile mt: accumulators ready
   uint64_t* pos_done = acc_full + MT;             // MMA -> channel threads: every round-0 MMA has read the h tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pos_done + 1);
+  uint64_t* h_free = pos_done + 1;                // [MT] channel threads of tile mt -> MMA: logits / pos of this tile consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_free + MT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +121,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       }
       mbar_init(act_full, EP);
       for (int m = 0; m < MT; ++m) mbar_init(&acc_full[m], 1);
+      for (int m = 0; m < MT; ++m) mbar_init(&h_free[m], EP / MT);
       mbar_init(pos_done, 1);
       fence_mbar_init();
     }
@@ -167,6 +169,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       uint32_t act_phase = 0;
+      uint32_t hfree_phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // Round 0 (B operand h): gamma1_pre = (W_g1 W_d2) h of every channel tile first — each committed to its own
         // barrier, so the channel warps of tile mt start epilogue 2 as early as possible — then pos = W_d2 h, which only
@@ -179,6 +182,12 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           if (step == 0 || step == 2 * MT) {
             mbar_wait(act_full, act_phase);
             act_phase ^= 1;
+            tc_fence_after_sync();
+          }
+          if (step < MT) {
+            // the accumulators of channel tile mt (logits in tmem_h, pos in tmem_pos) are released per channel tile: the
+            // gamma1 MMAs of tile i + 1 for mt = 0 run while the channel warps of mt = 1 are still in epilogue 3 of tile i
+            mbar_wait(&h_free[mt], hfree_phase ^ 1);
             tc_fence_after_sync();
           }
           const uint32_t acc = ((g == 0) ? tmem_pos : tmem_h) + mt * NT;
@@ -198,6 +207,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           if (g != 0) umma_commit(&acc_full[mt]);
           if (step == 2 * MT - 1) umma_commit(pos_done);   // the h tile may be overwritten by the next tile's stage A
         }
+        hfree_phase ^= 1;
       }
     }
   } else {
@@ -399,6 +409,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         if (has_next) {
           mbar_wait(pos_done, pos_phase);
           stage_a(s_rel_base + mb_next * NT);
+          mbar_arrive(act_full);   // this thread's part of the next h tile is written (fenced in stage_a)
         }
         if (POEM_VA_V_EARLY < 1) gather32(p.vtab, qi0, vv[0]);
         if (POEM_VA_V_EARLY < 2) gather32(p.vtab, qi0 + 1, vv[1]);
@@ -424,6 +435,7 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
           }
           // pass 2: exp, sum, weighted sum
           float sum = 0.f, acc = 0.f;
+          const float mx_s = mx * p.softmax_scale_log2e;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t a[16], ps[16];
@@ -433,19 +445,19 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t vp = vv[u][h * 8 + j];
-              const float e0 = fast_exp2((__uint_as_float(a[2 * j]) - mx) * p.softmax_scale_log2e);
-              const float e1 = fast_exp2((__uint_as_float(a[2 * j + 1]) - mx) * p.softmax_scale_log2e);
+              const float e0 = fast_exp2(fmaf(__uint_as_float(a[2 * j]), p.softmax_scale_log2e, -mx_s));
+              const float e1 = fast_exp2(fmaf(__uint_as_float(a[2 * j + 1]), p.softmax_scale_log2e, -mx_s));
               sum += e0 + e1;
-              acc = fmaf(e0, bf_lo(vp) + (__uint_as_float(ps[2 * j]) + bd2), acc);
-              acc = fmaf(e1, bf_hi(vp) + (__uint_as_float(ps[2 * j + 1]) + bd2), acc);
+              // b_d2 is constant over the neighbours: sum_j a_j (v_j + pos_j + b) = sum_j a_j (v_j + pos_j) + b
+              acc = fmaf(e0, bf_lo(vp) + __uint_as_float(ps[2 * j]), acc);
+              acc = fmaf(e1, bf_hi(vp) + __uint_as_float(ps[2 * j + 1]), acc);
             }
           }
-          if (qg < p.n_query) p.res[(size_t)qg * D + c] = f2op16(acc / sum);
+          if (qg < p.n_query) p.res[(size_t)qg * D + c] = f2op16(acc / sum + bd2);
         }
       }
       tc_fence_before_sync();
-      // this thread's TMEM reads of the tile are done and its part of the next h tile is written (fenced in stage_a)
-      if (has_next) mbar_arrive(act_full);
+      mbar_arrive(&h_free[mt]);   // this thread's TMEM reads of the tile (logits, pos of channel tile mt) are done
       mb = mb_next;
     }
   }

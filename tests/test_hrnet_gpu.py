@@ -72,7 +72,7 @@ def test_conv_nhwc(N, R, cin, cout, k, stride, relu, res, live):
     assert torch.isfinite(got).all()
     assert (got[..., cout:] == 0).all()                                  # padded channels stay exactly zero
     err = (got[..., :cout].permute(0, 3, 1, 2) - ref).abs().max().item()
-    assert err <= 1e-2 * max(1.0, ref.abs().max().item())                # bf16 output rounding, fp32 accumulation
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item())                # fp16 output rounding (2^-11), fp32 accumulation
 
 
 @pytest.mark.parametrize("N", [2, 5])
@@ -91,9 +91,9 @@ def test_stage4_matches_oracle(N):
         scale = w_.abs().max().item()
         print(f"stage4 N={N} branch {b}: max err {err.max().item():.4f} mean err {err.mean().item():.5f} "
               f"(|ref| max {scale:.2f}, mean {w_.abs().mean().item():.3f})")
-        # 3 modules x (8 bf16 convs per branch + fuse) with bf16 activations in between: 3e-2 of the output range
-        assert err.max().item() <= 3e-2 * scale
-        assert err.mean().item() <= 3e-3 * scale
+        # 3 modules x (8 fp16 convs per branch + fuse) with fp16 activations in between
+        assert err.max().item() <= 4e-3 * scale       # measured 1.2e-3 / 1e-4 of the range (fp16 activations between layers)
+        assert err.mean().item() <= 4e-4 * scale
 
 
 def test_stage4_matches_reference_golden():
@@ -110,11 +110,11 @@ def test_stage4_matches_reference_golden():
     want = [torch.from_numpy(z[f"y{b}"]) for b in range(4)]
     sub = [got[0][:, :, ::4, ::4], got[1][:, :, ::2, ::2], got[2], got[3]]
     for g_, w_ in zip(sub, want):
-        assert (g_ - w_).abs().max().item() <= 3e-2 * w_.abs().max().item()
+        assert (g_ - w_).abs().max().item() <= 4e-3 * w_.abs().max().item()
 
 
 # ------------------------------------------------------------------------------------------------ whole backbone (f1)
-def _check_maps(got, want, label, max_frac=5e-2, mean_frac=5e-3):
+def _check_maps(got, want, label, max_frac=6e-3, mean_frac=6e-4):
     for b, (g_, w_) in enumerate(zip(got, want)):
         assert g_.shape == w_.shape and torch.isfinite(g_).all()
         err = (g_ - w_).abs()
@@ -122,10 +122,10 @@ def _check_maps(got, want, label, max_frac=5e-2, mean_frac=5e-3):
         rel_l2 = ((g_ - w_).norm() / w_.norm()).item()
         print(f"{label} branch {b}: max err {err.max().item():.4f} mean err {err.mean().item():.5f} rel-L2 {rel_l2:.2e} "
               f"(|ref| max {scale:.2f}, mean {w_.abs().mean().item():.3f})")
-        # ~150 bf16 convolutions deep with bf16 activations in between
+        # ~150 fp16 convolutions deep with fp16 activations in between: measured max 2e-3 / mean 2e-4 of the range, rel-L2 1e-3
         assert err.max().item() <= max_frac * scale
         assert err.mean().item() <= mean_frac * scale
-        assert rel_l2 <= 2e-2
+        assert rel_l2 <= 3e-3
 
 
 @pytest.mark.parametrize("N", [1, 3])
@@ -217,12 +217,12 @@ def test_image_stage_matches_reference_golden():
     uv = res["pred_joints_uv"].cpu()
     duv = (uv - torch.from_numpy(z["pred_joints_uv"])).abs()
     print(f"pred_joints_uv golden: max |d| {duv.max().item():.4f} px, mean {duv.mean().item():.4f} px")
-    assert duv.max().item() <= 1.0 and duv.mean().item() <= 0.25          # 256-px image, bf16 conv stack
+    assert duv.max().item() <= 0.2 and duv.mean().item() <= 0.03          # 256-px image, fp16 conv stack (measured 0.057 / 0.008 px)
     intr, extr = synth.make_cameras(1, [n], meta["iseed"])
     rj = ImageStage.triangulate(res["pred_joints_uv"], intr, extr, [n]).cpu()
     drj = (rj - torch.from_numpy(z["ref_joints"])).norm(dim=-1)
     print(f"ref_joints golden: max {drj.max().item() * 1e3:.4f} mm")
-    assert drj.max().item() <= 1e-3                                       # 1 px at 0.6 m and f = 900 is 0.67 mm
+    assert drj.max().item() <= 1.5e-4                                     # 1 px at 0.6 m and f = 900 is 0.67 mm; measured 0.035 mm
 
 
 @pytest.mark.parametrize("views", [[2], [1, 3, 8], [10, 2]])
@@ -264,8 +264,8 @@ def test_heatmap_stage_matches_oracle(N):
     dh = (res["uv_hmap"].cpu() - want_h).abs()
     duv = (res["pred_joints_uv"].cpu() - want_uv).abs()
     print(f"heatmap N={N}: max |dh| {dh.max().item():.4f} mean {dh.mean().item():.5f}; uv max {duv.max().item():.4f} px")
-    assert dh.mean().item() <= 1e-2 and dh.max().item() <= 0.15
-    assert duv.max().item() <= 0.5
+    assert dh.mean().item() <= 1e-3 and dh.max().item() <= 1e-2          # measured 1.5e-4 / 1.1e-3
+    assert duv.max().item() <= 0.05                                      # measured 0.0125 px
 
 
 def test_images_to_mesh_pipeline():
@@ -296,4 +296,4 @@ def test_images_to_mesh_pipeline():
     got = head(mlvl_feat=feat, img_metas=m, reference_joints=ref_j.cuda())["all_coords_preds"].cpu()
     err = (got - want).norm(dim=-1)
     print(f"images->mesh: mean |ours - oracle| = {err.mean().item() * 1e3:.4f} mm, max {err.max().item() * 1e3:.3f} mm")
-    assert torch.isfinite(got).all() and err.mean().item() * 1e3 <= 1.0
+    assert torch.isfinite(got).all() and err.mean().item() * 1e3 <= 0.1   # north star: MPJPE within 0.1 mm (measured 0.06 mm)

@@ -33,8 +33,10 @@ def test_model_matches_oracle(views):
     err = (got["all_coords_preds"].cpu() - want["all_coords_preds"]).norm(dim=-1)
     print(f"model views={views}: uv max {duv:.3f} px, ref joints max {drj:.3f} mm, mesh mean {err.mean().item() * 1e3:.3f} mm "
           f"max {err.max().item() * 1e3:.2f} mm")
-    assert duv <= 0.5 and drj <= 0.5
-    assert torch.isfinite(got["all_coords_preds"]).all() and err.mean().item() * 1e3 <= 1.0
+    assert duv <= 0.05 and drj <= 0.05                   # measured 0.009 px / 0.007 mm
+    # north star: MPJPE within 0.1 mm of the reference (measured 0.015-0.06 mm; single points move by millimetres where
+    # the 0.007 mm shift of the hand centre flips a 32-NN set, see tests/test_parity_gpu.py)
+    assert torch.isfinite(got["all_coords_preds"]).all() and err.mean().item() * 1e3 <= 0.1
     for k in ("pred_joints_3d", "pred_verts_3d", "pred_joints_3d_rel", "pred_verts_3d_rel"):
         assert got[k].shape == want[k].shape
     assert torch.equal(got["pred_joints_3d"], got["all_coords_preds"][-1, :, :21])

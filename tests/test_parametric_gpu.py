@@ -128,9 +128,10 @@ def test_parametric_head_matches_reference_golden():
     """Whole medium_MANO head vs the real reference, O(1)-everywhere "stress" weights.
     Blocks 0..NB-2: same bounds as the non-parametric head.  Last block: the mesh is MANO(pose, shape) regressed from
     the last block's features, and `flat_verts` re-interprets (799, D) as (D, 799): one regressed value sums the
-    features of only ~3 queries, so a single 32-NN flip upstream (bf16 operands, see test_parity_gpu) moves a pose
-    parameter by O(0.05) and the whole hand with it.  In this adversarial regime the last block is therefore only
-    bounded loosely (measured: mean 4.0 mm, rotation matrices within 0.16, betas within 0.08), while the tail itself
+    features of only ~3 queries, so a single 32-NN flip upstream (5-10 % of the queries with these weights, see
+    test_parity_gpu) moves a pose parameter and the whole hand with it (lever ~0.1 m).  In this adversarial regime the
+    last block is therefore bounded on its parameters (measured with fp16 operands: mean 1.05 mm, worst vertex 6.6 mm,
+    rotation matrices within 0.018, betas within 0.018; bf16 operands in round 1: 4.0 mm / 0.16 / 0.08), while the tail itself
     is checked tightly: on the reference's own features (test_tail_kernel_matches_reference_golden) and for
     self-consistency here (returned mesh == MANO(returned pose, shape))."""
     dims, sd, feat, metas, ref_j, mano, gold = load_case()
@@ -148,8 +149,8 @@ def test_parametric_head_matches_reference_golden():
     dshape = (out["pred_shape"].cpu() - gold["pred_shape"]).abs().max().item()
     print("parametric head vs golden: mean per block (mm)", [round(e.mean().item() / MM, 4) for e in err],
           "max last (mm)", round(err[-1].max().item() / MM, 4), "rot diff", rot, "shape diff", dshape)
-    assert err[:-1].mean(dim=-1).max().item() <= 0.35 * MM
-    assert err[-1].mean().item() <= 8.0 * MM and rot <= 0.3 and dshape <= 0.15
+    assert err[:-1].mean(dim=-1).max().item() <= 0.06 * MM          # measured 0.016 / 0.028 mm
+    assert err[-1].mean().item() <= 2.5 * MM and rot <= 0.06 and dshape <= 0.06
     # the last block is root-centred on the hand centre exactly, and is the MANO mesh of the returned parameters
     assert torch.equal(got[-1, :, dims.center_idx], ref_j[:, dims.center_idx])
     v, j = orc.mano_forward(mano, out["pred_pose"].cpu().reshape(2, 48), out["pred_shape"].cpu(), dims.center_idx)
@@ -186,12 +187,13 @@ def test_parametric_head_init_weights_and_transformer_class():
     rot = same_rotation(out["pred_pose"].cpu(), want_pose)
     dshape = (out["pred_shape"].cpu() - want_shape).abs().max().item()
     print("  rot diff", rot, "shape diff", dshape, "|dMPJPE| last block (mm)", mpjpe_shift(got[-1], want[-1]) / MM)
-    # blocks 0..NB-2 inside the north-star bounds; the MANO mesh of the last block amplifies the bf16 feature error
-    # through the regressed rotations (lever ~0.1 m): measured mean 0.36 mm, worst vertex 1.9 mm (2.6e-3 relative)
-    assert rel[:-1].max().item() <= 1e-3 and err[:-1].mean(dim=(-1, -2)).max().item() <= 0.1 * MM
-    assert rel[-1].max().item() <= 6e-3 and err[-1].mean().item() <= 0.7 * MM
-    assert mpjpe_shift(got[-1], want[-1]) <= 0.2 * MM
-    assert rot <= 2e-2 and dshape <= 2e-2
+    # every block inside the north-star bound (1e-3 relative per point), the MANO mesh of the last block included: the
+    # regressed rotations amplify the feature error with a ~0.1 m lever, measured worst vertex 0.13 mm = 2.5e-4 relative
+    # (fp16 operands; bf16 operands in round 1: 1.9 mm = 2.6e-3)
+    assert rel.max().item() <= 1e-3 and err[:-1].mean(dim=(-1, -2)).max().item() <= 0.03 * MM
+    assert err[-1].mean().item() <= 0.08 * MM
+    assert mpjpe_shift(got[-1], want[-1]) <= 0.02 * MM
+    assert rot <= 3e-3 and dshape <= 3e-3
     # PtEmbedTRv4(query_xyz, query_feat, pt_xyz, pt_feats) -> (xyz (NB,B,799,3) normalised, pred_pose (B,48), pred_shape)
     tr = PtEmbedTRv4(dims, mano_params=mano)
     tr.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=True)
@@ -203,7 +205,7 @@ def test_parametric_head_init_weights_and_transformer_class():
     d_last = ((xyz[-1].cpu() + centre[:, None]) - want[-1]).norm(dim=-1)
     d_prev = ((xyz[:-1].cpu() * dims.radius + centre[None, :, None]) - want[:-1]).norm(dim=-1)
     print("  transformer class: last block max (mm)", d_last.max().item() / MM, "previous blocks mean (mm)", d_prev.mean().item() / MM)
-    assert d_last.max().item() <= 4.0 * MM and d_prev.mean().item() <= 0.1 * MM
+    assert d_last.max().item() <= 0.6 * MM and d_prev.mean().item() <= 0.03 * MM      # measured 0.14 / 0.007 mm
 
 
 def test_parametric_properties_at_benchmark_size():
