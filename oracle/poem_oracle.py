@@ -273,13 +273,20 @@ def axis_angle_to_rotmat(aa):
                         2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=-1).reshape(aa.shape[:-1] + (3, 3))
 
 
+# MANO kinematic tree (parent of each of the 16 joints), the fingertip vertices manotorch v0.0.2 appends for a right hand
+# and its 16 joints + 5 tips -> 21-joint hand order (third-party constants, restated; the product keeps its own copy in
+# poem_v2_b200/params.py and tests/test_oracle.py asserts the two agree)
+MANO_PARENTS = (-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14)
+MANO_TIP_VERTS = (745, 317, 444, 556, 673)
+MANO_JOINT_ORDER = (0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20)
+
+
 def mano_forward(mano, pose_aa, betas, center_idx=None):
     """manotorch v0.0.2 `ManoLayer(rot_mode="axisang", use_pca=False, flat_hand_mean=True, center_idx=...)` —
     the MANO linear-blend-skinning forward (Romero et al. 2017; third-party, absent offline, restated):
     shape blend -> joints -> pose blend -> kinematic chain -> skinning -> 16 joints + 5 tip vertices reordered to
     the 21-joint convention -> optional root-centring.  `mano`: dict of `synth.synthetic_mano()` roles.
     Returns verts (B,778,3), joints (B,21,3)."""
-    from poem_v2_b200.synth import MANO_JOINT_ORDER, MANO_PARENTS, MANO_TIP_VERTS
     B = pose_aa.shape[0]
     R = axis_angle_to_rotmat(pose_aa.reshape(B, 16, 3))                         # (B,16,3,3)
     pose_map = (R[:, 1:] - torch.eye(3, dtype=R.dtype)).reshape(B, 135)

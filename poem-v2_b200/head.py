@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nat
-from . import synth
+from . import params as _params
 from .config import HeadDims, dims_from_cfg
 from .pack import MANO_KEYS, PackedManoTail, PackedWeights, mano_zero_pose_template
 
@@ -81,7 +81,7 @@ class _NativeDecoder(nn.Module):
         self._mano = None if mano_params is None else _resolve_mano(dims, mano_params)
         self._packed_mano = None
         self._key_prefix = key_prefix           # "" for the head, "transformer." stripped for PtEmbedTRv4
-        shapes = synth.live_param_shapes(dims)
+        shapes = _params.live_param_shapes(dims)
         self._live = []
         for name, shape in shapes.items():
             if not name.startswith(key_prefix):
@@ -89,7 +89,7 @@ class _NativeDecoder(nn.Module):
             local = name[len(key_prefix):]
             self._live.append(local)
             self.add_param(local, torch.zeros(shape))
-        bps, a_xyz, a_idx = synth.load_assets()
+        bps, a_xyz, a_idx = _params.load_assets()
         self.register_buffer("bps_points", bps, persistent=False)
         self.register_buffer("anchor_xyz", a_xyz, persistent=False)
         self.register_buffer("anchor_idx", a_idx, persistent=False)
@@ -158,7 +158,7 @@ class _NativeDecoder(nn.Module):
                 else:
                     self._template = _resolve_template(self.dims, None)
             full = {}
-            for name, shape in synth.live_param_shapes(self.dims).items():   # head-only keys absent for the TR class
+            for name, shape in _params.live_param_shapes(self.dims).items():   # head-only keys absent for the TR class
                 full[name] = torch.zeros(shape)
             full.update(self.live_state())
             self._packed = PackedWeights(full, self.dims, device, self._template, self.bps_points, self.anchor_xyz,

@@ -193,7 +193,7 @@ def mano_zero_pose_template(mano, center_idx=9):
     """(799,3) joints ‖ vertices of the MANO layer at zero pose / zero shape, centred on joint `center_idx` — what the
     reference head recomputes on every forward (ptEmb_head.py:885-891).  At zero pose the skinning is the identity:
     vertices = v_template, the 16 joints = J_regressor · v_template, plus the 5 fingertip vertices, re-ordered."""
-    from .synth import MANO_JOINT_ORDER, MANO_TIP_VERTS
+    from .params import MANO_JOINT_ORDER, MANO_TIP_VERTS
     v = mano["v_template"].detach().to("cpu", torch.float64).reshape(778, 3)
     j16 = mano["J_regressor"].detach().to("cpu", torch.float64).reshape(16, 778) @ v
     j21 = torch.cat([j16, v[list(MANO_TIP_VERTS)]])[list(MANO_JOINT_ORDER)]
