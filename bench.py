@@ -284,6 +284,81 @@ def timed_head(size, V, B, dev, rank, sync, n_sets=2, min_ms=300.0, use_graph=Tr
     return ms, steps, ok
 
 
+def image_sharded_pass(dev, rank, world, sync, max_over_ranks, V=8, steps=20):
+    """SURVEY §8e, fewer samples than GPUs: ONE sample with V views served by `world` GPUs.  The B*V images are split
+    over the ranks (`shard.image_bounds`); every rank runs backbone + feat_decode + heatmap stage on its images, one
+    NCCL all_gather exchanges the (., 160, 16, 16) feature maps and the 2-D joints — the single exchange step of the
+    path — then every rank triangulates and runs the decoder on the whole sample (replicated; no further collective)."""
+    import torch.distributed as dist
+    from poem_v2_b200 import shard, synth
+    from poem_v2_b200.config import release_dims
+    from poem_v2_b200.hrnet import ImageStage
+    from poem_v2_b200.head import POEM_Generalized_Head
+    dims = release_dims("medium")
+    sd = synth.make_model_state_dict(dims, 0)
+    stage = ImageStage()
+    from poem_v2_b200.model import _IMAGE_PREFIXES
+    stage.load_state_dict({k: v for k, v in sd.items() if k.startswith(_IMAGE_PREFIXES)}, strict=True)
+    stage = stage.to(dev).eval()
+    head = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    head.load_state_dict({k[len("ptEmb_head."):]: v for k, v in sd.items() if k.startswith("ptEmb_head.")}, strict=True)
+    head = head.to(dev).eval()
+    batch = synth.make_batch(1, [V], 5)                      # same seed on every rank
+    img = batch["image"].reshape(-1, 3, 256, 256)
+    bounds = shard.image_bounds(V, world)
+    i0, i1 = bounds[rank]
+    img_local = img[i0:i1].to(dev)
+    intr = batch["target_cam_intr"].reshape(-1, 3, 3).to(dev)
+    extr = batch["target_cam_extr"].reshape(-1, 4, 4).to(dev)
+    metas = {"inp_img_shape": (256, 256), "cam_intr": intr, "cam_extr": extr, "master_id": [0], "cam_view_num": np.array([V])}
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_gather = []
+
+    def step(timed_gather=False):
+        if i1 > i0:
+            res = stage(img_local, return_uv=True)
+            feat_l, uv_l = res["mlvl_feat"], res["pred_joints_uv"]
+        else:
+            feat_l = torch.zeros(0, 160, 16, 16, device=dev)
+            uv_l = torch.zeros(0, 21, 2, device=dev)
+        if timed_gather:
+            ea.record()
+        feat = shard.gather_features(feat_l, V, bounds)
+        uv = shard.gather_features(uv_l, V, bounds)
+        if timed_gather:
+            eb.record()
+        ref_j = ImageStage.triangulate(uv, intr, extr, [V])
+        out = head(mlvl_feat=feat, img_metas=metas, reference_joints=ref_j)["all_coords_preds"]
+        if timed_gather:
+            torch.cuda.synchronize()
+            ms_gather.append(ea.elapsed_time(eb))
+        return out
+
+    for _ in range(3):
+        out = step()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    sync()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    for _ in range(5):
+        step(timed_gather=True)
+    sync()
+    g_ms = max_over_ranks(sorted(ms_gather)[len(ms_gather) // 2])
+    pad = max(b - a for a, b in bounds)
+    nbytes = world * pad * (160 * 16 * 16 + 21 * 2) * 4
+    ok = bool(torch.isfinite(out).all())
+    del stage, head
+    torch.cuda.empty_cache()
+    return {"workload": f"POEM-medium, 1 sample x {V} views, images sharded over {world} GPUs: backbone + feat_decode + heatmap on "
+                        f"{pad} image(s) per GPU, NCCL all_gather of the feature maps and 2-D joints, DLT + decoder replicated",
+            "ms_per_step": ms, "samples_per_s": 1e3 / ms, "all_gather_ms": g_ms, "all_gather_bytes_per_step": nbytes,
+            "finite": ok, "launch": "eager launches"}
+
+
 def image_half_lines(dev, peaks, n_images=256):
     """SURVEY §8a row a17 / §8f row f1 as sub-lines of the bench: HRNet-W40 stage 4 and the whole backbone on
     `n_images` synthetic images resident in HBM, with the roofline of each (tensor-bound by FLOP count; the C <= 80
@@ -564,6 +639,8 @@ def main():
                     r_["frac_of_path_roofline"] = r_["samples_per_s"] / n_gpus * fl[k_] / (pk["bf16_tflops"] * 1e12)
             named["large_sweep_gb64"] = {"workload": "BASELINE configs[4] POEM-large, view sweep 2-10, GLOBAL batch 64",
                                          "views": sweep}
+            if world > 1:
+                named["image_sharded_b1_v8"] = image_sharded_pass(dev, rank, world, barrier, max_over_ranks)
             named["scaling"] = "strong"
             named["launch"] = "CUDA-graph replay of the captured forward, 2 input sets rotated, >= 0.3 s timed per entry"
         except Exception as e:  # noqa: BLE001

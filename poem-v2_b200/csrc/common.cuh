@@ -15,6 +15,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining.  `pdl_wait` blocks until the predecessor grid has
+// completed and its memory is visible (a no-op for a normal launch) and must precede every global access that depends
+// on it; `pdl_trigger` lets the successor's CTAs be scheduled as soon as SM resources free up, so its prologue
+// (barrier init, TMEM allocation, descriptor prefetch, weight / bias preloads) overlaps this kernel's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -162,6 +162,9 @@ gemm_op16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, bias preload = weights) is independent of the predecessor kernel
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================

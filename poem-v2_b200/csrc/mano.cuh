@@ -16,6 +16,8 @@ namespace poem {
 // ------------------------------------------------------------------------------------------------
 __global__ void flat_verts_kernel(const float* __restrict__ feats, const float* __restrict__ w,
                                   const float* __restrict__ b, float* __restrict__ flat, int Q, int rows) {
+  pdl_wait();
+  pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -47,6 +49,8 @@ constexpr int kManoThreads = 1024, kManoWarps = kManoThreads / 32;   // one bloc
 
 // One block per sample.
 __global__ void __launch_bounds__(kManoThreads) mano_tail_kernel(const ManoTailArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float par[106];
   __shared__ float R[kManoJoints][9];
   __shared__ float pm[135];

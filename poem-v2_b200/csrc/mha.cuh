@@ -123,6 +123,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q,   // [B*Lq rows, l
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;   // buffer i at columns [128*i, 128*i + 128)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -82,9 +83,39 @@ struct TagScope {
 #define LAUNCH_CHECK(name)                                                                       \
   do {                                                                                           \
     cudaError_t _e = cudaGetLastError();                                                         \
+    if (g_launch_err != cudaSuccess) _e = g_launch_err, g_launch_err = cudaSuccess;              \
     prof_end(name);                                                                              \
     if (_e != cudaSuccess) return fail(POEM_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
+
+// Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor drains; every
+// kernel launched this way calls pdl_wait() before its first dependent global access (common.cuh).  POEM_PDL=0 in the
+// environment falls back to plain launches.
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("POEM_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+static thread_local cudaError_t g_launch_err = cudaSuccess;
+template <typename... Params, typename... Args>
+static void launch_pdl(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && !g_prof_on) ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+  if (e != cudaSuccess) g_launch_err = e;
+}
 
 extern "C" long long poem_kernel_launches(void) { return g_launches.load(); }
 extern "C" void poem_profile_enable(int on) {
@@ -237,9 +268,9 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, int M, i
   }
   prof_begin(st);
   if (ep.res_mode != RES_NONE)
-    gemm_op16_tc_kernel<BN, true><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
+    launch_pdl(gemm_op16_tc_kernel<BN, true>, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), st, ta, tw, M, N, K, ep, conv, pipe);
   else
-    gemm_op16_tc_kernel<BN, false><<<grid, GEMM_THREADS, smem, st>>>(ta, tw, M, N, K, ep, conv, pipe);
+    launch_pdl(gemm_op16_tc_kernel<BN, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)(smem), st, ta, tw, M, N, K, ep, conv, pipe);
   LAUNCH_CHECK("gemm_op16_tc_kernel");
   return POEM_OK;
 }
@@ -867,7 +898,7 @@ static int launch_mha_hd(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   dim3 grid((unsigned)(((Lq + MHA_BQ - 1) / MHA_BQ) * n_heads * B));   // full tiles first, partial tiles last
   const float scale_log2e = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
   prof_begin(st);
-  mha_fwd_tc_kernel<HD><<<grid, MHA_THREADS, MhaCfg<HD>::kSmemBytes, st>>>(tq, tk, tv, ctx, ld_ctx, Lq, Lk, q_col0,
+  launch_pdl(mha_fwd_tc_kernel<HD>, dim3(grid), dim3(MHA_THREADS), (size_t)(MhaCfg<HD>::kSmemBytes), st, tq, tk, tv, ctx, ld_ctx, Lq, Lk, q_col0,
                                                                            k_col0, v_col0, scale_log2e, n_heads);
   LAUNCH_CHECK("mha_fwd_tc_kernel");
   return POEM_OK;
@@ -911,7 +942,7 @@ static int launch_knn(const float* q, const float* r, int* idx, int B, int Lq, i
   const int threads = 256;
   const int blocks = (total * 32 + threads - 1) / threads;
   prof_begin(st);
-  knn32_kernel<<<blocks, threads, 0, st>>>(q, r, idx, Lq, Lr, total);
+  launch_pdl(knn32_kernel, dim3(blocks), dim3(threads), (size_t)(0), st, q, r, idx, Lq, Lr, total);
   LAUNCH_CHECK("knn32_kernel");
   return POEM_OK;
 }
@@ -921,7 +952,7 @@ static int launch_knn_bps(const float* q, const float* r, const int* perm, const
   const int total = B * Lq;
   const int threads = 256;
   prof_begin(st);
-  knn32_bps_kernel<<<(total * 32 + threads - 1) / threads, threads, 0, st>>>(q, r, perm, boxes, idx, Lq, Lr, total);
+  launch_pdl(knn32_bps_kernel, dim3((total * 32 + threads - 1) / threads), dim3(threads), (size_t)(0), st, q, r, perm, boxes, idx, Lq, Lr, total);
   LAUNCH_CHECK("knn32_bps_kernel");
   return POEM_OK;
 }
@@ -941,7 +972,7 @@ static int launch_layernorm(const float* x, const float* g, const float* b, floa
   if (D % 32 || D > 1024) return fail(POEM_E_BADDIM, "layernorm: D=%d", D);
   const int threads = 256;
   prof_begin(st);
-  layernorm_kernel<<<(rows * 32 + threads - 1) / threads, threads, 0, st>>>(x, g, b, y32, y16, rows, D, 1e-12f);
+  launch_pdl(layernorm_kernel, dim3((rows * 32 + threads - 1) / threads), dim3(threads), (size_t)(0), st, x, g, b, y32, y16, rows, D, 1e-12f);
   LAUNCH_CHECK("layernorm_kernel");
   return POEM_OK;
 }
@@ -994,7 +1025,7 @@ static int upload_view_tables(const int32_t* host_views, int B, int NV, int P, i
     ViewCountsParam vp;
     for (int b = 0; b < B; ++b) vp.n[b] = host_views[b];
     prof_begin(st);
-    view_tables_kernel<<<1, 256, 0, st>>>(vp, B, NV, P, dev);
+    launch_pdl(view_tables_kernel, dim3(1), dim3(256), (size_t)(0), st, vp, B, NV, P, dev);
     LAUNCH_CHECK("view_tables_kernel");
   } else {
     // a memcpy node would keep a pointer into this stack frame: refuse to be captured into a CUDA graph
@@ -1021,7 +1052,7 @@ static int launch_project_sample(const float* xmap, const float* intr, const flo
   if (P != SAMPLE_THREADS * 8) return fail(POEM_E_BADDIM, "sampler is specialised for P=4096 (got %d)", P);
   if (D % SAMPLE_CH || P % D) return fail(POEM_E_BADDIM, "sampler: D=%d must divide P and be a multiple of 32", D);
   prof_begin(st);
-  camera_prep_kernel<<<(NV + 63) / 64, 64, 0, st>>>(intr, extr, proj, NV);
+  launch_pdl(camera_prep_kernel, dim3((NV + 63) / 64), dim3(64), (size_t)(0), st, intr, extr, proj, NV);
   LAUNCH_CHECK("camera_prep_kernel");
   const size_t smem = (size_t)SAMPLE_PITCH * fh * fw * sizeof(float);
   if (smem > 48 * 1024) return fail(POEM_E_BADDIM, "feature map %dx%d too large for the sampler", fh, fw);
@@ -1113,7 +1144,7 @@ static int launch_sample_merge(const PoemWeights* w, const SmParams& sp, cudaStr
   POEM_TRY(make_tmap_op16(&t0b, w->merge0b.w, D / 2, D, D, 64, (uint32_t)(D / 2 < 128 ? D / 2 : 128)));
   const int grid = sp.n_tiles < num_sms() ? sp.n_tiles : num_sms();
   prof_begin(st);
-  sample_merge_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t0a, t0b, sp);
+  launch_pdl(sample_merge_kernel<D>, dim3(grid), dim3(Cfg::THREADS), (size_t)(Cfg::SMEM_BYTES), st, t0a, t0b, sp);
   LAUNCH_CHECK("sample_merge_kernel");
   return POEM_OK;
 }
@@ -1139,7 +1170,7 @@ static int launch_vecattn_fused(const PoemVecAttn* w, const VaParams& prm, cudaS
   const int slots = num_sms() * Cfg::CTAS_PER_SM;
   const int grid = tiles < slots ? tiles : slots;
   prof_begin(st);
-  va_fused_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(t1, t2, t3, prm);
+  launch_pdl(va_fused_kernel<D>, dim3(grid), dim3(Cfg::THREADS), (size_t)(Cfg::SMEM_BYTES), st, t1, t2, t3, prm);
   LAUNCH_CHECK("va_fused_kernel");
   return POEM_OK;
 }
@@ -1447,7 +1478,7 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
       if (!k.reg2_w || !k.reg2_b) return fail(POEM_E_NULL, "block %d: reg_branch.2 missing", i);
       const int threads = 256;
       prof_begin(st);
-      reg_out_kernel<<<((size_t)BQ * 32 + threads - 1) / threads, threads, 0, st>>>(
+      launch_pdl(reg_out_kernel, dim3(((size_t)BQ * 32 + threads - 1) / threads), dim3(threads), (size_t)(0), st, 
           p.r1_16, k.reg2_w, k.reg2_b, xyz_in, xyz_out, coords_out + (size_t)i * BQ * 3, centre, dims->radius, Q, D,
           BQ);
       LAUNCH_CHECK("reg_out_kernel");
@@ -1491,10 +1522,10 @@ extern "C" int poem_transformer_forward(const PoemDims* dims, const PoemWeights*
   CUDA_TRY(cudaMemcpyAsync(p.xyz, query_xyz, BQ * 3 * 4, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(p.qf32, query_feat, BQ * D * 4, cudaMemcpyDeviceToDevice, st));
   prof_begin(st);
-  f32_to_op16_kernel<<<(unsigned)((BQ * D + 255) / 256), 256, 0, st>>>(query_feat, p.qf16, BQ * D);
+  launch_pdl(f32_to_op16_kernel, dim3((unsigned)((BQ * D + 255) / 256)), dim3(256), (size_t)(0), st, query_feat, p.qf16, BQ * D);
   LAUNCH_CHECK("f32_to_op16_kernel");
   prof_begin(st);
-  f32_to_op16_kernel<<<(unsigned)((BP * D + 255) / 256), 256, 0, st>>>(pt_feats, p.ptf, BP * D);
+  launch_pdl(f32_to_op16_kernel, dim3((unsigned)((BP * D + 255) / 256)), dim3(256), (size_t)(0), st, pt_feats, p.ptf, BP * D);
   LAUNCH_CHECK("f32_to_op16_kernel");
   return run_blocks(dims, w, B, p, nullptr, out_xyz, out_feats, /*pt_is_bps=*/false, st);
 }
@@ -1510,7 +1541,7 @@ static int launch_parametric_tail(const PoemDims* dims, const PoemManoTail* m, i
   if (dims->center_idx < 0 || dims->center_idx >= 21) return fail(POEM_E_BADDIM, "center_idx=%d", dims->center_idx);
   const int rows = B * dims->embed_dims;
   prof_begin(st);
-  flat_verts_kernel<<<(unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, st>>>(feats, m->flat_w, m->flat_b, flat,
+  launch_pdl(flat_verts_kernel, dim3((unsigned)(((size_t)rows * 32 + 255) / 256)), dim3(256), (size_t)(0), st, feats, m->flat_w, m->flat_b, flat,
                                                                                  dims->n_query, rows);
   LAUNCH_CHECK("flat_verts_kernel");
   ManoTailArgs a;
@@ -1521,7 +1552,7 @@ static int launch_parametric_tail(const PoemDims* dims, const PoemManoTail* m, i
   a.coords = coords, a.pose_out = pose, a.shape_out = shape;
   a.D = dims->embed_dims, a.center_idx = dims->center_idx;
   prof_begin(st);
-  mano_tail_kernel<<<B, kManoThreads, 0, st>>>(a);
+  launch_pdl(mano_tail_kernel, dim3(B), dim3(kManoThreads), (size_t)(0), st, a);
   LAUNCH_CHECK("mano_tail_kernel");
   return POEM_OK;
 }
@@ -1600,7 +1631,7 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   {
     dim3 grid((F + 31) / 32, (C + 31) / 32, NV), block(32, 8);
     prof_begin(st);
-    nchw_to_rows_op16_kernel<<<grid, block, 0, st>>>(in->mlvl_feat, h.featT, C, F);
+    launch_pdl(nchw_to_rows_op16_kernel, dim3(grid), dim3(block), (size_t)(0), st, in->mlvl_feat, h.featT, C, F);
     LAUNCH_CHECK("nchw_to_rows_op16_kernel");
     GemmEpilogue e = epi_default(D);
     e.bias = w->input_proj.b;
@@ -1618,12 +1649,12 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   // ---- a3/a7: centre, normalised point sets
   prof_begin(st);
   // the hand centre is ALWAYS joint 9 (ptEmb_head.py:873); dims->center_idx only roots the MANO layer (a16)
-  gather_centre_kernel<<<(B * 3 + 127) / 128, 128, 0, st>>>(in->reference_joints, h.centre, kHandCentreJoint, B);
+  launch_pdl(gather_centre_kernel, dim3((B * 3 + 127) / 128), dim3(128), (size_t)(0), st, in->reference_joints, h.centre, kHandCentreJoint, B);
   LAUNCH_CHECK("gather_centre_kernel");
   {
     const int total = B * (P + Q) * 3;
     prof_begin(st);
-    normalise_points_kernel<<<(total + 255) / 256, 256, 0, st>>>(w->bps, w->template_xyz, h.centre, p.pt_xyz, p.xyz, P,
+    launch_pdl(normalise_points_kernel, dim3((total + 255) / 256), dim3(256), (size_t)(0), st, w->bps, w->template_xyz, h.centre, p.pt_xyz, p.xyz, P,
                                                                 Q, dims->radius, B, w->bps_chunk_box ? w->bps_perm : nullptr,
                                                                 p.pt_xyz_sorted);
     LAUNCH_CHECK("normalise_points_kernel");
@@ -1634,10 +1665,10 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   if (fused_merge) {
     if (!w->merge0a.w || !w->merge0a.b || !w->merge0b.w || !w->merge0b.b) return fail(POEM_E_NULL, "merge_net_feature.0 missing");
     prof_begin(st);
-    camera_prep_kernel<<<(NV + 63) / 64, 64, 0, st>>>(in->cam_intr, in->cam_extr, h.proj, NV);
+    launch_pdl(camera_prep_kernel, dim3((NV + 63) / 64), dim3(64), (size_t)(0), st, in->cam_intr, in->cam_extr, h.proj, NV);
     LAUNCH_CHECK("camera_prep_kernel");
     prof_begin(st);
-    sample_taps_kernel<<<(unsigned)(((size_t)NV * P + 255) / 256), 256, 0, st>>>(h.proj, w->bps, h.centre, vt.img_sample, h.taps, NV,
+    launch_pdl(sample_taps_kernel, dim3((unsigned)(((size_t)NV * P + 255) / 256)), dim3(256), (size_t)(0), st, h.proj, w->bps, h.centre, vt.img_sample, h.taps, NV,
                                                                                dims->feat_h, dims->feat_w, 1.0f / in->inp_img_w,
                                                                                1.0f / in->inp_img_h,
                                                                                (D == 128 ? SmCfg<128>::SLOTS : SmCfg<256>::SLOTS) * 4);
@@ -1698,7 +1729,7 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
   {
     const size_t total = (size_t)BQ * D;
     prof_begin(st);
-    broadcast_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w->query_embed, p.qf32, p.qf16, Q * D,
+    launch_pdl(broadcast_queries_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, w->query_embed, p.qf32, p.qf16, Q * D,
                                                                              total);
     LAUNCH_CHECK("broadcast_queries_kernel");
   }

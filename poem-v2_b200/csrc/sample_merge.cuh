@@ -40,6 +40,8 @@ __global__ void sample_taps_kernel(const float* __restrict__ proj, const float* 
                                    const float* __restrict__ centre, const int* __restrict__ img_sample,
                                    uint32_t* __restrict__ taps, int n_img, int FH, int FW, float inv_w, float inv_h,
                                    int pixel_pitch_bytes) {
+  pdl_wait();
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_img * SM_P) return;
   const int img = idx / SM_P, p = idx - img * SM_P;
@@ -196,6 +198,8 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the setup above only touched weights (biases) and on-chip state
+  pdl_trigger();
   const uint32_t tmem_acc1 = tmem_base;          // D columns
   const uint32_t tmem_acc2 = tmem_base + D;      // H columns
 

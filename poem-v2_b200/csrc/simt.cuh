@@ -11,6 +11,8 @@ namespace poem {
 // ------------------------------------------------------------------------------------------------
 __global__ void nchw_to_rows_op16_kernel(const float* __restrict__ feat, op16* __restrict__ rows, int C,
                                          int HW) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -33,6 +35,8 @@ __global__ void nchw_to_rows_op16_kernel(const float* __restrict__ feat, op16* _
 // ------------------------------------------------------------------------------------------------
 __global__ void camera_prep_kernel(const float* __restrict__ intr, const float* __restrict__ extr,
                                    float* __restrict__ proj, int n_img) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img) return;
   float a[4][8];
@@ -255,6 +259,8 @@ __global__ void merge_reduce_kernel(const op16* __restrict__ m, const int* __res
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ y_f32,
                                  op16* __restrict__ y_op16, int rows, int D, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -294,6 +300,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // ------------------------------------------------------------------------------------------------
 __global__ void knn32_kernel(const float* __restrict__ query, const float* __restrict__ ref, int* __restrict__ idx_out,
                              int Lq, int Lr, int n_query_total) {
+  pdl_wait();
+  pdl_trigger();
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (qi >= n_query_total) return;
@@ -349,6 +357,8 @@ __global__ void knn32_kernel(const float* __restrict__ query, const float* __res
 __global__ void knn32_bps_kernel(const float* __restrict__ query, const float* __restrict__ ref_sorted,
                                  const int* __restrict__ perm, const float* __restrict__ boxes,
                                  int* __restrict__ idx_out, int Lq, int Lr, int n_query_total) {
+  pdl_wait();
+  pdl_trigger();
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (qi >= n_query_total) return;
@@ -538,6 +548,8 @@ __global__ void reg_out_kernel(const op16* __restrict__ h, const float* __restri
                                const float* __restrict__ b2, const float* __restrict__ xyz_in,
                                float* __restrict__ xyz_out, float* __restrict__ coords_out,
                                const float* __restrict__ centre, float radius, int Lq, int D, int n_query) {
+  pdl_wait();
+  pdl_trigger();
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (qi >= n_query) return;
@@ -576,6 +588,8 @@ __global__ void normalise_points_kernel(const float* __restrict__ bps, const flo
                                         const float* __restrict__ centre, float* __restrict__ pt_xyz,
                                         float* __restrict__ q_xyz, int P, int Q, float radius, int B,
                                         const int* __restrict__ perm, float* __restrict__ pt_xyz_sorted) {
+  pdl_wait();
+  pdl_trigger();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = (P + Q) * 3;
   if (gid >= B * per) return;
@@ -598,11 +612,15 @@ __global__ void normalise_points_kernel(const float* __restrict__ bps, const flo
 // centre[b] = reference_joints[b, centre_idx]
 __global__ void gather_centre_kernel(const float* __restrict__ ref_joints, float* __restrict__ centre, int centre_idx,
                                      int B) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * 3) centre[i] = ref_joints[(i / 3) * 63 + centre_idx * 3 + (i % 3)];
 }
 
 __global__ void f32_to_op16_kernel(const float* __restrict__ x, op16* __restrict__ y, size_t n) {
+  pdl_wait();
+  pdl_trigger();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = f2op16(x[i]);
 }
@@ -610,6 +628,8 @@ __global__ void f32_to_op16_kernel(const float* __restrict__ x, op16* __restrict
 // broadcast the (Q,D) query embedding table to (B*Q, D) fp32 + op16
 __global__ void broadcast_queries_kernel(const float* __restrict__ table, float* __restrict__ out_f32,
                                          op16* __restrict__ out_op16, int QD, size_t total) {
+  pdl_wait();
+  pdl_trigger();
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const float v = table[gid % QD];
@@ -629,6 +649,8 @@ __host__ __device__ inline int merge_tiles_of(int n_views, int P) {
   return (P + tok - 1) / tok;
 }
 __global__ void view_tables_kernel(ViewCountsParam vc, int B, int NV, int P, int* __restrict__ dev) {
+  pdl_wait();
+  pdl_trigger();
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     int first = 0, tiles = 0;
     for (int i = 0; i < b; ++i) first += vc.n[i], tiles += merge_tiles_of(vc.n[i], P);
