@@ -37,7 +37,8 @@ typedef uint16_t poem_op16;
 
 /* Dimensions read from cfg.MODEL.HEAD (ptEmb_head.py:57-76,686-695; ptEmb_transformer.py:312-324). */
 typedef struct PoemDims {
-  int32_t embed_dims;   /* D: 128 | 256 | 512 | 1024 */
+  int32_t embed_dims;   /* D: 128 | 256 | 512 (POEM-small / -medium / -large); 1024 (POEM-huge, head dim 256) is rejected:
+                         * poem_workspace_bytes returns 0 and every entry point POEM_E_BADDIM */
   int32_t in_channels;  /* C: 160 */
   int32_t n_sample;     /* P: 4096 */
   int32_t n_query;      /* Q: 799 */

@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpoem_b200.so")
+LIB_PATH = os.environ.get("POEM_B200_LIB", os.path.join(CSRC, "libpoem_b200.so"))   # override: kernel experiments
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["poem_b200.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "conv3x3.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh", "hrnet.cuh", "mano.cuh"]

@@ -1248,7 +1248,10 @@ struct HeadPlan {    // everything in front of the blocks
 static int check_dims(const PoemDims* d) {
   if (!d) return fail(POEM_E_NULL, "dims is NULL");
   const int D = d->embed_dims;
-  if (!(D == 128 || D == 256 || D == 512 || D == 1024)) return fail(POEM_E_BADDIM, "embed_dims=%d unsupported", D);
+  if (D == 1024)   // POEM-huge (config/release/train_huge.yaml:188-190: D = 1024, 4 heads -> head dim 256)
+    return fail(POEM_E_BADDIM, "embed_dims=1024 (POEM-huge) is not built: the attention kernel has no head-dim-256 instantiation and "
+                               "the fused vector attention no D=1024 one");
+  if (!(D == 128 || D == 256 || D == 512)) return fail(POEM_E_BADDIM, "embed_dims=%d unsupported (128, 256, 512)", D);
   if (d->n_heads <= 0 || D % d->n_heads) return fail(POEM_E_BADDIM, "n_heads=%d", d->n_heads);
   const int hd = D / d->n_heads;
   if (!(hd == 32 || hd == 64 || hd == 128)) return fail(POEM_E_BADDIM, "head dim %d unsupported", hd);

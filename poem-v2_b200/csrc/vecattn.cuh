@@ -303,22 +303,30 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
       static_assert(TG * (D / 8) == EP, "stage A mapping: 8 tokens x 8 channels per channel thread");
       const int tg = et % TG;
       const int ch = (et / TG) * 8;
-      float4 wv[8];
+      // packed fp16 arithmetic (HFMA2: two channels per instruction): h is rounded to fp16 for the tensor core anyway,
+      // and the token-level MLPs are the precision-insensitive part of the path (scripts/precision_study2.py)
+      op16x2 wx[4], wy[4], wz[4], wb[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) wv[i] = s_wd1[ch + i];
+      for (int k = 0; k < 4; ++k) {
+        const float4 w0 = s_wd1[ch + 2 * k], w1 = s_wd1[ch + 2 * k + 1];
+        wx[k] = __floats2half2_rn(w0.x, w1.x);
+        wy[k] = __floats2half2_rn(w0.y, w1.y);
+        wz[k] = __floats2half2_rn(w0.z, w1.z);
+        wb[k] = __floats2half2_rn(w0.w, w1.w);
+      }
       uint8_t* blk = s_act + (ch >> 6) * (NT * 128);
       const uint32_t chunk = (uint32_t)(ch & 63) >> 3;
+      const op16x2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int t = tg + TG * i;
         const float4 rel = rel_buf[t];
+        const op16x2 rx = __float2half2_rn(rel.x), ry = __float2half2_rn(rel.y), rz = __float2half2_rn(rel.z);
         uint32_t pk[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4 w0 = wv[2 * k], w1 = wv[2 * k + 1];
-          const float h0 = fmaxf(fmaf(w0.x, rel.x, fmaf(w0.y, rel.y, fmaf(w0.z, rel.z, w0.w))), 0.f);
-          const float h1 = fmaxf(fmaf(w1.x, rel.x, fmaf(w1.y, rel.y, fmaf(w1.z, rel.z, w1.w))), 0.f);
-          pk[k] = pack_op16x2(h0, h1);
+          const op16x2 h2 = __hmax2(__hfma2(wx[k], rx, __hfma2(wy[k], ry, __hfma2(wz[k], rz, wb[k]))), zero2);
+          pk[k] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         *reinterpret_cast<uint4*>(blk + sw128_offset(t, chunk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
@@ -351,12 +359,13 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
         uint32_t kk[2][16];
         gather32(p.ktab, qi0, kk[0]);
         gather32(p.ktab, qi0 + 1, kk[1]);
-        float qv[2];
+        op16x2 qv2[2];        // (qt, qt) of this channel for the thread's two queries
+        const op16x2 zero2 = __floats2half2_rn(0.f, 0.f);
         uint32_t act1_q[2];   // smem address of (token row (qi0+u)*32, channel c) before the swizzle XOR
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int qg = q_first + qi0 + u;
-          qv[u] = (qg < p.n_query) ? op16_to_f(p.q[(size_t)qg * p.ldq + c]) : 0.f;
+          qv2[u] = __half2half2((qg < p.n_query) ? p.q[(size_t)qg * p.ldq + c] : __float2half(0.f));
           act1_q[u] = smem_u32(s_act1) + act_blk + (act_chunk << 4) + act_byte + (uint32_t)(qi0 + u) * (32 * 128);
         }
         // metadata of the next tile (its xyz loads queue up behind the kt gathers, all of it under the gamma1 GEMMs),
@@ -379,13 +388,18 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+              // relu(acc + qt - kt) for token rows 2j | 2j+1 of this channel, two tokens per packed instruction
               const uint32_t kp = kk[u][h * 8 + j];
-              const float v0 = fmaxf(__uint_as_float(r[2 * j]) + (qv[u] - bf_lo(kp)), 0.f);
-              const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + (qv[u] - bf_hi(kp)), 0.f);
+              const op16x2 d2 = __hsub2(qv2[u], *reinterpret_cast<const op16x2*>(&kp));
+              const uint32_t a2 = pack_op16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+              const op16x2 v2 = __hmax2(__hadd2(*reinterpret_cast<const op16x2*>(&a2), d2), zero2);
+              const uint32_t vb = *reinterpret_cast<const uint32_t*>(&v2);
               // token row t = (qi0+u)*32 + tl: SWIZZLE_128B flips address bits 4..6 with (t & 7) == (tl & 7)
               const int tl = h * 16 + 2 * j;
-              st_shared_b16((act1_q[u] ^ ((uint32_t)(tl & 7) << 4)) + tl * 128, v0);
-              st_shared_b16((act1_q[u] ^ ((uint32_t)((tl + 1) & 7) << 4)) + (tl + 1) * 128, v1);
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"((act1_q[u] ^ ((uint32_t)(tl & 7) << 4)) + tl * 128),
+                           "h"((unsigned short)(vb & 0xffffu)) : "memory");
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"((act1_q[u] ^ ((uint32_t)((tl + 1) & 7) << 4)) + (tl + 1) * 128),
+                           "h"((unsigned short)(vb >> 16)) : "memory");
             }
           }
         }

@@ -316,6 +316,13 @@ def test_errors_are_loud():
     metas_bad["master_id"] = [1]
     with pytest.raises(AssertionError):
         head(mlvl_feat=feat.cuda(), img_metas=metas_bad, reference_joints=ref_j.cuda())
+    # POEM-huge (D = 1024, head dim 256) is not built: rejected with a message, never computed approximately
+    from poem_v2_b200 import _native as nat
+    huge = POEM_Generalized_Head(release_dims("huge"), template_mesh=synth.standin_template()).cuda()
+    hf, hm, hr = synth.make_inputs(release_dims("huge"), 1, [2], 1)
+    with pytest.raises(nat.PoemError, match="POEM-huge"):
+        huge(mlvl_feat=hf.cuda(), img_metas=to_cuda(hm), reference_joints=hr.cuda())
+    del huge
     metas11 = to_cuda(metas)
     metas11["cam_view_num"] = np.array([11])
     with pytest.raises(Exception):
