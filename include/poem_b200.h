@@ -12,7 +12,9 @@
  *   - all device buffers are caller-allocated; the library allocates nothing and keeps no mutable global
  *     state besides the last-error string (thread local)
  *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*)
- *   - "op16" buffers are raw 16-bit bfloat16 (uint16_t storage)
+ *   - "op16" buffers hold the library's 16-bit tensor-core operand format: IEEE fp16 (binary16; uint16_t storage).  Every
+ *     fp32 -> op16 conversion inside the library saturates (no inf / NaN from a finite value); weights handed to the
+ *     library must already be finite fp16 (the Python packer raises when |w| > 65504)
  */
 #ifndef POEM_B200_H
 #define POEM_B200_H
