@@ -153,8 +153,32 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef POEM_MBAR_MODE
+#define POEM_MBAR_MODE 0   // 0: try_wait with a 10 ms suspend hint; 1: try_wait without a hint; 2: test_wait busy loop (experiments)
+#endif
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
+  if (POEM_MBAR_MODE == 0) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+  } else if (POEM_MBAR_MODE == 1) {
+    while (!mbar_try_wait_nohint(bar, parity)) {
+    }
+  } else {
+    while (!mbar_test_wait(bar, parity)) {
+    }
   }
 }
 

@@ -162,8 +162,9 @@ gemm_op16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above (barriers, TMEM, bias preload = weights) is independent of the predecessor kernel
-  pdl_wait();
+  // everything above (barriers, TMEM, bias preload = weights) is independent of the predecessor kernel; so is the
+  // resident weight slab of the W-stationary mode, which the TMA warp requests before it waits
+  if (warp != 0) pdl_wait();
   pdl_trigger();
 
   if (warp == 0) {
@@ -176,6 +177,7 @@ gemm_op16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < k_blocks; ++kb)
           tma_load_2d(s_wres + kb * Cfg::kWBytes, &tmap_w, wres_full, kb * GEMM_BK, my_n_tile * BN);
       }
+      pdl_wait();   // the A operand (and a residual) come from the predecessor kernel
       for (int it = it0; it < it_end; it += it_step) {
         const int m0 = (wst ? it : it / tiles_n) * GEMM_BM;
         const int n0 = (wst ? my_n_tile : it % tiles_n) * BN;

@@ -17,6 +17,7 @@
 #include "hrnet.cuh"
 #include "simt.cuh"
 #include "sample_merge.cuh"
+#include "qchain.cuh"
 #include "vecattn.cuh"
 #include "mano.cuh"
 
@@ -1408,6 +1409,46 @@ static SideStream& side_stream() {
   return s;
 }
 
+// Two chained Linear layers of the query stream in one kernel (qchain.cuh):
+//   C1 = A·W1^T + b1 (+ res32) [-> LayerNorm] -> out1_f32 / out1_h16 ;  out2 = act2(fp16(C1)·W2^T + b2)
+template <int D>
+static int launch_chain2_d(const char* tag, const op16* A, const PoemLinear& l1, const PoemLinear& l2, Chain2Params prm,
+                           cudaStream_t st) {
+  using Cfg = QcCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(chain2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  if (!A || !l1.w || !l2.w || !prm.out2) return fail(POEM_E_NULL, "chain2 %s: null operand", tag);
+  if (prm.N2 % Cfg::NC || prm.N2 > 4 * D || prm.ld2 % 16) return fail(POEM_E_BADDIM, "chain2 %s: N2=%d ld2=%d", tag, prm.N2, prm.ld2);
+  CUtensorMap ta, t1, t2;
+  POEM_TRY(make_tmap_op16(&ta, A, (uint64_t)prm.M, D, D, 64, 128));
+  POEM_TRY(make_tmap_op16(&t1, l1.w, D, D, D, 64, Cfg::NC));
+  POEM_TRY(make_tmap_op16(&t2, l2.w, (uint64_t)prm.N2, D, D, 64, Cfg::NC));
+  prm.b1 = l1.b;
+  prm.b2 = l2.b;
+  const int tiles = (prm.M + 127) / 128;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  TagScope ts(tag);
+  prof_begin(st);
+  launch_pdl(chain2_kernel<D>, dim3(grid), dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, ta, t1, t2, prm);
+  LAUNCH_CHECK("chain2_kernel");
+  return POEM_OK;
+}
+static int launch_chain2(int D, const char* tag, const op16* A, const PoemLinear& l1, const PoemLinear& l2,
+                         const Chain2Params& prm, cudaStream_t st) {
+  return D == 128 ? launch_chain2_d<128>(tag, A, l1, l2, prm, st) : launch_chain2_d<256>(tag, A, l1, l2, prm, st);
+}
+static Chain2Params chain2_params(int M, int D) {
+  Chain2Params c;
+  memset(&c, 0, sizeof(c));
+  c.M = M;
+  c.N2 = D;
+  c.ld2 = D;
+  return c;
+}
+
 static thread_local int32_t* g_nbr_export = nullptr;
 static thread_local size_t g_nbr_capacity = 0;
 extern "C" void poem_debug_export_neighbours(int32_t* device_buf, size_t capacity) {
@@ -1440,19 +1481,44 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
       TagScope ts("pt_proj");
       POEM_TRY(linear("pt_proj", p.ptf, D, k.pt_proj, BP, 6 * D, D, ACT_NONE, nullptr, nullptr, p.KK, st));
     }
-    POEM_TRY(linear("q_embed", p.qf16, D, k.embedding, BQ, D, D, ACT_NONE, nullptr, p.qe32, p.qe16, st));
+    // Query-stream segments: two chained layers per kernel for D <= 256 (qchain.cuh), separate GEMMs + LayerNorm otherwise
+    const bool qchain = !g_force_unfused && (D == 128 || D == 256);
+    if (qchain) {
+      Chain2Params c = chain2_params(BQ, D);             // embedding -> attn.self.query
+      c.out1_f32 = p.qe32;
+      c.out2 = p.qp16;
+      POEM_TRY(launch_chain2(D, "q_embed+mha_q", p.qf16, k.embedding, k.q1, c, st));
+    } else {
+      POEM_TRY(linear("q_embed", p.qf16, D, k.embedding, BQ, D, D, ACT_NONE, nullptr, p.qe32, p.qe16, st));
+      POEM_TRY(linear("mha_q", p.qe16, D, k.q1, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
+    }
     // MHA 1
-    POEM_TRY(linear("mha_q", p.qe16, D, k.q1, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
     POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 6 * D, 0, p.KK, 6 * D, 4 * D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
-    POEM_TRY(linear("mha_out", p.ctx16, D, k.o1, BQ, D, D, ACT_NONE, p.qe32, p.tmp32, nullptr, st));
-    POEM_TRY(launch_layernorm(p.tmp32, k.ln1_g, k.ln1_b, p.a1_32, p.a1_16, BQ, D, st));
+    if (qchain) {
+      Chain2Params c = chain2_params(BQ, D);             // attn.output.dense + residual + LayerNorm -> cross_attn.self.query
+      c.res32 = p.qe32, c.ln = 1, c.ln_g = k.ln1_g, c.ln_b = k.ln1_b;
+      c.out1_f32 = p.a1_32;
+      c.out2 = p.qp16;
+      POEM_TRY(launch_chain2(D, "mha_out+ln+mha_q", p.ctx16, k.o1, k.q2, c, st));
+    } else {
+      POEM_TRY(linear("mha_out", p.ctx16, D, k.o1, BQ, D, D, ACT_NONE, p.qe32, p.tmp32, nullptr, st));
+      POEM_TRY(launch_layernorm(p.tmp32, k.ln1_g, k.ln1_b, p.a1_32, p.a1_16, BQ, D, st));
+      POEM_TRY(linear("mha_q", p.a1_16, D, k.q2, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
+    }
     // MHA 2
-    POEM_TRY(linear("mha_q", p.a1_16, D, k.q2, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qp16, st));
     POEM_TRY(launch_mha(p.qp16, D, 0, p.KK, 6 * D, D, p.KK, 6 * D, 5 * D, p.ctx16, D, B, Q, P, D, dims->n_heads, st));
-    POEM_TRY(linear("mha_out", p.ctx16, D, k.o2, BQ, D, D, ACT_NONE, p.a1_32, p.tmp32, nullptr, st));
-    POEM_TRY(launch_layernorm(p.tmp32, k.ln2_g, k.ln2_b, p.a2_32, p.a2_16, BQ, D, st));
+    if (qchain) {
+      Chain2Params c = chain2_params(BQ, D);             // cross_attn.output.dense + residual + LayerNorm -> self-attention q | k | v
+      c.res32 = p.a1_32, c.ln = 1, c.ln_g = k.ln2_g, c.ln_b = k.ln2_b;
+      c.out1_f32 = p.a2_32;
+      c.N2 = 3 * D, c.ld2 = 3 * D, c.out2 = p.qkv16;
+      POEM_TRY(launch_chain2(D, "mha_out+ln+va_self_qkv", p.ctx16, k.o2, k.self_qkv, c, st));
+    } else {
+      POEM_TRY(linear("mha_out", p.ctx16, D, k.o2, BQ, D, D, ACT_NONE, p.a1_32, p.tmp32, nullptr, st));
+      POEM_TRY(launch_layernorm(p.tmp32, k.ln2_g, k.ln2_b, p.a2_32, p.a2_16, BQ, D, st));
+      POEM_TRY(linear("va_self_qkv", p.a2_16, D, k.self_qkv, BQ, 3 * D, D, ACT_NONE, nullptr, nullptr, p.qkv16, st));
+    }
     // vector self-attention
-    POEM_TRY(linear("va_self_qkv", p.a2_16, D, k.self_qkv, BQ, 3 * D, D, ACT_NONE, nullptr, nullptr, p.qkv16, st));
     const bool anchors = (i == 0);
     if (!anchors) {   // neighbour indices of this block: computed on the side stream since the previous block ended
       if (knn_on_side) CUDA_TRY(cudaStreamWaitEvent(st, side.join[i], 0));
@@ -1468,15 +1534,31 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
     POEM_TRY(launch_vector_attention(&k.self_attn, p.qkv16, 3 * D, p.qkv16 + D, 3 * D, p.qkv16 + 2 * D, 3 * D, xyz_in,
                                      xyz_in, anchors ? nullptr : p.idx_self, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, Q, D, p.res16, p.t0, p.t1, p.t2, st));
-    POEM_TRY(linear("va_fc2", p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
-    // vector cross-attention (queries <- BPS tokens)
-    POEM_TRY(linear("va_cross_q", p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
+    if (qchain) {
+      Chain2Params c = chain2_params(BQ, D);             // query_self_attn.fc2 + residual -> query_cross_attn.w_qs (folded)
+      c.res32 = p.a2_32;
+      c.out1_f32 = p.f1_32;
+      c.out2 = p.qc16;
+      POEM_TRY(launch_chain2(D, "va_fc2+va_cross_q", p.res16, k.self_attn.fc2, k.cross_q, c, st));
+    } else {
+      POEM_TRY(linear("va_fc2", p.res16, D, k.self_attn.fc2, BQ, D, D, ACT_NONE, p.a2_32, p.f1_32, p.f1_16, st));
+      // vector cross-attention (queries <- BPS tokens)
+      POEM_TRY(linear("va_cross_q", p.f1_16, D, k.cross_q, BQ, D, D, ACT_NONE, nullptr, nullptr, p.qc16, st));
+    }
     POEM_TRY(launch_vector_attention(&k.cross_attn, p.qc16, D, p.KK + 2 * D, 6 * D, p.KK + 3 * D, 6 * D, xyz_in,
                                      p.pt_xyz, anchors ? nullptr : p.idx_cross, anchors ? w->anchor_idx : nullptr,
                                      anchors ? w->anchor_xyz : nullptr, B, Q, P, D, p.res16, p.t0, p.t1, p.t2, st));
-    POEM_TRY(linear("va_fc2", p.res16, D, k.cross_attn.fc2, BQ, D, D, ACT_NONE, p.f1_32, p.f2_32, p.f2_16, st));
-    // coordinate regression
-    POEM_TRY(linear("reg1", p.f2_16, D, k.reg1, BQ, D, D, ACT_RELU, nullptr, nullptr, p.r1_16, st));
+    if (qchain) {
+      Chain2Params c = chain2_params(BQ, D);             // query_cross_attn.fc2 + residual -> reg_branch.0 + ReLU
+      c.res32 = p.f1_32;
+      c.out1_f32 = p.f2_32, c.out1_h16 = p.f2_16;
+      c.act2 = ACT_RELU, c.out2 = p.r1_16;
+      POEM_TRY(launch_chain2(D, "va_fc2+reg1", p.res16, k.cross_attn.fc2, k.reg1, c, st));
+    } else {
+      POEM_TRY(linear("va_fc2", p.res16, D, k.cross_attn.fc2, BQ, D, D, ACT_NONE, p.f1_32, p.f2_32, p.f2_16, st));
+      // coordinate regression
+      POEM_TRY(linear("reg1", p.f2_16, D, k.reg1, BQ, D, D, ACT_RELU, nullptr, nullptr, p.r1_16, st));
+    }
     {
       if (!k.reg2_w || !k.reg2_b) return fail(POEM_E_NULL, "block %d: reg_branch.2 missing", i);
       const int threads = 256;

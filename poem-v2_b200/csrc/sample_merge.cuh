@@ -198,7 +198,9 @@ sample_merge_kernel(const __grid_constant__ CUtensorMap tmap_w0a, const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // the setup above only touched weights (biases) and on-chip state
+  // PDL: the setup above only touched weights (biases) and on-chip state, and the TMA warp only ever streams weights:
+  // it runs ahead while the predecessor kernel drains, everybody else waits for it here
+  if (warp != 0) pdl_wait();
   pdl_trigger();
   const uint32_t tmem_acc1 = tmem_base;          // D columns
   const uint32_t tmem_acc2 = tmem_base + D;      // H columns

@@ -135,7 +135,9 @@ va_fused_kernel(const __grid_constant__ CUtensorMap tmap_wd2, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // the setup above only touched weights (fc_delta.0) and on-chip state
+  // PDL: the setup above only touched weights (fc_delta.0) and on-chip state, and the TMA warp only ever streams
+  // weights: it runs ahead while the predecessor kernel drains, everybody else waits for it here
+  if (warp != 0) pdl_wait();
   pdl_trigger();
   const uint32_t tmem_pos = tmem_base;                 // MT tiles of NT columns
   const uint32_t tmem_h = tmem_base + MT * NT;         // MT tiles of NT columns
