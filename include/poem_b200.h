@@ -150,6 +150,9 @@ void poem_debug_conv_mode(int mode);
  * regressed coordinates, so the parity tests compare against the oracle run on the SAME sets, and check the sets
  * separately (bit-exact given the coordinates).  NULL disables.  Not used by the product path. */
 void poem_debug_export_neighbours(int32_t* device_buf, size_t capacity);
+/* Test hook: while non-NULL, every whole-path call of this host thread copies the merged BPS features (stage boundary a6:
+ * `pt_feats` of ptEmb_head.py:926, op16 [B*P, D]) into the buffer (capacity in elements).  NULL disables. */
+void poem_debug_export_pt_feats(poem_op16* device_buf, size_t capacity);
 
 /* Bytes of device workspace poem_head_forward needs for (batch, n_images). */
 size_t poem_workspace_bytes(const PoemDims* dims, int batch, int n_images);
@@ -349,6 +352,15 @@ int poem_project_sample(const float* xmap, const float* cam_intr, const float* c
                         const float* centre, const int32_t* host_view_counts, int B, int n_images, int D, int P,
                         int fh, int fw, float img_w, float img_h, poem_op16* X, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* The gather side of rows a4 / a5 on its own: for every (image, BPS point) the four bilinear taps of
+ * F.grid_sample(align_corners=False, zero padding) after generate_grid_sample_proj (collation.py:48-65): pixel index
+ * y * fw + x of the taps nw, ne, sw, se (0 with weight 0 when the tap lies outside the map) and their weights.
+ * tap_pixels int32 [n_images, P, 4], tap_weights fp32 [n_images, P, 4]; workspace >= 128 KB + 96 bytes per (image, point)/4.
+ * This is the table the fused sampler / merge kernel gathers with. */
+int poem_sample_taps(const float* cam_intr, const float* cam_extr, const float* bps, const float* centre,
+                     const int32_t* host_view_counts, int B, int n_images, int P, int fh, int fw, float img_w, float img_h,
+                     int32_t* tap_pixels, float* tap_weights, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Vector attention core: res[b,i,:] = sum_j softmax_j(gamma(q_i - k_j + pos_ij)/sqrt(D)) * (v_j + pos_ij),
  * pos_ij = delta(xyz_i - nbr_xyz_j), in the folded form documented at PoemVecAttn:

@@ -140,10 +140,10 @@ class PoemInputs(C.Structure):
 
 # every symbol include/poem_b200.h declares
 EXPORTS = ["poem_abi_version", "poem_last_error", "poem_kernel_launches", "poem_profile_enable",
-           "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_debug_export_neighbours", "poem_hrnet_stage4_workspace_bytes",
+           "poem_profile_summary", "poem_debug_force_unfused", "poem_debug_conv_mode", "poem_debug_export_neighbours", "poem_debug_export_pt_feats", "poem_hrnet_stage4_workspace_bytes",
            "poem_hrnet_stage4_forward", "poem_conv_nhwc", "poem_hrnet_workspace_bytes", "poem_hrnet_forward", "poem_image_features_workspace_bytes", "poem_image_features", "poem_triangulate_dlt", "poem_pa_metrics", "poem_workspace_bytes", "poem_head_forward", "poem_staging_bytes",
            "poem_head_forward_host", "poem_transformer_workspace_bytes", "poem_transformer_forward", "poem_linear",
-           "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_vector_attention",
+           "poem_mha", "poem_knn32", "poem_knn32_bps", "poem_project_sample", "poem_sample_taps", "poem_vector_attention",
            "poem_vector_attention_workspace_bytes", "poem_layernorm", "poem_parametric_tail_workspace_bytes",
            "poem_parametric_tail", "poem_head_forward_parametric", "poem_head_forward_parametric_host"]
 
@@ -173,6 +173,8 @@ def load():
     lib.poem_debug_force_unfused.restype = None
     lib.poem_debug_export_neighbours.argtypes = [vp, sz]
     lib.poem_debug_export_neighbours.restype = None
+    lib.poem_debug_export_pt_feats.argtypes = [vp, sz]
+    lib.poem_debug_export_pt_feats.restype = None
     lib.poem_profile_summary.restype = sz
     lib.poem_profile_summary.argtypes = [C.c_char_p, sz]
     lib.poem_workspace_bytes.restype = sz
@@ -211,6 +213,8 @@ def load():
     lib.poem_knn32.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.poem_project_sample.restype = i
     lib.poem_project_sample.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, f, f, vp, vp, sz, vp]
+    lib.poem_sample_taps.restype = i
+    lib.poem_sample_taps.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, f, f, vp, vp, vp, sz, vp]
     lib.poem_vector_attention_workspace_bytes.restype = sz
     lib.poem_vector_attention_workspace_bytes.argtypes = [i, i, i]
     lib.poem_vector_attention.restype = i

@@ -1082,6 +1082,35 @@ extern "C" int poem_project_sample(const float* xmap, const float* cam_intr, con
                                reinterpret_cast<op16*>(X), (cudaStream_t)stream);
 }
 
+// Bilinear taps of every (image, BPS point): the gather indices and weights of rows a4 / a5 on their own
+extern "C" int poem_sample_taps(const float* cam_intr, const float* cam_extr, const float* bps, const float* centre,
+                                const int32_t* host_view_counts, int B, int n_images, int P, int fh, int fw, float img_w,
+                                float img_h, int32_t* tap_pixels, float* tap_weights, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!cam_intr || !cam_extr || !bps || !centre || !host_view_counts || !tap_pixels || !tap_weights || !workspace)
+    return fail(POEM_E_NULL, "sample_taps: null pointer");
+  if (P != SM_P || fh * fw != SM_F) return fail(POEM_E_BADDIM, "sample_taps: P=%d, %dx%d (4096 points, 256 pixels)", P, fh, fw);
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump bump{reinterpret_cast<uint8_t*>(workspace), 0};
+  int* tab = bump.take<int>(view_tables_ints(B, n_images));
+  float* proj = bump.take<float>((size_t)n_images * 24);
+  uint32_t* taps = bump.take<uint32_t>((size_t)n_images * (P / 4) * SM_TAP_WORDS);
+  if (bump.off > workspace_bytes) return fail(POEM_E_WORKSPACE, "sample_taps: workspace %zu < %zu", workspace_bytes, bump.off);
+  ViewTables vt;
+  POEM_TRY(upload_view_tables(host_view_counts, B, n_images, P, 64, tab, &vt, st));
+  prof_begin(st);
+  launch_pdl(camera_prep_kernel, dim3((n_images + 63) / 64), dim3(64), (size_t)0, st, cam_intr, cam_extr, proj, n_images);
+  LAUNCH_CHECK("camera_prep_kernel");
+  prof_begin(st);
+  launch_pdl(sample_taps_kernel, dim3((unsigned)(((size_t)n_images * P + 255) / 256)), dim3(256), (size_t)0, st, proj, bps, centre,
+             vt.img_sample, taps, n_images, fh, fw, 1.0f / img_w, 1.0f / img_h, 1);    // pixel pitch 1: offsets = pixel indices
+  LAUNCH_CHECK("sample_taps_kernel");
+  prof_begin(st);
+  unpack_taps_kernel<<<(unsigned)(((size_t)n_images * P + 255) / 256), 256, 0, st>>>(taps, tap_pixels, tap_weights, n_images);
+  LAUNCH_CHECK("unpack_taps_kernel");
+  return POEM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // vector attention
 // ------------------------------------------------------------------------------------------------
@@ -1449,6 +1478,12 @@ static Chain2Params chain2_params(int M, int D) {
   return c;
 }
 
+static thread_local op16* g_ptf_export = nullptr;     // test hook: merged BPS features (B*P, D) of the next whole-path call
+static thread_local size_t g_ptf_capacity = 0;
+extern "C" void poem_debug_export_pt_feats(poem_op16* device_buf, size_t capacity) {
+  g_ptf_export = reinterpret_cast<op16*>(device_buf);
+  g_ptf_capacity = device_buf ? capacity : 0;
+}
 static thread_local int32_t* g_nbr_export = nullptr;
 static thread_local size_t g_nbr_capacity = 0;
 extern "C" void poem_debug_export_neighbours(int32_t* device_buf, size_t capacity) {
@@ -1809,6 +1844,10 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
     e.ld_op16 = D;
     TagScope ts("merge1b");
     POEM_TRY(launch_gemm(h.H2, H, W16(w->merge1b), H, BP, D, H, e, st));
+  }
+  if (g_ptf_export != nullptr) {   // test hook: stage boundary a6 (merged BPS features, the `pt_feats` of ptEmb_head.py:926)
+    if ((size_t)BP * D > g_ptf_capacity) return fail(POEM_E_WORKSPACE, "pt_feats export buffer too small");
+    CUDA_TRY(cudaMemcpyAsync(g_ptf_export, p.ptf, (size_t)BP * D * sizeof(op16), cudaMemcpyDeviceToDevice, st));
   }
   // ---- a7: query features
   {

@@ -89,6 +89,20 @@ __global__ void sample_taps_kernel(const float* __restrict__ proj, const float* 
   o[1] = (o10 * pb) | ((o11 * pb) << 16);
 }
 
+// test helper: packed tap table -> (n_img, P, 4) pixel indices (nw, ne, sw, se; pixel pitch 1) and weights
+__global__ void unpack_taps_kernel(const uint32_t* __restrict__ taps, int32_t* __restrict__ pixels, float* __restrict__ weights,
+                                   int n_img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * SM_P) return;
+  const int img = idx / SM_P, p = idx - img * SM_P;
+  const uint32_t* t = taps + ((size_t)img * (SM_P / 4) + (p >> 2)) * SM_TAP_WORDS;
+  const uint32_t oa = t[16 + 2 * (p & 3)], ob = t[17 + 2 * (p & 3)];
+  pixels[idx * 4 + 0] = (int32_t)(oa & 0xffffu), pixels[idx * 4 + 1] = (int32_t)(oa >> 16);
+  pixels[idx * 4 + 2] = (int32_t)(ob & 0xffffu), pixels[idx * 4 + 3] = (int32_t)(ob >> 16);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) weights[idx * 4 + k] = __uint_as_float(t[4 * k + (p & 3)]);
+}
+
 template <int D>
 struct SmCfg {
   static_assert(D == 128 || D == 256, "fused sampler/merge kernel: D = 128 or 256 (D = 512 takes the un-fused path)");

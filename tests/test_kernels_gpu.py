@@ -181,6 +181,52 @@ def test_project_sample(lib, D, views):
     assert (ref == 0).float().mean().item() > 0.01                 # the out-of-image path was exercised
 
 
+@pytest.mark.parametrize("views", [[2, 3], [8], [1, 10, 4]])
+def test_sample_tap_indices_are_exact(lib, views):
+    """The gather indices of the bilinear sampler (rows a4 / a5; north star: bit-exact on index gathers): for every
+    (image, BPS point) the four tap pixels the kernels gather from must be the ones `F.grid_sample(align_corners=False)`
+    uses for the reference's projected grid, and out-of-image taps must carry weight 0.  A point whose pixel coordinate
+    lies within 1e-4 of a pixel centre line may legitimately land on either side (the projection is fp32 arithmetic in
+    a different order); there the interpolated VALUE is continuous, which the weight check below covers."""
+    import numpy as np
+    B, NV, P, F = len(views), sum(views), 4096, 16
+    dims = synth.HeadDims(embed_dims=128)
+    _, metas, refj = synth.make_inputs(dims, B, views, seed=7)
+    metas["cam_intr"][-1, 0, 2] += 120.0                       # part of the points outside the last image
+    bps, _, _ = synth.load_assets()
+    centre = refj[:, 9].contiguous()
+    pix = torch.zeros(NV, P, 4, dtype=torch.int32, device="cuda")
+    wts = torch.zeros(NV, P, 4, dtype=torch.float32, device="cuda")
+    wst, wsp, wsb = _ws(8 << 20)
+    vc = np.asarray(views, dtype=np.int32)
+    dv = [t.cuda() for t in (metas["cam_intr"], metas["cam_extr"], bps, centre)]
+    nat.check(lib.poem_sample_taps(_p(dv[0]), _p(dv[1]), _p(dv[2]), _p(dv[3]), vc.ctypes.data, B, NV, P, F, F, 256.0, 256.0,
+                                   _p(pix), _p(wts), wsp, wsb, _stream()))
+    torch.cuda.synchronize()
+    grid = orc.project_bps(bps[None] + centre[:, None], metas["cam_intr"], metas["cam_extr"], views,
+                           torch.tensor([256.0, 256.0]))[:, :, 0]           # (NV, P, 2) in [-1, 1] units
+    ix = ((grid[..., 0] + 1) * F - 1) / 2
+    iy = ((grid[..., 1] + 1) * F - 1) / 2
+    x0, y0 = torch.floor(ix), torch.floor(iy)
+    ax, ay = ix - x0, iy - y0
+    want_pix, want_w = [], []
+    for dy, dx, w in ((0, 0, (1 - ax) * (1 - ay)), (0, 1, ax * (1 - ay)), (1, 0, (1 - ax) * ay), (1, 1, ax * ay)):
+        xx, yy = x0 + dx, y0 + dy
+        ok = (xx >= 0) & (xx < F) & (yy >= 0) & (yy < F)
+        want_pix.append(torch.where(ok, (yy * F + xx), torch.zeros_like(xx)).to(torch.int32))
+        want_w.append(torch.where(ok, w, torch.zeros_like(w)))
+    want_pix, want_w = torch.stack(want_pix, -1), torch.stack(want_w, -1)
+    got_pix, got_w = pix.cpu(), wts.cpu()
+    near_edge = ((ix - ix.round()).abs() < 1e-4) | ((iy - iy.round()).abs() < 1e-4)
+    same = (got_pix == want_pix).all(dim=-1)
+    print(f"views={views}: {int((~same).sum())} of {same.numel()} points with different taps, "
+          f"{int((~same & ~near_edge).sum())} of them away from a pixel line; max |dw| {(got_w - want_w)[same].abs().max().item():.2e}")
+    assert (same | near_edge).all()                               # indices exact wherever they are well defined
+    assert (got_w - want_w)[same].abs().max().item() <= 5e-5      # weights: fp32 projection in a different order; measured 1.4e-5
+    assert (got_w[want_w == 0][same[..., None].expand_as(want_w)[want_w == 0]] == 0).all()   # zero padding exact
+    assert (want_w.sum(-1) < 0.5).float().mean().item() > 0.01    # the out-of-image path was exercised
+
+
 # ------------------------------------------------------------------------------------------ vector attention
 def _vecattn_weights(D, g):
     sd = {}

@@ -244,6 +244,37 @@ def test_host_entry_point_pipelines_calls_of_different_shapes():
             assert torch.equal(o, want)
 
 
+@pytest.mark.parametrize("name", ["small_ragged_b3", "medium_v8_b1", "small_v1_b2", "large_v2_b1"])
+def test_merged_bps_features_match_oracle(name):
+    """Stage boundary a6 on its own (input projection + positional term, projection, bilinear
+    sampling, the raw `.view` regroup, merge network): the merged BPS features `pt_feats` the kernels hand to the decoder
+    blocks (`poem_debug_export_pt_feats`, fp16) against the oracle's (ptEmb_head.py:926) on the golden inputs —
+    fused sampler/merge kernel for D <= 256, the four-kernel chain for POEM-large."""
+    from poem_v2_b200 import _native as nat
+    meta, dims, sd, feat, metas, ref_j, gold = load_case(name)
+    bps, a_xyz, a_idx = synth.load_assets()
+    st = {}
+    with torch.no_grad():
+        orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx, stages=st)
+    want = st["pt_feats"]                                     # (B, 4096, D) fp32
+    head = build_head(dims, sd)
+    buf = torch.zeros(want.shape, dtype=torch.float16, device="cuda")
+    lib = nat.load()
+    lib.poem_debug_export_pt_feats(buf.data_ptr(), buf.numel())
+    try:
+        head(mlvl_feat=feat.cuda(), img_metas=to_cuda(metas), reference_joints=ref_j.cuda())
+        torch.cuda.synchronize()
+    finally:
+        lib.poem_debug_export_pt_feats(None, 0)
+    got = buf.float().cpu()
+    err = (got - want).abs()
+    scale = want.abs().max().item()
+    rel_l2 = ((got - want).norm() / want.norm()).item()
+    print(f"{name}: pt_feats max |err| {err.max().item():.4e} ({err.max().item() / scale:.2e} of the range), rel-L2 {rel_l2:.2e}")
+    # fp16 operands through input_proj, the sampled rows and the two merge MLPs, fp16 storage of the result (2^-11)
+    assert rel_l2 <= 1e-3 and err.max().item() <= 2e-3 * scale        # measured 3.7e-4 ... 6.2e-4 / 5.5e-4 ... 7.4e-4
+
+
 @pytest.mark.parametrize("size,views", [("small", [1, 3, 7, 10, 8]), ("medium", [8, 8]), ("medium", [5, 1, 9])])
 def test_fused_sampler_merge_matches_the_unfused_chain(size, views):
     """sample_merge_kernel (sampler + merge MLP0 + cross-view reduce in one kernel, row tiles of floor(128 / N) tokens,
