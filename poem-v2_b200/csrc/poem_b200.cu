@@ -92,6 +92,16 @@ struct TagScope {
 // Launch with programmatic stream serialization (PDL): the kernel may be scheduled while its predecessor drains; every
 // kernel launched this way calls pdl_wait() before its first dependent global access (common.cuh).  POEM_PDL=0 in the
 // environment falls back to plain launches.
+static int split_parts() {   // POEM_SPLIT=<n>: batch slices whose decoder blocks run concurrently (default 2; 1 = one stream)
+  static int n = -1;
+  if (n < 0) {
+    const char* e = getenv("POEM_SPLIT");
+    n = e ? atoi(e) : 2;
+    if (n < 1) n = 1;
+    if (n > 4) n = 4;
+  }
+  return n;
+}
 static bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -1329,6 +1339,23 @@ static void plan_blocks(const PoemDims* d, int B, Bump& b, BlockPlan* p) {
   p->t2 = b.take<op16>(T * D);
 }
 
+// The view of a BlockPlan that starts at sample b0: every buffer is row-major over the samples of the batch
+// (xyz: per block a slab of the whole batch, so only the start moves; run_blocks strides it by the whole batch).
+static BlockPlan slice_plan(const BlockPlan& p, const PoemDims* d, int b0) {
+  const size_t D = d->embed_dims, P = d->n_sample, Q = d->n_query;
+  const size_t oP = (size_t)b0 * P, oQ = (size_t)b0 * Q, oT = oQ * 32;
+  BlockPlan s = p;
+  s.pt_xyz += oP * 3, s.pt_xyz_sorted += oP * 3, s.xyz += oQ * 3;
+  s.ptf += oP * D, s.KK += oP * 6 * D;
+  s.qf32 += oQ * D, s.qe32 += oQ * D, s.tmp32 += oQ * D, s.a1_32 += oQ * D, s.a2_32 += oQ * D, s.f1_32 += oQ * D, s.f2_32 += oQ * D;
+  s.qf16 += oQ * D, s.qe16 += oQ * D, s.qp16 += oQ * D, s.ctx16 += oQ * D, s.a1_16 += oQ * D, s.a2_16 += oQ * D;
+  s.qkv16 += oQ * 3 * D, s.res16 += oQ * D, s.f1_16 += oQ * D, s.qc16 += oQ * D, s.f2_16 += oQ * D, s.r1_16 += oQ * D;
+  s.ffn16 += oQ * 4 * D;
+  s.idx_self += oT, s.idx_cross += oT;
+  s.t0 += oT * D, s.t1 += oT * D, s.t2 += oT * D;
+  return s;
+}
+
 static void plan_head(const PoemDims* d, int B, int NV, Bump& b, HeadPlan* p) {
   const size_t D = d->embed_dims, C = d->in_channels, P = d->n_sample, F = 256;
   const size_t R = (size_t)NV * P, BP = (size_t)B * P;
@@ -1424,9 +1451,11 @@ static int current_device() {
   cudaGetDevice(&d);
   return (d >= 0 && d < kMaxDevices) ? d : 0;
 }
-static SideStream& side_stream() {
-  static thread_local SideStream per_dev[kMaxDevices];
-  SideStream& s = per_dev[current_device()];
+constexpr int kMaxParts = 4;    // the decoder blocks run on up to this many batch slices concurrently
+constexpr int kSideSlots = 2 * kMaxParts;   // slot k: 32-NN searches of slice k; slot kMaxParts + k: main stream of slice k (k >= 1)
+static SideStream& side_stream(int slot = 0) {
+  static thread_local SideStream per_dev[kMaxDevices][kSideSlots];
+  SideStream& s = per_dev[current_device()][slot];
   if (!s.ok) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess) {
       s.ok = true;
@@ -1501,16 +1530,21 @@ static int launch_block_knn(const PoemWeights* w, int B, int Q, int P, const Blo
 
 // a8-a13: the NB decoder blocks. Expects p.ptf (op16 BPS features), p.pt_xyz, p.xyz[0], p.qf32/p.qf16 filled.
 // coords_out[i] = nan_to_num(xyz_i) * radius + centre when centre != NULL, else the raw normalised xyz_i.
+// `B` samples starting at sample `b0` of a batch of `B_total` (plan, centre, coords_out, out_feats already point at
+// sample b0; per-block slabs of xyz / coords are B_total samples apart); `half` selects the 32-NN side stream.
 static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const BlockPlan& p, const float* centre,
-                      float* coords_out, float* out_feats, bool pt_is_bps, cudaStream_t st) {
+                      float* coords_out, float* out_feats, bool pt_is_bps, cudaStream_t st, int B_total = 0, int b0 = 0,
+                      int half = 0) {
   const int D = dims->embed_dims, P = dims->n_sample, Q = dims->n_query, NB = dims->n_blocks;
   const int BQ = B * Q, BP = B * P;
-  SideStream& side = side_stream();
+  if (B_total <= 0) B_total = B;
+  const size_t slab = (size_t)B_total * Q * 3;      // one block's coordinates of the whole batch
+  SideStream& side = side_stream(half);
   const bool knn_on_side = side.ok && !g_prof_on;   // per-launch event timing assumes one stream
   for (int i = 0; i < NB; ++i) {
     const PoemBlock& k = w->blocks[i];
-    float* xyz_in = p.xyz + (size_t)i * BQ * 3;
-    float* xyz_out = p.xyz + (size_t)(i + 1) * BQ * 3;
+    float* xyz_in = p.xyz + (size_t)i * slab;
+    float* xyz_out = p.xyz + (size_t)(i + 1) * slab;
     // BPS-token projections in one GEMM: K1 | K2 | kt_cross | v_cross | V1 | V2, all row-major
     {
       TagScope ts("pt_proj");
@@ -1559,11 +1593,11 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
       if (knn_on_side) CUDA_TRY(cudaStreamWaitEvent(st, side.join[i], 0));
       else POEM_TRY(launch_block_knn(w, B, Q, P, p, xyz_in, pt_is_bps, st));
       if (g_nbr_export != nullptr) {   // test hook: the index sets this block is about to use
-        const size_t T = (size_t)BQ * 32;
-        if ((size_t)(NB - 1) * 2 * T > g_nbr_capacity) return fail(POEM_E_WORKSPACE, "neighbour export buffer too small");
-        int32_t* dst = g_nbr_export + (size_t)(i - 1) * 2 * T;
+        const size_t T = (size_t)BQ * 32, T_all = (size_t)B_total * Q * 32;
+        if ((size_t)(NB - 1) * 2 * T_all > g_nbr_capacity) return fail(POEM_E_WORKSPACE, "neighbour export buffer too small");
+        int32_t* dst = g_nbr_export + (size_t)(i - 1) * 2 * T_all + (size_t)b0 * Q * 32;
         CUDA_TRY(cudaMemcpyAsync(dst, p.idx_self, T * 4, cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(dst + T, p.idx_cross, T * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dst + T_all, p.idx_cross, T * 4, cudaMemcpyDeviceToDevice, st));
       }
     }
     POEM_TRY(launch_vector_attention(&k.self_attn, p.qkv16, 3 * D, p.qkv16 + D, 3 * D, p.qkv16 + 2 * D, 3 * D, xyz_in,
@@ -1599,7 +1633,7 @@ static int run_blocks(const PoemDims* dims, const PoemWeights* w, int B, const B
       const int threads = 256;
       prof_begin(st);
       launch_pdl(reg_out_kernel, dim3(((size_t)BQ * 32 + threads - 1) / threads), dim3(threads), (size_t)(0), st, 
-          p.r1_16, k.reg2_w, k.reg2_b, xyz_in, xyz_out, coords_out + (size_t)i * BQ * 3, centre, dims->radius, Q, D,
+          p.r1_16, k.reg2_w, k.reg2_b, xyz_in, xyz_out, coords_out + (size_t)i * slab, centre, dims->radius, Q, D,
           BQ);
       LAUNCH_CHECK("reg_out_kernel");
     }
@@ -1857,8 +1891,34 @@ static int head_forward_impl(const PoemDims* dims, const PoemWeights* w, const P
                                                                              total);
     LAUNCH_CHECK("broadcast_queries_kernel");
   }
-  // ---- a8-a15
-  POEM_TRY(run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, /*pt_is_bps=*/true, st));
+  // ---- a8-a15.  The blocks of two (POEM_SPLIT=n: up to four) slices of the batch run on their own streams: every kernel of the path is a
+  // persistent grid with a tail (the attention kernel's last wave, the last partial round of tiles of the fused
+  // kernels, the 1.35 tiles per CTA of the query-stream kernels), and samples are independent, so the other half's
+  // kernels fill the SMs a tail leaves idle.  POEM_SPLIT=1 (or a profiled run) keeps everything on one stream.
+  int parts = g_prof_on ? 1 : split_parts();
+  while (parts > 1 && B / parts < 4) --parts;       // at least 4 samples per slice
+  for (int k = 0; k < parts && parts > 1; ++k)
+    if (!side_stream(k).ok || !side_stream(kMaxParts + k).ok) parts = 1;
+  if (parts <= 1) {
+    POEM_TRY(run_blocks(dims, w, B, p, h.centre, out_coords, out_feats, /*pt_is_bps=*/true, st));
+  } else {
+    SideStream& fork = side_stream(kMaxParts);       // its events fork / join the slices' streams
+    CUDA_TRY(cudaEventRecord(fork.fork[0], st));
+    int b0 = 0;
+    for (int k = 0; k < parts; ++k) {
+      const int Bk = B / parts + (k < B % parts ? 1 : 0);
+      cudaStream_t sk = (k == 0) ? st : side_stream(kMaxParts + k).stream;
+      if (k > 0) CUDA_TRY(cudaStreamWaitEvent(sk, fork.fork[0], 0));
+      const BlockPlan pk = slice_plan(p, dims, b0);
+      POEM_TRY(run_blocks(dims, w, Bk, pk, h.centre + (size_t)b0 * 3, out_coords + (size_t)b0 * Q * 3,
+                          out_feats ? out_feats + (size_t)b0 * Q * D : nullptr, true, sk, B, b0, k));
+      if (k > 0) {
+        CUDA_TRY(cudaEventRecord(side_stream(kMaxParts + k).join[0], sk));
+        CUDA_TRY(cudaStreamWaitEvent(st, side_stream(kMaxParts + k).join[0], 0));
+      }
+      b0 += Bk;
+    }
+  }
   // ---- a16: the last block's joints / vertices are replaced by the MANO output (tmp32 is free after the last LayerNorm)
   if (mano)
     POEM_TRY(launch_parametric_tail(dims, mano, B, out_feats ? out_feats : p.qf32, in->reference_joints,
