@@ -1,0 +1,111 @@
+/* C-ABI of the training-path primitives (libpoem_train.so, poem-v2_b200/csrc/poem_train.cu).
+ *
+ * SURVEY.md §8 row f3 ("training path"): what the reference gets from torch.autograd over
+ * lib/models/heads/ptEmb_head.py:825-964, lib/models/bricks/pt_metro_transformer.py:34-200 and
+ * lib/models/bricks/point_transformers.py:70-156 inside `scripts/train_ddp.py:96-116` (loss.backward(), clip_gradient,
+ * optimizer.step()).  The library holds the device kernels only — fp32 tensors in HBM, TF32 tcgen05 GEMMs, SIMT kernels
+ * for everything else; the forward/backward schedule of the head is host code (poem-v2_b200/train.py), the way the
+ * reference's schedule is Python.  Every pointer is a DEVICE pointer, every tensor dense row-major fp32 unless stated;
+ * `stream` is a cudaStream_t (NULL = default stream).  Functions return 0 or a negative POEM_TR_E_* code and leave a
+ * message for poem_tr_last_error().  Gradient outputs documented "+=" ACCUMULATE into the caller's buffer.
+ */
+#ifndef POEM_TRAIN_H_
+#define POEM_TRAIN_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POEM_TR_ABI_VERSION 1
+#define POEM_TR_OK 0
+#define POEM_TR_E_BADARG (-1)
+#define POEM_TR_E_ALIGN (-2)
+#define POEM_TR_E_CUDA (-3)
+
+int poem_tr_abi_version(void);
+const char* poem_tr_last_error(void);
+long long poem_tr_kernel_launches(void);
+
+/* C[b2,b1] (+)= alpha * op(A[b2,b1]) . op(B[b2,b1])^T (+ bias)         TF32 tensor cores, fp32 accumulate
+ *   a_mn == 0: A stored [M x K] (row pitch lda);  a_mn == 1: A stored [K x M] (row pitch lda)   — same for B with N.
+ *   batch: nb1 x nb2 problems; element strides (a_s1, a_s2), (b_s1, b_s2), (c_s1, c_s2); a stride of 0 shares the
+ *   operand along that axis; c stride 0 with extent > 1 sums the batch into one C (atomic accumulation).
+ *   bias: NULL, [N] (bias_on_m == 0) or [M] (bias_on_m == 1).  accumulate != 0: C += instead of C =.
+ *   pitches must be multiples of 4 elements and bases 16-byte aligned (TMA).  This one primitive is the forward, dgrad and
+ *   wgrad of every nn.Linear / 1x1 conv of the path and the five GEMMs of the attention core and its backward. */
+int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a_s1, long long a_s2, const float* B, int b_mn,
+                 long long ldb, long long b_s1, long long b_s2, float* C, long long ldc, long long c_s1, long long c_s2,
+                 int M, int N, int K, int nb1, int nb2, float alpha, const float* bias, int bias_on_m, int accumulate,
+                 void* stream);
+
+/* elementwise */
+int poem_tr_relu(float* y, long long n, void* stream);
+int poem_tr_relu_bwd(float* dy, const float* y, long long n, void* stream);          /* dy *= (y > 0) */
+int poem_tr_gelu(const float* x, float* y, long long n, void* stream);               /* exact erf GELU */
+int poem_tr_gelu_bwd(float* dy, const float* x, long long n, void* stream);
+int poem_tr_axpy(float* y, const float* x, float a, long long n, void* stream);      /* y += a x */
+int poem_tr_affine_rows(const float* x, const float* off, float a, float* out, long long rows, int rows_per_group,
+                        int n_groups, int cols, void* stream);                       /* out = a x + off[group] */
+int poem_tr_colsum(const float* dy, long long ld, long long M, int N, float* out, void* stream);        /* out[n] += */
+int poem_tr_sum_batch(const float* x, int B, long long n, float* out, void* stream);                     /* out += sum_b */
+int poem_tr_bcast_batch(const float* x, int B, long long n, float* out, void* stream);
+
+/* LayerNorm of (x + res) (res may be NULL), eps as given; saves xhat [M x D] and rstd [M] for the backward */
+int poem_tr_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float eps, float* y,
+                      float* xhat, float* rstd, long long M, int D, void* stream);
+int poem_tr_layernorm_bwd(const float* dy, const float* xhat, const float* rstd, const float* gamma, float* dx,
+                          float* dgamma, float* dbeta, long long M, int D, void* stream);   /* dgamma, dbeta += */
+
+/* softmax over rows of length L: P = softmax(S * scale) in place ; dS = P (dP - sum P dP) * scale over dP */
+int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, void* stream);
+int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, void* stream);
+
+/* vector attention (32 neighbours per query); edge e = query * 32 + slot */
+int poem_tr_va_make_idx(const int32_t* local_idx, const int32_t* anchor_idx, int B, int Q, int R, int32_t* gidx, void* stream);
+int poem_tr_va_rel(const float* q_xyz, const float* ref_xyz, const float* anchor_xyz, const int32_t* gidx, long long E,
+                   float* rel, void* stream);
+int poem_tr_lin3_relu(const float* rel, const float* W, const float* b, float* h, long long E, int D, void* stream);
+int poem_tr_lin3_bwd(const float* dh, const float* rel, const float* W, float* dW, float* db, float* drel /* or NULL */,
+                     long long E, int D, void* stream);
+int poem_tr_va_gather_t(const float* q, const float* ktab, const int32_t* gidx, const float* pos, float* t, long long E,
+                        int D, void* stream);
+int poem_tr_va_softmax_agg(float* a_w, const float* vtab, const float* pos, const int32_t* gidx, float scale, float* res,
+                           long long NQ, int D, void* stream);
+int poem_tr_va_softmax_agg_bwd(const float* dres, float* w_da, const float* vtab, const float* pos, const int32_t* gidx,
+                               float scale, float* dvp, long long NQ, int D, void* stream);
+int poem_tr_va_scatter(float* dt_dpos, const float* dvp, const int32_t* gidx, float* dq, float* dktab, float* dvtab,
+                       long long NQ, int D, void* stream);
+int poem_tr_va_drel_scatter(const float* drel, const int32_t* gidx, float* dxyz_q, float* dxyz_ref /* or NULL */,
+                            long long NQ, void* stream);
+
+/* reg_branch.2 : Linear(D, 3) (+ base coordinates) */
+int poem_tr_lin_n3(const float* x, const float* W, const float* b, const float* base, float* y, long long M, int D, void* stream);
+int poem_tr_lin_n3_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, long long M,
+                       int D, void* stream);
+
+/* camera projection of the BPS points + bilinear sampler (planes NCHW, hw x hw) and its scatter backward */
+int poem_tr_project(const float* bps, const float* centre, const float* cam_intr, const float* cam_extr,
+                    const int32_t* img_sample, int NV, int P, float inp_w, float inp_h, float* grid, void* stream);
+int poem_tr_sample(const float* planes, const float* grid, float* S, int NV, int D, int P, int hw, void* stream);
+int poem_tr_sample_bwd(const float* dS, const float* grid, float* dplanes, int NV, int D, int P, int hw, void* stream);
+
+/* cross-view merge (raw `.view` regroup: rows row0[b] + p * n[b] + v) */
+int poem_tr_merge_agg(const float* m, const int32_t* row0, const int32_t* nviews, int B, int P, int Dm, float* agg, void* stream);
+int poem_tr_merge_agg_bwd(const float* dagg, const float* m, const int32_t* row0, const int32_t* nviews, int B, int P,
+                          int Dm, float* dm, void* stream);
+int poem_tr_merge_out(const float* X, const float* y, const int32_t* row0, const int32_t* nviews, int B, int P, int D,
+                      float* out, void* stream);
+int poem_tr_merge_out_bwd(const float* dout, const int32_t* row0, const int32_t* nviews, int B, int P, int D, float* dX,
+                          float* dy, void* stream);
+
+/* gradient clipping as lib/utils/net_utils.py:122-132 applies it (clip_grad_norm_ on every parameter tensor by itself):
+ * sumsq[0] += |g|^2 ; g *= min(1, max_norm / (sqrt(sumsq[0]) + 1e-6)) */
+int poem_tr_sumsq(const float* g, long long n, float* sumsq, void* stream);
+int poem_tr_clip_scale(float* g, long long n, const float* sumsq, float max_norm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -11,7 +11,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("POEM_B200_LIB", os.path.join(CSRC, "libpoem_b200.so"))   # override: kernel experiments
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["poem_b200.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "conv3x3.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh", "hrnet.cuh", "mano.cuh"]
+HEADERS = ["common.cuh", "gemm.cuh", "conv3x3.cuh", "mha.cuh", "simt.cuh", "vecattn.cuh", "hrnet.cuh", "mano.cuh",
+           "sample_merge.cuh", "qchain.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -1,0 +1,393 @@
+// libpoem_train.so: launchers of the training-path primitives declared in include/poem_train.h.
+// Kernels: tgemm.cuh (TF32 tcgen05 GEMM, all operand major-ness combinations, batch + split-K) and train_simt.cuh.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/poem_train.h"
+#include "tgemm.cuh"
+#include "train_simt.cuh"
+
+using namespace poem;
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define TR_CHECK(name)                                                                              \
+  do {                                                                                              \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) return fail(POEM_TR_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" int poem_tr_abi_version(void) { return POEM_TR_ABI_VERSION; }
+extern "C" const char* poem_tr_last_error(void) { return g_err; }
+extern "C" long long poem_tr_kernel_launches(void) { return g_launches.load(); }
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+static inline int grid_for(long long n, int block = 256, int per_sm = 8) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 operand of the GEMM as a rank-4 tensor map (inner, rows, batch1, batch2).
+//   K-major : stored [rows x K]  -> inner = K,    outer = rows, box (32, box_rows)
+//   MN-major: stored [K x rows]  -> inner = rows, outer = K,    box (32, 32)
+static int make_tmap_f32(CUtensorMap* tm, const float* base, int mn_major, long long rows, long long K, long long ld,
+                         long long s1, long long s2, int nb1, int nb2, int box_rows, int* bc1, int* bc2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(POEM_TR_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+  *bc1 = (s1 == 0 || nb1 == 1), *bc2 = (s2 == 0 || nb2 == 1);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3) || (!*bc1 && (s1 & 3)) || (!*bc2 && (s2 & 3)))
+    return fail(POEM_TR_E_ALIGN, "GEMM operand needs a 16-byte aligned base and pitches in multiples of 4 floats (base=%p ld=%lld s1=%lld s2=%lld)",
+                (const void*)base, ld, s1, s2);
+  const long long inner = mn_major ? rows : K, outer = mn_major ? K : rows;
+  if (inner <= 0 || outer <= 0 || ld < inner) return fail(POEM_TR_E_BADARG, "GEMM operand extents (inner=%lld outer=%lld ld=%lld)", inner, outer, ld);
+  cuuint64_t gdim[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(*bc1 ? 1 : nb1), (cuuint64_t)(*bc2 ? 1 : nb2)};
+  const cuuint64_t plane = (cuuint64_t)ld * 4ull * (cuuint64_t)outer;
+  cuuint64_t gstride[3] = {(cuuint64_t)ld * 4ull, *bc1 ? plane : (cuuint64_t)s1 * 4ull, *bc2 ? plane : (cuuint64_t)s2 * 4ull};
+  cuuint32_t box[4] = {32u, (cuuint32_t)(mn_major ? 32 : box_rows), 1u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(POEM_TR_E_CUDA, "cuTensorMapEncodeTiled (fp32 rank 4) failed (%d)", (int)r);
+  return POEM_TR_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tgemm(const CUtensorMap& ta, const CUtensorMap& tb, const TgParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = TgCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "tgemm smem attribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  tgemm_kernel<BN, A_MN, B_MN><<<grid, TG_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  TR_CHECK("tgemm");
+  return POEM_TR_OK;
+}
+template <int BN>
+static int launch_tgemm_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TgParams& p, dim3 grid,
+                              cudaStream_t st) {
+  if (a_mn) return b_mn ? launch_tgemm<BN, true, true>(ta, tb, p, grid, st) : launch_tgemm<BN, true, false>(ta, tb, p, grid, st);
+  return b_mn ? launch_tgemm<BN, false, true>(ta, tb, p, grid, st) : launch_tgemm<BN, false, false>(ta, tb, p, grid, st);
+}
+
+extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a_s1, long long a_s2, const float* B,
+                            int b_mn, long long ldb, long long b_s1, long long b_s2, float* C, long long ldc,
+                            long long c_s1, long long c_s2, int M, int N, int K, int nb1, int nb2, float alpha,
+                            const float* bias, int bias_on_m, int accumulate, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || nb1 < 1 || nb2 < 1) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: bad arguments");
+  const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  CUtensorMap ta, tb;
+  TgParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_tmap_f32(&ta, A, a_mn, M, K, lda, a_s1, a_s2, nb1, nb2, TG_BM, &p.a_bc1, &p.a_bc2);
+  if (rc) return rc;
+  rc = make_tmap_f32(&tb, B, b_mn, N, K, ldb, b_s1, b_s2, nb1, nb2, BN, &p.b_bc1, &p.b_bc2);
+  if (rc) return rc;
+  p.M = M, p.N = N, p.K = K, p.nb1 = nb1, p.nb2 = nb2;
+  p.alpha = alpha, p.bias = bias, p.bias_on_m = bias_on_m;
+  p.C = C, p.ldc = ldc, p.c_s1 = c_s1, p.c_s2 = c_s2;
+  const int tiles = ((M + TG_BM - 1) / TG_BM) * ((N + BN - 1) / BN) * nb1 * nb2;
+  const bool batch_sum = (nb1 > 1 && c_s1 == 0) || (nb2 > 1 && c_s2 == 0);
+  int splits = 1;
+  const int kblocks = (K + TG_BK - 1) / TG_BK;
+  if (tiles < num_sms() && kblocks >= 32) {      // tall reduction (wgrad): spread K over the idle SMs
+    splits = (2 * num_sms() + tiles - 1) / tiles;
+    if (splits > kblocks / 8) splits = kblocks / 8;
+    if (splits < 1) splits = 1;
+  }
+  const int kb_per_split = (kblocks + splits - 1) / splits;
+  splits = (kblocks + kb_per_split - 1) / kb_per_split;
+  p.splits = splits, p.k_per_split = kb_per_split * TG_BK;
+  p.mode = (splits > 1 || batch_sum) ? TG_ATOMIC : (accumulate ? TG_ADD : TG_STORE);
+  if (p.mode == TG_ATOMIC && !accumulate) {      // atomic partial sums need a zeroed destination
+    const int e1 = c_s1 == 0 ? 1 : nb1, e2 = c_s2 == 0 ? 1 : nb2;
+    for (int i2 = 0; i2 < e2; ++i2)
+      for (int i1 = 0; i1 < e1; ++i1) {
+        cudaError_t e = cudaMemset2DAsync(C + i1 * c_s1 + i2 * c_s2, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
+        if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "poem_tr_gemm memset: %s", cudaGetErrorString(e));
+      }
+  }
+  dim3 grid((M + TG_BM - 1) / TG_BM, (N + BN - 1) / BN, nb1 * nb2 * splits);
+  if (grid.y > 65535u || grid.z > 65535u) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: grid too large (%u, %u)", grid.y, grid.z);
+  switch (BN) {
+    case 32: return launch_tgemm_major<32>(a_mn, b_mn, ta, tb, p, grid, st);
+    case 64: return launch_tgemm_major<64>(a_mn, b_mn, ta, tb, p, grid, st);
+    default: return launch_tgemm_major<128>(a_mn, b_mn, ta, tb, p, grid, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SIMT launchers
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" int poem_tr_relu(float* y, long long n, void* stream) {
+  tr_relu_kernel<<<grid_for(n), 256, 0, ST>>>(y, n);
+  TR_CHECK("relu");
+  return 0;
+}
+extern "C" int poem_tr_relu_bwd(float* dy, const float* y, long long n, void* stream) {
+  tr_relu_bwd_kernel<<<grid_for(n), 256, 0, ST>>>(dy, y, n);
+  TR_CHECK("relu_bwd");
+  return 0;
+}
+extern "C" int poem_tr_gelu(const float* x, float* y, long long n, void* stream) {
+  tr_gelu_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, n);
+  TR_CHECK("gelu");
+  return 0;
+}
+extern "C" int poem_tr_gelu_bwd(float* dy, const float* x, long long n, void* stream) {
+  tr_gelu_bwd_kernel<<<grid_for(n), 256, 0, ST>>>(dy, x, n);
+  TR_CHECK("gelu_bwd");
+  return 0;
+}
+extern "C" int poem_tr_axpy(float* y, const float* x, float a, long long n, void* stream) {
+  tr_axpy_kernel<<<grid_for(n), 256, 0, ST>>>(y, x, a, n);
+  TR_CHECK("axpy");
+  return 0;
+}
+extern "C" int poem_tr_affine_rows(const float* x, const float* off, float a, float* out, long long rows,
+                                   int rows_per_group, int n_groups, int cols, void* stream) {
+  tr_affine_rows_kernel<<<grid_for(rows * cols), 256, 0, ST>>>(x, off, a, out, rows, rows_per_group, n_groups, cols);
+  TR_CHECK("affine_rows");
+  return 0;
+}
+extern "C" int poem_tr_colsum(const float* dy, long long ld, long long M, int N, float* out, void* stream) {
+  long long slabs = (M + 255) / 256;
+  if (slabs > 4 * num_sms()) slabs = 4 * num_sms();
+  if (slabs < 1) slabs = 1;
+  dim3 grid((N + 31) / 32, (unsigned)slabs), block(32, 8);
+  tr_colsum_kernel<<<grid, block, 0, ST>>>(dy, ld, M, N, out);
+  TR_CHECK("colsum");
+  return 0;
+}
+extern "C" int poem_tr_sum_batch(const float* x, int B, long long n, float* out, void* stream) {
+  tr_sum_batch_kernel<<<grid_for(n), 256, 0, ST>>>(x, B, n, out);
+  TR_CHECK("sum_batch");
+  return 0;
+}
+extern "C" int poem_tr_bcast_batch(const float* x, int B, long long n, float* out, void* stream) {
+  tr_bcast_batch_kernel<<<grid_for(n * B), 256, 0, ST>>>(x, B, n, out);
+  TR_CHECK("bcast_batch");
+  return 0;
+}
+
+extern "C" int poem_tr_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float eps,
+                                 float* y, float* xhat, float* rstd, long long M, int D, void* stream) {
+  if (D > 1024) return fail(POEM_TR_E_BADARG, "layernorm: D = %d > 1024", D);
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((M + wpb - 1) / wpb);
+  if (D <= 128) tr_layernorm_fwd_kernel<4><<<grid, wpb * 32, 0, ST>>>(x, res, gamma, beta, eps, y, xhat, rstd, M, D);
+  else if (D <= 256) tr_layernorm_fwd_kernel<8><<<grid, wpb * 32, 0, ST>>>(x, res, gamma, beta, eps, y, xhat, rstd, M, D);
+  else if (D <= 512) tr_layernorm_fwd_kernel<16><<<grid, wpb * 32, 0, ST>>>(x, res, gamma, beta, eps, y, xhat, rstd, M, D);
+  else tr_layernorm_fwd_kernel<32><<<grid, wpb * 32, 0, ST>>>(x, res, gamma, beta, eps, y, xhat, rstd, M, D);
+  TR_CHECK("layernorm");
+  return 0;
+}
+extern "C" int poem_tr_layernorm_bwd(const float* dy, const float* xhat, const float* rstd, const float* gamma, float* dx,
+                                     float* dgamma, float* dbeta, long long M, int D, void* stream) {
+  if (D > 1024) return fail(POEM_TR_E_BADARG, "layernorm_bwd: D = %d > 1024", D);
+  const int wpb = 8;
+  long long g = (M + wpb - 1) / wpb;
+  if (g > 2 * num_sms()) g = 2 * num_sms();
+  const size_t sh = (size_t)2 * D * 4;
+  if (D <= 128) tr_layernorm_bwd_kernel<4><<<(unsigned)g, wpb * 32, sh, ST>>>(dy, xhat, rstd, gamma, dx, dgamma, dbeta, M, D);
+  else if (D <= 256) tr_layernorm_bwd_kernel<8><<<(unsigned)g, wpb * 32, sh, ST>>>(dy, xhat, rstd, gamma, dx, dgamma, dbeta, M, D);
+  else if (D <= 512) tr_layernorm_bwd_kernel<16><<<(unsigned)g, wpb * 32, sh, ST>>>(dy, xhat, rstd, gamma, dx, dgamma, dbeta, M, D);
+  else tr_layernorm_bwd_kernel<32><<<(unsigned)g, wpb * 32, sh, ST>>>(dy, xhat, rstd, gamma, dx, dgamma, dbeta, M, D);
+  TR_CHECK("layernorm_bwd");
+  return 0;
+}
+
+extern "C" int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, void* stream) {
+  if (rows > 0x7fffffffLL) return fail(POEM_TR_E_BADARG, "softmax_rows: too many rows");
+  tr_softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
+  TR_CHECK("softmax_rows");
+  return 0;
+}
+extern "C" int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, void* stream) {
+  if (rows > 0x7fffffffLL) return fail(POEM_TR_E_BADARG, "softmax_rows_bwd: too many rows");
+  tr_softmax_rows_bwd_kernel<<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
+  TR_CHECK("softmax_rows_bwd");
+  return 0;
+}
+
+extern "C" int poem_tr_va_make_idx(const int32_t* local_idx, const int32_t* anchor_idx, int B, int Q, int R, int32_t* gidx,
+                                   void* stream) {
+  tr_va_make_idx_kernel<<<grid_for((long long)B * Q * TR_NBR), 256, 0, ST>>>(local_idx, anchor_idx, B, Q, R, gidx);
+  TR_CHECK("va_make_idx");
+  return 0;
+}
+extern "C" int poem_tr_va_rel(const float* q_xyz, const float* ref_xyz, const float* anchor_xyz, const int32_t* gidx,
+                              long long E, float* rel, void* stream) {
+  tr_va_rel_kernel<<<grid_for(E), 256, 0, ST>>>(q_xyz, ref_xyz, anchor_xyz, gidx, E, rel);
+  TR_CHECK("va_rel");
+  return 0;
+}
+extern "C" int poem_tr_lin3_relu(const float* rel, const float* W, const float* b, float* h, long long E, int D, void* stream) {
+  tr_lin3_relu_kernel<<<grid_for(E * D), 256, 0, ST>>>(rel, W, b, h, E, D);
+  TR_CHECK("lin3_relu");
+  return 0;
+}
+extern "C" int poem_tr_lin3_bwd(const float* dh, const float* rel, const float* W, float* dW, float* db, float* drel,
+                                long long E, int D, void* stream) {
+  long long blocks = (E + 511) / 512;
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  if (blocks < 1) blocks = 1;
+  tr_lin3_wgrad_kernel<<<(unsigned)blocks, 256, 0, ST>>>(dh, rel, dW, db, E, D);
+  TR_CHECK("lin3_wgrad");
+  if (drel) {
+    tr_lin3_dgrad_kernel<<<grid_for(E * 32), 256, 0, ST>>>(dh, W, drel, E, D);
+    TR_CHECK("lin3_dgrad");
+  }
+  return 0;
+}
+extern "C" int poem_tr_va_gather_t(const float* q, const float* ktab, const int32_t* gidx, const float* pos, float* t,
+                                   long long E, int D, void* stream) {
+  tr_va_gather_t_kernel<<<grid_for(E * D), 256, 0, ST>>>(q, ktab, gidx, pos, t, E, D);
+  TR_CHECK("va_gather_t");
+  return 0;
+}
+extern "C" int poem_tr_va_softmax_agg(float* a_w, const float* vtab, const float* pos, const int32_t* gidx, float scale,
+                                      float* res, long long NQ, int D, void* stream) {
+  tr_va_softmax_agg_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D);
+  TR_CHECK("va_softmax_agg");
+  return 0;
+}
+extern "C" int poem_tr_va_softmax_agg_bwd(const float* dres, float* w_da, const float* vtab, const float* pos,
+                                          const int32_t* gidx, float scale, float* dvp, long long NQ, int D, void* stream) {
+  tr_va_softmax_agg_bwd_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(dres, w_da, vtab, pos, gidx, scale, dvp, NQ, D);
+  TR_CHECK("va_softmax_agg_bwd");
+  return 0;
+}
+extern "C" int poem_tr_va_scatter(float* dt_dpos, const float* dvp, const int32_t* gidx, float* dq, float* dktab,
+                                  float* dvtab, long long NQ, int D, void* stream) {
+  tr_va_scatter_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(dt_dpos, dvp, gidx, dq, dktab, dvtab, NQ, D);
+  TR_CHECK("va_scatter");
+  return 0;
+}
+extern "C" int poem_tr_va_drel_scatter(const float* drel, const int32_t* gidx, float* dxyz_q, float* dxyz_ref, long long NQ,
+                                       void* stream) {
+  tr_va_drel_scatter_kernel<<<grid_for(NQ * 3), 256, 0, ST>>>(drel, gidx, dxyz_q, dxyz_ref, NQ);
+  TR_CHECK("va_drel_scatter");
+  return 0;
+}
+
+extern "C" int poem_tr_lin_n3(const float* x, const float* W, const float* b, const float* base, float* y, long long M,
+                              int D, void* stream) {
+  const int wpb = 8;
+  tr_lin_n3_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, ST>>>(x, W, b, base, y, M, D);
+  TR_CHECK("lin_n3");
+  return 0;
+}
+extern "C" int poem_tr_lin_n3_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db,
+                                  long long M, int D, void* stream) {
+  long long g = M < 4 * num_sms() ? M : 4 * num_sms();
+  if (g < 1) g = 1;
+  tr_lin_n3_bwd_kernel<<<(unsigned)g, 256, 0, ST>>>(dy, x, W, dx, dW, db, M, D);
+  TR_CHECK("lin_n3_bwd");
+  return 0;
+}
+
+extern "C" int poem_tr_project(const float* bps, const float* centre, const float* cam_intr, const float* cam_extr,
+                               const int32_t* img_sample, int NV, int P, float inp_w, float inp_h, float* grid, void* stream) {
+  tr_project_kernel<<<grid_for((long long)NV * P), 256, 0, ST>>>(bps, centre, cam_intr, cam_extr, img_sample, NV, P, inp_w, inp_h, grid);
+  TR_CHECK("project");
+  return 0;
+}
+extern "C" int poem_tr_sample(const float* planes, const float* grid, float* S, int NV, int D, int P, int hw, void* stream) {
+  tr_sample_fwd_kernel<<<grid_for((long long)NV * P, 128, 16), 128, 0, ST>>>(planes, grid, S, NV, D, P, hw);
+  TR_CHECK("sample");
+  return 0;
+}
+extern "C" int poem_tr_sample_bwd(const float* dS, const float* grid, float* dplanes, int NV, int D, int P, int hw, void* stream) {
+  tr_sample_bwd_kernel<<<grid_for((long long)NV * P, 128, 16), 128, 0, ST>>>(dS, grid, dplanes, NV, D, P, hw);
+  TR_CHECK("sample_bwd");
+  return 0;
+}
+
+extern "C" int poem_tr_merge_agg(const float* m, const int32_t* row0, const int32_t* nviews, int B, int P, int Dm,
+                                 float* agg, void* stream) {
+  if (Dm > 256) return fail(POEM_TR_E_BADARG, "merge_agg: Dm = %d > 256", Dm);
+  const long long total = (long long)B * P;
+  tr_merge_agg_kernel<<<(unsigned)((total + 7) / 8), 256, 0, ST>>>(m, row0, nviews, P, Dm, agg, total);
+  TR_CHECK("merge_agg");
+  return 0;
+}
+extern "C" int poem_tr_merge_agg_bwd(const float* dagg, const float* m, const int32_t* row0, const int32_t* nviews, int B,
+                                     int P, int Dm, float* dm, void* stream) {
+  if (Dm > 256) return fail(POEM_TR_E_BADARG, "merge_agg_bwd: Dm = %d > 256", Dm);
+  const long long total = (long long)B * P;
+  tr_merge_agg_bwd_kernel<<<(unsigned)((total + 7) / 8), 256, 0, ST>>>(dagg, m, row0, nviews, P, Dm, dm, total);
+  TR_CHECK("merge_agg_bwd");
+  return 0;
+}
+extern "C" int poem_tr_merge_out(const float* X, const float* y, const int32_t* row0, const int32_t* nviews, int B, int P,
+                                 int D, float* out, void* stream) {
+  const long long total = (long long)B * P * D;
+  tr_merge_out_kernel<<<grid_for(total), 256, 0, ST>>>(X, y, row0, nviews, P, D, out, total);
+  TR_CHECK("merge_out");
+  return 0;
+}
+extern "C" int poem_tr_merge_out_bwd(const float* dout, const int32_t* row0, const int32_t* nviews, int B, int P, int D,
+                                     float* dX, float* dy, void* stream) {
+  const long long total = (long long)B * P * D;
+  tr_merge_out_bwd_kernel<<<grid_for(total), 256, 0, ST>>>(dout, row0, nviews, P, D, dX, dy, total);
+  TR_CHECK("merge_out_bwd");
+  return 0;
+}
+
+extern "C" int poem_tr_sumsq(const float* g, long long n, float* sumsq, void* stream) {
+  tr_sumsq_kernel<<<grid_for(n, 256, 2), 256, 0, ST>>>(g, n, sumsq);
+  TR_CHECK("sumsq");
+  return 0;
+}
+extern "C" int poem_tr_clip_scale(float* g, long long n, const float* sumsq, float max_norm, void* stream) {
+  tr_clip_scale_kernel<<<grid_for(n), 256, 0, ST>>>(g, n, sumsq, max_norm);
+  TR_CHECK("clip_scale");
+  return 0;
+}

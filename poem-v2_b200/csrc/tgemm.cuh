@@ -1,0 +1,224 @@
+// TF32 tcgen05 GEMM of the training path:  C[M,N] (+)= alpha * op(A) · op(B)^T (+ bias),  fp32 in HBM, fp32 accumulate.
+//   Each operand is either K-major (stored [rows x K], K contiguous) or MN-major (stored [K x rows], rows contiguous),
+//   so that the three GEMMs of a Linear layer read the SAME row-major tensors without a transpose pass:
+//     forward  y  = x · W^T      A = x  (K-major)   B = W  (K-major)
+//     dgrad    dx = dy · W       A = dy (K-major)   B = W  (MN-major: stored [N_out x K_in] = [K_g x N_g])
+//     wgrad    dW = dy^T · x     A = dy (MN-major)  B = x  (MN-major), reduction over the token rows
+//   and likewise Q·K^T, P·V, P^T·dO, dS·K, dS^T·Q of the attention backward (reference: autograd of
+//   lib/models/bricks/pt_metro_transformer.py:57-91, point_transformers.py:70-156, heads/ptEmb_head.py:745-771).
+//   TMA stages 128-byte (32 x fp32) SWIZZLE_128B rows; `tcgen05.mma kind::tf32` consumes 8 K-values per instruction;
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM), warps 2..5 = epilogue.  One 128 x BN tile per CTA, 2 CTAs/SM.
+//   A batch (two strides per operand, rank-4 tensor maps: per-slice bounds, zero fill outside) and a K split with atomic
+//   accumulation (tall reductions: wgrad) ride in blockIdx.z.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace poem {
+
+constexpr int TG_BM = 128;
+constexpr int TG_BK = 32;          // fp32 elements per 128-byte swizzle row
+constexpr int TG_STAGES = 3;
+constexpr int TG_THREADS = 192;
+constexpr int TG_ATOM_BYTES = TG_BK * 128;   // one MN-major atom: 32 K rows x 128 B
+
+enum TgMode : int { TG_STORE = 0, TG_ADD = 1, TG_ATOMIC = 2 };
+
+struct TgParams {
+  int M, N, K;
+  int nb1, nb2;            // batch extents (>= 1); blockIdx.z = (split * nb2 + b2) * nb1 + b1
+  int a_bc1, a_bc2;        // 1: operand A is shared along that batch axis (coordinate forced to 0)
+  int b_bc1, b_bc2;
+  int splits;              // K splits (>= 1); > 1 requires mode == TG_ATOMIC
+  int k_per_split;         // multiple of TG_BK
+  float alpha;
+  const float* bias;       // nullptr or [N] (bias_on_m == 0) / [M] (bias_on_m == 1); added by split 0 only
+  int bias_on_m;
+  float* C;
+  long long ldc, c_s1, c_s2;
+  int mode;
+};
+
+template <int BN>
+struct TgCfg {
+  static constexpr int kABytes = TG_BM * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = TG_STAGES * kStageBytes + 256 + 1024;   // + barriers + alignment slack
+};
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// kind::tf32: c_format F32 (1) [4,6); a/b_format TF32 (2) [7,10) / [10,13); a_major bit 15, b_major bit 16; N>>3 [17,23); M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Shared-memory descriptor of an MN-major fp32 (TF32) operand: 32-bit MN-major operands exist only in the
+// SWIZZLE_128B_BASE32B layout (layout type 1: 32-byte chunks XOR-swizzled inside 128-byte rows, pattern period 4 rows;
+// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Canonical form in 16-byte units
+// ((8, n), (4, k)) : ((1, LBO), (8, SBO)): a K row holds 32 consecutive MN values (128 B), SBO = 4 rows = 512 B,
+// LBO = distance to the next 32-value MN atom.
+__device__ __forceinline__ uint64_t make_mnmajor_desc_f32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(512u >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TG_THREADS, 2)
+tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TgParams p) {
+  using Cfg = TgCfg<BN>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                 // [TG_STAGES]
+  uint64_t* empty_bar = bars + TG_STAGES;    // [TG_STAGES]
+  uint64_t* acc_full = bars + 2 * TG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TG_STAGES + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TG_BM;
+  const int n0 = blockIdx.y * BN;
+  int z = blockIdx.z;
+  const int b1 = z % p.nb1;
+  z /= p.nb1;
+  const int b2 = z % p.nb2;
+  const int split = z / p.nb2;
+  const int k_begin = split * p.k_per_split;
+  const int k_end = min(p.K, k_begin + p.k_per_split);
+  const int n_kb = (k_end - k_begin + TG_BK - 1) / TG_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < TG_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const int a1 = p.a_bc1 ? 0 : b1, a2 = p.a_bc2 ? 0 : b2;
+      const int bb1 = p.b_bc1 ? 0 : b1, bb2 = p.b_bc2 ? 0 : b2;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int st = kb % TG_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TG_STAGES) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+        uint8_t* sa = smem + st * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int k0 = k_begin + kb * TG_BK;
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < TG_BM / 32; ++j) tma_load_4d(sa + j * TG_ATOM_BYTES, &tmap_a, &full_bar[st], m0 + 32 * j, k0, a1, a2);
+        } else {
+          tma_load_4d(sa, &tmap_a, &full_bar[st], k0, m0, a1, a2);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * TG_ATOM_BYTES, &tmap_b, &full_bar[st], n0 + 32 * j, k0, bb1, bb2);
+        } else {
+          tma_load_4d(sb, &tmap_b, &full_bar[st], k0, n0, bb1, bb2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32(TG_BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int st = kb % TG_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TG_STAGES) & 1;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + st * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < TG_BK / 8; ++k) {      // 8 K-values per kind::tf32 instruction
+          const uint64_t da = A_MN ? make_mnmajor_desc_f32(a_addr + k * 1024, TG_ATOM_BYTES) : make_kmajor_desc<128>(a_addr) + 2 * k;
+          const uint64_t db = B_MN ? make_mnmajor_desc_f32(b_addr + k * 1024, TG_ATOM_BYTES) : make_kmajor_desc<128>(b_addr) + 2 * k;
+          umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[st]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ===================== epilogue: TMEM lane quarter = warp % 4 =====================
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    const bool with_bias = (p.bias != nullptr) && split == 0;
+    float* crow = p.C + (long long)b1 * p.c_s1 + (long long)b2 * p.c_s2 + (long long)row * p.ldc;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_s1 & 3) == 0) && ((p.c_s2 & 3) == 0);
+    const float bias_m = (with_bias && p.bias_on_m && row < p.M) ? p.bias[row] : 0.f;
+    if (n_kb > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after_sync();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      if (n_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      const int col0 = n0 + c * 32;
+      if (row >= p.M || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = p.alpha * __uint_as_float(r[i]) + bias_m;
+        if (with_bias && !p.bias_on_m && col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+      }
+      if (p.mode == TG_ATOMIC) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) atomicAdd(crow + col0 + i, v[i]);
+      } else if (vec_ok && col0 + 32 <= p.N) {
+        float4* dst = reinterpret_cast<float4*>(crow + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (p.mode == TG_ADD) {
+            const float4 old = dst[i];
+            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+          }
+          dst[i] = o;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) crow[col0 + i] = (p.mode == TG_ADD ? crow[col0 + i] : 0.f) + v[i];
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+  }
+}
+
+}  // namespace poem

@@ -1,0 +1,646 @@
+// SIMT kernels of the training path (fp32): everything around the TF32 GEMMs of tgemm.cuh — activations, LayerNorm,
+// row softmax of the BERT cross-attention, the per-edge pieces of the vector attention (32 neighbours per query), the
+// bilinear sampler and the cross-view merge, each with its backward.  Reference: the autograd graph of
+// lib/models/heads/ptEmb_head.py:745-771,825-964, lib/models/bricks/pt_metro_transformer.py:34-91,
+// lib/models/bricks/point_transformers.py:70-156 (eval-mode arithmetic restated in oracle/poem_oracle.py).
+#pragma once
+#include "common.cuh"
+
+namespace poem {
+
+constexpr int TR_NBR = 32;   // neighbours per query (N_NEIGHBOR == N_NEIGHBOR_QUERY == 32 in every release config)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void tr_relu_kernel(float* y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaxf(y[i], 0.f);
+}
+__global__ void tr_relu_bwd_kernel(float* dy, const float* y, long long n) {   // dy *= (y > 0), y = ReLU output
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+__global__ void tr_gelu_kernel(const float* x, float* y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  }
+}
+__global__ void tr_gelu_bwd_kernel(float* dy, const float* x, long long n) {   // dy *= d/dx [x Phi(x)]
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * v * v);
+    dy[i] *= cdf + v * pdf;
+  }
+}
+__global__ void tr_axpy_kernel(float* y, const float* x, float a, long long n) {   // y += a * x
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+// out[r, :] = a * x[r, :] + off[(r / rows_per_group), :]   (cols <= 4; the metric <-> normalised coordinate maps)
+__global__ void tr_affine_rows_kernel(const float* x, const float* off, float a, float* out, long long rows,
+                                      int rows_per_group, int n_groups, int cols) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows * cols; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    const int g = (int)((r / rows_per_group) % n_groups);
+    out[i] = a * x[i] + (off ? off[g * cols + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums (bias gradients)
+// out[n] += sum_m dy[m, n]     grid (ceil(N/32), row slabs), block (32, 8)
+__global__ void tr_colsum_kernel(const float* dy, long long ld, long long M, int N, float* out) {
+  __shared__ float part[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (n < N)
+    for (long long m = blockIdx.y * 8 + threadIdx.y; m < M; m += (long long)gridDim.y * 8) acc += dy[m * ld + n];
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+// out[r, :] += sum_b x[b, r, :]    (gradient of a table broadcast over the batch: query_feat_embedding)
+__global__ void tr_sum_batch_kernel(const float* x, int B, long long n, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += x[b * n + i];
+    out[i] += s;
+  }
+}
+__global__ void tr_bcast_batch_kernel(const float* x, int B, long long n, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n * B; i += (long long)gridDim.x * blockDim.x)
+    out[i] = x[i % n];
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm (+ residual)
+// y = LN(x + res) * gamma + beta ; saves xhat and rstd.  One warp per row, D <= 1024.
+template <int kMaxPerLane>
+__global__ void tr_layernorm_fwd_kernel(const float* x, const float* res, const float* gamma, const float* beta,
+                                        float eps, float* y, float* xhat, float* rstd_out, long long M, int D) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[kMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < D) ? x[row * D + c] + (res ? res[row * D + c] : 0.f) : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + 32 * i;
+    const float d = (c < D) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + 32 * i;
+    if (c < D) {
+      const float h = (v[i] - mean) * rstd;
+      xhat[row * D + c] = h;
+      y[row * D + c] = h * gamma[c] + beta[c];
+    }
+  }
+  if (lane == 0) rstd_out[row] = rstd;
+}
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma ;  dgamma += sum dy * xhat ; dbeta += sum dy
+// one warp per row; each block folds its rows' dgamma/dbeta in shared memory, then one atomic per column.
+template <int kMaxPerLane>
+__global__ void tr_layernorm_bwd_kernel(const float* dy, const float* xhat, const float* rstd, const float* gamma,
+                                        float* dx, float* dgamma, float* dbeta, long long M, int D) {
+  extern __shared__ float sh[];   // [2 * D]
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
+    float g[kMaxPerLane], h[kMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        const float d = dy[row * D + c];
+        h[i] = xhat[row * D + c];
+        g[i] = d * gamma[c];
+        atomicAdd(&sh[c], d * h[i]);
+        atomicAdd(&sh[D + c], d);
+      } else {
+        g[i] = 0.f, h[i] = 0.f;
+      }
+      s1 += g[i];
+      s2 += g[i] * h[i];
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+    const float r = rstd[row];
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) dx[row * D + c] = r * (g[i] - s1 - h[i] * s2);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, sh[i]);
+    atomicAdd(dbeta + i, sh[D + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ row softmax (BERT attention)
+// P = softmax(S * scale) in place; one block (256 threads) per row of length L
+__global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  float* row = S + (long long)blockIdx.x * L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, row[i]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]);
+    bc = t;
+  }
+  __syncthreads();
+  m = bc;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float e = __expf((row[i] - m) * scale);
+    row[i] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    bc = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bc;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] *= inv;
+}
+// dS = P * (dP - sum(P * dP)) * scale, written over dP
+__global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, float scale) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const float* prow = P + (long long)blockIdx.x * L;
+  float* drow = dP + (long long)blockIdx.x * L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += prow[i] * drow[i];
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    bc = t;
+  }
+  __syncthreads();
+  const float dot = bc;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) drow[i] = prow[i] * (drow[i] - dot) * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ vector attention: edges
+// Edge e = (query i, neighbour slot j) = i * 32 + j.  gidx[e] = global row of the neighbour in the key/value tables.
+// local idx (B, Q, 32) -> global rows b * R + idx ; anchors (32) broadcast to every query (block 0)
+__global__ void tr_va_make_idx_kernel(const int* local_idx, const int* anchor_idx, int B, int Q, int R, int* gidx) {
+  const long long n = (long long)B * Q * TR_NBR;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(e / ((long long)Q * TR_NBR));
+    const int li = anchor_idx ? anchor_idx[e % TR_NBR] : local_idx[e];
+    gidx[e] = b * R + li;
+  }
+}
+// rel[e] = q_xyz[i] - (anchor_xyz[j] | ref_xyz[gidx[e]])
+__global__ void tr_va_rel_kernel(const float* q_xyz, const float* ref_xyz, const float* anchor_xyz, const int* gidx,
+                                 long long E, float* rel) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / TR_NBR;
+    const float* r = anchor_xyz ? anchor_xyz + 3 * (e % TR_NBR) : ref_xyz + 3 * (long long)gidx[e];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rel[3 * e + k] = q_xyz[3 * i + k] - r[k];
+  }
+}
+// h[e, :] = relu(W[:, 0:3] . rel[e] + b)      (fc_delta.0: Linear(3, D) + ReLU)   block = D threads? -> thread per (e, c)
+__global__ void tr_lin3_relu_kernel(const float* rel, const float* W, const float* b, float* h, long long E, int D) {
+  const long long n = E * D;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t / D;
+    const int c = (int)(t % D);
+    const float v = W[3 * c] * rel[3 * e] + W[3 * c + 1] * rel[3 * e + 1] + W[3 * c + 2] * rel[3 * e + 2] + b[c];
+    h[t] = fmaxf(v, 0.f);
+  }
+}
+// backward of the above given dh (already masked by the ReLU):
+//   wgrad: dW[c, k] += sum_e dh[e, c] rel[e, k] ; db[c] += sum_e dh[e, c]      thread = channel, block = edge slab
+//   dgrad: drel[e, k] = sum_c dh[e, c] W[c, k]                                  one warp per edge
+__global__ void tr_lin3_wgrad_kernel(const float* dh, const float* rel, float* dW, float* db, long long E, int D) {
+  const long long per_block = (E + gridDim.x - 1) / gridDim.x;
+  const long long e0 = blockIdx.x * per_block, e1 = min(E, e0 + per_block);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, bb = 0.f;
+    for (long long e = e0; e < e1; ++e) {
+      const float g = dh[e * D + c];
+      w0 += g * rel[3 * e], w1 += g * rel[3 * e + 1], w2 += g * rel[3 * e + 2], bb += g;
+    }
+    atomicAdd(dW + 3 * c, w0);
+    atomicAdd(dW + 3 * c + 1, w1);
+    atomicAdd(dW + 3 * c + 2, w2);
+    atomicAdd(db + c, bb);
+  }
+}
+__global__ void tr_lin3_dgrad_kernel(const float* dh, const float* W, float* drel, long long E, int D) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long e = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); e < E; e += (long long)gridDim.x * wpb) {
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float g = dh[e * D + c];
+      d0 += g * W[3 * c], d1 += g * W[3 * c + 1], d2 += g * W[3 * c + 2];
+    }
+    d0 = warp_sum(d0), d1 = warp_sum(d1), d2 = warp_sum(d2);
+    if (lane == 0) drel[3 * e] = d0, drel[3 * e + 1] = d1, drel[3 * e + 2] = d2;
+  }
+}
+// t[e, :] = q[i, :] - ktab[gidx[e], :] + pos[e, :]
+__global__ void tr_va_gather_t_kernel(const float* q, const float* ktab, const int* gidx, const float* pos, float* t,
+                                      long long E, int D) {
+  const long long n = E * D;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const long long e = x / D;
+    const int c = (int)(x % D);
+    t[x] = q[(e / TR_NBR) * D + c] - ktab[(long long)gidx[e] * D + c] + pos[x];
+  }
+}
+// w = softmax_j(a * scale) per (query, channel), written over a ; res[i, c] = sum_j w * (vtab[gidx] + pos)
+__global__ void tr_va_softmax_agg_kernel(float* a, const float* vtab, const float* pos, const int* gidx, float scale,
+                                         float* res, long long NQ, int D) {
+  const long long n = NQ * D;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const long long i = x / D;
+    const int c = (int)(x % D);
+    float v[TR_NBR];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TR_NBR; ++j) {
+      v[j] = a[(i * TR_NBR + j) * D + c] * scale;
+      m = fmaxf(m, v[j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < TR_NBR; ++j) {
+      v[j] = __expf(v[j] - m);
+      s += v[j];
+    }
+    const float inv = 1.0f / s;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < TR_NBR; ++j) {
+      const long long e = i * TR_NBR + j;
+      const float w = v[j] * inv;
+      a[e * D + c] = w;
+      acc += w * (vtab[(long long)gidx[e] * D + c] + pos[e * D + c]);
+    }
+    res[x] = acc;
+  }
+}
+// given dres: da (over w) = w * (dw - sum_j w dw) * scale with dw = dres * (v + pos) ; dvp = w * dres
+__global__ void tr_va_softmax_agg_bwd_kernel(const float* dres, float* w_da, const float* vtab, const float* pos,
+                                             const int* gidx, float scale, float* dvp, long long NQ, int D) {
+  const long long n = NQ * D;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const long long i = x / D;
+    const int c = (int)(x % D);
+    const float g = dres[x];
+    float w[TR_NBR], dw[TR_NBR];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < TR_NBR; ++j) {
+      const long long e = i * TR_NBR + j;
+      w[j] = w_da[e * D + c];
+      dw[j] = g * (vtab[(long long)gidx[e] * D + c] + pos[e * D + c]);
+      dot += w[j] * dw[j];
+    }
+#pragma unroll
+    for (int j = 0; j < TR_NBR; ++j) {
+      const long long e = i * TR_NBR + j;
+      w_da[e * D + c] = w[j] * (dw[j] - dot) * scale;
+      dvp[e * D + c] = w[j] * g;
+    }
+  }
+}
+// dq[i] += sum_j dt ; dktab[gidx] -= dt ; dvtab[gidx] += dvp ; dpos = dt + dvp (over dt)
+__global__ void tr_va_scatter_kernel(float* dt_dpos, const float* dvp, const int* gidx, float* dq, float* dktab,
+                                     float* dvtab, long long NQ, int D) {
+  const long long n = NQ * D;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const long long i = x / D;
+    const int c = (int)(x % D);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < TR_NBR; ++j) {
+      const long long e = i * TR_NBR + j;
+      const float d = dt_dpos[e * D + c];
+      const float p = dvp[e * D + c];
+      acc += d;
+      const long long r = (long long)gidx[e] * D + c;
+      atomicAdd(dktab + r, -d);
+      atomicAdd(dvtab + r, p);
+      dt_dpos[e * D + c] = d + p;
+    }
+    dq[x] += acc;
+  }
+}
+// dxyz_q[i] += sum_j drel[e] ; dxyz_ref[gidx[e]] -= drel[e] (when the neighbour coordinates are differentiable)
+__global__ void tr_va_drel_scatter_kernel(const float* drel, const int* gidx, float* dxyz_q, float* dxyz_ref, long long NQ) {
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < NQ * 3; x += (long long)gridDim.x * blockDim.x) {
+    const long long i = x / 3;
+    const int k = (int)(x % 3);
+    float acc = 0.f;
+    for (int j = 0; j < TR_NBR; ++j) {
+      const long long e = i * TR_NBR + j;
+      const float d = drel[3 * e + k];
+      acc += d;
+      if (dxyz_ref) atomicAdd(dxyz_ref + 3 * (long long)gidx[e] + k, -d);
+    }
+    atomicAdd(dxyz_q + x, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ reg_branch.2: Linear(D, 3)
+// y[m, :] = x[m, :] . W^T + b + base[m, :]     one warp per row
+__global__ void tr_lin_n3_kernel(const float* x, const float* W, const float* b, const float* base, float* y, long long M, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = x[row * D + c];
+    a0 += v * W[c], a1 += v * W[D + c], a2 += v * W[2 * D + c];
+  }
+  a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2);
+  if (lane == 0) {
+    y[3 * row] = a0 + b[0] + (base ? base[3 * row] : 0.f);
+    y[3 * row + 1] = a1 + b[1] + (base ? base[3 * row + 1] : 0.f);
+    y[3 * row + 2] = a2 + b[2] + (base ? base[3 * row + 2] : 0.f);
+  }
+}
+// dx[m, c] = sum_k dy[m, k] W[k, c] ; dW[k, c] += sum_m dy[m, k] x[m, c] ; db[k] += sum_m dy[m, k]
+__global__ void tr_lin_n3_bwd_kernel(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db,
+                                     long long M, int D) {
+  // thread = channel c (blockDim.x >= D handled by loop), block strides over row slabs
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float w0 = W[c], w1 = W[D + c], w2 = W[2 * D + c];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+      const float d0 = dy[3 * m], d1 = dy[3 * m + 1], d2 = dy[3 * m + 2];
+      const float v = x[m * D + c];
+      dx[m * D + c] = d0 * w0 + d1 * w1 + d2 * w2;
+      g0 += d0 * v, g1 += d1 * v, g2 += d2 * v;
+    }
+    atomicAdd(dW + c, g0);
+    atomicAdd(dW + D + c, g1);
+    atomicAdd(dW + 2 * D + c, g2);
+  }
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (long long m = blockIdx.x; m < M; m += gridDim.x) s += dy[3 * m + threadIdx.x];
+    atomicAdd(db + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ projection + bilinear sampler
+// uv[img, p] = pixel coordinates of BPS point p of the image's sample in the image's camera, in grid_sample units
+// (ptEmb_head.py:873-883, lib/utils/transform.py:898-930): T = inverse(cam_extr), q = K (R x + t), uv = q.xy / z / inp_res * 2 - 1
+__global__ void tr_project_kernel(const float* bps, const float* centre, const float* cam_intr, const float* cam_extr,
+                                  const int* img_sample, int NV, int P, float inp_w, float inp_h, float* grid) {
+  const long long n = (long long)NV * P;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(x / P);
+    const int pidx = (int)(x % P);
+    const float* E = cam_extr + 16 * img;
+    const float* K = cam_intr + 9 * img;
+    // inverse of the affine [A | t] (rows 0..2 of the 4x4): A^-1 by cofactors, t' = -A^-1 t
+    const float a00 = E[0], a01 = E[1], a02 = E[2], a10 = E[4], a11 = E[5], a12 = E[6], a20 = E[8], a21 = E[9], a22 = E[10];
+    const float c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const float c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+    const float c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+    const float idet = 1.0f / (a00 * c00 + a01 * c10 + a02 * c20);
+    const int b = img_sample[img];
+    const float X = bps[3 * pidx] + centre[3 * b] - E[3], Y = bps[3 * pidx + 1] + centre[3 * b + 1] - E[7],
+                Z = bps[3 * pidx + 2] + centre[3 * b + 2] - E[11];
+    const float xc = (c00 * X + c01 * Y + c02 * Z) * idet, yc = (c10 * X + c11 * Y + c12 * Z) * idet,
+                zc = (c20 * X + c21 * Y + c22 * Z) * idet;
+    const float qx = K[0] * xc + K[1] * yc + K[2] * zc, qy = K[3] * xc + K[4] * yc + K[5] * zc;
+    float qz = K[6] * xc + K[7] * yc + K[8] * zc;
+    if (fabsf(qz) < 1e-7f) qz = 1e-7f;
+    grid[2 * x] = qx / qz / inp_w * 2.f - 1.f;
+    grid[2 * x + 1] = qy / qz / inp_h * 2.f - 1.f;
+  }
+}
+__device__ __forceinline__ void bilinear_taps(float gx, float gy, int W, int H, int (&off)[4], float (&wt)[4]) {
+  const float ix = ((gx + 1.f) * W - 1.f) * 0.5f, iy = ((gy + 1.f) * H - 1.f) * 0.5f;   // align_corners = False
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float tx = ix - fx, ty = iy - fy;
+  const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+  const float ws[4] = {(1.f - tx) * (1.f - ty), tx * (1.f - ty), (1.f - tx) * ty, tx * ty};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool in = xs[k] >= 0 && xs[k] < W && ys[k] >= 0 && ys[k] < H;   // padding_mode = zeros
+    off[k] = in ? ys[k] * W + xs[k] : -1;
+    wt[k] = in ? ws[k] : 0.f;
+  }
+}
+// S[img, d, p] = bilinear(planes[img, d, :, :], grid[img, p])      planes NCHW (H x W = hw x hw)
+__global__ void tr_sample_fwd_kernel(const float* planes, const float* grid, float* S, int NV, int D, int P, int hw) {
+  const long long n = (long long)NV * P;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(x / P);
+    const int pidx = (int)(x % P);
+    int off[4];
+    float wt[4];
+    bilinear_taps(grid[2 * x], grid[2 * x + 1], hw, hw, off, wt);
+    const float* pl = planes + (long long)img * D * hw * hw;
+    float* out = S + (long long)img * D * P + pidx;
+    for (int d = 0; d < D; ++d) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (off[k] >= 0) acc += wt[k] * pl[(long long)d * hw * hw + off[k]];
+      out[(long long)d * P] = acc;
+    }
+  }
+}
+__global__ void tr_sample_bwd_kernel(const float* dS, const float* grid, float* dplanes, int NV, int D, int P, int hw) {
+  const long long n = (long long)NV * P;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(x / P);
+    const int pidx = (int)(x % P);
+    int off[4];
+    float wt[4];
+    bilinear_taps(grid[2 * x], grid[2 * x + 1], hw, hw, off, wt);
+    float* pl = dplanes + (long long)img * D * hw * hw;
+    const float* in = dS + (long long)img * D * P + pidx;
+    for (int d = 0; d < D; ++d) {
+      const float g = in[(long long)d * P];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (off[k] >= 0) atomicAdd(pl + (long long)d * hw * hw + off[k], wt[k] * g);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross-view merge
+// X rows of sample b: row0[b] + p * n[b] + v   (the raw `.view(1,-1,N,D)` regroup, ptEmb_head.py:745-771,910-926)
+// m = mlp0(X) [rows, Dm].  n > 1: agg[b*P+p] = sum_{v>=1} m_v * (m_v . m_0) ;  n == 1: agg = m_0
+__global__ void tr_merge_agg_kernel(const float* m, const int* row0, const int* nviews, int P, int Dm, float* agg,
+                                    long long total) {
+  // one warp per (b, p)
+  const int lane = threadIdx.x & 31;
+  const long long gp = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // b * P + p
+  if (gp >= total) return;
+  const int b = (int)(gp / P);
+  const int p = (int)(gp % P);
+  const int n = nviews[b];
+  const float* base = m + ((long long)row0[b] + (long long)p * n) * Dm;
+  constexpr int kMax = 8;   // Dm <= 256 (D <= 512)
+  float mast[kMax], acc[kMax];
+  _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    mast[i] = (c < Dm) ? base[c] : 0.f;
+    acc[i] = (n == 1) ? mast[i] : 0.f;
+  }
+  for (int v = 1; v < n; ++v) {
+    float o[kMax];
+    float dot = 0.f;
+    _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+      const int c = lane + 32 * i;
+      o[i] = (c < Dm) ? base[(long long)v * Dm + c] : 0.f;
+      dot += o[i] * mast[i];
+    }
+    dot = warp_sum(dot);
+    _Pragma("unroll") for (int i = 0; i < kMax; ++i) acc[i] += o[i] * dot;
+  }
+  _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    if (c < Dm) agg[gp * Dm + c] = acc[i];
+  }
+}
+// dm from dagg:  n > 1: dm_v = w_v dagg + (dagg . m_v) m_0 (v >= 1), dm_0 = sum_v (dagg . m_v) m_v ; n == 1: dm_0 = dagg
+__global__ void tr_merge_agg_bwd_kernel(const float* dagg, const float* m, const int* row0, const int* nviews, int P,
+                                        int Dm, float* dm, long long total) {
+  const int lane = threadIdx.x & 31;
+  const long long gp = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gp >= total) return;
+  const int b = (int)(gp / P);
+  const int p = (int)(gp % P);
+  const int n = nviews[b];
+  const long long r0 = ((long long)row0[b] + (long long)p * n) * Dm;
+  constexpr int kMax = 8;
+  float mast[kMax], g[kMax], dmast[kMax];
+  _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    mast[i] = (c < Dm) ? m[r0 + c] : 0.f;
+    g[i] = (c < Dm) ? dagg[gp * Dm + c] : 0.f;
+    dmast[i] = (n == 1) ? g[i] : 0.f;
+  }
+  for (int v = 1; v < n; ++v) {
+    float o[kMax];
+    float w = 0.f, go = 0.f;
+    _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+      const int c = lane + 32 * i;
+      o[i] = (c < Dm) ? m[r0 + (long long)v * Dm + c] : 0.f;
+      w += o[i] * mast[i];
+      go += o[i] * g[i];
+    }
+    w = warp_sum(w), go = warp_sum(go);
+    _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+      const int c = lane + 32 * i;
+      if (c < Dm) dm[r0 + (long long)v * Dm + c] = w * g[i] + go * mast[i];
+      dmast[i] += go * o[i];
+    }
+  }
+  _Pragma("unroll") for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    if (c < Dm) dm[r0 + c] = dmast[i];
+  }
+}
+// out[b*P+p, :] = X[row0[b] + p * n, :] + y[b*P+p, :] / n          (n == 1: divisor 1 as well: q + mlp1(mlp0(q)))
+__global__ void tr_merge_out_kernel(const float* X, const float* y, const int* row0, const int* nviews, int P, int D,
+                                    float* out, long long total) {
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+    const long long gp = x / D;
+    const int c = (int)(x % D);
+    const int b = (int)(gp / P);
+    const int p = (int)(gp % P);
+    const int n = nviews[b];
+    out[x] = X[((long long)row0[b] + (long long)p * n) * D + c] + y[x] / n;
+  }
+}
+// dX[row0[b] + p * n, :] += dout ; dy = dout / n
+__global__ void tr_merge_out_bwd_kernel(const float* dout, const int* row0, const int* nviews, int P, int D, float* dX,
+                                        float* dy, long long total) {
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+    const long long gp = x / D;
+    const int c = (int)(x % D);
+    const int b = (int)(gp / P);
+    const int p = (int)(gp % P);
+    const int n = nviews[b];
+    const float g = dout[x];
+    dX[((long long)row0[b] + (long long)p * n) * D + c] += g;
+    dy[x] = g / n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused gradient norm + clip
+// sumsq[0] += sum g^2 over one tensor ; then every tensor is scaled by min(1, max_norm / (sqrt(sumsq) + 1e-6))
+__global__ void tr_sumsq_kernel(const float* g, long long n, float* sumsq) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(sumsq, t);
+  }
+}
+__global__ void tr_clip_scale_kernel(float* g, long long n, const float* sumsq, float max_norm) {
+  const float coef = fminf(1.0f, max_norm / (sqrtf(sumsq[0]) + 1e-6f));
+  if (coef >= 1.0f) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) g[i] *= coef;
+}
+
+}  // namespace poem

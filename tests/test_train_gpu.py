@@ -1,0 +1,394 @@
+"""Training-path primitives (include/poem_train.h) against torch autograd of the same op on the CPU (fp64 where cheap).
+SURVEY §8 row f3.  GEMMs run on TF32 tensor cores: rel-L2 <= 1e-3 and every entry within 3e-3 of the |A|.|B| bound;
+SIMT kernels are fp32: 1e-5 of scale."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tn():
+    from poem_v2_b200 import _train_native as tn
+    tn.load()
+    return tn
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+def rel_l2(got, want):
+    return ((got.double() - want.double()).norm() / want.double().norm().clamp_min(1e-30)).item()
+
+
+def check_gemm(got, want, bound):
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, want) <= 1e-3, rel_l2(got, want)
+    assert ((got.double() - want.double()).abs() <= 3e-3 * bound.double() + 1e-6).all()
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,K", [(300, 128, 160), (128, 256, 32), (799, 96, 64), (70, 24, 40), (260, 160, 799)])
+def test_tgemm_major_combinations(tn, a_mn, b_mn, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + 2 * a_mn + b_mn)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ldm = (M + 3) // 4 * 4
+    ldn = (N + 3) // 4 * 4
+    ldk = (K + 3) // 4 * 4
+    if a_mn:
+        As = torch.zeros(K, ldm)
+        As[:, :M] = A.t()
+    else:
+        As = torch.zeros(M, ldk)
+        As[:, :K] = A
+    if b_mn:
+        Bs = torch.zeros(K, ldn)
+        Bs[:, :N] = B.t()
+    else:
+        Bs = torch.zeros(N, ldk)
+        Bs[:, :K] = B
+    out = torch.full((M, ldn), 7.0).cuda()
+    tn.gemm(dev(As), dev(Bs), out, M, N, K, a_mn=a_mn, b_mn=b_mn, lda=ldm if a_mn else ldk, ldb=ldn if b_mn else ldk,
+            ldc=ldn, alpha=0.5, bias=dev(bias))
+    torch.cuda.synchronize()
+    want = 0.5 * (A.double() @ B.double().t()) + bias.double()
+    check_gemm(out.cpu()[:, :N], want, 0.5 * (A.abs() @ B.abs().t()) + bias.abs())
+    if ldn > N:
+        assert (out.cpu()[:, N:] == 7.0).all()       # nothing written outside the N columns
+
+
+def test_tgemm_accumulate_bias_on_m_and_split_k(tn):
+    g = torch.Generator().manual_seed(5)
+    # wgrad shape: tall reduction, both operands MN-major, accumulation into an existing gradient (split-K, atomics)
+    T, No, Ki = 20000, 128, 96
+    dy, x = torch.randn(T, No, generator=g), torch.randn(T, Ki, generator=g)
+    dW0 = torch.randn(No, Ki, generator=g)
+    dW = dev(dW0.clone())
+    tn.gemm(dev(dy), dev(x), dW, No, Ki, T, a_mn=True, b_mn=True, accumulate=True)
+    torch.cuda.synchronize()
+    check_gemm(dW.cpu(), dW0.double() + dy.double().t() @ x.double(), dW0.abs() + dy.abs().t() @ x.abs())
+    dW2 = torch.full((No, Ki), 3.0).cuda()
+    tn.gemm(dev(dy), dev(x), dW2, No, Ki, T, a_mn=True, b_mn=True)                     # store mode zeroes first
+    torch.cuda.synchronize()
+    check_gemm(dW2.cpu(), dy.double().t() @ x.double(), dy.abs().t() @ x.abs())
+    # small problem, plain accumulate (read-modify-write) + bias along M
+    A, B = torch.randn(200, 64, generator=g), torch.randn(256, 64, generator=g)
+    bm = torch.randn(200, generator=g)
+    C0 = torch.randn(200, 256, generator=g)
+    Cd = dev(C0.clone())
+    tn.gemm(dev(A), dev(B), Cd, 200, 256, 64, bias=dev(bm), bias_on_m=True, accumulate=True)
+    torch.cuda.synchronize()
+    check_gemm(Cd.cpu(), C0.double() + A.double() @ B.double().t() + bm.double()[:, None], C0.abs() + A.abs() @ B.abs().t() + 1)
+
+
+def test_tgemm_batched_attention_shapes(tn):
+    """The five GEMMs of the attention core on (B, L, H, hd) tensors addressed in place (head = column slice)."""
+    g = torch.Generator().manual_seed(9)
+    Bn, H, hd, Lq, Lk = 2, 4, 32, 150, 260
+    D = H * hd
+    Q, Kt, V, dO = (torch.randn(Bn, L, D, generator=g) for L in (Lq, Lk, Lk, Lq))
+    Qd, Kd, Vd, dOd = dev(Q), dev(Kt), dev(V), dev(dO)
+    S = torch.zeros(Bn, H, Lq, Lk).cuda()
+    kw = dict(batch=(H, Bn))
+    tn.gemm(Qd, Kd, S, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=(hd, Lq * D), b_strides=(hd, Lk * D),
+            c_strides=(Lq * Lk, H * Lq * Lk), **kw)
+    torch.cuda.synchronize()
+    q4, k4, v4, do4 = (t.view(Bn, -1, H, hd).transpose(1, 2).double() for t in (Q, Kt, V, dO))
+    check_gemm(S.cpu(), q4 @ k4.transpose(-1, -2), q4.abs() @ k4.abs().transpose(-1, -2))
+    P = torch.softmax(S.cpu(), dim=-1)
+    Pd = dev(P)
+    ctx = torch.zeros(Bn, Lq, D).cuda()
+    tn.gemm(Pd, Vd, ctx, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=(Lq * Lk, H * Lq * Lk),
+            b_strides=(hd, Lk * D), c_strides=(hd, Lq * D), **kw)
+    torch.cuda.synchronize()
+    want = (P.double() @ v4).transpose(1, 2).reshape(Bn, Lq, D)
+    check_gemm(ctx.cpu(), want, (P.double() @ v4.abs()).transpose(1, 2).reshape(Bn, Lq, D))
+    dV = torch.zeros(Bn, Lk, D).cuda()                                   # dV = P^T dO : both MN-major
+    tn.gemm(Pd, dOd, dV, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=(Lq * Lk, H * Lq * Lk),
+            b_strides=(hd, Lq * D), c_strides=(hd, Lk * D), **kw)
+    torch.cuda.synchronize()
+    want = (P.double().transpose(-1, -2) @ do4).transpose(1, 2).reshape(Bn, Lk, D)
+    check_gemm(dV.cpu(), want, (P.double().transpose(-1, -2) @ do4.abs()).transpose(1, 2).reshape(Bn, Lk, D))
+    dP = torch.zeros(Bn, H, Lq, Lk).cuda()                               # dP = dO V^T
+    tn.gemm(dOd, Vd, dP, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=(hd, Lq * D), b_strides=(hd, Lk * D),
+            c_strides=(Lq * Lk, H * Lq * Lk), **kw)
+    dQ = torch.zeros(Bn, Lq, D).cuda()                                   # dQ = dS K : A K-major, B MN-major
+    tn.gemm(dP, Kd, dQ, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=(Lq * Lk, H * Lq * Lk),
+            b_strides=(hd, Lk * D), c_strides=(hd, Lq * D), **kw)
+    dK = torch.zeros(Bn, Lk, D).cuda()                                   # dK = dS^T Q : both MN-major
+    tn.gemm(dP, Qd, dK, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=(Lq * Lk, H * Lq * Lk),
+            b_strides=(hd, Lq * D), c_strides=(hd, Lk * D), **kw)
+    torch.cuda.synchronize()
+    dp = do4 @ v4.transpose(-1, -2)
+    check_gemm(dP.cpu(), dp, do4.abs() @ v4.abs().transpose(-1, -2))
+    dpg = dP.cpu().double()
+    check_gemm(dQ.cpu(), (dpg @ k4).transpose(1, 2).reshape(Bn, Lq, D), (dpg.abs() @ k4.abs()).transpose(1, 2).reshape(Bn, Lq, D))
+    check_gemm(dK.cpu(), (dpg.transpose(-1, -2) @ q4).transpose(1, 2).reshape(Bn, Lk, D),
+               (dpg.abs().transpose(-1, -2) @ q4.abs()).transpose(1, 2).reshape(Bn, Lk, D))
+
+
+def test_tgemm_conv1x1_layouts(tn):
+    """input_proj as the path runs it: NCHW planes, shared weight, batch over images, wgrad summed over the batch."""
+    g = torch.Generator().manual_seed(11)
+    NV, Cin, D, HW = 3, 160, 128, 256
+    feat = torch.randn(NV, Cin, HW, generator=g)
+    W, b = torch.randn(D, Cin, generator=g), torch.randn(D, generator=g)
+    planes = torch.zeros(NV, D, HW).cuda()
+    tn.gemm(dev(W), dev(feat), planes, D, HW, Cin, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1), b_strides=(Cin * HW, 0),
+            c_strides=(D * HW, 0), bias=dev(b), bias_on_m=True)
+    torch.cuda.synchronize()
+    want = torch.einsum("dc,ncp->ndp", W.double(), feat.double()) + b.double()[None, :, None]
+    check_gemm(planes.cpu(), want, torch.einsum("dc,ncp->ndp", W.abs(), feat.abs()) + 1)
+    dpl = torch.randn(NV, D, HW, generator=g)
+    dfeat = torch.zeros(NV, Cin, HW).cuda()                                   # dfeat = W^T dplanes
+    tn.gemm(dev(W), dev(dpl), dfeat, Cin, HW, D, a_mn=True, b_mn=True, lda=Cin, ldb=HW, ldc=HW, batch=(NV, 1),
+            b_strides=(D * HW, 0), c_strides=(Cin * HW, 0))
+    dW = torch.zeros(D, Cin).cuda()                                            # dW = sum_img dplanes feat^T
+    tn.gemm(dev(dpl), dev(feat), dW, D, Cin, HW, lda=HW, ldb=HW, ldc=Cin, batch=(NV, 1), a_strides=(D * HW, 0),
+            b_strides=(Cin * HW, 0), c_strides=(0, 0))
+    torch.cuda.synchronize()
+    check_gemm(dfeat.cpu(), torch.einsum("dc,ndp->ncp", W.double(), dpl.double()), torch.einsum("dc,ndp->ncp", W.abs(), dpl.abs()))
+    check_gemm(dW.cpu(), torch.einsum("ndp,ncp->dc", dpl.double(), feat.double()), torch.einsum("ndp,ncp->dc", dpl.abs(), feat.abs()))
+
+
+def close(got, want, tol=2e-5):
+    want = want.to(torch.float64)
+    scale = max(want.abs().max().item(), 1e-12)
+    err = (got.cpu().double() - want).abs().max().item()
+    assert err <= tol * scale, (err, scale)
+
+
+def test_elementwise_layernorm_softmax(tn):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 256, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(1000, 256, generator=g, dtype=torch.float64)
+    # relu / gelu
+    y = dev(x.detach().float())
+    tn.call("poem_tr_relu", y, y.numel())
+    close(y, torch.relu(x.detach()))
+    d = dev(dy.float())
+    tn.call("poem_tr_relu_bwd", d, y, y.numel())
+    close(d, dy * (x.detach() > 0))
+    yg = torch.empty_like(y)
+    xd = dev(x.detach().float())
+    tn.call("poem_tr_gelu", xd, yg, yg.numel())
+    ref = torch.nn.functional.gelu(x)
+    close(yg, ref.detach())
+    ref.backward(dy)
+    d = dev(dy.float())
+    tn.call("poem_tr_gelu_bwd", d, xd, d.numel())
+    close(d, x.grad, 1e-4)
+    # layernorm with residual
+    for D in (128, 256, 512):
+        x = torch.randn(333, D, generator=g, dtype=torch.float64, requires_grad=True)
+        r = torch.randn(333, D, generator=g, dtype=torch.float64, requires_grad=True)
+        gam = torch.randn(D, generator=g, dtype=torch.float64, requires_grad=True)
+        bet = torch.randn(D, generator=g, dtype=torch.float64, requires_grad=True)
+        dy = torch.randn(333, D, generator=g, dtype=torch.float64)
+        ref = torch.nn.functional.layer_norm(x + r, (D,), gam, bet, eps=1e-12)
+        ref.backward(dy)
+        y, xhat = torch.empty(333, D).cuda(), torch.empty(333, D).cuda()
+        rstd = torch.empty(333).cuda()
+        tn.call("poem_tr_layernorm", dev(x.detach().float()), dev(r.detach().float()), dev(gam.detach().float()),
+                dev(bet.detach().float()), 1e-12, y, xhat, rstd, 333, D)
+        close(y, ref.detach())
+        dx = torch.empty(333, D).cuda()
+        dgam, dbet = torch.zeros(D).cuda(), torch.zeros(D).cuda()
+        tn.call("poem_tr_layernorm_bwd", dev(dy.float()), xhat, rstd, dev(gam.detach().float()), dx, dgam, dbet, 333, D)
+        close(dx, x.grad, 1e-4)
+        close(dgam, gam.grad, 1e-4)
+        close(dbet, bet.grad, 1e-4)
+    # row softmax and its backward
+    S = torch.randn(77, 4096, generator=g, dtype=torch.float64, requires_grad=True)
+    dP = torch.randn(77, 4096, generator=g, dtype=torch.float64)
+    P = torch.softmax(S * 0.125, dim=-1)
+    P.backward(dP)
+    Sd = dev(S.detach().float())
+    tn.call("poem_tr_softmax_rows", Sd, 77, 4096, 0.125)
+    close(Sd, P.detach(), 1e-5)
+    dPd = dev(dP.float())
+    tn.call("poem_tr_softmax_rows_bwd", Sd, dPd, 77, 4096, 0.125)
+    close(dPd, S.grad, 1e-4)
+    # column sums / batch sums / axpy
+    out = torch.ones(256).cuda()
+    tn.call("poem_tr_colsum", dev(x.detach().float()[:, :256].contiguous()), 256, 333, 256, out)
+    close(out, 1 + x.detach()[:, :256].sum(0), 1e-5)
+    torch.cuda.synchronize()
+
+
+def test_vector_attention_edge_kernels(tn):
+    """forward + backward of the per-edge part of ptTransformerBlock (point_transformers.py:86-95) from the primitives,
+    against autograd of the formula in fp64 (GEMM layers replaced by torch on the CPU: only the SIMT kernels under test)."""
+    g = torch.Generator().manual_seed(21)
+    B, Q, R, D, K = 2, 40, 64, 128, 32
+    f64 = dict(generator=g, dtype=torch.float64)
+    q = torch.randn(B * Q, D, **f64).requires_grad_()
+    ktab = torch.randn(B * R, D, **f64).requires_grad_()
+    vtab = torch.randn(B * R, D, **f64).requires_grad_()
+    q_xyz = torch.randn(B * Q, 3, **f64).requires_grad_()
+    r_xyz = torch.randn(B * R, 3, **f64).requires_grad_()
+    W1 = torch.randn(D, 3, **f64).requires_grad_()
+    b1 = torch.randn(D, **f64).requires_grad_()
+    lidx = torch.randint(0, R, (B, Q, K), generator=g, dtype=torch.int32)
+    gidx = (lidx.long() + torch.arange(B)[:, None, None] * R).reshape(-1)
+    dres = torch.randn(B * Q, D, **f64)
+    scale = 1.0 / math.sqrt(D)
+    # reference (pos = relu(lin3(rel)) stands for the delta MLP, a = sin(t) stands for the gamma MLP)
+    rel = q_xyz[:, None, :] - r_xyz[gidx].view(B * Q, K, 3)
+    pos = torch.relu(rel @ W1.t() + b1)
+    t = q[:, None, :] - ktab[gidx].view(B * Q, K, D) + pos
+    w = torch.softmax(torch.sin(t) * scale, dim=1)
+    res = (w * (vtab[gidx].view(B * Q, K, D) + pos)).sum(1)
+    res.backward(dres)
+    # device
+    E = B * Q * K
+    gi = torch.empty(E, dtype=torch.int32).cuda()
+    tn.call("poem_tr_va_make_idx", dev(lidx), None, B, Q, R, gi)
+    assert torch.equal(gi.cpu().long(), gidx)
+    f = lambda t_: dev(t_.detach().float())  # noqa: E731
+    qd, kd, vd, qx, rx, W1d, b1d = f(q), f(ktab), f(vtab), f(q_xyz), f(r_xyz), f(W1), f(b1)
+    reld = torch.empty(E, 3).cuda()
+    tn.call("poem_tr_va_rel", qx, rx, None, gi, E, reld)
+    close(reld, rel.detach().reshape(E, 3))
+    posd = torch.empty(E, D).cuda()
+    tn.call("poem_tr_lin3_relu", reld, W1d, b1d, posd, E, D)
+    close(posd, pos.detach().reshape(E, D))
+    td = torch.empty(E, D).cuda()
+    tn.call("poem_tr_va_gather_t", qd, kd, gi, posd, td, E, D)
+    close(td, t.detach().reshape(E, D))
+    resd = torch.empty(B * Q, D).cuda()
+    ad = torch.sin(td)                                                                # stand-in for the gamma MLP (test only)
+    tn.call("poem_tr_va_softmax_agg", ad, vd, posd, gi, scale, resd, B * Q, D)     # ad now holds w
+    close(ad, w.detach().reshape(E, D))
+    close(resd, res.detach())
+    dvp = torch.empty(E, D).cuda()
+    tn.call("poem_tr_va_softmax_agg_bwd", f(dres), ad, vd, posd, gi, scale, dvp, B * Q, D)   # ad now holds da
+    td = ad * torch.cos(td)                                                            # dt = da * d sin(t)/dt
+    dq, dk, dv = torch.zeros(B * Q, D).cuda(), torch.zeros(B * R, D).cuda(), torch.zeros(B * R, D).cuda()
+    tn.call("poem_tr_va_scatter", td, dvp, gi, dq, dk, dv, B * Q, D)                  # td now holds dpos
+    close(dq, q.grad, 1e-4)
+    close(dk, ktab.grad, 1e-4)
+    close(dv, vtab.grad, 1e-4)
+    tn.call("poem_tr_relu_bwd", td, posd, td.numel())
+    dW1, db1 = torch.zeros(D, 3).cuda(), torch.zeros(D).cuda()
+    drel = torch.empty(E, 3).cuda()
+    tn.call("poem_tr_lin3_bwd", td, reld, W1d, dW1, db1, drel, E, D)
+    close(dW1, W1.grad, 1e-4)
+    close(db1, b1.grad, 1e-4)
+    dqx, drx = torch.zeros(B * Q, 3).cuda(), torch.zeros(B * R, 3).cuda()
+    tn.call("poem_tr_va_drel_scatter", drel, gi, dqx, drx, B * Q)
+    close(dqx, q_xyz.grad, 1e-4)
+    close(drx, r_xyz.grad, 1e-4)
+    # anchors (block 0): the same 32 rows / coordinates for every query
+    a_idx = torch.randint(0, R, (K,), generator=g, dtype=torch.int32)
+    a_xyz = torch.randn(K, 3, generator=g)
+    tn.call("poem_tr_va_make_idx", None, dev(a_idx), B, Q, R, gi)
+    want = (a_idx.long()[None, None] + torch.arange(B)[:, None, None] * R).expand(B, Q, K).reshape(-1)
+    assert torch.equal(gi.cpu().long(), want)
+    tn.call("poem_tr_va_rel", qx, None, dev(a_xyz), gi, E, reld)
+    close(reld, (q_xyz.detach()[:, None, :] - a_xyz.double()[None]).reshape(E, 3))
+    torch.cuda.synchronize()
+
+
+def test_reg_out_sampler_merge_clip(tn):
+    g = torch.Generator().manual_seed(31)
+    f64 = dict(generator=g, dtype=torch.float64)
+    f = lambda t_: dev(t_.detach().float())  # noqa: E731
+    # Linear(D, 3) + base
+    M, D = 500, 256
+    x = torch.randn(M, D, **f64).requires_grad_()
+    W = torch.randn(3, D, **f64).requires_grad_()
+    b = torch.randn(3, **f64).requires_grad_()
+    base = torch.randn(M, 3, **f64)
+    dy = torch.randn(M, 3, **f64)
+    y = x @ W.t() + b + base
+    y.backward(dy)
+    yd = torch.empty(M, 3).cuda()
+    tn.call("poem_tr_lin_n3", f(x), f(W), f(b), f(base), yd, M, D)
+    close(yd, y.detach())
+    dx, dW, db = torch.empty(M, D).cuda(), torch.zeros(3, D).cuda(), torch.zeros(3).cuda()
+    tn.call("poem_tr_lin_n3_bwd", f(dy), f(x), f(W), dx, dW, db, M, D)
+    close(dx, x.grad, 1e-4)
+    close(dW, W.grad, 1e-4)
+    close(db, b.grad, 1e-4)
+    # projection + sampler against F.grid_sample and the oracle's projection
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import poem_oracle as orc
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    dims = release_dims("small")
+    views = [2, 1, 3]
+    _, metas, ref_j = synth.make_inputs(dims, len(views), views, 4)
+    bps = synth.load_assets()[0]
+    centre = ref_j[:, 9]
+    grid_ref = orc.project_bps(bps[None] + centre[:, None], metas["cam_intr"], metas["cam_extr"], views,
+                               torch.tensor([float(metas["inp_img_shape"][0]), float(metas["inp_img_shape"][1])]))
+    NV, P, Dp, hw = sum(views), bps.shape[0], 64, 16
+    img_sample = torch.tensor([b_ for b_, n in enumerate(views) for _ in range(n)], dtype=torch.int32)
+    grid = torch.empty(NV, P, 2).cuda()
+    tn.call("poem_tr_project", dev(bps), dev(centre), dev(metas["cam_intr"]), dev(metas["cam_extr"]), dev(img_sample), NV, P,
+            float(metas["inp_img_shape"][0]), float(metas["inp_img_shape"][1]), grid)
+    assert (grid.cpu() - grid_ref[:, :, 0]).abs().max().item() <= 2e-4
+    planes = torch.randn(NV, Dp, hw, hw, **f64).requires_grad_()
+    gr = grid.cpu().double()[:, :, None, :]
+    S = torch.nn.functional.grid_sample(planes, gr, align_corners=False).squeeze(-1)
+    dS = torch.randn(NV, Dp, P, **f64)
+    S.backward(dS)
+    Sd = torch.empty(NV, Dp, P).cuda()
+    tn.call("poem_tr_sample", f(planes), grid, Sd, NV, Dp, P, hw)
+    close(Sd, S.detach(), 1e-4)
+    dpl = torch.zeros(NV, Dp, hw, hw).cuda()
+    tn.call("poem_tr_sample_bwd", f(dS), grid, dpl, NV, Dp, P, hw)
+    close(dpl, planes.grad, 1e-4)
+    # merge aggregate + output, ragged views incl. a single-view sample
+    Pm, Dm, Dd = 50, 64, 128
+    rows = sum(views) * Pm
+    m = torch.randn(rows, Dm, **f64).requires_grad_()
+    X = torch.randn(rows, Dd, **f64).requires_grad_()
+    yv = torch.randn(len(views) * Pm, Dd, **f64).requires_grad_()
+    row0 = torch.tensor([0, 2 * Pm, 3 * Pm], dtype=torch.int32)
+    nv = torch.tensor(views, dtype=torch.int32)
+    aggs, outs = [], []
+    for b_, n in enumerate(views):
+        mm = m[int(row0[b_]):int(row0[b_]) + Pm * n].view(Pm, n, Dm)
+        xx = X[int(row0[b_]):int(row0[b_]) + Pm * n].view(Pm, n, Dd)
+        if n == 1:
+            aggs.append(mm[:, 0])
+        else:
+            wv = (mm[:, 1:] * mm[:, :1]).sum(-1, keepdim=True)
+            aggs.append((mm[:, 1:] * wv).sum(1))
+        outs.append(xx[:, 0] + yv[b_ * Pm:(b_ + 1) * Pm] / n)
+    agg, out = torch.cat(aggs), torch.cat(outs)
+    dagg, dout = torch.randn(agg.shape, **f64), torch.randn(out.shape, **f64)
+    (agg * dagg).sum().backward()
+    aggd = torch.empty(agg.shape).cuda()
+    tn.call("poem_tr_merge_agg", f(m), dev(row0), dev(nv), len(views), Pm, Dm, aggd)
+    close(aggd, agg.detach(), 1e-4)
+    dm = torch.zeros(rows, Dm).cuda()
+    tn.call("poem_tr_merge_agg_bwd", f(dagg), f(m), dev(row0), dev(nv), len(views), Pm, Dm, dm)
+    close(dm, m.grad, 1e-4)
+    (out * dout).sum().backward()
+    outd = torch.empty(out.shape).cuda()
+    tn.call("poem_tr_merge_out", f(X), f(yv), dev(row0), dev(nv), len(views), Pm, Dd, outd)
+    close(outd, out.detach())
+    dX, dyv = torch.zeros(rows, Dd).cuda(), torch.empty(out.shape).cuda()
+    tn.call("poem_tr_merge_out_bwd", f(dout), dev(row0), dev(nv), len(views), Pm, Dd, dX, dyv)
+    close(dX, X.grad)
+    close(dyv, yv.grad)
+    # per-tensor gradient clipping (net_utils.clip_gradient)
+    gt = torch.randn(5000, generator=g) * 3
+    gd, ss = dev(gt), torch.zeros(1).cuda()
+    tn.call("poem_tr_sumsq", gd, gd.numel(), ss)
+    tn.call("poem_tr_clip_scale", gd, gd.numel(), ss, 1.0)
+    p = torch.nn.Parameter(torch.zeros(5000))
+    p.grad = gt.clone()
+    torch.nn.utils.clip_grad_norm_(p, 1.0, 2)
+    close(gd, p.grad.double(), 1e-5)
+    torch.cuda.synchronize()
