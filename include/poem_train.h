@@ -49,6 +49,7 @@ int poem_tr_axpy(float* y, const float* x, float a, long long n, void* stream); 
 int poem_tr_affine_rows(const float* x, const float* off, float a, float* out, long long rows, int rows_per_group,
                         int n_groups, int cols, void* stream);                       /* out = a x + off[group] */
 int poem_tr_colsum(const float* dy, long long ld, long long M, int N, float* out, void* stream);        /* out[n] += */
+int poem_tr_rowsum_groups(const float* x, long long rows, int cols, int group, float* out, void* stream);  /* out[row % group] += */
 int poem_tr_sum_batch(const float* x, int B, long long n, float* out, void* stream);                     /* out += sum_b */
 int poem_tr_bcast_batch(const float* x, int B, long long n, float* out, void* stream);
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     "poem_tr_axpy": [_P, _P, _F, _L, _P],
     "poem_tr_affine_rows": [_P, _P, _F, _P, _L, _I, _I, _I, _P],
     "poem_tr_colsum": [_P, _L, _L, _I, _P, _P],
+    "poem_tr_rowsum_groups": [_P, _L, _I, _I, _P, _P],
     "poem_tr_sum_batch": [_P, _I, _L, _P, _P],
     "poem_tr_bcast_batch": [_P, _I, _L, _P, _P],
     "poem_tr_layernorm": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _P],

@@ -205,6 +205,11 @@ extern "C" int poem_tr_colsum(const float* dy, long long ld, long long M, int N,
   TR_CHECK("colsum");
   return 0;
 }
+extern "C" int poem_tr_rowsum_groups(const float* x, long long rows, int cols, int group, float* out, void* stream) {
+  tr_rowsum_groups_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST>>>(x, rows, cols, group, out);
+  TR_CHECK("rowsum_groups");
+  return 0;
+}
 extern "C" int poem_tr_sum_batch(const float* x, int B, long long n, float* out, void* stream) {
   tr_sum_batch_kernel<<<grid_for(n), 256, 0, ST>>>(x, B, n, out);
   TR_CHECK("sum_batch");

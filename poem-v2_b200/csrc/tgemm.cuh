@@ -7,7 +7,11 @@
 //   and likewise Q·K^T, P·V, P^T·dO, dS·K, dS^T·Q of the attention backward (reference: autograd of
 //   lib/models/bricks/pt_metro_transformer.py:57-91, point_transformers.py:70-156, heads/ptEmb_head.py:745-771).
 //   TMA stages 128-byte (32 x fp32) SWIZZLE_128B rows; `tcgen05.mma kind::tf32` consumes 8 K-values per instruction;
-//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM), warps 2..5 = epilogue.  One 128 x BN tile per CTA, 2 CTAs/SM.
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM), warps 2..5 = operand rounding, then epilogue.  One 128 x BN tile
+//   per CTA, 2 CTAs/SM.  The tensor core TRUNCATES fp32 operands to TF32 (low 13 mantissa bits ignored: a biased error,
+//   measured 4.5e-3 on the regressed coordinates); warps 2..5 therefore round every landed stage to nearest
+//   (cvt.rna.tf32.f32, in place in shared memory, any layout) before the MMA warp may read it.  These GEMMs are
+//   HBM/L2-bound (K = D), the extra shared-memory pass hides behind the other resident CTA.
 //   A batch (two strides per operand, rank-4 tensor maps: per-slice bounds, zero fill outside) and a K split with atomic
 //   accumulation (tall reductions: wgrad) ride in blockIdx.z.
 #pragma once
@@ -84,8 +88,9 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = bars;                 // [TG_STAGES]
   uint64_t* empty_bar = bars + TG_STAGES;    // [TG_STAGES]
-  uint64_t* acc_full = bars + 2 * TG_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TG_STAGES + 1);
+  uint64_t* ready_bar = bars + 2 * TG_STAGES;   // [TG_STAGES] stage rounded to TF32 (128 arrivals)
+  uint64_t* acc_full = bars + 3 * TG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TG_STAGES + 1);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TG_BM;
@@ -105,6 +110,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     for (int s = 0; s < TG_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&ready_bar[s], 128);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -147,7 +153,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       for (int kb = 0; kb < n_kb; ++kb) {
         const int st = kb % TG_STAGES;
         const uint32_t ph = (uint32_t)(kb / TG_STAGES) & 1;
-        mbar_wait(&full_bar[st], ph);
+        mbar_wait(&ready_bar[st], ph);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + st * Cfg::kStageBytes);
         const uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -169,6 +175,24 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     float* crow = p.C + (long long)b1 * p.c_s1 + (long long)b2 * p.c_s2 + (long long)row * p.ldc;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_s1 & 3) == 0) && ((p.c_s2 & 3) == 0);
     const float bias_m = (with_bias && p.bias_on_m && row < p.M) ? p.bias[row] : 0.f;
+    // ---- main loop duty: round each landed stage to TF32 (nearest, ties away) in place
+    const int et = threadIdx.x - 64;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int st = kb % TG_STAGES;
+      mbar_wait(&full_bar[st], (uint32_t)(kb / TG_STAGES) & 1);
+      uint4* sp = reinterpret_cast<uint4*>(smem + st * Cfg::kStageBytes);
+#pragma unroll 4
+      for (int i = et; i < Cfg::kStageBytes / 16; i += 128) {
+        uint4 v = sp[i];
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.x) : "f"(__uint_as_float(v.x)));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.y) : "f"(__uint_as_float(v.y)));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.z) : "f"(__uint_as_float(v.z)));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.w) : "f"(__uint_as_float(v.w)));
+        sp[i] = v;
+      }
+      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      mbar_arrive(&ready_bar[st]);
+    }
     if (n_kb > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();

@@ -76,6 +76,16 @@ __global__ void tr_colsum_kernel(const float* dy, long long ld, long long M, int
     atomicAdd(out + n, s);
   }
 }
+// out[row % group] += sum_c x[row, c]     (bias gradient of an NCHW 1x1 conv: rows = (image, channel), cols = pixels)
+__global__ void tr_rowsum_groups_kernel(const float* x, long long rows, int cols, int group, float* out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += x[row * cols + c];
+  s = warp_sum(s);
+  if (lane == 0) atomicAdd(out + (row % group), s);
+}
 // out[r, :] += sum_b x[b, r, :]    (gradient of a table broadcast over the batch: query_feat_embedding)
 __global__ void tr_sum_batch_kernel(const float* x, int B, long long n, float* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

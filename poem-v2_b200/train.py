@@ -1,0 +1,463 @@
+"""Training path of the decoder head: forward with saved activations and the hand-written
+backward of `POEM_Generalized_Head.forward` (reference lib/models/heads/ptEmb_head.py:825-964,
+lib/models/bricks/pt_metro_transformer.py:34-200, lib/models/bricks/point_transformers.py:70-156), i.e. what
+`loss.backward()` does in the reference's `scripts/train_ddp.py:103-104`.
+
+All arithmetic runs in libpoem_train.so (include/poem_train.h): fp32 activations in HBM, TF32 tcgen05 GEMMs for every
+Linear / 1x1 conv / attention product (forward, dgrad and wgrad read the same row-major tensors through K-major or
+MN-major operand descriptors, no transposes), SIMT kernels for the rest; the 32-NN search is the inference library's
+`poem_knn32`.  This module is the schedule only — which kernel runs on which buffer, forward and in reverse — the part
+that is Python (torch.autograd) in the reference as well.  torch is used for device memory (`torch.empty`, `clone`,
+`zero_`) and the stream.  Everything is kept: the BERT attention probabilities (B*h*799*4096 fp32 per layer) and the
+per-edge tensors of the vector attention (B*799*32*D per layer) stay in HBM between forward and backward
+(~40 GB at POEM-medium, batch 32: sized for the 180 GB of a B200) instead of the reference's recompute
+(`cp.checkpoint`, point_transformers.py:63,119).
+
+Not covered (raises / documented in DESIGN.md): dropout > 0 (the release configs train with DROPOUT 0.1 inside the BERT
+layers; eval-mode arithmetic is what the reference's own gradients are pinned on in tests/golden/grad_small_b2.npz), the
+parametric MANO tail, D = 1024.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import _train_native as tn
+from . import params as _params
+from .config import HeadDims
+from .pack import sine_pos_3d
+
+NBR = 32
+
+
+class HeadTrainer:
+    """Holds fp32 master parameters `p[name]` and gradient buffers `g[name]` (reference state-dict names) on one GPU.
+
+        tr = HeadTrainer(dims, state_dict, template)
+        coords = tr.forward(mlvl_feat, img_metas, reference_joints)      # (NB, B, 799, 3), metres
+        dfeat = tr.backward(dcoords)                                     # d loss / d mlvl_feat ; tr.g[name] += d loss / d p
+    """
+
+    def __init__(self, dims: HeadDims, state_dict, template, assets=None, device="cuda"):
+        if dims.parametric:
+            raise NotImplementedError("training path: the parametric MANO tail has no backward yet")
+        if dims.embed_dims > 512 or dims.n_neighbor != NBR:
+            raise ValueError("training path: embed_dims <= 512 and 32 neighbours")
+        self.dims, self.dev = dims, torch.device(device)
+        tn.load()
+        self.lib = nat.load()
+        live = _params.live_param_shapes(dims)
+        self.p = {k: state_dict[k].detach().to(self.dev, torch.float32).contiguous().clone() for k in live}
+        self.g = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        bps, a_xyz, a_idx = assets if assets is not None else _params.load_assets()
+        self.bps = bps.to(self.dev, torch.float32).contiguous()
+        self.anchor_xyz = a_xyz.to(self.dev, torch.float32).contiguous()
+        self.anchor_idx = a_idx.to(self.dev, torch.int32).contiguous()
+        self.template = torch.as_tensor(template, dtype=torch.float32).reshape(dims.n_query, 3).to(self.dev).contiguous()
+        self.tape = None
+        self.last_neighbours = None
+
+    # ------------------------------------------------------------------------------------------ small helpers
+    def new(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.dev)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float32, device=self.dev)
+
+    def zero_grad(self):
+        for v in self.g.values():
+            v.zero_()
+
+    def lin(self, x, w, b=None, out=None, acc=False):
+        """y (+)= x W^T + b"""
+        M, K = x.shape
+        W = self.p[w]
+        N = W.shape[0]
+        y = out if out is not None else self.new(M, N)
+        tn.gemm(x, W, y, M, N, K, bias=self.p[b] if b else None, accumulate=acc)
+        return y
+
+    def lin_bwd(self, dy, x, w, b=None, need_dx=True, out=None, acc=False):
+        """g[w] += dy^T x ; g[b] += colsum(dy) ; returns dx (+)= dy W"""
+        M, N = dy.shape
+        K = x.shape[1]
+        if b:
+            tn.call("poem_tr_colsum", dy, N, M, N, self.g[b])
+        tn.gemm(dy, x, self.g[w], N, K, M, a_mn=True, b_mn=True, accumulate=True)
+        if not need_dx:
+            return None
+        dx = out if out is not None else self.new(M, K)
+        tn.gemm(dy, self.p[w], dx, M, K, N, b_mn=True, accumulate=acc)
+        return dx
+
+    def relu_(self, y):
+        tn.call("poem_tr_relu", y, y.numel())
+        return y
+
+    def relu_bwd_(self, dy, y):
+        tn.call("poem_tr_relu_bwd", dy, y, y.numel())
+        return dy
+
+    def ln(self, x, res, pre):
+        M, D = x.shape
+        y, xhat, rstd = self.new(M, D), self.new(M, D), self.new(M)
+        tn.call("poem_tr_layernorm", x, res, self.p[pre + ".weight"], self.p[pre + ".bias"], 1e-12, y, xhat, rstd, M, D)
+        return y, xhat, rstd
+
+    def ln_bwd(self, dy, xhat, rstd, pre):
+        M, D = dy.shape
+        dx = self.new(M, D)
+        tn.call("poem_tr_layernorm_bwd", dy, xhat, rstd, self.p[pre + ".weight"], dx, self.g[pre + ".weight"],
+                self.g[pre + ".bias"], M, D)
+        return dx
+
+    # ------------------------------------------------------------------------------------------ BERT cross-attention
+    def _attn_strides(self, B, Lq, Lk, D, H):
+        hd = D // H
+        return dict(batch=(H, B)), (hd, Lq * D), (hd, Lk * D), (Lq * Lk, H * Lq * Lk)
+
+    def bert_fwd(self, hid, enc, pre, B, Lq, Lk):
+        D, H = hid.shape[1], self.dims.n_heads
+        hd = D // H
+        kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
+        Q = self.lin(hid, pre + ".self.query.weight", pre + ".self.query.bias")
+        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias")
+        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias")
+        P = self.new(B, H, Lq, Lk)
+        tn.gemm(Q, K, P, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, **kw)
+        tn.call("poem_tr_softmax_rows", P, B * H * Lq, Lk, 1.0 / math.sqrt(hd))
+        ctx = self.new(B * Lq, D)
+        tn.gemm(P, V, ctx, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq, **kw)
+        o = self.lin(ctx, pre + ".output.dense.weight", pre + ".output.dense.bias")
+        y, xhat, rstd = self.ln(o, hid, pre + ".output.LayerNorm")
+        return y, dict(hid=hid, enc=enc, Q=Q, K=K, V=V, P=P, ctx=ctx, xhat=xhat, rstd=rstd, B=B, Lq=Lq, Lk=Lk)
+
+    def bert_bwd(self, dy, t, pre, denc):
+        """returns d hid; accumulates into denc"""
+        B, Lq, Lk = t["B"], t["Lq"], t["Lk"]
+        D, H = dy.shape[1], self.dims.n_heads
+        hd = D // H
+        kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
+        ds = self.ln_bwd(dy, t["xhat"], t["rstd"], pre + ".output.LayerNorm")        # grad of (o + hid)
+        dctx = self.lin_bwd(ds, t["ctx"], pre + ".output.dense.weight", pre + ".output.dense.bias")
+        P = t["P"]
+        dV = self.new(B * Lk, D)
+        tn.gemm(P, dctx, dV, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk, **kw)
+        dP = self.new(B, H, Lq, Lk)
+        tn.gemm(dctx, t["V"], dP, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, **kw)
+        tn.call("poem_tr_softmax_rows_bwd", P, dP, B * H * Lq, Lk, 1.0 / math.sqrt(hd))          # dP now holds dS
+        dQ = self.new(B * Lq, D)
+        tn.gemm(dP, t["K"], dQ, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq, **kw)
+        dK = self.new(B * Lk, D)
+        tn.gemm(dP, t["Q"], dK, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk, **kw)
+        del dP
+        self.lin_bwd(dQ, t["hid"], pre + ".self.query.weight", pre + ".self.query.bias", out=ds, acc=True)   # ds -> d hid
+        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True)
+        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True)
+        return ds
+
+    # ------------------------------------------------------------------------------------------ vector attention core
+    def va_core_fwd(self, q, ktab, vtab, gidx, rel, pre):
+        E, D = rel.shape[0], q.shape[1]
+        hd = self.new(E, D)
+        tn.call("poem_tr_lin3_relu", rel, self.p[pre + "fc_delta.0.weight"], self.p[pre + "fc_delta.0.bias"], hd, E, D)
+        pos = self.lin(hd, pre + "fc_delta.2.weight", pre + "fc_delta.2.bias")
+        t = self.new(E, D)
+        tn.call("poem_tr_va_gather_t", q, ktab, gidx, pos, t, E, D)
+        hg = self.relu_(self.lin(t, pre + "fc_gamma.0.weight", pre + "fc_gamma.0.bias"))
+        w = self.lin(hg, pre + "fc_gamma.2.weight", pre + "fc_gamma.2.bias")
+        res = self.new(q.shape[0], D)
+        tn.call("poem_tr_va_softmax_agg", w, vtab, pos, gidx, 1.0 / math.sqrt(D), res, q.shape[0], D)   # w <- softmax weights
+        return res, dict(q=q, ktab=ktab, vtab=vtab, gidx=gidx, rel=rel, hd=hd, pos=pos, t=t, hg=hg, w=w)
+
+    def va_core_bwd(self, dres, c, pre, dq, dktab, dvtab, dxyz_q=None, dxyz_ref=None):
+        """dq, dktab, dvtab (+=); coordinates: dxyz_q (+=, query side), dxyz_ref (+=, neighbour side) when given"""
+        NQ, D = dres.shape
+        E = NQ * NBR
+        gidx = c["gidx"]
+        dvp = self.new(E, D)
+        da = c["w"]                                                       # overwritten: the tape entry is dead afterwards
+        tn.call("poem_tr_va_softmax_agg_bwd", dres, da, c["vtab"], c["pos"], gidx, 1.0 / math.sqrt(D), dvp, NQ, D)
+        dhg = self.lin_bwd(da, c["hg"], pre + "fc_gamma.2.weight", pre + "fc_gamma.2.bias")
+        self.relu_bwd_(dhg, c["hg"])
+        dt = self.lin_bwd(dhg, c["t"], pre + "fc_gamma.0.weight", pre + "fc_gamma.0.bias")
+        del dhg
+        tn.call("poem_tr_va_scatter", dt, dvp, gidx, dq, dktab, dvtab, NQ, D)           # dt <- dpos
+        del dvp
+        dhd = self.lin_bwd(dt, c["hd"], pre + "fc_delta.2.weight", pre + "fc_delta.2.bias")
+        self.relu_bwd_(dhd, c["hd"])
+        drel = self.new(E, 3) if dxyz_q is not None else None
+        tn.call("poem_tr_lin3_bwd", dhd, c["rel"], self.p[pre + "fc_delta.0.weight"], self.g[pre + "fc_delta.0.weight"],
+                self.g[pre + "fc_delta.0.bias"], drel, E, D)
+        if drel is not None:
+            tn.call("poem_tr_va_drel_scatter", drel, gidx, dxyz_q, dxyz_ref, NQ)
+
+    def _neighbours(self, q_xyz, ref_xyz, B, Q, R, forced):
+        """global row indices (B*Q*32) of the 32 nearest reference points of every query"""
+        if forced is not None:
+            local = forced.to(self.dev, torch.int32).contiguous()
+        else:
+            local = self.new(B, Q, NBR, dtype=torch.int32)
+            nat.check(self.lib.poem_knn32(q_xyz.data_ptr(), ref_xyz.data_ptr(), local.data_ptr(), B, Q, R,
+                                          torch.cuda.current_stream().cuda_stream))
+        gidx = self.new(B * Q * NBR, dtype=torch.int32)
+        tn.call("poem_tr_va_make_idx", local, None, B, Q, R, gidx)
+        return gidx, local
+
+    def _anchor_idx(self, B, Q, R):
+        gidx = self.new(B * Q * NBR, dtype=torch.int32)
+        tn.call("poem_tr_va_make_idx", None, self.anchor_idx, B, Q, R, gidx)
+        return gidx
+
+    # ------------------------------------------------------------------------------------------ one point_METRO_block
+    def block_fwd(self, i, q_feats, q_xyz, pt_feats, pt_xyz, B, forced):
+        d = self.dims
+        Q, P, D = d.n_query, d.n_sample, d.embed_dims
+        p = f"transformer.pt_metro_encoder.{i}."
+        ps, pc = p + "encoder.vec_attn.query_self_attn.", p + "encoder.vec_attn.query_cross_attn."
+        t = dict(q_feats=q_feats, pt_feats=pt_feats)
+        qe = self.lin(q_feats, p + "embedding.weight", p + "embedding.bias")
+        ke = self.lin(pt_feats, p + "embedding.weight", p + "embedding.bias")
+        a1, t["attn1"] = self.bert_fwd(qe, ke, p + "encoder.attn", B, Q, P)
+        a2, t["attn2"] = self.bert_fwd(a1, ke, p + "encoder.cross_attn", B, Q, P)
+        E = B * Q * NBR
+        # --- vector self-attention over the queries (point_transformers.py:70-96)
+        if i == 0:
+            gs, gc = self._anchor_idx(B, Q, Q), self._anchor_idx(B, Q, P)
+            nb = None
+        else:
+            gs, ls = self._neighbours(q_xyz, q_xyz, B, Q, Q, None if forced is None else forced[0])
+            gc, lc = self._neighbours(q_xyz, pt_xyz, B, Q, P, None if forced is None else forced[1])
+            nb = torch.stack([ls, lc])
+        rel = self.new(E, 3)
+        tn.call("poem_tr_va_rel", q_xyz, q_xyz, self.anchor_xyz if i == 0 else None, gs, E, rel)
+        xs = self.lin(a2, ps + "fc1.weight", ps + "fc1.bias")
+        qs, ks, vs = self.lin(xs, ps + "w_qs.weight"), self.lin(xs, ps + "w_ks.weight"), self.lin(xs, ps + "w_vs.weight")
+        res_s, t["core_s"] = self.va_core_fwd(qs, ks, vs, gs, rel, ps)
+        f1 = a2.clone()
+        self.lin(res_s, ps + "fc2.weight", ps + "fc2.bias", out=f1, acc=True)
+        # --- vector cross-attention queries -> basis points (point_transformers.py:125-156)
+        rel_c = self.new(E, 3)
+        tn.call("poem_tr_va_rel", q_xyz, pt_xyz, self.anchor_xyz if i == 0 else None, gc, E, rel_c)
+        qc = self.lin(f1, pc + "w_qs.weight")
+        xc = self.lin(ke, pc + "fc1.weight", pc + "fc1.bias")
+        kc, vc = self.lin(xc, pc + "w_ks.weight"), self.lin(xc, pc + "w_vs.weight")
+        res_c, t["core_c"] = self.va_core_fwd(qc, kc, vc, gc, rel_c, pc)
+        f2 = f1.clone()
+        self.lin(res_c, pc + "fc2.weight", pc + "fc2.bias", out=f2, acc=True)
+        # --- regression branch + FFN
+        r = self.relu_(self.lin(f2, p + "encoder.vec_attn.reg_branch.0.weight", p + "encoder.vec_attn.reg_branch.0.bias"))
+        xyz = self.new(B * Q, 3)
+        tn.call("poem_tr_lin_n3", r, self.p[p + "encoder.vec_attn.reg_branch.2.weight"],
+                self.p[p + "encoder.vec_attn.reg_branch.2.bias"], q_xyz, xyz, B * Q, D)
+        hpre = self.lin(f2, p + "encoder.intermediate.dense.weight", p + "encoder.intermediate.dense.bias")
+        h = self.new(*hpre.shape)
+        tn.call("poem_tr_gelu", hpre, h, h.numel())
+        o = self.lin(h, p + "encoder.output.dense.weight", p + "encoder.output.dense.bias")
+        out, xhat, rstd = self.ln(o, f2, p + "encoder.output.LayerNorm")
+        t.update(qe=qe, ke=ke, a1=a1, a2=a2, xs=xs, res_s=res_s, f1=f1, xc=xc, res_c=res_c, f2=f2, r=r, hpre=hpre, h=h,
+                 xhat=xhat, rstd=rstd)
+        return out, xyz, t, nb
+
+    def block_bwd(self, i, t, dout, dxyz_out, dpt_feats, B):
+        """dout: grad of the block's feature output (None for the last block), dxyz_out: grad of its coordinates.
+        returns (d q_feats, d q_xyz or None); accumulates d pt_feats"""
+        d = self.dims
+        Q, P, D = d.n_query, d.n_sample, d.embed_dims
+        p = f"transformer.pt_metro_encoder.{i}."
+        ps, pc = p + "encoder.vec_attn.query_self_attn.", p + "encoder.vec_attn.query_cross_attn."
+        f2 = t["f2"]
+        if dout is not None:
+            df2 = self.ln_bwd(dout, t["xhat"], t["rstd"], p + "encoder.output.LayerNorm")       # grad of (o + f2)
+            dh = self.lin_bwd(df2, t["h"], p + "encoder.output.dense.weight", p + "encoder.output.dense.bias")
+            tn.call("poem_tr_gelu_bwd", dh, t["hpre"], dh.numel())
+            self.lin_bwd(dh, f2, p + "encoder.intermediate.dense.weight", p + "encoder.intermediate.dense.bias", out=df2, acc=True)
+            del dh
+        else:
+            df2 = self.zeros(B * Q, D)
+        dr = self.new(B * Q, D)
+        tn.call("poem_tr_lin_n3_bwd", dxyz_out, t["r"], self.p[p + "encoder.vec_attn.reg_branch.2.weight"], dr,
+                self.g[p + "encoder.vec_attn.reg_branch.2.weight"], self.g[p + "encoder.vec_attn.reg_branch.2.bias"], B * Q, D)
+        self.relu_bwd_(dr, t["r"])
+        self.lin_bwd(dr, f2, p + "encoder.vec_attn.reg_branch.0.weight", p + "encoder.vec_attn.reg_branch.0.bias", out=df2, acc=True)
+        dq_xyz = dxyz_out.clone() if i > 0 else None            # block 0 starts from the constant template
+        # --- vector cross-attention: f2 = fc2(res_c) + f1
+        df1 = df2.clone()
+        dres = self.lin_bwd(df2, t["res_c"], pc + "fc2.weight", pc + "fc2.bias")
+        dqc, dkc, dvc = self.zeros(B * Q, D), self.zeros(B * P, D), self.zeros(B * P, D)
+        self.va_core_bwd(dres, t["core_c"], pc, dqc, dkc, dvc, dq_xyz, None)             # basis points are constants
+        self.lin_bwd(dqc, t["f1"], pc + "w_qs.weight", out=df1, acc=True)
+        dxc = self.lin_bwd(dkc, t["xc"], pc + "w_ks.weight")
+        self.lin_bwd(dvc, t["xc"], pc + "w_vs.weight", out=dxc, acc=True)
+        dke = self.lin_bwd(dxc, t["ke"], pc + "fc1.weight", pc + "fc1.bias")
+        del dqc, dkc, dvc, dxc
+        # --- vector self-attention: f1 = fc2(res_s) + a2
+        da2 = df1.clone()
+        dres = self.lin_bwd(df1, t["res_s"], ps + "fc2.weight", ps + "fc2.bias")
+        dqs, dks, dvs = self.zeros(B * Q, D), self.zeros(B * Q, D), self.zeros(B * Q, D)
+        self.va_core_bwd(dres, t["core_s"], ps, dqs, dks, dvs, dq_xyz, dq_xyz)           # both ends are query coordinates
+        dxs = self.lin_bwd(dqs, t["xs"], ps + "w_qs.weight")
+        self.lin_bwd(dks, t["xs"], ps + "w_ks.weight", out=dxs, acc=True)
+        self.lin_bwd(dvs, t["xs"], ps + "w_vs.weight", out=dxs, acc=True)
+        self.lin_bwd(dxs, t["a2"], ps + "fc1.weight", ps + "fc1.bias", out=da2, acc=True)
+        # --- the two BERT cross-attention layers
+        da1 = self.bert_bwd(da2, t["attn2"], p + "encoder.cross_attn", dke)
+        dqe = self.bert_bwd(da1, t["attn1"], p + "encoder.attn", dke)
+        dq_feats = self.lin_bwd(dqe, t["q_feats"], p + "embedding.weight", p + "embedding.bias")
+        self.lin_bwd(dke, t["pt_feats"], p + "embedding.weight", p + "embedding.bias", out=dpt_feats, acc=True)
+        return dq_feats, dq_xyz
+
+    # ------------------------------------------------------------------------------------------ image features -> point features
+    def head_stage_fwd(self, feat, views, intr, extr, centre, inp_w, inp_h):
+        d = self.dims
+        D, C, P, hw = d.embed_dims, d.in_channels, d.n_sample, d.feat_hw
+        HW = hw * hw
+        NV, B = int(feat.shape[0]), len(views)
+        planes = self.new(NV, D, HW)
+        tn.gemm(self.p["input_proj.weight"], feat, planes, D, HW, C, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1),
+                b_strides=(C * HW, 0), c_strides=(D * HW, 0), bias=self.p["input_proj.bias"], bias_on_m=True)
+        F3 = 3 * d.pos_feats
+        sine = torch.cat([sine_pos_3d(int(n), hw, hw, d.pos_feats, d.pos_normalize) for n in views]).reshape(NV, F3, HW)
+        sine = sine.to(self.dev).contiguous()                                  # constant of the graph (petr_transformer.py:434-469)
+        tn.gemm(self.p["adapt_pos3d.weight"], sine, planes, D, HW, F3, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1),
+                b_strides=(F3 * HW, 0), c_strides=(D * HW, 0), bias=self.p["adapt_pos3d.bias"], bias_on_m=True, accumulate=True)
+        img_sample = torch.tensor([b for b, n in enumerate(views) for _ in range(int(n))], dtype=torch.int32, device=self.dev)
+        grid = self.new(NV, P, 2)
+        tn.call("poem_tr_project", self.bps, centre, intr, extr, img_sample, NV, P, float(inp_w), float(inp_h), grid)
+        S = self.new(NV, D, P)
+        tn.call("poem_tr_sample", planes, grid, S, NV, D, P, hw)
+        X = S.view(NV * P, D)                                   # the reference's raw `.view(1, -1, n, D)` regroup, per sample
+        row0 = torch.tensor(np.concatenate([[0], np.cumsum(views)[:-1]]) * P, dtype=torch.int32, device=self.dev)
+        nv = torch.tensor(np.asarray(views), dtype=torch.int32, device=self.dev)
+        h0 = self.relu_(self.lin(X, "merge_net_feature.0.0.weight", "merge_net_feature.0.0.bias"))
+        m = self.lin(h0, "merge_net_feature.0.2.weight", "merge_net_feature.0.2.bias")
+        Dm = m.shape[1]
+        agg = self.new(B * P, Dm)
+        tn.call("poem_tr_merge_agg", m, row0, nv, B, P, Dm, agg)
+        h1 = self.relu_(self.lin(agg, "merge_net_feature.1.0.weight", "merge_net_feature.1.0.bias"))
+        y = self.lin(h1, "merge_net_feature.1.2.weight", "merge_net_feature.1.2.bias")
+        pt = self.new(B * P, D)
+        tn.call("poem_tr_merge_out", X, y, row0, nv, B, P, D, pt)
+        return pt, dict(feat=feat, sine=sine, grid=grid, X=X, row0=row0, nv=nv, h0=h0, m=m, agg=agg, h1=h1, NV=NV, B=B)
+
+    def head_stage_bwd(self, dpt, t):
+        d = self.dims
+        D, C, P, hw = d.embed_dims, d.in_channels, d.n_sample, d.feat_hw
+        HW, NV, B = hw * hw, t["NV"], t["B"]
+        F3 = 3 * d.pos_feats
+        dX = self.zeros(NV * P, D)
+        dy = self.new(B * P, D)
+        tn.call("poem_tr_merge_out_bwd", dpt, t["row0"], t["nv"], B, P, D, dX, dy)
+        dh1 = self.lin_bwd(dy, t["h1"], "merge_net_feature.1.2.weight", "merge_net_feature.1.2.bias")
+        self.relu_bwd_(dh1, t["h1"])
+        dagg = self.lin_bwd(dh1, t["agg"], "merge_net_feature.1.0.weight", "merge_net_feature.1.0.bias")
+        Dm = dagg.shape[1]
+        dm = self.zeros(NV * P, Dm)
+        tn.call("poem_tr_merge_agg_bwd", dagg, t["m"], t["row0"], t["nv"], B, P, Dm, dm)
+        dh0 = self.lin_bwd(dm, t["h0"], "merge_net_feature.0.2.weight", "merge_net_feature.0.2.bias")
+        self.relu_bwd_(dh0, t["h0"])
+        self.lin_bwd(dh0, t["X"], "merge_net_feature.0.0.weight", "merge_net_feature.0.0.bias", out=dX, acc=True)
+        dplanes = self.zeros(NV, D, HW)
+        tn.call("poem_tr_sample_bwd", dX, t["grid"], dplanes, NV, D, P, hw)           # dX memory == dS (NV, D, P)
+        for b in ("input_proj.bias", "adapt_pos3d.bias"):
+            tn.call("poem_tr_rowsum_groups", dplanes, NV * D, HW, D, self.g[b])
+        tn.gemm(dplanes, t["feat"], self.g["input_proj.weight"], D, C, HW, lda=HW, ldb=HW, ldc=C, batch=(NV, 1),
+                a_strides=(D * HW, 0), b_strides=(C * HW, 0), c_strides=(0, 0), accumulate=True)
+        tn.gemm(dplanes, t["sine"], self.g["adapt_pos3d.weight"], D, F3, HW, lda=HW, ldb=HW, ldc=F3, batch=(NV, 1),
+                a_strides=(D * HW, 0), b_strides=(F3 * HW, 0), c_strides=(0, 0), accumulate=True)
+        dfeat = self.new(NV, C, hw, hw)
+        tn.gemm(self.p["input_proj.weight"], dplanes, dfeat, C, HW, D, a_mn=True, b_mn=True, lda=C, ldb=HW, ldc=HW,
+                batch=(NV, 1), b_strides=(D * HW, 0), c_strides=(C * HW, 0))
+        return dfeat
+
+    # ------------------------------------------------------------------------------------------ whole head
+    def forward(self, mlvl_feat, img_metas, reference_joints, neighbours=None):
+        """all_coords_preds (NB, B, 799, 3) in metres; keeps the activations for `backward`.
+        `neighbours` (NB-1, 2, B, 799, 32): test hook, use these 32-NN sets instead of searching."""
+        d = self.dims
+        views = [int(v) for v in np.asarray(img_metas["cam_view_num"]).reshape(-1)]
+        B = len(views)
+        Q, P, D = d.n_query, d.n_sample, d.embed_dims
+        feat = mlvl_feat.detach().to(self.dev, torch.float32).contiguous()
+        assert feat.shape[0] == sum(views) and feat.shape[1] == d.in_channels and tuple(feat.shape[-2:]) == (d.feat_hw, d.feat_hw)
+        intr = img_metas["cam_intr"].to(self.dev, torch.float32).contiguous()
+        extr = img_metas["cam_extr"].to(self.dev, torch.float32).contiguous()
+        refj = reference_joints.to(self.dev, torch.float32).contiguous()
+        centre = refj[:, 9].contiguous()                                            # ptEmb_head.py:873 (fixed joint 9)
+        inp_w, inp_h = img_metas["inp_img_shape"]
+        pt_feats, t_head = self.head_stage_fwd(feat.view(feat.shape[0], d.in_channels, -1), views, intr, extr, centre, inp_w, inp_h)
+        q_feats = self.new(B * Q, D)
+        tn.call("poem_tr_bcast_batch", self.p["query_feat_embedding.weight"], B, Q * D, q_feats)
+        # normalised coordinates ((x + c) - c) / r as the reference forms them (ptEmb_head.py:896-899)
+        pt_xyz, q_xyz = self.new(B * P, 3), self.new(B * Q, 3)
+        tmp = self.new(B * P, 3)
+        neg = (-centre / d.radius).contiguous()
+        tn.call("poem_tr_bcast_batch", self.bps, B, P * 3, pt_xyz)
+        tn.call("poem_tr_affine_rows", pt_xyz, centre, 1.0, tmp, B * P, P, B, 3)
+        tn.call("poem_tr_affine_rows", tmp, neg, 1.0 / d.radius, pt_xyz, B * P, P, B, 3)
+        tn.call("poem_tr_bcast_batch", self.template, B, Q * 3, q_xyz)
+        tn.call("poem_tr_affine_rows", q_xyz, centre, 1.0, tmp, B * Q, Q, B, 3)
+        tn.call("poem_tr_affine_rows", tmp, neg, 1.0 / d.radius, q_xyz, B * Q, Q, B, 3)
+        coords = self.new(d.n_blocks, B, Q, 3)
+        blocks, nbs = [], []
+        for i in range(d.n_blocks):
+            forced = None if (neighbours is None or i == 0) else neighbours[i - 1]
+            q_feats, q_xyz, tb, nb = self.block_fwd(i, q_feats, q_xyz, pt_feats, pt_xyz, B, forced)
+            blocks.append(tb)
+            if nb is not None:
+                nbs.append(nb)
+            tn.call("poem_tr_affine_rows", q_xyz, centre, d.radius, coords[i], B * Q, Q, B, 3)
+        self.last_neighbours = torch.stack(nbs) if nbs else None
+        self.tape = dict(head=t_head, blocks=blocks, B=B)
+        return coords
+
+    def backward(self, dcoords):
+        """dcoords (NB, B, 799, 3): d loss / d all_coords_preds.  Accumulates into `g`, returns d loss / d mlvl_feat."""
+        if self.tape is None:
+            raise RuntimeError("backward() without a forward()")
+        d = self.dims
+        Q, P, D = d.n_query, d.n_sample, d.embed_dims
+        B = self.tape["B"]
+        dc = dcoords.detach().to(self.dev, torch.float32).contiguous()
+        dpt = self.zeros(B * P, D)
+        dfe, dxyz_next = None, None
+        for i in reversed(range(d.n_blocks)):
+            dxyz = self.new(B * Q, 3)
+            tn.call("poem_tr_affine_rows", dc[i].reshape(B * Q, 3), None, d.radius, dxyz, B * Q, Q, B, 3)
+            if dxyz_next is not None:
+                tn.call("poem_tr_axpy", dxyz, dxyz_next, 1.0, dxyz.numel())
+            dfe, dxyz_next = self.block_bwd(i, self.tape["blocks"][i], dfe, dxyz, dpt, B)
+            self.tape["blocks"][i] = None                                           # free the block's activations
+        tn.call("poem_tr_sum_batch", dfe, B, Q * D, self.g["query_feat_embedding.weight"])
+        dfeat = self.head_stage_bwd(dpt, self.tape["head"])
+        self.tape = None
+        return dfeat
+
+    # ------------------------------------------------------------------------------------------ after backward
+    def clip_grad_norm_per_tensor(self, max_norm):
+        """lib/utils/net_utils.py:122-132: clip_grad_norm_(param, max_norm, 2) on every parameter tensor by itself."""
+        ss = self.zeros(len(self.g))
+        for j, g in enumerate(self.g.values()):
+            tn.call("poem_tr_sumsq", g, g.numel(), ss[j:j + 1])
+        for j, g in enumerate(self.g.values()):
+            tn.call("poem_tr_clip_scale", g, g.numel(), ss[j:j + 1], float(max_norm))
+        return ss
+
+
+class HeadFunction(torch.autograd.Function):
+    """torch.autograd bridge: `coords = HeadFunction.apply(trainer, mlvl_feat, img_metas, reference_joints, *params)` lets a
+    torch loss (the reference's `compute_loss`) and a torch backbone sit on either side of the hand-written head; the
+    parameter gradients come back through `trainer.g` in the order of `trainer.p`."""
+
+    @staticmethod
+    def forward(ctx, trainer, mlvl_feat, img_metas, reference_joints, *params):
+        ctx.trainer = trainer
+        return trainer.forward(mlvl_feat, img_metas, reference_joints)
+
+    @staticmethod
+    def backward(ctx, dcoords):
+        tr = ctx.trainer
+        tr.zero_grad()
+        dfeat = tr.backward(dcoords)
+        return (None, dfeat, None, None) + tuple(tr.g[k] for k in tr.p)

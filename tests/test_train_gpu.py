@@ -392,3 +392,181 @@ def test_reg_out_sampler_merge_clip(tn):
     torch.nn.utils.clip_grad_norm_(p, 1.0, 2)
     close(gd, p.grad.double(), 1e-5)
     torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------ whole head: forward + backward
+def _oracle_modules():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import poem_oracle as orc
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    return orc, synth, release_dims
+
+
+def _cuda_metas(metas):
+    m = dict(metas)
+    m["cam_intr"], m["cam_extr"] = metas["cam_intr"].cuda(), metas["cam_extr"].cuda()
+    return m
+
+
+class _tf32_oracle:
+    """Context manager: the oracle's Linear / 1x1-conv / attention matmuls see their operands rounded to TF32 (nearest,
+    ties away: what tgemm.cuh does before the tensor core reads them) with a straight-through gradient; the K = 3 and
+    N = 3 layers and the merge dot products stay fp32, as on the device.  The tensor core's accumulation is not emulated.
+    `relu_masks`: the on/off pattern of every ReLU of the path in call order (taken from the device's saved activations).
+    The gradient is discontinuous in the activations at every ReLU: on "stress" weights a 1e-3 difference of the
+    activations flips ~0.03 % of the units and that alone moves every gradient by sqrt(3e-4) ~ 2-5 % in relative L2
+    (measured: CPU fp32 oracle vs CPU TF32-operand oracle, median 3.5 %; scripts/train_diag.py)."""
+
+    def __init__(self, orc, relu_masks=None):
+        self.orc = orc
+        self.relu_masks = None if relu_masks is None else list(relu_masks)   # consumed in call order
+
+    @staticmethod
+    def rnd(t):
+        i = t.detach().contiguous().view(torch.int32)
+        r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+        return t + (r - t).detach()
+
+    def __enter__(self):
+        import types
+        import torch.nn.functional as TF
+        orc, rnd = self.orc, self.rnd
+        shim = types.SimpleNamespace(**{k: getattr(TF, k) for k in dir(TF) if not k.startswith("_")})
+
+        def linear(x, w, b=None):
+            if w.shape[0] == 3 or w.shape[1] == 3:
+                return TF.linear(x, w, b)
+            return TF.linear(rnd(x), rnd(w), b)
+
+        def conv2d(x, w, b=None, **kw):
+            return TF.conv2d(rnd(x), rnd(w), b, **kw)
+
+        def bert_cross_attention(sd_, prefix, hidden, enc, n_heads):
+            B, Lq, D = hidden.shape
+            hd = D // n_heads
+            split = lambda t: t.view(B, -1, n_heads, hd).transpose(1, 2)  # noqa: E731
+            q = split(linear(hidden, sd_[prefix + ".self.query.weight"], sd_[prefix + ".self.query.bias"]))
+            k = split(linear(enc, sd_[prefix + ".self.key.weight"], sd_[prefix + ".self.key.bias"]))
+            v = split(linear(enc, sd_[prefix + ".self.value.weight"], sd_[prefix + ".self.value.bias"]))
+            p = torch.softmax(rnd(q) @ rnd(k).transpose(-1, -2) / math.sqrt(hd), dim=-1)
+            ctx = (rnd(p) @ rnd(v)).transpose(1, 2).reshape(B, Lq, D)
+            o = linear(ctx, sd_[prefix + ".output.dense.weight"], sd_[prefix + ".output.dense.bias"])
+            return TF.layer_norm(o + hidden, (D,), sd_[prefix + ".output.LayerNorm.weight"],
+                                 sd_[prefix + ".output.LayerNorm.bias"], eps=1e-12)
+
+        shim.linear, shim.conv2d = linear, conv2d
+        if self.relu_masks is not None:
+            def relu(x):                      # ReLU with the device's on/off pattern (same idea as the forced 32-NN sets)
+                m = self.relu_masks.pop(0)
+                assert tuple(m.shape) == tuple(x.shape), (tuple(m.shape), tuple(x.shape))
+                return x * m
+            shim.relu = relu
+        self.saved = (orc.F, orc.bert_cross_attention)
+        orc.F, orc.bert_cross_attention = shim, bert_cross_attention
+        return self
+
+    def __exit__(self, *exc):
+        self.orc.F, self.orc.bert_cross_attention = self.saved
+        return False
+
+
+def test_head_backward_matches_oracle_autograd(tn):
+    """POEM-small, ragged views [2, 1], "stress" weights (the case of tests/golden/grad_small_b2.npz): gradients of every
+    live parameter and of mlvl_feat against torch.autograd through the fp32 oracle run on the SAME 32-NN sets (the search is
+    discontinuous), then the parameter-gradient norms against the golden written from the real reference head."""
+    import ast
+    import os
+    import numpy as np
+    from poem_v2_b200.train import HeadTrainer
+    orc, synth, release_dims = _oracle_modules()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad_small_b2.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    dims = release_dims(meta["size"])
+    sd = synth.make_state_dict(dims, meta["wseed"], "stress")
+    feat, metas, ref_j = synth.make_inputs(dims, len(meta["views"]), meta["views"], meta["iseed"])
+    bps, a_xyz, a_idx = synth.load_assets()
+    tr = HeadTrainer(dims, sd, synth.standin_template())
+    coords = tr.forward(feat.cuda(), _cuda_metas(metas), ref_j.cuda())
+    torch.cuda.synchronize()
+    nbr = tr.last_neighbours.long().cpu()
+    assert tuple(nbr.shape) == (dims.n_blocks - 1, 2, len(meta["views"]), dims.n_query, 32)
+    # oracle with autograd on the same discontinuous choices as the device run: the 32-NN sets and the ReLU on/off
+    # patterns (see _tf32_oracle), GEMM operands rounded where the device rounds them
+    views, P_ = meta["views"], dims.n_sample
+    th, masks, r0 = tr.tape["head"], [], 0
+    for b_, n in enumerate(views):
+        h0 = (th["h0"][r0:r0 + P_ * n] > 0).float().cpu()
+        masks.append(h0.view(1, P_, n, -1) if n > 1 else h0.view(1, P_, -1))
+        masks.append((th["h1"][b_ * P_:(b_ + 1) * P_] > 0).float().cpu().view(1, P_, -1))
+        r0 += P_ * n
+    Bn, Qn = len(views), dims.n_query
+    for tb in tr.tape["blocks"]:
+        for core in ("core_s", "core_c"):
+            masks.append((tb[core]["hd"] > 0).float().cpu().view(Bn, Qn, 32, -1))
+            masks.append((tb[core]["hg"] > 0).float().cpu().view(Bn, Qn, 32, -1))
+        masks.append((tb["r"] > 0).float().cpu().view(Bn, Qn, -1))
+    sdo = {k: (v.clone().requires_grad_(True) if k in tr.p else v) for k, v in sd.items()}
+    feato = feat.clone().requires_grad_(True)
+    with _tf32_oracle(orc, masks) as shim_ctx:
+        want = orc.head_forward(sdo, dims, feato, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx, neighbours=nbr)
+    assert not shim_ctx.relu_masks, "every exported ReLU pattern must have been consumed"
+    with torch.no_grad():
+        want32 = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx, neighbours=nbr)
+    e32 = (coords.cpu() - want32).norm(dim=-1)
+    print(f"train forward vs fp32 oracle (forced 32-NN): mean {e32.mean().item() * 1e3:.4f} mm, worst rel "
+          f"{(e32 / want32.norm(dim=-1)).max().item():.2e}")
+    assert (e32 / want32.norm(dim=-1)).max().item() <= 1e-3    # north-star tolerance on the training forward as well
+    err = (coords.cpu() - want.detach()).norm(dim=-1)
+    rel = (err / want.detach().norm(dim=-1)).max().item()
+    print(f"train forward vs TF32-operand oracle: mean {err.mean().item() * 1e3:.4f} mm, worst rel {rel:.2e}")
+    assert rel <= 1e-3, rel
+    g = torch.Generator().manual_seed(meta["iseed"] + 77)
+    target = want.detach() + 0.005 * torch.randn(want.shape, generator=g)
+    loss = ((want - target) * 1e3).pow(2).mean()
+    loss.backward()
+    # the backward under test gets the oracle's d loss / d coords (the loss is quadratic: with the device's own coords
+    # the 1e-3 forward difference over a 5 mm residual would show up as a ~1 % difference of every gradient)
+    dcoords = 2e6 * (want.detach() - target) / want.numel()
+    dfeat = tr.backward(dcoords.cuda())
+    torch.cuda.synchronize()
+    worst = {}
+    for k in tr.p:
+        ref = sdo[k].grad
+        got = tr.g[k].cpu()
+        if ref is None or ref.abs().max().item() == 0:          # FFN of the last block: its output is unused
+            assert got.abs().max().item() == 0, k
+            continue
+        if k.endswith("self.key.bias") or k.endswith("fc_gamma.2.bias"):
+            # softmax is invariant to a constant added to every key's / neighbour's score: the exact gradient is 0, the
+            # reference holds rounding noise; bound ours by the scale of a neighbouring bias gradient instead
+            other = k.replace("key", "query") if k.endswith("key.bias") else k.replace("fc_gamma.2", "fc_gamma.0")
+            assert got.norm().item() <= 1e-3 * sdo[other].grad.norm().item(), k
+            continue
+        worst[k] = rel_l2(got, ref)
+    worst["mlvl_feat"] = rel_l2(dfeat.cpu(), feato.grad)
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    print("train backward vs oracle autograd, worst rel-L2:", [(k.replace("transformer.pt_metro_encoder.", "b"), f"{v:.2e}") for k, v in top])
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/train_grad_errors.txt", "w") as fh:
+        for k, v in sorted(worst.items(), key=lambda kv: -kv[1]):
+            fh.write(f"{v:.3e}  {k}\n")
+    assert max(worst.values()) <= 2e-2, top
+    assert sorted(worst.values())[len(worst) // 2] <= 5e-3
+    # the real reference's gradients (its own 32-NN sets; norms of 13 parameters spread over the path)
+    tr2 = HeadTrainer(dims, sd, synth.standin_template())
+    c2 = tr2.forward(feat.cuda(), _cuda_metas(metas), ref_j.cuda())
+    with torch.no_grad():
+        ref_coords = orc.head_forward(sd, dims, feat, metas, ref_j, synth.standin_template(), bps, a_xyz, a_idx)
+    g = torch.Generator().manual_seed(meta["iseed"] + 77)
+    target = ref_coords + 0.005 * torch.randn(ref_coords.shape, generator=g)
+    tr2.backward(2e6 * (c2 - target.cuda()) / c2.numel())
+    torch.cuda.synchronize()
+    # un-forced: own 32-NN sets and ReLU patterns against the reference's, so only statistics can agree (see
+    # _tf32_oracle); the cancellation-heavy bias sums move most
+    dev_ = {k: abs(float(tr2.g[k].norm()) / float(z["norm:" + k]) - 1.0) for k in meta["keys"]}
+    print("gradient norms vs the reference golden, |ratio - 1|:", {k.replace("transformer.pt_metro_encoder.", "b").replace("encoder.", ""): f"{v:.3f}" for k, v in dev_.items()})
+    assert sorted(dev_.values())[len(dev_) // 2] <= 3e-2, dev_
+    assert max(dev_.values()) <= 0.3, dev_
