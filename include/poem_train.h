@@ -33,12 +33,14 @@ long long poem_tr_kernel_launches(void);
  *   batch: nb1 x nb2 problems; element strides (a_s1, a_s2), (b_s1, b_s2), (c_s1, c_s2); a stride of 0 shares the
  *   operand along that axis; c stride 0 with extent > 1 sums the batch into one C (atomic accumulation).
  *   bias: NULL, [N] (bias_on_m == 0) or [M] (bias_on_m == 1).  accumulate != 0: C += instead of C =.
+ *   relu != 0: C = max(., 0) after the bias (plain stores only).  relu_mask != NULL ([M x N], pitch ld_mask): C = 0 where
+ *   relu_mask <= 0 — the dgrad GEMM that feeds a ReLU's backward writes the masked gradient directly.
  *   pitches must be multiples of 4 elements and bases 16-byte aligned (TMA).  This one primitive is the forward, dgrad and
  *   wgrad of every nn.Linear / 1x1 conv of the path and the five GEMMs of the attention core and its backward. */
 int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a_s1, long long a_s2, const float* B, int b_mn,
                  long long ldb, long long b_s1, long long b_s2, float* C, long long ldc, long long c_s1, long long c_s2,
                  int M, int N, int K, int nb1, int nb2, float alpha, const float* bias, int bias_on_m, int accumulate,
-                 void* stream);
+                 int relu, const float* relu_mask, long long ld_mask, void* stream);
 
 /* elementwise */
 int poem_tr_relu(float* y, long long n, void* stream);
@@ -84,7 +86,7 @@ int poem_tr_va_drel_scatter(const float* drel, const int32_t* gidx, float* dxyz_
 /* reg_branch.2 : Linear(D, 3) (+ base coordinates) */
 int poem_tr_lin_n3(const float* x, const float* W, const float* b, const float* base, float* y, long long M, int D, void* stream);
 int poem_tr_lin_n3_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, long long M,
-                       int D, void* stream);
+                       int D, int x_is_relu /* dx = 0 where x <= 0 */, void* stream);
 
 /* camera projection of the BPS points + bilinear sampler (planes NCHW, hw x hw) and its scatter backward */
 int poem_tr_project(const float* bps, const float* centre, const float* cam_intr, const float* cam_extr,
@@ -105,6 +107,19 @@ int poem_tr_merge_out_bwd(const float* dout, const int32_t* row0, const int32_t*
  * sumsq[0] += |g|^2 ; g *= min(1, max_norm / (sqrt(sumsq[0]) + 1e-6)) */
 int poem_tr_sumsq(const float* g, long long n, float* sumsq, void* stream);
 int poem_tr_clip_scale(float* g, long long n, const float* sumsq, float max_norm, void* stream);
+
+/* the same on a flat gradient buffer (segment s = [off[s], off[s] + len[s]), device arrays): one launch per pass */
+int poem_tr_seg_sumsq(const float* g, const long long* off, const long long* len, int n_seg, float* sumsq, void* stream);
+int poem_tr_seg_clip(float* g, const long long* off, const long long* len, int n_seg, const float* sumsq, float max_norm,
+                     void* stream);
+/* torch.optim.Adam step on flat buffers (lib/utils/net_utils.py:57-63): L2 weight decay added to the gradient,
+ * bias-corrected first / second moments; `step` counts from 1 */
+int poem_tr_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step, void* stream);
+/* 3-D terms of compute_loss on the last block (lib/models/POEM.py:398-412): loss[0] += w_joints * MSE(joints) +
+ * w_verts * L1(verts); dcoords [n_blocks, B, n_joints + n_verts, 3] = d loss / d all_coords_preds */
+int poem_tr_coord_loss(const float* coords, const float* gt_joints, const float* gt_verts, int n_blocks, int B,
+                       int n_joints, int n_verts, float w_joints, float w_verts, float* loss, float* dcoords, void* stream);
 
 #ifdef __cplusplus
 }

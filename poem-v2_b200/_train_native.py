@@ -15,7 +15,7 @@ HEADERS = ["common.cuh", "tgemm.cuh", "train_simt.cuh"]
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 SIGNATURES = {
-    "poem_tr_gemm": [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P, _I, _I, _P],
+    "poem_tr_gemm": [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _L, _P],
     "poem_tr_relu": [_P, _L, _P],
     "poem_tr_relu_bwd": [_P, _P, _L, _P],
     "poem_tr_gelu": [_P, _P, _L, _P],
@@ -40,7 +40,7 @@ SIGNATURES = {
     "poem_tr_va_scatter": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
     "poem_tr_va_drel_scatter": [_P, _P, _P, _P, _L, _P],
     "poem_tr_lin_n3": [_P, _P, _P, _P, _P, _L, _I, _P],
-    "poem_tr_lin_n3_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _P],
+    "poem_tr_lin_n3_bwd": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "poem_tr_project": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
     "poem_tr_sample": [_P, _P, _P, _I, _I, _I, _I, _P],
     "poem_tr_sample_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
@@ -50,6 +50,10 @@ SIGNATURES = {
     "poem_tr_merge_out_bwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P],
     "poem_tr_sumsq": [_P, _L, _P, _P],
     "poem_tr_clip_scale": [_P, _L, _P, _F, _P],
+    "poem_tr_seg_sumsq": [_P, _P, _P, _I, _P, _P],
+    "poem_tr_seg_clip": [_P, _P, _P, _I, _P, _F, _P],
+    "poem_tr_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
+    "poem_tr_coord_loss": [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
 }
 EXPORTS = ["poem_tr_abi_version", "poem_tr_last_error", "poem_tr_kernel_launches"] + list(SIGNATURES)
 
@@ -102,22 +106,50 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name, *args):
+_prof = None     # list of (label, start event, end event) while profiling
+
+
+def profile(on=True):
+    """Per-call CUDA-event timing of the primitives (diagnostics: serialises nothing, adds two event records per call)."""
+    global _prof
+    _prof = [] if on else None
+
+
+def profile_summary():
+    """{label: (calls, total ms)} of the calls since profile(True); synchronises."""
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for label, a, b in _prof or []:
+        n, t = out.get(label, (0, 0.0))
+        out[label] = (n + 1, t + a.elapsed_time(b))
+    return out
+
+
+def call(name, *args, label=None):
     """Call a primitive; torch tensors are passed as device pointers, the current torch stream is appended."""
     import torch
     lib = load()
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    if _prof is not None:
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
     rc = getattr(lib, name)(*conv, _stream())
+    if _prof is not None:
+        eb.record()
+        _prof.append((label or name.replace("poem_tr_", ""), ea, eb))
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.poem_tr_last_error().decode()}")
 
 
 def gemm(A, B, Cout, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, batch=(1, 1),
-         a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0), alpha=1.0, bias=None, bias_on_m=False, accumulate=False):
+         a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0), alpha=1.0, bias=None, bias_on_m=False, accumulate=False,
+         relu=False, relu_mask=None):
     """C (+)= alpha * op(A) op(B)^T (+ bias), see include/poem_train.h.  Default pitches: dense row-major operands."""
     lda = lda if lda is not None else (M if a_mn else K)
     ldb = ldb if ldb is not None else (N if b_mn else K)
     ldc = ldc if ldc is not None else N
     call("poem_tr_gemm", A, int(a_mn), lda, a_strides[0], a_strides[1], B, int(b_mn), ldb, b_strides[0], b_strides[1],
          Cout, ldc, c_strides[0], c_strides[1], M, N, K, batch[0], batch[1], float(alpha), bias, int(bias_on_m),
-         int(accumulate))
+         int(accumulate), int(relu), relu_mask, (relu_mask.shape[-1] if relu_mask is not None else 0),
+         label=None if _prof is None else f"gemm {'T' if a_mn else 'N'}{'T' if b_mn else 'N'} {M}x{N}x{K} b{batch[0] * batch[1]}")

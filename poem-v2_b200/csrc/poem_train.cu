@@ -6,6 +6,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/poem_train.h"
@@ -44,6 +46,15 @@ static int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+static int agg_cap() {   // resident-block cap per SM of the per-query vector-attention kernels (POEM_TR_AGG_CAP, experiments)
+  static int c = 0;
+  if (c == 0) {
+    const char* e = getenv("POEM_TR_AGG_CAP");
+    c = e ? atoi(e) : 32;
+    if (c < 1) c = 1;
+  }
+  return c;
 }
 static inline int grid_for(long long n, int block = 256, int per_sm = 8) {
   long long g = (n + block - 1) / block;
@@ -118,7 +129,8 @@ static int launch_tgemm_major(int a_mn, int b_mn, const CUtensorMap& ta, const C
 extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a_s1, long long a_s2, const float* B,
                             int b_mn, long long ldb, long long b_s1, long long b_s2, float* C, long long ldc,
                             long long c_s1, long long c_s2, int M, int N, int K, int nb1, int nb2, float alpha,
-                            const float* bias, int bias_on_m, int accumulate, void* stream) {
+                            const float* bias, int bias_on_m, int accumulate, int relu, const float* relu_mask, long long ld_mask,
+                            void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || nb1 < 1 || nb2 < 1) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: bad arguments");
   const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
@@ -130,7 +142,7 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
   rc = make_tmap_f32(&tb, B, b_mn, N, K, ldb, b_s1, b_s2, nb1, nb2, BN, &p.b_bc1, &p.b_bc2);
   if (rc) return rc;
   p.M = M, p.N = N, p.K = K, p.nb1 = nb1, p.nb2 = nb2;
-  p.alpha = alpha, p.bias = bias, p.bias_on_m = bias_on_m;
+  p.alpha = alpha, p.bias = bias, p.bias_on_m = bias_on_m, p.relu = relu;
   p.C = C, p.ldc = ldc, p.c_s1 = c_s1, p.c_s2 = c_s2;
   const int tiles = ((M + TG_BM - 1) / TG_BM) * ((N + BN - 1) / BN) * nb1 * nb2;
   const bool batch_sum = (nb1 > 1 && c_s1 == 0) || (nb2 > 1 && c_s2 == 0);
@@ -145,6 +157,9 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
   splits = (kblocks + kb_per_split - 1) / kb_per_split;
   p.splits = splits, p.k_per_split = kb_per_split * TG_BK;
   p.mode = (splits > 1 || batch_sum) ? TG_ATOMIC : (accumulate ? TG_ADD : TG_STORE);
+  p.relu_mask = relu_mask, p.ld_mask = ld_mask;
+  if (relu_mask && (nb1 * nb2 != 1 || p.mode != TG_STORE)) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: relu_mask needs an unbatched plain store");
+  if (relu && p.mode != TG_STORE) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: relu needs a plain store (no split / accumulate)");
   if (p.mode == TG_ATOMIC && !accumulate) {      // atomic partial sums need a zeroed destination
     const int e1 = c_s1 == 0 ? 1 : nb1, e2 = c_s2 == 0 ? 1 : nb2;
     for (int i2 = 0; i2 < e2; ++i2)
@@ -250,13 +265,19 @@ extern "C" int poem_tr_layernorm_bwd(const float* dy, const float* xhat, const f
 
 extern "C" int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, void* stream) {
   if (rows > 0x7fffffffLL) return fail(POEM_TR_E_BADARG, "softmax_rows: too many rows");
-  tr_softmax_rows_kernel<<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
+  const bool al = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+  if (al && L == 4096) tr_softmax_rows_kernel<4><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
+  else if (al && L == 1024) tr_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
+  else tr_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
   TR_CHECK("softmax_rows");
   return 0;
 }
 extern "C" int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, void* stream) {
   if (rows > 0x7fffffffLL) return fail(POEM_TR_E_BADARG, "softmax_rows_bwd: too many rows");
-  tr_softmax_rows_bwd_kernel<<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
+  const bool al = ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(dP)) & 15) == 0;
+  if (al && L == 4096) tr_softmax_rows_bwd_kernel<4><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
+  else if (al && L == 1024) tr_softmax_rows_bwd_kernel<1><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
+  else tr_softmax_rows_bwd_kernel<0><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
   TR_CHECK("softmax_rows_bwd");
   return 0;
 }
@@ -274,7 +295,13 @@ extern "C" int poem_tr_va_rel(const float* q_xyz, const float* ref_xyz, const fl
   return 0;
 }
 extern "C" int poem_tr_lin3_relu(const float* rel, const float* W, const float* b, float* h, long long E, int D, void* stream) {
-  tr_lin3_relu_kernel<<<grid_for(E * D), 256, 0, ST>>>(rel, W, b, h, E, D);
+  if (D % 4 || D > 1024) return fail(POEM_TR_E_BADARG, "lin3_relu: D = %d", D);
+  {
+    dim3 block(D / 4, 256 / (D / 4) > 0 ? 256 / (D / 4) : 1);
+    long long g = (E + block.y - 1) / block.y;
+    if (g > 16LL * num_sms()) g = 16LL * num_sms();
+    tr_lin3_relu_kernel<<<(unsigned)g, block, 0, ST>>>(rel, W, b, h, E, D);
+  }
   TR_CHECK("lin3_relu");
   return 0;
 }
@@ -293,25 +320,34 @@ extern "C" int poem_tr_lin3_bwd(const float* dh, const float* rel, const float* 
 }
 extern "C" int poem_tr_va_gather_t(const float* q, const float* ktab, const int32_t* gidx, const float* pos, float* t,
                                    long long E, int D, void* stream) {
-  tr_va_gather_t_kernel<<<grid_for(E * D), 256, 0, ST>>>(q, ktab, gidx, pos, t, E, D);
+  if (D % 4 || D > 1024) return fail(POEM_TR_E_BADARG, "va_gather_t: D = %d", D);
+  {
+    dim3 block(D / 4, 256 / (D / 4) > 0 ? 256 / (D / 4) : 1);
+    long long g = (E + block.y - 1) / block.y;
+    if (g > 16LL * num_sms()) g = 16LL * num_sms();
+    tr_va_gather_t_kernel<<<(unsigned)g, block, 0, ST>>>(q, ktab, gidx, pos, t, E, D);
+  }
   TR_CHECK("va_gather_t");
   return 0;
 }
 extern "C" int poem_tr_va_softmax_agg(float* a_w, const float* vtab, const float* pos, const int32_t* gidx, float scale,
                                       float* res, long long NQ, int D, void* stream) {
-  tr_va_softmax_agg_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D);
+  int lg = 0;
+  while ((1 << lg) < D) ++lg;
+  if ((1 << lg) != D) return fail(POEM_TR_E_BADARG, "va_softmax_agg: D = %d is not a power of two", D);
+  tr_va_softmax_agg_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D, lg);
   TR_CHECK("va_softmax_agg");
   return 0;
 }
 extern "C" int poem_tr_va_softmax_agg_bwd(const float* dres, float* w_da, const float* vtab, const float* pos,
                                           const int32_t* gidx, float scale, float* dvp, long long NQ, int D, void* stream) {
-  tr_va_softmax_agg_bwd_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(dres, w_da, vtab, pos, gidx, scale, dvp, NQ, D);
+  tr_va_softmax_agg_bwd_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), D, 0, ST>>>(dres, w_da, vtab, pos, gidx, scale, dvp, NQ, D);
   TR_CHECK("va_softmax_agg_bwd");
   return 0;
 }
 extern "C" int poem_tr_va_scatter(float* dt_dpos, const float* dvp, const int32_t* gidx, float* dq, float* dktab,
                                   float* dvtab, long long NQ, int D, void* stream) {
-  tr_va_scatter_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(dt_dpos, dvp, gidx, dq, dktab, dvtab, NQ, D);
+  tr_va_scatter_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), D, 0, ST>>>(dt_dpos, dvp, gidx, dq, dktab, dvtab, NQ, D);
   TR_CHECK("va_scatter");
   return 0;
 }
@@ -330,10 +366,10 @@ extern "C" int poem_tr_lin_n3(const float* x, const float* W, const float* b, co
   return 0;
 }
 extern "C" int poem_tr_lin_n3_bwd(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db,
-                                  long long M, int D, void* stream) {
+                                  long long M, int D, int x_is_relu, void* stream) {
   long long g = M < 4 * num_sms() ? M : 4 * num_sms();
   if (g < 1) g = 1;
-  tr_lin_n3_bwd_kernel<<<(unsigned)g, 256, 0, ST>>>(dy, x, W, dx, dW, db, M, D);
+  tr_lin_n3_bwd_kernel<<<(unsigned)g, 256, 0, ST>>>(dy, x, W, dx, dW, db, M, D, x_is_relu);
   TR_CHECK("lin_n3_bwd");
   return 0;
 }
@@ -394,5 +430,33 @@ extern "C" int poem_tr_sumsq(const float* g, long long n, float* sumsq, void* st
 extern "C" int poem_tr_clip_scale(float* g, long long n, const float* sumsq, float max_norm, void* stream) {
   tr_clip_scale_kernel<<<grid_for(n), 256, 0, ST>>>(g, n, sumsq, max_norm);
   TR_CHECK("clip_scale");
+  return 0;
+}
+
+extern "C" int poem_tr_seg_sumsq(const float* g, const long long* off, const long long* len, int n_seg, float* sumsq, void* stream) {
+  tr_seg_sumsq_kernel<<<n_seg, 256, 0, ST>>>(g, off, len, sumsq);
+  TR_CHECK("seg_sumsq");
+  return 0;
+}
+extern "C" int poem_tr_seg_clip(float* g, const long long* off, const long long* len, int n_seg, const float* sumsq,
+                                float max_norm, void* stream) {
+  tr_seg_clip_kernel<<<n_seg, 256, 0, ST>>>(g, off, len, sumsq, max_norm);
+  TR_CHECK("seg_clip");
+  return 0;
+}
+extern "C" int poem_tr_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                            float eps, float weight_decay, int step, void* stream) {
+  if (step < 1) return fail(POEM_TR_E_BADARG, "adam: step counts from 1");
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  tr_adam_kernel<<<grid_for(n), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+  TR_CHECK("adam");
+  return 0;
+}
+extern "C" int poem_tr_coord_loss(const float* coords, const float* gt_joints, const float* gt_verts, int n_blocks, int B,
+                                  int n_joints, int n_verts, float w_joints, float w_verts, float* loss, float* dcoords,
+                                  void* stream) {
+  tr_coord_loss_kernel<<<grid_for((long long)n_blocks * B * (n_joints + n_verts) * 3), 256, 0, ST>>>(
+      coords, gt_joints, gt_verts, n_blocks, B, n_joints, n_verts, w_joints, w_verts, loss, dcoords);
+  TR_CHECK("coord_loss");
   return 0;
 }

@@ -42,6 +42,9 @@ struct TgParams {
   float* C;
   long long ldc, c_s1, c_s2;
   int mode;
+  int relu;                // max(., 0) after the bias (forward of Linear + ReLU)
+  const float* relu_mask;  // nullptr or [M, N] (pitch ld_mask, same batch strides as C): C = 0 where relu_mask <= 0 (dgrad into a ReLU)
+  long long ld_mask;
 };
 
 template <int BN>
@@ -172,7 +175,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const int quarter = warp & 3;
     const int row = m0 + quarter * 32 + lane;
     const bool with_bias = (p.bias != nullptr) && split == 0;
-    float* crow = p.C + (long long)b1 * p.c_s1 + (long long)b2 * p.c_s2 + (long long)row * p.ldc;
+    float* cbase = p.C + (long long)b1 * p.c_s1 + (long long)b2 * p.c_s2;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_s1 & 3) == 0) && ((p.c_s2 & 3) == 0);
     const float bias_m = (with_bias && p.bias_on_m && row < p.M) ? p.bias[row] : 0.f;
     // ---- main loop duty: round each landed stage to TF32 (nearest, ties away) in place
@@ -197,6 +200,11 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
+    // every stage has been consumed (acc_full follows the last MMA): the ring doubles as the transpose buffer.
+    // TMEM hands out one row per lane; a [32 x 36]-float pad per warp turns that into whole 128-byte row segments
+    // (four rows per store instruction), conflict-free for the 128-bit accesses on both sides.
+    float* stg = reinterpret_cast<float*>(smem) + quarter * (32 * 36);
+    const int rr4 = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -208,32 +216,57 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         for (int i = 0; i < 32; ++i) r[i] = 0u;
       }
       const int col0 = n0 + c * 32;
-      if (row >= p.M || col0 >= p.N) continue;
-      float v[32];
+      if (col0 >= p.N) break;                      // warp-uniform
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = p.alpha * __uint_as_float(r[i]) + bias_m;
-        if (with_bias && !p.bias_on_m && col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+      for (int i = 0; i < 8; ++i) {
+        float4 o;
+        o.x = p.alpha * __uint_as_float(r[4 * i]) + bias_m, o.y = p.alpha * __uint_as_float(r[4 * i + 1]) + bias_m;
+        o.z = p.alpha * __uint_as_float(r[4 * i + 2]) + bias_m, o.w = p.alpha * __uint_as_float(r[4 * i + 3]) + bias_m;
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * i) = o;
       }
-      if (p.mode == TG_ATOMIC) {
+      __syncwarp();
+      const int col = col0 + 4 * l8;
+      float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (with_bias && !p.bias_on_m) {
+        if (col + 0 < p.N) bn.x = __ldg(p.bias + col);
+        if (col + 1 < p.N) bn.y = __ldg(p.bias + col + 1);
+        if (col + 2 < p.N) bn.z = __ldg(p.bias + col + 2);
+        if (col + 3 < p.N) bn.w = __ldg(p.bias + col + 3);
+      }
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < p.N) atomicAdd(crow + col0 + i, v[i]);
-      } else if (vec_ok && col0 + 32 <= p.N) {
-        float4* dst = reinterpret_cast<float4*>(crow + col0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int it = 0; it < 8; ++it) {
+        const int rl = 4 * it + rr4;
+        const int grow = m0 + quarter * 32 + rl;
+        if (grow >= p.M || col >= p.N) continue;
+        float4 o = *reinterpret_cast<const float4*>(stg + rl * 36 + 4 * l8);
+        o.x += bn.x, o.y += bn.y, o.z += bn.z, o.w += bn.w;
+        if (p.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+        if (p.relu_mask != nullptr) {
+          const float* mk = p.relu_mask + (long long)grow * p.ld_mask + col;
+          if (!(mk[0] > 0.f)) o.x = 0.f;
+          if (col + 1 < p.N && !(mk[1] > 0.f)) o.y = 0.f;
+          if (col + 2 < p.N && !(mk[2] > 0.f)) o.z = 0.f;
+          if (col + 3 < p.N && !(mk[3] > 0.f)) o.w = 0.f;
+        }
+        float* dst = cbase + (long long)grow * p.ldc + col;
+        if (p.mode == TG_ATOMIC) {
+          atomicAdd(dst, o.x);
+          if (col + 1 < p.N) atomicAdd(dst + 1, o.y);
+          if (col + 2 < p.N) atomicAdd(dst + 2, o.z);
+          if (col + 3 < p.N) atomicAdd(dst + 3, o.w);
+        } else if (vec_ok && col + 4 <= p.N) {
           if (p.mode == TG_ADD) {
-            const float4 old = dst[i];
+            const float4 old = *reinterpret_cast<const float4*>(dst);
             o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
           }
-          dst[i] = o;
-        }
-      } else {
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < p.N) crow[col0 + i] = (p.mode == TG_ADD ? crow[col0 + i] : 0.f) + v[i];
+          for (int k = 0; k < 4; ++k)
+            if (col + k < p.N) dst[k] = (p.mode == TG_ADD ? dst[k] : 0.f) + ov[k];
+        }
       }
     }
   }

@@ -180,62 +180,82 @@ __global__ void tr_layernorm_bwd_kernel(const float* dy, const float* xhat, cons
 }
 
 // ------------------------------------------------------------------------------------------------ row softmax (BERT attention)
-// P = softmax(S * scale) in place; one block (256 threads) per row of length L
+// block-wide reductions for the row kernels (256 threads)
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = is_max ? fmaxf(t, red[w]) : t + red[w];
+  return t;
+}
+// P = softmax(S * scale) in place; one block (256 threads) per row of length L.  kV4 > 0: the row lives in registers
+// (L == 256 * 4 * kV4: one read, one write); kV4 == 0: generic three-pass version.
+template <int kV4>
 __global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
   __shared__ float red[8];
-  __shared__ float bc;
   float* row = S + (long long)blockIdx.x * L;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (kV4 > 0) {
+    float4 v[kV4 > 0 ? kV4 : 1];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kV4; ++i) {
+      v[i] = reinterpret_cast<const float4*>(row)[threadIdx.x + 256 * i];
+      m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+    m = block_reduce(m, true, red);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV4; ++i) {
+      v[i].x = __expf((v[i].x - m) * scale), v[i].y = __expf((v[i].y - m) * scale);
+      v[i].z = __expf((v[i].z - m) * scale), v[i].w = __expf((v[i].w - m) * scale);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float inv = 1.0f / block_reduce(s, false, red);
+#pragma unroll
+    for (int i = 0; i < kV4; ++i)
+      reinterpret_cast<float4*>(row)[threadIdx.x + 256 * i] = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+    return;
+  }
   float m = -INFINITY;
   for (int i = threadIdx.x; i < L; i += blockDim.x) m = fmaxf(m, row[i]);
-  m = warp_max(m);
-  if (lane == 0) red[warp] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = red[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]);
-    bc = t;
-  }
-  __syncthreads();
-  m = bc;
+  m = block_reduce(m, true, red);
   float s = 0.f;
   for (int i = threadIdx.x; i < L; i += blockDim.x) {
     const float e = __expf((row[i] - m) * scale);
     row[i] = e;
     s += e;
   }
-  s = warp_sum(s);
-  __syncthreads();
-  if (lane == 0) red[warp] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    bc = 1.0f / t;
-  }
-  __syncthreads();
-  const float inv = bc;
+  const float inv = 1.0f / block_reduce(s, false, red);
   for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] *= inv;
 }
 // dS = P * (dP - sum(P * dP)) * scale, written over dP
+template <int kV4>
 __global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, float scale) {
   __shared__ float red[8];
-  __shared__ float bc;
   const float* prow = P + (long long)blockIdx.x * L;
   float* drow = dP + (long long)blockIdx.x * L;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (kV4 > 0) {
+    float4 p[kV4 > 0 ? kV4 : 1], d[kV4 > 0 ? kV4 : 1];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kV4; ++i) {
+      p[i] = reinterpret_cast<const float4*>(prow)[threadIdx.x + 256 * i];
+      d[i] = reinterpret_cast<const float4*>(drow)[threadIdx.x + 256 * i];
+      s += (p[i].x * d[i].x + p[i].y * d[i].y) + (p[i].z * d[i].z + p[i].w * d[i].w);
+    }
+    const float dot = block_reduce(s, false, red);
+#pragma unroll
+    for (int i = 0; i < kV4; ++i)
+      reinterpret_cast<float4*>(drow)[threadIdx.x + 256 * i] =
+          make_float4(p[i].x * (d[i].x - dot) * scale, p[i].y * (d[i].y - dot) * scale, p[i].z * (d[i].z - dot) * scale,
+                      p[i].w * (d[i].w - dot) * scale);
+    return;
+  }
   float s = 0.f;
   for (int i = threadIdx.x; i < L; i += blockDim.x) s += prow[i] * drow[i];
-  s = warp_sum(s);
-  if (lane == 0) red[warp] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    bc = t;
-  }
-  __syncthreads();
-  const float dot = bc;
+  const float dot = block_reduce(s, false, red);
   for (int i = threadIdx.x; i < L; i += blockDim.x) drow[i] = prow[i] * (drow[i] - dot) * scale;
 }
 
@@ -260,14 +280,24 @@ __global__ void tr_va_rel_kernel(const float* q_xyz, const float* ref_xyz, const
     for (int k = 0; k < 3; ++k) rel[3 * e + k] = q_xyz[3 * i + k] - r[k];
   }
 }
-// h[e, :] = relu(W[:, 0:3] . rel[e] + b)      (fc_delta.0: Linear(3, D) + ReLU)   block = D threads? -> thread per (e, c)
+// h[e, :] = relu(W[:, 0:3] . rel[e] + b)      (fc_delta.0: Linear(3, D) + ReLU)
+// thread = 4 consecutive channels of one edge; blockDim.x = D / 4 lanes, blockDim.y edges per block
 __global__ void tr_lin3_relu_kernel(const float* rel, const float* W, const float* b, float* h, long long E, int D) {
-  const long long n = E * D;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const long long e = t / D;
-    const int c = (int)(t % D);
-    const float v = W[3 * c] * rel[3 * e] + W[3 * c + 1] * rel[3 * e + 1] + W[3 * c + 2] * rel[3 * e + 2] + b[c];
-    h[t] = fmaxf(v, 0.f);
+  const int c = threadIdx.x * 4;
+  float w[4][3], bb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    w[i][0] = W[3 * (c + i)], w[i][1] = W[3 * (c + i) + 1], w[i][2] = W[3 * (c + i) + 2];
+    bb[i] = b[c + i];
+  }
+  for (long long e = blockIdx.x * (long long)blockDim.y + threadIdx.y; e < E; e += (long long)gridDim.x * blockDim.y) {
+    const float r0 = rel[3 * e], r1 = rel[3 * e + 1], r2 = rel[3 * e + 2];
+    float4 o;
+    o.x = fmaxf(w[0][0] * r0 + w[0][1] * r1 + w[0][2] * r2 + bb[0], 0.f);
+    o.y = fmaxf(w[1][0] * r0 + w[1][1] * r1 + w[1][2] * r2 + bb[1], 0.f);
+    o.z = fmaxf(w[2][0] * r0 + w[2][1] * r1 + w[2][2] * r2 + bb[2], 0.f);
+    o.w = fmaxf(w[3][0] * r0 + w[3][1] * r1 + w[3][2] * r2 + bb[3], 0.f);
+    *reinterpret_cast<float4*>(h + e * D + c) = o;
   }
 }
 // backward of the above given dh (already masked by the ReLU):
@@ -301,23 +331,24 @@ __global__ void tr_lin3_dgrad_kernel(const float* dh, const float* W, float* dre
     if (lane == 0) drel[3 * e] = d0, drel[3 * e + 1] = d1, drel[3 * e + 2] = d2;
   }
 }
-// t[e, :] = q[i, :] - ktab[gidx[e], :] + pos[e, :]
+// t[e, :] = q[i, :] - ktab[gidx[e], :] + pos[e, :]        thread = 4 channels of one edge (blockDim.x = D / 4)
 __global__ void tr_va_gather_t_kernel(const float* q, const float* ktab, const int* gidx, const float* pos, float* t,
                                       long long E, int D) {
-  const long long n = E * D;
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
-    const long long e = x / D;
-    const int c = (int)(x % D);
-    t[x] = q[(e / TR_NBR) * D + c] - ktab[(long long)gidx[e] * D + c] + pos[x];
+  const int c = threadIdx.x * 4;
+  for (long long e = blockIdx.x * (long long)blockDim.y + threadIdx.y; e < E; e += (long long)gridDim.x * blockDim.y) {
+    const float4 qq = *reinterpret_cast<const float4*>(q + (e / TR_NBR) * D + c);
+    const float4 kk = *reinterpret_cast<const float4*>(ktab + (long long)gidx[e] * D + c);
+    const float4 pp = *reinterpret_cast<const float4*>(pos + e * D + c);
+    *reinterpret_cast<float4*>(t + e * D + c) = make_float4(qq.x - kk.x + pp.x, qq.y - kk.y + pp.y, qq.z - kk.z + pp.z, qq.w - kk.w + pp.w);
   }
 }
 // w = softmax_j(a * scale) per (query, channel), written over a ; res[i, c] = sum_j w * (vtab[gidx] + pos)
 __global__ void tr_va_softmax_agg_kernel(float* a, const float* vtab, const float* pos, const int* gidx, float scale,
-                                         float* res, long long NQ, int D) {
-  const long long n = NQ * D;
+                                         float* res, long long NQ, int D, int log2D) {
+  const long long n = NQ * D;       // flat (query, channel) index, D = 2^log2D
   for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
-    const long long i = x / D;
-    const int c = (int)(x % D);
+    const long long i = x >> log2D;
+    const int c = (int)(x & (D - 1));
     float v[TR_NBR];
     float m = -INFINITY;
 #pragma unroll
@@ -346,10 +377,9 @@ __global__ void tr_va_softmax_agg_kernel(float* a, const float* vtab, const floa
 // given dres: da (over w) = w * (dw - sum_j w dw) * scale with dw = dres * (v + pos) ; dvp = w * dres
 __global__ void tr_va_softmax_agg_bwd_kernel(const float* dres, float* w_da, const float* vtab, const float* pos,
                                              const int* gidx, float scale, float* dvp, long long NQ, int D) {
-  const long long n = NQ * D;
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
-    const long long i = x / D;
-    const int c = (int)(x % D);
+  const int c = threadIdx.x;        // blockDim.x == D
+  for (long long i = blockIdx.x; i < NQ; i += gridDim.x) {
+    const long long x = i * D + c;
     const float g = dres[x];
     float w[TR_NBR], dw[TR_NBR];
     float dot = 0.f;
@@ -371,10 +401,9 @@ __global__ void tr_va_softmax_agg_bwd_kernel(const float* dres, float* w_da, con
 // dq[i] += sum_j dt ; dktab[gidx] -= dt ; dvtab[gidx] += dvp ; dpos = dt + dvp (over dt)
 __global__ void tr_va_scatter_kernel(float* dt_dpos, const float* dvp, const int* gidx, float* dq, float* dktab,
                                      float* dvtab, long long NQ, int D) {
-  const long long n = NQ * D;
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
-    const long long i = x / D;
-    const int c = (int)(x % D);
+  const int c = threadIdx.x;        // blockDim.x == D
+  for (long long i = blockIdx.x; i < NQ; i += gridDim.x) {
+    const long long x = i * D + c;
     float acc = 0.f;
 #pragma unroll 4
     for (int j = 0; j < TR_NBR; ++j) {
@@ -425,8 +454,9 @@ __global__ void tr_lin_n3_kernel(const float* x, const float* W, const float* b,
   }
 }
 // dx[m, c] = sum_k dy[m, k] W[k, c] ; dW[k, c] += sum_m dy[m, k] x[m, c] ; db[k] += sum_m dy[m, k]
+// x_is_relu: x is a ReLU output and dx is wanted w.r.t. the ReLU's input (dx = 0 where x <= 0)
 __global__ void tr_lin_n3_bwd_kernel(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db,
-                                     long long M, int D) {
+                                     long long M, int D, int x_is_relu) {
   // thread = channel c (blockDim.x >= D handled by loop), block strides over row slabs
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     const float w0 = W[c], w1 = W[D + c], w2 = W[2 * D + c];
@@ -434,7 +464,7 @@ __global__ void tr_lin_n3_bwd_kernel(const float* dy, const float* x, const floa
     for (long long m = blockIdx.x; m < M; m += gridDim.x) {
       const float d0 = dy[3 * m], d1 = dy[3 * m + 1], d2 = dy[3 * m + 2];
       const float v = x[m * D + c];
-      dx[m * D + c] = d0 * w0 + d1 * w1 + d2 * w2;
+      dx[m * D + c] = (x_is_relu && !(v > 0.f)) ? 0.f : d0 * w0 + d1 * w1 + d2 * w2;
       g0 += d0 * v, g1 += d1 * v, g2 += d2 * v;
     }
     atomicAdd(dW + c, g0);
@@ -651,6 +681,78 @@ __global__ void tr_clip_scale_kernel(float* g, long long n, const float* sumsq, 
   const float coef = fminf(1.0f, max_norm / (sqrtf(sumsq[0]) + 1e-6f));
   if (coef >= 1.0f) return;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) g[i] *= coef;
+}
+
+// ------------------------------------------------------------------------------------------------ flat-buffer optimiser step
+// Parameters / gradients live in ONE flat buffer (segment s = elements [off[s], off[s] + len[s])): one launch each for
+// the per-tensor norms, the per-tensor clip (lib/utils/net_utils.py:122-132) and Adam (torch.optim.Adam semantics,
+// lib/utils/net_utils.py:57-63: L2 weight decay added to the gradient, bias-corrected moments).
+__global__ void tr_seg_sumsq_kernel(const float* g, const long long* off, const long long* len, float* sumsq) {
+  __shared__ float red[8];
+  const float* p = g + off[blockIdx.x];
+  const long long n = len[blockIdx.x];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += p[i] * p[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    sumsq[blockIdx.x] = t;
+  }
+}
+__global__ void tr_seg_clip_kernel(float* g, const long long* off, const long long* len, const float* sumsq, float max_norm) {
+  const float coef = fminf(1.0f, max_norm / (sqrtf(sumsq[blockIdx.x]) + 1e-6f));
+  if (coef >= 1.0f) return;
+  float* p = g + off[blockIdx.x];
+  const long long n = len[blockIdx.x];
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) p[i] *= coef;
+}
+__global__ void tr_adam_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                               float eps, float wd, float bc1, float bc2) {
+  const float step = lr / bc1, isq = rsqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] + wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi, v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) * isq + eps);
+  }
+}
+// 3-D terms of compute_loss on the last block (lib/models/POEM.py:398-412, release loss types): MSE on the 21 joints, L1
+// on the 778 vertices; writes d loss / d all_coords_preds (zero for the earlier blocks) and adds the loss to loss[0].
+__global__ void tr_coord_loss_kernel(const float* coords, const float* gt_joints, const float* gt_verts, int NB, int B,
+                                     int NJ, int NVt, float wj, float wv, float* loss, float* dcoords) {
+  __shared__ float red[8];
+  const int Q = NJ + NVt;
+  const long long per_block = (long long)B * Q * 3, total = per_block * NB;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float d = 0.f;
+    if (i >= per_block * (NB - 1)) {
+      const long long r = i - per_block * (NB - 1);
+      const int b = (int)(r / (Q * 3)), q = (int)((r / 3) % Q), k = (int)(r % 3);
+      if (q < NJ) {
+        const float e = coords[i] - gt_joints[((long long)b * NJ + q) * 3 + k];
+        acc += wj * e * e / (float)(B * NJ * 3);
+        d = wj * 2.f * e / (float)(B * NJ * 3);
+      } else {
+        const float e = coords[i] - gt_verts[((long long)b * NVt + (q - NJ)) * 3 + k];
+        acc += wv * fabsf(e) / (float)(B * NVt * 3);
+        d = wv * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) / (float)(B * NVt * 3);
+      }
+    }
+    dcoords[i] = d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(loss, t);
+  }
 }
 
 }  // namespace poem

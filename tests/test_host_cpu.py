@@ -437,3 +437,63 @@ def test_poly_exp2_constants_in_the_kernel_source():
     got = (p.astype(np.float32).view(np.int32) + (t.view(np.int32) << 23)).view(np.float32)
     ref = np.exp2(x.astype(np.float64))
     assert np.max(np.abs(got / ref - 1.0)) <= 8e-5
+
+
+# ------------------------------------------------------------------------------------------ training path: host logic
+def test_train_parameter_buckets_partition_the_flat_buffer():
+    """HeadTrainer keeps parameters / gradients as views of one flat buffer; the all-reduce buckets (head stage, one per
+    block) must tile it without gaps or overlap and every tensor must start 16-byte aligned (TMA operand)."""
+    from poem_v2_b200 import params, synth
+    from poem_v2_b200.config import release_dims
+    from poem_v2_b200.train import HeadTrainer
+    dims = release_dims("small")
+    tr = HeadTrainer(dims, synth.make_state_dict(dims, 0), synth.standin_template(), device="cpu")
+    spans = sorted(tr.buckets.values())
+    assert spans[0][0] == 0 and spans[-1][1] == tr.p_flat.numel()
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert set(tr.buckets) == {"head"} | {str(i) for i in range(dims.n_blocks)}
+    assert list(tr.p) == list(params.live_param_shapes(dims))
+    for k, v in tr.p.items():
+        assert v.data_ptr() % 16 == 0 and tr.g[k].data_ptr() % 16 == 0, k
+        assert v.shape == tr.g[k].shape
+    sd = synth.make_state_dict(dims, 0)
+    assert all(torch.equal(tr.p[k], sd[k].float()) for k in tr.p)
+    tr.g_flat.fill_(1.0)
+    tr.zero_grad()
+    assert float(tr.g_flat.abs().sum()) == 0.0
+
+
+def _bucket_allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    from poem_v2_b200.train import HeadTrainer, TrainStep
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dims = release_dims("small")
+    tr = HeadTrainer(dims, synth.make_state_dict(dims, 0), synth.standin_template(), device="cpu")
+    step = TrainStep(tr)
+    assert step.world == world
+    tr.g_flat.fill_(float(rank + 1))
+    for name in ("2", "1", "0", "head"):                 # the order the backward finishes them in
+        step._bucket_hook(name)
+    for h in step._pending:
+        h.wait()
+    q.put((rank, float(tr.g_flat.min()), float(tr.g_flat.max()), step.allreduce_bytes, tr.g_flat.numel() * 4))
+    dist.destroy_process_group()
+
+
+def test_train_gradient_buckets_average_over_ranks_gloo():
+    """world_size 2 on CPU (gloo): every gradient element ends up as the mean over ranks, each byte reduced once."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bucket_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p_ in procs:
+        p_.join(60)
+    for rank, lo, hi, reduced, total in res:
+        assert lo == hi == 1.5, (rank, lo, hi)
+        assert reduced == total
