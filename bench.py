@@ -9,6 +9,7 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -359,6 +360,54 @@ def image_sharded_pass(dev, rank, world, sync, max_over_ranks, V=8, steps=20):
             "finite": ok, "launch": "eager launches"}
 
 
+def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium", steps=5, warmup=2):
+    """SURVEY §8 f3 / BASELINE configs[3]: one optimisation step of the decoder head — zero_grad, forward with saved
+    activations, 3-D loss, hand-written backward, NCCL average of the gradient buckets (N > 1, overlapped with the
+    backward), per-tensor clip, Adam — at a FIXED global batch (strong scaling), every rank on gb / N samples.
+    POEM-medium (the MANO tail of medium_MANO has no backward yet).  Inputs resident on the device; CUDA-graph replay of
+    forward + loss + backward."""
+    from poem_v2_b200 import _train_native as tn
+    from poem_v2_b200.train import HeadTrainer, TrainStep
+    if gb % world:
+        return {"skipped": f"global batch {gb} does not divide over {world} GPUs"}
+    B = gb // world
+    dims = release_dims(size)
+    sd = synth.make_state_dict(dims, 0, "init")
+    tr = HeadTrainer(dims, sd, synth.standin_template(), device=dev)
+    step = TrainStep(tr, lr=1e-4, max_norm=1.0, graph=True)
+    feat, metas, ref_j = synth.make_inputs(dims, B, [V] * B, 100 + rank)
+    m = dict(metas)
+    m["cam_intr"], m["cam_extr"] = metas["cam_intr"].to(dev), metas["cam_extr"].to(dev)
+    feat, ref_j = feat.to(dev), ref_j.to(dev)
+    g = torch.Generator().manual_seed(7 + rank)
+    gt_j = (ref_j.cpu() + 0.002 * torch.randn(ref_j.shape, generator=g)).to(dev)
+    gt_v = (ref_j.cpu()[:, 9:10] + 0.05 * torch.randn(B, 778, 3, generator=g)).to(dev)
+    lib = tn.load()
+    losses = []
+    for _ in range(warmup):
+        losses.append(step(feat, m, ref_j, gt_j, gt_v))
+    sync()
+    l0 = lib.poem_tr_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses.append(step(feat, m, ref_j, gt_j, gt_v))
+    e1.record()
+    sync()
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    vals = [float(l_.item()) for l_ in losses]
+    return {"workload": f"training step of the decoder head, POEM-{size}, {V} views, GLOBAL batch {gb} (BASELINE configs[3] "
+                        f"without the MANO tail): forward + 3-D loss + backward + clip + Adam",
+            "samples_per_s": gb / ms * 1e3, "ms_per_step": ms, "steps": steps, "warmup": warmup, "global_batch": gb,
+            "batch_per_gpu": B, "views": V, "dtype": "tf32 tensor cores, fp32 storage",
+            "allreduce_bytes_per_step": int(step.allreduce_bytes), "collective": "NCCL all-reduce (AVG) of 4 gradient buckets"
+            if world > 1 else None, "kernels_per_step_in_graph_capture": None,
+            "kernel_launches_outside_graph_per_step": int((lib.poem_tr_kernel_launches() - l0) / steps),
+            "launch": "CUDA-graph replay (forward + loss + backward), eager clip + Adam", "loss_first": vals[0], "loss_last": vals[-1],
+            "finite": bool(all(math.isfinite(v) for v in vals)),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+
+
 def image_half_lines(dev, peaks, n_images=256):
     """SURVEY §8a row a17 / §8f row f1 as sub-lines of the bench: HRNet-W40 stage 4 and the whole backbone on
     `n_images` synthetic images resident in HBM, with the roofline of each (tensor-bound by FLOP count; the C <= 80
@@ -641,6 +690,8 @@ def main():
                                          "views": sweep}
             if world > 1:
                 named["image_sharded_b1_v8"] = image_sharded_pass(dev, rank, world, barrier, max_over_ranks)
+            torch.cuda.empty_cache()
+            named["train_medium_v8_gb32"] = train_step_pass(dev, rank, world, barrier, max_over_ranks)
             named["scaling"] = "strong"
             named["launch"] = "CUDA-graph replay of the captured forward, 2 input sets rotated, >= 0.3 s timed per entry"
         except Exception as e:  # noqa: BLE001

@@ -188,8 +188,47 @@ class POEM_Generalized_Head(_NativeDecoder):
         self.num_preds = dims.n_blocks            # read by the model shell (reference POEM.py:115)
         self.parametric_output = dims.parametric
 
-    @torch.no_grad()
+    # ---- training: autograd flows through the hand-written backward of poem_v2_b200/train.py ----
+    def train(self, mode=True):
+        """`head.train()` makes the live parameters trainable (the reference's are by default); `eval()` leaves them."""
+        super().train(mode)
+        if mode:
+            for p in self.parameters():
+                p.requires_grad_(True)
+        return self
+
+    def trainer(self):
+        """The HeadTrainer behind the training-mode forward.  On first use the module's parameters are re-homed into the
+        trainer's flat fp32 buffer (`param.data` becomes a view of it): optimisers, DDP and `state_dict()` keep working on
+        the same nn.Parameters, the kernels read the same memory, and the inference path re-packs when they change."""
+        dev = next(self.parameters()).device
+        tr = getattr(self, "_trainer", None)
+        if tr is None or tr.dev != dev:
+            from .train import HeadTrainer
+            if dev.type != "cuda":
+                raise nat.PoemError("training needs the module on a CUDA device: there is no CPU implementation")
+            if self._template is None:
+                self._template = _resolve_template(self.dims, None)
+            tr = HeadTrainer(self.dims, self.live_state(), self._template,
+                             assets=(self.bps_points, self.anchor_xyz, self.anchor_idx), device=dev)
+            named = dict(self.named_parameters())
+            for k in tr.p:
+                named[k[len(self._key_prefix):]].data = tr.p[k]
+            self._trainer = tr
+            self._trainer_params = [named[k[len(self._key_prefix):]] for k in tr.p]
+        return tr
+
     def forward(self, mlvl_feat, img_metas, reference_joints, **kwargs):
+        if self.training and torch.is_grad_enabled():
+            from .train import HeadFunction
+            _require_cuda(mlvl_feat, "mlvl_feat")
+            tr = self.trainer()
+            coords = HeadFunction.apply(tr, mlvl_feat, img_metas, reference_joints, *self._trainer_params)
+            return {"all_coords_preds": coords}
+        return self._forward_eval(mlvl_feat, img_metas, reference_joints, **kwargs)
+
+    @torch.no_grad()
+    def _forward_eval(self, mlvl_feat, img_metas, reference_joints, **kwargs):
         d = self.dims
         _require_cuda(mlvl_feat, "mlvl_feat")
         dev = mlvl_feat.device

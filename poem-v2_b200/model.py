@@ -61,7 +61,10 @@ class PtEmbedMultiviewStereoV2(nn.Module):
     def _forward_impl(self, batch, **kwargs):
         mode = kwargs.get("mode", "test")
         if mode == "train":
-            raise NotImplementedError("training branch (noisy GT reference joints, losses) is outside the built path")
+            raise NotImplementedError("training through this shell is not built: the image half (HRNet kernels) has no "
+                                      "backward.  Train with the head inside the reference's model — "
+                                      "POEM_Generalized_Head.train() routes autograd through the hand-written backward "
+                                      "(poem_v2_b200/train.py, INTEGRATION.md)")
         img = batch["image"]
         if not img.is_cuda:
             raise nat.PoemError("batch['image'] must be a CUDA tensor: there is no CPU implementation")
@@ -92,7 +95,8 @@ class PtEmbedMultiviewStereoV2(nn.Module):
 
     def forward(self, inputs, step_idx=0, mode="test", **kwargs):
         if mode == "train":
-            raise NotImplementedError("training_step is outside the built path (SURVEY §8f row f3)")
+            raise NotImplementedError("training_step of the whole model is not built (no backward for the image half); the "
+                                      "decoder head trains inside the reference's model, see INTEGRATION.md (SURVEY §8f row f3)")
         return self._forward_impl(inputs, mode=mode, **kwargs)
 
 

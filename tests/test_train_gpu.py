@@ -649,3 +649,47 @@ def test_train_step_eager_and_graph_agree_and_learn(tn):
     assert abs(losses["eager"][0] - losses["graph"][0]) <= 1e-5 * abs(losses["eager"][0])
     assert abs(losses["eager"][-1] - losses["graph"][-1]) <= 2e-3 * abs(losses["eager"][-1])
     assert losses["eager"][-1] < losses["eager"][0]
+
+
+def test_head_module_train_mode_autograd_bridge(tn):
+    """`POEM_Generalized_Head.train()`: torch autograd (a torch loss on top, an upstream tensor below, torch.optim on the
+    nn.Parameters) runs through the hand-written backward; eval() afterwards uses the updated weights."""
+    from poem_v2_b200.head import POEM_Generalized_Head
+    from poem_v2_b200.train import HeadTrainer
+    orc, synth, release_dims = _oracle_modules()
+    dims = release_dims("small")
+    sd = synth.make_state_dict(dims, 2, "init")
+    feat, metas, ref_j = synth.make_inputs(dims, 2, [1, 2], 6)
+    m = _cuda_metas(metas)
+    head = POEM_Generalized_Head(dims, template_mesh=synth.standin_template())
+    head.load_state_dict(sd, strict=True)
+    head = head.cuda().eval()
+    before = head(mlvl_feat=feat.cuda(), img_metas=dict(m), reference_joints=ref_j.cuda())["all_coords_preds"].clone()
+    head.train()
+    assert all(p.requires_grad for p in head.parameters())
+    x = feat.cuda().requires_grad_(True)
+    out = head(mlvl_feat=x, img_metas=dict(m), reference_joints=ref_j.cuda())["all_coords_preds"]
+    assert out.requires_grad and tuple(out.shape) == tuple(before.shape)
+    assert (out.detach() - before).norm(dim=-1).max().item() <= 1e-3 * before.norm(dim=-1).max().item()   # TF32 vs fp16 path
+    target = before + 0.003
+    loss = ((out - target) * 1e3).pow(2).mean()            # a torch loss on top of the custom function
+    opt = torch.optim.Adam(head.parameters(), lr=1e-4)
+    opt.zero_grad()
+    loss.backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and x.grad.abs().max().item() > 0
+    # same gradients as the trainer driven by hand
+    tr = HeadTrainer(dims, sd, synth.standin_template())
+    c2 = tr.forward(feat.cuda(), m, ref_j.cuda())
+    tr.backward(2e6 * (c2 - target) / c2.numel())
+    named = dict(head.named_parameters())
+    for k in ("input_proj.weight", "query_feat_embedding.weight", "transformer.pt_metro_encoder.1.encoder.attn.self.value.weight",
+              "transformer.pt_metro_encoder.2.encoder.vec_attn.reg_branch.2.weight"):
+        assert rel_l2(named[k].grad.cpu(), tr.g[k].cpu()) <= 1e-3, k
+    w0 = named["input_proj.weight"].detach().clone()
+    opt.step()
+    assert (named["input_proj.weight"].detach() - w0).abs().max().item() > 0
+    assert named["input_proj.weight"].data_ptr() == head.trainer().p["input_proj.weight"].data_ptr()   # still one storage
+    head.eval()
+    after = head(mlvl_feat=feat.cuda(), img_metas=dict(m), reference_joints=ref_j.cuda())["all_coords_preds"]
+    assert (after - before).abs().max().item() > 0          # the inference path re-packed the updated weights
+    assert torch.isfinite(after).all()
