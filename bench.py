@@ -367,6 +367,8 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
     POEM-medium (the MANO tail of medium_MANO has no backward yet).  Inputs resident on the device; CUDA-graph replay of
     forward + loss + backward."""
     from poem_v2_b200 import _train_native as tn
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
     from poem_v2_b200.train import HeadTrainer, TrainStep
     if gb % world:
         return {"skipped": f"global batch {gb} does not divide over {world} GPUs"}
@@ -506,6 +508,8 @@ def main():
                     help="skip BASELINE.json configs[3] / configs[4] (strong scaling at global batch 32 / 64)")
     ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S)
     ap.add_argument("--lean", action="store_true", help="only the main line (profiling runs)")
+    ap.add_argument("--train-only", action="store_true",
+                    help="only the training-step line (SURVEY §8 f3: global batch 32 over the job's GPUs, NCCL gradient all-reduce)")
     ap.add_argument("--torch-cuda-baseline", action="store_true", help=argparse.SUPPRESS)   # round-1 flags: now defaults
     ap.add_argument("--images-to-mesh", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -555,6 +559,27 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.train_only:
+        def _barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def _max_over_ranks(x):
+            if world == 1:
+                return x
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        r = train_step_pass(dev, rank, world, _barrier, _max_over_ranks)
+        if rank == 0:
+            tline = {"metric": "training samples/sec (decoder head step)", "value": r.get("samples_per_s"), "unit": "samples/s",
+                    "n_gpus": n_gpus, "higher_is_better": True, "scaling": "strong", "ms_per_step": r.get("ms_per_step"),
+                     "steps": r.get("steps"), "warmup": r.get("warmup"), "data": "synthetic", "train_medium_v8_gb32": r}
+            emit(tline)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     lib = nat.load()
     dims, head = make_head(size, dev)
 

@@ -582,7 +582,7 @@ class TrainStep:
         st["extr"].copy_(metas["cam_extr"])
         g.replay()
         self.coords = st["coords"]
-        return st["loss"]
+        return st["loss"].clone()              # the graph overwrites its loss buffer on the next replay
 
 
 class HeadFunction(torch.autograd.Function):

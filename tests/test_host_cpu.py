@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.poem_abi_version() == 2
 
 
+def test_train_library_exports_every_declared_symbol():
+    """include/poem_train.h <-> libpoem_train.so <-> the ctypes table (training-path primitives)."""
+    from poem_v2_b200 import _train_native as tnat
+    tnat.build()
+    header = open(os.path.join(ROOT, "include", "poem_train.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(poem_tr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(tnat.EXPORTS), declared ^ set(tnat.EXPORTS)
+    lib = tnat.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.poem_tr_abi_version() == 1
+    # argument counts of the ctypes table against the C declarations (the stream is the last parameter of every primitive)
+    for name, args in tnat.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+        assert m, name
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(args), name
+
+
 def test_workspace_query_and_dim_validation_need_no_gpu():
     import ctypes as C
     lib = nat.load()
