@@ -35,18 +35,23 @@ long long poem_tr_kernel_launches(void);
  *   bias: NULL, [N] (bias_on_m == 0) or [M] (bias_on_m == 1).  accumulate != 0: C += instead of C =.
  *   relu != 0: C = max(., 0) after the bias (plain stores only).  relu_mask != NULL ([M x N], pitch ld_mask): C = 0 where
  *   relu_mask <= 0 — the dgrad GEMM that feeds a ReLU's backward writes the masked gradient directly.
+ *   round_ops: bit 0 / bit 1 = round operand A / B to TF32 (nearest) before the tensor core reads it (forward GEMMs: the
+ *   1e-3 bound needs it); 0 = the tensor core truncates the fp32 operands (gradient GEMMs).
+ *   round_out != 0: C is stored rounded to TF32 — for tensors that are only ever GEMM operands again (their consumer then
+ *   passes round_ops without that operand's bit and skips the shared-memory pass).
  *   pitches must be multiples of 4 elements and bases 16-byte aligned (TMA).  This one primitive is the forward, dgrad and
  *   wgrad of every nn.Linear / 1x1 conv of the path and the five GEMMs of the attention core and its backward. */
 int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a_s1, long long a_s2, const float* B, int b_mn,
                  long long ldb, long long b_s1, long long b_s2, float* C, long long ldc, long long c_s1, long long c_s2,
                  int M, int N, int K, int nb1, int nb2, float alpha, const float* bias, int bias_on_m, int accumulate,
-                 int relu, const float* relu_mask, long long ld_mask, void* stream);
+                 int relu, const float* relu_mask, long long ld_mask, int round_ops, int round_out, void* stream);
 
 /* elementwise */
 int poem_tr_relu(float* y, long long n, void* stream);
 int poem_tr_relu_bwd(float* dy, const float* y, long long n, void* stream);          /* dy *= (y > 0) */
 int poem_tr_gelu(const float* x, float* y, long long n, void* stream);               /* exact erf GELU */
 int poem_tr_gelu_bwd(float* dy, const float* x, long long n, void* stream);
+int poem_tr_round_tf32(const float* x, float* y, long long n, void* stream);        /* y = x rounded to TF32 (nearest) */
 int poem_tr_axpy(float* y, const float* x, float a, long long n, void* stream);      /* y += a x */
 int poem_tr_affine_rows(const float* x, const float* off, float a, float* out, long long rows, int rows_per_group,
                         int n_groups, int cols, void* stream);                       /* out = a x + off[group] */

@@ -15,11 +15,12 @@ HEADERS = ["common.cuh", "tgemm.cuh", "train_simt.cuh"]
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 SIGNATURES = {
-    "poem_tr_gemm": [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _L, _P],
+    "poem_tr_gemm": [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _L, _I, _I, _P],
     "poem_tr_relu": [_P, _L, _P],
     "poem_tr_relu_bwd": [_P, _P, _L, _P],
     "poem_tr_gelu": [_P, _P, _L, _P],
     "poem_tr_gelu_bwd": [_P, _P, _L, _P],
+    "poem_tr_round_tf32": [_P, _P, _L, _P],
     "poem_tr_axpy": [_P, _P, _F, _L, _P],
     "poem_tr_affine_rows": [_P, _P, _F, _P, _L, _I, _I, _I, _P],
     "poem_tr_colsum": [_P, _L, _L, _I, _P, _P],
@@ -144,12 +145,12 @@ def call(name, *args, label=None):
 
 def gemm(A, B, Cout, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, batch=(1, 1),
          a_strides=(0, 0), b_strides=(0, 0), c_strides=(0, 0), alpha=1.0, bias=None, bias_on_m=False, accumulate=False,
-         relu=False, relu_mask=None):
+         relu=False, relu_mask=None, round_ops=3, round_out=False):
     """C (+)= alpha * op(A) op(B)^T (+ bias), see include/poem_train.h.  Default pitches: dense row-major operands."""
     lda = lda if lda is not None else (M if a_mn else K)
     ldb = ldb if ldb is not None else (N if b_mn else K)
     ldc = ldc if ldc is not None else N
     call("poem_tr_gemm", A, int(a_mn), lda, a_strides[0], a_strides[1], B, int(b_mn), ldb, b_strides[0], b_strides[1],
          Cout, ldc, c_strides[0], c_strides[1], M, N, K, batch[0], batch[1], float(alpha), bias, int(bias_on_m),
-         int(accumulate), int(relu), relu_mask, (relu_mask.shape[-1] if relu_mask is not None else 0),
+         int(accumulate), int(relu), relu_mask, (relu_mask.shape[-1] if relu_mask is not None else 0), int(round_ops), int(round_out),
          label=None if _prof is None else f"gemm {'T' if a_mn else 'N'}{'T' if b_mn else 'N'} {M}x{N}x{K} b{batch[0] * batch[1]}")

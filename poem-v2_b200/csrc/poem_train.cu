@@ -130,7 +130,7 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
                             int b_mn, long long ldb, long long b_s1, long long b_s2, float* C, long long ldc,
                             long long c_s1, long long c_s2, int M, int N, int K, int nb1, int nb2, float alpha,
                             const float* bias, int bias_on_m, int accumulate, int relu, const float* relu_mask, long long ld_mask,
-                            void* stream) {
+                            int round_ops, int round_out, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || nb1 < 1 || nb2 < 1) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: bad arguments");
   const int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
@@ -153,11 +153,13 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
     if (splits > kblocks / 8) splits = kblocks / 8;
     if (splits < 1) splits = 1;
   }
+  if (round_out || relu || relu_mask) splits = 1;   // these epilogues need the complete sum in one CTA
   const int kb_per_split = (kblocks + splits - 1) / splits;
   splits = (kblocks + kb_per_split - 1) / kb_per_split;
   p.splits = splits, p.k_per_split = kb_per_split * TG_BK;
   p.mode = (splits > 1 || batch_sum) ? TG_ATOMIC : (accumulate ? TG_ADD : TG_STORE);
-  p.relu_mask = relu_mask, p.ld_mask = ld_mask;
+  p.relu_mask = relu_mask, p.ld_mask = ld_mask, p.round_ops = round_ops & 3, p.round_out = round_out;
+  if (round_out && p.mode != TG_STORE) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: round_out needs a plain store");
   if (relu_mask && (nb1 * nb2 != 1 || p.mode != TG_STORE)) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: relu_mask needs an unbatched plain store");
   if (relu && p.mode != TG_STORE) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: relu needs a plain store (no split / accumulate)");
   if (p.mode == TG_ATOMIC && !accumulate) {      // atomic partial sums need a zeroed destination
@@ -168,7 +170,7 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
         if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "poem_tr_gemm memset: %s", cudaGetErrorString(e));
       }
   }
-  dim3 grid((M + TG_BM - 1) / TG_BM, (N + BN - 1) / BN, nb1 * nb2 * splits);
+  dim3 grid((N + BN - 1) / BN, (M + TG_BM - 1) / TG_BM, nb1 * nb2 * splits);
   if (grid.y > 65535u || grid.z > 65535u) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: grid too large (%u, %u)", grid.y, grid.z);
   switch (BN) {
     case 32: return launch_tgemm_major<32>(a_mn, b_mn, ta, tb, p, grid, st);
@@ -458,5 +460,11 @@ extern "C" int poem_tr_coord_loss(const float* coords, const float* gt_joints, c
   tr_coord_loss_kernel<<<grid_for((long long)n_blocks * B * (n_joints + n_verts) * 3), 256, 0, ST>>>(
       coords, gt_joints, gt_verts, n_blocks, B, n_joints, n_verts, w_joints, w_verts, loss, dcoords);
   TR_CHECK("coord_loss");
+  return 0;
+}
+
+extern "C" int poem_tr_round_tf32(const float* x, float* y, long long n, void* stream) {
+  tr_round_tf32_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, n);
+  TR_CHECK("round_tf32");
   return 0;
 }

@@ -15,6 +15,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// round to TF32 (nearest, ties away): producers of tensors that are only ever GEMM operands store them rounded, so the GEMM
+// can skip its shared-memory rounding pass for that operand (include/poem_train.h: round_ops / round_out)
+__device__ __forceinline__ float tf32r(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return __uint_as_float(y);
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -42,6 +49,15 @@ __global__ void tr_gelu_bwd_kernel(float* dy, const float* x, long long n) {   /
     const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * v * v);
     dy[i] *= cdf + v * pdf;
+  }
+}
+// y = x rounded to TF32 (nearest, ties away): the weights' operand copy, refreshed once per step, so that the GEMMs need
+// to round only their activation operand in shared memory
+__global__ void tr_round_tf32_kernel(const float* x, float* y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x[i]));
+    y[i] = __uint_as_float(r);
   }
 }
 __global__ void tr_axpy_kernel(float* y, const float* x, float a, long long n) {   // y += a * x
@@ -215,7 +231,7 @@ __global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
     const float inv = 1.0f / block_reduce(s, false, red);
 #pragma unroll
     for (int i = 0; i < kV4; ++i)
-      reinterpret_cast<float4*>(row)[threadIdx.x + 256 * i] = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+      reinterpret_cast<float4*>(row)[threadIdx.x + 256 * i] = make_float4(tf32r(v[i].x * inv), tf32r(v[i].y * inv), tf32r(v[i].z * inv), tf32r(v[i].w * inv));
     return;
   }
   float m = -INFINITY;
@@ -228,7 +244,7 @@ __global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
     s += e;
   }
   const float inv = 1.0f / block_reduce(s, false, red);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] *= inv;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] = tf32r(row[i] * inv);
 }
 // dS = P * (dP - sum(P * dP)) * scale, written over dP
 template <int kV4>
@@ -249,14 +265,14 @@ __global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, flo
 #pragma unroll
     for (int i = 0; i < kV4; ++i)
       reinterpret_cast<float4*>(drow)[threadIdx.x + 256 * i] =
-          make_float4(p[i].x * (d[i].x - dot) * scale, p[i].y * (d[i].y - dot) * scale, p[i].z * (d[i].z - dot) * scale,
-                      p[i].w * (d[i].w - dot) * scale);
+          make_float4(tf32r(p[i].x * (d[i].x - dot) * scale), tf32r(p[i].y * (d[i].y - dot) * scale),
+                      tf32r(p[i].z * (d[i].z - dot) * scale), tf32r(p[i].w * (d[i].w - dot) * scale));
     return;
   }
   float s = 0.f;
   for (int i = threadIdx.x; i < L; i += blockDim.x) s += prow[i] * drow[i];
   const float dot = block_reduce(s, false, red);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) drow[i] = prow[i] * (drow[i] - dot) * scale;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) drow[i] = tf32r(prow[i] * (drow[i] - dot) * scale);
 }
 
 // ------------------------------------------------------------------------------------------------ vector attention: edges
@@ -293,10 +309,10 @@ __global__ void tr_lin3_relu_kernel(const float* rel, const float* W, const floa
   for (long long e = blockIdx.x * (long long)blockDim.y + threadIdx.y; e < E; e += (long long)gridDim.x * blockDim.y) {
     const float r0 = rel[3 * e], r1 = rel[3 * e + 1], r2 = rel[3 * e + 2];
     float4 o;
-    o.x = fmaxf(w[0][0] * r0 + w[0][1] * r1 + w[0][2] * r2 + bb[0], 0.f);
-    o.y = fmaxf(w[1][0] * r0 + w[1][1] * r1 + w[1][2] * r2 + bb[1], 0.f);
-    o.z = fmaxf(w[2][0] * r0 + w[2][1] * r1 + w[2][2] * r2 + bb[2], 0.f);
-    o.w = fmaxf(w[3][0] * r0 + w[3][1] * r1 + w[3][2] * r2 + bb[3], 0.f);
+    o.x = tf32r(fmaxf(w[0][0] * r0 + w[0][1] * r1 + w[0][2] * r2 + bb[0], 0.f));
+    o.y = tf32r(fmaxf(w[1][0] * r0 + w[1][1] * r1 + w[1][2] * r2 + bb[1], 0.f));
+    o.z = tf32r(fmaxf(w[2][0] * r0 + w[2][1] * r1 + w[2][2] * r2 + bb[2], 0.f));
+    o.w = tf32r(fmaxf(w[3][0] * r0 + w[3][1] * r1 + w[3][2] * r2 + bb[3], 0.f));
     *reinterpret_cast<float4*>(h + e * D + c) = o;
   }
 }
@@ -339,7 +355,7 @@ __global__ void tr_va_gather_t_kernel(const float* q, const float* ktab, const i
     const float4 qq = *reinterpret_cast<const float4*>(q + (e / TR_NBR) * D + c);
     const float4 kk = *reinterpret_cast<const float4*>(ktab + (long long)gidx[e] * D + c);
     const float4 pp = *reinterpret_cast<const float4*>(pos + e * D + c);
-    *reinterpret_cast<float4*>(t + e * D + c) = make_float4(qq.x - kk.x + pp.x, qq.y - kk.y + pp.y, qq.z - kk.z + pp.z, qq.w - kk.w + pp.w);
+    *reinterpret_cast<float4*>(t + e * D + c) = make_float4(tf32r(qq.x - kk.x + pp.x), tf32r(qq.y - kk.y + pp.y), tf32r(qq.z - kk.z + pp.z), tf32r(qq.w - kk.w + pp.w));
   }
 }
 // w = softmax_j(a * scale) per (query, channel), written over a ; res[i, c] = sum_j w * (vtab[gidx] + pos)
@@ -393,7 +409,7 @@ __global__ void tr_va_softmax_agg_bwd_kernel(const float* dres, float* w_da, con
 #pragma unroll
     for (int j = 0; j < TR_NBR; ++j) {
       const long long e = i * TR_NBR + j;
-      w_da[e * D + c] = w[j] * (dw[j] - dot) * scale;
+      w_da[e * D + c] = tf32r(w[j] * (dw[j] - dot) * scale);
       dvp[e * D + c] = w[j] * g;
     }
   }
@@ -414,7 +430,7 @@ __global__ void tr_va_scatter_kernel(float* dt_dpos, const float* dvp, const int
       const long long r = (long long)gidx[e] * D + c;
       atomicAdd(dktab + r, -d);
       atomicAdd(dvtab + r, p);
-      dt_dpos[e * D + c] = d + p;
+      dt_dpos[e * D + c] = tf32r(d + p);
     }
     dq[x] += acc;
   }

@@ -29,6 +29,12 @@ from .config import HeadDims
 from .pack import sine_pos_3d
 
 NBR = 32
+# operand rounding of the gradient GEMMs (poem_tr_gemm round_ops).  3 (default): both operands rounded to nearest, like
+# the forward GEMMs (those always round: the 1e-3 bound on the coordinates needs it).  POEM_TR_GRAD_ROUND=0 lets the
+# tensor core truncate the gradient GEMMs' operands (a 2^-11 relative shrink of every product term) and drops their
+# shared-memory rounding pass: backward 82.8 -> 73.5 ms at batch 32, gradient error vs the oracle 3e-3 -> 4.9e-3 median,
+# 2.6e-2 -> 5.4e-2 on the conv biases.
+GRAD_ROUND = int(__import__("os").environ.get("POEM_TR_GRAD_ROUND", "3"))
 
 
 class HeadTrainer:
@@ -57,11 +63,13 @@ class HeadTrainer:
             total += (int(np.prod(shp)) + 3) // 4 * 4
         self.p_flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.g_flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self.p, self.g = {}, {}
+        self.pr_flat = torch.zeros(total, dtype=torch.float32, device=self.dev)   # TF32-rounded operand copy of the weights
+        self.p, self.g, self.pr = {}, {}, {}
         for k, shp in live.items():
             n = int(np.prod(shp))
             self.p[k] = self.p_flat[offs[k]:offs[k] + n].view(*shp)
             self.g[k] = self.g_flat[offs[k]:offs[k] + n].view(*shp)
+            self.pr[k] = self.pr_flat[offs[k]:offs[k] + n].view(*shp)
             self.p[k].copy_(state_dict[k].detach().to(self.dev, torch.float32).reshape(shp))
         keys = list(live)
         self.seg_off = torch.tensor([offs[k] for k in keys], dtype=torch.int64, device=self.dev)
@@ -91,27 +99,33 @@ class HeadTrainer:
     def zero_grad(self):
         self.g_flat.zero_()
 
-    def lin(self, x, w, b=None, out=None, acc=False, relu=False):
-        """y (+)= x W^T + b   (relu: y = max(., 0) in the GEMM epilogue)"""
+    def lin(self, x, w, b=None, out=None, acc=False, relu=False, x_clean=False, round_out=False):
+        """y (+)= x W^T + b   (relu: y = max(., 0) in the GEMM epilogue).  x_clean: x was stored TF32-rounded by its
+        producer (no rounding pass for it); round_out: y is only ever a GEMM operand again, store it rounded."""
         M, K = x.shape
-        W = self.p[w]
+        W = self.pr[w]                                # pre-rounded copy of the weight
         N = W.shape[0]
         y = out if out is not None else self.new(M, N)
-        tn.gemm(x, W, y, M, N, K, bias=self.p[b] if b else None, accumulate=acc, relu=relu)
+        tn.gemm(x, W, y, M, N, K, bias=self.p[b] if b else None, accumulate=acc, relu=relu, round_ops=0 if x_clean else 1,
+                round_out=round_out)
         return y
 
-    def lin_bwd(self, dy, x, w, b=None, need_dx=True, out=None, acc=False, relu_in=False):
+    def lin_bwd(self, dy, x, w, b=None, need_dx=True, out=None, acc=False, relu_in=False, dy_clean=False, x_clean=False,
+                round_out=False):
         """g[w] += dy^T x ; g[b] += colsum(dy) ; returns dx (+)= dy W.  relu_in: x is a ReLU output and the gradient
-        w.r.t. the ReLU's input is wanted (dx = 0 where x <= 0, applied in the GEMM epilogue)."""
+        w.r.t. the ReLU's input is wanted (dx = 0 where x <= 0, applied in the GEMM epilogue).  dy_clean / x_clean /
+        round_out as in `lin`."""
         M, N = dy.shape
         K = x.shape[1]
         if b:
             tn.call("poem_tr_colsum", dy, N, M, N, self.g[b])
-        tn.gemm(dy, x, self.g[w], N, K, M, a_mn=True, b_mn=True, accumulate=True)
+        ra, rb = (0 if dy_clean else 1), (0 if x_clean else 2)
+        tn.gemm(dy, x, self.g[w], N, K, M, a_mn=True, b_mn=True, accumulate=True, round_ops=GRAD_ROUND & (ra | rb))
         if not need_dx:
             return None
         dx = out if out is not None else self.new(M, K)
-        tn.gemm(dy, self.p[w], dx, M, K, N, b_mn=True, accumulate=acc, relu_mask=x if relu_in else None)
+        tn.gemm(dy, self.pr[w], dx, M, K, N, b_mn=True, accumulate=acc, relu_mask=x if relu_in else None,
+                round_ops=GRAD_ROUND & ra, round_out=round_out)
         return dx
 
     def relu_(self, y):
@@ -144,15 +158,17 @@ class HeadTrainer:
         D, H = hid.shape[1], self.dims.n_heads
         hd = D // H
         kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
-        Q = self.lin(hid, pre + ".self.query.weight", pre + ".self.query.bias")
-        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias")
-        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias")
+        # Q, K, V, P, ctx are only ever GEMM operands: stored TF32-rounded by their producers, no rounding pass downstream
+        Q = self.lin(hid, pre + ".self.query.weight", pre + ".self.query.bias", round_out=True)
+        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias", round_out=True)
+        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias", round_out=True)
         P = self.new(B, H, Lq, Lk)
-        tn.gemm(Q, K, P, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, **kw)
+        tn.gemm(Q, K, P, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, round_ops=0, **kw)
         tn.call("poem_tr_softmax_rows", P, B * H * Lq, Lk, 1.0 / math.sqrt(hd))
         ctx = self.new(B * Lq, D)
-        tn.gemm(P, V, ctx, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq, **kw)
-        o = self.lin(ctx, pre + ".output.dense.weight", pre + ".output.dense.bias")
+        tn.gemm(P, V, ctx, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq, round_ops=0,
+                round_out=True, **kw)
+        o = self.lin(ctx, pre + ".output.dense.weight", pre + ".output.dense.bias", x_clean=True)
         y, xhat, rstd = self.ln(o, hid, pre + ".output.LayerNorm")
         return y, dict(hid=hid, enc=enc, Q=Q, K=K, V=V, P=P, ctx=ctx, xhat=xhat, rstd=rstd, B=B, Lq=Lq, Lk=Lk)
 
@@ -163,21 +179,26 @@ class HeadTrainer:
         hd = D // H
         kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
         ds = self.ln_bwd(dy, t["xhat"], t["rstd"], pre + ".output.LayerNorm")        # grad of (o + hid)
-        dctx = self.lin_bwd(ds, t["ctx"], pre + ".output.dense.weight", pre + ".output.dense.bias")
+        dctx = self.lin_bwd(ds, t["ctx"], pre + ".output.dense.weight", pre + ".output.dense.bias", x_clean=True, round_out=True)
         P = t["P"]
+        # every operand below was stored rounded by its producer (P, dS by the softmax kernels; Q, K, V, dctx, dQ, dK, dV by
+        # GEMM epilogues): no rounding pass in these GEMMs
         dV = self.new(B * Lk, D)
-        tn.gemm(P, dctx, dV, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk, **kw)
+        tn.gemm(P, dctx, dV, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk,
+                round_ops=0, round_out=True, **kw)
         dP = self.new(B, H, Lq, Lk)
-        tn.gemm(dctx, t["V"], dP, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, **kw)
+        tn.gemm(dctx, t["V"], dP, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, round_ops=0, **kw)
         tn.call("poem_tr_softmax_rows_bwd", P, dP, B * H * Lq, Lk, 1.0 / math.sqrt(hd))          # dP now holds dS
         dQ = self.new(B * Lq, D)
-        tn.gemm(dP, t["K"], dQ, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq, **kw)
+        tn.gemm(dP, t["K"], dQ, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq,
+                round_ops=0, round_out=True, **kw)
         dK = self.new(B * Lk, D)
-        tn.gemm(dP, t["Q"], dK, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk, **kw)
+        tn.gemm(dP, t["Q"], dK, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk,
+                round_ops=0, round_out=True, **kw)
         del dP
-        self.lin_bwd(dQ, t["hid"], pre + ".self.query.weight", pre + ".self.query.bias", out=ds, acc=True)   # ds -> d hid
-        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True)
-        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True)
+        self.lin_bwd(dQ, t["hid"], pre + ".self.query.weight", pre + ".self.query.bias", out=ds, acc=True, dy_clean=True)   # ds -> d hid
+        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True, dy_clean=True)
+        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True, dy_clean=True)
         return ds
 
     # ------------------------------------------------------------------------------------------ vector attention core
@@ -185,11 +206,12 @@ class HeadTrainer:
         E, D = rel.shape[0], q.shape[1]
         hd = self.new(E, D)
         tn.call("poem_tr_lin3_relu", rel, self.p[pre + "fc_delta.0.weight"], self.p[pre + "fc_delta.0.bias"], hd, E, D)
-        pos = self.lin(hd, pre + "fc_delta.2.weight", pre + "fc_delta.2.bias")
+        # hd, t, hg (and da, dhg, dpos in the backward) are only ever GEMM operands: their producers store them TF32-rounded
+        pos = self.lin(hd, pre + "fc_delta.2.weight", pre + "fc_delta.2.bias", x_clean=True)
         t = self.new(E, D)
         tn.call("poem_tr_va_gather_t", q, ktab, gidx, pos, t, E, D)
-        hg = self.lin(t, pre + "fc_gamma.0.weight", pre + "fc_gamma.0.bias", relu=True)
-        w = self.lin(hg, pre + "fc_gamma.2.weight", pre + "fc_gamma.2.bias")
+        hg = self.lin(t, pre + "fc_gamma.0.weight", pre + "fc_gamma.0.bias", relu=True, x_clean=True, round_out=True)
+        w = self.lin(hg, pre + "fc_gamma.2.weight", pre + "fc_gamma.2.bias", x_clean=True)
         res = self.new(q.shape[0], D)
         tn.call("poem_tr_va_softmax_agg", w, vtab, pos, gidx, 1.0 / math.sqrt(D), res, q.shape[0], D)   # w <- softmax weights
         return res, dict(q=q, ktab=ktab, vtab=vtab, gidx=gidx, rel=rel, hd=hd, pos=pos, t=t, hg=hg, w=w)
@@ -202,12 +224,13 @@ class HeadTrainer:
         dvp = self.new(E, D)
         da = c["w"]                                                       # overwritten: the tape entry is dead afterwards
         tn.call("poem_tr_va_softmax_agg_bwd", dres, da, c["vtab"], c["pos"], gidx, 1.0 / math.sqrt(D), dvp, NQ, D)
-        dhg = self.lin_bwd(da, c["hg"], pre + "fc_gamma.2.weight", pre + "fc_gamma.2.bias", relu_in=True)
-        dt = self.lin_bwd(dhg, c["t"], pre + "fc_gamma.0.weight", pre + "fc_gamma.0.bias")
+        dhg = self.lin_bwd(da, c["hg"], pre + "fc_gamma.2.weight", pre + "fc_gamma.2.bias", relu_in=True, dy_clean=True,
+                           x_clean=True, round_out=True)
+        dt = self.lin_bwd(dhg, c["t"], pre + "fc_gamma.0.weight", pre + "fc_gamma.0.bias", dy_clean=True, x_clean=True)
         del dhg
         tn.call("poem_tr_va_scatter", dt, dvp, gidx, dq, dktab, dvtab, NQ, D)           # dt <- dpos
         del dvp
-        dhd = self.lin_bwd(dt, c["hd"], pre + "fc_delta.2.weight", pre + "fc_delta.2.bias", relu_in=True)
+        dhd = self.lin_bwd(dt, c["hd"], pre + "fc_delta.2.weight", pre + "fc_delta.2.bias", relu_in=True, dy_clean=True, x_clean=True)
         drel = self.new(E, 3) if dxyz_q is not None else None
         tn.call("poem_tr_lin3_bwd", dhd, c["rel"], self.p[pre + "fc_delta.0.weight"], self.g[pre + "fc_delta.0.weight"],
                 self.g[pre + "fc_delta.0.bias"], drel, E, D)
@@ -335,8 +358,8 @@ class HeadTrainer:
         HW = hw * hw
         NV, B = int(feat.shape[0]), len(views)
         planes = self.new(NV, D, HW)
-        tn.gemm(self.p["input_proj.weight"], feat, planes, D, HW, C, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1),
-                b_strides=(C * HW, 0), c_strides=(D * HW, 0), bias=self.p["input_proj.bias"], bias_on_m=True)
+        tn.gemm(self.pr["input_proj.weight"], feat, planes, D, HW, C, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1),
+                b_strides=(C * HW, 0), c_strides=(D * HW, 0), bias=self.p["input_proj.bias"], bias_on_m=True, round_ops=2)
         F3 = 3 * d.pos_feats
         key = tuple(int(n) for n in views)
         if key not in self._const:                  # constants of the graph for this view layout (host -> device once)
@@ -348,7 +371,7 @@ class HeadTrainer:
                 nv=torch.tensor(np.asarray(views), dtype=torch.int32, device=self.dev))
         cst = self._const[key]
         sine, img_sample, row0, nv = cst["sine"], cst["img_sample"], cst["row0"], cst["nv"]
-        tn.gemm(self.p["adapt_pos3d.weight"], sine, planes, D, HW, F3, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1),
+        tn.gemm(self.pr["adapt_pos3d.weight"], sine, planes, D, HW, F3, b_mn=True, ldb=HW, ldc=HW, batch=(NV, 1),
                 b_strides=(F3 * HW, 0), c_strides=(D * HW, 0), bias=self.p["adapt_pos3d.bias"], bias_on_m=True, accumulate=True)
         grid = self.new(NV, P, 2)
         tn.call("poem_tr_project", self.bps, centre, intr, extr, img_sample, NV, P, float(inp_w), float(inp_h), grid)
@@ -386,12 +409,12 @@ class HeadTrainer:
         for b in ("input_proj.bias", "adapt_pos3d.bias"):
             tn.call("poem_tr_rowsum_groups", dplanes, NV * D, HW, D, self.g[b])
         tn.gemm(dplanes, t["feat"], self.g["input_proj.weight"], D, C, HW, lda=HW, ldb=HW, ldc=C, batch=(NV, 1),
-                a_strides=(D * HW, 0), b_strides=(C * HW, 0), c_strides=(0, 0), accumulate=True)
+                a_strides=(D * HW, 0), b_strides=(C * HW, 0), c_strides=(0, 0), accumulate=True, round_ops=GRAD_ROUND)
         tn.gemm(dplanes, t["sine"], self.g["adapt_pos3d.weight"], D, F3, HW, lda=HW, ldb=HW, ldc=F3, batch=(NV, 1),
-                a_strides=(D * HW, 0), b_strides=(F3 * HW, 0), c_strides=(0, 0), accumulate=True)
+                a_strides=(D * HW, 0), b_strides=(F3 * HW, 0), c_strides=(0, 0), accumulate=True, round_ops=GRAD_ROUND)
         dfeat = self.new(NV, C, hw, hw)
-        tn.gemm(self.p["input_proj.weight"], dplanes, dfeat, C, HW, D, a_mn=True, b_mn=True, lda=C, ldb=HW, ldc=HW,
-                batch=(NV, 1), b_strides=(D * HW, 0), c_strides=(C * HW, 0))
+        tn.gemm(self.pr["input_proj.weight"], dplanes, dfeat, C, HW, D, a_mn=True, b_mn=True, lda=C, ldb=HW, ldc=HW,
+                batch=(NV, 1), b_strides=(D * HW, 0), c_strides=(C * HW, 0), round_ops=GRAD_ROUND)
         return dfeat
 
     # ------------------------------------------------------------------------------------------ whole head
@@ -399,6 +422,7 @@ class HeadTrainer:
         """all_coords_preds (NB, B, 799, 3) in metres; keeps the activations for `backward`.
         `neighbours` (NB-1, 2, B, 799, 32): test hook, use these 32-NN sets instead of searching."""
         d = self.dims
+        tn.call("poem_tr_round_tf32", self.p_flat, self.pr_flat, self.p_flat.numel())      # this step's operand copy of the weights
         views = [int(v) for v in np.asarray(img_metas["cam_view_num"]).reshape(-1)]
         B = len(views)
         Q, P, D = d.n_query, d.n_sample, d.embed_dims

@@ -224,10 +224,10 @@ def test_elementwise_layernorm_softmax(tn):
     P.backward(dP)
     Sd = dev(S.detach().float())
     tn.call("poem_tr_softmax_rows", Sd, 77, 4096, 0.125)
-    close(Sd, P.detach(), 1e-5)
+    close(Sd, P.detach(), 5e-4)                     # P and dS are stored TF32-rounded (they are only ever GEMM operands)
     dPd = dev(dP.float())
     tn.call("poem_tr_softmax_rows_bwd", Sd, dPd, 77, 4096, 0.125)
-    close(dPd, S.grad, 1e-4)
+    close(dPd, S.grad, 1e-3)
     # column sums / batch sums / axpy
     out = torch.ones(256).cuda()
     tn.call("poem_tr_colsum", dev(x.detach().float()[:, :256].contiguous()), 256, 333, 256, out)
@@ -271,33 +271,33 @@ def test_vector_attention_edge_kernels(tn):
     close(reld, rel.detach().reshape(E, 3))
     posd = torch.empty(E, D).cuda()
     tn.call("poem_tr_lin3_relu", reld, W1d, b1d, posd, E, D)
-    close(posd, pos.detach().reshape(E, D))
+    close(posd, pos.detach().reshape(E, D), 5e-4)   # stored TF32-rounded, like t, da and dpos below (GEMM operands only)
     td = torch.empty(E, D).cuda()
     tn.call("poem_tr_va_gather_t", qd, kd, gi, posd, td, E, D)
-    close(td, t.detach().reshape(E, D))
+    close(td, t.detach().reshape(E, D), 1e-3)
     resd = torch.empty(B * Q, D).cuda()
     ad = torch.sin(td)                                                                # stand-in for the gamma MLP (test only)
     tn.call("poem_tr_va_softmax_agg", ad, vd, posd, gi, scale, resd, B * Q, D)     # ad now holds w
-    close(ad, w.detach().reshape(E, D))
-    close(resd, res.detach())
+    close(ad, w.detach().reshape(E, D), 2e-3)
+    close(resd, res.detach(), 2e-3)
     dvp = torch.empty(E, D).cuda()
     tn.call("poem_tr_va_softmax_agg_bwd", f(dres), ad, vd, posd, gi, scale, dvp, B * Q, D)   # ad now holds da
     td = ad * torch.cos(td)                                                            # dt = da * d sin(t)/dt
     dq, dk, dv = torch.zeros(B * Q, D).cuda(), torch.zeros(B * R, D).cuda(), torch.zeros(B * R, D).cuda()
     tn.call("poem_tr_va_scatter", td, dvp, gi, dq, dk, dv, B * Q, D)                  # td now holds dpos
-    close(dq, q.grad, 1e-4)
-    close(dk, ktab.grad, 1e-4)
-    close(dv, vtab.grad, 1e-4)
+    close(dq, q.grad, 2e-3)
+    close(dk, ktab.grad, 2e-3)
+    close(dv, vtab.grad, 2e-3)
     tn.call("poem_tr_relu_bwd", td, posd, td.numel())
     dW1, db1 = torch.zeros(D, 3).cuda(), torch.zeros(D).cuda()
     drel = torch.empty(E, 3).cuda()
     tn.call("poem_tr_lin3_bwd", td, reld, W1d, dW1, db1, drel, E, D)
-    close(dW1, W1.grad, 1e-4)
-    close(db1, b1.grad, 1e-4)
+    close(dW1, W1.grad, 2e-3)
+    close(db1, b1.grad, 2e-3)
     dqx, drx = torch.zeros(B * Q, 3).cuda(), torch.zeros(B * R, 3).cuda()
     tn.call("poem_tr_va_drel_scatter", drel, gi, dqx, drx, B * Q)
-    close(dqx, q_xyz.grad, 1e-4)
-    close(drx, r_xyz.grad, 1e-4)
+    close(dqx, q_xyz.grad, 2e-3)
+    close(drx, r_xyz.grad, 2e-3)
     # anchors (block 0): the same 32 rows / coordinates for every query
     a_idx = torch.randint(0, R, (K,), generator=g, dtype=torch.int32)
     a_xyz = torch.randn(K, 3, generator=g)
