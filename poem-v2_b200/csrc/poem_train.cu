@@ -334,10 +334,7 @@ extern "C" int poem_tr_va_gather_t(const float* q, const float* ktab, const int3
 }
 extern "C" int poem_tr_va_softmax_agg(float* a_w, const float* vtab, const float* pos, const int32_t* gidx, float scale,
                                       float* res, long long NQ, int D, void* stream) {
-  int lg = 0;
-  while ((1 << lg) < D) ++lg;
-  if ((1 << lg) != D) return fail(POEM_TR_E_BADARG, "va_softmax_agg: D = %d is not a power of two", D);
-  tr_va_softmax_agg_kernel<<<grid_for(NQ * D, 128), 128, 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D, lg);
+  tr_va_softmax_agg_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), D, 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D);
   TR_CHECK("va_softmax_agg");
   return 0;
 }

@@ -183,6 +183,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     float* cbase = p.C + (long long)b1 * p.c_s1 + (long long)b2 * p.c_s2;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.c_s1 & 3) == 0) && ((p.c_s2 & 3) == 0);
     const float bias_m = (with_bias && p.bias_on_m && row < p.M) ? p.bias[row] : 0.f;
+    const bool mask_vec = ((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.relu_mask) & 15) == 0);
     // ---- main loop duty: round each landed stage to TF32 (nearest, ties away) in place
     const int et = threadIdx.x - 64;
     const int r_lo = (p.round_ops & 1) ? 0 : Cfg::kABytes / 16;
@@ -224,6 +225,28 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;                      // warp-uniform
+      // ReLU mask of this chunk, fetched before the transpose and the stores (a load behind a store to C could not be
+      // hoisted: the compiler must assume the two alias)
+      float4 mk[8];
+      if (p.relu_mask != nullptr) {
+        const int mcol = col0 + 4 * l8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = m0 + quarter * 32 + 4 * it + rr4;
+          mk[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (grow < p.M && mcol < p.N) {
+            const float* mp = p.relu_mask + (long long)grow * p.ld_mask + mcol;
+            if (mask_vec && mcol + 4 <= p.N) {
+              mk[it] = __ldg(reinterpret_cast<const float4*>(mp));
+            } else {
+              mk[it].x = __ldg(mp);
+              if (mcol + 1 < p.N) mk[it].y = __ldg(mp + 1);
+              if (mcol + 2 < p.N) mk[it].z = __ldg(mp + 2);
+              if (mcol + 3 < p.N) mk[it].w = __ldg(mp + 3);
+            }
+          }
+        }
+      }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -258,11 +281,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           o = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
         }
         if (p.relu_mask != nullptr) {
-          const float* mk = p.relu_mask + (long long)grow * p.ld_mask + col;
-          if (!(mk[0] > 0.f)) o.x = 0.f;
-          if (col + 1 < p.N && !(mk[1] > 0.f)) o.y = 0.f;
-          if (col + 2 < p.N && !(mk[2] > 0.f)) o.z = 0.f;
-          if (col + 3 < p.N && !(mk[3] > 0.f)) o.w = 0.f;
+          if (!(mk[it].x > 0.f)) o.x = 0.f;
+          if (!(mk[it].y > 0.f)) o.y = 0.f;
+          if (!(mk[it].z > 0.f)) o.z = 0.f;
+          if (!(mk[it].w > 0.f)) o.w = 0.f;
         }
         float* dst = cbase + (long long)grow * p.ldc + col;
         if (p.mode == TG_ATOMIC) {

@@ -359,17 +359,20 @@ __global__ void tr_va_gather_t_kernel(const float* q, const float* ktab, const i
   }
 }
 // w = softmax_j(a * scale) per (query, channel), written over a ; res[i, c] = sum_j w * (vtab[gidx] + pos)
-__global__ void tr_va_softmax_agg_kernel(float* a, const float* vtab, const float* pos, const int* gidx, float scale,
-                                         float* res, long long NQ, int D, int log2D) {
-  const long long n = NQ * D;       // flat (query, channel) index, D = 2^log2D
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
-    const long long i = x >> log2D;
-    const int c = (int)(x & (D - 1));
-    float v[TR_NBR];
+// every load of the item is issued before its first store (the pointers may alias as far as the compiler knows: a store
+// in the middle of the neighbour loop would serialise the 64 remaining loads behind it)
+__global__ void tr_va_softmax_agg_kernel(float* a, const float* __restrict__ vtab, const float* __restrict__ pos,
+                                         const int* __restrict__ gidx, float scale, float* __restrict__ res, long long NQ,
+                                         int D) {
+  const int c = threadIdx.x;        // blockDim.x == D
+  for (long long i = blockIdx.x; i < NQ; i += gridDim.x) {
+    float v[TR_NBR], vp[TR_NBR];
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < TR_NBR; ++j) {
-      v[j] = a[(i * TR_NBR + j) * D + c] * scale;
+      const long long e = i * TR_NBR + j;
+      v[j] = a[e * D + c] * scale;
+      vp[j] = vtab[(long long)gidx[e] * D + c] + pos[e * D + c];
       m = fmaxf(m, v[j]);
     }
     float s = 0.f;
@@ -382,12 +385,11 @@ __global__ void tr_va_softmax_agg_kernel(float* a, const float* vtab, const floa
     float acc = 0.f;
 #pragma unroll
     for (int j = 0; j < TR_NBR; ++j) {
-      const long long e = i * TR_NBR + j;
       const float w = v[j] * inv;
-      a[e * D + c] = w;
-      acc += w * (vtab[(long long)gidx[e] * D + c] + pos[e * D + c]);
+      a[(i * TR_NBR + j) * D + c] = w;
+      acc += w * vp[j];
     }
-    res[x] = acc;
+    res[i * D + c] = acc;
   }
 }
 // given dres: da (over w) = w * (dw - sum_j w dw) * scale with dw = dres * (v + pos) ; dvp = w * dres

@@ -160,8 +160,8 @@ class HeadTrainer:
         kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
         # Q, K, V, P, ctx are only ever GEMM operands: stored TF32-rounded by their producers, no rounding pass downstream
         Q = self.lin(hid, pre + ".self.query.weight", pre + ".self.query.bias", round_out=True)
-        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias", round_out=True)
-        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias", round_out=True)
+        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias", x_clean=True, round_out=True)     # enc = ke
+        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias", x_clean=True, round_out=True)
         P = self.new(B, H, Lq, Lk)
         tn.gemm(Q, K, P, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, round_ops=0, **kw)
         tn.call("poem_tr_softmax_rows", P, B * H * Lq, Lk, 1.0 / math.sqrt(hd))
@@ -197,8 +197,8 @@ class HeadTrainer:
                 round_ops=0, round_out=True, **kw)
         del dP
         self.lin_bwd(dQ, t["hid"], pre + ".self.query.weight", pre + ".self.query.bias", out=ds, acc=True, dy_clean=True)   # ds -> d hid
-        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True, dy_clean=True)
-        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True, dy_clean=True)
+        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True, dy_clean=True, x_clean=True)
+        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True, dy_clean=True, x_clean=True)
         return ds
 
     # ------------------------------------------------------------------------------------------ vector attention core
@@ -262,7 +262,7 @@ class HeadTrainer:
         ps, pc = p + "encoder.vec_attn.query_self_attn.", p + "encoder.vec_attn.query_cross_attn."
         t = dict(q_feats=q_feats, pt_feats=pt_feats)
         qe = self.lin(q_feats, p + "embedding.weight", p + "embedding.bias")
-        ke = self.lin(pt_feats, p + "embedding.weight", p + "embedding.bias")
+        ke = self.lin(pt_feats, p + "embedding.weight", p + "embedding.bias", round_out=True)    # ke, xc: GEMM operands only
         a1, t["attn1"] = self.bert_fwd(qe, ke, p + "encoder.attn", B, Q, P)
         a2, t["attn2"] = self.bert_fwd(a1, ke, p + "encoder.cross_attn", B, Q, P)
         E = B * Q * NBR
@@ -285,8 +285,8 @@ class HeadTrainer:
         rel_c = self.new(E, 3)
         tn.call("poem_tr_va_rel", q_xyz, pt_xyz, self.anchor_xyz if i == 0 else None, gc, E, rel_c)
         qc = self.lin(f1, pc + "w_qs.weight")
-        xc = self.lin(ke, pc + "fc1.weight", pc + "fc1.bias")
-        kc, vc = self.lin(xc, pc + "w_ks.weight"), self.lin(xc, pc + "w_vs.weight")
+        xc = self.lin(ke, pc + "fc1.weight", pc + "fc1.bias", x_clean=True, round_out=True)
+        kc, vc = self.lin(xc, pc + "w_ks.weight", x_clean=True), self.lin(xc, pc + "w_vs.weight", x_clean=True)
         res_c, t["core_c"] = self.va_core_fwd(qc, kc, vc, gc, rel_c, pc)
         f2 = f1.clone()
         self.lin(res_c, pc + "fc2.weight", pc + "fc2.bias", out=f2, acc=True)
@@ -331,9 +331,9 @@ class HeadTrainer:
         dqc, dkc, dvc = self.zeros(B * Q, D), self.zeros(B * P, D), self.zeros(B * P, D)
         self.va_core_bwd(dres, t["core_c"], pc, dqc, dkc, dvc, dq_xyz, None)             # basis points are constants
         self.lin_bwd(dqc, t["f1"], pc + "w_qs.weight", out=df1, acc=True)
-        dxc = self.lin_bwd(dkc, t["xc"], pc + "w_ks.weight")
-        self.lin_bwd(dvc, t["xc"], pc + "w_vs.weight", out=dxc, acc=True)
-        dke = self.lin_bwd(dxc, t["ke"], pc + "fc1.weight", pc + "fc1.bias")
+        dxc = self.lin_bwd(dkc, t["xc"], pc + "w_ks.weight", x_clean=True)
+        self.lin_bwd(dvc, t["xc"], pc + "w_vs.weight", out=dxc, acc=True, x_clean=True)
+        dke = self.lin_bwd(dxc, t["ke"], pc + "fc1.weight", pc + "fc1.bias", x_clean=True)
         del dqc, dkc, dvc, dxc
         # --- vector self-attention: f1 = fc2(res_s) + a2
         da2 = df1.clone()
