@@ -106,24 +106,24 @@ static int make_tmap_f32(CUtensorMap* tm, const float* base, int mn_major, long 
   return POEM_TR_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int STAGES>
 static int launch_tgemm(const CUtensorMap& ta, const CUtensorMap& tb, const TgParams& p, dim3 grid, cudaStream_t st) {
-  using Cfg = TgCfg<BN>;
+  using Cfg = TgCfg<BN, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN, A_MN, B_MN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "tgemm smem attribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  tgemm_kernel<BN, A_MN, B_MN><<<grid, TG_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  tgemm_kernel<BN, A_MN, B_MN, STAGES><<<grid, TG_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, p);
   TR_CHECK("tgemm");
   return POEM_TR_OK;
 }
-template <int BN>
+template <int BN, int STAGES>
 static int launch_tgemm_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TgParams& p, dim3 grid,
                               cudaStream_t st) {
-  if (a_mn) return b_mn ? launch_tgemm<BN, true, true>(ta, tb, p, grid, st) : launch_tgemm<BN, true, false>(ta, tb, p, grid, st);
-  return b_mn ? launch_tgemm<BN, false, true>(ta, tb, p, grid, st) : launch_tgemm<BN, false, false>(ta, tb, p, grid, st);
+  if (a_mn) return b_mn ? launch_tgemm<BN, true, true, STAGES>(ta, tb, p, grid, st) : launch_tgemm<BN, true, false, STAGES>(ta, tb, p, grid, st);
+  return b_mn ? launch_tgemm<BN, false, true, STAGES>(ta, tb, p, grid, st) : launch_tgemm<BN, false, false, STAGES>(ta, tb, p, grid, st);
 }
 
 extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a_s1, long long a_s2, const float* B,
@@ -172,10 +172,11 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
   }
   dim3 grid((N + BN - 1) / BN, (M + TG_BM - 1) / TG_BM, nb1 * nb2 * splits);
   if (grid.y > 65535u || grid.z > 65535u) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: grid too large (%u, %u)", grid.y, grid.z);
+  const bool shallow = kb_per_split <= 2;      // K <= 64: a two-stage ring is the whole K loop; three CTAs per SM
   switch (BN) {
-    case 32: return launch_tgemm_major<32>(a_mn, b_mn, ta, tb, p, grid, st);
-    case 64: return launch_tgemm_major<64>(a_mn, b_mn, ta, tb, p, grid, st);
-    default: return launch_tgemm_major<128>(a_mn, b_mn, ta, tb, p, grid, st);
+    case 32: return shallow ? launch_tgemm_major<32, 2>(a_mn, b_mn, ta, tb, p, grid, st) : launch_tgemm_major<32, 3>(a_mn, b_mn, ta, tb, p, grid, st);
+    case 64: return shallow ? launch_tgemm_major<64, 2>(a_mn, b_mn, ta, tb, p, grid, st) : launch_tgemm_major<64, 3>(a_mn, b_mn, ta, tb, p, grid, st);
+    default: return shallow ? launch_tgemm_major<128, 2>(a_mn, b_mn, ta, tb, p, grid, st) : launch_tgemm_major<128, 3>(a_mn, b_mn, ta, tb, p, grid, st);
   }
 }
 

@@ -23,7 +23,7 @@ namespace poem {
 
 constexpr int TG_BM = 128;
 constexpr int TG_BK = 32;          // fp32 elements per 128-byte swizzle row
-constexpr int TG_STAGES = 3;
+constexpr int TG_STAGES = 3;          // ring depth; 2 for problems with K <= 64 (three CTAs per SM instead of two)
 constexpr int TG_THREADS = 192;
 constexpr int TG_ATOM_BYTES = TG_BK * 128;   // one MN-major atom: 32 K rows x 128 B
 
@@ -50,12 +50,12 @@ struct TgParams {
   long long ld_mask;
 };
 
-template <int BN>
+template <int BN, int STAGES = TG_STAGES>
 struct TgCfg {
   static constexpr int kABytes = TG_BM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = TG_STAGES * kStageBytes + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int kSmemBytes = STAGES * kStageBytes + 256 + 1024;   // + barriers + alignment slack
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -85,10 +85,11 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc_f32(uint32_t smem_addr, ui
          (1ull << 46) | (1ull << 61);
 }
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TG_THREADS, 2)
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(TG_THREADS, (STAGES == 2 ? 3 : 2))
 tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TgParams p) {
-  using Cfg = TgCfg<BN>;
+  using Cfg = TgCfg<BN, STAGES>;
+  constexpr int TG_STAGES = STAGES;       // shadows the default depth inside the kernel
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * Cfg::kStageBytes);
