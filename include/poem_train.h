@@ -66,9 +66,21 @@ int poem_tr_layernorm(const float* x, const float* res, const float* gamma, cons
 int poem_tr_layernorm_bwd(const float* dy, const float* xhat, const float* rstd, const float* gamma, float* dx,
                           float* dgamma, float* dbeta, long long M, int D, void* stream);   /* dgamma, dbeta += */
 
-/* softmax over rows of length L: P = softmax(S * scale) in place ; dS = P (dP - sum P dP) * scale over dP */
-int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, void* stream);
-int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, void* stream);
+/* Dropout without stored masks: element i of site `site` is kept iff mix(seed[0], site, i) >= p * 2^32 (seed: DEVICE
+ * scalar the caller bumps every step, so captured graphs draw fresh masks).  y = keep ? x / (1 - p) : 0; the same call on
+ * a gradient is the backward.  Reference: nn.Dropout(hidden_dropout_prob) at pt_metro_transformer.py:117,185-186 and in
+ * the HF BertSelfOutput / BertOutput / BertSelfAttention the layers are built from (config/release: DROPOUT 0.1). */
+int poem_tr_dropout(const float* x, float* y, long long n, float p, const unsigned long long* seed, unsigned long long site,
+                    void* stream);
+
+/* softmax over rows of length L.  P_dropped == NULL: S <- P = softmax(S * scale), stored TF32-rounded.  P_dropped != NULL
+ * (attention-probability dropout): S <- P in full precision (the backward needs the un-dropped P), P_dropped <-
+ * keep ? P / (1 - p_drop) : 0, TF32-rounded (the operand of P.V and P^T.dO).
+ * backward: dS = P (d - sum P d) * scale over dP, d = dP, or with seed != NULL d = keep ? dP / (1 - p_drop) : 0 */
+int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, float* P_dropped, float p_drop,
+                         const unsigned long long* seed, unsigned long long site, void* stream);
+int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, float p_drop,
+                             const unsigned long long* seed, unsigned long long site, void* stream);
 
 /* vector attention (32 neighbours per query); edge e = query * 32 + slot */
 int poem_tr_va_make_idx(const int32_t* local_idx, const int32_t* anchor_idx, int B, int Q, int R, int32_t* gidx, void* stream);

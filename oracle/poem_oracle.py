@@ -101,6 +101,18 @@ def merge_views(sd, sampled, view_counts):
     return torch.cat(outs, dim=0)
 
 
+# Test hook (not in the reference): {site name: keep / (1 - p) mask} of the training-mode dropout layers, so that a device
+# run with dropout and the oracle can be compared on the same masks (nn.Dropout(hidden_dropout_prob) at
+# pt_metro_transformer.py:117,185-186 and inside HF BertSelfAttention / BertSelfOutput / BertOutput).  None = eval mode.
+DROPOUT_MASKS = None
+
+
+def _drop(name, x):
+    if DROPOUT_MASKS is None:
+        return x
+    return x * DROPOUT_MASKS[name].reshape(x.shape)
+
+
 # ------------------------------------------------------------------------------------------ a10
 def bert_cross_attention(sd, prefix, hidden, enc, n_heads):
     """HF 4.x `BertAttention` with `encoder_hidden_states`: Q from `hidden`, K/V from `enc`, no mask,
@@ -114,9 +126,9 @@ def bert_cross_attention(sd, prefix, hidden, enc, n_heads):
     q = split(F.linear(hidden, sd[prefix + ".self.query.weight"], sd[prefix + ".self.query.bias"]))
     k = split(F.linear(enc, sd[prefix + ".self.key.weight"], sd[prefix + ".self.key.bias"]))
     v = split(F.linear(enc, sd[prefix + ".self.value.weight"], sd[prefix + ".self.value.bias"]))
-    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    p = _drop(prefix + ".probs", torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1))
     ctx = (p @ v).transpose(1, 2).reshape(B, Lq, D)
-    o = F.linear(ctx, sd[prefix + ".output.dense.weight"], sd[prefix + ".output.dense.bias"])
+    o = _drop(prefix + ".hidden", F.linear(ctx, sd[prefix + ".output.dense.weight"], sd[prefix + ".output.dense.bias"]))
     return F.layer_norm(o + hidden, (D,), sd[prefix + ".output.LayerNorm.weight"],
                         sd[prefix + ".output.LayerNorm.bias"], eps=1e-12)
 
@@ -189,8 +201,8 @@ def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=N
     (lib/models/bricks/pt_metro_transformer.py:153-200, 56-91, 34-40); eval mode (dropout = identity)."""
     p = f"transformer.pt_metro_encoder.{i}."
     D = dims.embed_dims
-    qe = F.linear(q_feats, sd[p + "embedding.weight"], sd[p + "embedding.bias"])
-    ke = F.linear(pt_feats, sd[p + "embedding.weight"], sd[p + "embedding.bias"])
+    qe = _drop(p + "qe", F.linear(q_feats, sd[p + "embedding.weight"], sd[p + "embedding.bias"]))
+    ke = _drop(p + "ke", F.linear(pt_feats, sd[p + "embedding.weight"], sd[p + "embedding.bias"]))
     a1 = bert_cross_attention(sd, p + "encoder.attn", qe, ke, dims.n_heads)
     a2 = bert_cross_attention(sd, p + "encoder.cross_attn", a1, ke, dims.n_heads)
     anc = anchors if i == 0 else None
@@ -200,7 +212,7 @@ def metro_block(sd, i, dims, q_xyz, q_feats, pt_xyz, pt_feats, anchors, stages=N
                                     dims.n_neighbor, anc, nb_c)
     xyz = _mlp2(sd, p + "encoder.vec_attn.reg_branch", f2) + q_xyz
     h = F.gelu(F.linear(f2, sd[p + "encoder.intermediate.dense.weight"], sd[p + "encoder.intermediate.dense.bias"]))
-    o = F.linear(h, sd[p + "encoder.output.dense.weight"], sd[p + "encoder.output.dense.bias"])
+    o = _drop(p + "ffn", F.linear(h, sd[p + "encoder.output.dense.weight"], sd[p + "encoder.output.dense.bias"]))
     out = F.layer_norm(o + f2, (D,), sd[p + "encoder.output.LayerNorm.weight"],
                        sd[p + "encoder.output.LayerNorm.bias"], eps=1e-12)
     if stages is not None:

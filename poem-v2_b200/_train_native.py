@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("POEM_TRAIN_LIB", os.path.join(CSRC, "libpoem_train.so
 SOURCES = ["poem_train.cu"]
 HEADERS = ["common.cuh", "tgemm.cuh", "train_simt.cuh"]
 
-_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+_P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 
 SIGNATURES = {
     "poem_tr_gemm": [_P, _I, _L, _L, _L, _P, _I, _L, _L, _L, _P, _L, _L, _L, _I, _I, _I, _I, _I, _F, _P, _I, _I, _I, _P, _L, _I, _I, _P],
@@ -29,8 +29,9 @@ SIGNATURES = {
     "poem_tr_bcast_batch": [_P, _I, _L, _P, _P],
     "poem_tr_layernorm": [_P, _P, _P, _P, _F, _P, _P, _P, _L, _I, _P],
     "poem_tr_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
-    "poem_tr_softmax_rows": [_P, _L, _I, _F, _P],
-    "poem_tr_softmax_rows_bwd": [_P, _P, _L, _I, _F, _P],
+    "poem_tr_dropout": [_P, _P, _L, _F, _P, _U, _P],
+    "poem_tr_softmax_rows": [_P, _L, _I, _F, _P, _F, _P, _U, _P],
+    "poem_tr_softmax_rows_bwd": [_P, _P, _L, _I, _F, _F, _P, _U, _P],
     "poem_tr_va_make_idx": [_P, _P, _I, _I, _I, _P, _P],
     "poem_tr_va_rel": [_P, _P, _P, _P, _L, _P, _P],
     "poem_tr_lin3_relu": [_P, _P, _P, _P, _L, _I, _P],

@@ -26,6 +26,7 @@ class HeadDims:
     pos_normalize: bool = True
     feat_hw: int = 16            # HRNet stride-16 feature map (16x16 for 256x256 input)
     parametric: bool = False     # TRANSFORMER.PARAMETRIC_OUTPUT (medium_MANO)
+    dropout: float = 0.0         # TRANSFORMER.DROPOUT (training mode only: hidden + attention-probability dropout of the BERT layers)
 
     def as_dict(self):
         return asdict(self)
@@ -61,4 +62,4 @@ def dims_from_cfg(cfg) -> HeadDims:
                     n_heads=int(g(tr, "NUM_ATTENTION_HEADS")), n_neighbor=nn_,
                     radius=float(g(cfg, "RADIUS_SAMPLE")), center_idx=int(g(tr, "TRANSFORMER_CENTER_IDX", 9)),
                     pos_feats=int(g(pe, "NUM_FEATS")), pos_normalize=bool(g(pe, "NORMALIZE")),
-                    parametric=bool(g(tr, "PARAMETRIC_OUTPUT", False)))
+                    parametric=bool(g(tr, "PARAMETRIC_OUTPUT", False)), dropout=float(g(tr, "DROPOUT", 0.0) or 0.0))

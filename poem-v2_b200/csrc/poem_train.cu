@@ -266,21 +266,31 @@ extern "C" int poem_tr_layernorm_bwd(const float* dy, const float* xhat, const f
   return 0;
 }
 
-extern "C" int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, void* stream) {
+extern "C" int poem_tr_dropout(const float* x, float* y, long long n, float p, const unsigned long long* seed,
+                               unsigned long long site, void* stream) {
+  if (!(p >= 0.f && p < 1.f) || !seed) return fail(POEM_TR_E_BADARG, "dropout: p in [0, 1) and a device seed are needed");
+  tr_dropout_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, n, p, seed, site);
+  TR_CHECK("dropout");
+  return 0;
+}
+extern "C" int poem_tr_softmax_rows(float* S, long long rows, int L, float scale, float* P_dropped, float p_drop,
+                                    const unsigned long long* seed, unsigned long long site, void* stream) {
   if (rows > 0x7fffffffLL) return fail(POEM_TR_E_BADARG, "softmax_rows: too many rows");
-  const bool al = (reinterpret_cast<uintptr_t>(S) & 15) == 0;
-  if (al && L == 4096) tr_softmax_rows_kernel<4><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
-  else if (al && L == 1024) tr_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
-  else tr_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale);
+  if (P_dropped && (!seed || !(p_drop >= 0.f && p_drop < 1.f))) return fail(POEM_TR_E_BADARG, "softmax_rows: dropout needs a seed and p in [0, 1)");
+  const bool al = ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(P_dropped)) & 15) == 0;
+  if (al && L == 4096) tr_softmax_rows_kernel<4><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale, P_dropped, p_drop, seed, site);
+  else if (al && L == 1024) tr_softmax_rows_kernel<1><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale, P_dropped, p_drop, seed, site);
+  else tr_softmax_rows_kernel<0><<<(unsigned)rows, 256, 0, ST>>>(S, L, scale, P_dropped, p_drop, seed, site);
   TR_CHECK("softmax_rows");
   return 0;
 }
-extern "C" int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, void* stream) {
+extern "C" int poem_tr_softmax_rows_bwd(const float* P, float* dP, long long rows, int L, float scale, float p_drop,
+                                        const unsigned long long* seed, unsigned long long site, void* stream) {
   if (rows > 0x7fffffffLL) return fail(POEM_TR_E_BADARG, "softmax_rows_bwd: too many rows");
   const bool al = ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(dP)) & 15) == 0;
-  if (al && L == 4096) tr_softmax_rows_bwd_kernel<4><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
-  else if (al && L == 1024) tr_softmax_rows_bwd_kernel<1><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
-  else tr_softmax_rows_bwd_kernel<0><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale);
+  if (al && L == 4096) tr_softmax_rows_bwd_kernel<4><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale, p_drop, seed, site);
+  else if (al && L == 1024) tr_softmax_rows_bwd_kernel<1><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale, p_drop, seed, site);
+  else tr_softmax_rows_bwd_kernel<0><<<(unsigned)rows, 256, 0, ST>>>(P, dP, L, scale, p_drop, seed, site);
   TR_CHECK("softmax_rows_bwd");
   return 0;
 }

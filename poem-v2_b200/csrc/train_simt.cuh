@@ -28,6 +28,29 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ------------------------------------------------------------------------------------------------ dropout
+// Counter-based: element `idx` of dropout site `site` in the step whose seed is seed[0] is kept iff
+// mix(seed[0] + site * K1 + idx) >= p * 2^32 (splitmix64 finaliser).  Nothing is stored: the backward regenerates the
+// mask from the same (seed, site).  The seed lives in device memory so that a captured CUDA graph draws fresh masks on
+// every replay (the caller bumps it).  Reference: nn.Dropout at pt_metro_transformer.py:117,185-186 and inside the HF
+// BertSelfAttention / BertSelfOutput / BertOutput the layers are built from (hidden 0.1, attention probabilities 0.1).
+__device__ __forceinline__ bool tr_keep(unsigned long long seed, unsigned long long site, unsigned long long idx, uint32_t thr) {
+  unsigned long long z = seed + site * 0xD1B54A32D192ED03ull + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32) >= thr;
+}
+__device__ __forceinline__ uint32_t tr_drop_threshold(float p) { return (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f); }
+// y = keep ? x / (1 - p) : 0     (in place allowed; applied to a gradient with the same seed / site it is the backward)
+__global__ void tr_dropout_kernel(const float* x, float* y, long long n, float p, const unsigned long long* seed,
+                                  unsigned long long site) {
+  const unsigned long long sd = seed[0];
+  const uint32_t thr = tr_drop_threshold(p);
+  const float sc = 1.0f / (1.0f - p);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = tr_keep(sd, site, (unsigned long long)i, thr) ? x[i] * sc : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------ elementwise
 __global__ void tr_relu_kernel(float* y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -209,9 +232,17 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) 
 // P = softmax(S * scale) in place; one block (256 threads) per row of length L.  kV4 > 0: the row lives in registers
 // (L == 256 * 4 * kV4: one read, one write); kV4 == 0: generic three-pass version.
 template <int kV4>
-__global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
+__global__ void tr_softmax_rows_kernel(float* S, int L, float scale, float* Pd, float p_drop, const unsigned long long* seed,
+                                       unsigned long long site) {
+  // Pd == nullptr: P (TF32-rounded: a GEMM operand) over S.  Pd != nullptr (attention-probability dropout): S keeps the
+  // un-dropped P in full precision (the softmax backward needs it), Pd gets keep ? P / (1 - p) : 0, TF32-rounded.
   __shared__ float red[8];
   float* row = S + (long long)blockIdx.x * L;
+  float* drow = Pd ? Pd + (long long)blockIdx.x * L : nullptr;
+  const unsigned long long sd = Pd ? seed[0] : 0ull;
+  const uint32_t thr = tr_drop_threshold(p_drop);
+  const float sc = 1.0f / (1.0f - p_drop);
+  const unsigned long long base = (unsigned long long)blockIdx.x * (unsigned long long)L;
   if (kV4 > 0) {
     float4 v[kV4 > 0 ? kV4 : 1];
     float m = -INFINITY;
@@ -230,8 +261,18 @@ __global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
     }
     const float inv = 1.0f / block_reduce(s, false, red);
 #pragma unroll
-    for (int i = 0; i < kV4; ++i)
-      reinterpret_cast<float4*>(row)[threadIdx.x + 256 * i] = make_float4(tf32r(v[i].x * inv), tf32r(v[i].y * inv), tf32r(v[i].z * inv), tf32r(v[i].w * inv));
+    for (int i = 0; i < kV4; ++i) {
+      const float4 pv = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+      if (drow == nullptr) {
+        reinterpret_cast<float4*>(row)[threadIdx.x + 256 * i] = make_float4(tf32r(pv.x), tf32r(pv.y), tf32r(pv.z), tf32r(pv.w));
+      } else {
+        const unsigned long long e = base + 4ull * (threadIdx.x + 256 * i);
+        reinterpret_cast<float4*>(row)[threadIdx.x + 256 * i] = pv;
+        reinterpret_cast<float4*>(drow)[threadIdx.x + 256 * i] =
+            make_float4(tr_keep(sd, site, e, thr) ? tf32r(pv.x * sc) : 0.f, tr_keep(sd, site, e + 1, thr) ? tf32r(pv.y * sc) : 0.f,
+                        tr_keep(sd, site, e + 2, thr) ? tf32r(pv.z * sc) : 0.f, tr_keep(sd, site, e + 3, thr) ? tf32r(pv.w * sc) : 0.f);
+      }
+    }
     return;
   }
   float m = -INFINITY;
@@ -244,14 +285,29 @@ __global__ void tr_softmax_rows_kernel(float* S, int L, float scale) {
     s += e;
   }
   const float inv = 1.0f / block_reduce(s, false, red);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) row[i] = tf32r(row[i] * inv);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float pv = row[i] * inv;
+    if (drow == nullptr) {
+      row[i] = tf32r(pv);
+    } else {
+      row[i] = pv;
+      drow[i] = tr_keep(sd, site, base + (unsigned long long)i, thr) ? tf32r(pv * sc) : 0.f;
+    }
+  }
 }
-// dS = P * (dP - sum(P * dP)) * scale, written over dP
+// dS = P * (d - sum(P * d)) * scale, written over dP, with d = dP (no dropout) or d = keep ? dP / (1 - p) : 0 (dP is
+// then the gradient w.r.t. the DROPPED probabilities and P the un-dropped ones; mask regenerated from seed / site)
 template <int kV4>
-__global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, float scale) {
+__global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, float scale, float p_drop,
+                                           const unsigned long long* seed, unsigned long long site) {
   __shared__ float red[8];
   const float* prow = P + (long long)blockIdx.x * L;
   float* drow = dP + (long long)blockIdx.x * L;
+  const bool drop = seed != nullptr;
+  const unsigned long long sd = drop ? seed[0] : 0ull;
+  const uint32_t thr = tr_drop_threshold(p_drop);
+  const float sc = 1.0f / (1.0f - p_drop);
+  const unsigned long long base = (unsigned long long)blockIdx.x * (unsigned long long)L;
   if (kV4 > 0) {
     float4 p[kV4 > 0 ? kV4 : 1], d[kV4 > 0 ? kV4 : 1];
     float s = 0.f;
@@ -259,6 +315,11 @@ __global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, flo
     for (int i = 0; i < kV4; ++i) {
       p[i] = reinterpret_cast<const float4*>(prow)[threadIdx.x + 256 * i];
       d[i] = reinterpret_cast<const float4*>(drow)[threadIdx.x + 256 * i];
+      if (drop) {
+        const unsigned long long e = base + 4ull * (threadIdx.x + 256 * i);
+        d[i].x = tr_keep(sd, site, e, thr) ? d[i].x * sc : 0.f, d[i].y = tr_keep(sd, site, e + 1, thr) ? d[i].y * sc : 0.f;
+        d[i].z = tr_keep(sd, site, e + 2, thr) ? d[i].z * sc : 0.f, d[i].w = tr_keep(sd, site, e + 3, thr) ? d[i].w * sc : 0.f;
+      }
       s += (p[i].x * d[i].x + p[i].y * d[i].y) + (p[i].z * d[i].z + p[i].w * d[i].w);
     }
     const float dot = block_reduce(s, false, red);
@@ -270,9 +331,17 @@ __global__ void tr_softmax_rows_bwd_kernel(const float* P, float* dP, int L, flo
     return;
   }
   float s = 0.f;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) s += prow[i] * drow[i];
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float dv = drow[i];
+    if (drop) dv = tr_keep(sd, site, base + (unsigned long long)i, thr) ? dv * sc : 0.f;
+    s += prow[i] * dv;
+  }
   const float dot = block_reduce(s, false, red);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) drow[i] = tf32r(prow[i] * (drow[i] - dot) * scale);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float dv = drow[i];
+    if (drop) dv = tr_keep(sd, site, base + (unsigned long long)i, thr) ? dv * sc : 0.f;
+    drow[i] = tf32r(prow[i] * (dv - dot) * scale);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ vector attention: edges

@@ -193,6 +193,7 @@ class POEM_Generalized_Head(_NativeDecoder):
         """`head.train()` makes the live parameters trainable (the reference's are by default); `eval()` leaves them."""
         super().train(mode)
         if mode:
+            self._train_requested = True       # a freshly built module is `training` too, but only an explicit train() opts in
             for p in self.parameters():
                 p.requires_grad_(True)
         return self
@@ -219,8 +220,9 @@ class POEM_Generalized_Head(_NativeDecoder):
         return tr
 
     def forward(self, mlvl_feat, img_metas, reference_joints, **kwargs):
-        if self.training and torch.is_grad_enabled():
+        if self.training and torch.is_grad_enabled() and getattr(self, "_train_requested", False):
             from .train import HeadFunction
+            assert int(np.sum(np.asarray(img_metas["master_id"]))) == 0, "only support master_id is 0"
             _require_cuda(mlvl_feat, "mlvl_feat")
             tr = self.trainer()
             coords = HeadFunction.apply(tr, mlvl_feat, img_metas, reference_joints, *self._trainer_params)

@@ -13,9 +13,10 @@ per-edge tensors of the vector attention (B*799*32*D per layer) stay in HBM betw
 (~40 GB at POEM-medium, batch 32: sized for the 180 GB of a B200) instead of the reference's recompute
 (`cp.checkpoint`, point_transformers.py:63,119).
 
-Not covered (raises / documented in DESIGN.md): dropout > 0 (the release configs train with DROPOUT 0.1 inside the BERT
-layers; eval-mode arithmetic is what the reference's own gradients are pinned on in tests/golden/grad_small_b2.npz), the
-parametric MANO tail, D = 1024.
+Dropout (TRANSFORMER.DROPOUT, 0.1 in the release configs: on both embedding outputs, after the two attention output
+projections and the FFN output projection, and on the attention probabilities) is counter-based — masks are regenerated
+in the backward from a device seed, nothing is stored.  Not covered (raises / documented in DESIGN.md): the parametric
+MANO tail, D = 1024.
 """
 import math
 
@@ -45,7 +46,9 @@ class HeadTrainer:
         dfeat = tr.backward(dcoords)                                     # d loss / d mlvl_feat ; tr.g[name] += d loss / d p
     """
 
-    def __init__(self, dims: HeadDims, state_dict, template, assets=None, device="cuda"):
+    def __init__(self, dims: HeadDims, state_dict, template, assets=None, device="cuda", dropout=None):
+        """dropout: probability of the BERT layers' hidden / attention-probability dropout (None: dims.dropout, i.e.
+        TRANSFORMER.DROPOUT of the config; 0 = the eval-mode arithmetic the gradient goldens are pinned on)."""
         if dims.parametric:
             raise NotImplementedError("training path: the parametric MANO tail has no backward yet")
         if dims.embed_dims > 512 or dims.n_neighbor != NBR:
@@ -88,6 +91,34 @@ class HeadTrainer:
         self.template = torch.as_tensor(template, dtype=torch.float32).reshape(dims.n_query, 3).to(self.dev).contiguous()
         self.tape = None
         self.last_neighbours = None
+        self.p_drop = float(dims.dropout if dropout is None else dropout)
+        if not 0.0 <= self.p_drop < 1.0:
+            raise ValueError("dropout probability must be in [0, 1)")
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)    # device scalar: bumped every forward
+        self.drop_sites = {}                                                   # name -> (site id, shape) of the last forward
+        self._site = 0
+
+    def manual_seed(self, seed):
+        self.seed_dev.fill_(int(seed))
+
+    def dropout_(self, x, name=None, site=None):
+        """In place x <- keep ? x / (1 - p) : 0.  Forward: a new site (recorded under `name`); backward: pass the site."""
+        if self.p_drop == 0.0:
+            return None
+        if site is None:
+            site = self._site
+            self._site += 1
+            if name is not None:
+                self.drop_sites[name] = (site, tuple(x.shape))
+        tn.call("poem_tr_dropout", x, x, x.numel(), self.p_drop, self.seed_dev, site)
+        return site
+
+    def dropout_mask(self, name):
+        """keep / (1 - p) of a site of the last forward, regenerated (tests: the oracle is run on the same masks)."""
+        site, shape = self.drop_sites[name]
+        m = torch.ones(*shape, dtype=torch.float32, device=self.dev)
+        tn.call("poem_tr_dropout", m, m, m.numel(), self.p_drop, self.seed_dev, site)
+        return m
 
     # ------------------------------------------------------------------------------------------ small helpers
     def new(self, *shape, dtype=torch.float32):
@@ -154,23 +185,30 @@ class HeadTrainer:
         hd = D // H
         return dict(batch=(H, B)), (hd, Lq * D), (hd, Lk * D), (Lq * Lk, H * Lq * Lk)
 
-    def bert_fwd(self, hid, enc, pre, B, Lq, Lk):
+    def bert_fwd(self, hid, enc, pre, B, Lq, Lk, enc_clean=True):
         D, H = hid.shape[1], self.dims.n_heads
         hd = D // H
         kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
         # Q, K, V, P, ctx are only ever GEMM operands: stored TF32-rounded by their producers, no rounding pass downstream
         Q = self.lin(hid, pre + ".self.query.weight", pre + ".self.query.bias", round_out=True)
-        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias", x_clean=True, round_out=True)     # enc = ke
-        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias", x_clean=True, round_out=True)
+        K = self.lin(enc, pre + ".self.key.weight", pre + ".self.key.bias", x_clean=enc_clean, round_out=True)     # enc = ke
+        V = self.lin(enc, pre + ".self.value.weight", pre + ".self.value.bias", x_clean=enc_clean, round_out=True)
         P = self.new(B, H, Lq, Lk)
         tn.gemm(Q, K, P, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, round_ops=0, **kw)
-        tn.call("poem_tr_softmax_rows", P, B * H * Lq, Lk, 1.0 / math.sqrt(hd))
+        Pd, site_p = None, 0
+        if self.p_drop > 0.0:                       # attention-probability dropout: P (kept for the backward) and its dropped copy
+            Pd, site_p = self.new(B, H, Lq, Lk), self._site
+            self._site += 1
+            self.drop_sites[pre + ".probs"] = (site_p, (B, H, Lq, Lk))
+        tn.call("poem_tr_softmax_rows", P, B * H * Lq, Lk, 1.0 / math.sqrt(hd), Pd, self.p_drop, self.seed_dev, site_p)
         ctx = self.new(B * Lq, D)
-        tn.gemm(P, V, ctx, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq, round_ops=0,
-                round_out=True, **kw)
+        tn.gemm(P if Pd is None else Pd, V, ctx, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk,
+                c_strides=sq, round_ops=0, round_out=True, **kw)
         o = self.lin(ctx, pre + ".output.dense.weight", pre + ".output.dense.bias", x_clean=True)
+        site_h = self.dropout_(o, pre + ".hidden")                  # BertSelfOutput: dense -> dropout -> + residual -> LayerNorm
         y, xhat, rstd = self.ln(o, hid, pre + ".output.LayerNorm")
-        return y, dict(hid=hid, enc=enc, Q=Q, K=K, V=V, P=P, ctx=ctx, xhat=xhat, rstd=rstd, B=B, Lq=Lq, Lk=Lk)
+        return y, dict(hid=hid, enc=enc, Q=Q, K=K, V=V, P=P, Pd=Pd, ctx=ctx, xhat=xhat, rstd=rstd, B=B, Lq=Lq, Lk=Lk,
+                       site_p=site_p, site_h=site_h, enc_clean=enc_clean)
 
     def bert_bwd(self, dy, t, pre, denc):
         """returns d hid; accumulates into denc"""
@@ -178,17 +216,23 @@ class HeadTrainer:
         D, H = dy.shape[1], self.dims.n_heads
         hd = D // H
         kw, sq, sk, sp = self._attn_strides(B, Lq, Lk, D, H)
-        ds = self.ln_bwd(dy, t["xhat"], t["rstd"], pre + ".output.LayerNorm")        # grad of (o + hid)
-        dctx = self.lin_bwd(ds, t["ctx"], pre + ".output.dense.weight", pre + ".output.dense.bias", x_clean=True, round_out=True)
+        ds = self.ln_bwd(dy, t["xhat"], t["rstd"], pre + ".output.LayerNorm")        # grad of (dropout(o) + hid)
+        do = ds
+        if t["site_h"] is not None:
+            do = ds.clone()
+            self.dropout_(do, site=t["site_h"])
+        dctx = self.lin_bwd(do, t["ctx"], pre + ".output.dense.weight", pre + ".output.dense.bias", x_clean=True, round_out=True)
         P = t["P"]
+        Pv = P if t["Pd"] is None else t["Pd"]                      # what multiplied V in the forward
+        drop_seed = None if t["Pd"] is None else self.seed_dev
         # every operand below was stored rounded by its producer (P, dS by the softmax kernels; Q, K, V, dctx, dQ, dK, dV by
         # GEMM epilogues): no rounding pass in these GEMMs
         dV = self.new(B * Lk, D)
-        tn.gemm(P, dctx, dV, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk,
+        tn.gemm(Pv, dctx, dV, Lk, hd, Lq, a_mn=True, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sq, c_strides=sk,
                 round_ops=0, round_out=True, **kw)
         dP = self.new(B, H, Lq, Lk)
         tn.gemm(dctx, t["V"], dP, Lq, Lk, hd, lda=D, ldb=D, ldc=Lk, a_strides=sq, b_strides=sk, c_strides=sp, round_ops=0, **kw)
-        tn.call("poem_tr_softmax_rows_bwd", P, dP, B * H * Lq, Lk, 1.0 / math.sqrt(hd))          # dP now holds dS
+        tn.call("poem_tr_softmax_rows_bwd", P, dP, B * H * Lq, Lk, 1.0 / math.sqrt(hd), self.p_drop, drop_seed, t["site_p"])   # dP <- dS
         dQ = self.new(B * Lq, D)
         tn.gemm(dP, t["K"], dQ, Lq, hd, Lk, b_mn=True, lda=Lk, ldb=D, ldc=D, a_strides=sp, b_strides=sk, c_strides=sq,
                 round_ops=0, round_out=True, **kw)
@@ -197,8 +241,8 @@ class HeadTrainer:
                 round_ops=0, round_out=True, **kw)
         del dP
         self.lin_bwd(dQ, t["hid"], pre + ".self.query.weight", pre + ".self.query.bias", out=ds, acc=True, dy_clean=True)   # ds -> d hid
-        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True, dy_clean=True, x_clean=True)
-        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True, dy_clean=True, x_clean=True)
+        self.lin_bwd(dK, t["enc"], pre + ".self.key.weight", pre + ".self.key.bias", out=denc, acc=True, dy_clean=True, x_clean=t["enc_clean"])
+        self.lin_bwd(dV, t["enc"], pre + ".self.value.weight", pre + ".self.value.bias", out=denc, acc=True, dy_clean=True, x_clean=t["enc_clean"])
         return ds
 
     # ------------------------------------------------------------------------------------------ vector attention core
@@ -263,8 +307,11 @@ class HeadTrainer:
         t = dict(q_feats=q_feats, pt_feats=pt_feats)
         qe = self.lin(q_feats, p + "embedding.weight", p + "embedding.bias")
         ke = self.lin(pt_feats, p + "embedding.weight", p + "embedding.bias", round_out=True)    # ke, xc: GEMM operands only
-        a1, t["attn1"] = self.bert_fwd(qe, ke, p + "encoder.attn", B, Q, P)
-        a2, t["attn2"] = self.bert_fwd(a1, ke, p + "encoder.cross_attn", B, Q, P)
+        t["site_qe"] = self.dropout_(qe, p + "qe")                    # pt_metro_transformer.py:185-186
+        t["site_ke"] = self.dropout_(ke, p + "ke")
+        ke_clean = self.p_drop == 0.0                                  # x / (1 - p) is no longer TF32-representable
+        a1, t["attn1"] = self.bert_fwd(qe, ke, p + "encoder.attn", B, Q, P, ke_clean)
+        a2, t["attn2"] = self.bert_fwd(a1, ke, p + "encoder.cross_attn", B, Q, P, ke_clean)
         E = B * Q * NBR
         # --- vector self-attention over the queries (point_transformers.py:70-96)
         if i == 0:
@@ -285,7 +332,7 @@ class HeadTrainer:
         rel_c = self.new(E, 3)
         tn.call("poem_tr_va_rel", q_xyz, pt_xyz, self.anchor_xyz if i == 0 else None, gc, E, rel_c)
         qc = self.lin(f1, pc + "w_qs.weight")
-        xc = self.lin(ke, pc + "fc1.weight", pc + "fc1.bias", x_clean=True, round_out=True)
+        xc = self.lin(ke, pc + "fc1.weight", pc + "fc1.bias", x_clean=ke_clean, round_out=True)
         kc, vc = self.lin(xc, pc + "w_ks.weight", x_clean=True), self.lin(xc, pc + "w_vs.weight", x_clean=True)
         res_c, t["core_c"] = self.va_core_fwd(qc, kc, vc, gc, rel_c, pc)
         f2 = f1.clone()
@@ -299,6 +346,8 @@ class HeadTrainer:
         h = self.new(*hpre.shape)
         tn.call("poem_tr_gelu", hpre, h, h.numel())
         o = self.lin(h, p + "encoder.output.dense.weight", p + "encoder.output.dense.bias")
+        t["site_ffn"] = self.dropout_(o, p + "ffn")                    # BertOutput: dense -> dropout -> + residual -> LayerNorm
+        t["ke_clean"] = ke_clean
         out, xhat, rstd = self.ln(o, f2, p + "encoder.output.LayerNorm")
         t.update(qe=qe, ke=ke, a1=a1, a2=a2, xs=xs, res_s=res_s, f1=f1, xc=xc, res_c=res_c, f2=f2, r=r, hpre=hpre, h=h,
                  xhat=xhat, rstd=rstd)
@@ -313,8 +362,12 @@ class HeadTrainer:
         ps, pc = p + "encoder.vec_attn.query_self_attn.", p + "encoder.vec_attn.query_cross_attn."
         f2 = t["f2"]
         if dout is not None:
-            df2 = self.ln_bwd(dout, t["xhat"], t["rstd"], p + "encoder.output.LayerNorm")       # grad of (o + f2)
-            dh = self.lin_bwd(df2, t["h"], p + "encoder.output.dense.weight", p + "encoder.output.dense.bias")
+            df2 = self.ln_bwd(dout, t["xhat"], t["rstd"], p + "encoder.output.LayerNorm")       # grad of (dropout(o) + f2)
+            do = df2
+            if t["site_ffn"] is not None:
+                do = df2.clone()
+                self.dropout_(do, site=t["site_ffn"])
+            dh = self.lin_bwd(do, t["h"], p + "encoder.output.dense.weight", p + "encoder.output.dense.bias")
             tn.call("poem_tr_gelu_bwd", dh, t["hpre"], dh.numel())
             self.lin_bwd(dh, f2, p + "encoder.intermediate.dense.weight", p + "encoder.intermediate.dense.bias", out=df2, acc=True)
             del dh
@@ -333,7 +386,7 @@ class HeadTrainer:
         self.lin_bwd(dqc, t["f1"], pc + "w_qs.weight", out=df1, acc=True)
         dxc = self.lin_bwd(dkc, t["xc"], pc + "w_ks.weight", x_clean=True)
         self.lin_bwd(dvc, t["xc"], pc + "w_vs.weight", out=dxc, acc=True, x_clean=True)
-        dke = self.lin_bwd(dxc, t["ke"], pc + "fc1.weight", pc + "fc1.bias", x_clean=True)
+        dke = self.lin_bwd(dxc, t["ke"], pc + "fc1.weight", pc + "fc1.bias", x_clean=t["ke_clean"])
         del dqc, dkc, dvc, dxc
         # --- vector self-attention: f1 = fc2(res_s) + a2
         da2 = df1.clone()
@@ -347,6 +400,9 @@ class HeadTrainer:
         # --- the two BERT cross-attention layers
         da1 = self.bert_bwd(da2, t["attn2"], p + "encoder.cross_attn", dke)
         dqe = self.bert_bwd(da1, t["attn1"], p + "encoder.attn", dke)
+        if t["site_qe"] is not None:
+            self.dropout_(dqe, site=t["site_qe"])
+            self.dropout_(dke, site=t["site_ke"])
         dq_feats = self.lin_bwd(dqe, t["q_feats"], p + "embedding.weight", p + "embedding.bias")
         self.lin_bwd(dke, t["pt_feats"], p + "embedding.weight", p + "embedding.bias", out=dpt_feats, acc=True)
         return dq_feats, dq_xyz
@@ -423,6 +479,9 @@ class HeadTrainer:
         `neighbours` (NB-1, 2, B, 799, 32): test hook, use these 32-NN sets instead of searching."""
         d = self.dims
         tn.call("poem_tr_round_tf32", self.p_flat, self.pr_flat, self.p_flat.numel())      # this step's operand copy of the weights
+        if self.p_drop > 0.0:
+            self.seed_dev.add_(1)                                   # fresh masks every step (also under CUDA-graph replay)
+        self._site, self.drop_sites = 0, {}
         views = [int(v) for v in np.asarray(img_metas["cam_view_num"]).reshape(-1)]
         B = len(views)
         Q, P, D = d.n_query, d.n_sample, d.embed_dims

@@ -17,3 +17,4 @@ run hrnet 400 tests/test_hrnet_gpu.py
 run model 400 tests/test_model_gpu.py
 run metrics 200 tests/test_metrics_gpu.py
 run parametric 300 tests/test_parametric_gpu.py
+run train 600 tests/test_train_gpu.py

@@ -6,6 +6,11 @@ bash scripts/gpu_check.sh 2>&1 | grep -E "==|passed|failed"
 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_reference.json 2>/dev/null; echo "reference rc=$?"
 python scripts/bench_small_batch.py > gpurun_out/r2_small_batch.json 2>/dev/null
+# training path: the step line, eager-vs-graph table, live per-primitive profile, launch list
+python bench.py --train-only > gpurun_out/r2_bench_train.json 2> gpurun_out/r2_bench_train.err; echo "train bench rc=$?"
+bash scripts/train_gpu_checks.sh > gpurun_out/r2_train_checks.log 2>&1; echo "train checks rc=$?"
+POEM_TRAIN_PROF=1 python scripts/bench_train.py medium 8 32 > gpurun_out/r2_train_profile_b32.txt 2>&1
+bash scripts/ncu_train.sh 32 > /dev/null 2>&1; bash scripts/ncu_train.sh 4 > /dev/null 2>&1; echo "train launch lists rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
   python bench.py --lean --steps 2 --warmup 1 --no-graph --min-timed-s 0.01 > gpurun_out/r2_bench_under_ncu.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/r2_launches.csv)"
