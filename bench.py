@@ -375,8 +375,6 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
     B = gb // world
     dims = release_dims(size)
     sd = synth.make_state_dict(dims, 0, "init")
-    tr = HeadTrainer(dims, sd, synth.standin_template(), device=dev)
-    step = TrainStep(tr, lr=1e-4, max_norm=1.0, graph=True)
     feat, metas, ref_j = synth.make_inputs(dims, B, [V] * B, 100 + rank)
     m = dict(metas)
     m["cam_intr"], m["cam_extr"] = metas["cam_intr"].to(dev), metas["cam_extr"].to(dev)
@@ -385,26 +383,37 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
     gt_j = (ref_j.cpu() + 0.002 * torch.randn(ref_j.shape, generator=g)).to(dev)
     gt_v = (ref_j.cpu()[:, 9:10] + 0.05 * torch.randn(B, 778, 3, generator=g)).to(dev)
     lib = tn.load()
-    losses = []
-    for _ in range(warmup):
-        losses.append(step(feat, m, ref_j, gt_j, gt_v))
-    sync()
-    l0 = lib.poem_tr_kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        losses.append(step(feat, m, ref_j, gt_j, gt_v))
-    e1.record()
-    sync()
-    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
-    vals = [float(l_.item()) for l_ in losses]
+
+    def run(p_drop):
+        tr = HeadTrainer(dims, sd, synth.standin_template(), device=dev, dropout=p_drop)
+        tr.manual_seed(1234 + rank)
+        step = TrainStep(tr, lr=1e-4, max_norm=1.0, graph=True)
+        ls = []
+        for _ in range(warmup):
+            ls.append(step(feat, m, ref_j, gt_j, gt_v))
+        sync()
+        l0 = lib.poem_tr_kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ls.append(step(feat, m, ref_j, gt_j, gt_v))
+        e1.record()
+        sync()
+        ms_ = max_over_ranks(e0.elapsed_time(e1) / steps)
+        out = (ms_, [float(l_.item()) for l_ in ls], int(step.allreduce_bytes), int((lib.poem_tr_kernel_launches() - l0) / steps))
+        del step, tr
+        torch.cuda.empty_cache()
+        return out
+    ms0, _, _, _ = run(0.0)                               # eval-mode arithmetic (what the gradient goldens pin)
+    ms, vals, ar_bytes, outside = run(0.1)                # TRANSFORMER.DROPOUT of config/release/train_medium*.yaml
     return {"workload": f"training step of the decoder head, POEM-{size}, {V} views, GLOBAL batch {gb} (BASELINE configs[3] "
-                        f"without the MANO tail): forward + 3-D loss + backward + clip + Adam",
+                        f"without the MANO tail), dropout 0.1: forward + 3-D loss + backward + clip + Adam",
+            "dropout": 0.1, "ms_per_step_without_dropout": ms0, "samples_per_s_without_dropout": gb / ms0 * 1e3,
             "samples_per_s": gb / ms * 1e3, "ms_per_step": ms, "steps": steps, "warmup": warmup, "global_batch": gb,
             "batch_per_gpu": B, "views": V, "dtype": "tf32 tensor cores, fp32 storage",
-            "allreduce_bytes_per_step": int(step.allreduce_bytes), "collective": "NCCL all-reduce (AVG) of 4 gradient buckets"
-            if world > 1 else None, "kernels_per_step_in_graph_capture": None,
-            "kernel_launches_outside_graph_per_step": int((lib.poem_tr_kernel_launches() - l0) / steps),
+            "allreduce_bytes_per_step": ar_bytes, "collective": "NCCL all-reduce (AVG) of 4 gradient buckets"
+            if world > 1 else None,
+            "kernel_launches_outside_graph_per_step": outside,
             "launch": "CUDA-graph replay (forward + loss + backward), eager clip + Adam", "loss_first": vals[0], "loss_last": vals[-1],
             "finite": bool(all(math.isfinite(v) for v in vals)),
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
