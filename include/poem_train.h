@@ -138,6 +138,23 @@ int poem_tr_adam(float* p, const float* g, float* m, float* v, long long n, floa
 int poem_tr_coord_loss(const float* coords, const float* gt_joints, const float* gt_verts, int n_blocks, int B,
                        int n_joints, int n_verts, float w_joints, float w_verts, float* loss, float* dcoords, void* stream);
 
+/* Parametric (medium_MANO) tail of the last block, pt_metro_transformer.py:139-151 (forward as in poem_parametric_tail of
+ * poem_b200.h, on raw fp32 parameter pointers) and its backward.  MANO constants with the blend axis first: v_template
+ * [778*3], shapedirs [10][778*3], posedirs [135][778*3], j_regressor [16][778], skin_weights [778][16].
+ * forward: feats [B, Q, D] (re-interpreted as (B*D, Q) rows like the reference) -> flat [B*D] (kept for the backward),
+ * coords [B, Q, 3] (metric, root-centred on center_idx, + the sample's hand centre ref_joints[:, 9]), pose [B, 48], shape [B, 10].
+ * backward: dcoords (+ dpose / dshape or NULL) -> dfeats [B, Q, D] written, dflat [B*D] scratch; dflat_w [Q], dflat_b [1],
+ * dlin_w [106, D], dlin_b [106] += . */
+int poem_tr_mano_tail(const float* feats, const float* flat_w, const float* flat_b, const float* lin_w, const float* lin_b,
+                      const float* v_template, const float* shapedirs, const float* posedirs, const float* j_regressor,
+                      const float* skin_weights, const float* ref_joints, int center_idx, int B, int Q, int D, float* flat,
+                      float* coords, float* pose, float* shape, void* stream);
+int poem_tr_mano_tail_bwd(const float* feats, const float* flat_w, const float* lin_w, const float* lin_b,
+                          const float* v_template, const float* shapedirs, const float* posedirs, const float* j_regressor,
+                          const float* skin_weights, int center_idx, int B, int Q, int D, const float* flat,
+                          const float* dcoords, const float* dpose, const float* dshape, float* dflat, float* dfeats,
+                          float* dflat_w, float* dflat_b, float* dlin_w, float* dlin_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

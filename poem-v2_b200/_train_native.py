@@ -10,7 +10,7 @@ from . import _native as _nat
 CSRC = _nat.CSRC
 LIB_PATH = os.environ.get("POEM_TRAIN_LIB", os.path.join(CSRC, "libpoem_train.so"))
 SOURCES = ["poem_train.cu"]
-HEADERS = ["common.cuh", "tgemm.cuh", "train_simt.cuh"]
+HEADERS = ["common.cuh", "tgemm.cuh", "train_simt.cuh", "mano.cuh", "mano_bwd.cuh"]
 
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 
@@ -56,6 +56,8 @@ SIGNATURES = {
     "poem_tr_seg_clip": [_P, _P, _P, _I, _P, _F, _P],
     "poem_tr_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "poem_tr_coord_loss": [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
+    "poem_tr_mano_tail": [_P] * 11 + [_I, _I, _I, _I] + [_P] * 4 + [_P],
+    "poem_tr_mano_tail_bwd": [_P] * 9 + [_I, _I, _I, _I] + [_P] * 10 + [_P],
 }
 EXPORTS = ["poem_tr_abi_version", "poem_tr_last_error", "poem_tr_kernel_launches"] + list(SIGNATURES)
 

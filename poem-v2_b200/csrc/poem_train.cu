@@ -13,6 +13,7 @@
 #include "../../include/poem_train.h"
 #include "tgemm.cuh"
 #include "train_simt.cuh"
+#include "mano_bwd.cuh"
 
 using namespace poem;
 
@@ -474,5 +475,44 @@ extern "C" int poem_tr_coord_loss(const float* coords, const float* gt_joints, c
 extern "C" int poem_tr_round_tf32(const float* x, float* y, long long n, void* stream) {
   tr_round_tf32_kernel<<<grid_for(n), 256, 0, ST>>>(x, y, n);
   TR_CHECK("round_tf32");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ parametric (MANO) tail
+extern "C" int poem_tr_mano_tail(const float* feats, const float* flat_w, const float* flat_b, const float* lin_w,
+                                 const float* lin_b, const float* v_template, const float* shapedirs, const float* posedirs,
+                                 const float* j_regressor, const float* skin_weights, const float* ref_joints, int center_idx,
+                                 int B, int Q, int D, float* flat, float* coords, float* pose, float* shape, void* stream) {
+  if (Q != 21 + kManoVerts) return fail(POEM_TR_E_BADARG, "mano_tail: Q = %d, expected 799", Q);
+  const int rows = B * D;
+  flat_verts_kernel<<<(rows * 32 + 255) / 256, 256, 0, ST>>>(feats, flat_w, flat_b, flat, Q, rows);
+  TR_CHECK("flat_verts");
+  ManoTailArgs a;
+  a.lin_w = lin_w, a.lin_b = lin_b, a.v_template = v_template, a.shapedirs = shapedirs, a.posedirs = posedirs;
+  a.j_regressor = j_regressor, a.skin_weights = skin_weights, a.flat = flat, a.ref_joints = ref_joints;
+  a.coords = coords, a.pose_out = pose, a.shape_out = shape, a.D = D, a.center_idx = center_idx;
+  mano_tail_kernel<<<B, kManoThreads, 0, ST>>>(a);
+  TR_CHECK("mano_tail");
+  return 0;
+}
+extern "C" int poem_tr_mano_tail_bwd(const float* feats, const float* flat_w, const float* lin_w, const float* lin_b,
+                                     const float* v_template, const float* shapedirs, const float* posedirs,
+                                     const float* j_regressor, const float* skin_weights, int center_idx, int B, int Q, int D,
+                                     const float* flat, const float* dcoords, const float* dpose, const float* dshape,
+                                     float* dflat, float* dfeats, float* dflat_w, float* dflat_b, float* dlin_w, float* dlin_b,
+                                     void* stream) {
+  if (Q != 21 + kManoVerts) return fail(POEM_TR_E_BADARG, "mano_tail_bwd: Q = %d, expected 799", Q);
+  ManoTailBwdArgs a;
+  a.lin_w = lin_w, a.lin_b = lin_b, a.v_template = v_template, a.shapedirs = shapedirs, a.posedirs = posedirs;
+  a.j_regressor = j_regressor, a.skin_weights = skin_weights, a.flat = flat, a.dcoords = dcoords, a.dpose = dpose;
+  a.dshape = dshape, a.dflat = dflat, a.dlin_w = dlin_w, a.dlin_b = dlin_b, a.D = D, a.center_idx = center_idx;
+  mano_tail_bwd_kernel<<<B, kManoThreads, 0, ST>>>(a);
+  TR_CHECK("mano_tail_bwd");
+  const int rows = B * D;
+  int slabs = (rows + 63) / 64;
+  if (slabs > 4 * num_sms()) slabs = 4 * num_sms();
+  dim3 grid((Q + 31) / 32, slabs), block(32, 8);
+  tr_flat_verts_bwd_kernel<<<grid, block, 0, ST>>>(dflat, feats, flat_w, dfeats, dflat_w, dflat_b, Q, rows);
+  TR_CHECK("flat_verts_bwd");
   return 0;
 }

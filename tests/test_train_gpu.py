@@ -775,3 +775,58 @@ def test_head_backward_with_dropout_matches_oracle_on_the_same_masks(tn):
     c1 = tr.forward(feat.cuda(), _cuda_metas(metas), ref_j.cuda()).clone()
     c2 = tr.forward(feat.cuda(), _cuda_metas(metas), ref_j.cuda())
     assert (c1 - c2).abs().max().item() > 0
+
+
+def _mano_device_tensors(mano):
+    """MANO constants in the kernels' layout (blend axis first), as PackedManoTail lays them out."""
+    return dict(v_template=dev(mano["v_template"].reshape(778 * 3).float()),
+                shapedirs=dev(mano["shapedirs"].reshape(778 * 3, 10).t().float()),
+                posedirs=dev(mano["posedirs"].reshape(778 * 3, 135).t().float()),
+                j_regressor=dev(mano["J_regressor"].reshape(16, 778).float()),
+                skin_weights=dev(mano["weights"].reshape(778, 16).float()))
+
+
+def test_mano_tail_forward_and_backward_match_oracle_autograd(tn):
+    """Parametric tail of medium_MANO (pt_metro_transformer.py:139-151): flat_verts -> mano_linear -> 6-D rotations ->
+    axis-angle -> MANO linear-blend skinning -> root-centred joints | vertices.  Forward and the hand-written backward
+    (dual numbers for the rotation chain, reverse skinning / kinematic chain) against fp64 autograd through the oracle."""
+    orc, synth, release_dims = _oracle_modules()
+    dims = release_dims("medium_MANO")
+    D, Q, B = dims.embed_dims, dims.n_query, 3
+    g = torch.Generator().manual_seed(17)
+    f64 = dict(generator=g, dtype=torch.float64)
+    mano = {k: v.double() for k, v in synth.synthetic_mano(11).items()}
+    i = dims.n_blocks - 1
+    p = f"transformer.pt_metro_encoder.{i}."
+    ident6 = torch.tensor([1.0, 0, 0, 0, 1.0, 0], dtype=torch.float64).repeat(16)
+    sd = {p + "flat_verts.weight": (torch.randn(1, Q, **f64) / math.sqrt(Q)).requires_grad_(),
+          p + "flat_verts.bias": (0.1 * torch.randn(1, **f64)).requires_grad_(),
+          p + "mano_linear.weight": (0.6 * torch.randn(106, D, **f64) / math.sqrt(D)).requires_grad_(),
+          p + "mano_linear.bias": (torch.cat([ident6, torch.zeros(10, dtype=torch.float64)]) + 0.3 * torch.randn(106, **f64)).requires_grad_()}
+    feats = torch.randn(B, Q, D, **f64).requires_grad_()
+    ref_j = 0.1 * torch.randn(B, 21, 3, **f64)
+    xyz, pose, betas = orc.parametric_tail(sd, i, dims, feats, torch.zeros(B, Q, 3, dtype=torch.float64), mano)
+    coords = xyz + ref_j[:, 9:10]
+    gc, gp, gs = torch.randn(B, Q, 3, **f64), torch.randn(B, 48, **f64), torch.randn(B, 10, **f64)
+    ((coords * gc).sum() + (pose * gp).sum() + (betas * gs).sum()).backward()
+    # device
+    fl = lambda t_: dev(t_.detach().float())  # noqa: E731
+    md = _mano_device_tensors(mano)
+    fd, fw, fb, lw, lb = fl(feats), fl(sd[p + "flat_verts.weight"].reshape(-1)), fl(sd[p + "flat_verts.bias"]), \
+        fl(sd[p + "mano_linear.weight"]), fl(sd[p + "mano_linear.bias"])
+    flat, cd, pd, sh = torch.empty(B * D).cuda(), torch.empty(B, Q, 3).cuda(), torch.empty(B, 48).cuda(), torch.empty(B, 10).cuda()
+    tn.call("poem_tr_mano_tail", fd, fw, fb, lw, lb, md["v_template"], md["shapedirs"], md["posedirs"], md["j_regressor"],
+            md["skin_weights"], fl(ref_j), dims.center_idx, B, Q, D, flat, cd, pd, sh)
+    close(cd, coords.detach(), 1e-4)
+    close(pd, pose.detach(), 1e-4)
+    close(sh, betas.detach(), 1e-5)
+    dflat, dfeats = torch.empty(B * D).cuda(), torch.empty(B, Q, D).cuda()
+    dfw, dfb, dlw, dlb = torch.zeros(Q).cuda(), torch.zeros(1).cuda(), torch.zeros(106, D).cuda(), torch.zeros(106).cuda()
+    tn.call("poem_tr_mano_tail_bwd", fd, fw, lw, lb, md["v_template"], md["shapedirs"], md["posedirs"], md["j_regressor"],
+            md["skin_weights"], dims.center_idx, B, Q, D, flat, fl(gc), fl(gp), fl(gs), dflat, dfeats, dfw, dfb, dlw, dlb)
+    torch.cuda.synchronize()
+    for name, got, want in (("feats", dfeats, feats.grad), ("flat_verts.weight", dfw, sd[p + "flat_verts.weight"].grad.reshape(-1)),
+                            ("flat_verts.bias", dfb, sd[p + "flat_verts.bias"].grad), ("mano_linear.weight", dlw, sd[p + "mano_linear.weight"].grad),
+                            ("mano_linear.bias", dlb, sd[p + "mano_linear.bias"].grad)):
+        e = rel_l2(got.cpu(), want)
+        assert e <= 2e-4, (name, e)
