@@ -208,10 +208,16 @@ class POEM_Generalized_Head(_NativeDecoder):
             from .train import HeadTrainer
             if dev.type != "cuda":
                 raise nat.PoemError("training needs the module on a CUDA device: there is no CPU implementation")
+            if self.dims.parametric and self._mano is None:
+                self._mano = _resolve_mano(self.dims, None)
             if self._template is None:
-                self._template = _resolve_template(self.dims, None)
+                if self.dims.parametric:
+                    self._template = mano_zero_pose_template(self._mano, self.dims.center_idx)
+                else:
+                    self._template = _resolve_template(self.dims, None)
             tr = HeadTrainer(self.dims, self.live_state(), self._template,
-                             assets=(self.bps_points, self.anchor_xyz, self.anchor_idx), device=dev)
+                             assets=(self.bps_points, self.anchor_xyz, self.anchor_idx), device=dev,
+                             mano=self._mano if self.dims.parametric else None)
             named = dict(self.named_parameters())
             for k in tr.p:
                 named[k[len(self._key_prefix):]].data = tr.p[k]
@@ -225,8 +231,10 @@ class POEM_Generalized_Head(_NativeDecoder):
             assert int(np.sum(np.asarray(img_metas["master_id"]))) == 0, "only support master_id is 0"
             _require_cuda(mlvl_feat, "mlvl_feat")
             tr = self.trainer()
-            coords = HeadFunction.apply(tr, mlvl_feat, img_metas, reference_joints, *self._trainer_params)
-            return {"all_coords_preds": coords}
+            out = HeadFunction.apply(tr, mlvl_feat, img_metas, reference_joints, *self._trainer_params)
+            if self.dims.parametric:
+                return {"all_coords_preds": out[0], "pred_pose": out[1].view(-1, 16, 3), "pred_shape": out[2]}
+            return {"all_coords_preds": out}
         return self._forward_eval(mlvl_feat, img_metas, reference_joints, **kwargs)
 
     @torch.no_grad()

@@ -15,8 +15,8 @@ per-edge tensors of the vector attention (B*799*32*D per layer) stay in HBM betw
 
 Dropout (TRANSFORMER.DROPOUT, 0.1 in the release configs: on both embedding outputs, after the two attention output
 projections and the FFN output projection, and on the attention probabilities) is counter-based — masks are regenerated
-in the backward from a device seed, nothing is stored.  Not covered (raises / documented in DESIGN.md): the parametric
-MANO tail, D = 1024.
+in the backward from a device seed, nothing is stored.  The parametric MANO tail of medium_MANO (flat_verts, mano_linear, 6-D rotations ->
+axis-angle, MANO skinning) has its backward too (csrc/mano_bwd.cuh).  Not covered: D = 1024.
 """
 import math
 
@@ -46,11 +46,12 @@ class HeadTrainer:
         dfeat = tr.backward(dcoords)                                     # d loss / d mlvl_feat ; tr.g[name] += d loss / d p
     """
 
-    def __init__(self, dims: HeadDims, state_dict, template, assets=None, device="cuda", dropout=None):
+    def __init__(self, dims: HeadDims, state_dict, template, assets=None, device="cuda", dropout=None, mano=None):
         """dropout: probability of the BERT layers' hidden / attention-probability dropout (None: dims.dropout, i.e.
-        TRANSFORMER.DROPOUT of the config; 0 = the eval-mode arithmetic the gradient goldens are pinned on)."""
-        if dims.parametric:
-            raise NotImplementedError("training path: the parametric MANO tail has no backward yet")
+        TRANSFORMER.DROPOUT of the config; 0 = the eval-mode arithmetic the gradient goldens are pinned on).
+        mano: MANO model parameters (v_template, shapedirs, posedirs, J_regressor, weights) for a PARAMETRIC_OUTPUT head."""
+        if dims.parametric and mano is None:
+            raise ValueError("parametric (medium_MANO) head: pass the MANO model parameters, mano={v_template, shapedirs, ...}")
         if dims.embed_dims > 512 or dims.n_neighbor != NBR:
             raise ValueError("training path: embed_dims <= 512 and 32 neighbours")
         self.dims, self.dev = dims, torch.device(device)
@@ -89,6 +90,15 @@ class HeadTrainer:
         self.anchor_xyz = a_xyz.to(self.dev, torch.float32).contiguous()
         self.anchor_idx = a_idx.to(self.dev, torch.int32).contiguous()
         self.template = torch.as_tensor(template, dtype=torch.float32).reshape(dims.n_query, 3).to(self.dev).contiguous()
+        self.mano = None
+        if dims.parametric:                       # kernel layout: blend axis first (as pack.PackedManoTail)
+            f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()  # noqa: E731
+            self.mano = dict(v_template=f32(mano["v_template"].reshape(778 * 3)),
+                             shapedirs=f32(mano["shapedirs"].reshape(778 * 3, 10).t()),
+                             posedirs=f32(mano["posedirs"].reshape(778 * 3, 135).t()),
+                             j_regressor=f32(mano["J_regressor"].reshape(16, 778)),
+                             skin_weights=f32(mano["weights"].reshape(778, 16)))
+        self.pred_pose = self.pred_shape = None
         self.tape = None
         self.last_neighbours = None
         self.p_drop = float(dims.dropout if dropout is None else dropout)
@@ -513,12 +523,22 @@ class HeadTrainer:
             blocks.append(tb)
             if nb is not None:
                 nbs.append(nb)
-            tn.call("poem_tr_affine_rows", q_xyz, centre, d.radius, coords[i], B * Q, Q, B, 3)
+            if not (d.parametric and i == d.n_blocks - 1):
+                tn.call("poem_tr_affine_rows", q_xyz, centre, d.radius, coords[i], B * Q, Q, B, 3)
         self.last_neighbours = torch.stack(nbs) if nbs else None
         self.tape = dict(head=t_head, blocks=blocks, B=B)
+        if d.parametric:        # pt_metro_transformer.py:139-151,194-195: the last block's mesh comes from the MANO layer
+            pl = f"transformer.pt_metro_encoder.{d.n_blocks - 1}."
+            m = self.mano
+            flat, self.pred_pose, self.pred_shape = self.new(B * D), self.new(B, 48), self.new(B, 10)
+            tn.call("poem_tr_mano_tail", q_feats, self.p[pl + "flat_verts.weight"], self.p[pl + "flat_verts.bias"],
+                    self.p[pl + "mano_linear.weight"], self.p[pl + "mano_linear.bias"], m["v_template"], m["shapedirs"],
+                    m["posedirs"], m["j_regressor"], m["skin_weights"], refj, d.center_idx, B, Q, D, flat,
+                    coords[d.n_blocks - 1], self.pred_pose, self.pred_shape)
+            self.tape["tail"] = dict(feats=q_feats, flat=flat)
         return coords
 
-    def backward(self, dcoords, on_bucket_done=None):
+    def backward(self, dcoords, on_bucket_done=None, dpose=None, dshape=None):
         """dcoords (NB, B, 799, 3): d loss / d all_coords_preds.  Accumulates into `g`, returns d loss / d mlvl_feat.
         `on_bucket_done(name)`: called when every gradient of bucket `name` ("2", "1", "0", then "head") is final, so a
         data-parallel caller can start that bucket's all-reduce while the rest of the backward runs."""
@@ -530,9 +550,22 @@ class HeadTrainer:
         dc = dcoords.detach().to(self.dev, torch.float32).contiguous()
         dpt = self.zeros(B * P, D)
         dfe, dxyz_next = None, None
+        if d.parametric:        # MANO tail: d coords[-1] (and d pose / d shape of the parameter losses) -> d features of the last block
+            pl = f"transformer.pt_metro_encoder.{d.n_blocks - 1}."
+            m, tt = self.mano, self.tape["tail"]
+            f32 = lambda t: None if t is None else t.detach().to(self.dev, torch.float32).contiguous()  # noqa: E731
+            dfe, dflat = self.new(B * Q, D), self.new(B * D)
+            tn.call("poem_tr_mano_tail_bwd", tt["feats"], self.p[pl + "flat_verts.weight"], self.p[pl + "mano_linear.weight"],
+                    self.p[pl + "mano_linear.bias"], m["v_template"], m["shapedirs"], m["posedirs"], m["j_regressor"],
+                    m["skin_weights"], d.center_idx, B, Q, D, tt["flat"], dc[d.n_blocks - 1].reshape(B * Q, 3), f32(dpose),
+                    f32(dshape), dflat, dfe, self.g[pl + "flat_verts.weight"], self.g[pl + "flat_verts.bias"],
+                    self.g[pl + "mano_linear.weight"], self.g[pl + "mano_linear.bias"])
         for i in reversed(range(d.n_blocks)):
             dxyz = self.new(B * Q, 3)
-            tn.call("poem_tr_affine_rows", dc[i].reshape(B * Q, 3), None, d.radius, dxyz, B * Q, Q, B, 3)
+            if d.parametric and i == d.n_blocks - 1:
+                dxyz.zero_()                                   # the last block's own coordinates are overwritten by the MANO mesh
+            else:
+                tn.call("poem_tr_affine_rows", dc[i].reshape(B * Q, 3), None, d.radius, dxyz, B * Q, Q, B, 3)
             if dxyz_next is not None:
                 tn.call("poem_tr_axpy", dxyz, dxyz_next, 1.0, dxyz.numel())
             dfe, dxyz_next = self.block_bwd(i, self.tape["blocks"][i], dfe, dxyz, dpt, B)
@@ -676,11 +709,14 @@ class HeadFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, trainer, mlvl_feat, img_metas, reference_joints, *params):
         ctx.trainer = trainer
-        return trainer.forward(mlvl_feat, img_metas, reference_joints)
+        coords = trainer.forward(mlvl_feat, img_metas, reference_joints)
+        if trainer.dims.parametric:          # medium_MANO: pred_pose / pred_shape carry the parameter losses' gradients
+            return coords, trainer.pred_pose, trainer.pred_shape
+        return coords
 
     @staticmethod
-    def backward(ctx, dcoords):
+    def backward(ctx, dcoords, dpose=None, dshape=None):
         tr = ctx.trainer
         tr.zero_grad()
-        dfeat = tr.backward(dcoords)
+        dfeat = tr.backward(dcoords, dpose=dpose, dshape=dshape)
         return (None, dfeat, None, None) + tuple(tr.g[k].clone() for k in tr.p)

@@ -830,3 +830,68 @@ def test_mano_tail_forward_and_backward_match_oracle_autograd(tn):
                             ("mano_linear.bias", dlb, sd[p + "mano_linear.bias"].grad)):
         e = rel_l2(got.cpu(), want)
         assert e <= 2e-4, (name, e)
+
+
+def test_parametric_head_backward_matches_oracle_autograd(tn):
+    """PARAMETRIC_OUTPUT head (medium_MANO's structure at POEM-small width): decoder + MANO tail, gradients of every
+    parameter (incl. flat_verts / mano_linear of the last block) and of mlvl_feat against oracle autograd, with losses on the
+    coordinates, the predicted pose and the predicted shape."""
+    from dataclasses import replace
+    from poem_v2_b200.pack import mano_zero_pose_template
+    from poem_v2_b200.train import HeadTrainer
+    orc, synth, release_dims = _oracle_modules()
+    dims = replace(release_dims("small"), parametric=True)
+    views = [2, 1]
+    mano = synth.synthetic_mano(11)
+    sd = synth.make_state_dict(dims, 4, "init")
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 3)
+    bps, a_xyz, a_idx = synth.load_assets()
+    template = mano_zero_pose_template(mano, dims.center_idx)
+    tr = HeadTrainer(dims, sd, template, mano=mano)
+    coords = tr.forward(feat.cuda(), _cuda_metas(metas), ref_j.cuda())
+    torch.cuda.synchronize()
+    nbr = tr.last_neighbours.long().cpu()
+    P_, th, masks, r0 = dims.n_sample, tr.tape["head"], [], 0
+    for b_, n in enumerate(views):
+        h0 = (th["h0"][r0:r0 + P_ * n] > 0).float().cpu()
+        masks.append(h0.view(1, P_, n, -1) if n > 1 else h0.view(1, P_, -1))
+        masks.append((th["h1"][b_ * P_:(b_ + 1) * P_] > 0).float().cpu().view(1, P_, -1))
+        r0 += P_ * n
+    Bn, Qn = len(views), dims.n_query
+    for tb in tr.tape["blocks"]:
+        for core in ("core_s", "core_c"):
+            masks.append((tb[core]["hd"] > 0).float().cpu().view(Bn, Qn, 32, -1))
+            masks.append((tb[core]["hg"] > 0).float().cpu().view(Bn, Qn, 32, -1))
+        masks.append((tb["r"] > 0).float().cpu().view(Bn, Qn, -1))
+    sdo = {k: (v.clone().requires_grad_(True) if k in tr.p else v) for k, v in sd.items()}
+    feato = feat.clone().requires_grad_(True)
+    with _tf32_oracle(orc, masks):
+        want, pose, betas = orc.head_forward(sdo, dims, feato, metas, ref_j, template, bps, a_xyz, a_idx, neighbours=nbr, mano=mano)
+    err = (coords.cpu() - want.detach()).norm(dim=-1)
+    print(f"parametric train forward vs TF32-operand oracle: blocks 0..NB-2 mean {err[:-1].mean().item() * 1e3:.4f} mm, "
+          f"MANO mesh mean {err[-1].mean().item() * 1e3:.4f} mm; pose max {(tr.pred_pose.cpu() - pose.reshape(-1, 48).detach()).abs().max().item():.2e}")
+    assert err[:-1].mean().item() <= 5e-5 and err[-1].mean().item() <= 3e-4
+    g = torch.Generator().manual_seed(5)
+    gc = torch.randn(want.shape, generator=g) * 1e3
+    gp, gs = torch.randn(Bn, 48, generator=g), torch.randn(Bn, 10, generator=g)
+    ((want * gc).sum() + (pose.reshape(Bn, 48) * gp).sum() + (betas * gs).sum()).backward()
+    dfeat = tr.backward(gc.cuda(), dpose=gp.cuda(), dshape=gs.cuda())
+    torch.cuda.synchronize()
+    worst = {}
+    for k in tr.p:
+        ref = sdo[k].grad
+        got = tr.g[k].cpu()
+        if ref is None or ref.abs().max().item() == 0:
+            assert got.abs().max().item() == 0, k
+            continue
+        if k.endswith("self.key.bias") or k.endswith("fc_gamma.2.bias"):
+            continue
+        worst[k] = rel_l2(got, ref)
+    worst["mlvl_feat"] = rel_l2(dfeat.cpu(), feato.grad)
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    print("parametric train backward vs oracle autograd, worst rel-L2:", [(k.replace("transformer.pt_metro_encoder.", "b"), f"{v:.2e}") for k, v in top])
+    last = f"transformer.pt_metro_encoder.{dims.n_blocks - 1}."
+    for k in (last + "flat_verts.weight", last + "mano_linear.weight", last + "encoder.output.dense.weight"):
+        assert k in worst, k                                  # the tail and the last block's FFN now carry gradient
+    assert max(worst.values()) <= 5e-2, top
+    assert sorted(worst.values())[len(worst) // 2] <= 1e-2
