@@ -360,12 +360,12 @@ def image_sharded_pass(dev, rank, world, sync, max_over_ranks, V=8, steps=20):
             "finite": ok, "launch": "eager launches"}
 
 
-def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium", steps=5, warmup=2):
-    """SURVEY §8 f3 / BASELINE configs[3]: one optimisation step of the decoder head — zero_grad, forward with saved
+def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium_MANO", steps=5, warmup=2):
+    """SURVEY §8 f3 / BASELINE configs[3] (medium_MANO): one optimisation step of the decoder head — zero_grad, forward with saved
     activations, 3-D loss, hand-written backward, NCCL average of the gradient buckets (N > 1, overlapped with the
     backward), per-tensor clip, Adam — at a FIXED global batch (strong scaling), every rank on gb / N samples.
-    POEM-medium (the MANO tail of medium_MANO has no backward yet).  Inputs resident on the device; CUDA-graph replay of
-    forward + loss + backward."""
+    POEM-medium_MANO (decoder + parametric MANO tail, stand-in MANO parameters), dropout 0.1 as in the release config.
+    Inputs resident on the device; CUDA-graph replay of forward + loss + backward."""
     from poem_v2_b200 import _train_native as tn
     from poem_v2_b200 import synth
     from poem_v2_b200.config import release_dims
@@ -375,6 +375,12 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
     B = gb // world
     dims = release_dims(size)
     sd = synth.make_state_dict(dims, 0, "init")
+    mano = synth.synthetic_mano(11) if dims.parametric else None
+    if dims.parametric:
+        from poem_v2_b200.pack import mano_zero_pose_template
+        template = mano_zero_pose_template(mano, dims.center_idx)
+    else:
+        template = synth.standin_template()
     feat, metas, ref_j = synth.make_inputs(dims, B, [V] * B, 100 + rank)
     m = dict(metas)
     m["cam_intr"], m["cam_extr"] = metas["cam_intr"].to(dev), metas["cam_extr"].to(dev)
@@ -385,7 +391,7 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
     lib = tn.load()
 
     def run(p_drop):
-        tr = HeadTrainer(dims, sd, synth.standin_template(), device=dev, dropout=p_drop)
+        tr = HeadTrainer(dims, sd, template, device=dev, dropout=p_drop, mano=mano)
         tr.manual_seed(1234 + rank)
         step = TrainStep(tr, lr=1e-4, max_norm=1.0, graph=True)
         ls = []
@@ -406,8 +412,8 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
         return out
     ms0, _, _, _ = run(0.0)                               # eval-mode arithmetic (what the gradient goldens pin)
     ms, vals, ar_bytes, outside = run(0.1)                # TRANSFORMER.DROPOUT of config/release/train_medium*.yaml
-    return {"workload": f"training step of the decoder head, POEM-{size}, {V} views, GLOBAL batch {gb} (BASELINE configs[3] "
-                        f"without the MANO tail), dropout 0.1: forward + 3-D loss + backward + clip + Adam",
+    return {"workload": f"training step of the decoder head, POEM-{size}, {V} views, GLOBAL batch {gb} (BASELINE configs[3]: "
+                        f"decoder + MANO tail), dropout 0.1: forward + 3-D loss terms + backward + clip + Adam",
             "dropout": 0.1, "ms_per_step_without_dropout": ms0, "samples_per_s_without_dropout": gb / ms0 * 1e3,
             "samples_per_s": gb / ms * 1e3, "ms_per_step": ms, "steps": steps, "warmup": warmup, "global_batch": gb,
             "batch_per_gpu": B, "views": V, "dtype": "tf32 tensor cores, fp32 storage",
@@ -584,7 +590,7 @@ def main():
         if rank == 0:
             tline = {"metric": "training samples/sec (decoder head step)", "value": r.get("samples_per_s"), "unit": "samples/s",
                     "n_gpus": n_gpus, "higher_is_better": True, "scaling": "strong", "ms_per_step": r.get("ms_per_step"),
-                     "steps": r.get("steps"), "warmup": r.get("warmup"), "data": "synthetic", "train_medium_v8_gb32": r}
+                     "steps": r.get("steps"), "warmup": r.get("warmup"), "data": "synthetic", "train_medium_mano_v8_gb32": r}
             emit(tline)
         if world > 1:
             dist.destroy_process_group()
@@ -725,7 +731,7 @@ def main():
             if world > 1:
                 named["image_sharded_b1_v8"] = image_sharded_pass(dev, rank, world, barrier, max_over_ranks)
             torch.cuda.empty_cache()
-            named["train_medium_v8_gb32"] = train_step_pass(dev, rank, world, barrier, max_over_ranks)
+            named["train_medium_mano_v8_gb32"] = train_step_pass(dev, rank, world, barrier, max_over_ranks)
             named["scaling"] = "strong"
             named["launch"] = "CUDA-graph replay of the captured forward, 2 input sets rotated, >= 0.3 s timed per entry"
         except Exception as e:  # noqa: BLE001
