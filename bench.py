@@ -163,6 +163,62 @@ def torch_cuda_reference_pass(size, V, B, steps, warmup, dev, tf32):
     return B / ms * 1e3, ms
 
 
+def torch_cuda_train_reference_pass(size, V, B, dev, steps=2, warmup=1):
+    """Eager PyTorch training step of the same head on the SAME GPU (oracle port + torch.autograd + the 3-D loss terms +
+    per-tensor clip + torch.optim.Adam, TF32 matmuls on, eval-mode arithmetic): the denominator for the training line.
+    The oracle is checker code; it is executed here only as a baseline, never by the product path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import poem_oracle as orc
+    from poem_v2_b200 import synth
+    from poem_v2_b200.config import release_dims
+    dims = release_dims(size)
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(dims, 0).items()}
+    params = [v.requires_grad_(True) for v in sd.values() if v.dtype.is_floating_point]
+    mano = {k: v.to(dev) for k, v in synth.synthetic_mano(11).items()} if dims.parametric else None
+    if dims.parametric:
+        from poem_v2_b200.pack import mano_zero_pose_template
+        tmpl = mano_zero_pose_template(synth.synthetic_mano(11), dims.center_idx).to(dev)
+    else:
+        tmpl = synth.standin_template().to(dev)
+    feat, metas, ref_j = synth.make_inputs(dims, B, V, 1)
+    metas = dict(metas)
+    metas["cam_intr"], metas["cam_extr"] = metas["cam_intr"].to(dev), metas["cam_extr"].to(dev)
+    feat, ref_j = feat.to(dev), ref_j.to(dev)
+    bps, a_xyz, a_idx = [t.to(dev) for t in synth.load_assets()]
+    gt_v = ref_j[:, 9:10] + 0.05 * torch.randn(B, 778, 3, device=dev)
+    opt = torch.optim.Adam(params, lr=1e-4)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+
+    def one():
+        opt.zero_grad(set_to_none=True)
+        out = orc.head_forward(sd, dims, feat, metas, ref_j, tmpl, bps, a_xyz, a_idx, mano=mano)
+        coords = out[0] if dims.parametric else out
+        loss = torch.nn.functional.mse_loss(coords[-1, :, :21], ref_j) + torch.nn.functional.l1_loss(coords[-1, :, 21:], gt_v)
+        loss.backward()
+        for p_ in params:
+            if p_.grad is not None:
+                torch.nn.utils.clip_grad_norm_(p_, 1.0, 2)
+        opt.step()
+    try:
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    ms = e0.elapsed_time(e1) / steps
+    peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del opt, params, sd
+    torch.cuda.empty_cache()
+    return B / ms * 1e3, ms, peak
+
+
 def images_to_mesh_pass(size, V, B, dev, cpu_views, steps=10, warmup=3, eager=False):
     """SURVEY §8d metric (ii): samples/s of the whole evaluation forward (`PtEmbedMultiviewStereoV2._forward_impl`,
     POEM.py:251-333) from images resident in HBM (two image sets alternated, each >> L2), and the oracle port of the
@@ -360,7 +416,8 @@ def image_sharded_pass(dev, rank, world, sync, max_over_ranks, V=8, steps=20):
             "finite": ok, "launch": "eager launches"}
 
 
-def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium_MANO", steps=5, warmup=2):
+def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium_MANO", steps=5, warmup=2,
+                    eager_baseline=True):
     """SURVEY §8 f3 / BASELINE configs[3] (medium_MANO): one optimisation step of the decoder head — zero_grad, forward with saved
     activations, 3-D loss, hand-written backward, NCCL average of the gradient buckets (N > 1, overlapped with the
     backward), per-tensor clip, Adam — at a FIXED global batch (strong scaling), every rank on gb / N samples.
@@ -412,9 +469,23 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
         return out
     ms0, _, _, _ = run(0.0)                               # eval-mode arithmetic (what the gradient goldens pin)
     ms, vals, ar_bytes, outside = run(0.1)                # TRANSFORMER.DROPOUT of config/release/train_medium*.yaml
+    peak_ours = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    eager = None
+    if world == 1 and eager_baseline:
+        try:
+            torch.cuda.reset_peak_memory_stats(dev)
+            # the oracle's MANO layer builds CPU constants: the eager arm runs the decoder without the (negligible) tail
+            sps_e, ms_e, peak_e = torch_cuda_train_reference_pass(size.replace("_MANO", ""), V, min(B, 8), dev)
+            eager = {"what": "eager PyTorch (oracle port of the decoder, no MANO tail, + autograd + clip + torch.optim.Adam, TF32 on, "
+                             "no dropout) on the same GPU",
+                     "batch": min(B, 8), "ms_per_step": ms_e, "samples_per_s": sps_e, "peak_mem_gb": peak_e,
+                     "ours_over_eager": (gb / ms0 * 1e3) / sps_e}
+        except Exception as e:  # noqa: BLE001
+            eager = {"error": repr(e)[:200]}
+        torch.cuda.reset_peak_memory_stats(dev)
     return {"workload": f"training step of the decoder head, POEM-{size}, {V} views, GLOBAL batch {gb} (BASELINE configs[3]: "
                         f"decoder + MANO tail), dropout 0.1: forward + 3-D loss terms + backward + clip + Adam",
-            "dropout": 0.1, "ms_per_step_without_dropout": ms0, "samples_per_s_without_dropout": gb / ms0 * 1e3,
+            "torch_cuda_eager_training": eager, "dropout": 0.1, "ms_per_step_without_dropout": ms0, "samples_per_s_without_dropout": gb / ms0 * 1e3,
             "samples_per_s": gb / ms * 1e3, "ms_per_step": ms, "steps": steps, "warmup": warmup, "global_batch": gb,
             "batch_per_gpu": B, "views": V, "dtype": "tf32 tensor cores, fp32 storage",
             "allreduce_bytes_per_step": ar_bytes, "collective": "NCCL all-reduce (AVG) of 4 gradient buckets"
@@ -422,7 +493,7 @@ def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="me
             "kernel_launches_outside_graph_per_step": outside,
             "launch": "CUDA-graph replay (forward + loss + backward), eager clip + Adam", "loss_first": vals[0], "loss_last": vals[-1],
             "finite": bool(all(math.isfinite(v) for v in vals)),
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            "peak_mem_gb": peak_ours}
 
 
 def image_half_lines(dev, peaks, n_images=256):
