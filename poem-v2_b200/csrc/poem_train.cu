@@ -321,15 +321,17 @@ extern "C" int poem_tr_lin3_relu(const float* rel, const float* W, const float* 
 }
 extern "C" int poem_tr_lin3_bwd(const float* dh, const float* rel, const float* W, float* dW, float* db, float* drel,
                                 long long E, int D, void* stream) {
-  long long blocks = (E + 511) / 512;
-  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  if (D > 1024) return fail(POEM_TR_E_BADARG, "lin3_bwd: D = %d > 1024", D);
+  const int wpb = 8;
+  long long blocks = (E + wpb - 1) / wpb;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
   if (blocks < 1) blocks = 1;
-  tr_lin3_wgrad_kernel<<<(unsigned)blocks, 256, 0, ST>>>(dh, rel, dW, db, E, D);
-  TR_CHECK("lin3_wgrad");
-  if (drel) {
-    tr_lin3_dgrad_kernel<<<grid_for(E * 32), 256, 0, ST>>>(dh, W, drel, E, D);
-    TR_CHECK("lin3_dgrad");
-  }
+  const size_t shb = (size_t)4 * D * 4;
+  if (D <= 128) tr_lin3_bwd_kernel<4><<<(unsigned)blocks, wpb * 32, shb, ST>>>(dh, rel, W, dW, db, drel, E, D);
+  else if (D <= 256) tr_lin3_bwd_kernel<8><<<(unsigned)blocks, wpb * 32, shb, ST>>>(dh, rel, W, dW, db, drel, E, D);
+  else if (D <= 512) tr_lin3_bwd_kernel<16><<<(unsigned)blocks, wpb * 32, shb, ST>>>(dh, rel, W, dW, db, drel, E, D);
+  else tr_lin3_bwd_kernel<32><<<(unsigned)blocks, wpb * 32, shb, ST>>>(dh, rel, W, dW, db, drel, E, D);
+  TR_CHECK("lin3_bwd");
   return 0;
 }
 extern "C" int poem_tr_va_gather_t(const float* q, const float* ktab, const int32_t* gidx, const float* pos, float* t,
@@ -396,8 +398,17 @@ extern "C" int poem_tr_sample(const float* planes, const float* grid, float* S, 
   TR_CHECK("sample");
   return 0;
 }
-extern "C" int poem_tr_sample_bwd(const float* dS, const float* grid, float* dplanes, int NV, int D, int P, int hw, void* stream) {
-  tr_sample_bwd_kernel<<<grid_for((long long)NV * P, 128, 16), 128, 0, ST>>>(dS, grid, dplanes, NV, D, P, hw);
+extern "C" int poem_tr_sample_bwd(const float* dS, const float* grid_, float* dplanes, int NV, int D, int P, int hw, void* stream) {
+  const size_t shb = (size_t)kSbCh * hw * hw * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tr_sample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "sample_bwd smem attribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  if (shb > 200 * 1024) return fail(POEM_TR_E_BADARG, "sample_bwd: feature map %d x %d too large", hw, hw);
+  dim3 grid(NV, (D + kSbCh - 1) / kSbCh);
+  tr_sample_bwd_kernel<<<grid, 512, shb, ST>>>(dS, grid_, dplanes, NV, D, P, hw);
   TR_CHECK("sample_bwd");
   return 0;
 }

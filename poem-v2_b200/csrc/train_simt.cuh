@@ -385,35 +385,56 @@ __global__ void tr_lin3_relu_kernel(const float* rel, const float* W, const floa
     *reinterpret_cast<float4*>(h + e * D + c) = o;
   }
 }
-// backward of the above given dh (already masked by the ReLU):
-//   wgrad: dW[c, k] += sum_e dh[e, c] rel[e, k] ; db[c] += sum_e dh[e, c]      thread = channel, block = edge slab
-//   dgrad: drel[e, k] = sum_c dh[e, c] W[c, k]                                  one warp per edge
-__global__ void tr_lin3_wgrad_kernel(const float* dh, const float* rel, float* dW, float* db, long long E, int D) {
-  const long long per_block = (E + gridDim.x - 1) / gridDim.x;
-  const long long e0 = blockIdx.x * per_block, e1 = min(E, e0 + per_block);
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, bb = 0.f;
-    for (long long e = e0; e < e1; ++e) {
-      const float g = dh[e * D + c];
-      w0 += g * rel[3 * e], w1 += g * rel[3 * e + 1], w2 += g * rel[3 * e + 2], bb += g;
-    }
-    atomicAdd(dW + 3 * c, w0);
-    atomicAdd(dW + 3 * c + 1, w1);
-    atomicAdd(dW + 3 * c + 2, w2);
-    atomicAdd(db + c, bb);
-  }
-}
-__global__ void tr_lin3_dgrad_kernel(const float* dh, const float* W, float* drel, long long E, int D) {
+// backward of the above given dh (already masked by the ReLU), ONE pass over dh:
+//   dW[c, k] += sum_e dh[e, c] rel[e, k] ; db[c] += sum_e dh[e, c] ; drel[e, k] = sum_c dh[e, c] W[c, k] (optional)
+// warp per edge (lane = channels lane + 32 i), per-lane register accumulators for dW / db, folded per block in shared
+// memory and added to global with one atomic per entry.
+template <int kPerLane>
+__global__ void tr_lin3_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ rel, const float* __restrict__ W,
+                                   float* dW, float* db, float* drel, long long E, int D) {
+  extern __shared__ float sh[];          // [4 * D]
+  for (int i = threadIdx.x; i < 4 * D; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  float w0[kPerLane], w1[kPerLane], w2[kPerLane], a0[kPerLane], a1[kPerLane], a2[kPerLane], ab[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    const int c = lane + 32 * i;
+    w0[i] = c < D ? W[3 * c] : 0.f, w1[i] = c < D ? W[3 * c + 1] : 0.f, w2[i] = c < D ? W[3 * c + 2] : 0.f;
+    a0[i] = a1[i] = a2[i] = ab[i] = 0.f;
+  }
   for (long long e = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); e < E; e += (long long)gridDim.x * wpb) {
+    const float r0 = rel[3 * e], r1 = rel[3 * e + 1], r2 = rel[3 * e + 2];
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-    for (int c = lane; c < D; c += 32) {
-      const float g = dh[e * D + c];
-      d0 += g * W[3 * c], d1 += g * W[3 * c + 1], d2 += g * W[3 * c + 2];
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int c = lane + 32 * i;
+      const float g = c < D ? dh[e * D + c] : 0.f;
+      a0[i] += g * r0, a1[i] += g * r1, a2[i] += g * r2, ab[i] += g;
+      d0 += g * w0[i], d1 += g * w1[i], d2 += g * w2[i];
     }
-    d0 = warp_sum(d0), d1 = warp_sum(d1), d2 = warp_sum(d2);
-    if (lane == 0) drel[3 * e] = d0, drel[3 * e + 1] = d1, drel[3 * e + 2] = d2;
+    if (drel != nullptr) {
+      d0 = warp_sum(d0), d1 = warp_sum(d1), d2 = warp_sum(d2);
+      if (lane == 0) drel[3 * e] = d0, drel[3 * e + 1] = d1, drel[3 * e + 2] = d2;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    const int c = lane + 32 * i;
+    if (c < D) {
+      atomicAdd(&sh[c], a0[i]);
+      atomicAdd(&sh[D + c], a1[i]);
+      atomicAdd(&sh[2 * D + c], a2[i]);
+      atomicAdd(&sh[3 * D + c], ab[i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(dW + 3 * c, sh[c]);
+    atomicAdd(dW + 3 * c + 1, sh[D + c]);
+    atomicAdd(dW + 3 * c + 2, sh[2 * D + c]);
+    atomicAdd(db + c, sh[3 * D + c]);
   }
 }
 // t[e, :] = q[i, :] - ktab[gidx[e], :] + pos[e, :]        thread = 4 channels of one edge (blockDim.x = D / 4)
@@ -628,23 +649,33 @@ __global__ void tr_sample_fwd_kernel(const float* planes, const float* grid, flo
     }
   }
 }
-__global__ void tr_sample_bwd_kernel(const float* dS, const float* grid, float* dplanes, int NV, int D, int P, int hw) {
-  const long long n = (long long)NV * P;
-  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
-    const int img = (int)(x / P);
-    const int pidx = (int)(x % P);
+// block = (image, chunk of kSbCh channels): the chunk's planes are accumulated in shared memory (the 4 x P x kSbCh
+// scatter-adds of an image collide on 256 pixels: global atomics were 3.6 ms of a 95 ms step), then added to dplanes.
+constexpr int kSbCh = 64;
+__global__ void tr_sample_bwd_kernel(const float* __restrict__ dS, const float* __restrict__ grid, float* dplanes, int NV, int D,
+                                     int P, int hw) {
+  extern __shared__ float acc[];          // [kSbCh][hw * hw]
+  const int HW = hw * hw;
+  const int img = blockIdx.x, d0 = blockIdx.y * kSbCh;
+  const int nch = min(kSbCh, D - d0);
+  for (int i = threadIdx.x; i < kSbCh * HW; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  for (int pidx = threadIdx.x; pidx < P; pidx += blockDim.x) {
     int off[4];
     float wt[4];
+    const long long x = (long long)img * P + pidx;
     bilinear_taps(grid[2 * x], grid[2 * x + 1], hw, hw, off, wt);
-    float* pl = dplanes + (long long)img * D * hw * hw;
-    const float* in = dS + (long long)img * D * P + pidx;
-    for (int d = 0; d < D; ++d) {
+    const float* in = dS + ((long long)img * D + d0) * P + pidx;
+    for (int d = 0; d < nch; ++d) {
       const float g = in[(long long)d * P];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (off[k] >= 0) atomicAdd(pl + (long long)d * hw * hw + off[k], wt[k] * g);
+        if (off[k] >= 0) atomicAdd(&acc[d * HW + off[k]], wt[k] * g);
     }
   }
+  __syncthreads();
+  float* pl = dplanes + ((long long)img * D + d0) * HW;
+  for (int i = threadIdx.x; i < nch * HW; i += blockDim.x) pl[i] += acc[i];
 }
 
 // ------------------------------------------------------------------------------------------------ cross-view merge
