@@ -85,6 +85,96 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc_f32(uint32_t smem_addr, ui
          (1ull << 46) | (1ull << 61);
 }
 
+// One 32-row x 32-column piece of the accumulator (row `lane` of the warp's TMEM quarter in r[]) -> C: alpha, bias, ReLU,
+// TF32 rounding, ReLU mask, store / read-modify-write / atomic, transposed through the warp's [32 x 36] shared-memory pad
+// into whole 128-byte row segments (four rows per store instruction; conflict-free 128-bit accesses on both sides).
+__device__ __forceinline__ void tg_epilogue_chunk(const TgParams& p, const uint32_t (&r)[32], float* stg, int lane, int m_base,
+                                                  int col0, bool with_bias, float bias_m, bool vec_ok, bool mask_vec,
+                                                  float* cbase) {
+  const int rr4 = lane >> 3, l8 = lane & 7;
+  const int m0 = m_base, quarter = 0;       // m_base already includes the warp's quarter offset
+  // ReLU mask of this chunk, fetched before the transpose and the stores (a load behind a store to C could not be
+  // hoisted: the compiler must assume the two alias)
+  float4 mk[8];
+  if (p.relu_mask != nullptr) {
+    const int mcol = col0 + 4 * l8;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = m0 + quarter * 32 + 4 * it + rr4;
+      mk[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (grow < p.M && mcol < p.N) {
+        const float* mp = p.relu_mask + (long long)grow * p.ld_mask + mcol;
+        if (mask_vec && mcol + 4 <= p.N) {
+          mk[it] = __ldg(reinterpret_cast<const float4*>(mp));
+        } else {
+          mk[it].x = __ldg(mp);
+          if (mcol + 1 < p.N) mk[it].y = __ldg(mp + 1);
+          if (mcol + 2 < p.N) mk[it].z = __ldg(mp + 2);
+          if (mcol + 3 < p.N) mk[it].w = __ldg(mp + 3);
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 o;
+    o.x = p.alpha * __uint_as_float(r[4 * i]) + bias_m, o.y = p.alpha * __uint_as_float(r[4 * i + 1]) + bias_m;
+    o.z = p.alpha * __uint_as_float(r[4 * i + 2]) + bias_m, o.w = p.alpha * __uint_as_float(r[4 * i + 3]) + bias_m;
+    *reinterpret_cast<float4*>(stg + lane * 36 + 4 * i) = o;
+  }
+  __syncwarp();
+  const int col = col0 + 4 * l8;
+  float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (with_bias && !p.bias_on_m) {
+    if (col + 0 < p.N) bn.x = __ldg(p.bias + col);
+    if (col + 1 < p.N) bn.y = __ldg(p.bias + col + 1);
+    if (col + 2 < p.N) bn.z = __ldg(p.bias + col + 2);
+    if (col + 3 < p.N) bn.w = __ldg(p.bias + col + 3);
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rl = 4 * it + rr4;
+    const int grow = m0 + quarter * 32 + rl;
+    if (grow >= p.M || col >= p.N) continue;
+    float4 o = *reinterpret_cast<const float4*>(stg + rl * 36 + 4 * l8);
+    o.x += bn.x, o.y += bn.y, o.z += bn.z, o.w += bn.w;
+    if (p.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+    if (p.round_out) {
+      uint32_t t0, t1, t2, t3;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(o.x));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(o.y));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(o.z));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(o.w));
+      o = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
+    }
+    if (p.relu_mask != nullptr) {
+      if (!(mk[it].x > 0.f)) o.x = 0.f;
+      if (!(mk[it].y > 0.f)) o.y = 0.f;
+      if (!(mk[it].z > 0.f)) o.z = 0.f;
+      if (!(mk[it].w > 0.f)) o.w = 0.f;
+    }
+    float* dst = cbase + (long long)grow * p.ldc + col;
+    if (p.mode == TG_ATOMIC) {
+      atomicAdd(dst, o.x);
+      if (col + 1 < p.N) atomicAdd(dst + 1, o.y);
+      if (col + 2 < p.N) atomicAdd(dst + 2, o.z);
+      if (col + 3 < p.N) atomicAdd(dst + 3, o.w);
+    } else if (vec_ok && col + 4 <= p.N) {
+      if (p.mode == TG_ADD) {
+        const float4 old = *reinterpret_cast<const float4*>(dst);
+        o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+      }
+      *reinterpret_cast<float4*>(dst) = o;
+    } else {
+      const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (col + k < p.N) dst[k] = (p.mode == TG_ADD ? dst[k] : 0.f) + ov[k];
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(TG_THREADS, (STAGES == 2 ? 3 : 2))
 tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TgParams p) {
@@ -213,7 +303,6 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     // TMEM hands out one row per lane; a [32 x 36]-float pad per warp turns that into whole 128-byte row segments
     // (four rows per store instruction), conflict-free for the 128-bit accesses on both sides.
     float* stg = reinterpret_cast<float*>(smem) + quarter * (32 * 36);
-    const int rr4 = lane >> 3, l8 = lane & 7;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -226,86 +315,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;                      // warp-uniform
-      // ReLU mask of this chunk, fetched before the transpose and the stores (a load behind a store to C could not be
-      // hoisted: the compiler must assume the two alias)
-      float4 mk[8];
-      if (p.relu_mask != nullptr) {
-        const int mcol = col0 + 4 * l8;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int grow = m0 + quarter * 32 + 4 * it + rr4;
-          mk[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (grow < p.M && mcol < p.N) {
-            const float* mp = p.relu_mask + (long long)grow * p.ld_mask + mcol;
-            if (mask_vec && mcol + 4 <= p.N) {
-              mk[it] = __ldg(reinterpret_cast<const float4*>(mp));
-            } else {
-              mk[it].x = __ldg(mp);
-              if (mcol + 1 < p.N) mk[it].y = __ldg(mp + 1);
-              if (mcol + 2 < p.N) mk[it].z = __ldg(mp + 2);
-              if (mcol + 3 < p.N) mk[it].w = __ldg(mp + 3);
-            }
-          }
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 o;
-        o.x = p.alpha * __uint_as_float(r[4 * i]) + bias_m, o.y = p.alpha * __uint_as_float(r[4 * i + 1]) + bias_m;
-        o.z = p.alpha * __uint_as_float(r[4 * i + 2]) + bias_m, o.w = p.alpha * __uint_as_float(r[4 * i + 3]) + bias_m;
-        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * i) = o;
-      }
-      __syncwarp();
-      const int col = col0 + 4 * l8;
-      float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (with_bias && !p.bias_on_m) {
-        if (col + 0 < p.N) bn.x = __ldg(p.bias + col);
-        if (col + 1 < p.N) bn.y = __ldg(p.bias + col + 1);
-        if (col + 2 < p.N) bn.z = __ldg(p.bias + col + 2);
-        if (col + 3 < p.N) bn.w = __ldg(p.bias + col + 3);
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rl = 4 * it + rr4;
-        const int grow = m0 + quarter * 32 + rl;
-        if (grow >= p.M || col >= p.N) continue;
-        float4 o = *reinterpret_cast<const float4*>(stg + rl * 36 + 4 * l8);
-        o.x += bn.x, o.y += bn.y, o.z += bn.z, o.w += bn.w;
-        if (p.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-        if (p.round_out) {
-          uint32_t t0, t1, t2, t3;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t0) : "f"(o.x));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t1) : "f"(o.y));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t2) : "f"(o.z));
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t3) : "f"(o.w));
-          o = make_float4(__uint_as_float(t0), __uint_as_float(t1), __uint_as_float(t2), __uint_as_float(t3));
-        }
-        if (p.relu_mask != nullptr) {
-          if (!(mk[it].x > 0.f)) o.x = 0.f;
-          if (!(mk[it].y > 0.f)) o.y = 0.f;
-          if (!(mk[it].z > 0.f)) o.z = 0.f;
-          if (!(mk[it].w > 0.f)) o.w = 0.f;
-        }
-        float* dst = cbase + (long long)grow * p.ldc + col;
-        if (p.mode == TG_ATOMIC) {
-          atomicAdd(dst, o.x);
-          if (col + 1 < p.N) atomicAdd(dst + 1, o.y);
-          if (col + 2 < p.N) atomicAdd(dst + 2, o.z);
-          if (col + 3 < p.N) atomicAdd(dst + 3, o.w);
-        } else if (vec_ok && col + 4 <= p.N) {
-          if (p.mode == TG_ADD) {
-            const float4 old = *reinterpret_cast<const float4*>(dst);
-            o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-          }
-          *reinterpret_cast<float4*>(dst) = o;
-        } else {
-          const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (col + k < p.N) dst[k] = (p.mode == TG_ADD ? dst[k] : 0.f) + ov[k];
-        }
-      }
+      tg_epilogue_chunk(p, r, stg, lane, m0 + quarter * 32, col0, with_bias, bias_m, vec_ok, mask_vec, cbase);
     }
   }
   tc_fence_before_sync();

@@ -895,3 +895,4 @@ def test_parametric_head_backward_matches_oracle_autograd(tn):
         assert k in worst, k                                  # the tail and the last block's FFN now carry gradient
     assert max(worst.values()) <= 5e-2, top
     assert sorted(worst.values())[len(worst) // 2] <= 1e-2
+
