@@ -138,6 +138,20 @@ int poem_tr_adam(float* p, const float* g, float* m, float* v, long long n, floa
 int poem_tr_coord_loss(const float* coords, const float* gt_joints, const float* gt_verts, int n_blocks, int B,
                        int n_joints, int n_verts, float w_joints, float w_verts, float* loss, float* dcoords, void* stream);
 
+/* The head's terms of `PtEmbedMultiviewStereoV2.compute_loss` (lib/models/POEM.py:363-466, release loss types: joints l2,
+ * vertices l1, parameters l2) on the LAST block's prediction coords_last [B, 799, 3], with d loss_recon / d coords_last:
+ * losses[8] = {loss_3d_joints_from_mesh, loss_3d_joints, loss_3d_verts, loss_2d_joints, loss_2d_verts, loss_pose,
+ * loss_shape, loss_recon}.  j_regressor [16, 778] (MANO), cameras / target_joints_2d per image (cam_extr: camera -> master,
+ * inverted inside as the reference does), img_sample [NV] = sample of each image, img_scale = sqrt(W^2 + H^2).
+ * pred_pose / gt_pose [B, 48] and pred_shape / gt_shape [B, 10] (GT of each sample's first view) or NULL.
+ * The heat-map term of the reference's total loss belongs to the image half and is not included. */
+int poem_tr_compute_loss(const float* coords_last, const float* gt_joints, const float* gt_verts, const float* j_regressor,
+                         const float* cam_intr, const float* cam_extr, const int32_t* img_sample, const float* target_joints_2d,
+                         int B, int NV, float img_scale, float w_joints, float w_verts, float w_joints_2d, float w_verts_2d,
+                         const float* pred_pose, const float* gt_pose, const float* pred_shape, const float* gt_shape,
+                         float w_pose, float w_shape, float* losses, float* dcoords_last, float* dpose, float* dshape,
+                         void* stream);
+
 /* Parametric (medium_MANO) tail of the last block, pt_metro_transformer.py:139-151 (forward as in poem_parametric_tail of
  * poem_b200.h, on raw fp32 parameter pointers) and its backward.  MANO constants with the blend axis first: v_template
  * [778*3], shapedirs [10][778*3], posedirs [135][778*3], j_regressor [16][778], skin_weights [778][16].

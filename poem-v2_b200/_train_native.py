@@ -56,6 +56,7 @@ SIGNATURES = {
     "poem_tr_seg_clip": [_P, _P, _P, _I, _P, _F, _P],
     "poem_tr_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "poem_tr_coord_loss": [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
+    "poem_tr_compute_loss": [_P] * 8 + [_I, _I] + [_F] * 5 + [_P] * 4 + [_F, _F] + [_P] * 4 + [_P],
     "poem_tr_mano_tail": [_P] * 11 + [_I, _I, _I, _I] + [_P] * 4 + [_P],
     "poem_tr_mano_tail_bwd": [_P] * 9 + [_I, _I, _I, _I] + [_P] * 10 + [_P],
 }

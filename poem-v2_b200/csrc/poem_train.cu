@@ -527,3 +527,36 @@ extern "C" int poem_tr_mano_tail_bwd(const float* feats, const float* flat_w, co
   TR_CHECK("flat_verts_bwd");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ compute_loss (head terms)
+extern "C" int poem_tr_compute_loss(const float* coords_last, const float* gt_joints, const float* gt_verts,
+                                    const float* j_regressor, const float* cam_intr, const float* cam_extr,
+                                    const int32_t* img_sample, const float* target_joints_2d, int B, int NV, float img_scale,
+                                    float w_joints, float w_verts, float w_joints_2d, float w_verts_2d, const float* pred_pose,
+                                    const float* gt_pose, const float* pred_shape, const float* gt_shape, float w_pose,
+                                    float w_shape, float* losses, float* dcoords_last, float* dpose, float* dshape, void* stream) {
+  cudaError_t e = cudaMemsetAsync(losses, 0, 8 * sizeof(float), ST);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dcoords_last, 0, (size_t)B * kLossQ * 3 * sizeof(float), ST);
+  if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "compute_loss memset: %s", cudaGetErrorString(e));
+  TrLossArgs a;
+  a.coords = coords_last, a.gt_joints = gt_joints, a.gt_verts = gt_verts, a.j_regressor = j_regressor;
+  a.cam_intr = cam_intr, a.cam_extr = cam_extr, a.target_2d = target_joints_2d, a.img_sample = img_sample;
+  a.B = B, a.NV = NV, a.img_scale = img_scale, a.w_j = w_joints, a.w_v = w_verts, a.w_j2d = w_joints_2d, a.w_v2d = w_verts_2d;
+  a.losses = losses, a.dcoords = dcoords_last;
+  tr_loss_3d_kernel<<<B, 256, 0, ST>>>(a);
+  TR_CHECK("loss_3d");
+  if (w_joints_2d != 0.f || w_verts_2d != 0.f) {
+    if (!cam_intr || !cam_extr || !img_sample || !target_joints_2d) return fail(POEM_TR_E_BADARG, "compute_loss: the 2-D terms need cameras and targets");
+    tr_loss_2d_kernel<<<grid_for((long long)NV * kLossQ), 256, 0, ST>>>(a);
+    TR_CHECK("loss_2d");
+  }
+  if (pred_pose && gt_pose) {
+    tr_loss_mse_kernel<<<1, 256, 0, ST>>>(pred_pose, gt_pose, B * 48, w_pose, losses, 5, dpose);
+    TR_CHECK("loss_pose");
+  }
+  if (pred_shape && gt_shape) {
+    tr_loss_mse_kernel<<<1, 256, 0, ST>>>(pred_shape, gt_shape, B * 10, w_shape, losses, 6, dshape);
+    TR_CHECK("loss_shape");
+  }
+  return 0;
+}

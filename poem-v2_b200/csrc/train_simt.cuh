@@ -873,4 +873,169 @@ __global__ void tr_coord_loss_kernel(const float* coords, const float* gt_joints
   }
 }
 
+// ------------------------------------------------------------------------------------------------ compute_loss (head terms)
+// `PtEmbedMultiviewStereoV2.compute_loss` (lib/models/POEM.py:363-466, release loss types) on the LAST block's prediction:
+//   [0] loss_3d_joints_from_mesh  MSE(openpose(J_regressor . verts_pred), openpose(J_regressor . verts_gt))
+//   [1] loss_3d_joints            MSE(joints_pred, joints_gt)
+//   [2] loss_3d_verts             L1(verts_pred, verts_gt)          (the parametric variant centres both on the same GT joint: identical)
+//   [3] loss_2d_joints            mean over (view, joint) of |clamp(proj(joints_pred) - target_2d, +-s/2) / s|^2
+//   [4] loss_2d_verts             the same for the vertices, target = proj(verts_gt)
+//   [5] loss_pose, [6] loss_shape MSE on the MANO parameters (parametric heads)
+//   [7] loss_recon = w_j ([1] + [0]) + w_v [2] + w_j2d [3] + w_v2d [4] + w_pose [5] + w_shape [6]
+// (the heat-map term of the reference's total belongs to the image half).  Also writes d loss_recon / d coords (last block).
+struct TrLossArgs {
+  const float *coords, *gt_joints, *gt_verts, *j_regressor;      // [B, 799, 3], [B, 21, 3], [B, 778, 3], [16, 778]
+  const float *cam_intr, *cam_extr, *target_2d;                  // [NV, 9], [NV, 16], [NV, 21, 2]
+  const int* img_sample;                                         // [NV]
+  int B, NV;
+  float img_scale, w_j, w_v, w_j2d, w_v2d;
+  float *losses, *dcoords;                                       // [8], [B, 799, 3] (zeroed by the caller)
+};
+constexpr int kLossJ = 21, kLossV = 778, kLossQ = kLossJ + kLossV;
+
+// block per sample: the three 3-D terms
+__global__ void tr_loss_3d_kernel(const TrLossArgs a) {
+  __shared__ float dJ[16][3];
+  __shared__ float red[3][8];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int order[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
+  const int tips[5] = {744, 320, 443, 555, 672};        // lib/utils/misc.py:76-82 (mano_to_openpose)
+  const float* pj = a.coords + (size_t)b * kLossQ * 3;
+  const float* pv = pj + kLossJ * 3;
+  const float* jg = a.gt_joints + (size_t)b * kLossJ * 3;
+  const float* vg = a.gt_verts + (size_t)b * kLossV * 3;
+  float* dj = a.dcoords + (size_t)b * kLossQ * 3;
+  float* dv = dj + kLossJ * 3;
+  const float nj = 1.0f / (float)(a.B * kLossJ * 3), nv = 1.0f / (float)(a.B * kLossV * 3);
+  float l_jm = 0.f, l_j = 0.f, l_v = 0.f;
+  // regressed joints of predicted and GT mesh (16 x 3), one warp per (joint, component)
+  for (int o = warp; o < 48; o += (int)(blockDim.x >> 5)) {
+    const int j = o / 3, c = o % 3;
+    float acc = 0.f;
+    for (int v = lane; v < kLossV; v += 32) acc += a.j_regressor[j * kLossV + v] * (pv[v * 3 + c] - vg[v * 3 + c]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      dJ[j][c] = a.w_j * 2.f * acc * nj;
+      l_jm += acc * acc * nj;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kLossJ * 3; i += blockDim.x) {
+    const float e = pj[i] - jg[i];
+    l_j += e * e * nj;
+    atomicAdd(dj + i, a.w_j * 2.f * e * nj);
+  }
+  for (int i = tid; i < kLossV * 3; i += blockDim.x) {
+    const int v = i / 3, c = i % 3;
+    const float e = pv[i] - vg[i];
+    l_v += fabsf(e) * nv;
+    float g = a.w_v * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * nv;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) g += a.j_regressor[j * kLossV + v] * dJ[j][c];
+#pragma unroll
+    for (int t = 0; t < 5; ++t)
+      if (v == tips[t]) {
+        g += a.w_j * 2.f * e * nj;
+        l_jm += e * e * nj;
+      }
+    atomicAdd(dv + i, g);
+  }
+  (void)order;                                            // the 21-joint re-ordering does not change a mean over all joints
+  l_jm = warp_sum(l_jm), l_j = warp_sum(l_j), l_v = warp_sum(l_v);
+  if (lane == 0) red[0][warp] = l_jm, red[1][warp] = l_j, red[2][warp] = l_v;
+  __syncthreads();
+  if (tid < 3) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[tid][w];
+    atomicAdd(a.losses + tid, t);
+    atomicAdd(a.losses + 7, (tid == 2 ? a.w_v : a.w_j) * t);
+  }
+}
+
+// thread per (image, point): the two 2-D terms (loss_proj_to_multicam, POEM.py:335-361; camera = inverse of cam_extr)
+__global__ void tr_loss_2d_kernel(const TrLossArgs a) {
+  __shared__ float red[2][8];
+  const long long n = (long long)a.NV * kLossQ;
+  float l_j = 0.f, l_v = 0.f;
+  const float s = a.img_scale, lim = 0.5f * a.img_scale;
+  const float cj = 1.0f / (float)(a.NV * kLossJ), cv = 1.0f / (float)(a.NV * kLossV);
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(x / kLossQ), q = (int)(x % kLossQ);
+    const bool is_j = q < kLossJ;
+    const float w = is_j ? a.w_j2d : a.w_v2d;
+    if (w == 0.f) continue;
+    const int b = a.img_sample[img];
+    const float* E = a.cam_extr + 16 * img;
+    const float* K = a.cam_intr + 9 * img;
+    const float a00 = E[0], a01 = E[1], a02 = E[2], a10 = E[4], a11 = E[5], a12 = E[6], a20 = E[8], a21 = E[9], a22 = E[10];
+    const float c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const float c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+    const float c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+    const float idet = 1.0f / (a00 * c00 + a01 * c10 + a02 * c20);
+    const float Rm[9] = {c00 * idet, c01 * idet, c02 * idet, c10 * idet, c11 * idet, c12 * idet, c20 * idet, c21 * idet, c22 * idet};
+    // M = K . R (3 x 3): q = M (p - t_e)
+    float M[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) M[r * 3 + c] = K[r * 3] * Rm[c] + K[r * 3 + 1] * Rm[3 + c] + K[r * 3 + 2] * Rm[6 + c];
+    auto project = [&](const float* p, float& u, float& v, float& z) {
+      const float X = p[0] - E[3], Y = p[1] - E[7], Z = p[2] - E[11];
+      const float qx = M[0] * X + M[1] * Y + M[2] * Z, qy = M[3] * X + M[4] * Y + M[5] * Z;
+      z = M[6] * X + M[7] * Y + M[8] * Z;
+      if (fabsf(z) < 1e-7f) z = 1e-7f;
+      u = qx / z, v = qy / z;
+    };
+    const float* p = a.coords + ((size_t)b * kLossQ + q) * 3;
+    float u, v, z, tu, tv;
+    project(p, u, v, z);
+    if (is_j) {
+      tu = a.target_2d[((size_t)img * kLossJ + q) * 2], tv = a.target_2d[((size_t)img * kLossJ + q) * 2 + 1];
+    } else {
+      float tz;
+      project(a.gt_verts + ((size_t)b * kLossV + (q - kLossJ)) * 3, tu, tv, tz);
+    }
+    const float du = u - tu, dv = v - tv;
+    const bool cu = du < -lim || du > lim, cvv = dv < -lim || dv > lim;
+    const float ou = fminf(fmaxf(du, -lim), lim) / s, ov = fminf(fmaxf(dv, -lim), lim) / s;
+    const float norm = is_j ? cj : cv;
+    (is_j ? l_j : l_v) += (ou * ou + ov * ov) * norm;
+    // d / d(u, v), then through u = qx / z, v = qy / z and q = M (p - t)
+    const float gu = cu ? 0.f : w * 2.f * ou / s * norm, gv = cvv ? 0.f : w * 2.f * ov / s * norm;
+    const float gqx = gu / z, gqy = gv / z, gqz = -(gu * u + gv * v) / z;
+    float* d = a.dcoords + ((size_t)b * kLossQ + q) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(d + c, M[c] * gqx + M[3 + c] * gqy + M[6 + c] * gqz);
+  }
+  l_j = warp_sum(l_j), l_v = warp_sum(l_v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[0][warp] = l_j, red[1][warp] = l_v;
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    atomicAdd(a.losses + 3 + threadIdx.x, t);
+    atomicAdd(a.losses + 7, (threadIdx.x == 0 ? a.w_j2d : a.w_v2d) * t);
+  }
+}
+// MSE of a parameter vector (pose / shape): loss[slot] += mean (x - y)^2 ; loss[7] += w * that ; dx = w * 2 (x - y) / n
+__global__ void tr_loss_mse_kernel(const float* x, const float* y, int n, float w, float* losses, int slot, float* dx) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float e = x[i] - y[i];
+    acc += e * e / (float)n;
+    if (dx) dx[i] = w * 2.f * e / (float)n;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    atomicAdd(losses + slot, t);
+    atomicAdd(losses + 7, w * t);
+  }
+}
+
 }  // namespace poem

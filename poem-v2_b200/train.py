@@ -604,10 +604,21 @@ class TrainStep:
     (the eager schedule is ~520 launches from Python: launch-bound below batch ~16)."""
 
     def __init__(self, trainer, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=1.0, loss_weights=(1.0, 1.0),
-                 group=None, graph=False):
+                 group=None, graph=False, j_regressor=None, loss_cfg=None):
+        """loss_weights = (joints, vertices) of the built-in 3-D terms.  With `j_regressor` (MANO, (16, 778)) the step uses
+        the head's terms of the reference's compute_loss instead (poem_tr_compute_loss: + joints-from-mesh, the 2-D
+        projection terms when `target_joints_2d` is passed to the call, pose / shape for parametric heads); `loss_cfg`
+        holds the cfg.LOSS weights (JOINTS_LOSS_WEIGHT, VERTICES_LOSS_WEIGHT, JOINTS_2D_LOSS_WEIGHT, VERTICES_2D_LOSS_WEIGHT,
+        POSE_LOSS_WEIGHT, SHAPE_LOSS_WEIGHT; defaults of config/release)."""
         import torch.distributed as dist
         self.tr, self.lr, self.betas, self.eps, self.wd, self.max_norm = trainer, lr, betas, eps, weight_decay, max_norm
         self.wj, self.wv = loss_weights
+        self.jreg = None if j_regressor is None else j_regressor.detach().to(trainer.dev, torch.float32).reshape(16, 778).contiguous()
+        lc = dict(JOINTS_LOSS_WEIGHT=1.0, VERTICES_LOSS_WEIGHT=1.0, JOINTS_2D_LOSS_WEIGHT=1.0, VERTICES_2D_LOSS_WEIGHT=0.0,
+                  POSE_LOSS_WEIGHT=0.001, SHAPE_LOSS_WEIGHT=0.0005)
+        lc.update(loss_cfg or {})
+        self.loss_cfg = lc
+        self.losses = None                                   # the 8 terms of the last step (device), reference-loss mode
         self.m = torch.zeros_like(trainer.p_flat)
         self.v = torch.zeros_like(trainer.p_flat)
         self.t = 0
@@ -620,16 +631,39 @@ class TrainStep:
         self._pending = []
 
     # the part that is identical every step for fixed shapes
-    def _fwd_loss_bwd(self, feat, metas, refj, gt_j, gt_v, loss, on_bucket_done):
+    def _fwd_loss_bwd(self, feat, metas, refj, gt_j, gt_v, loss, on_bucket_done, extra=None):
         tr = self.tr
         d = tr.dims
         tr.zero_grad()
         loss.zero_()
         coords = tr.forward(feat, metas, refj)
         B = coords.shape[1]
-        dco = tr.new(*coords.shape)
-        tn.call("poem_tr_coord_loss", coords, gt_j, gt_v, d.n_blocks, B, 21, d.n_query - 21, float(self.wj), float(self.wv), loss, dco)
-        tr.backward(dco, on_bucket_done)
+        dpose = dshape = None
+        if self.jreg is None:
+            dco = tr.new(*coords.shape)
+            tn.call("poem_tr_coord_loss", coords, gt_j, gt_v, d.n_blocks, B, 21, d.n_query - 21, float(self.wj), float(self.wv), loss, dco)
+        else:                                                  # the reference's compute_loss (head terms) on the last block
+            ex, lc = extra or {}, self.loss_cfg
+            dco = tr.zeros(*coords.shape)
+            views = tuple(int(v) for v in np.asarray(metas["cam_view_num"]).reshape(-1))
+            cst = tr._const[views]
+            t2d = ex.get("target_joints_2d")
+            w2j = float(lc["JOINTS_2D_LOSS_WEIGHT"]) if t2d is not None else 0.0
+            w2v = float(lc["VERTICES_2D_LOSS_WEIGHT"]) if t2d is not None else 0.0
+            H, W = metas["inp_img_shape"]
+            par = d.parametric and ex.get("gt_pose") is not None
+            if par:
+                dpose, dshape = tr.new(B, 48), tr.new(B, 10)
+            losses = tr.new(8)
+            tn.call("poem_tr_compute_loss", coords[d.n_blocks - 1], gt_j, gt_v, self.jreg, metas["cam_intr"], metas["cam_extr"],
+                    cst["img_sample"], t2d, B, len(cst["img_sample"]), math.sqrt(float(W) ** 2 + float(H) ** 2),
+                    float(lc["JOINTS_LOSS_WEIGHT"]), float(lc["VERTICES_LOSS_WEIGHT"]), w2j, w2v,
+                    tr.pred_pose if par else None, ex.get("gt_pose") if par else None, tr.pred_shape if par else None,
+                    ex.get("gt_shape") if par else None, float(lc["POSE_LOSS_WEIGHT"]), float(lc["SHAPE_LOSS_WEIGHT"]), losses,
+                    dco[d.n_blocks - 1], dpose, dshape)
+            self.losses = losses
+            loss.copy_(losses[7:8])
+        tr.backward(dco, on_bucket_done, dpose=dpose, dshape=dshape)
         return coords
 
     def _bucket_hook(self, name):
@@ -642,9 +676,21 @@ class TrainStep:
             seg.div_(self.world)
             self._pending.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def __call__(self, mlvl_feat, img_metas, reference_joints, gt_joints, gt_verts):
+    def __call__(self, mlvl_feat, img_metas, reference_joints, gt_joints, gt_verts, target_joints_2d=None, gt_pose=None,
+                 gt_shape=None):
+        """One step; returns the loss (device scalar).  target_joints_2d (NV, 21, 2), gt_pose (B, 48) / gt_shape (B, 10) (the
+        first view's MANO parameters): inputs of the reference-loss mode (eager schedule only)."""
         tr = self.tr
         dev = tr.dev
+        extra = None
+        if self.jreg is not None:
+            if self.use_graph:
+                raise NotImplementedError("TrainStep: the reference-loss mode runs the eager schedule (graph=False)")
+            f32 = lambda t: None if t is None else t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+            extra = dict(target_joints_2d=f32(target_joints_2d), gt_pose=f32(gt_pose), gt_shape=f32(gt_shape))
+            img_metas = dict(img_metas)
+            img_metas["cam_intr"] = f32(img_metas["cam_intr"])
+            img_metas["cam_extr"] = f32(img_metas["cam_extr"])
         feat = mlvl_feat.detach().to(dev, torch.float32).contiguous()
         refj = reference_joints.to(dev, torch.float32).contiguous()
         gt_j = gt_joints.to(dev, torch.float32).contiguous()
@@ -653,7 +699,7 @@ class TrainStep:
         self.allreduce_bytes = 0
         if not self.use_graph:
             loss = tr.zeros(1)
-            self.coords = self._fwd_loss_bwd(feat, img_metas, refj, gt_j, gt_v, loss, hook)
+            self.coords = self._fwd_loss_bwd(feat, img_metas, refj, gt_j, gt_v, loss, hook, extra)
         else:
             loss = self._replay(feat, img_metas, refj, gt_j, gt_v)
             if self.world > 1:                         # graph replay: the buckets are final when the graph is

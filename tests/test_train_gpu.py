@@ -896,3 +896,85 @@ def test_parametric_head_backward_matches_oracle_autograd(tn):
     assert max(worst.values()) <= 5e-2, top
     assert sorted(worst.values())[len(worst) // 2] <= 1e-2
 
+
+
+def test_compute_loss_kernels_match_reference_golden_and_oracle_autograd(tn):
+    """The head's terms of compute_loss (POEM.py:363-466) on the device against tests/golden/loss_cases.npz — written from
+    the REAL `PtEmbedMultiviewStereoV2.compute_loss` — and d loss_recon / d (coords, pose, shape) against autograd through
+    the oracle's restatement: plain head with ragged views, parametric head."""
+    import ast
+    import os
+    import numpy as np
+    orc, synth, release_dims = _oracle_modules()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_cases.npz"))
+    cases = ast.literal_eval(str(z["meta"]))
+    weights = {"HEATMAP_JOINTS_WEIGHT": 10.0, "JOINTS_LOSS_WEIGHT": 1.0, "VERTICES_LOSS_WEIGHT": 1.0,
+               "JOINTS_2D_LOSS_WEIGHT": 1.0, "VERTICES_2D_LOSS_WEIGHT": 0.5}
+    jreg = synth.synthetic_mano(11)["J_regressor"]
+    for name, c in cases.items():
+        preds, gt = synth.make_loss_case(c["B"], c["V"], c["seed"], c["parametric"])
+        views = [int(v) for v in gt["cam_view_num"]]
+        B, NV = len(views), sum(views)
+        first = [sum(views[:j]) for j in range(B)]
+        coords = preds["all_coords_preds"].clone().requires_grad_(True)
+        p2 = dict(preds, all_coords_preds=coords)
+        if c["parametric"]:
+            p2["pred_pose"] = preds["pred_pose"].clone().requires_grad_(True)
+            p2["pred_shape"] = preds["pred_shape"].clone().requires_grad_(True)
+        ref = orc.compute_loss(p2, gt, weights, jreg, parametric=c["parametric"])
+        ref["loss_recon"].backward()
+        img_sample = torch.tensor([b for b, n in enumerate(views) for _ in range(n)], dtype=torch.int32)
+        H, W = gt["image"].shape[-2:]
+        losses, dco = torch.empty(8).cuda(), torch.empty(B, 799, 3).cuda()
+        dpose = torch.empty(B, 48).cuda() if c["parametric"] else None
+        dshape = torch.empty(B, 10).cuda() if c["parametric"] else None
+        tn.call("poem_tr_compute_loss", dev(preds["all_coords_preds"][-1]), dev(gt["master_joints_3d"].reshape(B, 21, 3)),
+                dev(gt["master_verts_3d"].reshape(B, 778, 3)), dev(jreg), dev(gt["target_cam_intr"].reshape(NV, 9)),
+                dev(gt["target_cam_extr"].reshape(NV, 16)), dev(img_sample), dev(gt["target_joints_2d"]), B, NV,
+                math.sqrt(float(W * W + H * H)), 1.0, 1.0, 1.0, 0.5,
+                dev(preds["pred_pose"].reshape(B, 48)) if c["parametric"] else None,
+                dev(gt["mano_pose"][first].reshape(B, 48)) if c["parametric"] else None,
+                dev(preds["pred_shape"]) if c["parametric"] else None, dev(gt["mano_shape"][first]) if c["parametric"] else None,
+                0.001, 0.0005, losses, dco, dpose, dshape)
+        got = losses.cpu().tolist()
+        keys = ["loss_3d_joints_from_mesh", "loss_3d_joints", "loss_3d_verts", "loss_2d_joints", "loss_2d_verts", "loss_pose",
+                "loss_shape", "loss_recon"]
+        for k, v in zip(keys, got):
+            if k in c["losses"]:
+                want = c["losses"][k]                                        # the real reference method's value
+                assert abs(v - want) <= 2e-5 * max(1.0, abs(want)) + 1e-9, (name, k, v, want)
+                assert abs(float(ref[k]) - want) <= 2e-6 * max(1.0, abs(want)) + 1e-9
+        assert rel_l2(dco.cpu(), coords.grad[-1]) <= 1e-4, (name, rel_l2(dco.cpu(), coords.grad[-1]))
+        assert coords.grad[:-1].abs().max().item() == 0                     # only the last block enters the loss
+        if c["parametric"]:
+            assert rel_l2(dpose.cpu(), p2["pred_pose"].grad.reshape(B, 48)) <= 1e-5
+            assert rel_l2(dshape.cpu(), p2["pred_shape"].grad) <= 1e-5
+
+
+def test_train_step_with_the_reference_loss_terms(tn):
+    """TrainStep in reference-loss mode (poem_tr_compute_loss: 3-D, joints-from-mesh, 2-D projection, pose / shape terms) on
+    a parametric POEM-small head: the eight loss terms are reported, ten steps lower loss_recon."""
+    from dataclasses import replace
+    from poem_v2_b200.pack import mano_zero_pose_template
+    from poem_v2_b200.train import HeadTrainer, TrainStep
+    orc, synth, release_dims = _oracle_modules()
+    dims = replace(release_dims("small"), parametric=True)
+    mano = synth.synthetic_mano(11)
+    views = [2, 1]
+    feat, metas, ref_j = synth.make_inputs(dims, len(views), views, 5)
+    m = _cuda_metas(metas)
+    g = torch.Generator().manual_seed(4)
+    gt_v = ref_j[:, 9:10] + 0.05 * torch.randn(len(views), 778, 3, generator=g)
+    t2d = 128.0 + 40.0 * torch.randn(sum(views), 21, 2, generator=g)
+    gt_pose, gt_shape = 0.1 * torch.randn(len(views), 48, generator=g), 0.5 * torch.randn(len(views), 10, generator=g)
+    tr = HeadTrainer(dims, synth.make_state_dict(dims, 3, "init"), mano_zero_pose_template(mano, dims.center_idx), mano=mano, dropout=0.1)
+    step = TrainStep(tr, lr=2e-4, max_norm=1.0, j_regressor=mano["J_regressor"], loss_cfg={"VERTICES_2D_LOSS_WEIGHT": 0.5})
+    hist = []
+    for _ in range(10):
+        loss = step(feat.cuda(), m, ref_j.cuda(), ref_j, gt_v, target_joints_2d=t2d, gt_pose=gt_pose, gt_shape=gt_shape)
+        terms = step.losses.cpu().tolist()
+        assert all(math.isfinite(v) for v in terms) and all(v > 0 for v in terms)
+        assert abs(float(loss.item()) - terms[7]) <= 1e-6 * abs(terms[7])
+        hist.append(terms[7])
+    print("reference-loss training, loss_recon:", [f"{v:.5f}" for v in hist])
+    assert hist[-1] < hist[0]
