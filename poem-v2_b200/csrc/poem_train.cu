@@ -348,19 +348,19 @@ extern "C" int poem_tr_va_gather_t(const float* q, const float* ktab, const int3
 }
 extern "C" int poem_tr_va_softmax_agg(float* a_w, const float* vtab, const float* pos, const int32_t* gidx, float scale,
                                       float* res, long long NQ, int D, void* stream) {
-  tr_va_softmax_agg_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), D, 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D);
+  tr_va_softmax_agg_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), (D < 256 ? D : 256), 0, ST>>>(a_w, vtab, pos, gidx, scale, res, NQ, D);
   TR_CHECK("va_softmax_agg");
   return 0;
 }
 extern "C" int poem_tr_va_softmax_agg_bwd(const float* dres, float* w_da, const float* vtab, const float* pos,
                                           const int32_t* gidx, float scale, float* dvp, long long NQ, int D, void* stream) {
-  tr_va_softmax_agg_bwd_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), D, 0, ST>>>(dres, w_da, vtab, pos, gidx, scale, dvp, NQ, D);
+  tr_va_softmax_agg_bwd_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), (D < 256 ? D : 256), 0, ST>>>(dres, w_da, vtab, pos, gidx, scale, dvp, NQ, D);
   TR_CHECK("va_softmax_agg_bwd");
   return 0;
 }
 extern "C" int poem_tr_va_scatter(float* dt_dpos, const float* dvp, const int32_t* gidx, float* dq, float* dktab,
                                   float* dvtab, long long NQ, int D, void* stream) {
-  tr_va_scatter_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), D, 0, ST>>>(dt_dpos, dvp, gidx, dq, dktab, dvtab, NQ, D);
+  tr_va_scatter_kernel<<<(unsigned)(NQ < (long long)agg_cap() * num_sms() ? NQ : (long long)agg_cap() * num_sms()), (D < 256 ? D : 256), 0, ST>>>(dt_dpos, dvp, gidx, dq, dktab, dvtab, NQ, D);
   TR_CHECK("va_scatter");
   return 0;
 }

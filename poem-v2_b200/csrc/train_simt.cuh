@@ -454,8 +454,8 @@ __global__ void tr_va_gather_t_kernel(const float* q, const float* ktab, const i
 __global__ void tr_va_softmax_agg_kernel(float* a, const float* __restrict__ vtab, const float* __restrict__ pos,
                                          const int* __restrict__ gidx, float scale, float* __restrict__ res, long long NQ,
                                          int D) {
-  const int c = threadIdx.x;        // blockDim.x == D
-  for (long long i = blockIdx.x; i < NQ; i += gridDim.x) {
+  for (long long i = blockIdx.x; i < NQ; i += gridDim.x)
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {          // blockDim.x = min(D, 256)
     float v[TR_NBR], vp[TR_NBR];
     float m = -INFINITY;
 #pragma unroll
@@ -485,8 +485,8 @@ __global__ void tr_va_softmax_agg_kernel(float* a, const float* __restrict__ vta
 // given dres: da (over w) = w * (dw - sum_j w dw) * scale with dw = dres * (v + pos) ; dvp = w * dres
 __global__ void tr_va_softmax_agg_bwd_kernel(const float* dres, float* w_da, const float* vtab, const float* pos,
                                              const int* gidx, float scale, float* dvp, long long NQ, int D) {
-  const int c = threadIdx.x;        // blockDim.x == D
-  for (long long i = blockIdx.x; i < NQ; i += gridDim.x) {
+  for (long long i = blockIdx.x; i < NQ; i += gridDim.x)
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {          // blockDim.x = min(D, 256)
     const long long x = i * D + c;
     const float g = dres[x];
     float w[TR_NBR], dw[TR_NBR];
@@ -509,8 +509,8 @@ __global__ void tr_va_softmax_agg_bwd_kernel(const float* dres, float* w_da, con
 // dq[i] += sum_j dt ; dktab[gidx] -= dt ; dvtab[gidx] += dvp ; dpos = dt + dvp (over dt)
 __global__ void tr_va_scatter_kernel(float* dt_dpos, const float* dvp, const int* gidx, float* dq, float* dktab,
                                      float* dvtab, long long NQ, int D) {
-  const int c = threadIdx.x;        // blockDim.x == D
-  for (long long i = blockIdx.x; i < NQ; i += gridDim.x) {
+  for (long long i = blockIdx.x; i < NQ; i += gridDim.x)
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {          // blockDim.x = min(D, 256)
     const long long x = i * D + c;
     float acc = 0.f;
 #pragma unroll 4

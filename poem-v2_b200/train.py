@@ -16,7 +16,8 @@ per-edge tensors of the vector attention (B*799*32*D per layer) stay in HBM betw
 Dropout (TRANSFORMER.DROPOUT, 0.1 in the release configs: on both embedding outputs, after the two attention output
 projections and the FFN output projection, and on the attention probabilities) is counter-based — masks are regenerated
 in the backward from a device seed, nothing is stored.  The parametric MANO tail of medium_MANO (flat_verts, mano_linear, 6-D rotations ->
-axis-angle, MANO skinning) has its backward too (csrc/mano_bwd.cuh).  Not covered: D = 1024.
+axis-angle, MANO skinning) has its backward too (csrc/mano_bwd.cuh).  Widths: D = 128 / 256 / 512 (small, medium, large);
+D = 1024 is refused like in the inference path.
 """
 import math
 

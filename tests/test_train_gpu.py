@@ -235,11 +235,12 @@ def test_elementwise_layernorm_softmax(tn):
     torch.cuda.synchronize()
 
 
-def test_vector_attention_edge_kernels(tn):
+@pytest.mark.parametrize("D", [128, 256, 512])
+def test_vector_attention_edge_kernels(tn, D):
     """forward + backward of the per-edge part of ptTransformerBlock (point_transformers.py:86-95) from the primitives,
     against autograd of the formula in fp64 (GEMM layers replaced by torch on the CPU: only the SIMT kernels under test)."""
     g = torch.Generator().manual_seed(21)
-    B, Q, R, D, K = 2, 40, 64, 128, 32
+    B, Q, R, K = 2, 40, 64, 32
     f64 = dict(generator=g, dtype=torch.float64)
     q = torch.randn(B * Q, D, **f64).requires_grad_()
     ktab = torch.randn(B * R, D, **f64).requires_grad_()
@@ -285,19 +286,19 @@ def test_vector_attention_edge_kernels(tn):
     td = ad * torch.cos(td)                                                            # dt = da * d sin(t)/dt
     dq, dk, dv = torch.zeros(B * Q, D).cuda(), torch.zeros(B * R, D).cuda(), torch.zeros(B * R, D).cuda()
     tn.call("poem_tr_va_scatter", td, dvp, gi, dq, dk, dv, B * Q, D)                  # td now holds dpos
-    close(dq, q.grad, 2e-3)
-    close(dk, ktab.grad, 2e-3)
-    close(dv, vtab.grad, 2e-3)
+    assert rel_l2(dq.cpu(), q.grad) <= 2e-3, rel_l2(dq.cpu(), q.grad)      # da / dpos are stored TF32-rounded
+    assert rel_l2(dk.cpu(), ktab.grad) <= 2e-3, rel_l2(dk.cpu(), ktab.grad)      # da / dpos are stored TF32-rounded
+    assert rel_l2(dv.cpu(), vtab.grad) <= 2e-3, rel_l2(dv.cpu(), vtab.grad)      # da / dpos are stored TF32-rounded
     tn.call("poem_tr_relu_bwd", td, posd, td.numel())
     dW1, db1 = torch.zeros(D, 3).cuda(), torch.zeros(D).cuda()
     drel = torch.empty(E, 3).cuda()
     tn.call("poem_tr_lin3_bwd", td, reld, W1d, dW1, db1, drel, E, D)
-    close(dW1, W1.grad, 2e-3)
-    close(db1, b1.grad, 2e-3)
+    assert rel_l2(dW1.cpu(), W1.grad) <= 2e-3, rel_l2(dW1.cpu(), W1.grad)      # da / dpos are stored TF32-rounded
+    assert rel_l2(db1.cpu(), b1.grad) <= 2e-3, rel_l2(db1.cpu(), b1.grad)      # da / dpos are stored TF32-rounded
     dqx, drx = torch.zeros(B * Q, 3).cuda(), torch.zeros(B * R, 3).cuda()
     tn.call("poem_tr_va_drel_scatter", drel, gi, dqx, drx, B * Q)
-    close(dqx, q_xyz.grad, 2e-3)
-    close(drx, r_xyz.grad, 2e-3)
+    assert rel_l2(dqx.cpu(), q_xyz.grad) <= 2e-3, rel_l2(dqx.cpu(), q_xyz.grad)      # da / dpos are stored TF32-rounded
+    assert rel_l2(drx.cpu(), r_xyz.grad) <= 2e-3, rel_l2(drx.cpu(), r_xyz.grad)      # da / dpos are stored TF32-rounded
     # anchors (block 0): the same 32 rows / coordinates for every query
     a_idx = torch.randint(0, R, (K,), generator=g, dtype=torch.int32)
     a_xyz = torch.randn(K, 3, generator=g)
