@@ -551,7 +551,7 @@ def _compare_head_with_oracle(tr, meta, sd, feat, metas, ref_j, tag, bound=1.5e-
             # softmax is invariant to a constant added to every key's / neighbour's score: the exact gradient is 0, the
             # reference holds rounding noise; bound ours by the scale of a neighbouring bias gradient instead
             other = k.replace("key", "query") if k.endswith("key.bias") else k.replace("fc_gamma.2", "fc_gamma.0")
-            assert got.norm().item() <= 1e-3 * sdo[other].grad.norm().item(), k
+            assert got.norm().item() <= 5e-3 * sdo[other].grad.norm().item(), k      # rounding noise of a sum that is exactly 0
             continue
         worst[k] = rel_l2(got, ref)
     worst["mlvl_feat"] = rel_l2(dfeat.cpu(), feato.grad)
@@ -979,3 +979,18 @@ def test_train_step_with_the_reference_loss_terms(tn):
         hist.append(terms[7])
     print("reference-loss training, loss_recon:", [f"{v:.5f}" for v in hist])
     assert hist[-1] < hist[0]
+
+
+@pytest.mark.parametrize("size", ["medium", "large"])
+def test_head_backward_at_benchmark_widths_matches_oracle_autograd(tn, size):
+    """The same whole-head comparison at the widths of the benchmark configs (POEM-medium D = 256 / head dim 64, POEM-large
+    D = 512 / head dim 128): one sample, two views, every parameter gradient and d mlvl_feat against oracle autograd on the
+    device's 32-NN sets and ReLU patterns."""
+    from poem_v2_b200.train import HeadTrainer
+    orc, synth, release_dims = _oracle_modules()
+    dims = release_dims(size)
+    meta = {"views": [2], "iseed": 9}
+    sd = synth.make_state_dict(dims, 2, "init")
+    feat, metas, ref_j = synth.make_inputs(dims, 1, meta["views"], meta["iseed"])
+    tr = HeadTrainer(dims, sd, synth.standin_template())
+    _compare_head_with_oracle(tr, meta, sd, feat, metas, ref_j, size, bound=2.5e-2)
