@@ -173,7 +173,10 @@ extern "C" int poem_tr_gemm(const float* A, int a_mn, long long lda, long long a
   }
   dim3 grid((N + BN - 1) / BN, (M + TG_BM - 1) / TG_BM, nb1 * nb2 * splits);
   if (grid.y > 65535u || grid.z > 65535u) return fail(POEM_TR_E_BADARG, "poem_tr_gemm: grid too large (%u, %u)", grid.y, grid.z);
-  const bool shallow = kb_per_split <= 2;      // K <= 64: a two-stage ring is the whole K loop; three CTAs per SM
+  // two-stage ring / three CTAs per SM: K <= 64 (the ring is the whole K loop), and the tall streaming GEMMs (many tiles,
+  // no split): they are bound by bytes in flight and by the epilogue's store bursts, a third resident CTA buys more of both
+  // (per-edge GEMM 0.47 -> 0.44 ms); the split-K wgrads keep three stages (0.26 vs 0.29 ms).
+  const bool shallow = kb_per_split <= 2 || (splits == 1 && !a_mn && tiles >= 4 * num_sms());      // K <= 64: a two-stage ring is the whole K loop; three CTAs per SM
   switch (BN) {
     case 32: return shallow ? launch_tgemm_major<32, 2>(a_mn, b_mn, ta, tb, p, grid, st) : launch_tgemm_major<32, 3>(a_mn, b_mn, ta, tb, p, grid, st);
     case 64: return shallow ? launch_tgemm_major<64, 2>(a_mn, b_mn, ta, tb, p, grid, st) : launch_tgemm_major<64, 3>(a_mn, b_mn, ta, tb, p, grid, st);
@@ -560,3 +563,10 @@ extern "C" int poem_tr_compute_loss(const float* coords_last, const float* gt_jo
   }
   return 0;
 }
+
+#if POEM_TG_TRACE
+extern "C" int poem_tr_debug_trace(unsigned long long* host_out, int n) {   // experiments: scripts/tgemm_trace.py
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_out, g_tg_trace, (size_t)n * 8, 0, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -21,6 +21,20 @@
 
 namespace poem {
 
+#ifndef POEM_TG_TRACE
+#define POEM_TG_TRACE 0      // 1: per-CTA phase timestamps (globaltimer, ns) into g_tg_trace (scripts/tgemm_trace.py)
+#endif
+#if POEM_TG_TRACE
+__device__ unsigned long long g_tg_trace[8192 * 16];
+__device__ __forceinline__ unsigned long long tg_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TG_MARK(slot) do { if ((threadIdx.x & 31) == 0) g_tg_trace[((blockIdx.y * gridDim.x + blockIdx.x) % 8192) * 16 + (slot)] = tg_now(); } while (0)
+#else
+#define TG_MARK(slot) do {} while (0)
+#endif
 constexpr int TG_BM = 128;
 constexpr int TG_BK = 32;          // fp32 elements per 128-byte swizzle row
 constexpr int TG_STAGES = 3;          // ring depth; 2 for problems with K <= 64 (three CTAs per SM instead of two)
@@ -124,6 +138,7 @@ __device__ __forceinline__ void tg_epilogue_chunk(const TgParams& p, const uint3
     *reinterpret_cast<float4*>(stg + lane * 36 + 4 * i) = o;
   }
   __syncwarp();
+  if (col0 < 32 && (threadIdx.x >> 5) == 2) TG_MARK(9);
   const int col = col0 + 4 * l8;
   float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
   if (with_bias && !p.bias_on_m) {
@@ -132,6 +147,7 @@ __device__ __forceinline__ void tg_epilogue_chunk(const TgParams& p, const uint3
     if (col + 2 < p.N) bn.z = __ldg(p.bias + col + 2);
     if (col + 3 < p.N) bn.w = __ldg(p.bias + col + 3);
   }
+  if (col0 < 32 && (threadIdx.x >> 5) == 2) TG_MARK(10);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rl = 4 * it + rr4;
@@ -203,6 +219,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int k_end = min(p.K, k_begin + p.k_per_split);
   const int n_kb = (k_end - k_begin + TG_BK - 1) / TG_BK;
 
+  if (warp == 0) TG_MARK(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -219,6 +236,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) TG_MARK(1);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -253,6 +271,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int st = kb % TG_STAGES;
         const uint32_t ph = (uint32_t)(kb / TG_STAGES) & 1;
         mbar_wait(p.round_ops ? &ready_bar[st] : &full_bar[st], ph);
+        if (kb == 0) TG_MARK(2);
+        if (kb == n_kb - 1) TG_MARK(6);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + st * Cfg::kStageBytes);
         const uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -299,6 +319,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
+    if (warp == 2) TG_MARK(3);
     // every stage has been consumed (acc_full follows the last MMA): the ring doubles as the transpose buffer.
     // TMEM hands out one row per lane; a [32 x 36]-float pad per warp turns that into whole 128-byte row segments
     // (four rows per store instruction), conflict-free for the 128-bit accesses on both sides.
@@ -309,6 +330,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (n_kb > 0) {
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
+        if (warp == 2 && c == 0) TG_MARK(8);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = 0u;
@@ -316,13 +338,16 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;                      // warp-uniform
       tg_epilogue_chunk(p, r, stg, lane, m0 + quarter * 32, col0, with_bias, bias_m, vec_ok, mask_vec, cbase);
+      if (warp == 2 && c == 0) TG_MARK(11);
     }
   }
+  if (warp == 2) TG_MARK(4);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+    TG_MARK(7);
   }
 }
 
