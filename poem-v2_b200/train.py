@@ -170,14 +170,6 @@ class HeadTrainer:
                 round_ops=GRAD_ROUND & ra, round_out=round_out)
         return dx
 
-    def relu_(self, y):
-        tn.call("poem_tr_relu", y, y.numel())
-        return y
-
-    def relu_bwd_(self, dy, y):
-        tn.call("poem_tr_relu_bwd", dy, y, y.numel())
-        return dy
-
     def ln(self, x, res, pre):
         M, D = x.shape
         y, xhat, rstd = self.new(M, D), self.new(M, D), self.new(M)
