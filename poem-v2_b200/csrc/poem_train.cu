@@ -39,14 +39,15 @@ extern "C" const char* poem_tr_last_error(void) { return g_err; }
 extern "C" long long poem_tr_kernel_launches(void) { return g_launches.load(); }
 
 static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 static int agg_cap() {   // resident-block cap per SM of the per-query vector-attention kernels (POEM_TR_AGG_CAP, experiments)
   static int c = 0;
@@ -56,6 +57,11 @@ static int agg_cap() {   // resident-block cap per SM of the per-query vector-at
     if (c < 1) c = 1;
   }
   return c;
+}
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? dev : 0;
 }
 static inline int grid_for(long long n, int block = 256, int per_sm = 8) {
   long long g = (n + block - 1) / block;
@@ -110,11 +116,12 @@ static int make_tmap_f32(CUtensorMap* tm, const float* base, int mn_major, long 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 static int launch_tgemm(const CUtensorMap& ta, const CUtensorMap& tb, const TgParams& p, dim3 grid, cudaStream_t st) {
   using Cfg = TgCfg<BN, STAGES>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};       // function attributes are per device
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN, A_MN, B_MN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "tgemm smem attribute: %s", cudaGetErrorString(e));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   tgemm_kernel<BN, A_MN, B_MN, STAGES><<<grid, TG_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, p);
   TR_CHECK("tgemm");
@@ -403,11 +410,12 @@ extern "C" int poem_tr_sample(const float* planes, const float* grid, float* S, 
 }
 extern "C" int poem_tr_sample_bwd(const float* dS, const float* grid_, float* dplanes, int NV, int D, int P, int hw, void* stream) {
   const size_t shb = (size_t)kSbCh * hw * hw * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};       // function attributes are per device
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tr_sample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return fail(POEM_TR_E_CUDA, "sample_bwd smem attribute: %s", cudaGetErrorString(e));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   if (shb > 200 * 1024) return fail(POEM_TR_E_BADARG, "sample_bwd: feature map %d x %d too large", hw, hw);
   dim3 grid(NV, (D + kSbCh - 1) / kSbCh);

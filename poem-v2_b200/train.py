@@ -31,6 +31,20 @@ from .config import HeadDims
 from .pack import sine_pos_3d
 
 NBR = 32
+
+
+def _on_own_device(fn):
+    """The primitives launch on torch's CURRENT device / stream: run the method with the trainer's device current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = self.dev if hasattr(self, "dev") else self.tr.dev
+        if dev.type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapped
 # operand rounding of the gradient GEMMs (poem_tr_gemm round_ops).  3 (default): both operands rounded to nearest, like
 # the forward GEMMs (those always round: the 1e-3 bound on the coordinates needs it).  POEM_TR_GRAD_ROUND=0 lets the
 # tensor core truncate the gradient GEMMs' operands (a 2^-11 relative shrink of every product term) and drops their
@@ -477,6 +491,7 @@ class HeadTrainer:
         return dfeat
 
     # ------------------------------------------------------------------------------------------ whole head
+    @_on_own_device
     def forward(self, mlvl_feat, img_metas, reference_joints, neighbours=None):
         """all_coords_preds (NB, B, 799, 3) in metres; keeps the activations for `backward`.
         `neighbours` (NB-1, 2, B, 799, 32): test hook, use these 32-NN sets instead of searching."""
@@ -531,6 +546,7 @@ class HeadTrainer:
             self.tape["tail"] = dict(feats=q_feats, flat=flat)
         return coords
 
+    @_on_own_device
     def backward(self, dcoords, on_bucket_done=None, dpose=None, dshape=None):
         """dcoords (NB, B, 799, 3): d loss / d all_coords_preds.  Accumulates into `g`, returns d loss / d mlvl_feat.
         `on_bucket_done(name)`: called when every gradient of bucket `name` ("2", "1", "0", then "head") is final, so a
@@ -573,6 +589,7 @@ class HeadTrainer:
         return dfeat
 
     # ------------------------------------------------------------------------------------------ after backward
+    @_on_own_device
     def clip_grad_norm_per_tensor(self, max_norm):
         """lib/utils/net_utils.py:122-132: clip_grad_norm_(param, max_norm, 2) on every parameter tensor by itself.
         Two launches over the flat gradient buffer; returns the squared norms (device, one per tensor)."""
@@ -669,6 +686,7 @@ class TrainStep:
             seg.div_(self.world)
             self._pending.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    @_on_own_device
     def __call__(self, mlvl_feat, img_metas, reference_joints, gt_joints, gt_verts, target_joints_2d=None, gt_pose=None,
                  gt_shape=None):
         """One step; returns the loss (device scalar).  target_joints_2d (NV, 21, 2), gt_pose (B, 48) / gt_shape (B, 10) (the
