@@ -416,7 +416,7 @@ def image_sharded_pass(dev, rank, world, sync, max_over_ranks, V=8, steps=20):
             "finite": ok, "launch": "eager launches"}
 
 
-def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium_MANO", steps=5, warmup=2,
+def train_step_pass(dev, rank, world, sync, max_over_ranks, gb=32, V=8, size="medium_MANO", steps=8, warmup=3,
                     eager_baseline=True):
     """SURVEY §8 f3 / BASELINE configs[3] (medium_MANO): one optimisation step of the decoder head — zero_grad, forward with saved
     activations, 3-D loss, hand-written backward, NCCL average of the gradient buckets (N > 1, overlapped with the
