@@ -238,14 +238,20 @@ def images_to_mesh_pass(size, V, B, dev, cpu_views, steps=10, warmup=3, eager=Fa
     for i in range(warmup):
         model(batches[i & 1], mode="test")
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        out = model(batches[i & 1], mode="test")["all_coords_preds"]
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    # the eager model forward is ~400 launches from Python: a host hiccup inside the 0.2 s region shows up as a 40 % slower
+    # step (seen once: 29.9 vs 20.8 ms), so the region is timed three times and the repeats are reported beside the best
+    rounds = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            out = model(batches[i & 1], mode="test")["all_coords_preds"]
+        e1.record()
+        torch.cuda.synchronize()
+        rounds.append(e0.elapsed_time(e1) / steps)
+    ms = min(rounds)
     res = {"value": B / ms * 1e3, "unit": "samples/s", "images_per_s": B * V / ms * 1e3, "ms_per_step": ms,
+           "ms_per_step_of_each_timed_round": rounds,
            "workload": f"POEM-{size}: {B} samples x {V} views of 3x256x256 -> mesh (backbone + feat_decode + heatmap + "
                        f"DLT + decoder)", "finite": bool(torch.isfinite(out).all())}
     del model
