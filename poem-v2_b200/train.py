@@ -496,6 +496,8 @@ class HeadTrainer:
         """all_coords_preds (NB, B, 799, 3) in metres; keeps the activations for `backward`.
         `neighbours` (NB-1, 2, B, 799, 32): test hook, use these 32-NN sets instead of searching."""
         d = self.dims
+        if self.dev.type != "cuda":
+            raise nat.PoemError("the training path has no CPU implementation: build the trainer on a CUDA device")
         tn.call("poem_tr_round_tf32", self.p_flat, self.pr_flat, self.p_flat.numel())      # this step's operand copy of the weights
         if self.p_drop > 0.0:
             self.seed_dev.add_(1)                                   # fresh masks every step (also under CUDA-graph replay)

@@ -481,6 +481,9 @@ def test_train_parameter_buckets_partition_the_flat_buffer():
     tr.g_flat.fill_(1.0)
     tr.zero_grad()
     assert float(tr.g_flat.abs().sum()) == 0.0
+    feat, metas, ref_j = synth.make_inputs(dims, 1, [2], 1)
+    with pytest.raises(nat.PoemError, match="no CPU implementation"):      # no fallback: the kernels are the only path
+        tr.forward(feat, metas, ref_j)
 
 
 def _bucket_allreduce_worker(rank, world, port, q):
